@@ -1,0 +1,151 @@
+"""ctypes front-end of the canonical CPU restatement (oracle/taxim_canon.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this module.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "_build" / "libtaxim_canon.so"
+_MAX_BLURS = 8
+
+
+def build(force: bool = False) -> Path:
+    """Compile the C restatement (gcc, no GPU needed)."""
+    src = _HERE / "taxim_canon.c"
+    if force or not _LIB.exists() or _LIB.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "_build/libtaxim_canon.so"], check=True, capture_output=True)
+    return _LIB
+
+
+class _Cfg(C.Structure):
+    _fields_ = [
+        ("H", C.c_int), ("W", C.c_int), ("num_bins", C.c_int), ("pixmm", C.c_float),
+        ("calib_h", C.c_float), ("calib_w", C.c_float), ("contact_scale", C.c_float), ("n_blurs", C.c_int),
+        ("ksx", C.c_int * _MAX_BLURS), ("ksy", C.c_int * _MAX_BLURS),
+        ("off_x", C.c_int * _MAX_BLURS), ("off_y", C.c_int * _MAX_BLURS),
+    ]
+
+
+class _FotsCfg(C.Structure):
+    _fields_ = [
+        ("H", C.c_int), ("W", C.c_int), ("rows", C.c_int), ("cols", C.c_int),
+        ("lamb", C.c_double * 3), ("mm2pix", C.c_double), ("shear_max_px", C.c_double), ("theta_max_rad", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB))
+        _lib.canon_taxim_render.restype = C.c_int
+        _lib.canon_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a: np.ndarray | None, t):
+    return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+class CanonTaxim:
+    """Canonical Taxim optical path. ``taps`` = [(x taps, y taps)] for the pyramid levels + the final blur."""
+
+    def __init__(self, H, W, poly_grad, background, gel_map, taps, pixmm=0.0295, num_bins=125, calib_hw=(480, 640),
+                 contact_scale=0.4, gelpad_height_m=0.0045, gelpad_to_cam_min_m=0.024):
+        self.H, self.W = int(H), int(W)
+        self.poly = np.ascontiguousarray(poly_grad, np.float32)
+        self.bg = np.ascontiguousarray(background, np.float32)
+        self.gel = None if gel_map is None else np.ascontiguousarray(gel_map, np.float32)
+        assert self.poly.shape == (3, num_bins, num_bins, 6) and self.bg.shape == (3, H, W)
+        cfg = _Cfg()
+        cfg.H, cfg.W, cfg.num_bins, cfg.pixmm = self.H, self.W, num_bins, pixmm
+        cfg.calib_h, cfg.calib_w, cfg.contact_scale = calib_hw[0], calib_hw[1], contact_scale
+        cfg.n_blurs = len(taps)
+        flat, off = [], 0
+        for l, (kx, ky) in enumerate(taps):
+            kx = np.asarray(kx, np.float32)
+            ky = np.asarray(ky, np.float32)
+            cfg.ksx[l], cfg.ksy[l] = kx.size, ky.size
+            cfg.off_x[l] = off
+            off += kx.size
+            cfg.off_y[l] = off
+            off += ky.size
+            flat += [kx, ky]
+        self.taps = np.ascontiguousarray(np.concatenate(flat), np.float32)
+        self.cfg = cfg
+        self.gelpad_height_m, self.gelpad_to_cam_min_m = gelpad_height_m, gelpad_to_cam_min_m
+
+    def indentation_depth(self, hm_mm: np.ndarray) -> np.ndarray:
+        hm = np.ascontiguousarray(hm_mm, np.float32)
+        out = np.empty(hm.shape[0], np.float32)
+        lib().canon_indentation_depth(_p(hm, C.c_float), hm.shape[0], self.H, self.W, C.c_float(self.gelpad_height_m),
+                                      C.c_float(self.gelpad_to_cam_min_m), _p(out, C.c_float))
+        return out
+
+    def render(self, hm_mm: np.ndarray, press_mm: np.ndarray, want=("deformed", "mask", "idx", "rgb")) -> dict:
+        hm = np.ascontiguousarray(hm_mm, np.float32)
+        N = hm.shape[0]
+        pr = np.ascontiguousarray(press_mm, np.float32)
+        out = {}
+        dg = np.empty((N, self.H, self.W), np.float32) if "deformed" in want else None
+        mk = np.empty((N, self.H, self.W), np.uint8) if "mask" in want else None
+        im = np.empty((N, self.H, self.W), np.int32) if "idx" in want else None
+        idr = np.empty((N, self.H, self.W), np.int32) if "idx" in want else None
+        rgb = np.empty((N, self.H, self.W, 3), np.float32) if "rgb" in want else None
+        rc = lib().canon_taxim_render(C.byref(self.cfg), _p(self.taps, C.c_float), _p(self.poly, C.c_float),
+                                      _p(self.bg, C.c_float), _p(self.gel, C.c_float), _p(hm, C.c_float),
+                                      _p(pr, C.c_float), N, _p(dg, C.c_float), _p(mk, C.c_uint8), _p(im, C.c_int32),
+                                      _p(idr, C.c_int32), _p(rgb, C.c_float))
+        if rc != 0:
+            raise MemoryError("canon_taxim_render failed")
+        out.update(deformed=dg, mask=mk, idx_mag=im, idx_dir=idr, rgb=rgb)
+        return out
+
+
+class CanonFots:
+    """Canonical FOTS marker motion with the per-env trajectory state the reference keeps in python lists."""
+
+    def __init__(self, H=240, W=320, rows=9, cols=11, x0=15, y0=26, lamb=(0.00125, 0.00021, 0.00038), mm2pix=19.58):
+        c = _FotsCfg()
+        c.H, c.W, c.rows, c.cols = H, W, rows, cols
+        c.lamb[:] = lamb
+        c.mm2pix, c.shear_max_px, c.theta_max_rad = mm2pix, 10.0, 60.0 / 180.0 * math.pi
+        self.cfg, self.M = c, rows * cols
+        self.mx = np.empty(self.M, np.int32)
+        self.my = np.empty(self.M, np.int32)
+        lib().canon_fots_grid(C.byref(c), C.c_double(x0), C.c_double(y0), _p(self.mx, C.c_int32), _p(self.my, C.c_int32))
+        self.traj0 = None
+        self.traj_len = None
+
+    def reset(self, N):
+        self.traj0 = np.zeros((N, 4), np.float32)
+        self.traj_len = np.zeros(N, np.int32)
+
+    def step(self, deformed, mask, press, theta) -> np.ndarray:
+        N = deformed.shape[0]
+        if self.traj0 is None or self.traj0.shape[0] != N:
+            self.reset(N)
+        dg = np.ascontiguousarray(deformed, np.float32)
+        mk = np.ascontiguousarray(mask, np.uint8)
+        pr = np.ascontiguousarray(press, np.float32)
+        th = np.ascontiguousarray(theta, np.float32)
+        out = np.empty((N, 2, self.M, 2), np.float32)
+        lib().canon_fots_step(C.byref(self.cfg), _p(self.mx, C.c_int32), _p(self.my, C.c_int32), _p(dg, C.c_float),
+                              _p(mk, C.c_uint8), _p(pr, C.c_float), _p(th, C.c_float), N, _p(self.traj0, C.c_float),
+                              _p(self.traj_len, C.c_int32), _p(out, C.c_float))
+        return out
+
+
+def num_threads() -> int:
+    return int(lib().canon_num_threads())

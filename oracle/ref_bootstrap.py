@@ -1,0 +1,128 @@
+"""Imports the UNMODIFIED reference implementation from /root/reference (read-only) -- TEST INFRASTRUCTURE ONLY.
+
+Works only in the build container (the GPU box has no /root/reference); used by oracle/make_golden.py to generate
+the committed fixtures under tests/golden/ and by the container-only tests that pin the canonical restatement
+against the executed reference.
+
+Nothing is copied: the reference modules are imported by path and called through their own entry points
+(``sim.Taxim`` / ``TaximTorch.render_direct`` and the name-mangled privates the reference's FOTS wrapper itself
+uses, fots_marker_sim.py:128-129; ``MarkerMotion.marker_sim``).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF_ROOT = Path("/root/reference")
+TAXIM_PKG = REF_ROOT / "source/tacex/tacex/simulation_approaches/gpu_taxim"
+FOTS_FILE = REF_ROOT / "source/tacex/tacex/simulation_approaches/fots/sim/marker_motion.py"
+CALIB_DIR = REF_ROOT / "source/tacex_assets/tacex_assets/data/Sensors/GelSight_Mini/calibs/640x480"
+
+
+def available() -> bool:
+    return TAXIM_PKG.exists() and CALIB_DIR.exists()
+
+
+_taxim = None
+
+
+def load_taxim(device: str = "cpu"):
+    """``sim.Taxim(calib_folder=..., backend='torch')`` of the reference. torch_scatter is only used by the shadow
+    branch (taxim_torch.py:330), which every GelSight Mini preset disables, so an empty stub module suffices."""
+    global _taxim
+    if _taxim is None:
+        sys.modules.setdefault("torch_scatter", types.ModuleType("torch_scatter"))
+        if str(TAXIM_PKG) not in sys.path:
+            sys.path.insert(0, str(TAXIM_PKG))
+        import sim  # noqa: PLC0415  (the reference's gpu_taxim/sim package)
+
+        _taxim = sim.Taxim(calib_folder=CALIB_DIR, backend="torch", device=device)
+    return _taxim
+
+
+def load_marker_motion_cls():
+    spec = importlib.util.spec_from_file_location("ref_marker_motion", str(FOTS_FILE))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.MarkerMotion
+
+
+def ref_indentation_depth(hm_mm: torch.Tensor, gelpad_height=0.0045, min_dist=0.024) -> torch.Tensor:
+    """Verbatim arithmetic of TaximSimulator.compute_indentation_depth (taxim_sim.py:115-131); the class itself
+    cannot be imported without Isaac Sim (omni.usd)."""
+    height_map = hm_mm / 1000
+    min_distance_obj = height_map.amin((1, 2))
+    dist_obj_sensor_case = min_distance_obj - min_dist
+    dist_obj_sensor_case = torch.where(dist_obj_sensor_case < 0, 0, dist_obj_sensor_case)
+    return torch.where(dist_obj_sensor_case <= gelpad_height, (gelpad_height - dist_obj_sensor_case) * 1000, 0)
+
+
+def ref_tables(tx, shape=(240, 320)) -> dict:
+    return {
+        "poly_grad": tx._TaximTorch__poly_grad.clone(),
+        "background": tx._TaximTorch__get_background_img_cached(tuple(shape)).clone(),
+        "gel_map": tx._TaximTorch__get_gel_map_cached(tuple(shape)).clone(),
+        "gel_map_shift": tx._TaximTorch__gel_map_shift,
+    }
+
+
+def ref_render(tx, hm_mm: torch.Tensor, press_mm: torch.Tensor) -> torch.Tensor:
+    """(N,H,W,3) exactly as TaximSimulator.optical_simulation returns it (taxim_sim.py:104-111)."""
+    return tx.render_direct(hm_mm, with_shadow=False, press_depth=press_mm, orig_hm_fmt=False).movedim(1, 3).contiguous()
+
+
+def ref_deformed_gel(tx, hm_mm: torch.Tensor, press_mm: torch.Tensor):
+    sh = tx._TaximTorch__get_shifted_height_map(press_mm, hm_mm)
+    return tx._TaximTorch__compute_gel_pad_deformation(sh)
+
+
+def ref_normals_bins(tx, deformed: torch.Tensor):
+    """grad_mag, grad_dir, idx_mag, idx_dir as __render computes them (taxim_torch.py:237-247)."""
+    px = deformed / tx.sensor_params.pixmm
+    mag, dr = tx._TaximTorch__generate_normals(-px)
+    x_binr = 0.5 * torch.pi / (tx.sensor_params.num_bins - 1)
+    y_binr = 2 * torch.pi / (tx.sensor_params.num_bins - 1)
+    return mag, dr, torch.floor(mag / x_binr).long(), torch.floor((dr + torch.pi) / y_binr).long()
+
+
+class RefFots:
+    """The reference's per-env FOTS loop (fots_marker_sim.py:128-182) around the unmodified ``MarkerMotion``; the yaw
+    that the reference reads from Isaac Lab's FrameTransformer is an input here."""
+
+    def __init__(self, tx, rows=9, cols=11, x0=15, y0=26, mm2pix=19.58, W=320, H=240):
+        MarkerMotion = load_marker_motion_cls()
+        bg = tx._TaximTorch__get_background_img_cached((H, W)).movedim(0, 2).cpu().numpy()
+        self.mm = MarkerMotion(frame0_blur=bg, mm2pix=mm2pix, num_markers_col=cols, num_markers_row=rows,
+                               tactile_img_width=W, tactile_img_height=H, lamb=[0.00125, 0.00021, 0.00038], x0=x0, y0=y0)
+        self.tx = tx
+        self.init = np.stack((self.mm.init_marker_x_pos, self.mm.init_marker_y_pos), axis=-1).reshape(-1, 2)
+        self.traj = None
+
+    def step(self, hm_mm: torch.Tensor, press_mm: torch.Tensor, theta: np.ndarray) -> torch.Tensor:
+        N = hm_mm.shape[0]
+        if self.traj is None:
+            self.traj = [[] for _ in range(N)]
+        deformed_gel, contact_mask = ref_deformed_gel(self.tx, hm_mm, press_mm)
+        deformed_gel = deformed_gel.max() - deformed_gel
+        out = torch.zeros((N, 2, self.init.shape[0], 2))
+        out[:, 0] = torch.tensor(self.init)
+        for env_id in range(N):
+            if press_mm[env_id].item() > 0.0:
+                contact_points = torch.argwhere(contact_mask[env_id])
+                mean = torch.mean(contact_points.float(), dim=0).cpu().numpy()
+                mean[0] = (mean[0] - self.mm.tactile_img_height / 2) / self.mm.mm2pix
+                mean[1] = (mean[1] - self.mm.tactile_img_width / 2) / self.mm.mm2pix
+                self.traj[env_id].append([mean[1], mean[0], theta[env_id]])
+                mx, my = self.mm.marker_sim(deformed_gel[env_id].cpu().numpy(), contact_mask[env_id].cpu().numpy(),
+                                            self.traj[env_id])
+            else:
+                self.traj[env_id] = []
+                mx, my = self.mm.init_marker_x_pos, self.mm.init_marker_y_pos
+            out[env_id, 1] = torch.tensor(np.stack((mx, my), axis=-1).reshape(-1, 2))
+        return out

@@ -1,0 +1,436 @@
+/*
+ * oracle/taxim_canon.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Canonical CPU restatement (plain C, float32, fixed operation order) of the
+ * reference's tactile hot path:
+ *   - TaximSimulator.compute_indentation_depth   (ref: source/tacex/tacex/simulation_approaches/gpu_taxim/taxim_sim.py:115-131)
+ *   - TaximTorch.__get_shifted_height_map        (ref: .../gpu_taxim/sim/taxim_torch.py:432-441)
+ *   - TaximTorch.__compute_gel_pad_deformation   (ref: taxim_torch.py:443-473)
+ *   - TaximTorch.__gaussian_blur / fast_conv2d   (ref: taxim_torch.py:382-412, 19-44)  -- restated as a direct separable
+ *                                                  reflect-padded correlation (mathematically identical to the FFT path)
+ *   - TaximTorch.__generate_normals              (ref: taxim_torch.py:475-503)
+ *   - bin + polynomial lookup in __render        (ref: taxim_torch.py:243-258)
+ *   - FOTS MarkerMotion._motion_callback etc.    (ref: .../fots/sim/marker_motion.py:78-120,144-219)
+ *   - FOTSMarkerSimulator glue                   (ref: .../fots/fots_marker_sim.py:114-184)
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this library.
+ * The product (tacex_b200/) never links or calls it.
+ *
+ * Parity status: PINNED against the executed reference (oracle/make_golden.py runs the reference's own
+ * TaximTorch / MarkerMotion here and commits the vectors under tests/golden/); the reference's own tests
+ * hold no golden vectors for this path.
+ *
+ * Canonical choices: blur = horizontal pass then vertical pass, each output
+ * accumulated as acc = fmaf(w[k], x[k], acc) for k ascending from an initial 0.0f; gel map == 0 when the
+ * caller passes gel == NULL; atanf / atan2f are the fixed polynomial below (identical text in the CUDA kernel).
+ *
+ * Build: gcc -O2 -ffp-contract=off -mfma -shared -fPIC (see oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define CANON_MAX_BLURS 8
+
+typedef struct {
+    int H, W;
+    int num_bins;           /* 125 */
+    float pixmm;            /* 0.0295 */
+    float calib_h, calib_w; /* 480, 640 */
+    float contact_scale;    /* 0.4 */
+    int n_blurs;            /* pyramid levels + 1 final blur (7) */
+    int ksx[CANON_MAX_BLURS];
+    int ksy[CANON_MAX_BLURS];
+    /* taps: for blur l, x taps at taps + off_x[l] (ksx[l] floats), y taps at taps + off_y[l] */
+    int off_x[CANON_MAX_BLURS];
+    int off_y[CANON_MAX_BLURS];
+} canon_cfg;
+
+/* ---------------- canonical elementary functions (float32, fixed op order) ---------------- */
+
+/* Cephes-style atanf; every operation is a single IEEE float32 op (no contraction). */
+static float canon_atanf(float xx)
+{
+    float x = fabsf(xx);
+    float y;
+    if (x > 2.414213562373095f) { /* tan(3 pi / 8) */
+        y = 1.5707963267948966f;
+        x = -(1.0f / x);
+    } else if (x > 0.4142135623730950f) { /* tan(pi / 8) */
+        y = 0.7853981633974483f;
+        x = (x - 1.0f) / (x + 1.0f);
+    } else {
+        y = 0.0f;
+    }
+    float z = x * x;
+    float p = 8.05374449538e-2f;
+    p = fmaf(p, z, -1.38776856032e-1f);
+    p = fmaf(p, z, 1.99777106478e-1f);
+    p = fmaf(p, z, -3.33329491539e-1f);
+    p = p * z;
+    p = fmaf(p, x, x);
+    y = y + p;
+    return (xx < 0.0f) ? -y : y;
+}
+
+static float canon_atan2f(float y, float x)
+{
+    const float PI_F = 3.14159265358979323846f;
+    const float PIO2_F = 1.5707963267948966f;
+    if (x == 0.0f) {
+        if (y > 0.0f) return PIO2_F;
+        if (y < 0.0f) return -PIO2_F;
+        return 0.0f;
+    }
+    float z = canon_atanf(y / x);
+    if (x < 0.0f) {
+        if (y < 0.0f) return z - PI_F;
+        return z + PI_F;
+    }
+    return z;
+}
+
+static inline int reflect_idx(int i, int n)
+{
+    /* torch 'reflect' padding (no edge repeat); valid for |overhang| < n */
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+/* one separable blur: tmp = horizontal(src), dst = vertical(tmp) */
+static void canon_blur(const float* src, float* tmp, float* dst, int H, int W, const float* kx, int ksx, const float* ky,
+                       int ksy)
+{
+    int rx = (ksx - 1) / 2, ry = (ksy - 1) / 2;
+    for (int y = 0; y < H; ++y) {
+        const float* row = src + (size_t)y * W;
+        for (int x = 0; x < W; ++x) {
+            float acc = 0.0f;
+            for (int k = 0; k < ksx; ++k) acc = fmaf(kx[k], row[reflect_idx(x + k - rx, W)], acc);
+            tmp[(size_t)y * W + x] = acc;
+        }
+    }
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            float acc = 0.0f;
+            for (int k = 0; k < ksy; ++k) acc = fmaf(ky[k], tmp[(size_t)reflect_idx(y + k - ry, H) * W + x], acc);
+            dst[(size_t)y * W + x] = acc;
+        }
+    }
+}
+
+/* ref: taxim_sim.py:115-131 */
+void canon_indentation_depth(const float* hm_mm, int N, int H, int W, float gelpad_height_m, float gelpad_to_cam_min_m,
+                             float* depth_mm)
+{
+    for (int n = 0; n < N; ++n) {
+        const float* p = hm_mm + (size_t)n * H * W;
+        float m = p[0];
+        for (int i = 1; i < H * W; ++i) m = fminf(m, p[i]);
+        float d = m / 1000.0f;
+        d = d - gelpad_to_cam_min_m;
+        if (d < 0.0f) d = 0.0f;
+        depth_mm[n] = (d <= gelpad_height_m) ? (gelpad_height_m - d) * 1000.0f : 0.0f;
+    }
+}
+
+/*
+ * Full optical path for a batch.
+ *   hm_mm   [N][H][W]   height map in mm (as GelSightSensor._get_height_map produces it)
+ *   press   [N]         indentation depth in mm
+ *   taps                concatenated 1-D Gaussian taps (see canon_cfg)
+ *   poly    [3][nb][nb][6], bg [3][H][W], gel [H][W] or NULL (== 0)
+ * outputs (any may be NULL): deformed [N][H][W], mask [N][H][W] u8, idx_mag/idx_dir [N][H][W] i32, rgb [N][H][W][3]
+ */
+int canon_taxim_render(const canon_cfg* cfg, const float* taps, const float* poly, const float* bg, const float* gel,
+                       const float* hm_mm, const float* press, int N, float* deformed, uint8_t* mask_out,
+                       int32_t* idx_mag_out, int32_t* idx_dir_out, float* rgb)
+{
+    const int H = cfg->H, W = cfg->W, HW = H * W, nb = cfg->num_bins;
+    int status = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int n = 0; n < N; ++n) {
+        float* h = (float*)malloc(sizeof(float) * HW);
+        float* j = (float*)malloc(sizeof(float) * HW);
+        float* b = (float*)malloc(sizeof(float) * HW);
+        float* t1 = (float*)malloc(sizeof(float) * HW);
+        float* t2 = (float*)malloc(sizeof(float) * HW);
+        uint8_t* mk = (uint8_t*)malloc(HW);
+        float* mag = (float*)malloc(sizeof(float) * HW);
+        float* dir = (float*)malloc(sizeof(float) * HW);
+        if (!h || !j || !b || !t1 || !t2 || !mk || !mag || !dir) {
+            status = -1;
+        } else {
+            const float* hm = hm_mm + (size_t)n * HW;
+            /* ref: taxim_torch.py:441  height_map - amin - press */
+            float m = hm[0];
+            for (int i = 1; i < HW; ++i) m = fminf(m, hm[i]);
+            for (int i = 0; i < HW; ++i) h[i] = (hm[i] - m) - press[n];
+            /* ref: taxim_torch.py:449-461 */
+            float hmin = h[0];
+            for (int i = 1; i < HW; ++i) hmin = fminf(hmin, h[i]);
+            float pd = -hmin;
+            float thr = (-pd) * cfg->contact_scale;
+            for (int i = 0; i < HW; ++i) {
+                float g = gel ? gel[i] : 0.0f;
+                int contact = h[i] < 0.0f;
+                j[i] = fminf(h[i], g);
+                mk[i] = (uint8_t)(((j[i] - g) < thr) && contact);
+            }
+            /* ref: taxim_torch.py:464-471 */
+            memcpy(b, j, sizeof(float) * HW);
+            for (int l = 0; l < cfg->n_blurs; ++l) {
+                canon_blur(b, t1, t2, H, W, taps + cfg->off_x[l], cfg->ksx[l], taps + cfg->off_y[l], cfg->ksy[l]);
+                if (l < cfg->n_blurs - 1) {
+                    for (int i = 0; i < HW; ++i) b[i] = mk[i] ? j[i] : t2[i];
+                } else {
+                    memcpy(b, t2, sizeof(float) * HW);
+                }
+            }
+            if (deformed) memcpy(deformed + (size_t)n * HW, b, sizeof(float) * HW);
+            if (mask_out) memcpy(mask_out + (size_t)n * HW, mk, HW);
+
+            if (rgb || idx_mag_out || idx_dir_out) {
+                /* ref: taxim_torch.py:237-238, 475-503 ; z = -(deformed / pixmm) */
+                for (int i = 0; i < HW; ++i) t1[i] = -(b[i] / cfg->pixmm);
+                const float sy = (float)H, sx = (float)W;
+                for (int y = 1; y < H - 1; ++y) {
+                    for (int x = 1; x < W - 1; ++x) {
+                        float top = t1[(y - 1) * W + x], bot = t1[(y + 1) * W + x];
+                        float left = t1[y * W + x - 1], right = t1[y * W + x + 1];
+                        float dzdx = (bot - top) / 2.0f;
+                        float dzdy = (right - left) / 2.0f;
+                        float gx = (dzdx * sy) / cfg->calib_h;
+                        float gy = (dzdy * sx) / cfg->calib_w;
+                        float tt = sqrtf(gx * gx + gy * gy);
+                        mag[y * W + x] = canon_atanf(tt);
+                        dir[y * W + x] = (tt != 0.0f) ? canon_atan2f(gx / tt, gy / tt) : 0.0f;
+                    }
+                }
+                /* replicate pad by 1 (ref: taxim_torch.py:501-502) */
+                for (int y = 0; y < H; ++y) {
+                    int yy = y < 1 ? 1 : (y > H - 2 ? H - 2 : y);
+                    for (int x = 0; x < W; ++x) {
+                        int xx = x < 1 ? 1 : (x > W - 2 ? W - 2 : x);
+                        if (yy != y || xx != x) {
+                            mag[y * W + x] = mag[yy * W + xx];
+                            dir[y * W + x] = dir[yy * W + xx];
+                        }
+                    }
+                }
+                /* ref: taxim_torch.py:241-258 */
+                const float x_binr = (float)(0.5 * M_PI / (nb - 1));
+                const float y_binr = (float)(2.0 * M_PI / (nb - 1));
+                const float pi_f = (float)M_PI;
+                for (int y = 0; y < H; ++y) {
+                    for (int x = 0; x < W; ++x) {
+                        int i = y * W + x;
+                        int im = (int)floorf(mag[i] / x_binr);
+                        int id = (int)floorf((dir[i] + pi_f) / y_binr);
+                        if (idx_mag_out) idx_mag_out[(size_t)n * HW + i] = im;
+                        if (idx_dir_out) idx_dir_out[(size_t)n * HW + i] = id;
+                        if (rgb) {
+                            if (im < 0) im = 0;
+                            if (im > nb - 1) im = nb - 1;
+                            if (id < 0) id = 0;
+                            if (id > nb - 1) id = nb - 1;
+                            /* features: x = col * calib_w / W, y = row * calib_h / H (ref: taxim_torch.py:139-157) */
+                            float xf = (float)x * (cfg->calib_w / (float)W);
+                            float yf = (float)y * (cfg->calib_h / (float)H);
+                            float f0 = xf * xf, f1 = yf * yf, f2 = xf * yf;
+                            for (int c = 0; c < 3; ++c) {
+                                const float* p = poly + (((size_t)c * nb + im) * nb + id) * 6;
+                                float s = p[5];
+                                s = fmaf(p[4], yf, s);
+                                s = fmaf(p[3], xf, s);
+                                s = fmaf(p[2], f2, s);
+                                s = fmaf(p[1], f1, s);
+                                s = fmaf(p[0], f0, s);
+                                s = s + bg[(size_t)c * HW + i];
+                                s = fminf(fmaxf(s, 0.0f), 1.0f);
+                                rgb[((size_t)n * HW + i) * 3 + c] = s;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        free(h); free(j); free(b); free(t1); free(t2); free(mk); free(mag); free(dir);
+    }
+    return status;
+}
+
+/* ---------------- FOTS marker motion (float64 like the NumPy reference) ---------------- */
+
+typedef struct {
+    int H, W;
+    int rows, cols;        /* marker grid */
+    double lamb[3];        /* dilate, shear, twist */
+    double mm2pix;         /* 19.58 */
+    double shear_max_px;   /* 10 */
+    double theta_max_rad;  /* 60 deg */
+} canon_fots_cfg;
+
+/* ref: marker_motion.py:58-76 -- np.linspace(x0, W - x0, cols, dtype=int) */
+void canon_fots_grid(const canon_fots_cfg* c, double x0, double y0, int32_t* mx /*[rows*cols]*/, int32_t* my)
+{
+    for (int r = 0; r < c->rows; ++r) {
+        for (int q = 0; q < c->cols; ++q) {
+            double stepx = c->cols > 1 ? ((double)(c->W - x0) - x0) / (double)(c->cols - 1) : 0.0;
+            double stepy = c->rows > 1 ? ((double)(c->H - y0) - y0) / (double)(c->rows - 1) : 0.0;
+            double vx = (q == c->cols - 1 && c->cols > 1) ? (double)(c->W - x0) : x0 + stepx * q;
+            double vy = (r == c->rows - 1 && c->rows > 1) ? (double)(c->H - y0) : y0 + stepy * r;
+            mx[r * c->cols + q] = (int32_t)vx; /* astype(int) truncates toward zero */
+            my[r * c->cols + q] = (int32_t)vy;
+        }
+    }
+}
+
+/*
+ * One FOTS step for a batch (restates fots_marker_sim.py:128-182 + marker_motion.py:144-219).
+ *   deformed [N][H][W] f32, mask [N][H][W] u8, press [N], theta [N]
+ *   traj0 [N][4] inout: (x0_mm, y0_mm, theta0, valid) -- first in-contact sample of the current contact episode
+ *   traj_len [N] inout: number of samples in the episode (reference keeps a python list; only [0], [-1], len matter)
+ *   markers [N][2][M][2] out, M = rows*cols; [:,0] initial, [:,1] current, last dim (x, y)
+ */
+void canon_fots_step(const canon_fots_cfg* c, const int32_t* mx, const int32_t* my, const float* deformed,
+                     const uint8_t* mask, const float* press, const float* theta, int N, float* traj0,
+                     int32_t* traj_len, float* markers)
+{
+    const int H = c->H, W = c->W, HW = H * W, M = c->rows * c->cols;
+    for (int n = 0; n < N; ++n) {
+        float* out0 = markers + (size_t)n * 2 * M * 2;
+        float* out1 = out0 + (size_t)M * 2;
+        for (int m = 0; m < M; ++m) {
+            out0[2 * m] = (float)mx[m];
+            out0[2 * m + 1] = (float)my[m];
+        }
+        if (!(press[n] > 0.0f)) {
+            traj_len[n] = 0;
+            traj0[4 * n + 3] = 0.0f;
+            for (int m = 0; m < M; ++m) {
+                out1[2 * m] = (float)mx[m];
+                out1[2 * m + 1] = (float)my[m];
+            }
+            continue;
+        }
+        const float* b = deformed + (size_t)n * HW;
+        const uint8_t* mk = mask + (size_t)n * HW;
+        /* contact centroid: torch.mean(argwhere(mask).float(), dim=0) -- float32 mean; restated with exact
+           integer sums then one float32 division (differs from torch's float32 summation by <= a few ulp) */
+        double srow = 0.0, scol = 0.0;
+        long cnt = 0;
+        float bmax = b[0];
+        for (int i = 0; i < HW; ++i) {
+            bmax = fmaxf(bmax, b[i]);
+            if (mk[i]) {
+                srow += (double)(i / W);
+                scol += (double)(i % W);
+                ++cnt;
+            }
+        }
+        float mrow = (float)(srow / (double)cnt); /* NaN when cnt == 0, like torch.mean of an empty tensor */
+        float mcol = (float)(scol / (double)cnt);
+        /* numpy float32 arithmetic with python-float scalars stays float32 (NumPy 2) */
+        float cy = (mrow - (float)(H / 2.0)) / (float)c->mm2pix;
+        float cx = (mcol - (float)(W / 2.0)) / (float)c->mm2pix;
+        float th = theta[n];
+        if (traj_len[n] == 0) {
+            traj0[4 * n + 0] = cx;
+            traj0[4 * n + 1] = cy;
+            traj0[4 * n + 2] = th;
+            traj0[4 * n + 3] = 1.0f;
+        }
+        traj_len[n] += 1;
+
+        /* depth = (max(b) - b) - min(...) = max(b) - b ; /10 (float32, marker_motion.py:146-149).
+           The reference subtracts the BATCH max and then the per-env min; that is per-env (max_b - b) up to
+           one float32 rounding. */
+        /* contact list: markers whose initial integer position lies on the mask */
+        double dxs[1024], dys[1024];
+        for (int m = 0; m < M; ++m) { dxs[m] = 0.0; dys[m] = 0.0; }
+        int ncontact = 0;
+        for (int q = 0; q < c->cols; ++q) {
+            for (int r = 0; r < c->rows; ++r) {
+                int m = r * c->cols + q;
+                int yp = my[m], xp = mx[m];
+                if (yp >= H || yp < 0 || xp >= W || xp < 0) continue;
+                if (mk[yp * W + xp] == 1) {
+                    float hgt = (bmax - b[yp * W + xp]) / 10.0f;
+                    ++ncontact;
+                    /* dilate contribution of this contact point on every marker (marker_motion.py:111-120) */
+                    for (int k = 0; k < M; ++k) {
+                        double ox = (double)(mx[k] - xp), oy = (double)(my[k] - yp);
+                        double g = exp(-c->lamb[0] * (ox * ox + oy * oy));
+                        dxs[k] += (double)hgt * ox * g;
+                        dys[k] += (double)hgt * oy * g;
+                    }
+                }
+            }
+        }
+        if (ncontact == 0) {
+            for (int m = 0; m < M; ++m) {
+                out1[2 * m] = (float)mx[m];
+                out1[2 * m + 1] = (float)my[m];
+            }
+            continue;
+        }
+        int have_traj = traj_len[n] >= 2;
+        double scx = 0, scy = 0, shx = 0, shy = 0, tcx = 0, tcy = 0, cm1 = 0, sn = 0;
+        if (have_traj) {
+            /* python: float32 scalar * python float -> float32 in NumPy 2 ; int() truncates toward zero */
+            float x0 = traj0[4 * n + 0], y0 = traj0[4 * n + 1], t0 = traj0[4 * n + 2];
+            scx = (double)(int)(x0 * (float)c->mm2pix + (float)(W / 2.0));
+            scy = (double)(int)(y0 * (float)c->mm2pix + (float)(H / 2.0));
+            shx = (double)(int)((cx - x0) * (float)c->mm2pix);
+            shy = (double)(int)((cy - y0) * (float)c->mm2pix);
+            if (shx > c->shear_max_px) shx = c->shear_max_px;
+            if (shx < -c->shear_max_px) shx = -c->shear_max_px;
+            if (shy > c->shear_max_px) shy = c->shear_max_px;
+            if (shy < -c->shear_max_px) shy = -c->shear_max_px;
+            tcx = (double)(int)(cx * (float)c->mm2pix + (float)(W / 2.0));
+            tcy = (double)(int)(cy * (float)c->mm2pix + (float)(H / 2.0));
+            /* np.clip / np.cos / np.sin on a float32 scalar stay float32 (NumPy 2 weak python scalars) */
+            float thf = th - t0;
+            float tmax = (float)c->theta_max_rad;
+            if (thf > tmax) thf = tmax;
+            if (thf < -tmax) thf = -tmax;
+            cm1 = (double)cosf(thf - 1.0f); /* sic: cos(theta - 1), marker_motion.py:98-99 */
+            sn = (double)sinf(thf);
+        }
+        for (int m = 0; m < M; ++m) {
+            double px = (double)mx[m], py = (double)my[m];
+            double nx = px + dxs[m], ny = py + dys[m];
+            if (have_traj) {
+                double ox = px - scx, oy = py - scy;
+                double g = exp(-c->lamb[1] * (ox * ox + oy * oy));
+                nx += shx * g;
+                ny += shy * g;
+                ox = px - tcx;
+                oy = py - tcy;
+                g = exp(-c->lamb[2] * (ox * ox + oy * oy));
+                double rx = ox * cm1 - oy * sn;
+                double ry = ox * sn + oy * cm1;
+                nx += rx * g;
+                ny += ry * g;
+            }
+            out1[2 * m] = (float)nx;
+            out1[2 * m + 1] = (float)ny;
+        }
+    }
+}
+
+int canon_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,176 @@
+"""Synthetic ("recorded") contact depth maps that stand in for Isaac Sim's RTX depth camera.
+
+The reference obtains the height map from the sensor camera's depth image of the indenter
+(ref: source/tacex/tacex/gelsight_sensor.py:581-593). That upstream producer is out of scope; the
+benchmark and the parity tests replace it with the analytic indenters of SURVEY.md section 8(d):
+
+  config 0: one sphere (r = 3 mm) pressed 1 mm, centred
+  config 1: spheres, random centre / press, 10 % of the envs without contact (seed 0)
+  config 2: sphere / flat cylinder / 90 deg wedge / 60 deg cone, random pose + in-plane yaw (seed 1),
+            plus a FOTS trajectory (first-contact pose, then shear and twist)
+
+All generators are deterministic (``torch.Generator`` on the CPU) so the GPU box reproduces the inputs
+of the committed golden fixtures without access to the reference checkout.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+# GelSight Mini geometry (ref: source/tacex_assets/tacex_assets/sensors/gelsight_mini/gsmini_cfg.py:22-32,51-52)
+CLIP_MIN_M = 0.024
+CLIP_MAX_M = 0.029
+GELPAD_HEIGHT_M = 0.0045
+GEL_SURFACE_M = CLIP_MIN_M + GELPAD_HEIGHT_M  # 0.0285 m from the camera
+PIXEL_PITCH_M_320 = 0.0295e-3 * 640 / 320  # 0.059 mm per pixel at 320 x 240
+
+
+def _grid(H: int, W: int, pitch: float) -> tuple[torch.Tensor, torch.Tensor]:
+    ys = (torch.arange(H, dtype=torch.float64) - H / 2 + 0.5) * pitch
+    xs = (torch.arange(W, dtype=torch.float64) - W / 2 + 0.5) * pitch
+    Y, X = torch.meshgrid(ys, xs, indexing="ij")
+    return X, Y
+
+
+def indenter_profile(kind: int, X: torch.Tensor, Y: torch.Tensor, size: float) -> torch.Tensor:
+    """Height of the indenter surface above its lowest point [m]; +inf outside its footprint.
+
+    kind 0 sphere (radius ``size``), 1 flat cylinder (radius ``size``), 2 wedge (90 deg edge along y, half
+    width ``size``), 3 cone (60 deg apex, base radius ``size``).
+    """
+    rho2 = X * X + Y * Y
+    inf = torch.full_like(X, float("inf"))
+    if kind == 0:
+        z = size - torch.sqrt(torch.clamp(size * size - rho2, min=0.0))
+        return torch.where(rho2 < size * size, z, inf)
+    if kind == 1:
+        return torch.where(rho2 < size * size, torch.zeros_like(X), inf)
+    if kind == 2:
+        z = X.abs()  # 90 deg edge: slope 1 on both flanks
+        return torch.where((X.abs() < size) & (Y.abs() < 2.0 * size), z, inf)
+    if kind == 3:
+        z = torch.sqrt(rho2) / math.tan(math.radians(30.0))  # 60 deg full apex angle
+        return torch.where(rho2 < size * size, z, inf)
+    raise ValueError(f"unknown indenter kind {kind}")
+
+
+def depth_map(
+    kind: int,
+    size_m: float,
+    cx_m: float,
+    cy_m: float,
+    yaw: float,
+    press_m: float,
+    H: int = 240,
+    W: int = 320,
+    pitch: float = PIXEL_PITCH_M_320,
+    contact: bool = True,
+) -> torch.Tensor:
+    """Camera depth image [m] (float32, H x W) of one indenter pressed ``press_m`` into the gel."""
+    if not contact:
+        return torch.full((H, W), CLIP_MAX_M, dtype=torch.float32)
+    X, Y = _grid(H, W, pitch)
+    Xc, Yc = X - cx_m, Y - cy_m
+    c, s = math.cos(yaw), math.sin(yaw)
+    Xr = c * Xc + s * Yc
+    Yr = -s * Xc + c * Yc
+    z = indenter_profile(kind, Xr, Yr, size_m)
+    d = torch.clamp(GEL_SURFACE_M - press_m + z, max=CLIP_MAX_M)
+    return d.to(torch.float32)
+
+
+def height_map_mm(depth_m: torch.Tensor, clip_max_m: float = CLIP_MAX_M) -> torch.Tensor:
+    """GelSightSensor._get_height_map (ref: gelsight_sensor.py:581-593): inf -> clip max, metres -> mm."""
+    hm = depth_m.clone()
+    hm[torch.isinf(hm)] = clip_max_m
+    hm *= 1000
+    return hm
+
+
+def config0(H: int = 240, W: int = 320) -> dict:
+    d = depth_map(0, 3e-3, 0.0, 0.0, 0.0, 1e-3, H, W)[None]
+    return {"depth_m": d, "kind": torch.zeros(1, dtype=torch.int64)}
+
+
+def config1(n_envs: int = 256, seed: int = 0, H: int = 240, W: int = 320) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    cx = (torch.rand(n_envs, generator=g, dtype=torch.float64) * 8 - 4) * 1e-3
+    cy = (torch.rand(n_envs, generator=g, dtype=torch.float64) * 6 - 3) * 1e-3
+    p = (0.2 + torch.rand(n_envs, generator=g, dtype=torch.float64) * 1.3) * 1e-3
+    nocontact = torch.rand(n_envs, generator=g, dtype=torch.float64) < 0.10
+    d = torch.stack(
+        [
+            depth_map(0, 3e-3, cx[i].item(), cy[i].item(), 0.0, p[i].item(), H, W, contact=not bool(nocontact[i]))
+            for i in range(n_envs)
+        ]
+    )
+    return {"depth_m": d, "kind": torch.zeros(n_envs, dtype=torch.int64), "contact": ~nocontact}
+
+
+def config2(n_envs: int = 1024, seed: int = 1, H: int = 240, W: int = 320) -> dict:
+    """Random primitive indenters + a two-sample FOTS trajectory per env.
+
+    Returns depth maps for the FIRST contact sample (``depth_m0``, yaw ``theta0``) and for the CURRENT sample
+    (``depth_m``, yaw ``theta``): the indenter is sheared by U(-0.5, 0.5) mm and twisted by U(-30, 30) deg.
+    """
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.rand(n_envs, generator=g, dtype=torch.float64)  # noqa: E731
+    kind = torch.randint(0, 4, (n_envs,), generator=g)
+    u_size = r()
+    cx = (r() * 8 - 4) * 1e-3
+    cy = (r() * 6 - 3) * 1e-3
+    p = (0.2 + r() * 1.3) * 1e-3
+    yaw0 = (r() * 2 - 1) * math.pi
+    sx = (r() - 0.5) * 1e-3
+    sy = (r() - 0.5) * 1e-3
+    dth = (r() * 2 - 1) * math.radians(30.0)
+    nocontact = r() < 0.10
+    size = torch.empty(n_envs, dtype=torch.float64)
+    for i in range(n_envs):
+        k = int(kind[i])
+        lo, hi = {0: (1.5, 4.0), 1: (1.0, 3.0), 2: (1.0, 3.0), 3: (1.5, 4.0)}[k]
+        size[i] = (lo + (hi - lo) * u_size[i]) * 1e-3
+    d0, d1 = [], []
+    for i in range(n_envs):
+        c = not bool(nocontact[i])
+        d0.append(depth_map(int(kind[i]), size[i].item(), cx[i].item(), cy[i].item(), yaw0[i].item(), p[i].item(), H, W, contact=c))
+        d1.append(
+            depth_map(
+                int(kind[i]), size[i].item(), (cx[i] + sx[i]).item(), (cy[i] + sy[i]).item(), (yaw0[i] + dth[i]).item(),
+                p[i].item(), H, W, contact=c,
+            )
+        )
+    return {
+        "depth_m0": torch.stack(d0),
+        "depth_m": torch.stack(d1),
+        "theta0": yaw0.to(torch.float32),
+        "theta": (yaw0 + dth).to(torch.float32),
+        "kind": kind,
+        "contact": ~nocontact,
+    }
+
+
+def golden_config1(H: int = 240, W: int = 320) -> torch.Tensor:
+    """Height maps [mm] of the committed ``config1_sub`` fixture: 4 config-1 spheres + 1 env without contact."""
+    d = config1(4, seed=0, H=H, W=W)["depth_m"]
+    d = torch.cat([d, depth_map(0, 3e-3, 0.0, 0.0, 0.0, 0.0, H, W, contact=False)[None]])
+    return height_map_mm(d)
+
+
+def golden_config2(H: int = 240, W: int = 320) -> dict:
+    """Inputs of the committed ``config2_sub`` fixture (8 envs, two trajectory samples)."""
+    c2 = config2(8, seed=1, H=H, W=W)
+    return {"hm0": height_map_mm(c2["depth_m0"]), "hm1": height_map_mm(c2["depth_m"]), "theta0": c2["theta0"],
+            "theta": c2["theta"], "kind": c2["kind"]}
+
+
+def bench_batch(n_envs: int, seed: int = 0, H: int = 240, W: int = 320, n_unique: int = 64) -> torch.Tensor:
+    """Height maps [mm] for the benchmark: ``n_unique`` config-1 style sphere presses tiled to ``n_envs``.
+
+    Generating thousands of analytic maps on the host is slow; the benchmark tiles a pool of unique maps (every
+    env still runs the full path -- there is no caching anywhere in the engine)."""
+    pool = height_map_mm(config1(min(n_unique, n_envs), seed, H, W)["depth_m"])
+    reps = (n_envs + pool.shape[0] - 1) // pool.shape[0]
+    return pool.repeat(reps, 1, 1)[:n_envs].contiguous()
