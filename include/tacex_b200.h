@@ -1,0 +1,140 @@
+/*
+ * tacex_b200.h -- C ABI of the B200-native tactile-image synthesis engine (libtacex_b200.so).
+ *
+ * The reference (DH-Ng/TacEx) has no FFI on this path: its plug-in boundary is the Python ABC
+ * GelSightSimulator (ref: source/tacex/tacex/simulation_approaches/gelsight_simulator.py:17-56) whose
+ * implementations run torch / NumPy code in-process. This library is what a drop-in implementation of
+ * that ABC binds (via ctypes): every entry point below replaces one reference
+ * function of the hot path, cited at its declaration.
+ *
+ * Conventions
+ *   - plain C types only; all data pointers are DEVICE pointers owned by the caller (e.g. torch tensors),
+ *     except where a parameter is documented as a host pointer;
+ *   - every call is asynchronous and ordered on the CUDA stream given at tx_create; no call synchronises
+ *     the host except tx_create / tx_upload_tables / tx_destroy / the *_host convenience entry points;
+ *   - return value: TX_OK (0) or a negative tx_status; tx_last_error() returns a message for the last
+ *     failure on that handle; no C++ exception crosses the boundary;
+ *   - a handle is bound to one (device, stream) and is not thread-safe; different handles are independent.
+ *   - images are row-major [N][H][W]; RGB output is [N][H][W][3] float32 in [0, 1] (NHWC, as
+ *     TaximSimulator.optical_simulation returns it, ref: .../gpu_taxim/taxim_sim.py:80-113).
+ */
+#ifndef TACEX_B200_H
+#define TACEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TX_ABI_VERSION 1
+#define TX_MAX_BLURS 8
+#define TX_MAX_TAPS 64
+#define TX_MAX_MARKERS 256
+
+typedef enum {
+    TX_OK = 0,
+    TX_ERR_INVALID_ARG = -1,
+    TX_ERR_UNSUPPORTED = -2, /* shape / kernel radii this build has no specialisation for */
+    TX_ERR_CUDA = -3,
+    TX_ERR_NO_TABLES = -4,
+    TX_ERR_NO_DEVICE = -5,
+    TX_ERR_STATE = -6
+} tx_status;
+
+typedef struct tx_handle tx_handle;
+
+/* Optical + marker configuration. Mirrors TaximSimulatorCfg / params.json / FOTSMarkerSimulatorCfg
+ * (ref: .../gpu_taxim/taxim_sim_cfg.py:12-36, .../gpu_taxim/sim/taxim_impl.py:17-62,
+ *       .../fots/fots_marker_sim_cfg.py:15-75, .../fots/fots_marker_sim.py:77). */
+typedef struct {
+    int abi_version;           /* TX_ABI_VERSION */
+    int H, W;                  /* tactile image shape (240, 320) */
+    int max_envs;              /* upper bound of N for scratch allocation */
+    int num_bins;              /* 125 */
+    float pixmm;               /* 0.0295 (NOT rescaled with the resolution) */
+    float calib_h, calib_w;    /* 480, 640 */
+    float contact_scale;       /* 0.4 */
+    float gelpad_height_m;     /* 0.0045 */
+    float gelpad_to_cam_min_m; /* 0.024 */
+    int n_blurs;               /* pyramid levels + final blur (7) */
+    int ksx[TX_MAX_BLURS];     /* odd tap counts along x (W) per blur */
+    int ksy[TX_MAX_BLURS];     /* odd tap counts along y (H) per blur */
+    float taps_x[TX_MAX_BLURS][TX_MAX_TAPS]; /* normalised float32 Gaussian taps (host computes them exactly */
+    float taps_y[TX_MAX_BLURS][TX_MAX_TAPS]; /*  as taxim_torch.py:363-367 does)                              */
+    /* FOTS marker model */
+    int marker_rows, marker_cols; /* 9 x 11 (reference default) or 7 x 9 (63 markers) */
+    float marker_x0, marker_y0;   /* 15, 26 */
+    double fots_lambda[3];        /* dilate, shear, twist: 0.00125, 0.00021, 0.00038 */
+    double mm2pix;                /* 19.58 */
+    double shear_max_px;          /* 10 */
+    double theta_max_rad;         /* 60 deg */
+} tx_config;
+
+typedef struct {
+    uint64_t render_calls, frames_rendered, fots_calls, depth_calls;
+    uint64_t kernels_launched; /* total kernels this handle has launched */
+} tx_counters;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+
+int tx_abi_version(void);
+
+/* Creates a handle on CUDA device `device` bound to `cuda_stream` (a cudaStream_t cast to void*, NULL = the
+ * legacy default stream). Fails with TX_ERR_NO_DEVICE when no CUDA device is usable -- there is no CPU path. */
+int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx_handle** out);
+void tx_destroy(tx_handle* h);
+const char* tx_last_error(const tx_handle* h); /* h may be NULL: returns the last creation error */
+int tx_get_counters(const tx_handle* h, tx_counters* out);
+
+/* Uploads the calibration tables (HOST pointers, copied and re-laid-out on the device):
+ *   poly_grad  [3][nb][nb][6] float32, RGB channel order  (ref: taxim_torch.py:73-80 `__poly_grad`)
+ *   background [3][H][W]      float32                     (ref: taxim_torch.py:136-137 background at (H, W))
+ *   gel_map    [H][W] float32 or NULL for a flat gel map (== 0 after the shift; ref: taxim_torch.py:82-90,159-164) */
+int tx_upload_tables(tx_handle* h, const float* poly_grad, const float* background, const float* gel_map);
+
+/* ---- hot path --------------------------------------------------------------------------------------------- */
+
+/* Replaces TaximSimulator.compute_indentation_depth (ref: .../gpu_taxim/taxim_sim.py:115-131).
+ *   height_mm [N][H][W] -> depth_mm [N] */
+int tx_indentation_depth(tx_handle* h, const float* height_mm, int N, float* depth_mm);
+
+/* Replaces TaximTorch.render_direct(with_shadow=False, press_depth=...) + the NHWC copy
+ * (ref: .../gpu_taxim/sim/taxim_torch.py:174-195, 225-258, 432-503; .../gpu_taxim/taxim_sim.py:104-111).
+ *   height_mm [N][H][W]
+ *   press_mm  [N] or NULL: NULL = compute the indentation depth inside the same kernel (fused
+ *             compute_indentation_depth + optical_simulation) and, if depth_out != NULL, store it there
+ *   rgb       [N][H][W][3]
+ *   deformed  optional [N][H][W]  deformed gel height (mm), the reference's `__compute_gel_pad_deformation` output
+ *   mask      optional [N][H][W]  uint8 shrunken contact mask
+ * When the handle has a marker grid, the per-env inputs of the FOTS model (mask centroid sums, max of the
+ * deformed gel, gel height and mask at the marker positions) are recorded for a following tx_fots_markers. */
+int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
+              float* deformed, uint8_t* mask);
+
+/* Replaces FOTSMarkerSimulator.marker_motion_simulation + MarkerMotion.marker_sim
+ * (ref: .../fots/fots_marker_sim.py:114-184, .../fots/sim/marker_motion.py:78-120,144-219) using the gel
+ * deformation recorded by the preceding tx_render of the SAME batch (no second blur pyramid).
+ *   press_mm [N]  indentation depth (> 0 = in contact), theta [N] relative yaw of the indenter (rad)
+ *   traj0    [N][4] in/out  (x0_mm, y0_mm, theta0, valid): first in-contact sample of the contact episode
+ *   traj_len [N]    in/out  samples in the current episode
+ *   markers  [N][2][M][2]   [:,0] initial, [:,1] current marker (x, y) in pixels */
+int tx_fots_markers(tx_handle* h, const float* press_mm, const float* theta, int N, float* traj0, int32_t* traj_len,
+                    float* markers);
+
+/* Initial marker grid (host pointers, M ints each). ref: marker_motion.py:58-76 */
+int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my);
+
+/* ---- host-buffer convenience (the end-to-end path the benchmark times) -------------------------------------- */
+
+/* height_mm_host [N][H][W] pinned or pageable HOST memory -> rgb_host [N][H][W][3], depth_host [N] (optional),
+ * markers_host [N][2][M][2] (optional, needs theta_host). Copies H2D, runs the fused path, copies D2H and
+ * synchronises the stream before returning. */
+int tx_step_host(tx_handle* h, const float* height_mm_host, const float* theta_host, int N, float* rgb_host,
+                 float* depth_host, float* markers_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACEX_B200_H */

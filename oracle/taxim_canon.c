@@ -197,20 +197,25 @@ int canon_taxim_render(const canon_cfg* cfg, const float* taps, const float* pol
             if (mask_out) memcpy(mask_out + (size_t)n * HW, mk, HW);
 
             if (rgb || idx_mag_out || idx_dir_out) {
-                /* ref: taxim_torch.py:237-238, 475-503 ; z = -(deformed / pixmm) */
-                for (int i = 0; i < HW; ++i) t1[i] = -(b[i] / cfg->pixmm);
-                const float sy = (float)H, sx = (float)W;
+                /* ref: taxim_torch.py:237-238, 475-503. Canonical (GPU-friendly) operation order, each step one
+                   float32 op: zs = b * (1/pixmm); central differences * 0.5; scale by H/calib_h, W/calib_w;
+                   tt = sqrt(fma(gx, gx, gy*gy)); dir = atan2(gx, gy) (the reference normalises both by tt first,
+                   which is the same angle). Differences to the literal reference sequence are <= 1-2 ulp, far inside
+                   the reference's own FFT noise. */
+                const float inv_pixmm = 1.0f / cfg->pixmm;
+                const float sy = (float)H / cfg->calib_h, sx = (float)W / cfg->calib_w;
+                for (int i = 0; i < HW; ++i) t1[i] = b[i] * inv_pixmm;
                 for (int y = 1; y < H - 1; ++y) {
                     for (int x = 1; x < W - 1; ++x) {
                         float top = t1[(y - 1) * W + x], bot = t1[(y + 1) * W + x];
                         float left = t1[y * W + x - 1], right = t1[y * W + x + 1];
-                        float dzdx = (bot - top) / 2.0f;
-                        float dzdy = (right - left) / 2.0f;
-                        float gx = (dzdx * sy) / cfg->calib_h;
-                        float gy = (dzdy * sx) / cfg->calib_w;
-                        float tt = sqrtf(gx * gx + gy * gy);
+                        float dzdx = (top - bot) * 0.5f;
+                        float dzdy = (left - right) * 0.5f;
+                        float gx = dzdx * sy;
+                        float gy = dzdy * sx;
+                        float tt = sqrtf(fmaf(gx, gx, gy * gy));
                         mag[y * W + x] = canon_atanf(tt);
-                        dir[y * W + x] = (tt != 0.0f) ? canon_atan2f(gx / tt, gy / tt) : 0.0f;
+                        dir[y * W + x] = (tt != 0.0f) ? canon_atan2f(gx, gy) : 0.0f;
                     }
                 }
                 /* replicate pad by 1 (ref: taxim_torch.py:501-502) */
@@ -225,14 +230,15 @@ int canon_taxim_render(const canon_cfg* cfg, const float* taps, const float* pol
                     }
                 }
                 /* ref: taxim_torch.py:241-258 */
-                const float x_binr = (float)(0.5 * M_PI / (nb - 1));
-                const float y_binr = (float)(2.0 * M_PI / (nb - 1));
+                const float inv_xbin = (float)(1.0 / (0.5 * M_PI / (nb - 1)));
+                const float inv_ybin = (float)(1.0 / (2.0 * M_PI / (nb - 1)));
                 const float pi_f = (float)M_PI;
+                const float fx = cfg->calib_w / (float)W, fy = cfg->calib_h / (float)H;
                 for (int y = 0; y < H; ++y) {
                     for (int x = 0; x < W; ++x) {
                         int i = y * W + x;
-                        int im = (int)floorf(mag[i] / x_binr);
-                        int id = (int)floorf((dir[i] + pi_f) / y_binr);
+                        int im = (int)floorf(mag[i] * inv_xbin);
+                        int id = (int)floorf((dir[i] + pi_f) * inv_ybin);
                         if (idx_mag_out) idx_mag_out[(size_t)n * HW + i] = im;
                         if (idx_dir_out) idx_dir_out[(size_t)n * HW + i] = id;
                         if (rgb) {
@@ -241,8 +247,8 @@ int canon_taxim_render(const canon_cfg* cfg, const float* taps, const float* pol
                             if (id < 0) id = 0;
                             if (id > nb - 1) id = nb - 1;
                             /* features: x = col * calib_w / W, y = row * calib_h / H (ref: taxim_torch.py:139-157) */
-                            float xf = (float)x * (cfg->calib_w / (float)W);
-                            float yf = (float)y * (cfg->calib_h / (float)H);
+                            float xf = (float)x * fx;
+                            float yf = (float)y * fy;
                             float f0 = xf * xf, f1 = yf * yf, f2 = xf * yf;
                             for (int c = 0; c < 3; ++c) {
                                 const float* p = poly + (((size_t)c * nb + im) * nb + id) * 6;

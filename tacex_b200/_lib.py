@@ -1,0 +1,80 @@
+"""ctypes binding of libtacex_b200.so (C ABI: include/tacex_b200.h).
+
+The library is the product; there is NO CPU fallback: if the shared object is missing or no Blackwell GPU is
+present, construction fails loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+TX_MAX_BLURS = 8
+TX_MAX_TAPS = 64
+TX_MAX_MARKERS = 256
+TX_ABI_VERSION = 1
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtacex_b200.so"
+
+
+class TxConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int),
+        ("H", C.c_int), ("W", C.c_int), ("max_envs", C.c_int), ("num_bins", C.c_int),
+        ("pixmm", C.c_float), ("calib_h", C.c_float), ("calib_w", C.c_float), ("contact_scale", C.c_float),
+        ("gelpad_height_m", C.c_float), ("gelpad_to_cam_min_m", C.c_float),
+        ("n_blurs", C.c_int),
+        ("ksx", C.c_int * TX_MAX_BLURS), ("ksy", C.c_int * TX_MAX_BLURS),
+        ("taps_x", (C.c_float * TX_MAX_TAPS) * TX_MAX_BLURS), ("taps_y", (C.c_float * TX_MAX_TAPS) * TX_MAX_BLURS),
+        ("marker_rows", C.c_int), ("marker_cols", C.c_int), ("marker_x0", C.c_float), ("marker_y0", C.c_float),
+        ("fots_lambda", C.c_double * 3), ("mm2pix", C.c_double), ("shear_max_px", C.c_double),
+        ("theta_max_rad", C.c_double),
+    ]
+
+
+class TxCounters(C.Structure):
+    _fields_ = [("render_calls", C.c_uint64), ("frames_rendered", C.c_uint64), ("fots_calls", C.c_uint64),
+                ("depth_calls", C.c_uint64), ("kernels_launched", C.c_uint64)]
+
+
+class TxError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
+    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host",
+]
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and declare the prototypes. Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TxError(f"{LIB_PATH} is missing: run `python -m tacex_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, fp, ip, u8p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # device pointers travel as integers
+    lib.tx_abi_version.restype = C.c_int
+    lib.tx_create.argtypes = [C.POINTER(TxConfig), C.c_int, vp, C.POINTER(C.c_void_p)]
+    lib.tx_create.restype = C.c_int
+    lib.tx_destroy.argtypes = [C.c_void_p]
+    lib.tx_destroy.restype = None
+    lib.tx_last_error.argtypes = [C.c_void_p]
+    lib.tx_last_error.restype = C.c_char_p
+    lib.tx_get_counters.argtypes = [C.c_void_p, C.POINTER(TxCounters)]
+    lib.tx_upload_tables.argtypes = [C.c_void_p, fp, fp, fp]
+    lib.tx_indentation_depth.argtypes = [C.c_void_p, fp, C.c_int, fp]
+    lib.tx_render.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp, u8p]
+    lib.tx_fots_markers.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, ip, fp]
+    lib.tx_marker_grid.argtypes = [C.c_void_p, ip, ip]
+    lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
+    for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_fots_markers",
+                 "tx_marker_grid", "tx_step_host"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib

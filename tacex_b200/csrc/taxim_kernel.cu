@@ -1,0 +1,474 @@
+// taxim_kernel.cu -- fused Taxim optical model for sm_100a: one 2-CTA cluster per 240x320 frame.
+//
+// Replaces (ref = /root/reference/source/tacex/tacex/simulation_approaches/gpu_taxim):
+//   taxim_sim.py:115-131          compute_indentation_depth           (fused when press_in == NULL)
+//   sim/taxim_torch.py:432-441    __get_shifted_height_map
+//   sim/taxim_torch.py:443-473    __compute_gel_pad_deformation  (6-level Gaussian pyramid + masked re-imposition + final blur)
+//   sim/taxim_torch.py:475-503    __generate_normals
+//   sim/taxim_torch.py:243-258    bin -> polynomial table -> + background -> clip
+//   taxim_sim.py:104-111          NCHW -> NHWC
+//
+// Data layout: each CTA of the cluster owns 120 rows of the frame as ONE float32 plane resident in shared memory
+// (153,600 B, staged by a bulk-async TMA copy of the contiguous half frame). Every blur level runs in place:
+//   horizontal pass  one warp per row, the row lives in registers (12 virtual columns per lane incl. reflect
+//                    padding), neighbours reached with warp shuffles, taps from __constant__ memory;
+//   halo exchange    the rows next to the CTA boundary are written straight from registers into the peer CTA's
+//                    halo buffer through distributed shared memory, then ONE cluster barrier;
+//   vertical pass    one thread per column marching from the image edge towards the CTA boundary with a sliding
+//                    register window (in place, reads run ahead of writes);
+//   re-imposition    plane[mask] = joined height map, mask kept as a bit plane (4.8 KB).
+// The epilogue computes normals, bins, the polynomial lookup and stores NHWC RGB. Nothing but the input frame and
+// the RGB frame touches HBM (algorithmic traffic: 307,200 B in + 921,600 B out per frame).
+#include "tx_common.cuh"
+#include "tx_kernels.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace tx {
+
+__constant__ float c_taps[TX_MAX_BLURS][2][TX_MAX_TAPS];
+
+cudaError_t upload_taps(const float* host_taps /*[TX_MAX_BLURS][2][TX_MAX_TAPS]*/, cudaStream_t s)
+{
+    return cudaMemcpyToSymbolAsync(c_taps, host_taps, sizeof(float) * TX_MAX_BLURS * 2 * TX_MAX_TAPS, 0,
+                                   cudaMemcpyHostToDevice, s);
+}
+
+// ---- shared memory carve-up ---------------------------------------------------------------------------------
+constexpr int HB0_ROWS = 30; // even levels (radius 30, 8, 2, 2)
+constexpr int HB1_ROWS = 16; // odd levels (radius 16, 4, 1) and the 1-row epilogue halo
+constexpr int SM_PLANE = 0;
+constexpr int SM_HB0 = SM_PLANE + HALF_H * IMG_W * 4;
+constexpr int SM_HB1 = SM_HB0 + HB0_ROWS * IMG_W * 4;
+constexpr int SM_MASK = SM_HB1 + HB1_ROWS * IMG_W * 4;
+constexpr int SM_MISC = SM_MASK + HALF_H * (IMG_W / 32) * 4;
+constexpr int SM_TOTAL = SM_MISC + 256;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+struct Misc {
+    uint64_t mbar;
+    float xch_min[2];
+    float red_f[NWARPS];
+    unsigned red_u[3][NWARPS];
+};
+static_assert(sizeof(Misc) <= 256, "misc");
+
+int taxim_smem_bytes() { return SM_TOTAL; }
+
+// ---- horizontal pass: warp per row, row in registers, shuffles ------------------------------------------------
+// Lane i owns virtual columns v = 12*i + j - 32 (j = 0..11); virtual columns outside [0, 320) hold the reflected
+// pixels (torch 'reflect'), so the correlation is uniform over the warp. PUSH: also store the result row into the
+// peer CTA's halo buffer (row index = distance from the CTA boundary).
+template <int L, int RAD>
+__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, int lane, unsigned q)
+{
+    constexpr int D = (RAD + 11) / 12;
+    const int v0 = 12 * lane - 32;
+#pragma unroll 1
+    for (int rr = 0; rr < HALF_H / NWARPS; ++rr) {
+        const int row = warp * (HALF_H / NWARPS) + rr;
+        float* rp = plane + row * IMG_W;
+        float x[12], acc[12];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int vb = v0 + 4 * e;
+            if (vb >= 0 && vb <= IMG_W - 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rp + vb);
+                x[4 * e + 0] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int v = vb + u;
+                    v = v < 0 ? -v : (v > IMG_W - 1 ? 2 * (IMG_W - 1) - v : v);
+                    x[4 * e + u] = rp[v];
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 12; ++m) acc[m] = 0.0f;
+#pragma unroll
+        for (int d = -D; d <= D; ++d) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                if (12 * d + j >= -RAD && 12 * d + j - 11 <= RAD) {
+                    const float y = (d == 0) ? x[j] : __shfl_sync(0xffffffffu, x[j], (lane + d) & 31);
+#pragma unroll
+                    for (int m = 0; m < 12; ++m) {
+                        const int k = 12 * d + j - m;
+                        if (k >= -RAD && k <= RAD) acc[m] = __fmaf_rn(c_taps[L][0][k + RAD], y, acc[m]);
+                    }
+                }
+            }
+        }
+        __syncwarp(); // every lane has consumed the old row before anyone overwrites it
+        // distance of this row from the CTA boundary (q = 0: boundary below row 119; q = 1: above row 0)
+        const int dist = q == 0 ? (HALF_H - 1 - row) : row;
+        const bool push = dist < RAD;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int vb = v0 + 4 * e;
+            if (vb >= 0 && vb <= IMG_W - 4) {
+                const float4 t = make_float4(acc[4 * e + 0], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+                *reinterpret_cast<float4*>(rp + vb) = t;
+                if (push) *reinterpret_cast<float4*>(hb_remote + dist * IMG_W + vb) = t;
+            }
+        }
+    }
+}
+
+// ---- vertical pass: thread per column, sliding register window, in place --------------------------------------
+// Position t = 0..119 counts rows from the IMAGE edge of this CTA's half (q = 0: t = local row, marching down;
+// q = 1 (REV): t = 119 - local row, marching up). Positions < 0 are the reflected rows, positions >= 120 come from
+// the halo buffer (rows of the peer CTA by distance from the boundary). Tap order is always ascending image row.
+template <int L, int RAD, int R, bool REV>
+__device__ __forceinline__ void vpass_dir(float* plane, const float* hb, int col)
+{
+    constexpr int WN = R + 2 * RAD;
+    constexpr int NB = HALF_H / R;
+    static_assert(HALF_H % R == 0 && R + RAD <= HALF_H, "block size");
+    float win[WN];
+    float* p0 = plane + (REV ? (HALF_H - 1) * IMG_W : 0) + col;
+    constexpr int S = REV ? -IMG_W : IMG_W;
+#pragma unroll
+    for (int i = 0; i < WN; ++i) {
+        int t = i - RAD;
+        t = t < 0 ? -t : t;
+        win[i] = p0[t * S];
+    }
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) {
+        float acc[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) acc[m] = 0.0f;
+        if (!REV) {
+#pragma unroll
+            for (int k = 0; k <= 2 * RAD; ++k) {
+#pragma unroll
+                for (int m = 0; m < R; ++m) acc[m] = __fmaf_rn(c_taps[L][1][k], win[m + k], acc[m]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 2 * RAD; k >= 0; --k) {
+#pragma unroll
+                for (int m = 0; m < R; ++m) acc[m] = __fmaf_rn(c_taps[L][1][2 * RAD - k], win[m + k], acc[m]);
+            }
+        }
+        float* po = p0 + (b * R) * S;
+#pragma unroll
+        for (int m = 0; m < R; ++m) po[m * S] = acc[m];
+        if (b + 1 < NB) {
+#pragma unroll
+            for (int i = 0; i < 2 * RAD; ++i) win[i] = win[i + R];
+            const int tb = (b + 1) * R - RAD;
+#pragma unroll
+            for (int i = 2 * RAD; i < WN; ++i) {
+                const int t = tb + i;
+                // t >= 120 -> halo row (t - 120); only rows < RAD are ever used by outputs < 120
+                const float* src = (t < HALF_H) ? (p0 + t * S) : (hb + min(t - HALF_H, RAD - 1) * IMG_W + col);
+                win[i] = *src;
+            }
+        }
+    }
+}
+
+template <int L, int RAD, int R>
+__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q)
+{
+    if (tid < IMG_W) {
+        if (q == 0)
+            vpass_dir<L, RAD, R, false>(plane, hb, tid);
+        else
+            vpass_dir<L, RAD, R, true>(plane, hb, tid);
+    }
+}
+
+// ---- masked re-imposition: plane[mask] = min(h, gel) recomputed from the input frame (L2 hit) ------------------
+__device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits, const float* __restrict__ hm_half,
+                                         const float* __restrict__ gel_half, float m, float press, int warp, int lane)
+{
+    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
+        const unsigned bits = maskbits[w];
+        if (bits == 0u) continue;
+        if ((bits >> lane) & 1u) {
+            const int idx = w * 32 + lane; // row * 320 + seg * 32 + lane
+            const float h = __fadd_rn(__fadd_rn(__ldg(hm_half + idx), -m), -press);
+            const float g = gel_half ? __ldg(gel_half + idx) : 0.0f;
+            plane[idx] = fminf(h, g);
+        }
+    }
+}
+
+template <int L, int RAD, int R, bool FINAL>
+__device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
+                                           const float* hm_half, const float* gel_half, float m, float press, int tid,
+                                           int warp, int lane, unsigned q, cg::cluster_group& cluster)
+{
+    hpass<L, RAD>(plane, hb_remote, warp, lane, q);
+    cluster.sync(); // rows + pushed halo rows visible in both CTAs
+    vpass<L, RAD, R>(plane, hb_local, tid, q);
+    __syncthreads();
+    if (!FINAL) {
+        reimpose(plane, maskbits, hm_half, gel_half, m, press, warp, lane);
+        __syncthreads();
+    }
+}
+
+// ---- the fused kernel -------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_fused_kernel(const TaximArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* plane = reinterpret_cast<float*>(smem + SM_PLANE);
+    float* hb0 = reinterpret_cast<float*>(smem + SM_HB0);
+    float* hb1 = reinterpret_cast<float*>(smem + SM_HB1);
+    unsigned* maskbits = reinterpret_cast<unsigned*>(smem + SM_MASK);
+    Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned q = cluster.block_rank(); // 0 = rows 0..119, 1 = rows 120..239
+    const int n = blockIdx.x >> 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t half_off = (size_t)n * IMG_H * IMG_W + (size_t)q * HALF_H * IMG_W;
+    const float* hm_half = p.hm + half_off;
+    const float* gel_half = p.gel ? p.gel + (size_t)q * HALF_H * IMG_W : nullptr;
+    float* hb0_remote = cluster.map_shared_rank(hb0, q ^ 1u);
+    float* hb1_remote = cluster.map_shared_rank(hb1, q ^ 1u);
+    Misc* misc_remote = cluster.map_shared_rank(misc, q ^ 1u);
+
+    // ---- stage the half frame with bulk-async copies (TMA) ----------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&misc->mbar, 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        constexpr uint32_t CH = HALF_H * IMG_W * 4 / 4; // 4 chunks of 38,400 B
+        mbar_expect_tx(&misc->mbar, HALF_H * IMG_W * 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            bulk_g2s(reinterpret_cast<unsigned char*>(plane) + c * CH,
+                     reinterpret_cast<const unsigned char*>(hm_half) + c * CH, CH, &misc->mbar);
+    }
+    mbar_wait(&misc->mbar, 0);
+
+    // ---- frame minimum (ref: taxim_torch.py:441, taxim_sim.py:116-117) ----------------------------------------
+    float mloc = __int_as_float(0x7f800000);
+    {
+        const float4* p4 = reinterpret_cast<const float4*>(plane);
+        for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) {
+            const float4 t = p4[i];
+            mloc = fminf(fminf(mloc, fminf(t.x, t.y)), fminf(t.z, t.w));
+        }
+    }
+    mloc = warp_min(mloc);
+    if (lane == 0) misc->red_f[warp] = mloc;
+    __syncthreads();
+    if (tid == 0) {
+        float v = misc->red_f[0];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) v = fminf(v, misc->red_f[w]);
+        misc->xch_min[q] = v;
+        misc_remote->xch_min[q] = v;
+    }
+    cluster.sync();
+    const float m = fminf(misc->xch_min[0], misc->xch_min[1]);
+
+    // ---- indentation depth (explicit, or fused: ref taxim_sim.py:115-131) --------------------------------------
+    float press;
+    if (p.press_in) {
+        press = __ldg(p.press_in + n);
+    } else {
+        float d = __fdiv_rn(m, 1000.0f);
+        d = __fadd_rn(d, -p.gelpad_min);
+        d = d < 0.0f ? 0.0f : d;
+        press = (d <= p.gelpad_h) ? __fmul_rn(__fadd_rn(p.gelpad_h, -d), 1000.0f) : 0.0f;
+    }
+    if (p.depth_out && q == 0 && tid == 0) p.depth_out[n] = press;
+
+    // ---- shifted height map, contact mask, joined map (ref: taxim_torch.py:441-461) -----------------------------
+    // min over the frame of ((hm - m) - press) is exactly -press, so pressing_depth_mm == press.
+    const float thr = __fmul_rn(-press, p.contact_scale);
+    unsigned cnt = 0, srow = 0, scol = 0;
+    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
+        const int idx = w * 32 + lane;
+        const float h = __fadd_rn(__fadd_rn(plane[idx], -m), -press);
+        const float g = gel_half ? __ldg(gel_half + idx) : 0.0f;
+        const bool contact = h < 0.0f;
+        const float j = fminf(h, g);
+        const bool mk = (__fadd_rn(j, -g) < thr) && contact;
+        plane[idx] = j;
+        const unsigned bits = __ballot_sync(0xffffffffu, mk);
+        if (lane == 0) maskbits[w] = bits;
+        if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
+        if (mk) {
+            cnt += 1u;
+            srow += (unsigned)(q * HALF_H + idx / IMG_W);
+            scol += (unsigned)(idx % IMG_W);
+        }
+    }
+    if (p.aux_sums) {
+        cnt = warp_sum_u32(cnt);
+        srow = warp_sum_u32(srow);
+        scol = warp_sum_u32(scol);
+        if (lane == 0) {
+            misc->red_u[0][warp] = cnt;
+            misc->red_u[1][warp] = srow;
+            misc->red_u[2][warp] = scol;
+        }
+    }
+    __syncthreads();
+    if (p.aux_sums && tid < 3) {
+        unsigned s = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) s += misc->red_u[tid][w];
+        p.aux_sums[((size_t)n * 2 + q) * 4 + tid] = s;
+    }
+
+    // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
+    // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
+    const bool active = (p.gel != nullptr) || (press > 0.0f);
+    if (active) {
+        blur_level<0, 30, 20, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<1, 16, 30, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<2, 8, 40, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<3, 4, 40, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<4, 2, 40, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<5, 1, 40, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<6, 2, 40, true>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+    }
+
+    // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
+    {
+        const int brow = q == 0 ? HALF_H - 1 : 0;
+        for (int x = tid; x < IMG_W; x += NTHREADS) hb1_remote[x] = plane[brow * IMG_W + x];
+    }
+    if (p.deformed_out) {
+        const float4* s4 = reinterpret_cast<const float4*>(plane);
+        float4* d4 = reinterpret_cast<float4*>(p.deformed_out + half_off);
+        for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) d4[i] = s4[i];
+    }
+    if (p.aux_bmax) {
+        float bm = -__int_as_float(0x7f800000);
+        for (int i = tid; i < HALF_H * IMG_W; i += NTHREADS) bm = fmaxf(bm, plane[i]);
+        bm = warp_max(bm);
+        if (lane == 0) misc->red_f[warp] = bm;
+        __syncthreads();
+        if (tid == 0) {
+            float v = misc->red_f[0];
+#pragma unroll
+            for (int w = 1; w < NWARPS; ++w) v = fmaxf(v, misc->red_f[w]);
+            p.aux_bmax[(size_t)n * 2 + q] = v;
+        }
+        for (int k = tid; k < p.M; k += NTHREADS) {
+            const int my = p.mk_y[k], mx = p.mk_x[k];
+            const int ly = my - (int)q * HALF_H;
+            if (ly >= 0 && ly < HALF_H && mx >= 0 && mx < IMG_W) {
+                p.aux_b[(size_t)n * p.M + k] = plane[ly * IMG_W + mx];
+                p.aux_m[(size_t)n * p.M + k] = (unsigned char)((maskbits[ly * (IMG_W / 32) + (mx >> 5)] >> (mx & 31)) & 1u);
+            }
+        }
+    }
+    cluster.sync();
+
+    // ---- normals -> bins -> polynomial -> + background -> clip -> NHWC (ref: taxim_torch.py:475-503, 243-258) ---
+    const float PI_F = 3.14159265358979323846f;
+    const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
+    float* rgb_half = p.rgb + half_off * 3;
+    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
+        const int row = w / (IMG_W / 32);
+        const int x = (w % (IMG_W / 32)) * 32 + lane;
+        const int gy_ = (int)q * HALF_H + row; // image row
+        // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
+        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
+        const int xx = min(max(x, 1), IMG_W - 2);
+        const float* up = (yy - 1 >= 0) ? plane + (yy - 1) * IMG_W : hb1;
+        const float* dn = (yy + 1 < HALF_H) ? plane + (yy + 1) * IMG_W : hb1;
+        const float top = __fmul_rn(up[xx], p.inv_pixmm), bot = __fmul_rn(dn[xx], p.inv_pixmm);
+        const float lef = __fmul_rn(plane[yy * IMG_W + xx - 1], p.inv_pixmm);
+        const float rig = __fmul_rn(plane[yy * IMG_W + xx + 1], p.inv_pixmm);
+        const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
+        const float gy = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
+        int im = 0, id;
+        {
+            const float tt = __fsqrt_rn(__fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+            float dir = 0.0f;
+            if (tt != 0.0f) {
+                const float mag = atanf_c(tt);
+                dir = atan2f_c(gx, gy);
+                im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
+            }
+            id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
+        }
+        im = min(max(im, 0), p.nb - 1);
+        id = min(max(id, 0), p.nb - 1);
+        const float4* pp = p.poly + ((size_t)im * p.nb + id) * 5; // [nb][nb][3][6] padded to 20 floats
+        const float xf = __fmul_rn((float)x, p.fx), yf = __fmul_rn((float)gy_, p.fy);
+        const float f0 = __fmul_rn(xf, xf), f1 = __fmul_rn(yf, yf), f2 = __fmul_rn(xf, yf);
+        float c[20];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            const float4 t = __ldg(pp + e);
+            c[4 * e] = t.x; c[4 * e + 1] = t.y; c[4 * e + 2] = t.z; c[4 * e + 3] = t.w;
+        }
+        const size_t pix = (size_t)row * IMG_W + x;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* pc = c + 6 * ch;
+            float s = pc[5];
+            s = __fmaf_rn(pc[4], yf, s);
+            s = __fmaf_rn(pc[3], xf, s);
+            s = __fmaf_rn(pc[2], f2, s);
+            s = __fmaf_rn(pc[1], f1, s);
+            s = __fmaf_rn(pc[0], f0, s);
+            s = __fadd_rn(s, __ldg(bg_half + pix * 3 + ch));
+            s = fminf(fmaxf(s, 0.0f), 1.0f);
+            rgb_half[pix * 3 + ch] = s;
+        }
+    }
+}
+
+cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    taxim_fused_kernel<<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- stand-alone indentation depth (ref: taxim_sim.py:115-131): one CTA per frame, HBM-bound -------------------
+__global__ void __launch_bounds__(256) indentation_depth_kernel(const float* __restrict__ hm, float* __restrict__ out,
+                                                                float gelpad_h, float gelpad_min)
+{
+    __shared__ float red[8];
+    const float4* p4 = reinterpret_cast<const float4*>(hm + (size_t)blockIdx.x * IMG_H * IMG_W);
+    float m = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < IMG_H * IMG_W / 4; i += 256) {
+        const float4 t = __ldg(p4 + i);
+        m = fminf(fminf(m, fminf(t.x, t.y)), fminf(t.z, t.w));
+    }
+    m = warp_min(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v = fminf(v, red[w]);
+        float d = __fdiv_rn(v, 1000.0f);
+        d = __fadd_rn(d, -gelpad_min);
+        d = d < 0.0f ? 0.0f : d;
+        out[blockIdx.x] = (d <= gelpad_h) ? __fmul_rn(__fadd_rn(gelpad_h, -d), 1000.0f) : 0.0f;
+    }
+}
+
+cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s)
+{
+    indentation_depth_kernel<<<N, 256, 0, s>>>(hm, out, gelpad_h, gelpad_min);
+    return cudaGetLastError();
+}
+
+} // namespace tx

@@ -1,0 +1,353 @@
+// tx_api.cu -- the C ABI of libtacex_b200.so (see include/tacex_b200.h for the contract and reference citations).
+#include "tx_kernels.h"
+#include <math.h>
+#include <new>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace tx;
+
+struct tx_handle {
+    tx_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    tx_counters ctr{};
+    bool have_tables = false;
+    // device tables
+    float4* d_poly = nullptr; // [nb][nb][20]
+    float* d_bg = nullptr;    // [H][W][3]
+    float* d_gel = nullptr;   // [H][W] or nullptr
+    // marker grid
+    int M = 0;
+    std::vector<int32_t> mx, my;
+    int* d_mx = nullptr;
+    int* d_my = nullptr;
+    // FOTS inputs recorded by tx_render
+    unsigned* d_aux_sums = nullptr;
+    float* d_aux_bmax = nullptr;
+    float* d_aux_b = nullptr;
+    unsigned char* d_aux_m = nullptr;
+    int aux_valid_n = 0;
+    // tx_step_host staging
+    float* d_hm = nullptr;
+    float* d_rgb = nullptr;
+    float* d_depth = nullptr;
+    float* d_theta = nullptr;
+    float* d_traj0 = nullptr;
+    int* d_traj_len = nullptr;
+    float* d_markers = nullptr;
+    int host_cap = 0;
+};
+
+static std::string g_create_err;
+
+static int fail(tx_handle* h, int code, const std::string& msg)
+{
+    if (h)
+        h->err = msg;
+    else
+        g_create_err = msg;
+    return code;
+}
+#define TX_CUDA(h, expr)                                                                                              \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+            return fail((h), TX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+extern "C" int tx_abi_version(void) { return TX_ABI_VERSION; }
+
+// np.linspace(x0, W - x0, cols, dtype=int) (ref: marker_motion.py:58-60): float64 linspace, truncation toward zero
+static void marker_axis(double lo, double hi, int n, std::vector<int32_t>& out)
+{
+    out.resize(n);
+    const double step = n > 1 ? (hi - lo) / (double)(n - 1) : 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double v = (i == n - 1 && n > 1) ? hi : lo + step * i;
+        out[i] = (int32_t)v;
+    }
+}
+
+extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx_handle** out)
+{
+    if (!cfg || !out) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != TX_ABI_VERSION) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: ABI version mismatch");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, TX_ERR_NO_DEVICE, "tx_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: bad device index");
+    if (cfg->H != IMG_H || cfg->W != IMG_W)
+        return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: this build is specialised for 240 x 320 frames");
+    static const int want[7] = {61, 33, 17, 9, 5, 3, 5};
+    if (cfg->n_blurs != 7) return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: expected 6 pyramid levels + final blur");
+    for (int l = 0; l < 7; ++l)
+        if (cfg->ksx[l] != want[l] || cfg->ksy[l] != want[l])
+            return fail(nullptr, TX_ERR_UNSUPPORTED,
+                        "tx_create: kernel sizes must be 61,33,17,9,5,3,5 (GelSight Mini at 320x240)");
+    if (cfg->max_envs <= 0) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: max_envs must be positive");
+    const int M = cfg->marker_rows * cfg->marker_cols;
+    if (M < 0 || M > TX_MAX_MARKERS) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: too many markers");
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        return fail(nullptr, TX_ERR_NO_DEVICE, "tx_create: an sm_100a (Blackwell) device is required");
+
+    tx_handle* h = new (std::nothrow) tx_handle();
+    if (!h) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: out of host memory");
+    h->cfg = *cfg;
+    h->device = device;
+    h->stream = (cudaStream_t)cuda_stream;
+    h->M = M;
+#define TX_CUDA_C(expr)                                                                                               \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess) {                                                                                      \
+            fail(nullptr, TX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+            tx_destroy(h);                                                                                            \
+            return TX_ERR_CUDA;                                                                                       \
+        }                                                                                                             \
+    } while (0)
+    TX_CUDA_C(cudaSetDevice(device));
+    // taps -> __constant__ memory, [blur][0 = x, 1 = y][tap]
+    {
+        std::vector<float> t((size_t)TX_MAX_BLURS * 2 * TX_MAX_TAPS, 0.0f);
+        for (int l = 0; l < cfg->n_blurs; ++l)
+            for (int k = 0; k < TX_MAX_TAPS; ++k) {
+                t[((size_t)l * 2 + 0) * TX_MAX_TAPS + k] = k < cfg->ksx[l] ? cfg->taps_x[l][k] : 0.0f;
+                t[((size_t)l * 2 + 1) * TX_MAX_TAPS + k] = k < cfg->ksy[l] ? cfg->taps_y[l][k] : 0.0f;
+            }
+        TX_CUDA_C(upload_taps(t.data(), h->stream));
+        TX_CUDA_C(cudaStreamSynchronize(h->stream));
+    }
+    if (M > 0) {
+        std::vector<int32_t> ax, ay;
+        marker_axis(cfg->marker_x0, (double)cfg->W - cfg->marker_x0, cfg->marker_cols, ax);
+        marker_axis(cfg->marker_y0, (double)cfg->H - cfg->marker_y0, cfg->marker_rows, ay);
+        h->mx.resize(M);
+        h->my.resize(M);
+        for (int r = 0; r < cfg->marker_rows; ++r)
+            for (int c = 0; c < cfg->marker_cols; ++c) {
+                h->mx[r * cfg->marker_cols + c] = ax[c];
+                h->my[r * cfg->marker_cols + c] = ay[r];
+            }
+        TX_CUDA_C(cudaMalloc(&h->d_mx, sizeof(int) * M));
+        TX_CUDA_C(cudaMalloc(&h->d_my, sizeof(int) * M));
+        TX_CUDA_C(cudaMemcpy(h->d_mx, h->mx.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+        TX_CUDA_C(cudaMemcpy(h->d_my, h->my.data(), sizeof(int) * M, cudaMemcpyHostToDevice));
+        const size_t N = (size_t)cfg->max_envs;
+        TX_CUDA_C(cudaMalloc(&h->d_aux_sums, sizeof(unsigned) * 8 * N));
+        TX_CUDA_C(cudaMalloc(&h->d_aux_bmax, sizeof(float) * 2 * N));
+        TX_CUDA_C(cudaMalloc(&h->d_aux_b, sizeof(float) * M * N));
+        TX_CUDA_C(cudaMalloc(&h->d_aux_m, M * N));
+        TX_CUDA_C(cudaMemset(h->d_aux_m, 0, M * N));
+        TX_CUDA_C(cudaMemset(h->d_aux_b, 0, sizeof(float) * M * N));
+    }
+#undef TX_CUDA_C
+    *out = h;
+    return TX_OK;
+}
+
+extern "C" void tx_destroy(tx_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_mx); cudaFree(h->d_my);
+    cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
+    cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
+    cudaFree(h->d_traj_len); cudaFree(h->d_markers);
+    delete h;
+}
+
+extern "C" const char* tx_last_error(const tx_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int tx_get_counters(const tx_handle* h, tx_counters* out)
+{
+    if (!h || !out) return TX_ERR_INVALID_ARG;
+    *out = h->ctr;
+    return TX_OK;
+}
+
+extern "C" int tx_upload_tables(tx_handle* h, const float* poly_grad, const float* background, const float* gel_map)
+{
+    if (!h || !poly_grad || !background) return fail(h, TX_ERR_INVALID_ARG, "tx_upload_tables: null argument");
+    TX_CUDA(h, cudaSetDevice(h->device));
+    const int nb = h->cfg.num_bins, H = h->cfg.H, W = h->cfg.W;
+    // poly [3][nb][nb][6] -> [nb][nb][3*6 padded to 20]: one 80-byte record per bin
+    std::vector<float> poly((size_t)nb * nb * 20, 0.0f);
+    for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < nb; ++a)
+            for (int b = 0; b < nb; ++b)
+                for (int k = 0; k < 6; ++k)
+                    poly[((size_t)a * nb + b) * 20 + c * 6 + k] = poly_grad[(((size_t)c * nb + a) * nb + b) * 6 + k];
+    // background [3][H][W] -> [H][W][3] (the output layout)
+    std::vector<float> bg((size_t)H * W * 3);
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < H * W; ++i) bg[(size_t)i * 3 + c] = background[(size_t)c * H * W + i];
+    if (!h->d_poly) TX_CUDA(h, cudaMalloc(&h->d_poly, poly.size() * sizeof(float)));
+    if (!h->d_bg) TX_CUDA(h, cudaMalloc(&h->d_bg, bg.size() * sizeof(float)));
+    TX_CUDA(h, cudaMemcpy(h->d_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_bg, bg.data(), bg.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (gel_map) {
+        if (!h->d_gel) TX_CUDA(h, cudaMalloc(&h->d_gel, sizeof(float) * H * W));
+        TX_CUDA(h, cudaMemcpy(h->d_gel, gel_map, sizeof(float) * H * W, cudaMemcpyHostToDevice));
+    } else if (h->d_gel) {
+        cudaFree(h->d_gel);
+        h->d_gel = nullptr;
+    }
+    h->have_tables = true;
+    return TX_OK;
+}
+
+extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N, float* depth_mm)
+{
+    if (!h || !height_mm || !depth_mm || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_indentation_depth: bad argument");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    TX_CUDA(h, launch_indentation_depth(height_mm, depth_mm, N, h->cfg.gelpad_height_m, h->cfg.gelpad_to_cam_min_m,
+                                        h->stream));
+    h->ctr.depth_calls++;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb,
+                         float* depth_out, float* deformed, uint8_t* mask)
+{
+    if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render: bad argument");
+    if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
+    if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
+    if (((uintptr_t)height_mm & 15u) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u)))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_render: device buffers must be 16-byte aligned");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    TaximArgs a{};
+    a.hm = height_mm;
+    a.press_in = press_mm;
+    a.gel = h->d_gel;
+    a.poly = h->d_poly;
+    a.bg_hwc = h->d_bg;
+    a.rgb = rgb;
+    a.depth_out = depth_out;
+    a.deformed_out = deformed;
+    a.mask_out = mask;
+    if (h->M > 0) {
+        a.aux_sums = h->d_aux_sums;
+        a.aux_bmax = h->d_aux_bmax;
+        a.aux_b = h->d_aux_b;
+        a.aux_m = h->d_aux_m;
+        a.mk_x = h->d_mx;
+        a.mk_y = h->d_my;
+        a.M = h->M;
+    }
+    const tx_config& c = h->cfg;
+    a.inv_pixmm = 1.0f / c.pixmm;
+    a.sy = (float)c.H / c.calib_h;
+    a.sx = (float)c.W / c.calib_w;
+    a.fx = c.calib_w / (float)c.W;
+    a.fy = c.calib_h / (float)c.H;
+    a.contact_scale = c.contact_scale;
+    a.gelpad_h = c.gelpad_height_m;
+    a.gelpad_min = c.gelpad_to_cam_min_m;
+    a.inv_xbin = (float)(1.0 / (0.5 * M_PI / (c.num_bins - 1)));
+    a.inv_ybin = (float)(1.0 / (2.0 * M_PI / (c.num_bins - 1)));
+    a.nb = c.num_bins;
+    TX_CUDA(h, launch_taxim(a, N, h->stream));
+    h->aux_valid_n = h->M > 0 ? N : 0;
+    h->ctr.render_calls++;
+    h->ctr.frames_rendered += (uint64_t)N;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_fots_markers(tx_handle* h, const float* press_mm, const float* theta, int N, float* traj0,
+                               int32_t* traj_len, float* markers)
+{
+    if (!h || !press_mm || !theta || !traj0 || !traj_len || !markers || N < 0)
+        return fail(h, TX_ERR_INVALID_ARG, "tx_fots_markers: bad argument");
+    if (h->M <= 0) return fail(h, TX_ERR_STATE, "tx_fots_markers: handle has no marker grid");
+    if (N != h->aux_valid_n) return fail(h, TX_ERR_STATE, "tx_fots_markers: call tx_render on the same batch first");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    FotsArgs f{};
+    f.aux_sums = h->d_aux_sums;
+    f.aux_bmax = h->d_aux_bmax;
+    f.aux_b = h->d_aux_b;
+    f.aux_m = h->d_aux_m;
+    f.mk_x = h->d_mx;
+    f.mk_y = h->d_my;
+    f.press = press_mm;
+    f.theta = theta;
+    f.traj0 = traj0;
+    f.traj_len = traj_len;
+    f.markers = markers;
+    f.M = h->M;
+    f.rows = h->cfg.marker_rows;
+    f.cols = h->cfg.marker_cols;
+    f.lamb0 = h->cfg.fots_lambda[0];
+    f.lamb1 = h->cfg.fots_lambda[1];
+    f.lamb2 = h->cfg.fots_lambda[2];
+    f.mm2pix = h->cfg.mm2pix;
+    f.shear_max = h->cfg.shear_max_px;
+    f.theta_max = h->cfg.theta_max_rad;
+    TX_CUDA(h, launch_fots(f, N, h->stream));
+    h->ctr.fots_calls++;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my)
+{
+    if (!h || !mx || !my) return TX_ERR_INVALID_ARG;
+    memcpy(mx, h->mx.data(), sizeof(int32_t) * h->M);
+    memcpy(my, h->my.data(), sizeof(int32_t) * h->M);
+    return TX_OK;
+}
+
+extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const float* theta_host, int N, float* rgb_host,
+                            float* depth_host, float* markers_host)
+{
+    if (!h || !height_mm_host || !rgb_host || N <= 0) return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: bad argument");
+    if (markers_host && (!theta_host || h->M <= 0))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: markers need theta and a marker grid");
+    if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: N exceeds max_envs");
+    TX_CUDA(h, cudaSetDevice(h->device));
+    const size_t HW = (size_t)IMG_H * IMG_W;
+    if (h->host_cap < N) {
+        cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
+        cudaFree(h->d_traj_len); cudaFree(h->d_markers);
+        h->d_hm = h->d_rgb = h->d_depth = h->d_theta = h->d_traj0 = h->d_markers = nullptr;
+        h->d_traj_len = nullptr;
+        h->host_cap = 0;
+        const size_t cap = (size_t)h->cfg.max_envs;
+        TX_CUDA(h, cudaMalloc(&h->d_hm, sizeof(float) * HW * cap));
+        TX_CUDA(h, cudaMalloc(&h->d_rgb, sizeof(float) * HW * 3 * cap));
+        TX_CUDA(h, cudaMalloc(&h->d_depth, sizeof(float) * cap));
+        TX_CUDA(h, cudaMalloc(&h->d_theta, sizeof(float) * cap));
+        TX_CUDA(h, cudaMalloc(&h->d_traj0, sizeof(float) * 4 * cap));
+        TX_CUDA(h, cudaMalloc(&h->d_traj_len, sizeof(int) * cap));
+        TX_CUDA(h, cudaMemset(h->d_traj0, 0, sizeof(float) * 4 * cap));
+        TX_CUDA(h, cudaMemset(h->d_traj_len, 0, sizeof(int) * cap));
+        if (h->M > 0) TX_CUDA(h, cudaMalloc(&h->d_markers, sizeof(float) * 4 * h->M * cap));
+        h->host_cap = (int)cap;
+    }
+    TX_CUDA(h, cudaMemcpyAsync(h->d_hm, height_mm_host, sizeof(float) * HW * N, cudaMemcpyHostToDevice, h->stream));
+    int rc = tx_render(h, h->d_hm, nullptr, N, h->d_rgb, h->d_depth, nullptr, nullptr);
+    if (rc != TX_OK) return rc;
+    if (markers_host) {
+        TX_CUDA(h, cudaMemcpyAsync(h->d_theta, theta_host, sizeof(float) * N, cudaMemcpyHostToDevice, h->stream));
+        rc = tx_fots_markers(h, h->d_depth, h->d_theta, N, h->d_traj0, h->d_traj_len, h->d_markers);
+        if (rc != TX_OK) return rc;
+        TX_CUDA(h, cudaMemcpyAsync(markers_host, h->d_markers, sizeof(float) * 4 * h->M * N, cudaMemcpyDeviceToHost,
+                                   h->stream));
+    }
+    TX_CUDA(h, cudaMemcpyAsync(rgb_host, h->d_rgb, sizeof(float) * HW * 3 * N, cudaMemcpyDeviceToHost, h->stream));
+    if (depth_host)
+        TX_CUDA(h, cudaMemcpyAsync(depth_host, h->d_depth, sizeof(float) * N, cudaMemcpyDeviceToHost, h->stream));
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return TX_OK;
+}

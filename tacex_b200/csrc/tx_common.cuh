@@ -1,0 +1,117 @@
+// tx_common.cuh -- shared device helpers for the sm_100a kernels of libtacex_b200.
+//
+// Canonical float32 elementary functions: every operation is one IEEE-754 binary32 op in a fixed order
+// (compile with -fmad=false so nvcc never contracts a*b+c on its own); the CPU checker under oracle/
+// restates the same sequences, which is what makes bin indices bit-comparable between CPU and GPU.
+#pragma once
+#include "tx_kernels.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tx {
+
+// ---- canonical atan / atan2 (Cephes-style polynomial) ------------------------------
+__device__ __forceinline__ float atanf_c(float xx)
+{
+    float x = fabsf(xx);
+    float y;
+    if (x > 2.414213562373095f) {
+        y = 1.5707963267948966f;
+        x = -__fdiv_rn(1.0f, x);
+    } else if (x > 0.4142135623730950f) {
+        y = 0.7853981633974483f;
+        x = __fdiv_rn(__fadd_rn(x, -1.0f), __fadd_rn(x, 1.0f));
+    } else {
+        y = 0.0f;
+    }
+    float z = __fmul_rn(x, x);
+    float p = 8.05374449538e-2f;
+    p = __fmaf_rn(p, z, -1.38776856032e-1f);
+    p = __fmaf_rn(p, z, 1.99777106478e-1f);
+    p = __fmaf_rn(p, z, -3.33329491539e-1f);
+    p = __fmul_rn(p, z);
+    p = __fmaf_rn(p, x, x);
+    y = __fadd_rn(y, p);
+    return (xx < 0.0f) ? -y : y;
+}
+
+__device__ __forceinline__ float atan2f_c(float y, float x)
+{
+    const float PI_F = 3.14159265358979323846f;
+    const float PIO2_F = 1.5707963267948966f;
+    if (x == 0.0f) {
+        if (y > 0.0f) return PIO2_F;
+        if (y < 0.0f) return -PIO2_F;
+        return 0.0f;
+    }
+    float z = atanf_c(__fdiv_rn(y, x));
+    if (x < 0.0f) {
+        if (y < 0.0f) return __fadd_rn(z, -PI_F);
+        return __fadd_rn(z, PI_F);
+    }
+    return z;
+}
+
+// ---- mbarrier + bulk async copy (TMA, 1-D) -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on an mbarrier; size multiple of 16 B
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- warp reductions ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_min(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+} // namespace tx

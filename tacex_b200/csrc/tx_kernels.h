@@ -1,0 +1,59 @@
+// tx_kernels.h -- internal launch interface between the C-ABI layer (tx_api.cu) and the kernels.
+#pragma once
+#include "../../include/tacex_b200.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tx {
+
+constexpr int IMG_H = 240;
+constexpr int IMG_W = 320;
+constexpr int HALF_H = 120;   // rows owned by one CTA of the 2-CTA cluster
+constexpr int NTHREADS = 384; // 12 warps
+constexpr int NWARPS = NTHREADS / 32;
+
+struct TaximArgs {
+    const float* hm;       // [N][240][320] mm
+    const float* press_in; // [N] or nullptr (fused indentation depth)
+    const float* gel;      // [240][320] or nullptr (flat)
+    const float4* poly;    // [nb][nb][20] (3 channels x 6 coefficients, padded)
+    const float* bg_hwc;   // [240][320][3]
+    float* rgb;            // [N][240][320][3]
+    float* depth_out;      // [N] or nullptr
+    float* deformed_out;   // [N][240][320] or nullptr
+    unsigned char* mask_out; // [N][240][320] or nullptr
+    // FOTS inputs recorded per env (all nullptr when no marker grid is configured)
+    unsigned* aux_sums; // [N][2][4]  (count, sum_row, sum_col, -) per CTA half
+    float* aux_bmax;    // [N][2]
+    float* aux_b;       // [N][M]
+    unsigned char* aux_m; // [N][M]
+    const int* mk_x;
+    const int* mk_y;
+    int M;
+    float inv_pixmm, sy, sx, fx, fy, contact_scale, gelpad_h, gelpad_min, inv_xbin, inv_ybin;
+    int nb;
+};
+
+struct FotsArgs {
+    const unsigned* aux_sums;
+    const float* aux_bmax;
+    const float* aux_b;
+    const unsigned char* aux_m;
+    const int* mk_x;
+    const int* mk_y;
+    const float* press;
+    const float* theta;
+    float* traj0;     // [N][4]
+    int* traj_len;    // [N]
+    float* markers;   // [N][2][M][2]
+    int M, rows, cols;
+    double lamb0, lamb1, lamb2, mm2pix, shear_max, theta_max;
+};
+
+cudaError_t upload_taps(const float* host_taps, cudaStream_t s);
+int taxim_smem_bytes();
+cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
+cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);
+cudaError_t launch_fots(const FotsArgs& a, int N, cudaStream_t s);
+
+} // namespace tx

@@ -1,0 +1,158 @@
+"""TactileEngine -- thin PyTorch-facing owner of one ``tx_handle`` (device memory + stream plumbing only).
+
+All arithmetic of the hot path happens inside libtacex_b200.so (hand-written sm_100a kernels); torch supplies the
+device tensors and the CUDA stream. There is no fallback: without the library or without a CUDA device the
+constructor raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from .calib import TaximTables
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class TactileEngine:
+    def __init__(
+        self,
+        tables: TaximTables,
+        max_envs: int,
+        device: str | torch.device = "cuda",
+        marker_rows: int = 0,
+        marker_cols: int = 0,
+        marker_x0: float = 15.0,
+        marker_y0: float = 26.0,
+        fots_lambda: tuple[float, float, float] = (0.00125, 0.00021, 0.00038),
+        mm2pix: float = 19.58,
+        gelpad_height_m: float = 0.0045,
+        gelpad_to_cam_min_m: float = 0.024,
+        use_current_stream: bool = True,
+    ):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.TxError("TactileEngine needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.TxError(f"TactileEngine needs a CUDA device, got {self.device}")
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.dev_index)
+        self.tables = tables
+        H, W = tables.shape
+        self.H, self.W, self.max_envs = H, W, int(max_envs)
+        self.M = marker_rows * marker_cols
+        p = tables.params
+
+        cfg = _lib.TxConfig()
+        cfg.abi_version = _lib.TX_ABI_VERSION
+        cfg.H, cfg.W, cfg.max_envs, cfg.num_bins = H, W, self.max_envs, p.num_bins
+        cfg.pixmm, cfg.calib_h, cfg.calib_w, cfg.contact_scale = p.pixmm, p.calib_h, p.calib_w, p.contact_scale
+        cfg.gelpad_height_m, cfg.gelpad_to_cam_min_m = gelpad_height_m, gelpad_to_cam_min_m
+        taps = p.blur_taps((H, W))
+        if len(taps) > _lib.TX_MAX_BLURS:
+            raise _lib.TxError("too many blur levels")
+        cfg.n_blurs = len(taps)
+        for l, (kx, ky) in enumerate(taps):
+            if kx.numel() > _lib.TX_MAX_TAPS or ky.numel() > _lib.TX_MAX_TAPS:
+                raise _lib.TxError("blur kernel too large")
+            cfg.ksx[l], cfg.ksy[l] = kx.numel(), ky.numel()
+            for k, v in enumerate(kx.tolist()):
+                cfg.taps_x[l][k] = v
+            for k, v in enumerate(ky.tolist()):
+                cfg.taps_y[l][k] = v
+        cfg.marker_rows, cfg.marker_cols = marker_rows, marker_cols
+        cfg.marker_x0, cfg.marker_y0 = marker_x0, marker_y0
+        cfg.fots_lambda[:] = fots_lambda
+        cfg.mm2pix, cfg.shear_max_px, cfg.theta_max_rad = mm2pix, 10.0, 60.0 / 180.0 * math.pi
+        self.cfg = cfg
+
+        with torch.cuda.device(self.dev_index):
+            self.stream = torch.cuda.current_stream() if use_current_stream else torch.cuda.Stream()
+            h = C.c_void_p()
+            rc = self.lib.tx_create(C.byref(cfg), self.dev_index, C.c_void_p(self.stream.cuda_stream), C.byref(h))
+            if rc != 0:
+                raise _lib.TxError(f"tx_create failed ({rc}): {self.lib.tx_last_error(None).decode()}")
+            self.h = h
+            poly = tables.poly_grad.contiguous().float()
+            bg = tables.background.contiguous().float()
+            gel = tables.gel_map.contiguous().float() if tables.gel_map is not None else None
+            self._check(self.lib.tx_upload_tables(self.h, _ptr(poly), _ptr(bg), _ptr(gel)))
+        if self.M:
+            import numpy as np
+
+            mx = np.empty(self.M, np.int32)
+            my = np.empty(self.M, np.int32)
+            self._check(self.lib.tx_marker_grid(self.h, mx.ctypes.data, my.ctypes.data))
+            self.marker_x, self.marker_y = mx, my
+
+    # -- plumbing ------------------------------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise _lib.TxError(f"libtacex_b200 error {rc}: {self.lib.tx_last_error(self.h).decode()}")
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.tx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def counters(self) -> dict:
+        c = _lib.TxCounters()
+        self._check(self.lib.tx_get_counters(self.h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in c._fields_}
+
+    def _chk_hm(self, hm: torch.Tensor) -> int:
+        if hm.device != self.device or hm.dtype != torch.float32 or not hm.is_contiguous():
+            raise _lib.TxError("height map must be a contiguous float32 tensor on the engine's device")
+        if hm.dim() != 3 or tuple(hm.shape[1:]) != (self.H, self.W):
+            raise _lib.TxError(f"height map must have shape (N, {self.H}, {self.W})")
+        return hm.shape[0]
+
+    # -- hot path --------------------------------------------------------------------------------------------------
+    def indentation_depth(self, hm: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        N = self._chk_hm(hm)
+        out = torch.empty(N, device=self.device) if out is None else out
+        self._check(self.lib.tx_indentation_depth(self.h, _ptr(hm), N, _ptr(out)))
+        return out
+
+    def render(
+        self,
+        hm: torch.Tensor,
+        press: torch.Tensor | None = None,
+        out: torch.Tensor | None = None,
+        depth_out: torch.Tensor | None = None,
+        deformed_out: torch.Tensor | None = None,
+        mask_out: torch.Tensor | None = None,
+    ) -> torch.Tensor:
+        """RGB (N, H, W, 3) float32. ``press`` None = fused indentation depth (stored into ``depth_out``)."""
+        N = self._chk_hm(hm)
+        out = torch.empty((N, self.H, self.W, 3), device=self.device) if out is None else out
+        self._check(self.lib.tx_render(self.h, _ptr(hm), _ptr(press), N, _ptr(out), _ptr(depth_out), _ptr(deformed_out),
+                                       _ptr(mask_out)))
+        return out
+
+    def fots_markers(self, press: torch.Tensor, theta: torch.Tensor, traj0: torch.Tensor, traj_len: torch.Tensor,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+        N = press.shape[0]
+        out = torch.empty((N, 2, self.M, 2), device=self.device) if out is None else out
+        self._check(self.lib.tx_fots_markers(self.h, _ptr(press), _ptr(theta), N, _ptr(traj0), _ptr(traj_len), _ptr(out)))
+        return out
+
+    def step_host(self, hm_host: torch.Tensor, rgb_host: torch.Tensor, depth_host: torch.Tensor | None = None,
+                  theta_host: torch.Tensor | None = None, markers_host: torch.Tensor | None = None) -> None:
+        """End-to-end call on HOST buffers (H2D + fused path + D2H inside), what bench.py's ``e2e`` times."""
+        N = hm_host.shape[0]
+        self._check(self.lib.tx_step_host(self.h, _ptr(hm_host), _ptr(theta_host), N, _ptr(rgb_host), _ptr(depth_host),
+                                          _ptr(markers_host)))
