@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- tactile frames/s of the B200-native engine (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the tactile hot path over a batch of E synthetic contact depth maps per GPU
+(height map -> indentation depth -> Taxim RGB 320x240 -> FOTS 63-marker motion), i.e. what one
+``GelSightSensor`` update does for E parallel environments. Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W = 240, 320
+FRAME_IN_BYTES = H * W * 4            # float32 height map
+FRAME_OUT_BYTES = H * W * 3 * 4       # float32 NHWC RGB
+MARKER_ROWS, MARKER_COLS = 7, 9       # 63 markers (BASELINE.json north_star; the reference default 11x9 is parity-tested)
+M = MARKER_ROWS * MARKER_COLS
+ALGO_BYTES_PER_FRAME = FRAME_IN_BYTES + FRAME_OUT_BYTES  # 1,228,800 B
+METRIC = "tactile frames/sec (320x240 RGB+markers) @4096 envs, 1/2/4/8 B200"
+
+
+def _peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_port_fps(n_frames: int, with_markers: bool = True) -> tuple[float, int, str]:
+    """Times the CPU checker (oracle/ C restatement of the reference algorithm, OpenMP over frames) on a bounded
+    sample of the same workload. This is the ONLY place bench.py executes anything under oracle/."""
+    import numpy as np
+
+    from oracle import canon
+    from tacex_b200 import synth
+    from tacex_b200.calib import TaximTables
+
+    t = TaximTables.load(ROOT / "tests" / "golden" / "gsmini_tables_320x240.npz")
+    cn = canon.CanonTaxim(H, W, t.poly_grad.numpy(), t.background.numpy(), None, t.params.blur_taps((H, W)))
+    cf = canon.CanonFots(H, W, MARKER_ROWS, MARKER_COLS, 15, 26)
+    hm = synth.bench_batch(n_frames, n_unique=min(64, n_frames)).numpy()
+    th = np.zeros(n_frames, np.float32)
+    cn.render(hm[:8], cn.indentation_depth(hm[:8]))  # warm-up
+    t0 = time.perf_counter()
+    press = cn.indentation_depth(hm)
+    o = cn.render(hm, press, want=("deformed", "mask", "rgb"))
+    if with_markers:
+        cf.step(o["deformed"], o["mask"], press, th)
+    dt = time.perf_counter() - t0
+    return n_frames / dt, canon.num_threads(), f"{n_frames} frames of the same workload (config-1 sphere presses), one pass"
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's algorithm on the host cores. The reference's own implementation is Python
+    (torch + NumPy) inside /root/reference, which does not exist on the GPU box, so the timed code is the oracle's
+    C port of it (kind = "port"), with all host threads it can use (OpenMP over frames)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 256
+    vals = []
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_port_fps(64)
+    for _ in range(max(1, min(args.steps, 5))):
+        fps, cores, sample = cpu_port_fps(n)
+        vals.append(fps)
+    v = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": 1, "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n}-frame bounded sample per step of: {args.envs} envs x 320x240, Taxim RGB + FOTS {M}-marker motion"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (weak scaling)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "none"], help="N>1: all-gather of the RGB observation")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tacex_b200 import synth
+    from tacex_b200.calib import TaximTables
+    from tacex_b200.engine import TactileEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    E, K, Wm = args.envs, args.steps, max(args.warmup, 3)
+
+    tables = TaximTables.load(ROOT / "tests" / "golden" / "gsmini_tables_320x240.npz")
+    eng = TactileEngine(tables, max_envs=E, device=dev, marker_rows=MARKER_ROWS, marker_cols=MARKER_COLS)
+
+    # ---- synthetic "recorded" depth maps: the shard of envs [rank*E, (rank+1)*E) ---------------------------------
+    hm_host = synth.bench_batch(E, seed=rank, n_unique=64).pin_memory()
+    theta_host = torch.zeros(E).pin_memory()
+    hm = hm_host.to(dev)
+    theta = theta_host.to(dev)
+    depth = torch.empty(E, device=dev)
+    rgb = torch.empty((E, H, W, 3), device=dev)
+    markers = torch.empty((E, 2, M, 2), device=dev)
+    traj0 = torch.zeros((E, 4), device=dev)
+    traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
+    gathered = torch.empty((world * E, H, W, 3), device=dev) if (world > 1 and args.obs_gather == "fp32") else None
+
+    def step():
+        eng.render(hm, None, out=rgb, depth_out=depth)
+        eng.fots_markers(depth, theta, traj0, traj_len, out=markers)
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered, rgb)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(Wm):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    c0 = eng.counters()["kernels_launched"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.counters()["kernels_launched"] - c0
+
+    # ---- dominant kernel alone (roofline.achieved): K launches of the fused Taxim kernel --------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        eng.render(hm, None, out=rgb, depth_out=depth)
+    e1.record()
+    torch.cuda.synchronize()
+    kern_ms = e0.elapsed_time(e1) / K
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) --------------
+    rgb_host = torch.empty((E, H, W, 3)).pin_memory()
+    depth_host = torch.empty(E).pin_memory()
+    markers_host = torch.empty((E, 2, M, 2)).pin_memory()
+    Ke = max(2, min(K, 5))
+    eng.step_host(hm_host, rgb_host, depth_host, theta_host, markers_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        eng.step_host(hm_host, rgb_host, depth_host, theta_host, markers_host)  # synchronises the stream itself
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / Ke
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- max over ranks ------------------------------------------------------------------------------------------
+    t = torch.tensor([ms, kern_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kern_ms, e2e_s = t.tolist()
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        frames = world * E * K
+        value = frames / (ms / 1e3)
+        ach = ALGO_BYTES_PER_FRAME * E / (kern_ms / 1e3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            tj = json.loads(tp.read_text())
+            traffic = tj.get("dram_bytes_per_frame", 0) * E if tj.get("dram_bytes_per_frame") else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{E} envs/GPU x 320x240: indentation depth + Taxim RGB + FOTS {M}-marker motion, sphere indenters "
+                            f"(config-1 distribution, 10% no contact); gel FEM substep not included",
+                "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"dp{world} (contiguous env shards)",
+                "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2)",
+                "obs_gather": (args.obs_gather if world > 1 else "n/a"),
+            },
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "kernel": "taxim_fused_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * E,
+                         "peak_source": peak_src,
+                         "note": "FP32-FMA bound (exact separable pyramid, 266 MAC/px): see DESIGN.md section 5"},
+            "e2e": {"value": world * E / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": E * (FRAME_IN_BYTES + 4),
+                    "d2h_bytes_per_step": E * (FRAME_OUT_BYTES + 4 + M * 16), "api": "tx_step_host (C ABI, pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            fps, cores, sample = cpu_port_fps(256)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

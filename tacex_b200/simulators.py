@@ -1,0 +1,327 @@
+"""Drop-in implementations of the reference's simulator plug-in interface, backed by libtacex_b200.so.
+
+Interface mirrored (same method names, argument meaning, return shapes, error behaviour):
+  GelSightSimulator ABC          ref: source/tacex/tacex/simulation_approaches/gelsight_simulator.py:17-56
+  GelSightSimulatorCfg           ref: .../gelsight_simulator_cfg.py:7-16
+  TaximSimulatorCfg              ref: .../gpu_taxim/taxim_sim_cfg.py:12-36
+  TaximSimulator                 ref: .../gpu_taxim/taxim_sim.py:20-138
+  FOTSMarkerSimulatorCfg         ref: .../fots/fots_marker_sim_cfg.py:15-75
+  FOTSMarkerSimulator            ref: .../fots/fots_marker_sim.py:25-184
+
+When the reference package ``tacex`` is importable (inside Isaac Lab) the classes below subclass ITS
+``GelSightSimulator`` so ``GelSightSensor`` accepts them unchanged; otherwise they subclass the local ABC.
+Select them with ``cfg.simulation_approach_class = B200TaximSimulator``.
+"""
+
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any
+
+import torch
+import torch.nn.functional as F
+
+from .calib import TaximTables
+from .engine import TactileEngine
+
+try:  # inside Isaac Lab: plug into the reference's own ABC
+    from tacex.simulation_approaches.gelsight_simulator import GelSightSimulator as _RefBase  # type: ignore
+except Exception:  # headless / no Isaac Sim
+    _RefBase = None
+
+
+class _LocalGelSightSimulator(ABC):
+    """Same contract as the reference ABC (gelsight_simulator.py:17-56)."""
+
+    def __init__(self, sensor, cfg):
+        self.cfg = cfg
+        self.sensor = sensor
+        self._device = self.sensor.device if self.cfg.device is None else self.cfg.device
+
+    @abstractmethod
+    def _initialize_impl(self):
+        raise NotImplementedError
+
+    def optical_simulation(self):
+        raise NotImplementedError
+
+    def marker_motion_simulation(self):
+        raise NotImplementedError
+
+    def compute_indentation_depth(self):
+        raise NotImplementedError
+
+    @abstractmethod
+    def reset(self):
+        raise NotImplementedError
+
+    def _set_debug_vis_impl(self, debug_vis: bool):
+        raise NotImplementedError(f"Debug visualization is not implemented for {self.__class__.__name__}.")
+
+    def _debug_vis_callback(self, event):
+        raise NotImplementedError(f"Debug visualization is not implemented for {self.__class__.__name__}.")
+
+
+GelSightSimulator = _RefBase if _RefBase is not None else _LocalGelSightSimulator
+
+
+# ---- cfg classes (plain dataclasses; field-for-field the reference's @configclass definitions) -------------------
+@dataclass
+class GelSightSimulatorCfg:
+    simulation_approach_class: type | None = None
+    device: str | None = "cuda"
+
+
+@dataclass
+class TaximSimulatorCfg(GelSightSimulatorCfg):
+    simulation_approach_class: type | None = None  # None -> B200TaximSimulator
+    calib_folder_path: str = ""
+    device: str | None = "cuda"
+    with_shadow: bool = False
+    tactile_img_res: tuple = (320, 240)  # (W, H)
+    gelpad_height: float = 0.0045
+    gelpad_to_camera_min_distance: float = 0.024
+
+    def __post_init__(self):
+        if self.simulation_approach_class is None:
+            self.simulation_approach_class = B200TaximSimulator
+
+
+@dataclass
+class MarkerParams:
+    num_markers_col: int = 11
+    num_markers_row: int = 9
+    num_markers: int = 99
+    x0: float = 15.0
+    y0: float = 26.0
+    dx: float = 26.0
+    dy: float = 29.0
+
+
+@dataclass
+class FOTSMarkerSimulatorCfg(GelSightSimulatorCfg):
+    simulation_approach_class: type | None = None  # None -> B200FOTSMarkerSimulator
+    calib_folder_path: str = ""
+    device: str | None = None
+    with_shadow: bool = False
+    tactile_img_res: tuple = (320, 240)
+    lamb: list = field(default_factory=list)  # ignored, like the reference (fots_marker_sim.py:77 hard-codes it)
+    ball_radius: float = 4.70 / 2
+    mm_to_pixel: float = 19.58
+    pyramid_kernel_size: list = field(default_factory=list)
+    kernel_size: int = 0
+    marker_params: MarkerParams = field(default_factory=MarkerParams)
+    init_marker_pos: tuple = ([[]], [[]])
+    frame_transformer_cfg: Any = None
+
+    def __post_init__(self):
+        if self.simulation_approach_class is None:
+            self.simulation_approach_class = B200FOTSMarkerSimulator
+
+
+def _load_tables(path: str, shape: tuple[int, int]) -> TaximTables:
+    p = Path(path)
+    if p.is_dir():
+        return TaximTables.from_calib_folder(p, shape)
+    return TaximTables.load(p)
+
+
+def _is_cuda(dev) -> bool:
+    return torch.device(dev).type == "cuda"
+
+
+class B200TaximSimulator(GelSightSimulator):
+    """Taxim optical simulation on the fused sm_100a kernel (drop-in for ``TaximSimulator``)."""
+
+    cfg: TaximSimulatorCfg
+
+    def __init__(self, sensor, cfg: TaximSimulatorCfg):
+        self.sensor = sensor
+        super().__init__(sensor=sensor, cfg=cfg)
+
+    def _initialize_impl(self):
+        self._device = self.sensor.device if self.cfg.device is None else self.cfg.device
+        if not _is_cuda(self._device):
+            raise RuntimeError("B200TaximSimulator runs on a CUDA (sm_100a) device only; there is no CPU path")
+        if self.cfg.with_shadow:
+            raise NotImplementedError("with_shadow=True is not implemented (every GelSight Mini preset disables it)")
+        self._num_envs = self.sensor._num_envs
+        W, H = self.cfg.tactile_img_res
+        self.img_res = self.cfg.tactile_img_res
+        tables = _load_tables(self.cfg.calib_folder_path, (H, W))
+        mcfg = getattr(self.sensor.cfg, "marker_motion_sim_cfg", None)
+        rows = cols = 0
+        x0 = y0 = 0.0
+        mm2pix = 19.58
+        if mcfg is not None and hasattr(mcfg, "marker_params") and hasattr(mcfg, "mm_to_pixel"):
+            rows, cols = mcfg.marker_params.num_markers_row, mcfg.marker_params.num_markers_col
+            x0, y0, mm2pix = mcfg.marker_params.x0, mcfg.marker_params.y0, mcfg.mm_to_pixel
+        self.engine = TactileEngine(
+            tables, max_envs=self._num_envs, device=self._device, marker_rows=rows, marker_cols=cols, marker_x0=x0,
+            marker_y0=y0, mm2pix=mm2pix, gelpad_height_m=self.cfg.gelpad_height,
+            gelpad_to_cam_min_m=self.cfg.gelpad_to_camera_min_distance,
+        )
+        dev = self.engine.device
+        self._indentation_depth = torch.zeros((self._num_envs,), device=dev)
+        self._own_rgb = torch.zeros((self._num_envs, H, W, 3), device=dev)
+        self.tactile_rgb_img = self._own_rgb
+        # tactile image without indentation (the reference shows the resized background, taxim_sim.py:62-75)
+        self.background_img = tables.background.movedim(0, 2).contiguous().to(dev)
+        self.tactile_rgb_img[:] = self.background_img
+        self._stamp = None  # (height-map identity/version, indentation-depth version) of the last fused launch
+        self._sensor_depth_version = None
+
+    # -- helpers ---------------------------------------------------------------------------------------------------
+    def _height_map(self) -> torch.Tensor:
+        hm = self.sensor._data.output["height_map"]
+        W, H = self.cfg.tactile_img_res
+        if (hm.shape[1], hm.shape[2]) != (H, W):
+            # camera resolution != tactile resolution: bilinear + antialias like torchvision's F.resize (taxim_sim.py:88-89)
+            hm = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0]
+        if hm.device != self.engine.device:
+            hm = hm.to(self.engine.device)
+        return hm.contiguous()
+
+    def _rgb_target(self) -> torch.Tensor:
+        """Render straight into the sensor-owned output tensor when it exists: ``output[:] = returned`` in the sensor
+        (gelsight_sensor.py:373-375) then degenerates to a self-copy, which torch skips (same storage, same layout)."""
+        out = self.sensor._data.output.get("tactile_rgb") if self.sensor._data.output else None
+        t = self._own_rgb
+        if (isinstance(out, torch.Tensor) and out.shape == t.shape and out.dtype == t.dtype and out.device == t.device
+                and out.is_contiguous()):
+            self.tactile_rgb_img = out
+            return out
+        return t
+
+    def _hm_stamp(self):
+        hm = self.sensor._data.output["height_map"]
+        return (hm.data_ptr(), hm._version, tuple(hm.shape))
+
+    # -- plug-in interface -------------------------------------------------------------------------------------------
+    def compute_indentation_depth(self):
+        """Indentation depth [mm] (ref: taxim_sim.py:115-131). Runs the FUSED kernel: the RGB frame of the same
+        height map is produced in the same launch and reused by ``optical_simulation`` if nothing changed."""
+        hm = self._height_map()
+        self.engine.render(hm, None, out=self._rgb_target(), depth_out=self._indentation_depth)
+        self._stamp = (self._hm_stamp(), self._indentation_depth._version)
+        return self._indentation_depth
+
+    def optical_simulation(self):
+        """Tactile RGB (num_envs, H, W, 3) float32 in [0, 1] (ref: taxim_sim.py:80-113)."""
+        if self._stamp != (self._hm_stamp(), self._indentation_depth._version):
+            hm = self._height_map()
+            self.engine.render(hm, self._indentation_depth, out=self._rgb_target())
+            self._stamp = (self._hm_stamp(), self._indentation_depth._version)
+        sd = getattr(self.sensor, "_indentation_depth", None)
+        self._sensor_depth_version = sd._version if isinstance(sd, torch.Tensor) else None
+        return self.tactile_rgb_img
+
+    def reset(self):
+        self._indentation_depth = torch.zeros((self._num_envs,), device=self.engine.device)
+        self.tactile_rgb_img = self._own_rgb  # never clobber the sensor-owned output (it keeps the last render)
+        self.tactile_rgb_img[:] = self.background_img
+        self._stamp = None
+
+    def _set_debug_vis_impl(self, debug_vis: bool):
+        pass  # GUI only in the reference (omni.ui); nothing to do headless
+
+    def _debug_vis_callback(self, event):
+        pass
+
+
+class B200FOTSMarkerSimulator(GelSightSimulator):
+    """FOTS marker motion on the GPU (drop-in for ``FOTSMarkerSimulator``); reuses the gel deformation of the
+    optical simulator's last launch instead of recomputing the blur pyramid."""
+
+    cfg: FOTSMarkerSimulatorCfg
+
+    def __init__(self, sensor, cfg: FOTSMarkerSimulatorCfg):
+        self.sensor = sensor
+        super().__init__(sensor=sensor, cfg=cfg)
+        self.frame_transformer = None
+        if self.cfg.frame_transformer_cfg is not None:
+            from isaaclab.sensors import FrameTransformer  # type: ignore  # only inside Isaac Lab
+
+            self.frame_transformer = FrameTransformer(self.cfg.frame_transformer_cfg)
+
+    def _initialize_impl(self):
+        self._device = self.sensor.device if self.cfg.device is None else self.cfg.device
+        self._num_envs = self.sensor._num_envs
+        if (self.sensor.optical_simulator is not None) and isinstance(self.sensor.optical_simulator, B200TaximSimulator):
+            self._taxim: B200TaximSimulator = self.sensor.optical_simulator
+        else:
+            raise RuntimeError(
+                "Currently FOTS simulation approach has to be used in combination with GPU-Taxim as optical-simulator."
+            )
+        eng = self._taxim.engine
+        if eng.M != self.cfg.marker_params.num_markers_row * self.cfg.marker_params.num_markers_col:
+            raise RuntimeError("marker grid of the optical simulator's engine does not match marker_params")
+        self.engine = eng
+        dev = eng.device
+        self._indentation_depth = torch.zeros((self._num_envs,), device=dev)
+        self.init_marker_pos = torch.stack(
+            (torch.from_numpy(eng.marker_x).float(), torch.from_numpy(eng.marker_y).float()), dim=-1
+        )
+        self.img_res = self.cfg.tactile_img_res
+        self.marker_data = torch.zeros((self._num_envs, 2, eng.M, 2), device=dev)
+        self.marker_data[:, 0] = self.init_marker_pos.to(dev)
+        self.marker_data[:, 1] = self.init_marker_pos.to(dev)
+        # per-env trajectory state: first sample of the contact episode + number of samples. The reference keeps a
+        # python list per env in sensor._data.output["traj"]; only traj[0], traj[-1] and len() are ever used.
+        self.traj0 = torch.zeros((self._num_envs, 4), device=dev)
+        self.traj_len = torch.zeros((self._num_envs,), device=dev, dtype=torch.int32)
+        self.sensor._data.output["traj"] = self.traj0
+        self.theta = torch.zeros((self._num_envs,), device=dev)
+        self._scratch_rgb = None
+        if self.frame_transformer is not None:
+            self.frame_transformer._initialize_impl()
+            self.frame_transformer._is_initialized = True
+
+    def _relative_yaw(self) -> torch.Tensor:
+        """Yaw of the indenter relative to the sensor (ref: fots_marker_sim.py:147-159 via FrameTransformer);
+        headless: the recorded value in sensor._data.output['indenter_yaw'] (zeros if absent)."""
+        if self.frame_transformer is not None:
+            from isaaclab.utils.math import euler_xyz_from_quat  # type: ignore
+
+            self.frame_transformer.update(dt=0.001)
+            _, _, yaw = euler_xyz_from_quat(self.frame_transformer.data.target_quat_source[:, 0])
+            return yaw.to(self.engine.device, torch.float32).contiguous()
+        yaw = self.sensor._data.output.get("indenter_yaw")
+        if yaw is None:
+            return self.theta
+        return yaw.to(self.engine.device, torch.float32).contiguous()
+
+    def marker_motion_simulation(self):
+        """(num_envs, 2, M, 2): [:,0] initial, [:,1] current marker (x, y) px (ref: fots_marker_sim.py:114-184)."""
+        self._indentation_depth = self.sensor._indentation_depth
+        press = self._indentation_depth.to(self.engine.device, torch.float32).contiguous()
+        tx = self._taxim
+        # The engine still holds the gel deformation of the optical simulator's last launch. It is valid for this call
+        # iff the height map has not changed since and the sensor's indentation-depth buffer is the unmodified copy
+        # GelSightSensor made of the simulator's buffer (gelsight_sensor.py:361-365) -- tracked with tensor versions,
+        # no host synchronisation. Otherwise recompute it for exactly (height_map, sensor._indentation_depth), as the
+        # reference always does (fots_marker_sim.py:128-129).
+        reuse = (
+            tx._stamp is not None
+            and tx._stamp == (tx._hm_stamp(), tx._indentation_depth._version)
+            and tx._sensor_depth_version == self.sensor._indentation_depth._version
+        )
+        if not reuse:
+            if self._scratch_rgb is None:
+                self._scratch_rgb = torch.empty_like(tx.tactile_rgb_img)
+            self.engine.render(tx._height_map(), press, out=self._scratch_rgb)
+            tx._stamp = None  # the engine's recorded deformation no longer belongs to the optical simulator's frame
+        self.theta = self._relative_yaw()
+        self.engine.fots_markers(press, self.theta, self.traj0, self.traj_len, out=self.marker_data)
+        return self.marker_data
+
+    def reset(self):
+        pass
+
+    def _set_debug_vis_impl(self, debug_vis: bool):
+        pass
+
+    def _debug_vis_callback(self, event):
+        pass

@@ -1,0 +1,123 @@
+"""CPU suite: host-side logic of the product (no compute calls into the CUDA library)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, H, ROOT, W
+
+
+def test_gaussian_taps_match_reference_kernels(tables, golden):
+    """calib.gaussian_taps reproduces the reference's kernels bit-for-bit: outer(ky, kx) == its 2-D kernel
+    (taxim_torch.py:363-379) and the kernel sizes are 61,33,17,9,5,3 + 5."""
+    taps = tables.params.blur_taps((H, W))
+    assert [len(a) for a, _ in taps] == [61, 33, 17, 9, 5, 3, 5]
+    ex = golden["gsmini_ref_extras"]
+    for l, (kx, ky) in enumerate(taps):
+        k2 = torch.mm(ky[:, None], kx[None, :]).numpy()
+        assert np.array_equal(k2, ex[f"k2d_{l}"]), l
+        assert abs(float(kx.sum()) - 1) < 1e-6
+        assert torch.equal(kx, kx.flip(0)), "taps must be exactly symmetric"
+
+
+def test_tables_roundtrip(tables, tmp_path):
+    from tacex_b200.calib import TaximTables
+
+    p = tmp_path / "t.npz"
+    tables.save(p)
+    t2 = TaximTables.load(p)
+    assert torch.equal(t2.poly_grad, tables.poly_grad) and torch.equal(t2.background, tables.background)
+    assert t2.gel_map is None and t2.shape == (H, W)
+    assert t2.params.pixmm == pytest.approx(0.0295) and t2.params.num_bins == 125
+
+
+@pytest.mark.refbox
+def test_calib_loader_against_reference_tables(tables):
+    """Our init-time table preparation (direct separable blur) against the reference's FFT-based one."""
+    from oracle import ref_bootstrap as rb
+
+    if not rb.available():
+        pytest.skip("reference checkout not present on this machine")
+    from tacex_b200.calib import TaximTables
+
+    t = TaximTables.from_calib_folder(rb.CALIB_DIR, (H, W))
+    assert torch.equal(t.poly_grad, tables.poly_grad)
+    assert (t.background - tables.background).abs().max() < 1e-6
+    assert t.gel_map is None and abs(t.gel_map_shift - 5.0) < 1e-6
+
+
+def test_header_symbols_exported():
+    """Every function include/tacex_b200.h declares is exported by the built library (no compute call)."""
+    from tacex_b200 import _lib, build
+
+    hdr = (ROOT / "include" / "tacex_b200.h").read_text()
+    declared = set(re.findall(r"\b(tx_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"tx_handle", "tx_config", "tx_counters", "tx_status"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib_path = build.build_lib()
+    lib = C.CDLL(str(lib_path))
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.tx_abi_version.restype = C.c_int
+    assert lib.tx_abi_version() == _lib.TX_ABI_VERSION
+
+
+def test_config_struct_layout_matches_header():
+    """ctypes mirror of tx_config has the size the C compiler gives the header's struct."""
+    import subprocess
+    import tempfile
+
+    from tacex_b200 import _lib
+
+    src = '#include "tacex_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu\\n", sizeof(tx_config), sizeof(tx_counters));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "s.c").write_text(src)
+        subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(Path(d) / "s.c"), "-o", str(Path(d) / "s")], check=True)
+        a, b = subprocess.run([str(Path(d) / "s")], capture_output=True, text=True, check=True).stdout.split()
+    assert int(a) == C.sizeof(_lib.TxConfig) and int(b) == C.sizeof(_lib.TxCounters)
+
+
+def test_no_cpu_fallback_without_gpu(tables):
+    """The product fails loudly when there is no CUDA device (no silent CPU / oracle path)."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tacex_b200 import _lib, engine
+
+    with pytest.raises(_lib.TxError):
+        engine.TactileEngine(tables, max_envs=4)
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "tacex_b200").rglob("*.py"):
+        txt = p.read_text()
+        assert "import oracle" not in txt and "from oracle" not in txt, p
+    for p in (ROOT / "tacex_b200" / "csrc").glob("*"):
+        assert not re.search(r'#include\s+"[^"]*oracle', p.read_text()), p
+
+
+def test_synth_shapes_and_determinism():
+    from tacex_b200 import synth
+
+    a = synth.config1(3, seed=0)["depth_m"]
+    b = synth.config1(3, seed=0)["depth_m"]
+    assert torch.equal(a, b) and a.shape == (3, H, W) and a.dtype == torch.float32
+    assert float(a.max()) <= 0.029 + 1e-9 and float(a.min()) >= 0.0285 - 1.5e-3 - 1e-6
+    c = synth.config2(4, seed=1)
+    assert set(c) >= {"depth_m0", "depth_m", "theta0", "theta", "kind"}
+    hm = synth.bench_batch(10, n_unique=4)
+    assert hm.shape == (10, H, W) and torch.equal(hm[0], hm[4])
+
+
+def test_sensor_cfg_mirrors_reference_fields():
+    from tacex_b200 import sensor, simulators
+
+    cfg = sensor.gelsight_mini_cfg(str(GOLDEN / "gsmini_tables_320x240.npz"), num_envs=2)
+    assert cfg.optical_sim_cfg.simulation_approach_class is simulators.B200TaximSimulator
+    assert cfg.marker_motion_sim_cfg.simulation_approach_class is simulators.B200FOTSMarkerSimulator
+    assert cfg.optical_sim_cfg.tactile_img_res == (320, 240) and cfg.sensor_camera_cfg.clipping_range == (0.024, 0.029)
+    assert cfg.marker_motion_sim_cfg.marker_params.num_markers == 99
+    for f in ("calib_folder_path", "device", "with_shadow", "tactile_img_res", "gelpad_height", "gelpad_to_camera_min_distance"):
+        assert hasattr(cfg.optical_sim_cfg, f)
