@@ -126,6 +126,10 @@ int tx_fots_markers(tx_handle* h, const float* press_mm, const float* theta, int
 /* Initial marker grid (host pointers, M ints each). ref: marker_motion.py:58-76 */
 int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my);
 
+/* Profiling hook: when `ticks` (device, [2*N][40] int64) is non-NULL, every CTA of the following tx_render launches
+ * stores clock64() stamps at its phase boundaries there (used by tools/phase_times.py; NULL disables). */
+int tx_debug_set_ticks(tx_handle* h, long long* ticks);
+
 /* ---- host-buffer convenience (the end-to-end path the benchmark times) -------------------------------------- */
 
 /* height_mm_host [N][H][W] pinned or pageable HOST memory -> rgb_host [N][H][W][3], depth_host [N] (optional),

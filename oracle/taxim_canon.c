@@ -20,8 +20,9 @@
  * TaximTorch / MarkerMotion here and commits the vectors under tests/golden/); the reference's own tests
  * hold no golden vectors for this path.
  *
- * Canonical choices: blur = horizontal pass then vertical pass, each output
- * accumulated as acc = fmaf(w[k], x[k], acc) for k ascending from an initial 0.0f; gel map == 0 when the
+ * Canonical choices: blur = horizontal pass then vertical pass; horizontal outputs are
+ * accumulated as acc = fmaf(w[k], x[k], acc) for k ascending from an initial 0.0f, vertical outputs centre-outward
+ * with the symmetric pair summed first: acc = w[c]*x0; acc = fmaf(w[c+d], x[-d] + x[+d], acc), d = 1..r; gel map == 0 when the
  * caller passes gel == NULL; atanf / atan2f are the fixed polynomial below (identical text in the CUDA kernel).
  *
  * Build: gcc -O2 -ffp-contract=off -mfma -shared -fPIC (see oracle/Makefile).
@@ -116,10 +117,16 @@ static void canon_blur(const float* src, float* tmp, float* dst, int H, int W, c
             tmp[(size_t)y * W + x] = acc;
         }
     }
+    /* vertical: centre-outward, symmetric pairs summed first (direction independent):
+       acc = w[c] * x[y]; acc = fma(w[c + d], x[y - d] + x[y + d], acc) for d = 1..ry */
     for (int y = 0; y < H; ++y) {
         for (int x = 0; x < W; ++x) {
-            float acc = 0.0f;
-            for (int k = 0; k < ksy; ++k) acc = fmaf(ky[k], tmp[(size_t)reflect_idx(y + k - ry, H) * W + x], acc);
+            float acc = ky[ry] * tmp[(size_t)y * W + x];
+            for (int d = 1; d <= ry; ++d) {
+                float a = tmp[(size_t)reflect_idx(y - d, H) * W + x];
+                float b = tmp[(size_t)reflect_idx(y + d, H) * W + x];
+                acc = fmaf(ky[ry + d], a + b, acc);
+            }
             dst[(size_t)y * W + x] = acc;
         }
     }

@@ -14,7 +14,9 @@ TX_MAX_TAPS = 64
 TX_MAX_MARKERS = 256
 TX_ABI_VERSION = 1
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtacex_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("TACEX_B200_LIB", Path(__file__).resolve().parent / "lib" / "libtacex_b200.so"))
 
 
 class TxConfig(C.Structure):
@@ -46,7 +48,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host",
+    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks",
 ]
 
 
@@ -73,6 +75,8 @@ def load() -> C.CDLL:
     lib.tx_fots_markers.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, ip, fp]
     lib.tx_marker_grid.argtypes = [C.c_void_p, ip, ip]
     lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
+    lib.tx_debug_set_ticks.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tx_debug_set_ticks.restype = C.c_int
     for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_fots_markers",
                  "tx_marker_grid", "tx_step_host"):
         getattr(lib, name).restype = C.c_int

@@ -42,8 +42,9 @@ constexpr int SM_PLANE = 0;
 constexpr int SM_HB0 = SM_PLANE + HALF_H * IMG_W * 4;
 constexpr int SM_HB1 = SM_HB0 + HB0_ROWS * IMG_W * 4;
 constexpr int SM_MASK = SM_HB1 + HB1_ROWS * IMG_W * 4;
-constexpr int SM_MISC = SM_MASK + HALF_H * (IMG_W / 32) * 4;
-constexpr int SM_TOTAL = SM_MISC + 256;
+constexpr int SM_MLIST = SM_MASK + HALF_H * (IMG_W / 32) * 4; // u16 indices of the non-empty mask words
+constexpr int SM_MISC = SM_MLIST + HALF_H * (IMG_W / 32) * 2;
+constexpr int SM_TOTAL = SM_MISC + 512;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Misc {
@@ -51,8 +52,9 @@ struct Misc {
     float xch_min[2];
     float red_f[NWARPS];
     unsigned red_u[3][NWARPS];
+    int nlist;
 };
-static_assert(sizeof(Misc) <= 256, "misc");
+static_assert(sizeof(Misc) <= 512, "misc");
 
 int taxim_smem_bytes() { return SM_TOTAL; }
 
@@ -60,33 +62,41 @@ int taxim_smem_bytes() { return SM_TOTAL; }
 // Lane i owns virtual columns v = 12*i + j - 32 (j = 0..11); virtual columns outside [0, 320) hold the reflected
 // pixels (torch 'reflect'), so the correlation is uniform over the warp. PUSH: also store the result row into the
 // peer CTA's halo buffer (row index = distance from the CTA boundary).
+__device__ __forceinline__ void load_row12(const float* rp, int v0, bool interior, float (&x)[12])
+{
+    if (interior) { // lanes 3..28: three aligned 128-bit loads (conflict-free within each quarter warp)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const float4 t = *reinterpret_cast<const float4*>(rp + v0 + 4 * e);
+            x[4 * e + 0] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
+        }
+    } else { // the six edge lanes hold the reflected columns
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            int v = v0 + j;
+            v = v < 0 ? -v : (v > IMG_W - 1 ? 2 * (IMG_W - 1) - v : v);
+            x[j] = rp[v];
+        }
+    }
+}
+
 template <int L, int RAD>
 __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, int lane, unsigned q)
 {
     constexpr int D = (RAD + 11) / 12;
+    constexpr int ROWS = HALF_H / NWARPS;
     const int v0 = 12 * lane - 32;
+    const bool interior = (lane >= 3) && (lane <= 28);
+    float xn[12];
+    load_row12(plane + (warp * ROWS) * IMG_W, v0, interior, xn);
 #pragma unroll 1
-    for (int rr = 0; rr < HALF_H / NWARPS; ++rr) {
-        const int row = warp * (HALF_H / NWARPS) + rr;
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const int row = warp * ROWS + rr;
         float* rp = plane + row * IMG_W;
         float x[12], acc[12];
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int vb = v0 + 4 * e;
-            if (vb >= 0 && vb <= IMG_W - 4) {
-                const float4 t = *reinterpret_cast<const float4*>(rp + vb);
-                x[4 * e + 0] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    int v = vb + u;
-                    v = v < 0 ? -v : (v > IMG_W - 1 ? 2 * (IMG_W - 1) - v : v);
-                    x[4 * e + u] = rp[v];
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < 12; ++m) acc[m] = 0.0f;
+        for (int j = 0; j < 12; ++j) { x[j] = xn[j]; acc[j] = 0.0f; }
+        if (rr + 1 < ROWS) load_row12(rp + IMG_W, v0, interior, xn); // prefetch the next row (other row: no hazard)
 #pragma unroll
         for (int d = -D; d <= D; ++d) {
 #pragma unroll
@@ -101,9 +111,8 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, 
                 }
             }
         }
-        __syncwarp(); // every lane has consumed the old row before anyone overwrites it
-        // distance of this row from the CTA boundary (q = 0: boundary below row 119; q = 1: above row 0)
-        const int dist = q == 0 ? (HALF_H - 1 - row) : row;
+        // the shuffles above are warp-synchronous: every lane has consumed the old row before anyone overwrites it
+        const int dist = q == 0 ? (HALF_H - 1 - row) : row; // distance from the CTA boundary
         const bool push = dist < RAD;
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
@@ -119,17 +128,18 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, 
 
 // ---- vertical pass: thread per column, sliding register window, in place --------------------------------------
 // Position t = 0..119 counts rows from the IMAGE edge of this CTA's half (q = 0: t = local row, marching down;
-// q = 1 (REV): t = 119 - local row, marching up). Positions < 0 are the reflected rows, positions >= 120 come from
-// the halo buffer (rows of the peer CTA by distance from the boundary). Tap order is always ascending image row.
-template <int L, int RAD, int R, bool REV>
-__device__ __forceinline__ void vpass_dir(float* plane, const float* hb, int col)
+// q = 1: t = 119 - local row, marching up). Positions < 0 are the reflected rows, positions >= 120 come from
+// the halo buffer (rows of the peer CTA by distance from the boundary).
+template <int L, int RAD, int R>
+__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q)
 {
+    if (tid >= IMG_W) return;
     constexpr int WN = R + 2 * RAD;
     constexpr int NB = HALF_H / R;
     static_assert(HALF_H % R == 0 && R + RAD <= HALF_H, "block size");
     float win[WN];
-    float* p0 = plane + (REV ? (HALF_H - 1) * IMG_W : 0) + col;
-    constexpr int S = REV ? -IMG_W : IMG_W;
+    float* p0 = plane + (q ? (HALF_H - 1) * IMG_W : 0) + tid;
+    const int S = q ? -IMG_W : IMG_W;
 #pragma unroll
     for (int i = 0; i < WN; ++i) {
         int t = i - RAD;
@@ -139,20 +149,14 @@ __device__ __forceinline__ void vpass_dir(float* plane, const float* hb, int col
 #pragma unroll 1
     for (int b = 0; b < NB; ++b) {
         float acc[R];
+        // centre-outward, symmetric pair summed first: independent of the marching direction
 #pragma unroll
-        for (int m = 0; m < R; ++m) acc[m] = 0.0f;
-        if (!REV) {
+        for (int m = 0; m < R; ++m) acc[m] = __fmul_rn(c_taps[L][1][RAD], win[m + RAD]);
 #pragma unroll
-            for (int k = 0; k <= 2 * RAD; ++k) {
+        for (int d = 1; d <= RAD; ++d) {
 #pragma unroll
-                for (int m = 0; m < R; ++m) acc[m] = __fmaf_rn(c_taps[L][1][k], win[m + k], acc[m]);
-            }
-        } else {
-#pragma unroll
-            for (int k = 2 * RAD; k >= 0; --k) {
-#pragma unroll
-                for (int m = 0; m < R; ++m) acc[m] = __fmaf_rn(c_taps[L][1][2 * RAD - k], win[m + k], acc[m]);
-            }
+            for (int m = 0; m < R; ++m)
+                acc[m] = __fmaf_rn(c_taps[L][1][RAD + d], __fadd_rn(win[m + RAD - d], win[m + RAD + d]), acc[m]);
         }
         float* po = p0 + (b * R) * S;
 #pragma unroll
@@ -165,53 +169,67 @@ __device__ __forceinline__ void vpass_dir(float* plane, const float* hb, int col
             for (int i = 2 * RAD; i < WN; ++i) {
                 const int t = tb + i;
                 // t >= 120 -> halo row (t - 120); only rows < RAD are ever used by outputs < 120
-                const float* src = (t < HALF_H) ? (p0 + t * S) : (hb + min(t - HALF_H, RAD - 1) * IMG_W + col);
+                const float* src = (t < HALF_H) ? (p0 + t * S) : (hb + min(t - HALF_H, RAD - 1) * IMG_W + tid);
                 win[i] = *src;
             }
         }
     }
 }
 
-template <int L, int RAD, int R>
-__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q)
-{
-    if (tid < IMG_W) {
-        if (q == 0)
-            vpass_dir<L, RAD, R, false>(plane, hb, tid);
-        else
-            vpass_dir<L, RAD, R, true>(plane, hb, tid);
-    }
-}
-
 // ---- masked re-imposition: plane[mask] = min(h, gel) recomputed from the input frame (L2 hit) ------------------
-__device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits, const float* __restrict__ hm_half,
-                                         const float* __restrict__ gel_half, float m, float press, int warp, int lane)
+// `list` holds the indices of the mask words with at least one bit set (built once per frame).
+__device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits, const unsigned short* list, int nlist,
+                                         const float* __restrict__ hm_half, const float* __restrict__ gel_half, float m,
+                                         float press, int warp, int lane)
 {
-    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
-        const unsigned bits = maskbits[w];
-        if (bits == 0u) continue;
-        if ((bits >> lane) & 1u) {
-            const int idx = w * 32 + lane; // row * 320 + seg * 32 + lane
-            const float h = __fadd_rn(__fadd_rn(__ldg(hm_half + idx), -m), -press);
-            const float g = gel_half ? __ldg(gel_half + idx) : 0.0f;
-            plane[idx] = fminf(h, g);
+    for (int i0 = warp * 4; i0 < nlist; i0 += NWARPS * 4) {
+        float v[4];
+        int idx[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            on[u] = false;
+            if (i < nlist) {
+                const int w = list[i];
+                idx[u] = w * 32 + lane;
+                on[u] = (maskbits[w] >> lane) & 1u;
+                if (on[u]) v[u] = __ldg(hm_half + idx[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (on[u]) {
+                const float h = __fadd_rn(__fadd_rn(v[u], -m), -press);
+                const float g = gel_half ? __ldg(gel_half + idx[u]) : 0.0f;
+                plane[idx[u]] = fminf(h, g);
+            }
         }
     }
 }
 
+#define TX_TICK(slot)                                                                                                 \
+    do {                                                                                                              \
+        if (tk && tid == 0) tk[(slot)] = clock64();                                                                   \
+    } while (0)
+
 template <int L, int RAD, int R, bool FINAL>
 __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
-                                           const float* hm_half, const float* gel_half, float m, float press, int tid,
-                                           int warp, int lane, unsigned q, cg::cluster_group& cluster)
+                                           const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half, float m, float press, int tid,
+                                           int warp, int lane, unsigned q, cg::cluster_group& cluster, long long* tk)
 {
     hpass<L, RAD>(plane, hb_remote, warp, lane, q);
+    TX_TICK(4 + 4 * L + 0);
     cluster.sync(); // rows + pushed halo rows visible in both CTAs
+    TX_TICK(4 + 4 * L + 1);
     vpass<L, RAD, R>(plane, hb_local, tid, q);
     __syncthreads();
+    TX_TICK(4 + 4 * L + 2);
     if (!FINAL) {
-        reimpose(plane, maskbits, hm_half, gel_half, m, press, warp, lane);
+        reimpose(plane, maskbits, mlist, nlist, hm_half, gel_half, m, press, warp, lane);
         __syncthreads();
     }
+    TX_TICK(4 + 4 * L + 3);
 }
 
 // ---- the fused kernel -------------------------------------------------------------------------------------------
@@ -222,6 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     float* hb0 = reinterpret_cast<float*>(smem + SM_HB0);
     float* hb1 = reinterpret_cast<float*>(smem + SM_HB1);
     unsigned* maskbits = reinterpret_cast<unsigned*>(smem + SM_MASK);
+    unsigned short* mlist = reinterpret_cast<unsigned short*>(smem + SM_MLIST);
     Misc* misc = reinterpret_cast<Misc*>(smem + SM_MISC);
 
     cg::cluster_group cluster = cg::this_cluster();
@@ -234,12 +253,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     float* hb0_remote = cluster.map_shared_rank(hb0, q ^ 1u);
     float* hb1_remote = cluster.map_shared_rank(hb1, q ^ 1u);
     Misc* misc_remote = cluster.map_shared_rank(misc, q ^ 1u);
+    long long* tk = p.ticks ? p.ticks + (size_t)blockIdx.x * 40 : nullptr; // optional per-CTA phase clock stamps
+    TX_TICK(0);
 
     // ---- stage the half frame with bulk-async copies (TMA) ----------------------------------------------------
     if (tid == 0) {
         mbar_init(&misc->mbar, 1);
         fence_mbar_init();
         fence_proxy_async();
+        misc->nlist = 0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -251,6 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
                      reinterpret_cast<const unsigned char*>(hm_half) + c * CH, CH, &misc->mbar);
     }
     mbar_wait(&misc->mbar, 0);
+    TX_TICK(1);
 
     // ---- frame minimum (ref: taxim_torch.py:441, taxim_sim.py:116-117) ----------------------------------------
     float mloc = __int_as_float(0x7f800000);
@@ -273,6 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     }
     cluster.sync();
     const float m = fminf(misc->xch_min[0], misc->xch_min[1]);
+    TX_TICK(2);
 
     // ---- indentation depth (explicit, or fused: ref taxim_sim.py:115-131) --------------------------------------
     float press;
@@ -290,21 +314,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     // min over the frame of ((hm - m) - press) is exactly -press, so pressing_depth_mm == press.
     const float thr = __fmul_rn(-press, p.contact_scale);
     unsigned cnt = 0, srow = 0, scol = 0;
-    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
-        const int idx = w * 32 + lane;
-        const float h = __fadd_rn(__fadd_rn(plane[idx], -m), -press);
-        const float g = gel_half ? __ldg(gel_half + idx) : 0.0f;
-        const bool contact = h < 0.0f;
-        const float j = fminf(h, g);
-        const bool mk = (__fadd_rn(j, -g) < thr) && contact;
-        plane[idx] = j;
-        const unsigned bits = __ballot_sync(0xffffffffu, mk);
-        if (lane == 0) maskbits[w] = bits;
-        if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
-        if (mk) {
-            cnt += 1u;
-            srow += (unsigned)(q * HALF_H + idx / IMG_W);
-            scol += (unsigned)(idx % IMG_W);
+    constexpr int NWORDS = HALF_H * (IMG_W / 32);
+    static_assert(NWORDS % (NWARPS * 4) == 0, "h/mask pass unroll");
+    for (int w0 = warp * 4; w0 < NWORDS; w0 += NWARPS * 4) {
+        float pv[4], gv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = (w0 + u) * 32 + lane;
+            pv[u] = plane[idx];
+            gv[u] = gel_half ? __ldg(gel_half + idx) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int w = w0 + u;
+            const int idx = w * 32 + lane;
+            const float h = __fadd_rn(__fadd_rn(pv[u], -m), -press);
+            const bool contact = h < 0.0f;
+            const float j = fminf(h, gv[u]);
+            const bool mk = (__fadd_rn(j, -gv[u]) < thr) && contact;
+            plane[idx] = j;
+            const unsigned bits = __ballot_sync(0xffffffffu, mk);
+            if (lane == 0) {
+                maskbits[w] = bits;
+                if (bits) mlist[atomicAdd(&misc->nlist, 1)] = (unsigned short)w;
+            }
+            if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
+            if (mk) { // row / column from the word index (one word = 32 consecutive columns of one row)
+                cnt += 1u;
+                srow += (unsigned)(q * HALF_H) + (unsigned)w / (IMG_W / 32);
+                scol += ((unsigned)w % (IMG_W / 32)) * 32u + (unsigned)lane;
+            }
         }
     }
     if (p.aux_sums) {
@@ -324,18 +363,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         for (int w = 0; w < NWARPS; ++w) s += misc->red_u[tid][w];
         p.aux_sums[((size_t)n * 2 + q) * 4 + tid] = s;
     }
+    const int nlist = misc->nlist;
 
+    TX_TICK(3);
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     const bool active = (p.gel != nullptr) || (press > 0.0f);
     if (active) {
-        blur_level<0, 30, 20, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<1, 16, 30, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<2, 8, 40, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<3, 4, 40, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<4, 2, 40, false>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<5, 1, 40, false>(plane, hb1, hb1_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
-        blur_level<6, 2, 40, true>(plane, hb0, hb0_remote, maskbits, hm_half, gel_half, m, press, tid, warp, lane, q, cluster);
+        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
     }
 
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
@@ -370,62 +411,121 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         }
     }
     cluster.sync();
+    TX_TICK(32);
 
     // ---- normals -> bins -> polynomial -> + background -> clip -> NHWC (ref: taxim_torch.py:475-503, 243-258) ---
+    // One thread per 4 consecutive pixels of a row: 128-bit loads of the background / stores of the RGB frame, four
+    // independent math chains, twenty table loads in flight. Warps whose pixels are all flat (exact zero gradient,
+    // the common case outside the deformed region) skip the transcendental math.
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
-    for (int w = warp; w < HALF_H * (IMG_W / 32); w += NWARPS) {
-        const int row = w / (IMG_W / 32);
-        const int x = (w % (IMG_W / 32)) * 32 + lane;
+    const int id_flat = min(max((int)floorf(__fmul_rn(__fadd_rn(0.0f, PI_F), p.inv_ybin)), 0), p.nb - 1);
+    // coefficients of the flat bin (mag = 0, dir = 0): shared by every flat pixel, kept in registers
+    float cflat[18];
+    {
+        const float4* pf = p.poly + (size_t)id_flat * 5;
+        const float4 a0 = __ldg(pf), a1 = __ldg(pf + 1), a2 = __ldg(pf + 2), a3 = __ldg(pf + 3), a4 = __ldg(pf + 4);
+        const float t20[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
+                               a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int i = 0; i < 18; ++i) cflat[i] = t20[i];
+    }
+    constexpr int QPR = IMG_W / 4; // quads per row
+#pragma unroll 1
+    for (int qd = tid; qd < HALF_H * QPR; qd += NTHREADS) {
+        const int row = qd / QPR;
+        const int x0 = (qd - row * QPR) * 4;
         const int gy_ = (int)q * HALF_H + row; // image row
         // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
-        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
-        const int xx = min(max(x, 1), IMG_W - 2);
-        const float* up = (yy - 1 >= 0) ? plane + (yy - 1) * IMG_W : hb1;
-        const float* dn = (yy + 1 < HALF_H) ? plane + (yy + 1) * IMG_W : hb1;
-        const float top = __fmul_rn(up[xx], p.inv_pixmm), bot = __fmul_rn(dn[xx], p.inv_pixmm);
-        const float lef = __fmul_rn(plane[yy * IMG_W + xx - 1], p.inv_pixmm);
-        const float rig = __fmul_rn(plane[yy * IMG_W + xx + 1], p.inv_pixmm);
-        const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
-        const float gy = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
-        int im = 0, id;
-        {
-            const float tt = __fsqrt_rn(__fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-            float dir = 0.0f;
-            if (tt != 0.0f) {
-                const float mag = atanf_c(tt);
-                dir = atan2f_c(gx, gy);
-                im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
+        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixels
+        const float* ctr = plane + yy * IMG_W;
+        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1;
+        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1;
+        const float4 cu = *reinterpret_cast<const float4*>(up + x0);
+        const float4 cd = *reinterpret_cast<const float4*>(dn + x0);
+        const float4 cc = *reinterpret_cast<const float4*>(ctr + x0);
+        const float c6[6] = {ctr[max(x0 - 1, 0)], cc.x, cc.y, cc.z, cc.w, ctr[min(x0 + 4, IMG_W - 1)]};
+        const float u4[4] = {cu.x, cu.y, cu.z, cu.w}, d4[4] = {cd.x, cd.y, cd.z, cd.w};
+        float gx[4], gy[4], tt[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float top = __fmul_rn(u4[i], p.inv_pixmm), bot = __fmul_rn(d4[i], p.inv_pixmm);
+            const float lef = __fmul_rn(c6[i], p.inv_pixmm), rig = __fmul_rn(c6[i + 2], p.inv_pixmm);
+            gx[i] = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
+            gy[i] = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
+        }
+        if (x0 == 0) { gx[0] = gx[1]; gy[0] = gy[1]; }                 // column 0 samples column 1
+        if (x0 == IMG_W - 4) { gx[3] = gx[2]; gy[3] = gy[2]; }         // column 319 samples column 318
+        // tt = sqrt(s2) is zero iff s2 is zero: flat pixels (exact zero gradient) need no sqrt / atan
+        float s2[4];
+        bool nonflat = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
+            nonflat |= s2[i] != 0.0f;
+        }
+        const bool warp_nonflat = __any_sync(0xffffffffu, nonflat) && !(p.dbg & 4);
+        const size_t pix = (size_t)row * IMG_W + x0;
+        const float4* bg4 = reinterpret_cast<const float4*>(bg_half + pix * 3);
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, b2 = b0;
+        if (!(p.dbg & 2)) { b0 = __ldg(bg4); b1 = __ldg(bg4 + 1); b2 = __ldg(bg4 + 2); }
+        const float bgv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+        float o[12];
+        const float yf = __fmul_rn((float)gy_, p.fy);
+        const float f1 = __fmul_rn(yf, yf);
+        const float4* pp[4];
+        if (warp_nonflat) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                tt[i] = __fsqrt_rn(s2[i]);
+                const float mag = atanf_c(tt[i]);
+                const float dir = (tt[i] != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f;
+                int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
+                int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
+                im = min(max(im, 0), p.nb - 1);
+                id = min(max(id, 0), p.nb - 1);
+                pp[i] = p.poly + (size_t)(im * p.nb + id) * 5; // [nb][nb][3][6] padded to 20 floats
             }
-            id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
         }
-        im = min(max(im, 0), p.nb - 1);
-        id = min(max(id, 0), p.nb - 1);
-        const float4* pp = p.poly + ((size_t)im * p.nb + id) * 5; // [nb][nb][3][6] padded to 20 floats
-        const float xf = __fmul_rn((float)x, p.fx), yf = __fmul_rn((float)gy_, p.fy);
-        const float f0 = __fmul_rn(xf, xf), f1 = __fmul_rn(yf, yf), f2 = __fmul_rn(xf, yf);
-        float c[20];
 #pragma unroll
-        for (int e = 0; e < 5; ++e) {
-            const float4 t = __ldg(pp + e);
-            c[4 * e] = t.x; c[4 * e + 1] = t.y; c[4 * e + 2] = t.z; c[4 * e + 3] = t.w;
+        for (int i = 0; i < 4; ++i) {
+            float cf[18];
+            if (warp_nonflat) {
+                const float4 a0 = __ldg(pp[i]), a1 = __ldg(pp[i] + 1), a2 = __ldg(pp[i] + 2), a3 = __ldg(pp[i] + 3),
+                             a4 = __ldg(pp[i] + 4);
+                const float t20[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
+                                       a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int k = 0; k < 18; ++k) cf[k] = t20[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 18; ++k) cf[k] = cflat[k];
+            }
+            const float xf = __fmul_rn((float)(x0 + i), p.fx);
+            const float f0 = __fmul_rn(xf, xf), f2 = __fmul_rn(xf, yf);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float* pc = cf + 6 * ch;
+                float s = pc[5];
+                s = __fmaf_rn(pc[4], yf, s);
+                s = __fmaf_rn(pc[3], xf, s);
+                s = __fmaf_rn(pc[2], f2, s);
+                s = __fmaf_rn(pc[1], f1, s);
+                s = __fmaf_rn(pc[0], f0, s);
+                s = __fadd_rn(s, bgv[3 * i + ch]);
+                o[3 * i + ch] = fminf(fmaxf(s, 0.0f), 1.0f);
+            }
         }
-        const size_t pix = (size_t)row * IMG_W + x;
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float* pc = c + 6 * ch;
-            float s = pc[5];
-            s = __fmaf_rn(pc[4], yf, s);
-            s = __fmaf_rn(pc[3], xf, s);
-            s = __fmaf_rn(pc[2], f2, s);
-            s = __fmaf_rn(pc[1], f1, s);
-            s = __fmaf_rn(pc[0], f0, s);
-            s = __fadd_rn(s, __ldg(bg_half + pix * 3 + ch));
-            s = fminf(fmaxf(s, 0.0f), 1.0f);
-            rgb_half[pix * 3 + ch] = s;
+        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
+        if (!(p.dbg & 1) || o[0] < -1.0f) {
+            o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+            o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+            o4[2] = make_float4(o[8], o[9], o[10], o[11]);
         }
     }
+    __syncthreads();
+    TX_TICK(33);
 }
 
 cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)

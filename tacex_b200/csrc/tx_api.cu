@@ -3,6 +3,7 @@
 #include <math.h>
 #include <new>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -40,6 +41,10 @@ struct tx_handle {
     int* d_traj_len = nullptr;
     float* d_markers = nullptr;
     int host_cap = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined host path
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    long long* d_ticks = nullptr; // not owned
+    int dbg = 0;
 };
 
 static std::string g_create_err;
@@ -160,6 +165,10 @@ extern "C" void tx_destroy(tx_handle* h)
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
     cudaFree(h->d_traj_len); cudaFree(h->d_markers);
+    for (auto e : h->ev_in) cudaEventDestroy(e);
+    for (auto e : h->ev_done) cudaEventDestroy(e);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
 }
 
@@ -256,6 +265,8 @@ extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* pres
     a.inv_xbin = (float)(1.0 / (0.5 * M_PI / (c.num_bins - 1)));
     a.inv_ybin = (float)(1.0 / (2.0 * M_PI / (c.num_bins - 1)));
     a.nb = c.num_bins;
+    a.ticks = h->d_ticks;
+    a.dbg = h->dbg;
     TX_CUDA(h, launch_taxim(a, N, h->stream));
     h->aux_valid_n = h->M > 0 ? N : 0;
     h->ctr.render_calls++;
@@ -300,6 +311,16 @@ extern "C" int tx_fots_markers(tx_handle* h, const float* press_mm, const float*
     return TX_OK;
 }
 
+extern "C" int tx_debug_set_ticks(tx_handle* h, long long* ticks)
+{
+    if (!h) return TX_ERR_INVALID_ARG;
+    h->d_ticks = ticks;
+    h->dbg = 0;
+    const char* e = getenv("TX_DEBUG_FLAGS"); // profiling experiments (tools/phase_times.py); never set in production
+    if (e) h->dbg = atoi(e);
+    return TX_OK;
+}
+
 extern "C" int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my)
 {
     if (!h || !mx || !my) return TX_ERR_INVALID_ARG;
@@ -335,19 +356,51 @@ extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const flo
         if (h->M > 0) TX_CUDA(h, cudaMalloc(&h->d_markers, sizeof(float) * 4 * h->M * cap));
         h->host_cap = (int)cap;
     }
-    TX_CUDA(h, cudaMemcpyAsync(h->d_hm, height_mm_host, sizeof(float) * HW * N, cudaMemcpyHostToDevice, h->stream));
-    int rc = tx_render(h, h->d_hm, nullptr, N, h->d_rgb, h->d_depth, nullptr, nullptr);
-    if (rc != TX_OK) return rc;
-    if (markers_host) {
-        TX_CUDA(h, cudaMemcpyAsync(h->d_theta, theta_host, sizeof(float) * N, cudaMemcpyHostToDevice, h->stream));
-        rc = tx_fots_markers(h, h->d_depth, h->d_theta, N, h->d_traj0, h->d_traj_len, h->d_markers);
-        if (rc != TX_OK) return rc;
-        TX_CUDA(h, cudaMemcpyAsync(markers_host, h->d_markers, sizeof(float) * 4 * h->M * N, cudaMemcpyDeviceToHost,
-                                   h->stream));
+    // Pipelined over chunks of envs: H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap
+    // (three streams, PCIe is full duplex). The chunks are disjoint slices of the same device buffers.
+    const int CH = 256;
+    const int nch = (N + CH - 1) / CH;
+    if (!h->s_in) {
+        TX_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        TX_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     }
-    TX_CUDA(h, cudaMemcpyAsync(rgb_host, h->d_rgb, sizeof(float) * HW * 3 * N, cudaMemcpyDeviceToHost, h->stream));
-    if (depth_host)
-        TX_CUDA(h, cudaMemcpyAsync(depth_host, h->d_depth, sizeof(float) * N, cudaMemcpyDeviceToHost, h->stream));
+    while ((int)h->ev_in.size() < nch) {
+        cudaEvent_t a, b;
+        TX_CUDA(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        TX_CUDA(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_in.push_back(a);
+        h->ev_done.push_back(b);
+    }
+    // the copy streams must not run ahead of work already queued on the caller's stream
+    TX_CUDA(h, cudaEventRecord(h->ev_done[0], h->stream));
+    TX_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done[0], 0));
+    TX_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_done[0], 0));
+    for (int c = 0; c < nch; ++c) {
+        const int n0 = c * CH, n = (N - n0 < CH) ? N - n0 : CH;
+        TX_CUDA(h, cudaMemcpyAsync(h->d_hm + HW * n0, height_mm_host + HW * n0, sizeof(float) * HW * n,
+                                   cudaMemcpyHostToDevice, h->s_in));
+        if (markers_host)
+            TX_CUDA(h, cudaMemcpyAsync(h->d_theta + n0, theta_host + n0, sizeof(float) * n, cudaMemcpyHostToDevice, h->s_in));
+        TX_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
+        TX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+        int rc = tx_render(h, h->d_hm + HW * n0, nullptr, n, h->d_rgb + HW * 3 * n0, h->d_depth + n0, nullptr, nullptr);
+        if (rc != TX_OK) return rc;
+        if (markers_host) {
+            rc = tx_fots_markers(h, h->d_depth + n0, h->d_theta + n0, n, h->d_traj0 + 4 * n0, h->d_traj_len + n0,
+                                 h->d_markers + (size_t)4 * h->M * n0);
+            if (rc != TX_OK) return rc;
+        }
+        TX_CUDA(h, cudaEventRecord(h->ev_done[c], h->stream));
+        TX_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_done[c], 0));
+        TX_CUDA(h, cudaMemcpyAsync(rgb_host + HW * 3 * n0, h->d_rgb + HW * 3 * n0, sizeof(float) * HW * 3 * n,
+                                   cudaMemcpyDeviceToHost, h->s_out));
+        if (markers_host)
+            TX_CUDA(h, cudaMemcpyAsync(markers_host + (size_t)4 * h->M * n0, h->d_markers + (size_t)4 * h->M * n0,
+                                       sizeof(float) * 4 * h->M * n, cudaMemcpyDeviceToHost, h->s_out));
+        if (depth_host)
+            TX_CUDA(h, cudaMemcpyAsync(depth_host + n0, h->d_depth + n0, sizeof(float) * n, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    TX_CUDA(h, cudaStreamSynchronize(h->s_out));
     TX_CUDA(h, cudaStreamSynchronize(h->stream));
     return TX_OK;
 }

@@ -11,45 +11,35 @@
 namespace tx {
 
 // ---- canonical atan / atan2 (Cephes-style polynomial) ------------------------------
+// Branch-free forms (one IEEE division each); bit-identical to the branchy CPU restatement:
+//   |x| > tan(3pi/8): t = (-1)/x   == -(1/x)        |x| > tan(pi/8): t = (x-1)/(x+1)        else: t = x/1 == x
 __device__ __forceinline__ float atanf_c(float xx)
 {
-    float x = fabsf(xx);
-    float y;
-    if (x > 2.414213562373095f) {
-        y = 1.5707963267948966f;
-        x = -__fdiv_rn(1.0f, x);
-    } else if (x > 0.4142135623730950f) {
-        y = 0.7853981633974483f;
-        x = __fdiv_rn(__fadd_rn(x, -1.0f), __fadd_rn(x, 1.0f));
-    } else {
-        y = 0.0f;
-    }
-    float z = __fmul_rn(x, x);
+    const float x = fabsf(xx);
+    const bool big = x > 2.414213562373095f;
+    const bool mid = x > 0.4142135623730950f;
+    const float num = big ? -1.0f : (mid ? __fadd_rn(x, -1.0f) : x);
+    const float den = big ? x : (mid ? __fadd_rn(x, 1.0f) : 1.0f);
+    const float y0 = big ? 1.5707963267948966f : (mid ? 0.7853981633974483f : 0.0f);
+    const float t = __fdiv_rn(num, den);
+    const float z = __fmul_rn(t, t);
     float p = 8.05374449538e-2f;
     p = __fmaf_rn(p, z, -1.38776856032e-1f);
     p = __fmaf_rn(p, z, 1.99777106478e-1f);
     p = __fmaf_rn(p, z, -3.33329491539e-1f);
     p = __fmul_rn(p, z);
-    p = __fmaf_rn(p, x, x);
-    y = __fadd_rn(y, p);
+    p = __fmaf_rn(p, t, t);
+    const float y = __fadd_rn(y0, p);
     return (xx < 0.0f) ? -y : y;
 }
 
+// atan2 for (y, x) not both zero. x == 0 gives y/x = +-inf and atanf_c(+-inf) = +-pi/2 exactly as the explicit case.
 __device__ __forceinline__ float atan2f_c(float y, float x)
 {
     const float PI_F = 3.14159265358979323846f;
-    const float PIO2_F = 1.5707963267948966f;
-    if (x == 0.0f) {
-        if (y > 0.0f) return PIO2_F;
-        if (y < 0.0f) return -PIO2_F;
-        return 0.0f;
-    }
-    float z = atanf_c(__fdiv_rn(y, x));
-    if (x < 0.0f) {
-        if (y < 0.0f) return __fadd_rn(z, -PI_F);
-        return __fadd_rn(z, PI_F);
-    }
-    return z;
+    const float z = atanf_c(__fdiv_rn(y, x));
+    const float adj = (y < 0.0f) ? -PI_F : PI_F;
+    return (x < 0.0f) ? __fadd_rn(z, adj) : z;
 }
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) -----------------------------------------------------------------

@@ -9,7 +9,10 @@ namespace tx {
 constexpr int IMG_H = 240;
 constexpr int IMG_W = 320;
 constexpr int HALF_H = 120;   // rows owned by one CTA of the 2-CTA cluster
-constexpr int NTHREADS = 384; // 12 warps
+#ifndef TX_NTHREADS
+#define TX_NTHREADS 480
+#endif
+constexpr int NTHREADS = TX_NTHREADS; // 15 warps (12 warps = 384 is the other supported value)
 constexpr int NWARPS = NTHREADS / 32;
 
 struct TaximArgs {
@@ -32,6 +35,8 @@ struct TaximArgs {
     int M;
     float inv_pixmm, sy, sx, fx, fy, contact_scale, gelpad_h, gelpad_min, inv_xbin, inv_ybin;
     int nb;
+    int dbg;          // profiling experiments only (0 in production): bit0 skip RGB stores, bit1 skip bg loads, bit2 force flat path
+    long long* ticks; // optional [2N][40] phase clock stamps (profiling builds of the host call only)
 };
 
 struct FotsArgs {

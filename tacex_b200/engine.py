@@ -150,6 +150,10 @@ class TactileEngine:
         self._check(self.lib.tx_fots_markers(self.h, _ptr(press), _ptr(theta), N, _ptr(traj0), _ptr(traj_len), _ptr(out)))
         return out
 
+    def set_phase_ticks(self, ticks: torch.Tensor | None) -> None:
+        """Profiling: int64 device tensor (2*N, 40) receiving per-CTA phase clock stamps, or None to disable."""
+        self._check(self.lib.tx_debug_set_ticks(self.h, _ptr(ticks)))
+
     def step_host(self, hm_host: torch.Tensor, rgb_host: torch.Tensor, depth_host: torch.Tensor | None = None,
                   theta_host: torch.Tensor | None = None, markers_host: torch.Tensor | None = None) -> None:
         """End-to-end call on HOST buffers (H2D + fused path + D2H inside), what bench.py's ``e2e`` times."""
