@@ -1,0 +1,669 @@
+/*
+ * oracle/fem_canon.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Float64 CPU restatement of the gel FEM substep of the reference (libuipc CUDA backend driven by TacEx):
+ *   Newton / line-search driver   ref: source/tacex_uipc/libuipc/src/backends/cuda/engine/sim_engine_do_advance.cu:200-360
+ *   BDF1 predict / update / kinetic ref: .../finite_element/bdf/fem_bdf1_time_integrator.cu:19-77,
+ *                                       .../finite_element/bdf/finite_element_bdf1_kinetic.cu:17-82
+ *   Stable Neo-Hookean 3D          ref: .../finite_element/constitutions/stable_neo_hookean_3d.cu:68-165 and
+ *                                       .../constitutions/sym/stable_neo_hookean_3d.inl (energy, dE/dF, d2E/dF2)
+ *   F, dFdx, Dm^-1, rest "volume"  ref: .../finite_element/fem_utils.cu:50-120, finite_element_method.cu:957-982
+ *   make_spd (clamp negative eigenvalues) ref: .../utils/make_spd.h:7-19
+ *   soft position constraint       ref: .../finite_element/constraints/soft_position_constraint.cu:99-179,
+ *                                       .../animator/global_animator.cu:64-70 (substep ratio)
+ *   IPC barrier (D = squared distance) ref: .../contact_system/contact_models/sym/codim_ipc_contact.inl,
+ *                                       vertex-vs-implicit-surface form: .../ipc_vertex_half_plane_normal_contact.cu,
+ *                                       .../ipc_vertex_half_plane_contact_function.h:29-58
+ *   PCG + 3x3 block-Jacobi         ref: .../linear_system/linear_pcg.cu:45-140, .../finite_element/fem_diag_preconditioner.cu:112-164
+ *   Newton tolerance               ref: .../newton_tolerance/max_translation_checker.cu:25-50
+ *   TacEx-side constants           ref: source/tacex_uipc/tacex_uipc/sim/uipc_sim.py:32-131, objects/uipc_object.py:442-470,
+ *                                       sim/uipc_attachments.py:118-142
+ *
+ * Re-design stated in DESIGN.md: the indenter is a PRESCRIBED rigid analytic body (sphere / oriented box), so contact is
+ * the reference's vertex-vs-implicit-surface barrier generalised from a half-plane to a signed-distance function, the
+ * broad phase (LBVH) disappears, and the CCD step bound is the conservative-advancement bound of a 1-Lipschitz SDF.
+ * Friction is not restated yet.
+ *
+ * PARITY UNPINNED: libuipc cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it has no CPU
+ * backend) and its tests hold no golden positions for this path. This restatement is pinned only
+ * by its own known-answer tests (finite differences, dense solves, eigh) under tests/.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this library.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    int V, T, A, S; /* vertices, tets, attached (soft-constrained) vertices, contact (surface) vertices */
+    double dt;
+    double gravity[3];
+    double mu, lambda;      /* Lame parameters */
+    double attach_strength; /* strength ratio s of the soft position constraint */
+    double d_hat, kappa;    /* barrier activation distance [m], stiffness [Pa] */
+    int newton_max_iter;
+    double velocity_tol; /* abs tol = velocity_tol * dt */
+    double pcg_tol_rate;
+    int pcg_max_iter_ratio;
+    int ls_max_iter;
+    int substep;
+} fem_cfg;
+
+typedef struct {
+    int type;         /* 0 sphere, 1 oriented box */
+    double c[3];      /* centre (world) */
+    double R[9];      /* rotation, row-major, world = R * local */
+    double h[3];      /* half extents (box) or h[0] = radius (sphere) */
+} fem_indenter;
+
+typedef struct {
+    int converged, newton_iters, pcg_iters, ls_halvings;
+    double min_dist, last_res, energy;
+} fem_stats;
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* small dense helpers                                                                                                */
+static double det3(const double* F) /* column-major vec: F(a,b) = F[3*b+a] */
+{
+    return F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
+}
+
+/* cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major), n <= 12. A is destroyed. */
+static void jacobi_evd(int n, double* A, double* w, double* Vv)
+{
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Vv[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                if (i != j) off += A[i * n + j] * A[i * n + j];
+                else diag += A[i * n + j] * A[i * n + j];
+            }
+        if (off <= 1e-30 * (diag + 1e-300)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) { /* rotate columns p, q */
+                    double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq;
+                    A[k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) { /* rotate rows p, q */
+                    double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk;
+                    A[q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    double vkp = Vv[k * n + p], vkq = Vv[k * n + q];
+                    Vv[k * n + p] = c * vkp - s * vkq;
+                    Vv[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+/* make_spd: H <- V max(L, 0) V^T. Fast path: an LDL^T factorisation with all pivots > 0 proves H is already PD. */
+void fem_spd_project(int n, double* H)
+{
+    double L[144], D[12];
+    int pd = 1;
+    for (int j = 0; j < n && pd; ++j) {
+        double d = H[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k] * D[k];
+        if (!(d > 0.0)) { pd = 0; break; }
+        D[j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = H[i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k] * D[k];
+            L[i * n + j] = s / d;
+        }
+    }
+    if (pd) return;
+    double A[144], w[12], Vv[144];
+    memcpy(A, H, sizeof(double) * n * n);
+    jacobi_evd(n, A, w, Vv);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Vv[i * n + k] * (w[k] < 0.0 ? 0.0 : w[k]) * Vv[j * n + k];
+            H[i * n + j] = s;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Stable Neo-Hookean: Psi = lambda/2 (J-1)^2 - mu (J-1) + mu/2 (I_C - 3) + mu^2/lambda^2  (sym/stable_neo_hookean_3d.inl) */
+void fem_snh(const double* F, double mu, double lambda, double* E, double* g /*9*/, double* H /*81 row-major*/)
+{
+    const double J = det3(F);
+    double IC = 0.0;
+    for (int i = 0; i < 9; ++i) IC += F[i] * F[i];
+    if (E) *E = 0.5 * lambda * (J - 1.0) * (J - 1.0) - mu * (J - 1.0) + 0.5 * mu * (IC - 3.0) + mu * mu / (lambda * lambda);
+    /* dJ/dF = cofactor: columns are cross products of the other two columns (fem_utils.cu:50-52) */
+    double gJ[9];
+    const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
+    gJ[0] = f1[1] * f2[2] - f1[2] * f2[1]; gJ[1] = f1[2] * f2[0] - f1[0] * f2[2]; gJ[2] = f1[0] * f2[1] - f1[1] * f2[0];
+    gJ[3] = f2[1] * f0[2] - f2[2] * f0[1]; gJ[4] = f2[2] * f0[0] - f2[0] * f0[2]; gJ[5] = f2[0] * f0[1] - f2[1] * f0[0];
+    gJ[6] = f0[1] * f1[2] - f0[2] * f1[1]; gJ[7] = f0[2] * f1[0] - f0[0] * f1[2]; gJ[8] = f0[0] * f1[1] - f0[1] * f1[0];
+    const double c = lambda * (J - 1.0) - mu;
+    if (g)
+        for (int i = 0; i < 9; ++i) g[i] = mu * F[i] + c * gJ[i];
+    if (H) {
+        /* H = mu I + c * d2J/dF2 + lambda gJ gJ^T ; d2J/dF2 blocks are cross-product matrices of the columns */
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) H[i * 9 + j] = lambda * gJ[i] * gJ[j] + (i == j ? mu : 0.0);
+        /* block (col a, col b) of d2J/dF2: d(gJ_col_a)/d(f_b). gJ0 = f1 x f2, gJ1 = f2 x f0, gJ2 = f0 x f1.
+           d(u x v)/dv = [u]_x , d(u x v)/du = -[v]_x */
+        const double* f[3] = {f0, f1, f2};
+        for (int a = 0; a < 3; ++a) {
+            int b1 = (a + 1) % 3, b2 = (a + 2) % 3; /* gJ_a = f_b1 x f_b2 */
+            /* d gJ_a / d f_b2 = [f_b1]_x ; d gJ_a / d f_b1 = -[f_b2]_x */
+            const double* u = f[b1];
+            const double* v = f[b2];
+            double Ux[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
+            double Vx[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+            for (int r = 0; r < 3; ++r)
+                for (int s = 0; s < 3; ++s) {
+                    H[(3 * a + r) * 9 + (3 * b2 + s)] += c * Ux[r * 3 + s];
+                    H[(3 * a + r) * 9 + (3 * b1 + s)] -= c * Vx[r * 3 + s];
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* IPC barrier on the squared distance D, thickness xi = 0 (sym/codim_ipc_contact.inl) */
+void fem_barrier(double D, double d_hat, double kappa, double* B, double* dB, double* ddB)
+{
+    const double D0 = d_hat * d_hat;
+    if (!(D < D0)) { if (B) *B = 0; if (dB) *dB = 0; if (ddB) *ddB = 0; return; }
+    const double t = D - D0, lg = log(D / D0);
+    if (B) *B = -kappa * t * t * lg;
+    if (dB) *dB = -kappa * (2.0 * t * lg + t * t / D);
+    if (ddB) *ddB = -kappa * (2.0 * lg + 4.0 * t / D - t * t / (D * D));
+}
+
+/* signed distance of a world point to the indenter, unit normal n = grad d, Hd = hessian of d (row-major) */
+void fem_indenter_sdf(const fem_indenter* I, const double* x, double* d, double* n, double* Hd)
+{
+    double p[3], q[3];
+    for (int i = 0; i < 3; ++i) q[i] = x[i] - I->c[i];
+    for (int i = 0; i < 3; ++i) p[i] = I->R[0 * 3 + i] * q[0] + I->R[1 * 3 + i] * q[1] + I->R[2 * 3 + i] * q[2]; /* R^T q */
+    double nl[3] = {0, 0, 0}, Hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (I->type == 0) {
+        double r = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        *d = r - I->h[0];
+        for (int i = 0; i < 3; ++i) nl[i] = p[i] / r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Hl[i * 3 + j] = ((i == j ? 1.0 : 0.0) - nl[i] * nl[j]) / r;
+    } else {
+        double u[3], sgn[3], qq[3];
+        int act[3], nact = 0;
+        for (int i = 0; i < 3; ++i) {
+            sgn[i] = p[i] < 0 ? -1.0 : 1.0;
+            qq[i] = fabs(p[i]) - I->h[i];
+            act[i] = qq[i] > 0.0;
+            u[i] = act[i] ? qq[i] : 0.0;
+            nact += act[i];
+        }
+        if (nact > 0) {
+            double r = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            *d = r;
+            for (int i = 0; i < 3; ++i) nl[i] = sgn[i] * u[i] / r;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    Hl[i * 3 + j] = (act[i] && act[j]) ? ((i == j ? 1.0 : 0.0) - nl[i] * nl[j]) / r : 0.0;
+        } else { /* inside: distance to the nearest face (negative) */
+            int k = 0;
+            for (int i = 1; i < 3; ++i)
+                if (qq[i] > qq[k]) k = i;
+            *d = qq[k];
+            nl[k] = sgn[k];
+        }
+    }
+    for (int i = 0; i < 3; ++i) n[i] = I->R[i * 3 + 0] * nl[0] + I->R[i * 3 + 1] * nl[1] + I->R[i * 3 + 2] * nl[2];
+    if (Hd) { /* R Hl R^T */
+        double T[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += I->R[i * 3 + k] * Hl[k * 3 + j];
+                T[i * 3 + j] = s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += T[i * 3 + k] * I->R[j * 3 + k];
+                Hd[i * 3 + j] = s;
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* mesh precomputation: Dm^-1, elastic rest volume (det Dm, the reference's quirk Q10, or det/6), lumped mass (true volume) */
+void fem_precompute(int V, int T, const double* X, const int32_t* tets, double density, int rest_volume_det,
+                    double* Dm_inv /*[T][9] row-major*/, double* vol /*[T]*/, double* mass /*[V]*/)
+{
+    for (int i = 0; i < V; ++i) mass[i] = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const int32_t* e = tets + 4 * t;
+        double Dm[9]; /* row-major, columns = X1-X0, X2-X0, X3-X0 */
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 3; ++k) Dm[a * 3 + k] = X[3 * e[k + 1] + a] - X[3 * e[0] + a];
+        double det = Dm[0] * (Dm[4] * Dm[8] - Dm[5] * Dm[7]) - Dm[1] * (Dm[3] * Dm[8] - Dm[5] * Dm[6]) +
+                     Dm[2] * (Dm[3] * Dm[7] - Dm[4] * Dm[6]);
+        double* B = Dm_inv + 9 * t;
+        B[0] = (Dm[4] * Dm[8] - Dm[5] * Dm[7]) / det; B[1] = (Dm[2] * Dm[7] - Dm[1] * Dm[8]) / det; B[2] = (Dm[1] * Dm[5] - Dm[2] * Dm[4]) / det;
+        B[3] = (Dm[5] * Dm[6] - Dm[3] * Dm[8]) / det; B[4] = (Dm[0] * Dm[8] - Dm[2] * Dm[6]) / det; B[5] = (Dm[2] * Dm[3] - Dm[0] * Dm[5]) / det;
+        B[6] = (Dm[3] * Dm[7] - Dm[4] * Dm[6]) / det; B[7] = (Dm[1] * Dm[6] - Dm[0] * Dm[7]) / det; B[8] = (Dm[0] * Dm[4] - Dm[1] * Dm[3]) / det;
+        vol[t] = rest_volume_det ? det : det / 6.0;
+        for (int k = 0; k < 4; ++k) mass[e[k]] += density * (det / 6.0) / 4.0;
+    }
+}
+
+/* W (4x3): dF_ab/dx_(v,c) = delta_ac W[v][b] ; W[v] = row v-1 of Dm^-1 for v = 1..3, W[0] = -(sum of the rows) */
+static void tet_W(const double* B, double W[4][3])
+{
+    for (int b = 0; b < 3; ++b) {
+        W[1][b] = B[0 * 3 + b];
+        W[2][b] = B[1 * 3 + b];
+        W[3][b] = B[2 * 3 + b];
+        W[0][b] = -(B[0 * 3 + b] + B[1 * 3 + b] + B[2 * 3 + b]);
+    }
+}
+
+static void tet_F(const double* x, const int32_t* e, const double W[4][3], double* F /*col-major vec*/)
+{
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+            double s = 0;
+            for (int v = 0; v < 4; ++v) s += x[3 * e[v] + a] * W[v][b];
+            F[3 * b + a] = s;
+        }
+}
+
+typedef struct {
+    const fem_cfg* cfg;
+    const int32_t* tets;
+    const double *Dm_inv, *vol, *mass;
+    const int32_t *attach, *surf;
+    const double* aim;   /* [A][3] */
+    const double* x_prev;
+    const double* x_tilde;
+    double ratio;        /* animation substep ratio */
+    fem_indenter ind;    /* current (interpolated) indenter */
+} fem_ctx;
+
+static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
+{
+    const fem_cfg* g = c->cfg;
+    double E = 0.0;
+    const double dt2 = g->dt * g->dt;
+    for (int i = 0; i < g->V; ++i) {
+        double s = 0;
+        for (int a = 0; a < 3; ++a) { double d = x[3 * i + a] - c->x_tilde[3 * i + a]; s += d * d; }
+        E += 0.5 * c->mass[i] * s;
+    }
+    for (int t = 0; t < g->T; ++t) {
+        double W[4][3], F[9], e;
+        tet_W(c->Dm_inv + 9 * t, W);
+        tet_F(x, c->tets + 4 * t, W, F);
+        fem_snh(F, g->mu, g->lambda, &e, 0, 0);
+        E += dt2 * c->vol[t] * e;
+    }
+    for (int k = 0; k < g->A; ++k) {
+        int i = c->attach[k];
+        double s = 0;
+        for (int a = 0; a < 3; ++a) {
+            double aimx = c->x_prev[3 * i + a] + (c->aim[3 * k + a] - c->x_prev[3 * i + a]) * c->ratio;
+            double d = x[3 * i + a] - aimx;
+            s += d * d;
+        }
+        E += 0.5 * g->attach_strength * c->mass[i] * s;
+    }
+    double md = 1e300;
+    for (int k = 0; k < g->S; ++k) {
+        int i = c->surf[k];
+        double d, n[3], B;
+        fem_indenter_sdf(&c->ind, x + 3 * i, &d, n, 0);
+        if (d < md) md = d;
+        if (d <= 0.0) { E = INFINITY; continue; }
+        fem_barrier(d * d, g->d_hat, g->kappa * dt2, &B, 0, 0);
+        E += B;
+    }
+    if (min_dist) *min_dist = md;
+    return E;
+}
+
+/* gradient G [V][3], per-tet projected H9 (scaled by dt^2 vol) [T][81], diagonal 3x3 blocks Dg [V][9] (row-major) and
+   contact blocks Hc [S][9] */
+static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, double* Dg, double* Hc)
+{
+    const fem_cfg* g = c->cfg;
+    const double dt2 = g->dt * g->dt;
+    memset(G, 0, sizeof(double) * 3 * g->V);
+    memset(Dg, 0, sizeof(double) * 9 * g->V);
+    for (int i = 0; i < g->V; ++i) {
+        for (int a = 0; a < 3; ++a) {
+            G[3 * i + a] += c->mass[i] * (x[3 * i + a] - c->x_tilde[3 * i + a]);
+            Dg[9 * i + 4 * a] += c->mass[i];
+        }
+    }
+    for (int t = 0; t < g->T; ++t) {
+        const int32_t* e = c->tets + 4 * t;
+        double W[4][3], F[9], dEdF[9];
+        double* H = H9 + 81 * t;
+        tet_W(c->Dm_inv + 9 * t, W);
+        tet_F(x, e, W, F);
+        fem_snh(F, g->mu, g->lambda, 0, dEdF, H);
+        const double s = dt2 * c->vol[t];
+        for (int i = 0; i < 9; ++i) dEdF[i] *= s;
+        for (int i = 0; i < 81; ++i) H[i] *= s;
+        fem_spd_project(9, H);
+        for (int v = 0; v < 4; ++v)
+            for (int a = 0; a < 3; ++a) {
+                double sum = 0;
+                for (int b = 0; b < 3; ++b) sum += dEdF[3 * b + a] * W[v][b];
+                G[3 * e[v] + a] += sum;
+            }
+        /* diagonal block of dFdx^T H dFdx for vertex v: D_ac = sum_{b,b'} W[v][b] H[(3b+a),(3b'+c)] W[v][b'] */
+        for (int v = 0; v < 4; ++v)
+            for (int a = 0; a < 3; ++a)
+                for (int cc = 0; cc < 3; ++cc) {
+                    double sum = 0;
+                    for (int b = 0; b < 3; ++b)
+                        for (int b2 = 0; b2 < 3; ++b2) sum += W[v][b] * H[(3 * b + a) * 9 + (3 * b2 + cc)] * W[v][b2];
+                    Dg[9 * e[v] + 3 * a + cc] += sum;
+                }
+    }
+    for (int k = 0; k < g->A; ++k) {
+        int i = c->attach[k];
+        const double sm = g->attach_strength * c->mass[i];
+        for (int a = 0; a < 3; ++a) {
+            double aimx = c->x_prev[3 * i + a] + (c->aim[3 * k + a] - c->x_prev[3 * i + a]) * c->ratio;
+            G[3 * i + a] += sm * (x[3 * i + a] - aimx);
+            Dg[9 * i + 4 * a] += sm;
+        }
+    }
+    for (int k = 0; k < g->S; ++k) {
+        int i = c->surf[k];
+        double d, n[3], Hd[9], dB, ddB;
+        double* Hk = Hc + 9 * k;
+        memset(Hk, 0, sizeof(double) * 9);
+        fem_indenter_sdf(&c->ind, x + 3 * i, &d, n, Hd);
+        if (!(d * d < g->d_hat * g->d_hat) || d <= 0.0) continue;
+        fem_barrier(d * d, g->d_hat, g->kappa * dt2, 0, &dB, &ddB);
+        double dD[3];
+        for (int a = 0; a < 3; ++a) dD[a] = 2.0 * d * n[a];
+        for (int a = 0; a < 3; ++a) G[3 * i + a] += dB * dD[a];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Hk[3 * a + b] = ddB * dD[a] * dD[b] + dB * 2.0 * (n[a] * n[b] + d * Hd[3 * a + b]);
+        fem_spd_project(3, Hk);
+        for (int j = 0; j < 9; ++j) Dg[9 * i + j] += Hk[j];
+    }
+}
+
+static void apply_A(const fem_ctx* c, const double* H9, const double* Hc, const double* p, double* y)
+{
+    const fem_cfg* g = c->cfg;
+    for (int i = 0; i < g->V; ++i)
+        for (int a = 0; a < 3; ++a) y[3 * i + a] = c->mass[i] * p[3 * i + a];
+    for (int t = 0; t < g->T; ++t) {
+        const int32_t* e = c->tets + 4 * t;
+        double W[4][3], P[9], Q[9];
+        tet_W(c->Dm_inv + 9 * t, W);
+        tet_F(p, e, W, P); /* dFdx p */
+        const double* H = H9 + 81 * t;
+        for (int i = 0; i < 9; ++i) {
+            double s = 0;
+            for (int j = 0; j < 9; ++j) s += H[i * 9 + j] * P[j];
+            Q[i] = s;
+        }
+        for (int v = 0; v < 4; ++v)
+            for (int a = 0; a < 3; ++a) {
+                double s = 0;
+                for (int b = 0; b < 3; ++b) s += Q[3 * b + a] * W[v][b];
+                y[3 * e[v] + a] += s;
+            }
+    }
+    for (int k = 0; k < g->A; ++k) {
+        int i = c->attach[k];
+        for (int a = 0; a < 3; ++a) y[3 * i + a] += g->attach_strength * c->mass[i] * p[3 * i + a];
+    }
+    for (int k = 0; k < g->S; ++k) {
+        int i = c->surf[k];
+        const double* Hk = Hc + 9 * k;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) y[3 * i + a] += Hk[3 * a + b] * p[3 * i + b];
+    }
+}
+
+static void inv3(const double* M, double* R)
+{
+    double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    R[0] = (M[4] * M[8] - M[5] * M[7]) / det; R[1] = (M[2] * M[7] - M[1] * M[8]) / det; R[2] = (M[1] * M[5] - M[2] * M[4]) / det;
+    R[3] = (M[5] * M[6] - M[3] * M[8]) / det; R[4] = (M[0] * M[8] - M[2] * M[6]) / det; R[5] = (M[2] * M[3] - M[0] * M[5]) / det;
+    R[6] = (M[3] * M[7] - M[4] * M[6]) / det; R[7] = (M[1] * M[6] - M[0] * M[7]) / det; R[8] = (M[0] * M[4] - M[1] * M[3]) / det;
+}
+
+/* PCG with 3x3 block-Jacobi, x0 = 0, stop when |r.z| <= tol_rate * |r0.z0| (linear_pcg.cu:45-140) */
+static int pcg(const fem_ctx* c, const double* H9, const double* Hc, const double* Dg, const double* b, double* xs,
+               double* r, double* z, double* p, double* Ap, double* Dinv)
+{
+    const fem_cfg* g = c->cfg;
+    const int n = 3 * g->V;
+    for (int i = 0; i < g->V; ++i) inv3(Dg + 9 * i, Dinv + 9 * i);
+#define PRECOND(zz, rr)                                                                                               \
+    for (int i = 0; i < g->V; ++i)                                                                                    \
+        for (int a = 0; a < 3; ++a)                                                                                   \
+            zz[3 * i + a] = Dinv[9 * i + 3 * a] * rr[3 * i] + Dinv[9 * i + 3 * a + 1] * rr[3 * i + 1] +               \
+                            Dinv[9 * i + 3 * a + 2] * rr[3 * i + 2];
+    memset(xs, 0, sizeof(double) * n);
+    memcpy(r, b, sizeof(double) * n);
+    PRECOND(z, r);
+    memcpy(p, z, sizeof(double) * n);
+    double rz = 0;
+    for (int i = 0; i < n; ++i) rz += r[i] * z[i];
+    const double rz0 = fabs(rz);
+    if (rz0 == 0.0) return 0;
+    int k;
+    const int max_iter = g->pcg_max_iter_ratio * n;
+    for (k = 1; k < max_iter; ++k) {
+        apply_A(c, H9, Hc, p, Ap);
+        double pAp = 0;
+        for (int i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+        const double alpha = rz / pAp;
+        for (int i = 0; i < n; ++i) { xs[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        PRECOND(z, r);
+        double rzn = 0;
+        for (int i = 0; i < n; ++i) rzn += r[i] * z[i];
+        if (fabs(rzn) <= g->pcg_tol_rate * rz0) break;
+        const double beta = rzn / rz;
+        for (int i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+        rz = rzn;
+    }
+#undef PRECOND
+    return k;
+}
+
+static void lerp_indenter(const fem_indenter* a, const fem_indenter* b, double s, fem_indenter* o)
+{
+    *o = *b; /* orientation / shape of the target; the centre moves linearly */
+    for (int i = 0; i < 3; ++i) o->c[i] = a->c[i] + (b->c[i] - a->c[i]) * s;
+}
+
+/*
+ * One implicit-Euler IPC step for ONE gel. State x, v, x_prev [V][3] in/out.
+ *   aim [A][3]: target positions of the attached vertices at the end of the step
+ *   ind_prev / ind_next: indenter pose at the beginning / end of the step (same shape and orientation)
+ */
+void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,
+              const int32_t* attach, const int32_t* surf, const double* aim, const fem_indenter* ind_prev,
+              const fem_indenter* ind_next, double* x, double* v, double* x_prev, fem_stats* st)
+{
+    const int n = 3 * g->V;
+    double* xt = (double*)malloc(sizeof(double) * n);
+    double* G = (double*)malloc(sizeof(double) * n);
+    double* dx = (double*)malloc(sizeof(double) * n);
+    double* x0 = (double*)malloc(sizeof(double) * n);
+    double* r = (double*)malloc(sizeof(double) * n);
+    double* z = (double*)malloc(sizeof(double) * n);
+    double* p = (double*)malloc(sizeof(double) * n);
+    double* Ap = (double*)malloc(sizeof(double) * n);
+    double* H9 = (double*)malloc(sizeof(double) * 81 * g->T);
+    double* Dg = (double*)malloc(sizeof(double) * 9 * g->V);
+    double* Dinv = (double*)malloc(sizeof(double) * 9 * g->V);
+    double* Hc = (double*)malloc(sizeof(double) * 9 * (g->S > 0 ? g->S : 1));
+    fem_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
+    c.x_prev = x_prev; c.x_tilde = xt;
+    memset(st, 0, sizeof(*st));
+
+    /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */
+    for (int i = 0; i < g->V; ++i)
+        for (int a = 0; a < 3; ++a)
+            xt[3 * i + a] = x_prev[3 * i + a] + g->gravity[a] * g->dt * g->dt + v[3 * i + a] * g->dt;
+
+    const double abs_tol = g->velocity_tol * g->dt;
+    double res0 = 0.0, ccd_alpha = 1.0, ind_s = 0.0;
+    double umax = 0.0; /* length of the indenter's translation over the step */
+    for (int i = 0; i < 3; ++i) umax += (ind_next->c[i] - ind_prev->c[i]) * (ind_next->c[i] - ind_prev->c[i]);
+    umax = sqrt(umax);
+    int it;
+    for (it = 0; it < g->newton_max_iter; ++it) {
+        double t = ((double)it + 1.0) / (double)g->substep;
+        c.ratio = t < 1.0 ? t : 1.0;
+        /* advance the prescribed indenter towards its target without tunnelling: an SDF is 1-Lipschitz, so moving
+           the body by delta changes every distance by at most delta; allow half of the current minimum gap */
+        if (ind_s < 1.0) {
+            lerp_indenter(ind_prev, ind_next, ind_s, &c.ind);
+            double md = 1e300;
+            for (int k = 0; k < g->S; ++k) {
+                double d, nn[3];
+                fem_indenter_sdf(&c.ind, x + 3 * surf[k], &d, nn, 0);
+                if (d < md) md = d;
+            }
+            double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
+            if (ds < 0.0) ds = 0.0;
+            ind_s = ind_s + ds < 1.0 ? ind_s + ds : 1.0;
+        }
+        lerp_indenter(ind_prev, ind_next, ind_s, &c.ind);
+
+        grad_hess(&c, x, G, H9, Dg, Hc);
+        for (int i = 0; i < n; ++i) G[i] = -G[i];
+        st->pcg_iters += pcg(&c, H9, Hc, Dg, G, dx, r, z, p, Ap, Dinv);
+
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) if (fabs(dx[i]) > res) res = fabs(dx[i]);
+        if (it == 0) res0 = res;
+        const double rel = res == 0.0 ? 0.0 : res / res0;
+        const int converged = (res <= abs_tol) || (rel <= 0.001);
+        st->last_res = res;
+        if (it > 0 && converged && ccd_alpha >= 1.0 && c.ratio >= 1.0 && ind_s >= 1.0) { st->converged = 1; break; }
+
+        /* line search (sim_engine_do_advance.cu:276-347) */
+        memcpy(x0, x, sizeof(double) * n);
+        double alpha = 1.0;
+        /* CCD against the indenter: conservative advancement, keep 20 % of the gap (cf. eta = 0.1 ACCD) */
+        for (int k = 0; k < g->S; ++k) {
+            int i = surf[k];
+            double d, nn[3];
+            fem_indenter_sdf(&c.ind, x0 + 3 * i, &d, nn, 0);
+            double len = sqrt(dx[3 * i] * dx[3 * i] + dx[3 * i + 1] * dx[3 * i + 1] + dx[3 * i + 2] * dx[3 * i + 2]);
+            if (len > 0.0 && d < 2.0 * len + g->d_hat) {
+                double a = 0.8 * d / len;
+                if (a < alpha) alpha = a;
+            }
+        }
+        ccd_alpha = alpha;
+        const double E0 = total_energy(&c, x0, 0);
+        for (int i = 0; i < n; ++i) x[i] = x0[i] + alpha * dx[i];
+        double E = total_energy(&c, x, &st->min_dist);
+        if (!converged) {
+            int ls = 0;
+            while (ls < g->ls_max_iter) {
+                if (E <= E0) break;
+                alpha *= 0.5;
+                for (int i = 0; i < n; ++i) x[i] = x0[i] + alpha * dx[i];
+                E = total_energy(&c, x, &st->min_dist);
+                ++ls;
+                ++st->ls_halvings;
+            }
+        }
+        st->energy = E;
+    }
+    st->newton_iters = it;
+    /* update velocity (fem_bdf1_time_integrator.cu:58-77) */
+    for (int i = 0; i < n; ++i) { v[i] = (x[i] - x_prev[i]) * (1.0 / g->dt); x_prev[i] = x[i]; }
+    free(xt); free(G); free(dx); free(x0); free(r); free(z); free(p); free(Ap); free(H9); free(Dg); free(Dinv); free(Hc);
+}
+
+/* batch driver (OpenMP over gels) */
+void fem_step_batch(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,
+                    const int32_t* attach, const int32_t* surf, const double* aim /*[N][A][3]*/,
+                    const fem_indenter* ind_prev /*[N]*/, const fem_indenter* ind_next /*[N]*/, int N, double* x, double* v,
+                    double* x_prev, fem_stats* st)
+{
+#pragma omp parallel for schedule(dynamic)
+    for (int e = 0; e < N; ++e) {
+        size_t o = (size_t)e * 3 * g->V;
+        fem_step(g, tets, Dm_inv, vol, mass, attach, surf, aim + (size_t)e * 3 * g->A, ind_prev + e, ind_next + e, x + o,
+                 v + o, x_prev + o, st + e);
+    }
+}
+
+/* ---- KAT helpers exported for tests -------------------------------------------------------------------------------- */
+/* dense assembly of the Newton matrix and right-hand side at state x (small meshes only) */
+void fem_assemble_dense(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,
+                        const int32_t* attach, const int32_t* surf, const double* aim, const fem_indenter* ind,
+                        const double* x, const double* x_prev, const double* x_tilde, double ratio, double* Aout /*[n][n]*/,
+                        double* bout /*[n]*/, double* energy)
+{
+    const int n = 3 * g->V;
+    fem_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
+    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind;
+    double* G = (double*)malloc(sizeof(double) * n);
+    double* H9 = (double*)malloc(sizeof(double) * 81 * g->T);
+    double* Dg = (double*)malloc(sizeof(double) * 9 * g->V);
+    double* Hc = (double*)malloc(sizeof(double) * 9 * (g->S > 0 ? g->S : 1));
+    double* e = (double*)calloc(n, sizeof(double));
+    double* y = (double*)malloc(sizeof(double) * n);
+    grad_hess(&c, x, G, H9, Dg, Hc);
+    for (int j = 0; j < n; ++j) {
+        e[j] = 1.0;
+        apply_A(&c, H9, Hc, e, y);
+        for (int i = 0; i < n; ++i) Aout[(size_t)i * n + j] = y[i];
+        e[j] = 0.0;
+    }
+    for (int i = 0; i < n; ++i) bout[i] = -G[i];
+    if (energy) *energy = total_energy(&c, x, 0);
+    free(G); free(H9); free(Dg); free(Hc); free(e); free(y);
+}
+
+int fem_pcg_solve(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,
+                  const int32_t* attach, const int32_t* surf, const double* aim, const fem_indenter* ind, const double* x,
+                  const double* x_prev, const double* x_tilde, double ratio, double* sol)
+{
+    const int n = 3 * g->V;
+    fem_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
+    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind;
+    double* buf = (double*)malloc(sizeof(double) * (6 * n + 81 * g->T + 18 * g->V + 9 * (g->S + 1)));
+    double *G = buf, *r = G + n, *z = r + n, *p = z + n, *Ap = p + n, *H9 = Ap + n, *Dg = H9 + 81 * g->T, *Dinv = Dg + 9 * g->V,
+           *Hc = Dinv + 9 * g->V;
+    grad_hess(&c, x, G, H9, Dg, Hc);
+    for (int i = 0; i < n; ++i) G[i] = -G[i];
+    int k = pcg(&c, H9, Hc, Dg, G, sol, r, z, p, Ap, Dinv);
+    free(buf);
+    return k;
+}

@@ -1,0 +1,210 @@
+"""CPU suite for the gel FEM restatement (oracle/fem_canon.c). libuipc cannot run here (PARITY UNPINNED), so the
+restatement is pinned by known-answer tests: finite differences, numpy.linalg.eigh / solve (protocol P5)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import fem_canon as fc
+from tacex_b200 import gel_mesh
+
+MU, LAM = gel_mesh.lame(1e4, 0.49)[1], gel_mesh.lame(1e4, 0.49)[0]
+
+
+def _snh(F):
+    F = np.ascontiguousarray(F, np.float64)
+    E = C.c_double()
+    g = np.zeros(9)
+    H = np.zeros((9, 9))
+    fc.lib().fem_snh(fc._d(F), C.c_double(MU), C.c_double(LAM), C.byref(E), fc._d(g), fc._d(H))
+    return E.value, g, H
+
+
+def test_snh_energy_gradient_hessian_finite_differences():
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        F = (np.eye(3) + 0.2 * rng.standard_normal((3, 3))).T.reshape(-1)  # column-major vec
+        E, g, H = _snh(F)
+        J = np.linalg.det(F.reshape(3, 3).T)
+        ref = 0.5 * LAM * (J - 1) ** 2 - MU * (J - 1) + 0.5 * MU * ((F ** 2).sum() - 3) + MU ** 2 / LAM ** 2
+        assert abs(E - ref) <= 1e-9 * abs(ref)
+        h = 1e-6
+        gfd = np.zeros(9)
+        Hfd = np.zeros((9, 9))
+        for i in range(9):
+            d = np.zeros(9)
+            d[i] = h
+            Ep, gp, _ = _snh(F + d)
+            Em, gm, _ = _snh(F - d)
+            gfd[i] = (Ep - Em) / (2 * h)
+            Hfd[:, i] = (gp - gm) / (2 * h)
+        assert np.abs(g - gfd).max() <= 1e-5 * np.abs(g).max()
+        assert np.abs(H - Hfd).max() <= 1e-5 * np.abs(H).max()
+        assert np.abs(H - H.T).max() <= 1e-12 * np.abs(H).max()
+
+
+def test_snh_rest_state_is_stress_free_minimum():
+    E, g, H = _snh(np.eye(3).reshape(-1))
+    assert np.abs(g).max() < 1e-9 and abs(E - MU ** 2 / LAM ** 2) < 1e-9
+
+
+@pytest.mark.parametrize("n", [3, 9, 12])
+def test_make_spd_matches_eigh(n):
+    rng = np.random.default_rng(n)
+    for trial in range(4):
+        A = rng.standard_normal((n, n))
+        A = A + A.T
+        if trial == 3:
+            A = A @ A.T + np.eye(n)  # already PD: must be returned unchanged (LDL^T fast path)
+        w, V = np.linalg.eigh(A)
+        ref = (V * np.maximum(w, 0)) @ V.T
+        H = A.copy()
+        fc.lib().fem_spd_project(n, fc._d(H))
+        assert np.abs(H - ref).max() <= 1e-10 * np.abs(A).max()
+        assert np.linalg.eigvalsh(H).min() >= -1e-10 * np.abs(A).max()
+        if trial == 3:
+            assert np.array_equal(H, A)
+
+
+def test_barrier_derivatives_and_limits():
+    dhat, kappa = 5e-4, 1e10 * 1e-4
+    f = lambda D: [v.value for v in _bar(D, dhat, kappa)]  # noqa: E731
+
+    def _bar(D, dh, k):
+        B, dB, ddB = C.c_double(), C.c_double(), C.c_double()
+        fc.lib().fem_barrier(C.c_double(D), C.c_double(dh), C.c_double(k), C.byref(B), C.byref(dB), C.byref(ddB))
+        return B, dB, ddB
+
+    D0 = dhat * dhat
+    assert f(D0) == [0, 0, 0] and f(2 * D0) == [0, 0, 0]  # zero at and beyond d_hat (Appendix E)
+    for D in (0.9 * D0, 0.5 * D0, 0.05 * D0):
+        B, dB, ddB = f(D)
+        h = D * 1e-5
+        assert B > 0 and dB < 0 and ddB > 0
+        assert abs((f(D + h)[0] - f(D - h)[0]) / (2 * h) - dB) <= 1e-6 * abs(dB)
+        assert abs((f(D + h)[1] - f(D - h)[1]) / (2 * h) - ddB) <= 1e-6 * abs(ddB)
+    assert f(1e-12 * D0)[0] > f(1e-6 * D0)[0] > 10 * f(0.5 * D0)[0]  # grows (logarithmically) without bound towards contact
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_indenter_sdf_gradient_and_hessian(kind):
+    rng = np.random.default_rng(kind)
+    th = 0.4
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    ind = fc.make_indenter(kind, (1e-3, -2e-3, 5e-3), (3e-3, 2e-3, 1e-3), R)
+
+    def sdf(x):
+        d = C.c_double()
+        n = np.zeros(3)
+        H = np.zeros((3, 3))
+        fc.lib().fem_indenter_sdf(C.byref(ind), fc._d(np.ascontiguousarray(x)), C.byref(d), fc._d(n), fc._d(H))
+        return d.value, n, H
+
+    for _ in range(20):
+        x = np.array([1e-3, -2e-3, 5e-3]) + rng.standard_normal(3) * 6e-3
+        d, n, H = sdf(x)
+        if d <= 1e-4:
+            continue
+        assert abs(np.linalg.norm(n) - 1) < 1e-12
+        h = 1e-7
+        nfd = np.array([(sdf(x + h * e)[0] - sdf(x - h * e)[0]) / (2 * h) for e in np.eye(3)])
+        assert np.abs(n - nfd).max() < 1e-5
+        Hfd = np.stack([(sdf(x + h * e)[1] - sdf(x - h * e)[1]) / (2 * h) for e in np.eye(3)], 1)
+        assert np.abs(H - Hfd).max() < 1e-3 * max(1.0, np.abs(H).max())
+
+
+def _small():
+    m = gel_mesh.box_gel(cells=(3, 3, 2))
+    return m, fc.CanonFem(m, velocity_tol=1e-3)
+
+
+def test_mass_and_volume_quirk():
+    m = gel_mesh.box_gel()
+    a = fc.CanonFem(m, rest_volume_det=True)
+    b = fc.CanonFem(m, rest_volume_det=False)
+    vol = 20.75e-3 * 25.25e-3 * 4.5e-3
+    assert abs(a.mass.sum() - 1e3 * vol) < 1e-12  # lumped mass uses the TRUE volume
+    assert abs(b.vol.sum() - vol) < 1e-15 and abs(a.vol.sum() - 6 * vol) < 1e-14  # elastic "volume" = det(Dm), quirk Q10
+    assert (m.tets.max() == len(m.X) - 1) and len(m.tets) == 2160 and len(m.X) == 572
+
+
+def test_pcg_matches_dense_solve():
+    m, cf = _small()
+    g = cf.cfg
+    n = 3 * g.V
+    rng = np.random.default_rng(1)
+    x = cf.X + 2e-5 * rng.standard_normal(cf.X.shape)
+    xp = cf.X.copy()
+    xt = cf.X.copy()
+    aim = cf.X[cf.attach].copy()
+    ind = fc.make_indenter(0, (0, 0, 4.5e-3 + 3e-3 + 2e-4), (3e-3, 0, 0))
+    A = np.zeros((n, n))
+    b = np.zeros(n)
+    E = C.c_double()
+    args = (C.byref(g), fc._i(cf.tets), fc._d(cf.Dm_inv), fc._d(cf.vol), fc._d(cf.mass), fc._i(cf.attach), fc._i(cf.surf),
+            fc._d(aim), C.byref(ind), fc._d(x), fc._d(xp), fc._d(xt), C.c_double(1.0))
+    fc.lib().fem_assemble_dense(*args, fc._d(A), fc._d(b), C.byref(E))
+    assert np.abs(A - A.T).max() <= 1e-9 * np.abs(A).max()
+    assert np.linalg.eigvalsh(A).min() > 0  # SPD after projection
+    sol = np.zeros(n)
+    g.pcg_tol_rate = 1e-16
+    it = fc.lib().fem_pcg_solve(*args, fc._d(sol))
+    g.pcg_tol_rate = 1e-3
+    ref = np.linalg.solve(A, b)
+    assert it > 1 and np.abs(sol - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_gradient_of_total_energy_finite_differences():
+    m, cf = _small()
+    g = cf.cfg
+    n = 3 * g.V
+    rng = np.random.default_rng(2)
+    x = cf.X + 1e-5 * rng.standard_normal(cf.X.shape)
+    xp, xt = cf.X.copy(), cf.X + 1e-6
+    aim = cf.X[cf.attach].copy()
+    ind = fc.make_indenter(1, (0, 0, 4.5e-3 + 1e-3 + 3e-4), (4e-3, 4e-3, 1e-3))
+
+    def eval_(xx):
+        A = np.zeros((n, n)); b = np.zeros(n); E = C.c_double()
+        fc.lib().fem_assemble_dense(C.byref(g), fc._i(cf.tets), fc._d(cf.Dm_inv), fc._d(cf.vol), fc._d(cf.mass),
+                                    fc._i(cf.attach), fc._i(cf.surf), fc._d(aim), C.byref(ind),
+                                    fc._d(np.ascontiguousarray(xx)), fc._d(xp), fc._d(xt), C.c_double(1.0), fc._d(A), fc._d(b),
+                                    C.byref(E))
+        return E.value, b
+
+    E0, b = eval_(x)
+    idx = rng.choice(n, 12, replace=False)
+    for i in idx:
+        d = np.zeros(n); d[i] = 1e-9
+        Ep, _ = eval_((x.reshape(-1) + d).reshape(x.shape))
+        Em, _ = eval_((x.reshape(-1) - d).reshape(x.shape))
+        fd = (Ep - Em) / 2e-9
+        assert abs(-b[i] - fd) <= 1e-4 * max(abs(fd), np.abs(b).max() * 1e-3)
+
+
+def test_rigid_translation_of_aims_has_zero_elastic_energy_and_rest_is_fixed_point():
+    m, cf = _small()
+    x, v, xp = cf.new_state(1)
+    cf.cfg.gravity[:] = (0, 0, 0)
+    far = fc.make_indenter(0, (0, 0, 1.0), (1e-3, 0, 0))
+    st = cf.step(x, v, xp, cf.X[cf.attach][None], [far], [far])
+    assert np.abs(x[0] - cf.X).max() < 1e-12 and st[0]["converged"] == 1
+
+
+def test_press_keeps_gap_positive_and_is_monotone():
+    m = gel_mesh.box_gel()
+    cf = fc.CanonFem(m, velocity_tol=1e-3)
+    x, v, xp = cf.new_state(1)
+    aim = cf.X[cf.attach][None]
+    r = 3e-3
+    z0 = 4.5e-3 + r + 4e-4
+    prev = fc.make_indenter(0, (0, 0, z0), (r, 0, 0))
+    tops = []
+    for s in range(6):
+        nxt = fc.make_indenter(0, (0, 0, z0 - 1e-3 * (s + 1) / 6), (r, 0, 0))
+        st = cf.step(x, v, xp, aim, [prev], [nxt])
+        prev = nxt
+        assert st[0]["min_dist"] > 0 and np.isfinite(x).all()
+        tops.append(x[0][:, 2].max() - 0)  # track
+    centre = np.argmin(np.abs(cf.X[:, 0]) + np.abs(cf.X[:, 1]) - cf.X[:, 2])
+    assert x[0][centre, 2] < cf.X[centre, 2] - 3e-4  # the gel under the sphere moved down by > 0.3 mm
