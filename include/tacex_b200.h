@@ -138,6 +138,61 @@ int tx_debug_set_ticks(tx_handle* h, long long* ticks);
 int tx_step_host(tx_handle* h, const float* height_mm_host, const float* theta_host, int N, float* rgb_host,
                  float* depth_host, float* markers_host);
 
+/* ==== gel FEM substep (UIPC-style) =================================================================================
+ * Replaces UipcSim.step() = world.advance() + world.retrieve() for the gel pads of all sensors
+ * (ref: source/tacex_uipc/tacex_uipc/sim/uipc_sim.py:250-252 -> libuipc SimEngine::do_advance,
+ *  source/tacex_uipc/libuipc/src/backends/cuda/engine/sim_engine_do_advance.cu:16-387) and the FEM marker read-out
+ * (ref: source/tacex/tacex/simulation_approaches/fem_based/mani_skill_sim.py:82-86). All state is float64 like libuipc. */
+
+typedef struct {
+    int type;    /* 0 sphere, 1 oriented box */
+    double c[3]; /* centre, world frame [m] */
+    double R[9]; /* rotation, row-major, world = R * local */
+    double h[3]; /* box half extents, or h[0] = sphere radius */
+} tx_fem_indenter;
+
+typedef struct {
+    int converged, newton_iters, pcg_iters, ls_halvings;
+    double min_dist, last_res, energy;
+} tx_fem_stats;
+
+/* ref for the defaults: source/tacex_uipc/tacex_uipc/sim/uipc_sim.py:32-131 (dt 0.01, Newton max 1024, velocity_tol 0.05,
+ * PCG tol 1e-3, line search 8, d_hat, contact resistance 10 GPa), objects/uipc_object.py:59-84 (E, nu, rho) */
+typedef struct {
+    int V, T, A, S;
+    double dt, gravity[3];
+    double mu, lambda, density;
+    double attach_strength;
+    double d_hat, kappa;
+    int newton_max_iter;
+    double velocity_tol, pcg_tol_rate;
+    int pcg_max_iter_ratio, ls_max_iter, substep;
+    int rest_volume_det; /* 1: elastic rest "volume" = det(Dm) as libuipc does; 0: det/6 */
+} tx_fem_config;
+
+typedef struct tx_fem tx_fem;
+
+/* Mesh arrays are HOST pointers: X [V][3] rest positions, tets [T][4], attach [A], surf [S] vertex ids. */
+int tx_fem_create(const tx_fem_config* cfg, const double* X, const int32_t* tets, const int32_t* attach, const int32_t* surf,
+                  int device, void* cuda_stream, tx_fem** out);
+void tx_fem_destroy(tx_fem* f);
+const char* tx_fem_last_error(const tx_fem* f);
+/* lumped vertex masses (HOST pointer, V doubles) -- ref: libuipc/src/geometry/compute_vertex_volume.cpp:20-52 */
+int tx_fem_get_mass(const tx_fem* f, double* mass);
+
+/* One implicit-Euler IPC step for N gels (DEVICE pointers): x, v, x_prev [N][V][3] in/out; aim [N][A][3] target positions
+ * of the attached vertices; ind_prev / ind_next [N] pose of the prescribed indenter at the start / end of the step;
+ * stats [N] or NULL. */
+int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* aim, const tx_fem_indenter* ind_prev,
+                const tx_fem_indenter* ind_next, int N, tx_fem_stats* stats);
+
+/* FEM marker read-out. set: HOST pointers, tri [M][3] surface-triangle vertex ids and barycentric weights [M][3] per marker,
+ * camera pose (cam_R row-major world = R * cam, cam_t) and pinhole intrinsics. run: x DEVICE [N][V][3] ->
+ * markers DEVICE [N][2][M][2] ([:,0] rest, [:,1] current, (u, v) pixels). */
+int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const double* weights, const double* cam_R, const double* cam_t,
+                       double fx, double fy, double cx, double cy);
+int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers);
+
 #ifdef __cplusplus
 }
 #endif

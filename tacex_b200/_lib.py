@@ -39,6 +39,24 @@ class TxCounters(C.Structure):
                 ("depth_calls", C.c_uint64), ("kernels_launched", C.c_uint64)]
 
 
+class TxFemConfig(C.Structure):
+    _fields_ = [("V", C.c_int), ("T", C.c_int), ("A", C.c_int), ("S", C.c_int), ("dt", C.c_double),
+                ("gravity", C.c_double * 3), ("mu", C.c_double), ("lam", C.c_double), ("density", C.c_double),
+                ("attach_strength", C.c_double), ("d_hat", C.c_double), ("kappa", C.c_double),
+                ("newton_max_iter", C.c_int), ("velocity_tol", C.c_double), ("pcg_tol_rate", C.c_double),
+                ("pcg_max_iter_ratio", C.c_int), ("ls_max_iter", C.c_int), ("substep", C.c_int),
+                ("rest_volume_det", C.c_int)]
+
+
+class TxFemIndenter(C.Structure):
+    _fields_ = [("type", C.c_int), ("c", C.c_double * 3), ("R", C.c_double * 9), ("h", C.c_double * 3)]
+
+
+class TxFemStats(C.Structure):
+    _fields_ = [("converged", C.c_int), ("newton_iters", C.c_int), ("pcg_iters", C.c_int), ("ls_halvings", C.c_int),
+                ("min_dist", C.c_double), ("last_res", C.c_double), ("energy", C.c_double)]
+
+
 class TxError(RuntimeError):
     pass
 
@@ -49,6 +67,8 @@ _lib = None
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
     "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks",
+    "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
+    "tx_fem_markers",
 ]
 
 
@@ -77,6 +97,17 @@ def load() -> C.CDLL:
     lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
     lib.tx_debug_set_ticks.argtypes = [C.c_void_p, C.c_void_p]
     lib.tx_debug_set_ticks.restype = C.c_int
+    lib.tx_fem_create.argtypes = [C.POINTER(TxFemConfig), vp, vp, vp, vp, C.c_int, vp, C.POINTER(C.c_void_p)]
+    lib.tx_fem_destroy.argtypes = [C.c_void_p]
+    lib.tx_fem_destroy.restype = None
+    lib.tx_fem_last_error.argtypes = [C.c_void_p]
+    lib.tx_fem_last_error.restype = C.c_char_p
+    lib.tx_fem_get_mass.argtypes = [C.c_void_p, vp]
+    lib.tx_fem_step.argtypes = [C.c_void_p, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    lib.tx_fem_set_markers.argtypes = [C.c_void_p, C.c_int, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.tx_fem_markers.argtypes = [C.c_void_p, vp, C.c_int, vp]
+    for name in ("tx_fem_create", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers", "tx_fem_markers"):
+        getattr(lib, name).restype = C.c_int
     for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_fots_markers",
                  "tx_marker_grid", "tx_step_host"):
         getattr(lib, name).restype = C.c_int

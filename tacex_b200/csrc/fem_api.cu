@@ -1,0 +1,199 @@
+// fem_api.cu -- C ABI of the gel FEM substep (see include/tacex_b200.h).
+#include "tx_kernels.h"
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tx;
+
+struct tx_fem {
+    tx_fem_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<double> mass;
+    int *d_tets = nullptr, *d_attach = nullptr, *d_surf = nullptr;
+    double *d_Dm_inv = nullptr, *d_vol = nullptr, *d_mass = nullptr, *d_X = nullptr, *d_h9 = nullptr, *d_tsc = nullptr;
+    int *d_adj_off = nullptr, *d_adj = nullptr;
+    int grid = 0;
+    // markers
+    int M = 0;
+    int* d_tri = nullptr;
+    double* d_w = nullptr;
+    double cam_R[9], cam_t[3], fx = 0, fy = 0, cx = 0, cy = 0;
+};
+
+static std::string g_fem_err;
+static int ffail(tx_fem* f, int code, const std::string& m)
+{
+    if (f) f->err = m; else g_fem_err = m;
+    return code;
+}
+#define FEM_CUDA(f, expr)                                                                                             \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess) return ffail((f), TX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+    } while (0)
+
+extern "C" const char* tx_fem_last_error(const tx_fem* f) { return f ? f->err.c_str() : g_fem_err.c_str(); }
+
+extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int32_t* tets, const int32_t* attach,
+                             const int32_t* surf, int device, void* cuda_stream, tx_fem** out)
+{
+    if (!c || !X || !tets || !out || (c->A > 0 && !attach) || (c->S > 0 && !surf))
+        return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return ffail(nullptr, TX_ERR_NO_DEVICE, "tx_fem_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: bad device index");
+    if (c->V <= 0 || c->T <= 0 || c->substep <= 0) return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: bad sizes");
+    if (fem_smem_bytes(c->V, c->S) > 227 * 1024)
+        return ffail(nullptr, TX_ERR_UNSUPPORTED, "tx_fem_create: mesh too large for the shared-memory resident solver");
+    tx_fem* f = new (std::nothrow) tx_fem();
+    if (!f) return ffail(nullptr, TX_ERR_INVALID_ARG, "out of host memory");
+    f->cfg = *c;
+    f->device = device;
+    f->stream = (cudaStream_t)cuda_stream;
+    // precompute Dm^-1, elastic rest volume, lumped mass (ref: finite_element_method.cu:957-982, 721-744)
+    std::vector<double> Dmi((size_t)9 * c->T), vol(c->T);
+    f->mass.assign(c->V, 0.0);
+    for (int t = 0; t < c->T; ++t) {
+        const int32_t* e = tets + 4 * t;
+        for (int k = 0; k < 4; ++k)
+            if (e[k] < 0 || e[k] >= c->V) { delete f; return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: tet index out of range"); }
+        double Dm[9];
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 3; ++k) Dm[a * 3 + k] = X[3 * e[k + 1] + a] - X[3 * e[0] + a];
+        const double det = Dm[0] * (Dm[4] * Dm[8] - Dm[5] * Dm[7]) - Dm[1] * (Dm[3] * Dm[8] - Dm[5] * Dm[6]) +
+                           Dm[2] * (Dm[3] * Dm[7] - Dm[4] * Dm[6]);
+        if (!(det > 0.0)) { delete f; return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: inverted or degenerate tet"); }
+        double* B = Dmi.data() + 9 * t;
+        B[0] = (Dm[4] * Dm[8] - Dm[5] * Dm[7]) / det; B[1] = (Dm[2] * Dm[7] - Dm[1] * Dm[8]) / det; B[2] = (Dm[1] * Dm[5] - Dm[2] * Dm[4]) / det;
+        B[3] = (Dm[5] * Dm[6] - Dm[3] * Dm[8]) / det; B[4] = (Dm[0] * Dm[8] - Dm[2] * Dm[6]) / det; B[5] = (Dm[2] * Dm[3] - Dm[0] * Dm[5]) / det;
+        B[6] = (Dm[3] * Dm[7] - Dm[4] * Dm[6]) / det; B[7] = (Dm[1] * Dm[6] - Dm[0] * Dm[7]) / det; B[8] = (Dm[0] * Dm[4] - Dm[1] * Dm[3]) / det;
+        vol[t] = c->rest_volume_det ? det : det / 6.0;
+        for (int k = 0; k < 4; ++k) f->mass[e[k]] += c->density * (det / 6.0) / 4.0;
+    }
+#define FEM_CUDA_C(expr)                                                                                              \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess) {                                                                                      \
+            ffail(nullptr, TX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+            tx_fem_destroy(f);                                                                                        \
+            return TX_ERR_CUDA;                                                                                       \
+        }                                                                                                             \
+    } while (0)
+    FEM_CUDA_C(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FEM_CUDA_C(cudaGetDeviceProperties(&prop, device));
+    f->grid = prop.multiProcessorCount; // one persistent CTA per SM
+    FEM_CUDA_C(cudaMalloc(&f->d_tets, sizeof(int) * 4 * c->T));
+    FEM_CUDA_C(cudaMalloc(&f->d_attach, sizeof(int) * (c->A > 0 ? c->A : 1)));
+    FEM_CUDA_C(cudaMalloc(&f->d_surf, sizeof(int) * (c->S > 0 ? c->S : 1)));
+    FEM_CUDA_C(cudaMalloc(&f->d_Dm_inv, sizeof(double) * 9 * c->T));
+    FEM_CUDA_C(cudaMalloc(&f->d_vol, sizeof(double) * c->T));
+    FEM_CUDA_C(cudaMalloc(&f->d_mass, sizeof(double) * c->V));
+    FEM_CUDA_C(cudaMalloc(&f->d_X, sizeof(double) * 3 * c->V));
+    FEM_CUDA_C(cudaMalloc(&f->d_h9, sizeof(double) * 45 * (size_t)c->T * f->grid));
+    FEM_CUDA_C(cudaMalloc(&f->d_tsc, sizeof(double) * 48 * (size_t)c->T * f->grid));
+    {   // vertex -> (tet, local vertex) incidence in CSR form, ascending tet order
+        std::vector<int> off(c->V + 1, 0), adj((size_t)4 * c->T);
+        for (int t = 0; t < c->T; ++t)
+            for (int k = 0; k < 4; ++k) off[tets[4 * t + k] + 1]++;
+        for (int i = 0; i < c->V; ++i) off[i + 1] += off[i];
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int t = 0; t < c->T; ++t)
+            for (int k = 0; k < 4; ++k) adj[cur[tets[4 * t + k]]++] = 4 * t + k;
+        FEM_CUDA_C(cudaMalloc(&f->d_adj_off, sizeof(int) * (c->V + 1)));
+        FEM_CUDA_C(cudaMalloc(&f->d_adj, sizeof(int) * 4 * c->T));
+        FEM_CUDA_C(cudaMemcpy(f->d_adj_off, off.data(), sizeof(int) * (c->V + 1), cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_adj, adj.data(), sizeof(int) * 4 * c->T, cudaMemcpyHostToDevice));
+    }
+    FEM_CUDA_C(cudaMemcpy(f->d_tets, tets, sizeof(int) * 4 * c->T, cudaMemcpyHostToDevice));
+    if (c->A > 0) FEM_CUDA_C(cudaMemcpy(f->d_attach, attach, sizeof(int) * c->A, cudaMemcpyHostToDevice));
+    if (c->S > 0) FEM_CUDA_C(cudaMemcpy(f->d_surf, surf, sizeof(int) * c->S, cudaMemcpyHostToDevice));
+    FEM_CUDA_C(cudaMemcpy(f->d_Dm_inv, Dmi.data(), sizeof(double) * 9 * c->T, cudaMemcpyHostToDevice));
+    FEM_CUDA_C(cudaMemcpy(f->d_vol, vol.data(), sizeof(double) * c->T, cudaMemcpyHostToDevice));
+    FEM_CUDA_C(cudaMemcpy(f->d_mass, f->mass.data(), sizeof(double) * c->V, cudaMemcpyHostToDevice));
+    FEM_CUDA_C(cudaMemcpy(f->d_X, X, sizeof(double) * 3 * c->V, cudaMemcpyHostToDevice));
+#undef FEM_CUDA_C
+    *out = f;
+    return TX_OK;
+}
+
+extern "C" void tx_fem_destroy(tx_fem* f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->d_tets); cudaFree(f->d_attach); cudaFree(f->d_surf); cudaFree(f->d_Dm_inv); cudaFree(f->d_vol);
+    cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_h9); cudaFree(f->d_tsc); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
+    cudaFree(f->d_tri); cudaFree(f->d_w);
+    delete f;
+}
+
+extern "C" int tx_fem_get_mass(const tx_fem* f, double* mass)
+{
+    if (!f || !mass) return TX_ERR_INVALID_ARG;
+    for (int i = 0; i < f->cfg.V; ++i) mass[i] = f->mass[i];
+    return TX_OK;
+}
+
+extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* aim, const tx_fem_indenter* ind_prev,
+                           const tx_fem_indenter* ind_next, int N, tx_fem_stats* stats)
+{
+    if (!f || !x || !v || !x_prev || !ind_prev || !ind_next || N < 0 || (f->cfg.A > 0 && !aim))
+        return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_step: bad argument");
+    if (N == 0) return TX_OK;
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    const tx_fem_config& c = f->cfg;
+    FemArgs a{};
+    a.N = N; a.V = c.V; a.T = c.T; a.A = c.A; a.S = c.S;
+    a.tets = f->d_tets; a.Dm_inv = f->d_Dm_inv; a.vol = f->d_vol; a.mass = f->d_mass; a.attach = f->d_attach; a.surf = f->d_surf;
+    a.x = x; a.v = v; a.x_prev = x_prev; a.aim = aim; a.ind_prev = ind_prev; a.ind_next = ind_next; a.stats = stats;
+    a.h9_scratch = f->d_h9;
+    a.tet_scratch = f->d_tsc;
+    a.adj_off = f->d_adj_off;
+    a.adj = f->d_adj;
+    a.dt = c.dt;
+    for (int i = 0; i < 3; ++i) a.gravity[i] = c.gravity[i];
+    a.mu = c.mu; a.lambda = c.lambda; a.attach_strength = c.attach_strength; a.d_hat = c.d_hat; a.kappa = c.kappa;
+    a.velocity_tol = c.velocity_tol; a.pcg_tol_rate = c.pcg_tol_rate; a.newton_max_iter = c.newton_max_iter;
+    a.pcg_max_iter_ratio = c.pcg_max_iter_ratio; a.ls_max_iter = c.ls_max_iter; a.substep = c.substep;
+    const int grid = N < f->grid ? N : f->grid;
+    FEM_CUDA(f, launch_fem_step(a, grid, f->stream));
+    return TX_OK;
+}
+
+extern "C" int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const double* weights, const double* cam_R,
+                                  const double* cam_t, double fx, double fy, double cx, double cy)
+{
+    if (!f || M <= 0 || !tri || !weights || !cam_R || !cam_t) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_markers: bad argument");
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    cudaFree(f->d_tri); cudaFree(f->d_w);
+    f->d_tri = nullptr; f->d_w = nullptr;
+    FEM_CUDA(f, cudaMalloc(&f->d_tri, sizeof(int) * 3 * M));
+    FEM_CUDA(f, cudaMalloc(&f->d_w, sizeof(double) * 3 * M));
+    FEM_CUDA(f, cudaMemcpy(f->d_tri, tri, sizeof(int) * 3 * M, cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_w, weights, sizeof(double) * 3 * M, cudaMemcpyHostToDevice));
+    f->M = M;
+    for (int i = 0; i < 9; ++i) f->cam_R[i] = cam_R[i];
+    for (int i = 0; i < 3; ++i) f->cam_t[i] = cam_t[i];
+    f->fx = fx; f->fy = fy; f->cx = cx; f->cy = cy;
+    return TX_OK;
+}
+
+extern "C" int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers)
+{
+    if (!f || !x || !markers || N < 0) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_markers: bad argument");
+    if (f->M <= 0) return ffail(f, TX_ERR_STATE, "tx_fem_markers: call tx_fem_set_markers first");
+    if (N == 0) return TX_OK;
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    FemMarkerArgs m{};
+    m.V = f->cfg.V; m.M = f->M; m.tri = f->d_tri; m.weights = f->d_w; m.x_rest = f->d_X; m.x = x; m.out = markers;
+    for (int i = 0; i < 9; ++i) m.cam_R[i] = f->cam_R[i];
+    for (int i = 0; i < 3; ++i) m.cam_t[i] = f->cam_t[i];
+    m.fx = f->fx; m.fy = f->fy; m.cx = f->cx; m.cy = f->cy;
+    FEM_CUDA(f, launch_fem_markers(m, N, f->stream));
+    return TX_OK;
+}

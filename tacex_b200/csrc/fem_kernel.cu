@@ -1,0 +1,666 @@
+// fem_kernel.cu -- batched gel FEM substep (UIPC-style implicit Euler + IPC barrier), one persistent CTA per gel.
+//
+// Replaces, for the gel pad of every sensor in the batch (ref = /root/reference/source/tacex_uipc/libuipc/src/backends/cuda):
+//   engine/sim_engine_do_advance.cu:200-360            Newton loop, convergence test, line search, velocity update
+//   finite_element/bdf/*.cu                            BDF1 predict / kinetic energy, gradient, Hessian / update
+//   finite_element/constitutions/stable_neo_hookean_3d.cu:68-165 (+ sym/stable_neo_hookean_3d.inl)   SNH energy / dE/dF / d2E/dF2
+//   utils/make_spd.h:7-19                              SPD projection of the 9x9 / 3x3 Hessians
+//   finite_element/constraints/soft_position_constraint.cu:99-179   attachment of the gel to the sensor case
+//   contact_system/contact_models/ipc_vertex_half_plane_normal_contact.cu + sym/codim_ipc_contact.inl   barrier
+//   linear_system/linear_pcg.cu:45-140, finite_element/fem_diag_preconditioner.cu:112-164              PCG + block Jacobi
+//   newton_tolerance/max_translation_checker.cu:25-50  tolerance
+// The reference runs ONE scene with dozens of kernel launches and host synchronisations per Newton iteration
+// (cuBLAS dots, CUB reductions, radix-sorted triplet assembly); here the whole step of one gel runs inside one CTA
+// without leaving the SM: vectors live in shared memory (float64), the operator is applied matrix-free from the per-tet
+// projected 9x9 Hessians (symmetric packed, L2-resident scratch of the CTA), reductions are block reductions, and the
+// element -> vertex assembly is a gather in fixed CSR order (no atomics), so results are bitwise reproducible.
+// The indenter is a prescribed analytic rigid body (sphere / oriented box): no broad phase is needed.
+#include "tx_kernels.h"
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace tx {
+
+constexpr int FEM_THREADS = 256;
+
+// ---- small dense helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double det3cm(const double* F)
+{
+    return F[0] * (F[4] * F[8] - F[7] * F[5]) - F[3] * (F[1] * F[8] - F[7] * F[2]) + F[6] * (F[1] * F[5] - F[4] * F[2]);
+}
+
+template <int n>
+__device__ void jacobi_evd(double* A, double* w, double* Vv)
+{
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) Vv[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                if (i != j) off += A[i * n + j] * A[i * n + j];
+                else diag += A[i * n + j] * A[i * n + j];
+            }
+        if (off <= 1e-30 * (diag + 1e-300)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq;
+                    A[k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk;
+                    A[q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = Vv[k * n + p], vkq = Vv[k * n + q];
+                    Vv[k * n + p] = c * vkp - s * vkq;
+                    Vv[k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+// make_spd with the LDL^T fast path (an all-positive-pivot factorisation proves H is already positive definite)
+template <int n>
+__device__ void spd_project(double* H)
+{
+    double L[n * n], D[n];
+    bool pd = true;
+    for (int j = 0; j < n && pd; ++j) {
+        double d = H[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k] * D[k];
+        if (!(d > 0.0)) { pd = false; break; }
+        D[j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = H[i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k] * D[k];
+            L[i * n + j] = s / d;
+        }
+    }
+    if (pd) return;
+    double A[n * n], w[n], Vv[n * n];
+    for (int i = 0; i < n * n; ++i) A[i] = H[i];
+    jacobi_evd<n>(A, w, Vv);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) s += Vv[i * n + k] * (w[k] < 0.0 ? 0.0 : w[k]) * Vv[j * n + k];
+            H[i * n + j] = s;
+        }
+}
+
+// Stable Neo-Hookean (sym/stable_neo_hookean_3d.inl): energy, dPsi/dF (9), d2Psi/dF2 (81, row-major)
+__device__ void snh(const double* F, double mu, double lambda, double* E, double* g, double* H)
+{
+    const double J = det3cm(F);
+    if (E) {
+        double IC = 0.0;
+        for (int i = 0; i < 9; ++i) IC += F[i] * F[i];
+        *E = 0.5 * lambda * (J - 1.0) * (J - 1.0) - mu * (J - 1.0) + 0.5 * mu * (IC - 3.0) + mu * mu / (lambda * lambda);
+    }
+    if (!g && !H) return;
+    double gJ[9];
+    const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
+    gJ[0] = f1[1] * f2[2] - f1[2] * f2[1]; gJ[1] = f1[2] * f2[0] - f1[0] * f2[2]; gJ[2] = f1[0] * f2[1] - f1[1] * f2[0];
+    gJ[3] = f2[1] * f0[2] - f2[2] * f0[1]; gJ[4] = f2[2] * f0[0] - f2[0] * f0[2]; gJ[5] = f2[0] * f0[1] - f2[1] * f0[0];
+    gJ[6] = f0[1] * f1[2] - f0[2] * f1[1]; gJ[7] = f0[2] * f1[0] - f0[0] * f1[2]; gJ[8] = f0[0] * f1[1] - f0[1] * f1[0];
+    const double c = lambda * (J - 1.0) - mu;
+    if (g)
+        for (int i = 0; i < 9; ++i) g[i] = mu * F[i] + c * gJ[i];
+    if (H) {
+        for (int i = 0; i < 9; ++i)
+            for (int j = 0; j < 9; ++j) H[i * 9 + j] = lambda * gJ[i] * gJ[j] + (i == j ? mu : 0.0);
+        for (int a = 0; a < 3; ++a) {
+            const int b1 = (a + 1) % 3, b2 = (a + 2) % 3;
+            const double* u = F + 3 * b1;
+            const double* v = F + 3 * b2;
+            const double Ux[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
+            const double Vx[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+            for (int r = 0; r < 3; ++r)
+                for (int s = 0; s < 3; ++s) {
+                    H[(3 * a + r) * 9 + (3 * b2 + s)] += c * Ux[r * 3 + s];
+                    H[(3 * a + r) * 9 + (3 * b1 + s)] -= c * Vx[r * 3 + s];
+                }
+        }
+    }
+}
+
+__device__ __forceinline__ void barrier_fn(double D, double d_hat, double kappa, double* B, double* dB, double* ddB)
+{
+    const double D0 = d_hat * d_hat;
+    if (!(D < D0)) { if (B) *B = 0; if (dB) *dB = 0; if (ddB) *ddB = 0; return; }
+    const double t = D - D0, lg = log(D / D0);
+    if (B) *B = -kappa * t * t * lg;
+    if (dB) *dB = -kappa * (2.0 * t * lg + t * t / D);
+    if (ddB) *ddB = -kappa * (2.0 * lg + 4.0 * t / D - t * t / (D * D));
+}
+
+__device__ void indenter_sdf(const FemIndenter& I, const double* x, double* d, double* n, double* Hd)
+{
+    double p[3], q[3];
+    for (int i = 0; i < 3; ++i) q[i] = x[i] - I.c[i];
+    for (int i = 0; i < 3; ++i) p[i] = I.R[0 * 3 + i] * q[0] + I.R[1 * 3 + i] * q[1] + I.R[2 * 3 + i] * q[2];
+    double nl[3] = {0, 0, 0}, Hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (I.type == 0) {
+        const double r = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        *d = r - I.h[0];
+        for (int i = 0; i < 3; ++i) nl[i] = p[i] / r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Hl[i * 3 + j] = ((i == j ? 1.0 : 0.0) - nl[i] * nl[j]) / r;
+    } else {
+        double u[3], sgn[3], qq[3];
+        bool act[3];
+        int nact = 0;
+        for (int i = 0; i < 3; ++i) {
+            sgn[i] = p[i] < 0 ? -1.0 : 1.0;
+            qq[i] = fabs(p[i]) - I.h[i];
+            act[i] = qq[i] > 0.0;
+            u[i] = act[i] ? qq[i] : 0.0;
+            nact += act[i] ? 1 : 0;
+        }
+        if (nact > 0) {
+            const double r = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+            *d = r;
+            for (int i = 0; i < 3; ++i) nl[i] = sgn[i] * u[i] / r;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    Hl[i * 3 + j] = (act[i] && act[j]) ? ((i == j ? 1.0 : 0.0) - nl[i] * nl[j]) / r : 0.0;
+        } else {
+            int k = 0;
+            for (int i = 1; i < 3; ++i)
+                if (qq[i] > qq[k]) k = i;
+            *d = qq[k];
+            nl[k] = sgn[k];
+        }
+    }
+    for (int i = 0; i < 3; ++i) n[i] = I.R[i * 3 + 0] * nl[0] + I.R[i * 3 + 1] * nl[1] + I.R[i * 3 + 2] * nl[2];
+    if (Hd) {
+        double T[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += I.R[i * 3 + k] * Hl[k * 3 + j];
+                T[i * 3 + j] = s;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += T[i * 3 + k] * I.R[j * 3 + k];
+                Hd[i * 3 + j] = s;
+            }
+    }
+}
+
+__device__ __forceinline__ void tet_W(const double* __restrict__ B, double W[4][3])
+{
+    for (int b = 0; b < 3; ++b) {
+        W[1][b] = B[0 * 3 + b];
+        W[2][b] = B[1 * 3 + b];
+        W[3][b] = B[2 * 3 + b];
+        W[0][b] = -(B[0 * 3 + b] + B[1 * 3 + b] + B[2 * 3 + b]);
+    }
+}
+
+__device__ __forceinline__ void tet_F(const double* x, const int* e, const double W[4][3], double* F)
+{
+    for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+            double s = 0;
+            for (int v = 0; v < 4; ++v) s += x[3 * e[v] + a] * W[v][b];
+            F[3 * b + a] = s;
+        }
+}
+
+// ---- block reductions (deterministic: fixed tree over a fixed thread -> element mapping) -----------------------------
+struct Red {
+    double buf[FEM_THREADS / 32];
+    double result;
+};
+
+template <int OP> // 0 sum, 1 min, 2 max
+__device__ double block_reduce(double v, Red* red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = OP == 0 ? v + t : (OP == 1 ? fmin(v, t) : fmax(v, t));
+    }
+    __syncthreads(); // protects red->result of a previous call
+    if ((threadIdx.x & 31) == 0) red->buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = red->buf[0];
+        for (int w = 1; w < FEM_THREADS / 32; ++w) s = OP == 0 ? s + red->buf[w] : (OP == 1 ? fmin(s, red->buf[w]) : fmax(s, red->buf[w]));
+        red->result = s;
+    }
+    __syncthreads();
+    return red->result;
+}
+
+// symmetric packed index of a 9x9 matrix (upper triangle, row-major)
+__device__ __forceinline__ int sym9(int i, int j)
+{
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    return a * 9 - a * (a - 1) / 2 + (b - a);
+}
+
+struct FemShared {
+    double* x; double* xt; double* dx; double* x0; double* r; double* z; double* p; double* Ap; double* G;
+    double* Dg;  // [V][9]  diagonal blocks, inverted in place for the preconditioner
+    double* Hc;  // [S][9]
+    Red* red;
+};
+
+__device__ double total_energy(const FemArgs& a, const FemShared& s, const double* x, const double* xprev_g,
+                               const double* aim_g, const FemIndenter& ind, double ratio, double* min_dist, double* h9_unused)
+{
+    const double dt2 = a.dt * a.dt;
+    double E = 0.0, md = 1e300;
+    bool bad = false;
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
+        double q = 0;
+        for (int c = 0; c < 3; ++c) { const double d = x[3 * i + c] - s.xt[3 * i + c]; q += d * d; }
+        E += 0.5 * a.mass[i] * q;
+    }
+    for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
+        double W[4][3], F[9], e;
+        int ev[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
+        tet_W(a.Dm_inv + 9 * t, W);
+        tet_F(x, ev, W, F);
+        snh(F, a.mu, a.lambda, &e, nullptr, nullptr);
+        E += dt2 * a.vol[t] * e;
+    }
+    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
+        const int i = a.attach[k];
+        double q = 0;
+        for (int c = 0; c < 3; ++c) {
+            const double xp = xprev_g[3 * i + c];
+            const double aimx = xp + (aim_g[3 * k + c] - xp) * ratio;
+            const double d = x[3 * i + c] - aimx;
+            q += d * d;
+        }
+        E += 0.5 * a.attach_strength * a.mass[i] * q;
+    }
+    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+        const int i = a.surf[k];
+        double d, n[3], B;
+        indenter_sdf(ind, x + 3 * i, &d, n, nullptr);
+        md = fmin(md, d);
+        if (d <= 0.0) { bad = true; continue; }
+        barrier_fn(d * d, a.d_hat, a.kappa * dt2, &B, nullptr, nullptr);
+        E += B;
+    }
+    E = block_reduce<0>(E, s.red);
+    md = block_reduce<1>(md, s.red);
+    const double anybad = block_reduce<2>(bad ? 1.0 : 0.0, s.red);
+    if (min_dist) *min_dist = md;
+    return anybad > 0.0 ? INFINITY : E;
+}
+
+__device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xprev_g, const double* aim_g,
+                          const FemIndenter& ind, double ratio, double* h9 /*[T][45] scratch*/, double* tsc /*[T][48]*/)
+{
+    const double dt2 = a.dt * a.dt;
+    for (int i = threadIdx.x; i < 3 * a.V; i += FEM_THREADS) s.G[i] = 0.0;
+    for (int i = threadIdx.x; i < 9 * a.V; i += FEM_THREADS) s.Dg[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
+        for (int c = 0; c < 3; ++c) {
+            s.G[3 * i + c] = a.mass[i] * (s.x[3 * i + c] - s.xt[3 * i + c]);
+            s.Dg[9 * i + 4 * c] = a.mass[i];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
+        int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
+        double W[4][3], F[9], dEdF[9], H[81];
+        tet_W(a.Dm_inv + 9 * t, W);
+        tet_F(s.x, e, W, F);
+        snh(F, a.mu, a.lambda, nullptr, dEdF, H);
+        const double sc = dt2 * a.vol[t];
+        for (int i = 0; i < 9; ++i) dEdF[i] *= sc;
+        for (int i = 0; i < 81; ++i) H[i] *= sc;
+        spd_project<9>(H);
+        double* hp = h9 + (size_t)t * 45;
+        for (int i = 0; i < 9; ++i)
+            for (int j = i; j < 9; ++j) hp[sym9(i, j)] = H[i * 9 + j];
+        double* to = tsc + (size_t)t * 48; // [0..11] gradient, [12 + 9 v ..] diagonal block of local vertex v
+        for (int v = 0; v < 4; ++v)
+            for (int c = 0; c < 3; ++c) {
+                double sum = 0;
+                for (int b = 0; b < 3; ++b) sum += dEdF[3 * b + c] * W[v][b];
+                to[3 * v + c] = sum;
+            }
+        for (int v = 0; v < 4; ++v)
+            for (int c = 0; c < 3; ++c)
+                for (int cc = 0; cc < 3; ++cc) {
+                    double sum = 0;
+                    for (int b = 0; b < 3; ++b)
+                        for (int b2 = 0; b2 < 3; ++b2) sum += W[v][b] * H[(3 * b + c) * 9 + (3 * b2 + cc)] * W[v][b2];
+                    to[12 + 9 * v + 3 * c + cc] = sum;
+                }
+    }
+    __syncthreads();
+    // deterministic assembly: every vertex sums its incident tets in CSR order (no atomics -> bitwise reproducible)
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
+        double g3[3] = {s.G[3 * i], s.G[3 * i + 1], s.G[3 * i + 2]};
+        double d9[9];
+        for (int j = 0; j < 9; ++j) d9[j] = s.Dg[9 * i + j];
+        for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
+            const int tv = a.adj[q];
+            const double* to = tsc + (size_t)(tv >> 2) * 48;
+            const int v = tv & 3;
+            for (int c = 0; c < 3; ++c) g3[c] += to[3 * v + c];
+            for (int j = 0; j < 9; ++j) d9[j] += to[12 + 9 * v + j];
+        }
+        for (int c = 0; c < 3; ++c) s.G[3 * i + c] = g3[c];
+        for (int j = 0; j < 9; ++j) s.Dg[9 * i + j] = d9[j];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
+        const int i = a.attach[k];
+        const double sm = a.attach_strength * a.mass[i];
+        for (int c = 0; c < 3; ++c) {
+            const double xp = xprev_g[3 * i + c];
+            const double aimx = xp + (aim_g[3 * k + c] - xp) * ratio;
+            s.G[3 * i + c] += sm * (s.x[3 * i + c] - aimx);
+            s.Dg[9 * i + 4 * c] += sm;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+        const int i = a.surf[k];
+        double d, n[3], Hd[9], dB, ddB, Hk[9];
+        for (int j = 0; j < 9; ++j) Hk[j] = 0.0;
+        indenter_sdf(ind, s.x + 3 * i, &d, n, Hd);
+        if ((d * d < a.d_hat * a.d_hat) && d > 0.0) {
+            barrier_fn(d * d, a.d_hat, a.kappa * dt2, nullptr, &dB, &ddB);
+            double dD[3];
+            for (int c = 0; c < 3; ++c) dD[c] = 2.0 * d * n[c];
+            for (int c = 0; c < 3; ++c) s.G[3 * i + c] += dB * dD[c];
+            for (int c = 0; c < 3; ++c)
+                for (int b = 0; b < 3; ++b) Hk[3 * c + b] = ddB * dD[c] * dD[b] + dB * 2.0 * (n[c] * n[b] + d * Hd[3 * c + b]);
+            spd_project<3>(Hk);
+            for (int j = 0; j < 9; ++j) s.Dg[9 * i + j] += Hk[j];
+        }
+        for (int j = 0; j < 9; ++j) s.Hc[9 * k + j] = Hk[j];
+    }
+    __syncthreads();
+}
+
+__device__ void apply_A(const FemArgs& a, const FemShared& s, const double* h9, double* tsc, const double* p, double* y)
+{
+    for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
+        int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
+        double W[4][3], P[9], Q[9], Hs[45];
+        tet_W(a.Dm_inv + 9 * t, W);
+        tet_F(p, e, W, P);
+        const double* hp = h9 + (size_t)t * 45;
+#pragma unroll
+        for (int i = 0; i < 45; ++i) Hs[i] = hp[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            double q = 0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q += Hs[sym9(i, j)] * P[j];
+            Q[i] = q;
+        }
+        double* to = tsc + (size_t)t * 48;
+        for (int v = 0; v < 4; ++v)
+            for (int c = 0; c < 3; ++c) {
+                double q = 0;
+                for (int b = 0; b < 3; ++b) q += Q[3 * b + c] * W[v][b];
+                to[3 * v + c] = q;
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) { // deterministic gather in CSR order
+        double y3[3];
+        for (int c = 0; c < 3; ++c) y3[c] = a.mass[i] * p[3 * i + c];
+        for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
+            const int tv = a.adj[q];
+            const double* to = tsc + (size_t)(tv >> 2) * 48 + 3 * (tv & 3);
+            for (int c = 0; c < 3; ++c) y3[c] += to[c];
+        }
+        for (int c = 0; c < 3; ++c) y[3 * i + c] = y3[c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
+        const int i = a.attach[k];
+        for (int c = 0; c < 3; ++c) y[3 * i + c] += a.attach_strength * a.mass[i] * p[3 * i + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+        const int i = a.surf[k];
+        for (int c = 0; c < 3; ++c)
+            for (int b = 0; b < 3; ++b) y[3 * i + c] += s.Hc[9 * k + 3 * c + b] * p[3 * i + b];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void precond(const FemArgs& a, const FemShared& s, double* z, const double* r)
+{
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS)
+        for (int c = 0; c < 3; ++c)
+            z[3 * i + c] = s.Dg[9 * i + 3 * c] * r[3 * i] + s.Dg[9 * i + 3 * c + 1] * r[3 * i + 1] + s.Dg[9 * i + 3 * c + 2] * r[3 * i + 2];
+    __syncthreads();
+}
+
+__device__ double dot_n(const FemShared& s, const double* u, const double* v, int n)
+{
+    double q = 0;
+    for (int i = threadIdx.x; i < n; i += FEM_THREADS) q += u[i] * v[i];
+    return block_reduce<0>(q, s.red);
+}
+
+// PCG, x0 = 0, b = s.G (already negated); solution in s.dx (linear_pcg.cu:45-140)
+__device__ int pcg(const FemArgs& a, const FemShared& s, const double* h9, double* tsc)
+{
+    const int n = 3 * a.V;
+    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) { // invert the diagonal blocks in place
+        double* M = s.Dg + 9 * i;
+        const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
+        const double det = m0 * (m4 * m8 - m5 * m7) - m1 * (m3 * m8 - m5 * m6) + m2 * (m3 * m7 - m4 * m6);
+        M[0] = (m4 * m8 - m5 * m7) / det; M[1] = (m2 * m7 - m1 * m8) / det; M[2] = (m1 * m5 - m2 * m4) / det;
+        M[3] = (m5 * m6 - m3 * m8) / det; M[4] = (m0 * m8 - m2 * m6) / det; M[5] = (m2 * m3 - m0 * m5) / det;
+        M[6] = (m3 * m7 - m4 * m6) / det; M[7] = (m1 * m6 - m0 * m7) / det; M[8] = (m0 * m4 - m1 * m3) / det;
+    }
+    for (int i = threadIdx.x; i < n; i += FEM_THREADS) { s.dx[i] = 0.0; s.r[i] = s.G[i]; }
+    __syncthreads();
+    precond(a, s, s.z, s.r);
+    for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.p[i] = s.z[i];
+    __syncthreads();
+    double rz = dot_n(s, s.r, s.z, n);
+    const double rz0 = fabs(rz);
+    if (rz0 == 0.0) return 0;
+    int k;
+    const int max_iter = a.pcg_max_iter_ratio * n;
+    for (k = 1; k < max_iter; ++k) {
+        apply_A(a, s, h9, tsc, s.p, s.Ap);
+        const double pAp = dot_n(s, s.p, s.Ap, n);
+        const double alpha = rz / pAp;
+        for (int i = threadIdx.x; i < n; i += FEM_THREADS) { s.dx[i] += alpha * s.p[i]; s.r[i] -= alpha * s.Ap[i]; }
+        __syncthreads();
+        precond(a, s, s.z, s.r);
+        const double rzn = dot_n(s, s.r, s.z, n);
+        if (fabs(rzn) <= a.pcg_tol_rate * rz0) break;
+        const double beta = rzn / rz;
+        for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.p[i] = s.z[i] + beta * s.p[i];
+        __syncthreads();
+        rz = rzn;
+    }
+    return k;
+}
+
+__device__ __forceinline__ FemIndenter lerp_ind(const FemIndenter& a, const FemIndenter& b, double t)
+{
+    FemIndenter o = b;
+    for (int i = 0; i < 3; ++i) o.c[i] = a.c[i] + (b.c[i] - a.c[i]) * t;
+    return o;
+}
+
+__global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 3 * a.V;
+    double* base = reinterpret_cast<double*>(smem_raw);
+    FemShared s;
+    s.x = base; s.xt = s.x + n; s.dx = s.xt + n; s.x0 = s.dx + n; s.r = s.x0 + n; s.z = s.r + n; s.p = s.z + n; s.Ap = s.p + n;
+    s.G = s.Ap + n;
+    s.Dg = s.G + n;
+    s.Hc = s.Dg + 9 * a.V;
+    s.red = reinterpret_cast<Red*>(s.Hc + 9 * a.S);
+    double* h9 = a.h9_scratch + (size_t)blockIdx.x * a.T * 45;
+    double* tsc = a.tet_scratch + (size_t)blockIdx.x * a.T * 48;
+
+    for (int env = blockIdx.x; env < a.N; env += gridDim.x) {
+        double* xg = a.x + (size_t)env * n;
+        double* vg = a.v + (size_t)env * n;
+        double* xpg = a.x_prev + (size_t)env * n;
+        const double* aim_g = a.aim + (size_t)env * 3 * a.A;
+        const FemIndenter ind_prev = a.ind_prev[env], ind_next = a.ind_next[env];
+        // predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed
+        for (int i = threadIdx.x; i < n; i += FEM_THREADS) {
+            s.x[i] = xg[i];
+            s.xt[i] = xpg[i] + a.gravity[i % 3] * a.dt * a.dt + vg[i] * a.dt;
+        }
+        __syncthreads();
+        const double abs_tol = a.velocity_tol * a.dt;
+        double res0 = 0.0, ccd_alpha = 1.0, ind_s = 0.0, last_res = 0.0, min_dist = 0.0, energy = 0.0;
+        double umax = 0.0;
+        for (int i = 0; i < 3; ++i) umax += (ind_next.c[i] - ind_prev.c[i]) * (ind_next.c[i] - ind_prev.c[i]);
+        umax = sqrt(umax);
+        int it, pcg_total = 0, ls_total = 0, conv = 0;
+        for (it = 0; it < a.newton_max_iter; ++it) {
+            const double tt = ((double)it + 1.0) / (double)a.substep;
+            const double ratio = tt < 1.0 ? tt : 1.0;
+            if (ind_s < 1.0) { // advance the prescribed indenter by at most half of the current minimum gap
+                const FemIndenter cur = lerp_ind(ind_prev, ind_next, ind_s);
+                double md = 1e300;
+                for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+                    double d, nn[3];
+                    indenter_sdf(cur, s.x + 3 * a.surf[k], &d, nn, nullptr);
+                    md = fmin(md, d);
+                }
+                md = block_reduce<1>(md, s.red);
+                double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
+                if (ds < 0.0) ds = 0.0;
+                ind_s = ind_s + ds < 1.0 ? ind_s + ds : 1.0;
+            }
+            const FemIndenter ind = lerp_ind(ind_prev, ind_next, ind_s);
+
+            grad_hess(a, s, xpg, aim_g, ind, ratio, h9, tsc);
+            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.G[i] = -s.G[i];
+            __syncthreads();
+            pcg_total += pcg(a, s, h9, tsc);
+
+            double res = 0.0;
+            for (int i = threadIdx.x; i < n; i += FEM_THREADS) res = fmax(res, fabs(s.dx[i]));
+            res = block_reduce<2>(res, s.red);
+            if (it == 0) res0 = res;
+            const double rel = res == 0.0 ? 0.0 : res / res0;
+            const bool converged = (res <= abs_tol) || (rel <= 0.001);
+            last_res = res;
+            if (it > 0 && converged && ccd_alpha >= 1.0 && ratio >= 1.0 && ind_s >= 1.0) { conv = 1; break; }
+
+            // line search (sim_engine_do_advance.cu:276-347)
+            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x0[i] = s.x[i];
+            __syncthreads();
+            double alpha = 1.0;
+            for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+                const int i = a.surf[k];
+                double d, nn[3];
+                indenter_sdf(ind, s.x0 + 3 * i, &d, nn, nullptr);
+                const double len = sqrt(s.dx[3 * i] * s.dx[3 * i] + s.dx[3 * i + 1] * s.dx[3 * i + 1] + s.dx[3 * i + 2] * s.dx[3 * i + 2]);
+                if (len > 0.0 && d < 2.0 * len + a.d_hat) alpha = fmin(alpha, 0.8 * d / len);
+            }
+            alpha = block_reduce<1>(alpha, s.red);
+            ccd_alpha = alpha;
+            const double E0 = total_energy(a, s, s.x0, xpg, aim_g, ind, ratio, nullptr, nullptr);
+            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x[i] = s.x0[i] + alpha * s.dx[i];
+            __syncthreads();
+            double E = total_energy(a, s, s.x, xpg, aim_g, ind, ratio, &min_dist, nullptr);
+            if (!converged) {
+                int ls = 0;
+                while (ls < a.ls_max_iter) {
+                    if (E <= E0) break;
+                    alpha *= 0.5;
+                    for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x[i] = s.x0[i] + alpha * s.dx[i];
+                    __syncthreads();
+                    E = total_energy(a, s, s.x, xpg, aim_g, ind, ratio, &min_dist, nullptr);
+                    ++ls;
+                    ++ls_total;
+                }
+            }
+            energy = E;
+        }
+        // update velocity (fem_bdf1_time_integrator.cu:58-77), write back
+        for (int i = threadIdx.x; i < n; i += FEM_THREADS) {
+            const double xn = s.x[i];
+            vg[i] = (xn - xpg[i]) * (1.0 / a.dt);
+            xpg[i] = xn;
+            xg[i] = xn;
+        }
+        if (threadIdx.x == 0 && a.stats) {
+            FemStats st;
+            st.converged = conv; st.newton_iters = it; st.pcg_iters = pcg_total; st.ls_halvings = ls_total;
+            st.min_dist = min_dist; st.last_res = last_res; st.energy = energy;
+            a.stats[env] = st;
+        }
+        __syncthreads();
+    }
+}
+
+size_t fem_smem_bytes(int V, int S) { return sizeof(double) * (9 * 3 * (size_t)V + 9 * (size_t)V + 9 * (size_t)S) + sizeof(Red) + 64; }
+
+cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st)
+{
+    const size_t smem = fem_smem_bytes(a.V, a.S);
+    cudaError_t e = cudaFuncSetAttribute(fem_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fem_step_kernel<<<grid, FEM_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- FEM marker read-out: barycentric interpolation on the gel's top surface + pinhole projection ----------------------
+// ref: source/tacex/tacex/simulation_approaches/fem_based/sim/tactile_sensor_sapienipc_modified.py:354-413 (gen_marker_flow;
+// the weights are precomputed once here, the reference recomputes them every step and only for env 0)
+__global__ void fem_marker_kernel(const FemMarkerArgs m)
+{
+    const int env = blockIdx.x;
+    for (int k = threadIdx.x; k < m.M; k += blockDim.x) {
+        const int* tri = m.tri + 3 * k;
+        const double* w = m.weights + 3 * k;
+        float* out = m.out + ((size_t)env * 2 * m.M + k) * 2;
+        for (int which = 0; which < 2; ++which) {
+            const double* X = which == 0 ? m.x_rest : m.x + (size_t)env * 3 * m.V;
+            double pw[3] = {0, 0, 0};
+            for (int c = 0; c < 3; ++c) pw[c] = w[0] * X[3 * tri[0] + c] + w[1] * X[3 * tri[1] + c] + w[2] * X[3 * tri[2] + c];
+            // world -> camera frame: p_cam = Rc^T (p - tc)
+            double pc[3];
+            for (int c = 0; c < 3; ++c)
+                pc[c] = m.cam_R[0 * 3 + c] * (pw[0] - m.cam_t[0]) + m.cam_R[1 * 3 + c] * (pw[1] - m.cam_t[1]) + m.cam_R[2 * 3 + c] * (pw[2] - m.cam_t[2]);
+            const double u = m.fx * pc[0] / pc[2] + m.cx, vv = m.fy * pc[1] / pc[2] + m.cy;
+            float* o = out + (size_t)which * m.M * 2;
+            o[0] = (float)u;
+            o[1] = (float)vv;
+        }
+    }
+}
+
+cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st)
+{
+    fem_marker_kernel<<<N, 128, 0, st>>>(m);
+    return cudaGetLastError();
+}
+
+} // namespace tx

@@ -55,6 +55,44 @@ struct FotsArgs {
     double lamb0, lamb1, lamb2, mm2pix, shear_max, theta_max;
 };
 
+// ---- gel FEM ---------------------------------------------------------------------------------------------------------
+typedef tx_fem_indenter FemIndenter;
+typedef tx_fem_stats FemStats;
+
+struct FemArgs {
+    int N, V, T, A, S;
+    const int* tets;       // [T][4]
+    const double* Dm_inv;  // [T][9]
+    const double* vol;     // [T]   elastic rest "volume" (det Dm or det Dm / 6)
+    const double* mass;    // [V]
+    const int* attach;     // [A]
+    const int* surf;       // [S]
+    double* x; double* v; double* x_prev; // [N][V][3]
+    const double* aim;     // [N][A][3]
+    const FemIndenter* ind_prev; const FemIndenter* ind_next; // [N]
+    FemStats* stats;       // [N] or nullptr
+    double* h9_scratch;    // [grid][T][45]
+    double* tet_scratch;   // [grid][T][48] per-tet contributions (12 gradient / operator outputs + 4 diagonal 3x3 blocks)
+    const int* adj_off;    // [V+1] CSR of the vertex -> (tet, local vertex) incidence, entries = 4 * tet + local
+    const int* adj;        // [4T]
+    double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate;
+    int newton_max_iter, pcg_max_iter_ratio, ls_max_iter, substep;
+};
+
+struct FemMarkerArgs {
+    int V, M;
+    const int* tri;        // [M][3] vertex ids of the surface triangle carrying marker k
+    const double* weights; // [M][3] barycentric weights
+    const double* x_rest;  // [V][3]
+    const double* x;       // [N][V][3]
+    float* out;            // [N][2][M][2]
+    double cam_R[9], cam_t[3], fx, fy, cx, cy;
+};
+
+size_t fem_smem_bytes(int V, int S);
+cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
+
 cudaError_t upload_taps(const float* host_taps, cudaStream_t s);
 int taxim_smem_bytes();
 cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);

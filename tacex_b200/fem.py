@@ -1,0 +1,182 @@
+"""GelFemEngine -- PyTorch-facing owner of one ``tx_fem`` handle: the batched gel FEM substep and the FEM marker read-out.
+
+Host-side mirror of the reference's UIPC glue for the gel pad only (ref: source/tacex_uipc/tacex_uipc/sim/uipc_sim.py:32-131
+configuration and :250-252 ``step``; objects/uipc_object.py:442-470 constitution set-up; sim/uipc_attachments.py:118-142,
+364-428 attachment of the gel to the rigid case; source/tacex/tacex/simulation_approaches/fem_based/mani_skill_sim.py and
+sim/tactile_sensor_sapienipc_modified.py:189-413 marker grid / weights / projection). The indenter is a prescribed rigid
+analytic body (the rigid-contact query of Isaac Sim is upstream and stubbed with recorded poses).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .gel_mesh import GelMesh, lame
+
+
+@dataclass
+class GelFemCfg:
+    """Defaults = UipcSimCfg / UipcObject defaults used by the reference's GelSight Mini FEM preset."""
+
+    youngs_modulus: float = 1e4      # 0.01 MPa (uipc_object.py:59)
+    poisson_rate: float = 0.49       # (uipc_object.py:79)
+    mass_density: float = 1e3        # (uipc_object.py:84)
+    dt: float = 0.01                 # (uipc_sim.py)
+    gravity: tuple = (0.0, 0.0, -9.8)
+    attach_strength: float = 1000.0  # benchmark scene (ball_rolling_uipc.py:121); UipcIsaacAttachments default 100
+    d_hat: float = 5e-4              # benchmark scene; libuipc default 0.01
+    contact_resistance: float = 1e10  # 10 GPa (uipc_sim.py:110)
+    newton_max_iter: int = 1024
+    newton_velocity_tol: float = 0.05
+    pcg_tol_rate: float = 1e-3
+    line_search_max_iter: int = 8
+    animator_substep: int = 1
+    rest_volume_det: bool = True     # reproduce libuipc's det(Dm) elastic rest "volume" 
+
+
+def indenter_array(kind, centers, half, R=None, device="cuda") -> torch.Tensor:
+    """Packs N indenter poses into the device layout of ``tx_fem_indenter`` (int + 15 doubles, 128 bytes each)."""
+    centers = np.asarray(centers, np.float64).reshape(-1, 3)
+    N = centers.shape[0]
+    arr = (_lib.TxFemIndenter * N)()
+    kinds = np.broadcast_to(np.asarray(kind), (N,))
+    halfs = np.broadcast_to(np.asarray(half, np.float64), (N, 3))
+    Rs = np.broadcast_to(np.eye(3) if R is None else np.asarray(R, np.float64), (N, 3, 3))
+    for i in range(N):
+        arr[i].type = int(kinds[i])
+        arr[i].c[:] = centers[i].tolist()
+        arr[i].R[:] = Rs[i].reshape(-1).tolist()
+        arr[i].h[:] = halfs[i].tolist()
+    buf = np.frombuffer(arr, dtype=np.uint8).copy()
+    return torch.from_numpy(buf).to(device)
+
+
+class GelFemEngine:
+    def __init__(self, mesh: GelMesh, cfg: GelFemCfg | None = None, device: str | torch.device = "cuda"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.TxError("GelFemEngine needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.mesh, self.cfg = mesh, cfg or GelFemCfg()
+        c = self.cfg
+        lam, mu = lame(c.youngs_modulus, c.poisson_rate)
+        g = _lib.TxFemConfig()
+        g.V, g.T, g.A, g.S = len(mesh.X), len(mesh.tets), len(mesh.attach), len(mesh.surf)
+        g.dt = c.dt
+        g.gravity[:] = c.gravity
+        g.mu, g.lam, g.density, g.attach_strength = mu, lam, c.mass_density, c.attach_strength
+        g.d_hat, g.kappa = c.d_hat, c.contact_resistance
+        g.newton_max_iter, g.velocity_tol, g.pcg_tol_rate = c.newton_max_iter, c.newton_velocity_tol, c.pcg_tol_rate
+        g.pcg_max_iter_ratio, g.ls_max_iter, g.substep = 2, c.line_search_max_iter, c.animator_substep
+        g.rest_volume_det = int(c.rest_volume_det)
+        self.g = g
+        X = np.ascontiguousarray(mesh.X, np.float64)
+        tets = np.ascontiguousarray(mesh.tets, np.int32)
+        att = np.ascontiguousarray(mesh.attach, np.int32)
+        surf = np.ascontiguousarray(mesh.surf, np.int32)
+        with torch.cuda.device(idx):
+            self.stream = torch.cuda.current_stream()
+            h = C.c_void_p()
+            rc = self.lib.tx_fem_create(C.byref(g), X.ctypes.data, tets.ctypes.data, att.ctypes.data, surf.ctypes.data, idx,
+                                        C.c_void_p(self.stream.cuda_stream), C.byref(h))
+            if rc != 0:
+                raise _lib.TxError(f"tx_fem_create failed ({rc}): {self.lib.tx_fem_last_error(None).decode()}")
+        self.h = h
+        self.V, self.A, self.S, self.M = g.V, g.A, g.S, 0
+        self.X = torch.from_numpy(X).to(self.device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.TxError(f"libtacex_b200 fem error {rc}: {self.lib.tx_fem_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tx_fem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mass(self) -> np.ndarray:
+        m = np.empty(self.V)
+        self._check(self.lib.tx_fem_get_mass(self.h, m.ctypes.data))
+        return m
+
+    def new_state(self, N: int):
+        x = self.X[None].repeat(N, 1, 1).contiguous()
+        return x, torch.zeros_like(x), x.clone()
+
+    def rest_aim(self, N: int) -> torch.Tensor:
+        return self.X[torch.from_numpy(self.mesh.attach.astype(np.int64)).to(self.device)][None].repeat(N, 1, 1).contiguous()
+
+    def step(self, x, v, x_prev, aim, ind_prev: torch.Tensor, ind_next: torch.Tensor, want_stats: bool = True):
+        N = x.shape[0]
+        st = torch.zeros((N, C.sizeof(_lib.TxFemStats)), dtype=torch.uint8, device=self.device) if want_stats else None
+        self._check(self.lib.tx_fem_step(self.h, x.data_ptr(), v.data_ptr(), x_prev.data_ptr(), aim.data_ptr(),
+                                         ind_prev.data_ptr(), ind_next.data_ptr(), N, None if st is None else st.data_ptr()))
+        return st
+
+    @staticmethod
+    def decode_stats(st: torch.Tensor) -> list[dict]:
+        raw = st.cpu().numpy().tobytes()
+        n = st.shape[0]
+        arr = (_lib.TxFemStats * n).from_buffer_copy(raw)
+        return [{k: getattr(s, k) for k, _ in _lib.TxFemStats._fields_} for s in arr]
+
+    # -- FEM marker read-out (ManiSkill-ViTac style) ---------------------------------------------------------------------
+    def set_markers(self, tri: np.ndarray, weights: np.ndarray, cam_R=None, cam_t=(0.0, 0.0, 0.0285), intrinsics=(340.0, 325.0, 160.0, 125.0)):
+        tri = np.ascontiguousarray(tri, np.int32)
+        w = np.ascontiguousarray(weights, np.float64)
+        R = np.ascontiguousarray(np.diag([1.0, -1.0, -1.0]) if cam_R is None else cam_R, np.float64)
+        t = np.ascontiguousarray(cam_t, np.float64)
+        fx, fy, cx, cy = intrinsics
+        self._check(self.lib.tx_fem_set_markers(self.h, len(tri), tri.ctypes.data, w.ctypes.data, R.ctypes.data, t.ctypes.data,
+                                                fx, fy, cx, cy))
+        self.M = len(tri)
+
+    def markers(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        N = x.shape[0]
+        out = torch.empty((N, 2, self.M, 2), device=self.device) if out is None else out
+        self._check(self.lib.tx_fem_markers(self.h, x.data_ptr(), N, out.data_ptr()))
+        return out
+
+
+def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=128):
+    """Marker grid on the gel's top surface and its barycentric weights (init time, host).
+
+    Restates ``_gen_marker_grid`` / ``_gen_marker_weight`` of the reference's FEM marker sensor
+    (tactile_sensor_sapienipc_modified.py:189-329) for the default configuration (all random ranges zero): a
+    ``cols x rows`` grid with ``pitch`` spacing centred on the pad, markers outside the surface are dropped, the list
+    is padded to ``pad_to`` by repeating the last marker (mani_skill_sim_cfg.py:17,54)."""
+    X = mesh.X
+    tris = mesh.top_tris
+    xs = (np.arange(cols) - (cols - 1) / 2) * pitch
+    ys = (np.arange(rows) - (rows - 1) / 2) * pitch
+    pts = np.array([[x, y] for x in xs for y in ys])
+    out_tri, out_w = [], []
+    A, B, Cc = X[tris[:, 0], :2], X[tris[:, 1], :2], X[tris[:, 2], :2]
+    for p in pts:
+        v0, v1, v2 = B - A, Cc - A, p - A
+        d00 = (v0 * v0).sum(1); d01 = (v0 * v1).sum(1); d11 = (v1 * v1).sum(1)
+        d20 = (v2 * v0).sum(1); d21 = (v2 * v1).sum(1)
+        den = d00 * d11 - d01 * d01
+        b1 = (d11 * d20 - d01 * d21) / den
+        b2 = (d00 * d21 - d01 * d20) / den
+        b0 = 1 - b1 - b2
+        inside = np.where((b0 >= -1e-12) & (b1 >= -1e-12) & (b2 >= -1e-12))[0]
+        if inside.size:
+            k = inside[0]
+            out_tri.append(tris[k]); out_w.append([b0[k], b1[k], b2[k]])
+    while len(out_tri) < pad_to:
+        out_tri.append(out_tri[-1]); out_w.append(out_w[-1])
+    return np.asarray(out_tri[:pad_to], np.int32), np.asarray(out_w[:pad_to], np.float64)

@@ -1,0 +1,98 @@
+"""GPU parity tests of the batched gel FEM substep against the float64 CPU restatement (protocol P5; PARITY UNPINNED vs
+libuipc itself, see oracle/fem_canon.c)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cells, vtol, N):
+    from oracle import fem_canon as fc
+    from tacex_b200 import fem, gel_mesh
+
+    m = gel_mesh.box_gel(cells=cells)
+    cfg = fem.GelFemCfg(newton_velocity_tol=vtol)
+    eng = fem.GelFemEngine(m, cfg)
+    cf = fc.CanonFem(m, velocity_tol=vtol)
+    return m, eng, cf, fc
+
+
+def test_mass_and_rest_fixed_point():
+    m, eng, cf, fc = _setup((10, 12, 3), 1e-3, 2)
+    assert np.allclose(eng.mass(), cf.mass, rtol=0, atol=1e-18)
+    x, v, xp = eng.new_state(2)
+    from tacex_b200 import fem
+
+    far = fem.indenter_array(0, [[0, 0, 1.0]] * 2, (1e-3, 0, 0))
+    st = eng.step(x, v, xp, eng.rest_aim(2), far, far)
+    torch.cuda.synchronize()
+    s = eng.decode_stats(st)
+    assert all(q["converged"] == 1 for q in s)
+    # gravity sag of a 10 kPa gel attached at its bottom is tiny but non-zero and identical in both envs
+    # the element -> vertex assembly is an ordered gather (no atomics): results are bitwise reproducible
+    assert torch.equal(x[0], x[1]) and float((x[0] - eng.X).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("kind,half", [(0, (3e-3, 0, 0)), (1, (2e-3, 3e-3, 1e-3))])
+def test_press_30_steps_matches_cpu_restatement(kind, half):
+    """Vertex positions within 1e-4 m (target: << 1e-6 m) of the float64 CPU restatement after each of 30 steps, tolerances
+    tightened on both sides (velocity_tol 1e-3 m/s); two envs with different indenter offsets."""
+    from tacex_b200 import fem
+
+    m, eng, cf, fc = _setup((10, 12, 3), 1e-3, 2)
+    N = 2
+    offs = np.array([[0.0, 0.0], [4e-3, -5e-3]])  # centre press and a press near the edge / corner
+    top = 4.5e-3
+    z0 = top + (half[0] if kind == 0 else half[2]) + 4e-4
+    th = 0.3
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]) if kind == 1 else np.eye(3)
+    x, v, xp = eng.new_state(N)
+    aim = eng.rest_aim(N)
+    xc, vc, xpc = cf.new_state(N)
+    aimc = cf.X[cf.attach][None].repeat(N, 0)
+    ctr = lambda s: [[offs[i, 0], offs[i, 1], z0 - 1e-3 * s / 30] for i in range(N)]  # noqa: E731
+    worst = 0.0
+    for s in range(30):
+        ip = fem.indenter_array(kind, ctr(s), half, R)
+        inx = fem.indenter_array(kind, ctr(s + 1), half, R)
+        st = eng.step(x, v, xp, aim, ip, inx)
+        cst = cf.step(xc, vc, xpc, aimc, [fc.make_indenter(kind, c, half, R) for c in ctr(s)],
+                      [fc.make_indenter(kind, c, half, R) for c in ctr(s + 1)])
+        torch.cuda.synchronize()
+        d = np.abs(x.cpu().numpy() - xc).max()
+        worst = max(worst, d)
+        gs = eng.decode_stats(st)
+        assert d <= 1e-4, f"step {s}: {d}"
+        for i in range(N):
+            assert gs[i]["min_dist"] > 0 and np.isfinite(gs[i]["energy"])
+            assert gs[i]["newton_iters"] == cst[i]["newton_iters"], (s, gs[i], cst[i])
+    print(f"kind {kind}: max |x_gpu - x_cpu| over 30 steps = {worst:.3e} m")
+    # observed: ~1e-9 m (sphere) and ~1.5e-6 m (rotated box: the box SDF is only C0 across face/edge/corner regions, so
+    # last-bit differences of log / reductions are amplified); the bar of protocol P5 is 1e-4 m
+    assert worst <= (1e-7 if kind == 0 else 1e-5)
+    assert float((x[0] - eng.X).abs().max()) > 3e-4  # the gel really deformed
+
+
+def test_marker_readout_projection():
+    from tacex_b200 import fem, gel_mesh
+
+    m = gel_mesh.box_gel()
+    eng = fem.GelFemEngine(m)
+    tri, w = fem.marker_grid_weights(m)
+    assert tri.shape == (128, 3) and np.allclose(w.sum(1), 1)
+    eng.set_markers(tri, w)
+    x, v, xp = eng.new_state(3)
+    x[1, :, 0] += 1e-3  # rigid shift of env 1 by 1 mm in x
+    mk = eng.markers(x).cpu().numpy()
+    torch.cuda.synchronize()
+    # numpy reference of the same read-out
+    X = m.X
+    P = (w[:, :, None] * X[tri]).sum(1)
+    Rc = np.diag([1.0, -1.0, -1.0]); tc = np.array([0, 0, 0.0285])
+    pc = (P - tc) @ Rc
+    u = 340 * pc[:, 0] / pc[:, 2] + 160; vv = 325 * pc[:, 1] / pc[:, 2] + 125
+    assert np.abs(mk[0, 0, :, 0] - u).max() < 1e-3 and np.abs(mk[0, 0, :, 1] - vv).max() < 1e-3
+    assert np.array_equal(mk[0, 0], mk[0, 1]) and np.array_equal(mk[2], mk[0])
+    du = mk[1, 1, :, 0] - mk[1, 0, :, 0]
+    assert np.allclose(du, 340 * 1e-3 / pc[:, 2], atol=1e-3)  # 1 mm at 24 mm -> ~14 px
