@@ -113,7 +113,12 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
     FEM_CUDA_C(cudaMemcpy(f->d_tets, tets, sizeof(int) * 4 * c->T, cudaMemcpyHostToDevice));
     if (c->A > 0) FEM_CUDA_C(cudaMemcpy(f->d_attach, attach, sizeof(int) * c->A, cudaMemcpyHostToDevice));
     if (c->S > 0) FEM_CUDA_C(cudaMemcpy(f->d_surf, surf, sizeof(int) * c->S, cudaMemcpyHostToDevice));
-    FEM_CUDA_C(cudaMemcpy(f->d_Dm_inv, Dmi.data(), sizeof(double) * 9 * c->T, cudaMemcpyHostToDevice));
+    {   // structure-of-arrays [9][T] for coalesced per-tet loads
+        std::vector<double> soa((size_t)9 * c->T);
+        for (int t = 0; t < c->T; ++t)
+            for (int k = 0; k < 9; ++k) soa[(size_t)k * c->T + t] = Dmi[(size_t)9 * t + k];
+        FEM_CUDA_C(cudaMemcpy(f->d_Dm_inv, soa.data(), sizeof(double) * 9 * c->T, cudaMemcpyHostToDevice));
+    }
     FEM_CUDA_C(cudaMemcpy(f->d_vol, vol.data(), sizeof(double) * c->T, cudaMemcpyHostToDevice));
     FEM_CUDA_C(cudaMemcpy(f->d_mass, f->mass.data(), sizeof(double) * c->V, cudaMemcpyHostToDevice));
     FEM_CUDA_C(cudaMemcpy(f->d_X, X, sizeof(double) * 3 * c->V, cudaMemcpyHostToDevice));

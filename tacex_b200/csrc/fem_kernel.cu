@@ -69,6 +69,25 @@ __device__ void jacobi_evd(double* A, double* w, double* Vv)
     for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
 
+// LDL^T with all pivots > 0 proves that H is positive definite (then make_spd is the identity)
+template <int n>
+__device__ bool is_pd(const double* H)
+{
+    double L[n * n], D[n];
+    for (int j = 0; j < n; ++j) {
+        double d = H[j * n + j];
+        for (int k = 0; k < j; ++k) d -= L[j * n + k] * L[j * n + k] * D[k];
+        if (!(d > 0.0)) return false;
+        D[j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = H[i * n + j];
+            for (int k = 0; k < j; ++k) s -= L[i * n + k] * L[j * n + k] * D[k];
+            L[i * n + j] = s / d;
+        }
+    }
+    return true;
+}
+
 // make_spd with the LDL^T fast path (an all-positive-pivot factorisation proves H is already positive definite)
 template <int n>
 __device__ void spd_project(double* H)
@@ -132,6 +151,142 @@ __device__ void snh(const double* F, double mu, double lambda, double* E, double
                 }
         }
     }
+}
+
+// ---- analytic SPD projection of the stable Neo-Hookean Hessian --------------------------------------------------------
+// make_spd (utils/make_spd.h:7-19) clamps the negative eigenvalues of d2Psi/dF2. For Psi = mu/2 (I_C - 3) - mu (J - 1) +
+// lambda/2 (J - 1)^2 the Hessian is H = mu I + c H_J + lambda g_J g_J^T with c = lambda (J - 1) - mu. In the frame of the
+// rotation-variant SVD F = U S V^T (det U = det V = 1) it is block diagonal: a 3x3 "scaling" block on (d11, d22, d33),
+//   A = mu I + c [[0, s3, s2], [s3, 0, s1], [s2, s1, 0]] + lambda w w^T,  w = (s2 s3, s1 s3, s1 s2),
+// and, for every index pair (i, j) with third index k, a 2x2 block [[mu, -c s_k], [-c s_k, mu]] on (d_ij, d_ji) whose
+// eigenpairs are the twist (1, -1)/sqrt2 : mu + c s_k and the flip (1, 1)/sqrt2 : mu - c s_k. Clamping those nine
+// eigenvalues and rotating back gives the same matrix as the numeric 9x9 eigen-decomposition the reference (and the CPU
+// checker) use, at a fraction of the cost and without spilling an 81-entry work matrix per thread.
+__device__ __forceinline__ void jrot(double& app, double& aqq, double& apq, double& arp, double& arq, double& vp0,
+                                     double& vq0, double& vp1, double& vq1, double& vp2, double& vq2)
+{
+    if (apq == 0.0) return;
+    const double theta = (aqq - app) / (2.0 * apq);
+    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+    const double app_n = app - t * apq, aqq_n = aqq + t * apq;
+    const double arp_n = c * arp - s * arq, arq_n = s * arp + c * arq;
+    app = app_n; aqq = aqq_n; apq = 0.0; arp = arp_n; arq = arq_n;
+    double a, b;
+    a = vp0; b = vq0; vp0 = c * a - s * b; vq0 = s * a + c * b;
+    a = vp1; b = vq1; vp1 = c * a - s * b; vq1 = s * a + c * b;
+    a = vp2; b = vq2; vp2 = c * a - s * b; vq2 = s * a + c * b;
+}
+
+// eigen-decomposition of a symmetric 3x3 (a00 a01 a02 a11 a12 a22); eigenvectors are the COLUMNS of V (row-major v[r][c])
+__device__ __forceinline__ void jacobi3(double a00, double a01, double a02, double a11, double a12, double a22, double w[3],
+                                        double v[3][3])
+{
+    double v00 = 1, v01 = 0, v02 = 0, v10 = 0, v11 = 1, v12 = 0, v20 = 0, v21 = 0, v22 = 1;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = a01 * a01 + a02 * a02 + a12 * a12;
+        if (off <= 1e-32 * (a00 * a00 + a11 * a11 + a22 * a22 + 1e-300)) break;
+        jrot(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21); // (p, q) = (0, 1), r = 2
+        jrot(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22); // (0, 2), r = 1
+        jrot(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22); // (1, 2), r = 0
+    }
+    w[0] = a00; w[1] = a11; w[2] = a22;
+    v[0][0] = v00; v[0][1] = v01; v[0][2] = v02; v[1][0] = v10; v[1][1] = v11; v[1][2] = v12; v[2][0] = v20; v[2][1] = v21; v[2][2] = v22;
+}
+
+// H (81, row-major over the column-major vec(F)) <- scale * SPD-projected SNH Hessian at F
+__device__ void snh_hessian_spd_analytic(const double* F, double mu, double lambda, double scale, double* H)
+{
+    // C = F^T F
+    double Cm[6];
+    {
+        const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
+        Cm[0] = f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2];
+        Cm[1] = f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2];
+        Cm[2] = f0[0] * f2[0] + f0[1] * f2[1] + f0[2] * f2[2];
+        Cm[3] = f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2];
+        Cm[4] = f1[0] * f2[0] + f1[1] * f2[1] + f1[2] * f2[2];
+        Cm[5] = f2[0] * f2[0] + f2[1] * f2[1] + f2[2] * f2[2];
+    }
+    double w[3], V[3][3];
+    jacobi3(Cm[0], Cm[1], Cm[2], Cm[3], Cm[4], Cm[5], w, V);
+    // sort columns by descending eigenvalue
+#define SWAPC(i, j)                                                                                                    \
+    if (w[i] < w[j]) {                                                                                                \
+        double t_ = w[i]; w[i] = w[j]; w[j] = t_;                                                                     \
+        for (int r_ = 0; r_ < 3; ++r_) { t_ = V[r_][i]; V[r_][i] = V[r_][j]; V[r_][j] = t_; }                         \
+    }
+    SWAPC(0, 1) SWAPC(0, 2) SWAPC(1, 2)
+#undef SWAPC
+    const double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
+                        V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+    if (detV < 0.0)
+        for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
+    // U: u0 = F v0 / |.|, u1 = Gram-Schmidt(F v1), u2 = u0 x u1 ; signed singular values s_i = u_i . F v_i
+    double Fv[3][3]; // Fv[i] = F v_i
+    for (int i = 0; i < 3; ++i)
+        for (int r = 0; r < 3; ++r) Fv[i][r] = F[r] * V[0][i] + F[3 + r] * V[1][i] + F[6 + r] * V[2][i];
+    double U[3][3]; // columns u_i stored as U[r][i]
+    double n0 = sqrt(Fv[0][0] * Fv[0][0] + Fv[0][1] * Fv[0][1] + Fv[0][2] * Fv[0][2]);
+    for (int r = 0; r < 3; ++r) U[r][0] = Fv[0][r] / n0;
+    double d01 = U[0][0] * Fv[1][0] + U[1][0] * Fv[1][1] + U[2][0] * Fv[1][2];
+    double t1[3] = {Fv[1][0] - d01 * U[0][0], Fv[1][1] - d01 * U[1][0], Fv[1][2] - d01 * U[2][0]};
+    double n1 = sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+    for (int r = 0; r < 3; ++r) U[r][1] = t1[r] / n1;
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    double sg[3];
+    for (int i = 0; i < 3; ++i) sg[i] = U[0][i] * Fv[i][0] + U[1][i] * Fv[i][1] + U[2][i] * Fv[i][2];
+    const double J = sg[0] * sg[1] * sg[2];
+    const double c = lambda * (J - 1.0) - mu;
+    // scaling block
+    const double sw[3] = {sg[1] * sg[2], sg[0] * sg[2], sg[0] * sg[1]};
+    double aw[3], Q[3][3];
+    jacobi3(mu + lambda * sw[0] * sw[0], c * sg[2] + lambda * sw[0] * sw[1], c * sg[1] + lambda * sw[0] * sw[2],
+            mu + lambda * sw[1] * sw[1], c * sg[0] + lambda * sw[1] * sw[2], mu + lambda * sw[2] * sw[2], aw, Q);
+    double Ap[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double q = 0;
+            for (int k = 0; k < 3; ++k) q += Q[i][k] * (aw[k] < 0.0 ? 0.0 : aw[k]) * Q[j][k];
+            Ap[i][j] = q * scale;
+        }
+    // rotated-frame Hessian Hh over indices (a, b) of d-hat, idx = 3 b + a (column-major like vec F)
+    double Hh[81];
+    for (int i = 0; i < 81; ++i) Hh[i] = 0.0;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Hh[(4 * i) * 9 + 4 * j] = Ap[i][j]; // (i,i) <-> (j,j): idx 3i+i = 4i
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j) {
+            const int k = 3 - i - j;
+            const double lt = mu + c * sg[k], lf = mu - c * sg[k];
+            const double ltp = lt < 0.0 ? 0.0 : lt, lfp = lf < 0.0 ? 0.0 : lf;
+            const double dd = 0.5 * (ltp + lfp) * scale, od = 0.5 * (lfp - ltp) * scale;
+            const int pij = 3 * j + i, pji = 3 * i + j; // d_ij: row i, col j
+            Hh[pij * 9 + pij] = dd; Hh[pji * 9 + pji] = dd; Hh[pij * 9 + pji] = od; Hh[pji * 9 + pij] = od;
+        }
+    // rotate back: vec(dF) = T vec(d-hat), T[(3 j + i), (3 b + a)] = U[i][a] V[j][b];  H = T Hh T^T
+    double tmp[81]; // tmp = T Hh
+    for (int r = 0; r < 9; ++r) {
+        const int i = r % 3, j = r / 3;
+        for (int q2 = 0; q2 < 9; ++q2) {
+            double acc = 0;
+            for (int p2 = 0; p2 < 9; ++p2) {
+                const double h = Hh[p2 * 9 + q2];
+                if (h != 0.0) acc += U[i][p2 % 3] * V[j][p2 / 3] * h;
+            }
+            tmp[r * 9 + q2] = acc;
+        }
+    }
+    for (int r = 0; r < 9; ++r)
+        for (int r2 = 0; r2 < 9; ++r2) {
+            const int k = r2 % 3, l = r2 / 3;
+            double acc = 0;
+            for (int q2 = 0; q2 < 9; ++q2) acc += tmp[r * 9 + q2] * U[k][q2 % 3] * V[l][q2 / 3];
+            H[r * 9 + r2] = acc;
+        }
 }
 
 __device__ __forceinline__ void barrier_fn(double D, double d_hat, double kappa, double* B, double* dB, double* ddB)
@@ -200,22 +355,33 @@ __device__ void indenter_sdf(const FemIndenter& I, const double* x, double* d, d
     }
 }
 
-__device__ __forceinline__ void tet_W(const double* __restrict__ B, double W[4][3])
+// Dm^-1 is stored structure-of-arrays ([9][T]) so that consecutive threads (tets) read consecutive addresses
+__device__ __forceinline__ void tet_W(const double* __restrict__ Bsoa, int t, int T, double W[4][3])
 {
+#pragma unroll
     for (int b = 0; b < 3; ++b) {
-        W[1][b] = B[0 * 3 + b];
-        W[2][b] = B[1 * 3 + b];
-        W[3][b] = B[2 * 3 + b];
-        W[0][b] = -(B[0 * 3 + b] + B[1 * 3 + b] + B[2 * 3 + b]);
+        const double b0 = Bsoa[(0 * 3 + b) * T + t], b1 = Bsoa[(1 * 3 + b) * T + t], b2 = Bsoa[(2 * 3 + b) * T + t];
+        W[1][b] = b0;
+        W[2][b] = b1;
+        W[3][b] = b2;
+        W[0][b] = -(b0 + b1 + b2);
     }
 }
 
 __device__ __forceinline__ void tet_F(const double* x, const int* e, const double W[4][3], double* F)
 {
+    double xe[4][3];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xe[v][a] = x[3 * e[v] + a];
+#pragma unroll
     for (int b = 0; b < 3; ++b)
+#pragma unroll
         for (int a = 0; a < 3; ++a) {
             double s = 0;
-            for (int v = 0; v < 4; ++v) s += x[3 * e[v] + a] * W[v][b];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) s += xe[v][a] * W[v][b];
             F[3 * b + a] = s;
         }
 }
@@ -274,7 +440,7 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         double W[4][3], F[9], e;
         int ev[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
-        tet_W(a.Dm_inv + 9 * t, W);
+        tet_W(a.Dm_inv, t, a.T, W);
         tet_F(x, ev, W, F);
         snh(F, a.mu, a.lambda, &e, nullptr, nullptr);
         E += dt2 * a.vol[t] * e;
@@ -323,22 +489,21 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xp
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
         double W[4][3], F[9], dEdF[9], H[81];
-        tet_W(a.Dm_inv + 9 * t, W);
+        tet_W(a.Dm_inv, t, a.T, W);
         tet_F(s.x, e, W, F);
         snh(F, a.mu, a.lambda, nullptr, dEdF, H);
         const double sc = dt2 * a.vol[t];
         for (int i = 0; i < 9; ++i) dEdF[i] *= sc;
         for (int i = 0; i < 81; ++i) H[i] *= sc;
-        spd_project<9>(H);
-        double* hp = h9 + (size_t)t * 45;
+        if (!is_pd<9>(H)) snh_hessian_spd_analytic(F, a.mu, a.lambda, sc, H);
         for (int i = 0; i < 9; ++i)
-            for (int j = i; j < 9; ++j) hp[sym9(i, j)] = H[i * 9 + j];
-        double* to = tsc + (size_t)t * 48; // [0..11] gradient, [12 + 9 v ..] diagonal block of local vertex v
+            for (int j = i; j < 9; ++j) h9[(size_t)sym9(i, j) * a.T + t] = H[i * 9 + j];
+        double* to = tsc + t; // SoA [48][T]: rows 0..11 gradient, rows 12 + 9 v .. diagonal block of local vertex v
         for (int v = 0; v < 4; ++v)
             for (int c = 0; c < 3; ++c) {
                 double sum = 0;
                 for (int b = 0; b < 3; ++b) sum += dEdF[3 * b + c] * W[v][b];
-                to[3 * v + c] = sum;
+                to[(size_t)(3 * v + c) * a.T] = sum;
             }
         for (int v = 0; v < 4; ++v)
             for (int c = 0; c < 3; ++c)
@@ -346,7 +511,7 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xp
                     double sum = 0;
                     for (int b = 0; b < 3; ++b)
                         for (int b2 = 0; b2 < 3; ++b2) sum += W[v][b] * H[(3 * b + c) * 9 + (3 * b2 + cc)] * W[v][b2];
-                    to[12 + 9 * v + 3 * c + cc] = sum;
+                    to[(size_t)(12 + 9 * v + 3 * c + cc) * a.T] = sum;
                 }
     }
     __syncthreads();
@@ -357,10 +522,10 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xp
         for (int j = 0; j < 9; ++j) d9[j] = s.Dg[9 * i + j];
         for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
             const int tv = a.adj[q];
-            const double* to = tsc + (size_t)(tv >> 2) * 48;
+            const double* to = tsc + (tv >> 2);
             const int v = tv & 3;
-            for (int c = 0; c < 3; ++c) g3[c] += to[3 * v + c];
-            for (int j = 0; j < 9; ++j) d9[j] += to[12 + 9 * v + j];
+            for (int c = 0; c < 3; ++c) g3[c] += to[(size_t)(3 * v + c) * a.T];
+            for (int j = 0; j < 9; ++j) d9[j] += to[(size_t)(12 + 9 * v + j) * a.T];
         }
         for (int c = 0; c < 3; ++c) s.G[3 * i + c] = g3[c];
         for (int j = 0; j < 9; ++j) s.Dg[9 * i + j] = d9[j];
@@ -402,11 +567,10 @@ __device__ void apply_A(const FemArgs& a, const FemShared& s, const double* h9, 
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
         double W[4][3], P[9], Q[9], Hs[45];
-        tet_W(a.Dm_inv + 9 * t, W);
+        tet_W(a.Dm_inv, t, a.T, W);
         tet_F(p, e, W, P);
-        const double* hp = h9 + (size_t)t * 45;
 #pragma unroll
-        for (int i = 0; i < 45; ++i) Hs[i] = hp[i];
+        for (int i = 0; i < 45; ++i) Hs[i] = h9[(size_t)i * a.T + t];
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             double q = 0;
@@ -414,12 +578,14 @@ __device__ void apply_A(const FemArgs& a, const FemShared& s, const double* h9, 
             for (int j = 0; j < 9; ++j) q += Hs[sym9(i, j)] * P[j];
             Q[i] = q;
         }
-        double* to = tsc + (size_t)t * 48;
+#pragma unroll
         for (int v = 0; v < 4; ++v)
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double q = 0;
+#pragma unroll
                 for (int b = 0; b < 3; ++b) q += Q[3 * b + c] * W[v][b];
-                to[3 * v + c] = q;
+                tsc[(size_t)(3 * v + c) * a.T + t] = q;
             }
     }
     __syncthreads();
@@ -428,8 +594,8 @@ __device__ void apply_A(const FemArgs& a, const FemShared& s, const double* h9, 
         for (int c = 0; c < 3; ++c) y3[c] = a.mass[i] * p[3 * i + c];
         for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
             const int tv = a.adj[q];
-            const double* to = tsc + (size_t)(tv >> 2) * 48 + 3 * (tv & 3);
-            for (int c = 0; c < 3; ++c) y3[c] += to[c];
+            const double* to = tsc + (size_t)(3 * (tv & 3)) * a.T + (tv >> 2);
+            for (int c = 0; c < 3; ++c) y3[c] += to[(size_t)c * a.T];
         }
         for (int c = 0; c < 3; ++c) y[3 * i + c] = y3[c];
     }

@@ -1,0 +1,24 @@
+"""Timing of the batched gel FEM substep (config 3: box indenter pressed 0 -> 1 mm over 30 steps)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tacex_b200 import fem, gel_mesh
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+m = gel_mesh.box_gel()
+eng = fem.GelFemEngine(m)
+rng = np.random.default_rng(2)
+offs = rng.uniform(-1, 1, (N, 2)) * np.array([6e-3, 8e-3])
+half = (2e-3, 3e-3, 1e-3)
+z0 = 4.5e-3 + half[2] + 4e-4
+x, v, xp = eng.new_state(N); aim = eng.rest_aim(N)
+ctr = lambda s: np.concatenate([offs, np.full((N, 1), z0 - 1e-3 * s / 30)], 1)
+inds = [fem.indenter_array(1, ctr(s), half) for s in range(steps + 1)]
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+tot_newton = 0; tot_pcg = 0
+for s in range(steps):
+    e0.record(); st = eng.step(x, v, xp, aim, inds[s], inds[s + 1]); e1.record(); torch.cuda.synchronize()
+    d = eng.decode_stats(st)
+    nn = np.mean([q["newton_iters"] for q in d]); pc = np.mean([q["pcg_iters"] for q in d]); cv = np.mean([q["converged"] for q in d])
+    print(f"step {s}: {e0.elapsed_time(e1):8.2f} ms  newton {nn:.2f}  pcg {pc:.1f}  converged {cv:.2f}  min_dist {min(q['min_dist'] for q in d):.2e}")
+print(f"-> {N / (e0.elapsed_time(e1) / 1e3):.0f} gel-steps/s at the last step")
