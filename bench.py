@@ -95,6 +95,72 @@ def cpu_port_fps(n_frames: int, with_markers: bool = True) -> tuple[float, int, 
     return n_frames / dt, canon.num_threads(), f"{n_frames} frames of the same workload (config-1 sphere presses), one pass"
 
 
+def fem_cpu_port(n_gels: int = 64) -> tuple[float, int, str]:
+    """Gel FEM substep on the host cores with the float64 CPU restatement (libuipc itself has no CPU backend)."""
+    import numpy as np
+
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh
+
+    m = gel_mesh.box_gel()
+    cf = fc.CanonFem(m)
+    rng = np.random.default_rng(2)
+    offs = rng.uniform(-1, 1, (n_gels, 2)) * np.array([6e-3, 8e-3])
+    half = (2e-3, 3e-3, 1e-3)
+    z0 = 4.5e-3 + half[2] + 4e-4
+    x, v, xp = cf.new_state(n_gels)
+    aim = cf.X[cf.attach][None].repeat(n_gels, 0)
+    mk = lambda s: [fc.make_indenter(1, (o[0], o[1], z0 - 1e-3 * s / 30), half) for o in offs]  # noqa: E731
+    cf.step(x, v, xp, aim, mk(0), mk(1))
+    t0 = time.perf_counter()
+    for s in (1, 2):
+        cf.step(x, v, xp, aim, mk(s), mk(s + 1))
+    dt = time.perf_counter() - t0
+    from oracle import canon
+
+    return 2 * n_gels / dt, canon.num_threads(), f"{n_gels} gels x 2 steps of the config-3 box press (float64 CPU restatement)"
+
+
+def fem_gpu(E: int, steps: int, dev) -> dict:
+    """Config 3 extra: batched gel FEM substep + FEM marker read-out for E gels (box indenter pressed 0 -> 1 mm in 30 steps)."""
+    import numpy as np
+    import torch
+
+    from tacex_b200 import fem, gel_mesh
+
+    m = gel_mesh.box_gel()
+    eng = fem.GelFemEngine(m, device=dev)
+    tri, w = fem.marker_grid_weights(m)
+    eng.set_markers(tri, w)
+    rng = np.random.default_rng(2)
+    offs = rng.uniform(-1, 1, (E, 2)) * np.array([6e-3, 8e-3])
+    half = (2e-3, 3e-3, 1e-3)
+    z0 = 4.5e-3 + half[2] + 4e-4
+    x, v, xp = eng.new_state(E)
+    aim = eng.rest_aim(E)
+    ctr = lambda s: np.concatenate([offs, np.full((E, 1), z0 - 1e-3 * s / 30)], 1)  # noqa: E731
+    inds = [fem.indenter_array(1, ctr(s), half, device=dev) for s in range(steps + 3)]
+    mk = torch.empty((E, 2, 128, 2), device=dev)
+    for s in range(2):
+        eng.step(x, v, xp, aim, inds[s], inds[s + 1], want_stats=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st = None
+    for s in range(2, 2 + steps):
+        st = eng.step(x, v, xp, aim, inds[s], inds[s + 1], want_stats=True)
+        eng.markers(x, out=mk)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    d = eng.decode_stats(st)
+    return {"workload": f"{E} gels (572 verts / 2160 tets, float64): implicit-Euler IPC substep + FEM marker read-out",
+            "gel_steps_per_s": E / (ms / 1e3), "ms_per_step": ms,
+            "newton_iters_mean": float(np.mean([q["newton_iters"] for q in d])),
+            "pcg_iters_mean": float(np.mean([q["pcg_iters"] for q in d])),
+            "compulsory_bytes_per_gel_step": 315136}
+
+
 def run_reference(args) -> None:
     """--impl reference: the reference's algorithm on the host cores. The reference's own implementation is Python
     (torch + NumPy) inside /root/reference, which does not exist on the GPU box, so the timed code is the oracle's
@@ -130,6 +196,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "none"], help="N>1: all-gather of the RGB observation")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fem", action="store_true", help="skip the extra gel-FEM measurement (config 3)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -141,6 +208,7 @@ def main() -> None:
     from tacex_b200 import synth
     from tacex_b200.calib import TaximTables
     from tacex_b200.engine import TactileEngine
+    from tacex_b200.shard import all_gather_obs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,7 +240,7 @@ def main() -> None:
         eng.render(hm, None, out=rgb, depth_out=depth)
         eng.fots_markers(depth, theta, traj0, traj_len, out=markers)
         if gathered is not None:
-            dist.all_gather_into_tensor(gathered, rgb)
+            all_gather_obs(rgb, gathered)
 
     def barrier():
         if world > 1:
@@ -220,6 +288,11 @@ def main() -> None:
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- config 3 extra: the optional gel FEM substep, measured in the same run (not part of `value`) -------------
+    fem_extra = None
+    if not args.no_fem and world == 1:
+        fem_extra = fem_gpu(min(E, 4096), 3, dev)
+
     # ---- max over ranks ------------------------------------------------------------------------------------------
     t = torch.tensor([ms, kern_ms, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -242,7 +315,7 @@ def main() -> None:
             "data": "synthetic",
             "config": {
                 "workload": f"{E} envs/GPU x 320x240: indentation depth + Taxim RGB + FOTS {M}-marker motion, sphere indenters "
-                            f"(config-1 distribution, 10% no contact); gel FEM substep not included",
+                            f"(config-1 distribution, 10% no contact); the optional gel FEM substep (config 3) is reported separately under fem_gel_substep",
                 "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"dp{world} (contiguous env shards)",
                 "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2)",
                 "obs_gather": (args.obs_gather if world > 1 else "n/a"),
@@ -259,6 +332,12 @@ def main() -> None:
         if not args.no_cpu_baseline:
             fps, cores, sample = cpu_port_fps(256)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        if fem_extra is not None:
+            line["fem_gel_substep"] = fem_extra
+            if not args.no_cpu_baseline:
+                g, cores, sample = fem_cpu_port(64)
+                line["fem_gel_substep"]["cpu_baseline"] = {"value": g, "unit": "gel-steps/s", "cores": cores, "kind": "port",
+                                                           "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -180,3 +180,48 @@ def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=
     while len(out_tri) < pad_to:
         out_tri.append(out_tri[-1]); out_w.append(out_w[-1])
     return np.asarray(out_tri[:pad_to], np.int32), np.asarray(out_w[:pad_to], np.float64)
+
+
+class GelPadSim:
+    """Batched stand-in for ``UipcSim`` + the gel ``UipcObject`` of every sensor (ref: uipc_sim.py:250-252 ``step`` =
+    ``world.advance(); world.retrieve()``; objects/uipc_object_deformable_data.py:135-147 ``surf_nodal_pos_w``): owns the
+    float64 state of N gels on the device and advances all of them with one kernel launch per step. The reference supports
+    exactly one environment here ("UIPC based envs can only be run with --num_envs=1", docs/source/showcases/ball_rolling.md:23)."""
+
+    def __init__(self, num_envs: int, mesh: GelMesh | None = None, cfg: GelFemCfg | None = None, device="cuda"):
+        from .gel_mesh import box_gel
+
+        self.mesh = mesh or box_gel()
+        self.engine = GelFemEngine(self.mesh, cfg, device)
+        self.num_envs = num_envs
+        self.x, self.v, self.x_prev = self.engine.new_state(num_envs)
+        self.aim = self.engine.rest_aim(num_envs)
+        self._ind_prev = None
+        self.last_stats = None
+
+    @property
+    def nodal_pos_w(self) -> torch.Tensor:
+        return self.x
+
+    @property
+    def surf_nodal_pos_w(self) -> torch.Tensor:
+        idx = torch.from_numpy(np.unique(self.mesh.top_tris).astype(np.int64)).to(self.x.device)
+        return self.x[:, idx]
+
+    def reset(self, env_ids=None):
+        ids = slice(None) if env_ids is None else env_ids
+        self.x[ids] = self.engine.X
+        self.x_prev[ids] = self.engine.X
+        self.v[ids] = 0
+
+    def set_attachment_aim(self, aim: torch.Tensor):
+        """Target positions of the attached (bottom-layer) vertices, e.g. transformed by the sensor-case pose
+        (ref: uipc_attachments.py:364-428)."""
+        self.aim.copy_(aim)
+
+    def step(self, indenter: torch.Tensor, want_stats: bool = True):
+        """``indenter``: packed ``tx_fem_indenter`` array of the poses at the END of this step (see indenter_array)."""
+        prev = indenter if self._ind_prev is None else self._ind_prev
+        self.last_stats = self.engine.step(self.x, self.v, self.x_prev, self.aim, prev, indenter, want_stats)
+        self._ind_prev = indenter
+        return self.last_stats

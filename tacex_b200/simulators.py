@@ -20,6 +20,7 @@ from dataclasses import dataclass, field
 from pathlib import Path
 from typing import Any
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -316,6 +317,92 @@ class B200FOTSMarkerSimulator(GelSightSimulator):
         self.theta = self._relative_yaw()
         self.engine.fots_markers(press, self.theta, self.traj0, self.traj_len, out=self.marker_data)
         return self.marker_data
+
+    def reset(self):
+        pass
+
+    def _set_debug_vis_impl(self, debug_vis: bool):
+        pass
+
+    def _debug_vis_callback(self, event):
+        pass
+
+
+# ---- FEM based marker simulation (ManiSkill-ViTac style) ------------------------------------------------------------------
+@dataclass
+class ManiSkillMarkerParams:
+    num_markers: int = 128
+    x0: float = 0
+    y0: float = 0
+    dx: float = 0
+    dy: float = 0
+
+
+@dataclass
+class ManiSkillSimulatorCfg(GelSightSimulatorCfg):
+    """Field-for-field ``ManiSkillSimulatorCfg`` (ref: .../fem_based/mani_skill_sim_cfg.py:10-70)."""
+
+    simulation_approach_class: type | None = None  # None -> B200ManiSkillSimulator
+    calib_folder_path: str = ""
+    device: str | None = "cuda"
+    marker_interval_range: tuple = (2.0625, 2.0625)
+    marker_rotation_range: float = 0.0
+    marker_translation_range: tuple = (0.0, 0.0)
+    marker_pos_shift_range: tuple = (0.0, 0.0)
+    marker_random_noise: float = 0.0
+    marker_lose_tracking_probability: float = 0.0
+    normalize: bool = False
+    marker_flow_size: int = 128
+    camera_params: tuple = (340, 325, 160, 125, 0.0)
+    tactile_img_res: tuple = (320, 240)
+    marker_params: ManiSkillMarkerParams = field(default_factory=ManiSkillMarkerParams)
+
+    def __post_init__(self):
+        if self.simulation_approach_class is None:
+            self.simulation_approach_class = B200ManiSkillSimulator
+
+
+class B200ManiSkillSimulator(GelSightSimulator):
+    """Marker flow from the FEM gel surface (drop-in for ``ManiSkillSimulator``, ref: .../fem_based/mani_skill_sim.py:20-86 and
+    sim/tactile_sensor_sapienipc_modified.py:189-413): barycentric markers on the gel's top surface projected with the
+    sensor camera. ``sensor.gelpad_obj`` must be a :class:`tacex_b200.fem.GelPadSim`. Unlike the reference (env 0 only, weights
+    recomputed every step) every env is read out in one launch with weights computed once."""
+
+    cfg: ManiSkillSimulatorCfg
+
+    def __init__(self, sensor, cfg: ManiSkillSimulatorCfg):
+        self.sensor = sensor
+        super().__init__(sensor=sensor, cfg=cfg)
+
+    def _initialize_impl(self):
+        from .fem import GelPadSim, marker_grid_weights
+
+        self._device = self.sensor.device if self.cfg.device is None else self.cfg.device
+        self._num_envs = self.sensor._num_envs
+        gel = self.sensor.gelpad_obj
+        if not isinstance(gel, GelPadSim):
+            raise RuntimeError("B200ManiSkillSimulator needs sensor.gelpad_obj to be a tacex_b200.fem.GelPadSim")
+        self.gel = gel
+        if any(abs(v) > 0 for v in (self.cfg.marker_rotation_range, *self.cfg.marker_translation_range,
+                                    *self.cfg.marker_pos_shift_range, self.cfg.marker_random_noise,
+                                    self.cfg.marker_lose_tracking_probability)):
+            raise NotImplementedError("randomised marker grids are not implemented (all ranges are 0 in the reference presets)")
+        tri, w = marker_grid_weights(gel.mesh, pitch=self.cfg.marker_interval_range[0] * 1e-3, pad_to=self.cfg.marker_flow_size)
+        fx, fy, cx, cy = self.cfg.camera_params[:4]
+        gel.engine.set_markers(tri, w, intrinsics=(fx, fy, cx, cy))
+        self.marker_data = torch.zeros((self._num_envs, 2, self.cfg.marker_flow_size, 2), device=gel.engine.device)
+        self._indentation_depth = torch.zeros((self._num_envs,), device=gel.engine.device)
+
+    def marker_motion_simulation(self):
+        self.gel.engine.markers(self.gel.x, out=self.marker_data)
+        return self.marker_data
+
+    def compute_indentation_depth(self):
+        """Largest downward displacement of the gel's top surface [mm]."""
+        top = torch.from_numpy(np.unique(self.gel.mesh.top_tris).astype(np.int64)).to(self.gel.x.device)
+        dz = (self.gel.engine.X[top, 2][None] - self.gel.x[:, top, 2]).amax(1)
+        self._indentation_depth[:] = torch.clamp(dz, min=0) * 1000
+        return self._indentation_depth
 
     def reset(self):
         pass
