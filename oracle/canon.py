@@ -149,3 +149,18 @@ class CanonFots:
 
 def num_threads() -> int:
     return int(lib().canon_num_threads())
+
+
+def use_all_threads() -> int:
+    """OpenMP thread count = all host CPUs (torchrun sets OMP_NUM_THREADS=1 in the workers)."""
+    import os
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().canon_set_threads(n)
+    try:
+        from . import fem_canon
+
+        fem_canon.lib().fem_set_threads(n)
+    except Exception:
+        pass
+    return num_threads()

@@ -619,6 +619,16 @@ void fem_step_batch(const fem_cfg* g, const int32_t* tets, const double* Dm_inv,
     }
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+void fem_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 /* ---- KAT helpers exported for tests -------------------------------------------------------------------------------- */
 /* dense assembly of the Newton matrix and right-hand side at state x (small meshes only) */
 void fem_assemble_dense(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,

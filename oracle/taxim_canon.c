@@ -439,6 +439,14 @@ void canon_fots_step(const canon_fots_cfg* c, const int32_t* mx, const int32_t* 
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for all host threads explicitly */
+void canon_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 int canon_num_threads(void)
 {
 #ifdef _OPENMP
