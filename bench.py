@@ -248,7 +248,7 @@ def main() -> None:
     state = {"i": 0}
 
     def step():
-        i = state["i"] & 1
+        i = (state["i"] & 1) if do_gather else 0
         state["i"] += 1
         if do_gather:
             torch.cuda.current_stream().wait_event(ev_free[i])  # the gather that read this buffer two steps ago is done

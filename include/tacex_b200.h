@@ -129,6 +129,8 @@ int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my);
 /* Profiling hook: when `ticks` (device, [2*N][40] int64) is non-NULL, every CTA of the following tx_render launches
  * stores clock64() stamps at its phase boundaries there (used by tools/phase_times.py; NULL disables). */
 int tx_debug_set_ticks(tx_handle* h, long long* ticks);
+/* Test hook: bit 3 (8) forces the exact (slow) division / sqrt path of the epilogue; other bits are profiling ablations. */
+int tx_debug_set_flags(tx_handle* h, int flags);
 
 /* ---- host-buffer convenience (the end-to-end path the benchmark times) -------------------------------------- */
 

@@ -66,7 +66,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks",
+    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers",
 ]
@@ -97,6 +97,8 @@ def load() -> C.CDLL:
     lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
     lib.tx_debug_set_ticks.argtypes = [C.c_void_p, C.c_void_p]
     lib.tx_debug_set_ticks.restype = C.c_int
+    lib.tx_debug_set_flags.argtypes = [C.c_void_p, C.c_int]
+    lib.tx_debug_set_flags.restype = C.c_int
     lib.tx_fem_create.argtypes = [C.POINTER(TxFemConfig), vp, vp, vp, vp, C.c_int, vp, C.POINTER(C.c_void_p)]
     lib.tx_fem_destroy.argtypes = [C.c_void_p]
     lib.tx_fem_destroy.restype = None

@@ -53,6 +53,8 @@ struct Misc {
     float red_f[NWARPS];
     unsigned red_u[3][NWARPS];
     int nlist;
+    int bbox[4];      // contact bounding box of this half (image coordinates): row min, row max, col min, col max
+    int bbox_peer[4]; // the peer CTA's box
 };
 static_assert(sizeof(Misc) <= 512, "misc");
 
@@ -80,23 +82,33 @@ __device__ __forceinline__ void load_row12(const float* rp, int v0, bool interio
     }
 }
 
+// Only the rows [la, lb] (local) can hold non-zero values (exact zeros elsewhere: a blur of zeros is +0.0f bit for bit),
+// so only they are processed, interleaved over the warps; skipped rows inside the push range send zeros to the peer.
 template <int L, int RAD>
-__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, int lane, unsigned q)
+__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, int warp, int lane, unsigned q, int la, int lb)
 {
     constexpr int D = (RAD + 11) / 12;
-    constexpr int ROWS = HALF_H / NWARPS;
     const int v0 = 12 * lane - 32;
     const bool interior = (lane >= 3) && (lane <= 28);
+    // zero halo rows for the skipped rows of the push range (the halo buffers are reused across levels)
+    for (int i = tid; i < RAD * (IMG_W / 4); i += NTHREADS) {
+        const int dist = i / (IMG_W / 4);
+        const int row = q == 0 ? (HALF_H - 1 - dist) : dist;
+        if (row < la || row > lb)
+            reinterpret_cast<float4*>(hb_remote + dist * IMG_W)[i - dist * (IMG_W / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int nact = lb - la + 1;
+    if (warp >= nact) return;
     float xn[12];
-    load_row12(plane + (warp * ROWS) * IMG_W, v0, interior, xn);
+    load_row12(plane + (la + warp) * IMG_W, v0, interior, xn);
 #pragma unroll 1
-    for (int rr = 0; rr < ROWS; ++rr) {
-        const int row = warp * ROWS + rr;
+    for (int k = warp; k < nact; k += NWARPS) {
+        const int row = la + k;
         float* rp = plane + row * IMG_W;
         float x[12], acc[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) { x[j] = xn[j]; acc[j] = 0.0f; }
-        if (rr + 1 < ROWS) load_row12(rp + IMG_W, v0, interior, xn); // prefetch the next row (other row: no hazard)
+        if (k + NWARPS < nact) load_row12(rp + NWARPS * IMG_W, v0, interior, xn); // prefetch this warp's next row
 #pragma unroll
         for (int d = -D; d <= D; ++d) {
 #pragma unroll
@@ -105,8 +117,8 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, 
                     const float y = (d == 0) ? x[j] : __shfl_sync(0xffffffffu, x[j], (lane + d) & 31);
 #pragma unroll
                     for (int m = 0; m < 12; ++m) {
-                        const int k = 12 * d + j - m;
-                        if (k >= -RAD && k <= RAD) acc[m] = __fmaf_rn(c_taps[L][0][k + RAD], y, acc[m]);
+                        const int kk = 12 * d + j - m;
+                        if (kk >= -RAD && kk <= RAD) acc[m] = __fmaf_rn(c_taps[L][0][kk + RAD], y, acc[m]);
                     }
                 }
             }
@@ -131,23 +143,26 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int warp, 
 // q = 1: t = 119 - local row, marching up). Positions < 0 are the reflected rows, positions >= 120 come from
 // the halo buffer (rows of the peer CTA by distance from the boundary).
 template <int L, int RAD, int R>
-__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q)
+__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q, int ca, int ncols, int ta, int tb)
 {
-    if (tid >= IMG_W) return;
+    // only columns [ca, ca + ncols) and positions [ta, tb] can become non-zero; everything else stays exactly +0.0f
+    if (tid >= ncols || tb < ta) return;
     constexpr int WN = R + 2 * RAD;
-    constexpr int NB = HALF_H / R;
-    static_assert(HALF_H % R == 0 && R + RAD <= HALF_H, "block size");
+    static_assert(HALF_H % R == 0, "block size");
+    const int col = ca + tid;
     float win[WN];
-    float* p0 = plane + (q ? (HALF_H - 1) * IMG_W : 0) + tid;
+    float* p0 = plane + (q ? (HALF_H - 1) * IMG_W : 0) + col;
+    const float* hbc = hb + col;
     const int S = q ? -IMG_W : IMG_W;
+    const int b0 = ta / R, b1 = tb / R;
 #pragma unroll
     for (int i = 0; i < WN; ++i) {
-        int t = i - RAD;
-        t = t < 0 ? -t : t;
-        win[i] = p0[t * S];
+        const int t = b0 * R - RAD + i;
+        const float* src = (t < 0) ? (p0 + (-t) * S) : ((t < HALF_H) ? (p0 + t * S) : (hbc + min(t - HALF_H, RAD - 1) * IMG_W));
+        win[i] = *src;
     }
 #pragma unroll 1
-    for (int b = 0; b < NB; ++b) {
+    for (int b = b0; b <= b1; ++b) {
         float acc[R];
         // centre-outward, symmetric pair summed first: independent of the marching direction
 #pragma unroll
@@ -161,15 +176,15 @@ __device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, un
         float* po = p0 + (b * R) * S;
 #pragma unroll
         for (int m = 0; m < R; ++m) po[m * S] = acc[m];
-        if (b + 1 < NB) {
+        if (b < b1) {
 #pragma unroll
             for (int i = 0; i < 2 * RAD; ++i) win[i] = win[i + R];
-            const int tb = (b + 1) * R - RAD;
+            const int tbase = (b + 1) * R - RAD;
 #pragma unroll
             for (int i = 2 * RAD; i < WN; ++i) {
-                const int t = tb + i;
+                const int t = tbase + i;
                 // t >= 120 -> halo row (t - 120); only rows < RAD are ever used by outputs < 120
-                const float* src = (t < HALF_H) ? (p0 + t * S) : (hb + min(t - HALF_H, RAD - 1) * IMG_W + tid);
+                const float* src = (t < HALF_H) ? (p0 + t * S) : (hbc + min(t - HALF_H, RAD - 1) * IMG_W);
                 win[i] = *src;
             }
         }
@@ -213,16 +228,31 @@ __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits,
         if (tk && tid == 0) tk[(slot)] = clock64();                                                                   \
     } while (0)
 
+// Region = bounding box (image coordinates) outside of which the plane is exactly zero at the start of the level.
+struct Region {
+    int r0, r1, c0, c1;
+};
+
 template <int L, int RAD, int R, bool FINAL>
 __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
-                                           const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half, float m, float press, int tid,
-                                           int warp, int lane, unsigned q, cg::cluster_group& cluster, long long* tk)
+                                           const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half,
+                                           float m, float press, int tid, int warp, int lane, unsigned q, Region& rg,
+                                           cg::cluster_group& cluster, long long* tk)
 {
-    hpass<L, RAD>(plane, hb_remote, warp, lane, q);
+    const int base = (int)q * HALF_H;
+    hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1));
     TX_TICK(4 + 4 * L + 0);
     cluster.sync(); // rows + pushed halo rows visible in both CTAs
     TX_TICK(4 + 4 * L + 1);
-    vpass<L, RAD, R>(plane, hb_local, tid, q);
+    {
+        const int ca = max(rg.c0 - RAD, 0), cb = min(rg.c1 + RAD, IMG_W - 1);
+        const int ro0 = max(rg.r0 - RAD, 0), ro1 = min(rg.r1 + RAD, IMG_H - 1); // output rows (image)
+        // position t counts from the image edge of this half: q = 0: t = image row; q = 1: t = 239 - image row
+        const int ta = q == 0 ? ro0 : max(IMG_H - 1 - ro1, 0);
+        const int tb = q == 0 ? min(ro1, HALF_H - 1) : min(IMG_H - 1 - ro0, HALF_H - 1);
+        vpass<L, RAD, R>(plane, hb_local, tid, q, ca, cb - ca + 1, ta, tb);
+        rg.r0 = ro0; rg.r1 = ro1; rg.c0 = ca; rg.c1 = cb;
+    }
     __syncthreads();
     TX_TICK(4 + 4 * L + 2);
     if (!FINAL) {
@@ -230,6 +260,50 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
         __syncthreads();
     }
     TX_TICK(4 + 4 * L + 3);
+}
+
+// polynomial colour of one pixel: 3 channels x 6 coefficients (cf[6 ch + k], k over x^2, y^2, xy, x, y, 1), + background, clip
+__device__ __forceinline__ void poly_rgb(const float* cf, float xf, float yf, float f0, float f1, float f2, const float* bgv,
+                                         float* o)
+{
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* pc = cf + 6 * ch;
+        float s = pc[5];
+        s = __fmaf_rn(pc[4], yf, s);
+        s = __fmaf_rn(pc[3], xf, s);
+        s = __fmaf_rn(pc[2], f2, s);
+        s = __fmaf_rn(pc[1], f1, s);
+        s = __fmaf_rn(pc[0], f0, s);
+        s = __fadd_rn(s, bgv[ch]);
+        o[ch] = fminf(fmaxf(s, 0.0f), 1.0f);
+    }
+}
+
+// RGB of a pixel with exactly zero gradient (mag = 0, dir = 0), for every pixel position: computed once per calibration
+// with the same operation sequence the fused kernel uses, so copying it is bit-identical to evaluating it
+__global__ void flat_rgb_kernel(const TaximArgs p, float* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= IMG_H * IMG_W) return;
+    const float PI_F = 3.14159265358979323846f;
+    const int id_flat = min(max((int)floorf(__fmul_rn(__fadd_rn(0.0f, PI_F), p.inv_ybin)), 0), p.nb - 1);
+    const float4* pf = p.poly + (size_t)id_flat * 5;
+    const float4 a0 = __ldg(pf), a1 = __ldg(pf + 1), a2 = __ldg(pf + 2), a3 = __ldg(pf + 3), a4 = __ldg(pf + 4);
+    const float cf[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
+                          a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+    const int y = i / IMG_W, x = i - y * IMG_W;
+    const float xf = __fmul_rn((float)x, p.fx), yf = __fmul_rn((float)y, p.fy);
+    const float bgv[3] = {p.bg_hwc[3 * i], p.bg_hwc[3 * i + 1], p.bg_hwc[3 * i + 2]};
+    float o[3];
+    poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), __fmul_rn(yf, yf), __fmul_rn(xf, yf), bgv, o);
+    out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+
+cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s)
+{
+    flat_rgb_kernel<<<(IMG_H * IMG_W + 255) / 256, 256, 0, s>>>(a, flat_rgb);
+    return cudaGetLastError();
 }
 
 // ---- the fused kernel -------------------------------------------------------------------------------------------
@@ -262,6 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         fence_mbar_init();
         fence_proxy_async();
         misc->nlist = 0;
+        misc->bbox[0] = IMG_H; misc->bbox[1] = -1; misc->bbox[2] = IMG_W; misc->bbox[3] = -1;
     }
     __syncthreads();
     if (tid == 0) {
@@ -334,9 +409,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             const bool mk = (__fadd_rn(j, -gv[u]) < thr) && contact;
             plane[idx] = j;
             const unsigned bits = __ballot_sync(0xffffffffu, mk);
+            const unsigned cbits = __ballot_sync(0xffffffffu, contact);
             if (lane == 0) {
                 maskbits[w] = bits;
                 if (bits) mlist[atomicAdd(&misc->nlist, 1)] = (unsigned short)w;
+                if (cbits) { // grow the contact bounding box (the joined map is non-zero exactly where h < 0)
+                    const int rrow = (int)(q * HALF_H) + w / (IMG_W / 32), cb0 = (w % (IMG_W / 32)) * 32;
+                    atomicMin(&misc->bbox[0], rrow);
+                    atomicMax(&misc->bbox[1], rrow);
+                    atomicMin(&misc->bbox[2], cb0 + __ffs(cbits) - 1);
+                    atomicMax(&misc->bbox[3], cb0 + 31 - __clz(cbits));
+                }
             }
             if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
             if (mk) { // row / column from the word index (one word = 32 consecutive columns of one row)
@@ -364,19 +447,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         p.aux_sums[((size_t)n * 2 + q) * 4 + tid] = s;
     }
     const int nlist = misc->nlist;
+    if (tid < 4) misc_remote->bbox_peer[tid] = misc->bbox[tid];
+    cluster.sync();
+    Region rg;
+    rg.r0 = min(misc->bbox[0], misc->bbox_peer[0]);
+    rg.r1 = max(misc->bbox[1], misc->bbox_peer[1]);
+    rg.c0 = min(misc->bbox[2], misc->bbox_peer[2]);
+    rg.c1 = max(misc->bbox[3], misc->bbox_peer[3]);
+    if (p.gel != nullptr) { rg.r0 = 0; rg.r1 = IMG_H - 1; rg.c0 = 0; rg.c1 = IMG_W - 1; } // a gel map makes the plane dense
 
     TX_TICK(3);
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     const bool active = (p.gel != nullptr) || (press > 0.0f);
     if (active) {
-        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
-        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, cluster, tk);
+        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
     }
 
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
@@ -414,110 +505,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     TX_TICK(32);
 
     // ---- normals -> bins -> polynomial -> + background -> clip -> NHWC (ref: taxim_torch.py:475-503, 243-258) ---
-    // One thread per 4 consecutive pixels of a row: 128-bit loads of the background / stores of the RGB frame, four
-    // independent math chains, twenty table loads in flight. Warps whose pixels are all flat (exact zero gradient,
-    // the common case outside the deformed region) skip the transcendental math.
+    // One thread per 4 consecutive pixels of a row, 128-bit loads / stores. Three paths, chosen per warp:
+    //   (1) the warp's pixels lie outside the non-zero region of the deformed gel (+1 px for the central differences) or
+    //       all have an exactly zero gradient: copy the precomputed flat RGB (bit-identical to evaluating it);
+    //   (2) otherwise: canonical atan / atan2, bins, and a cooperative gather of the 80-byte table records through a
+    //       per-warp staging area (5 lanes read one record contiguously instead of 32 scattered requests per load).
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
+    const float* flat_half = p.flat_rgb + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
-    const int id_flat = min(max((int)floorf(__fmul_rn(__fadd_rn(0.0f, PI_F), p.inv_ybin)), 0), p.nb - 1);
-    // coefficients of the flat bin (mag = 0, dir = 0): shared by every flat pixel, kept in registers
-    float cflat[18];
-    {
-        const float4* pf = p.poly + (size_t)id_flat * 5;
-        const float4 a0 = __ldg(pf), a1 = __ldg(pf + 1), a2 = __ldg(pf + 2), a3 = __ldg(pf + 3), a4 = __ldg(pf + 4);
-        const float t20[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
-                               a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-        for (int i = 0; i < 18; ++i) cflat[i] = t20[i];
-    }
+    float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (15 x 2560 B = 38,400 B)
     constexpr int QPR = IMG_W / 4; // quads per row
+    const bool dense = active;     // without contact the whole frame is flat
 #pragma unroll 1
     for (int qd = tid; qd < HALF_H * QPR; qd += NTHREADS) {
         const int row = qd / QPR;
         const int x0 = (qd - row * QPR) * 4;
         const int gy_ = (int)q * HALF_H + row; // image row
-        // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
-        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixels
-        const float* ctr = plane + yy * IMG_W;
-        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1;
-        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1;
-        const float4 cu = *reinterpret_cast<const float4*>(up + x0);
-        const float4 cd = *reinterpret_cast<const float4*>(dn + x0);
-        const float4 cc = *reinterpret_cast<const float4*>(ctr + x0);
-        const float c6[6] = {ctr[max(x0 - 1, 0)], cc.x, cc.y, cc.z, cc.w, ctr[min(x0 + 4, IMG_W - 1)]};
-        const float u4[4] = {cu.x, cu.y, cu.z, cu.w}, d4[4] = {cd.x, cd.y, cd.z, cd.w};
-        float gx[4], gy[4], tt[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float top = __fmul_rn(u4[i], p.inv_pixmm), bot = __fmul_rn(d4[i], p.inv_pixmm);
-            const float lef = __fmul_rn(c6[i], p.inv_pixmm), rig = __fmul_rn(c6[i + 2], p.inv_pixmm);
-            gx[i] = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
-            gy[i] = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
-        }
-        if (x0 == 0) { gx[0] = gx[1]; gy[0] = gy[1]; }                 // column 0 samples column 1
-        if (x0 == IMG_W - 4) { gx[3] = gx[2]; gy[3] = gy[2]; }         // column 319 samples column 318
-        // tt = sqrt(s2) is zero iff s2 is zero: flat pixels (exact zero gradient) need no sqrt / atan
-        float s2[4];
+        const size_t pix = (size_t)row * IMG_W + x0;
+        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
+        const bool inreg = dense && gy_ >= rg.r0 - 1 && gy_ <= rg.r1 + 1 && x0 + 3 >= rg.c0 - 1 && x0 <= rg.c1 + 1;
         bool nonflat = false;
+        float gx[4], gy[4], s2[4];
+        if (__any_sync(0xffffffffu, inreg)) {
+            // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
+            const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixels
+            const float* ctr = plane + yy * IMG_W;
+            const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1;
+            const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1;
+            const float4 cu = *reinterpret_cast<const float4*>(up + x0);
+            const float4 cd = *reinterpret_cast<const float4*>(dn + x0);
+            const float4 cc = *reinterpret_cast<const float4*>(ctr + x0);
+            const float c6[6] = {ctr[max(x0 - 1, 0)], cc.x, cc.y, cc.z, cc.w, ctr[min(x0 + 4, IMG_W - 1)]};
+            const float u4[4] = {cu.x, cu.y, cu.z, cu.w}, d4[4] = {cd.x, cd.y, cd.z, cd.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
-            nonflat |= s2[i] != 0.0f;
+            for (int i = 0; i < 4; ++i) {
+                const float top = __fmul_rn(u4[i], p.inv_pixmm), bot = __fmul_rn(d4[i], p.inv_pixmm);
+                const float lef = __fmul_rn(c6[i], p.inv_pixmm), rig = __fmul_rn(c6[i + 2], p.inv_pixmm);
+                gx[i] = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
+                gy[i] = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
+            }
+            if (x0 == 0) { gx[0] = gx[1]; gy[0] = gy[1]; }         // column 0 samples column 1
+            if (x0 == IMG_W - 4) { gx[3] = gx[2]; gy[3] = gy[2]; } // column 319 samples column 318
+            // tt = sqrt(s2) is zero iff s2 is zero: flat pixels (exact zero gradient) need no sqrt / atan
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
+                nonflat |= s2[i] != 0.0f;
+            }
         }
         const bool warp_nonflat = __any_sync(0xffffffffu, nonflat) && !(p.dbg & 4);
-        const size_t pix = (size_t)row * IMG_W + x0;
+        if (!warp_nonflat) {
+            if (tk && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tk + 38), 1ull);
+            const float4* f4 = reinterpret_cast<const float4*>(flat_half + pix * 3);
+            const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
+            o4[0] = t0; o4[1] = t1; o4[2] = t2;
+            continue;
+        }
         const float4* bg4 = reinterpret_cast<const float4*>(bg_half + pix * 3);
-        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, b2 = b0;
-        if (!(p.dbg & 2)) { b0 = __ldg(bg4); b1 = __ldg(bg4 + 1); b2 = __ldg(bg4 + 2); }
+        const float4 b0 = __ldg(bg4), b1 = __ldg(bg4 + 1), b2 = __ldg(bg4 + 2);
         const float bgv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+        int bin[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float tt = __fsqrt_rn(s2[i]);
+            const float mag = atanf_c(tt);
+            const float dir = (tt != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f;
+            int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
+            int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
+            im = min(max(im, 0), p.nb - 1);
+            id = min(max(id, 0), p.nb - 1);
+            bin[i] = im * p.nb + id; // record index into [nb][nb][20 floats]
+        }
+        if (tk && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tk + 37), 1ull);
         float o[12];
         const float yf = __fmul_rn((float)gy_, p.fy);
         const float f1 = __fmul_rn(yf, yf);
-        const float4* pp[4];
-        if (warp_nonflat) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                tt[i] = __fsqrt_rn(s2[i]);
-                const float mag = atanf_c(tt[i]);
-                const float dir = (tt[i] != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f;
-                int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
-                int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
-                im = min(max(im, 0), p.nb - 1);
-                id = min(max(id, 0), p.nb - 1);
-                pp[i] = p.poly + (size_t)(im * p.nb + id) * 5; // [nb][nb][3][6] padded to 20 floats
-            }
-        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float cf[18];
-            if (warp_nonflat) {
-                const float4 a0 = __ldg(pp[i]), a1 = __ldg(pp[i] + 1), a2 = __ldg(pp[i] + 2), a3 = __ldg(pp[i] + 3),
-                             a4 = __ldg(pp[i] + 4);
-                const float t20[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
-                                       a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+            // cooperative gather: float4 number idx = e * 32 + lane of the 32 x 5 float4 this warp needs
+            __syncwarp();
 #pragma unroll
-                for (int k = 0; k < 18; ++k) cf[k] = t20[k];
-            } else {
+            for (int e = 0; e < 5; ++e) {
+                const int idx = e * 32 + lane;
+                const int rec = idx / 5, part = idx - rec * 5;
+                const int bsrc = __shfl_sync(0xffffffffu, bin[i], rec);
+                reinterpret_cast<float4*>(stage)[idx] = __ldg(p.poly + (size_t)bsrc * 5 + part);
+            }
+            __syncwarp();
+            float cf[20];
 #pragma unroll
-                for (int k = 0; k < 18; ++k) cf[k] = cflat[k];
+            for (int e = 0; e < 5; ++e) {
+                const float4 t = reinterpret_cast<const float4*>(stage)[lane * 5 + e];
+                cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
             }
             const float xf = __fmul_rn((float)(x0 + i), p.fx);
-            const float f0 = __fmul_rn(xf, xf), f2 = __fmul_rn(xf, yf);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const float* pc = cf + 6 * ch;
-                float s = pc[5];
-                s = __fmaf_rn(pc[4], yf, s);
-                s = __fmaf_rn(pc[3], xf, s);
-                s = __fmaf_rn(pc[2], f2, s);
-                s = __fmaf_rn(pc[1], f1, s);
-                s = __fmaf_rn(pc[0], f0, s);
-                s = __fadd_rn(s, bgv[3 * i + ch]);
-                o[3 * i + ch] = fminf(fmaxf(s, 0.0f), 1.0f);
-            }
+            poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), f1, __fmul_rn(xf, yf), bgv + 3 * i, o + 3 * i);
         }
-        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
         if (!(p.dbg & 1) || o[0] < -1.0f) {
             o4[0] = make_float4(o[0], o[1], o[2], o[3]);
             o4[1] = make_float4(o[4], o[5], o[6], o[7]);

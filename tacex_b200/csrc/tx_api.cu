@@ -21,6 +21,7 @@ struct tx_handle {
     float4* d_poly = nullptr; // [nb][nb][20]
     float* d_bg = nullptr;    // [H][W][3]
     float* d_gel = nullptr;   // [H][W] or nullptr
+    float* d_flat = nullptr;  // [H][W][3] flat-pixel RGB
     // marker grid
     int M = 0;
     std::vector<int32_t> mx, my;
@@ -63,6 +64,8 @@ static int fail(tx_handle* h, int code, const std::string& msg)
         if (_e != cudaSuccess)                                                                                        \
             return fail((h), TX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
     } while (0)
+
+static void fill_taxim_consts(const tx_handle* h, TaximArgs& a);
 
 extern "C" int tx_abi_version(void) { return TX_ABI_VERSION; }
 
@@ -161,7 +164,7 @@ extern "C" void tx_destroy(tx_handle* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_mx); cudaFree(h->d_my);
+    cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
     cudaFree(h->d_traj_len); cudaFree(h->d_markers);
@@ -208,8 +211,36 @@ extern "C" int tx_upload_tables(tx_handle* h, const float* poly_grad, const floa
         cudaFree(h->d_gel);
         h->d_gel = nullptr;
     }
+    if (!h->d_flat) TX_CUDA(h, cudaMalloc(&h->d_flat, sizeof(float) * H * W * 3));
+    {
+        TaximArgs a{};
+        fill_taxim_consts(h, a);
+        TX_CUDA(h, launch_flat_rgb(a, h->d_flat, h->stream));
+        TX_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->ctr.kernels_launched++;
+    }
     h->have_tables = true;
     return TX_OK;
+}
+
+static void fill_taxim_consts(const tx_handle* h, TaximArgs& a)
+{
+    const tx_config& c = h->cfg;
+    a.gel = h->d_gel;
+    a.poly = h->d_poly;
+    a.bg_hwc = h->d_bg;
+    a.flat_rgb = h->d_flat;
+    a.inv_pixmm = 1.0f / c.pixmm;
+    a.sy = (float)c.H / c.calib_h;
+    a.sx = (float)c.W / c.calib_w;
+    a.fx = c.calib_w / (float)c.W;
+    a.fy = c.calib_h / (float)c.H;
+    a.contact_scale = c.contact_scale;
+    a.gelpad_h = c.gelpad_height_m;
+    a.gelpad_min = c.gelpad_to_cam_min_m;
+    a.inv_xbin = (float)(1.0 / (0.5 * M_PI / (c.num_bins - 1)));
+    a.inv_ybin = (float)(1.0 / (2.0 * M_PI / (c.num_bins - 1)));
+    a.nb = c.num_bins;
 }
 
 extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N, float* depth_mm)
@@ -237,9 +268,7 @@ extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* pres
     TaximArgs a{};
     a.hm = height_mm;
     a.press_in = press_mm;
-    a.gel = h->d_gel;
-    a.poly = h->d_poly;
-    a.bg_hwc = h->d_bg;
+    fill_taxim_consts(h, a);
     a.rgb = rgb;
     a.depth_out = depth_out;
     a.deformed_out = deformed;
@@ -253,18 +282,6 @@ extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* pres
         a.mk_y = h->d_my;
         a.M = h->M;
     }
-    const tx_config& c = h->cfg;
-    a.inv_pixmm = 1.0f / c.pixmm;
-    a.sy = (float)c.H / c.calib_h;
-    a.sx = (float)c.W / c.calib_w;
-    a.fx = c.calib_w / (float)c.W;
-    a.fy = c.calib_h / (float)c.H;
-    a.contact_scale = c.contact_scale;
-    a.gelpad_h = c.gelpad_height_m;
-    a.gelpad_min = c.gelpad_to_cam_min_m;
-    a.inv_xbin = (float)(1.0 / (0.5 * M_PI / (c.num_bins - 1)));
-    a.inv_ybin = (float)(1.0 / (2.0 * M_PI / (c.num_bins - 1)));
-    a.nb = c.num_bins;
     a.ticks = h->d_ticks;
     a.dbg = h->dbg;
     TX_CUDA(h, launch_taxim(a, N, h->stream));
@@ -318,6 +335,13 @@ extern "C" int tx_debug_set_ticks(tx_handle* h, long long* ticks)
     h->dbg = 0;
     const char* e = getenv("TX_DEBUG_FLAGS"); // profiling experiments (tools/phase_times.py); never set in production
     if (e) h->dbg = atoi(e);
+    return TX_OK;
+}
+
+extern "C" int tx_debug_set_flags(tx_handle* h, int flags)
+{
+    if (!h) return TX_ERR_INVALID_ARG;
+    h->dbg = flags;
     return TX_OK;
 }
 

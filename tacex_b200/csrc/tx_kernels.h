@@ -21,6 +21,7 @@ struct TaximArgs {
     const float* gel;      // [240][320] or nullptr (flat)
     const float4* poly;    // [nb][nb][20] (3 channels x 6 coefficients, padded)
     const float* bg_hwc;   // [240][320][3]
+    const float* flat_rgb; // [240][320][3] RGB of a flat (zero-gradient) pixel: clip(poly(bin(0, 0)) + background)
     float* rgb;            // [N][240][320][3]
     float* depth_out;      // [N] or nullptr
     float* deformed_out;   // [N][240][320] or nullptr
@@ -96,6 +97,7 @@ cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
 cudaError_t upload_taps(const float* host_taps, cudaStream_t s);
 int taxim_smem_bytes();
 cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
+cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);
 cudaError_t launch_fots(const FotsArgs& a, int N, cudaStream_t s);
 

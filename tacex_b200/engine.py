@@ -154,6 +154,9 @@ class TactileEngine:
         """Profiling: int64 device tensor (2*N, 40) receiving per-CTA phase clock stamps, or None to disable."""
         self._check(self.lib.tx_debug_set_ticks(self.h, _ptr(ticks)))
 
+    def set_debug_flags(self, flags: int) -> None:
+        self._check(self.lib.tx_debug_set_flags(self.h, int(flags)))
+
     def step_host(self, hm_host: torch.Tensor, rgb_host: torch.Tensor, depth_host: torch.Tensor | None = None,
                   theta_host: torch.Tensor | None = None, markers_host: torch.Tensor | None = None) -> None:
         """End-to-end call on HOST buffers (H2D + fused path + D2H inside), what bench.py's ``e2e`` times."""
