@@ -113,6 +113,13 @@ int tx_indentation_depth(tx_handle* h, const float* height_mm, int N, float* dep
 int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
               float* deformed, uint8_t* mask);
 
+/* Same as tx_render(press_mm = NULL) but takes the sensor camera's DEPTH image in metres and fuses
+ * GelSightSensor._get_height_map (ref: source/tacex/tacex/gelsight_sensor.py:581-593: inf -> far clipping plane,
+ * metres -> millimetres) into the load stage. height_mm_out (optional, [N][H][W]) receives the height map the
+ * sensor publishes as data.output["height_map"]. */
+int tx_render_depth(tx_handle* h, const float* depth_m, float clip_max_m, int N, float* rgb, float* depth_out,
+                    float* height_mm_out);
+
 /* Replaces FOTSMarkerSimulator.marker_motion_simulation + MarkerMotion.marker_sim
  * (ref: .../fots/fots_marker_sim.py:114-184, .../fots/sim/marker_motion.py:78-120,144-219) using the gel
  * deformation recorded by the preceding tx_render of the SAME batch (no second blur pyramid).

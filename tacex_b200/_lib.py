@@ -66,7 +66,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
+    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers",
 ]
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
     lib.tx_upload_tables.argtypes = [C.c_void_p, fp, fp, fp]
     lib.tx_indentation_depth.argtypes = [C.c_void_p, fp, C.c_int, fp]
     lib.tx_render.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp, u8p]
+    lib.tx_render_depth.argtypes = [C.c_void_p, fp, C.c_float, C.c_int, fp, fp, fp]
+    lib.tx_render_depth.restype = C.c_int
     lib.tx_fots_markers.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, ip, fp]
     lib.tx_marker_grid.argtypes = [C.c_void_p, ip, ip]
     lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
@@ -110,7 +112,7 @@ def load() -> C.CDLL:
     lib.tx_fem_markers.argtypes = [C.c_void_p, vp, C.c_int, vp]
     for name in ("tx_fem_create", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers", "tx_fem_markers"):
         getattr(lib, name).restype = C.c_int
-    for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_fots_markers",
+    for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_fots_markers",
                  "tx_marker_grid", "tx_step_host"):
         getattr(lib, name).restype = C.c_int
     _lib = lib

@@ -195,7 +195,7 @@ __device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, un
 // `list` holds the indices of the mask words with at least one bit set (built once per frame).
 __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits, const unsigned short* list, int nlist,
                                          const float* __restrict__ hm_half, const float* __restrict__ gel_half, float m,
-                                         float press, int warp, int lane)
+                                         float press, int warp, int lane, float depth_clip)
 {
     for (int i0 = warp * 4; i0 < nlist; i0 += NWARPS * 4) {
         float v[4];
@@ -209,7 +209,10 @@ __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits,
                 const int w = list[i];
                 idx[u] = w * 32 + lane;
                 on[u] = (maskbits[w] >> lane) & 1u;
-                if (on[u]) v[u] = __ldg(hm_half + idx[u]);
+                if (on[u]) {
+                    v[u] = __ldg(hm_half + idx[u]);
+                    if (depth_clip > 0.0f) v[u] = __fmul_rn(isinf(v[u]) ? depth_clip : v[u], 1000.0f);
+                }
             }
         }
 #pragma unroll
@@ -237,7 +240,7 @@ template <int L, int RAD, int R, bool FINAL>
 __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
                                            const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half,
                                            float m, float press, int tid, int warp, int lane, unsigned q, Region& rg,
-                                           cg::cluster_group& cluster, long long* tk)
+                                           cg::cluster_group& cluster, long long* tk, float depth_clip)
 {
     const int base = (int)q * HALF_H;
     hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1));
@@ -256,7 +259,7 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
     __syncthreads();
     TX_TICK(4 + 4 * L + 2);
     if (!FINAL) {
-        reimpose(plane, maskbits, mlist, nlist, hm_half, gel_half, m, press, warp, lane);
+        reimpose(plane, maskbits, mlist, nlist, hm_half, gel_half, m, press, warp, lane, depth_clip);
         __syncthreads();
     }
     TX_TICK(4 + 4 * L + 3);
@@ -349,6 +352,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     }
     mbar_wait(&misc->mbar, 0);
     TX_TICK(1);
+
+    // ---- optional fused GelSightSensor._get_height_map (ref: gelsight_sensor.py:581-593): depth [m] -> height map [mm] ----
+    if (p.input_is_depth) {
+        float4* p4w = reinterpret_cast<float4*>(plane);
+        float4* o4w = p.hm_out ? reinterpret_cast<float4*>(p.hm_out + half_off) : nullptr;
+        for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) {
+            float4 t = p4w[i];
+            t.x = __fmul_rn(isinf(t.x) ? p.clip_max_m : t.x, 1000.0f);
+            t.y = __fmul_rn(isinf(t.y) ? p.clip_max_m : t.y, 1000.0f);
+            t.z = __fmul_rn(isinf(t.z) ? p.clip_max_m : t.z, 1000.0f);
+            t.w = __fmul_rn(isinf(t.w) ? p.clip_max_m : t.w, 1000.0f);
+            p4w[i] = t;
+            if (o4w) o4w[i] = t;
+        }
+        __syncthreads();
+    }
 
     // ---- frame minimum (ref: taxim_torch.py:441, taxim_sim.py:116-117) ----------------------------------------
     float mloc = __int_as_float(0x7f800000);
@@ -457,17 +476,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     if (p.gel != nullptr) { rg.r0 = 0; rg.r1 = IMG_H - 1; rg.c0 = 0; rg.c1 = IMG_W - 1; } // a gel map makes the plane dense
 
     TX_TICK(3);
+    const float depth_clip = p.input_is_depth ? p.clip_max_m : 0.0f; // > 0: the input frame is a depth image in metres
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     const bool active = (p.gel != nullptr) || (press > 0.0f);
     if (active) {
-        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
-        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk);
+        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
     }
 
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------

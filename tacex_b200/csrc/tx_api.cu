@@ -255,8 +255,26 @@ extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N,
     return TX_OK;
 }
 
+static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out);
+
 extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb,
                          float* depth_out, float* deformed, uint8_t* mask)
+{
+    return render_impl(h, height_mm, press_mm, N, rgb, depth_out, deformed, mask, 0, 0.0f, nullptr);
+}
+
+extern "C" int tx_render_depth(tx_handle* h, const float* depth_m, float clip_max_m, int N, float* rgb, float* depth_out,
+                               float* height_mm_out)
+{
+    if (!(clip_max_m > 0.0f)) return fail(h, TX_ERR_INVALID_ARG, "tx_render_depth: clip_max_m must be positive");
+    if (height_mm_out && ((uintptr_t)height_mm_out & 15u))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_render_depth: device buffers must be 16-byte aligned");
+    return render_impl(h, depth_m, nullptr, N, rgb, depth_out, nullptr, nullptr, 1, clip_max_m, height_mm_out);
+}
+
+static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out)
 {
     if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render: bad argument");
     if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
@@ -268,6 +286,9 @@ extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* pres
     TaximArgs a{};
     a.hm = height_mm;
     a.press_in = press_mm;
+    a.input_is_depth = input_is_depth;
+    a.clip_max_m = clip_max_m;
+    a.hm_out = hm_out;
     fill_taxim_consts(h, a);
     a.rgb = rgb;
     a.depth_out = depth_out;

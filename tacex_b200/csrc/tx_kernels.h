@@ -18,6 +18,9 @@ constexpr int NWARPS = NTHREADS / 32;
 struct TaximArgs {
     const float* hm;       // [N][240][320] mm
     const float* press_in; // [N] or nullptr (fused indentation depth)
+    int input_is_depth;    // 1: `hm` holds the camera depth image in metres (inf = no hit): mm = (isinf ? clip_max : d) * 1000
+    float clip_max_m;      // far clipping plane of the sensor camera [m]
+    float* hm_out;         // optional [N][240][320]: the height map in mm (what GelSightSensor publishes as 'height_map')
     const float* gel;      // [240][320] or nullptr (flat)
     const float4* poly;    // [nb][nb][20] (3 channels x 6 coefficients, padded)
     const float* bg_hwc;   // [240][320][3]

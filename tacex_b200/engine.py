@@ -143,6 +143,15 @@ class TactileEngine:
                                        _ptr(mask_out)))
         return out
 
+    def render_depth(self, depth_m: torch.Tensor, clip_max_m: float, out: torch.Tensor | None = None,
+                     depth_out: torch.Tensor | None = None, height_map_out: torch.Tensor | None = None) -> torch.Tensor:
+        """Fused ``_get_height_map`` + ``compute_indentation_depth`` + ``optical_simulation`` from the raw camera depth [m]."""
+        N = self._chk_hm(depth_m)
+        out = torch.empty((N, self.H, self.W, 3), device=self.device) if out is None else out
+        self._check(self.lib.tx_render_depth(self.h, _ptr(depth_m), float(clip_max_m), N, _ptr(out), _ptr(depth_out),
+                                             _ptr(height_map_out)))
+        return out
+
     def fots_markers(self, press: torch.Tensor, theta: torch.Tensor, traj0: torch.Tensor, traj_len: torch.Tensor,
                      out: torch.Tensor | None = None) -> torch.Tensor:
         N = press.shape[0]

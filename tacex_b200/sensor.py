@@ -223,7 +223,15 @@ class GelSightSensor:
     def _update_buffers_impl(self, env_ids):
         """ref: gelsight_sensor.py:342-378 -- same order: height map, indentation depth, RGB, markers."""
         self._frame[env_ids] += 1
-        if self.compute_indentation_depth_func is not None:
+        fused = None
+        if (self.compute_indentation_depth_func is not None and self._camera_depth is not None
+                and self.cfg.compute_indentation_depth_class == "optical_sim"
+                and hasattr(self.optical_simulator, "fused_update_from_depth")):
+            # the depth pre-processing of _get_height_map is fused into the kernel's load stage (tx_render_depth)
+            fused = self.optical_simulator.fused_update_from_depth(self._camera_depth, self.cfg.sensor_camera_cfg.clipping_range[1])
+        if fused is not None:
+            self._indentation_depth[:] = fused
+        elif self.compute_indentation_depth_func is not None:
             self._get_height_map()
             self._indentation_depth[:] = self.compute_indentation_depth_func()
         if (self.optical_simulator is not None) and ("tactile_rgb" in self.cfg.data_types):

@@ -209,6 +209,19 @@ class B200TaximSimulator(GelSightSimulator):
         self._stamp = (self._hm_stamp(), self._indentation_depth._version)
         return self._indentation_depth
 
+    def fused_update_from_depth(self, depth_m: torch.Tensor, clip_max_m: float):
+        """One launch for GelSightSensor._get_height_map + compute_indentation_depth + optical_simulation, starting from the
+        raw camera depth [m] (headless sensor only; the reference sensor calls the three steps separately). Fills the
+        sensor's ``height_map`` output in place and returns the indentation depth."""
+        hm = self.sensor._data.output["height_map"]
+        W, H = self.cfg.tactile_img_res
+        if tuple(depth_m.shape[1:]) != (H, W) or hm.shape != depth_m.shape or not hm.is_contiguous() or hm.device != self.engine.device:
+            return None
+        self.engine.render_depth(depth_m.contiguous(), clip_max_m, out=self._rgb_target(), depth_out=self._indentation_depth,
+                                 height_map_out=hm)
+        self._stamp = (self._hm_stamp(), self._indentation_depth._version)
+        return self._indentation_depth
+
     def optical_simulation(self):
         """Tactile RGB (num_envs, H, W, 3) float32 in [0, 1] (ref: taxim_sim.py:80-113)."""
         if self._stamp != (self._hm_stamp(), self._indentation_depth._version):

@@ -133,6 +133,22 @@ def test_full_size_batch_roundtrip_property(eng, tables):
     assert float(out.min()) >= 0 and float(out.max()) <= 1
 
 
+def test_fused_depth_preprocessing(eng, inputs):
+    """tx_render_depth (raw camera depth in metres, inf = no hit) == _get_height_map in torch + tx_render, bit for bit."""
+    from tacex_b200 import synth
+
+    d = synth.config2(8, seed=1)["depth_m"].clone()
+    d[d >= synth.CLIP_MAX_M] = float("inf")  # what the RTX depth camera returns where nothing is hit
+    dd = d.cuda()
+    hm_ref = synth.height_map_mm(d).cuda()
+    dep_a, dep_b = torch.empty(8, device="cuda"), torch.empty(8, device="cuda")
+    hm_out = torch.empty((8, H, W), device="cuda")
+    a = eng.render_depth(dd, synth.CLIP_MAX_M, depth_out=dep_a, height_map_out=hm_out).clone()
+    b = eng.render(hm_ref, None, depth_out=dep_b)
+    torch.cuda.synchronize()
+    assert torch.equal(hm_out, hm_ref) and torch.equal(dep_a, dep_b) and torch.equal(a, b)
+
+
 def test_invalid_arguments_raise(eng, tables):
     from tacex_b200 import _lib
 
