@@ -310,6 +310,7 @@ cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s)
 }
 
 // ---- the fused kernel -------------------------------------------------------------------------------------------
+template <bool DEPTH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_fused_kernel(const TaximArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -354,7 +355,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     TX_TICK(1);
 
     // ---- optional fused GelSightSensor._get_height_map (ref: gelsight_sensor.py:581-593): depth [m] -> height map [mm] ----
-    if (p.input_is_depth) {
+    if (DEPTH) {
         float4* p4w = reinterpret_cast<float4*>(plane);
         float4* o4w = p.hm_out ? reinterpret_cast<float4*>(p.hm_out + half_off) : nullptr;
         for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) {
@@ -476,7 +477,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     if (p.gel != nullptr) { rg.r0 = 0; rg.r1 = IMG_H - 1; rg.c0 = 0; rg.c1 = IMG_W - 1; } // a gel map makes the plane dense
 
     TX_TICK(3);
-    const float depth_clip = p.input_is_depth ? p.clip_max_m : 0.0f; // > 0: the input frame is a depth image in metres
+    const float depth_clip = DEPTH ? p.clip_max_m : 0.0f; // > 0: the input frame is a depth image in metres
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     const bool active = (p.gel != nullptr) || (press > 0.0f);
@@ -576,7 +577,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         }
         const bool warp_nonflat = __any_sync(0xffffffffu, nonflat) && !(p.dbg & 4);
         if (!warp_nonflat) {
-            if (tk && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tk + 38), 1ull);
             const float4* f4 = reinterpret_cast<const float4*>(flat_half + pix * 3);
             const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
             o4[0] = t0; o4[1] = t1; o4[2] = t2;
@@ -597,7 +597,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             id = min(max(id, 0), p.nb - 1);
             bin[i] = im * p.nb + id; // record index into [nb][nb][20 floats]
         }
-        if (tk && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(tk + 37), 1ull);
         float o[12];
         const float yf = __fmul_rn((float)gy_, p.fy);
         const float f1 = __fmul_rn(yf, yf);
@@ -636,11 +635,16 @@ cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(taxim_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    taxim_fused_kernel<<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
+    if (a.input_is_depth)
+        taxim_fused_kernel<true><<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
+    else
+        taxim_fused_kernel<false><<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
     return cudaGetLastError();
 }
 

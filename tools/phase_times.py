@@ -33,7 +33,6 @@ for L in range(7):
     names[4 + 4 * L] = f"L{L} hpass"; names[5 + 4 * L] = f"L{L} cluster.sync"; names[6 + 4 * L] = f"L{L} vpass"; names[7 + 4 * L] = f"L{L} reimpose"
 names[32] = "halo+aux+sync"; names[33] = "epilogue"
 prev = 0; tot = (tk[:, 33] - tk[:, 0]).mean().item()
-print("epilogue warp-iterations per CTA: fallback %.1f, non-flat %.1f, flat-copy %.1f" % (tk[:,36].mean().item(), tk[:,37].mean().item(), tk[:,38].mean().item()))
 print(f"CTAs in contact: {tk.shape[0]}, total cycles/CTA {tot:.0f}")
 for k in sorted(names):
     d = (tk[:, k] - tk[:, prev]).mean().item(); prev = k
