@@ -411,6 +411,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     unsigned cnt = 0, srow = 0, scol = 0;
     constexpr int NWORDS = HALF_H * (IMG_W / 32);
     static_assert(NWORDS % (NWARPS * 4) == 0, "h/mask pass unroll");
+    // contact bounding box of this warp's words (warp-uniform registers; merged with 4 shared atomics per warp at the end)
+    int bb_r0 = IMG_H, bb_r1 = -1, bb_c0 = IMG_W, bb_c1 = -1;
     for (int w0 = warp * 4; w0 < NWORDS; w0 += NWARPS * 4) {
         float pv[4], gv[4];
 #pragma unroll
@@ -430,24 +432,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             plane[idx] = j;
             const unsigned bits = __ballot_sync(0xffffffffu, mk);
             const unsigned cbits = __ballot_sync(0xffffffffu, contact);
-            if (lane == 0) {
-                maskbits[w] = bits;
-                if (bits) mlist[atomicAdd(&misc->nlist, 1)] = (unsigned short)w;
-                if (cbits) { // grow the contact bounding box (the joined map is non-zero exactly where h < 0)
-                    const int rrow = (int)(q * HALF_H) + w / (IMG_W / 32), cb0 = (w % (IMG_W / 32)) * 32;
-                    atomicMin(&misc->bbox[0], rrow);
-                    atomicMax(&misc->bbox[1], rrow);
-                    atomicMin(&misc->bbox[2], cb0 + __ffs(cbits) - 1);
-                    atomicMax(&misc->bbox[3], cb0 + 31 - __clz(cbits));
+            if (lane == 0) maskbits[w] = bits;
+            if (cbits) { // grow the contact bounding box (the joined map is non-zero exactly where h < 0)
+                const int rrow = (int)(q * HALF_H) + w / (IMG_W / 32), cb0 = (w % (IMG_W / 32)) * 32;
+                bb_r0 = min(bb_r0, rrow);
+                bb_r1 = max(bb_r1, rrow);
+                bb_c0 = min(bb_c0, cb0 + __ffs(cbits) - 1);
+                bb_c1 = max(bb_c1, cb0 + 31 - __clz(cbits));
+            }
+            if (bits) {
+                if (lane == 0) mlist[atomicAdd(&misc->nlist, 1)] = (unsigned short)w;
+                if (mk) { // row / column from the word index (one word = 32 consecutive columns of one row)
+                    cnt += 1u;
+                    srow += (unsigned)(q * HALF_H) + (unsigned)w / (IMG_W / 32);
+                    scol += ((unsigned)w % (IMG_W / 32)) * 32u + (unsigned)lane;
                 }
             }
             if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
-            if (mk) { // row / column from the word index (one word = 32 consecutive columns of one row)
-                cnt += 1u;
-                srow += (unsigned)(q * HALF_H) + (unsigned)w / (IMG_W / 32);
-                scol += ((unsigned)w % (IMG_W / 32)) * 32u + (unsigned)lane;
-            }
         }
+    }
+    if (lane == 0 && bb_r1 >= 0) {
+        atomicMin(&misc->bbox[0], bb_r0);
+        atomicMax(&misc->bbox[1], bb_r1);
+        atomicMin(&misc->bbox[2], bb_c0);
+        atomicMax(&misc->bbox[3], bb_c1);
     }
     if (p.aux_sums) {
         cnt = warp_sum_u32(cnt);
@@ -526,29 +534,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     TX_TICK(32);
 
     // ---- normals -> bins -> polynomial -> + background -> clip -> NHWC (ref: taxim_torch.py:475-503, 243-258) ---
-    // One thread per 4 consecutive pixels of a row, 128-bit loads / stores. Three paths, chosen per warp:
-    //   (1) the warp's pixels lie outside the non-zero region of the deformed gel (+1 px for the central differences) or
-    //       all have an exactly zero gradient: copy the precomputed flat RGB (bit-identical to evaluating it);
-    //   (2) otherwise: canonical atan / atan2, bins, and a cooperative gather of the 80-byte table records through a
-    //       per-warp staging area (5 lanes read one record contiguously instead of 32 scattered requests per load).
+    // One thread per 4 consecutive pixels of a row, 128-bit loads / stores. The deformed gel is exactly zero outside the
+    // region `rg`, so only the pixels of the rectangle rg + 1 px (central differences; the replicate-padded border rows /
+    // columns follow their inner neighbour) can have a non-zero gradient:
+    //   (1) outside the rectangle: copy the precomputed flat RGB (bit-identical to evaluating it);
+    //   (2) inside: threads are mapped densely onto the rectangle; canonical atan / atan2, bins, and a cooperative gather
+    //       of the 80-byte table records through a per-warp staging area (5 lanes read one record contiguously instead
+    //       of 32 scattered requests per load).
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
     const float* flat_half = p.flat_rgb + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
     float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (15 x 2560 B = 38,400 B)
     constexpr int QPR = IMG_W / 4; // quads per row
-    const bool dense = active;     // without contact the whole frame is flat
-#pragma unroll 1
+    int ry0 = 0, ry1 = -1, xa = 0, xb = -1; // rectangle in LOCAL rows / image columns (empty without contact)
+    if (active && !(p.dbg & 4)) {
+        const int base = (int)q * HALF_H;
+        const int a0 = rg.r0 - 1 <= 1 ? 0 : rg.r0 - 1;                     // row 0 samples row 1
+        const int a1 = rg.r1 + 1 >= IMG_H - 2 ? IMG_H - 1 : rg.r1 + 1;     // row 239 samples row 238
+        ry0 = max(a0, base) - base;
+        ry1 = min(a1, base + HALF_H - 1) - base;
+        xa = rg.c0 - 1 <= 1 ? 0 : ((rg.c0 - 1) & ~3);                      // column 0 samples column 1
+        xb = rg.c1 + 1 >= IMG_W - 2 ? IMG_W - 1 : ((rg.c1 + 1) | 3);       // column 319 samples column 318
+    }
+    const int nq = xb >= xa ? (xb - xa + 1) >> 2 : 0;
+    const int total = ry1 >= ry0 ? nq * (ry1 - ry0 + 1) : 0;
+    // (1) flat copy of everything outside the rectangle
+#pragma unroll 2
     for (int qd = tid; qd < HALF_H * QPR; qd += NTHREADS) {
         const int row = qd / QPR;
         const int x0 = (qd - row * QPR) * 4;
+        if (total > 0 && row >= ry0 && row <= ry1 && x0 >= xa && x0 <= xb) continue;
+        const size_t pix = (size_t)row * IMG_W + x0;
+        const float4* f4 = reinterpret_cast<const float4*>(flat_half + pix * 3);
+        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
+        const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
+        o4[0] = t0; o4[1] = t1; o4[2] = t2;
+    }
+    // (2) the rectangle
+#pragma unroll 1
+    for (int qb = warp * 32; qb < total; qb += NTHREADS) {
+        const bool valid = qb + lane < total;
+        const int qd = valid ? qb + lane : total - 1;
+        const int rr = qd / nq;
+        const int row = ry0 + rr;
+        const int x0 = xa + (qd - rr * nq) * 4;
         const int gy_ = (int)q * HALF_H + row; // image row
         const size_t pix = (size_t)row * IMG_W + x0;
         float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
-        const bool inreg = dense && gy_ >= rg.r0 - 1 && gy_ <= rg.r1 + 1 && x0 + 3 >= rg.c0 - 1 && x0 <= rg.c1 + 1;
-        bool nonflat = false;
         float gx[4], gy[4], s2[4];
-        if (__any_sync(0xffffffffu, inreg)) {
+        {
             // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
             const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixels
             const float* ctr = plane + yy * IMG_W;
@@ -568,19 +603,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             }
             if (x0 == 0) { gx[0] = gx[1]; gy[0] = gy[1]; }         // column 0 samples column 1
             if (x0 == IMG_W - 4) { gx[3] = gx[2]; gy[3] = gy[2]; } // column 319 samples column 318
-            // tt = sqrt(s2) is zero iff s2 is zero: flat pixels (exact zero gradient) need no sqrt / atan
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
-                nonflat |= s2[i] != 0.0f;
-            }
-        }
-        const bool warp_nonflat = __any_sync(0xffffffffu, nonflat) && !(p.dbg & 4);
-        if (!warp_nonflat) {
-            const float4* f4 = reinterpret_cast<const float4*>(flat_half + pix * 3);
-            const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
-            o4[0] = t0; o4[1] = t1; o4[2] = t2;
-            continue;
+            for (int i = 0; i < 4; ++i) s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
         }
         const float4* bg4 = reinterpret_cast<const float4*>(bg_half + pix * 3);
         const float4 b0 = __ldg(bg4), b1 = __ldg(bg4 + 1), b2 = __ldg(bg4 + 2);
@@ -588,14 +612,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         int bin[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float tt = __fsqrt_rn(s2[i]);
-            const float mag = atanf_c(tt);
-            const float dir = (tt != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f;
+            // tt = sqrt(s2) is zero iff s2 is zero: a flat pixel (exact zero gradient) lands in bin (0, dir = 0)
+            const float tt = (p.dbg & 16) ? s2[i] : __fsqrt_rn(s2[i]);
+            const float mag = (p.dbg & 16) ? tt : atanf_c(tt);
+            const float dir = (p.dbg & 16) ? gx[i] : ((tt != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f);
             int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
             int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
             im = min(max(im, 0), p.nb - 1);
             id = min(max(id, 0), p.nb - 1);
             bin[i] = im * p.nb + id; // record index into [nb][nb][20 floats]
+            if (p.dbg & 32) bin[i] = 62;
         }
         float o[12];
         const float yf = __fmul_rn((float)gy_, p.fy);
@@ -621,7 +647,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             const float xf = __fmul_rn((float)(x0 + i), p.fx);
             poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), f1, __fmul_rn(xf, yf), bgv + 3 * i, o + 3 * i);
         }
-        if (!(p.dbg & 1) || o[0] < -1.0f) {
+        if (valid && (!(p.dbg & 1) || o[0] < -1.0f)) {
             o4[0] = make_float4(o[0], o[1], o[2], o[3]);
             o4[1] = make_float4(o[4], o[5], o[6], o[7]);
             o4[2] = make_float4(o[8], o[9], o[10], o[11]);

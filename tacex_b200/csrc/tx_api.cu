@@ -353,7 +353,6 @@ extern "C" int tx_debug_set_ticks(tx_handle* h, long long* ticks)
 {
     if (!h) return TX_ERR_INVALID_ARG;
     h->d_ticks = ticks;
-    h->dbg = 0;
     const char* e = getenv("TX_DEBUG_FLAGS"); // profiling experiments (tools/phase_times.py); never set in production
     if (e) h->dbg = atoi(e);
     return TX_OK;

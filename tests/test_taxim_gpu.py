@@ -74,6 +74,34 @@ def test_vs_reference_golden(eng, tables, inputs, golden, name):
         print(f"{name}: raw RGB L_inf vs reference {d.max():.4f} (reference self-consistency floor 0.078)")
 
 
+def test_region_edges_vs_canonical_oracle(eng, canon_taxim):
+    """The kernel skips exact-zero rows / columns and maps the normal / colour stage onto the non-zero rectangle: contacts
+    whose grown bounding box (radii 30+16+8+4+2+1+2 = 63 px) ends 0..3 px from an image border, crosses the CTA boundary
+    (row 120) or touches the border exercise every clipping branch (incl. the replicate-padded border row / column)."""
+    frames = []
+    for top in (62, 63, 64, 65, 66, 67):            # grown region starts at row top - 63 in {-1..4}
+        for size, left in ((9, 150), (40, 64), (3, 66)):
+            hm = np.full((H, W), 29.0, np.float32)
+            yy, xx = np.mgrid[0:size, 0:size]
+            hm[top:top + size, left:left + size] = 27.5 + 0.02 * ((yy - size / 2) ** 2 + (xx - size / 2) ** 2) ** 0.5
+            frames.append(hm)
+            frames.append(hm[::-1, ::-1].copy())     # same distances from the bottom / right borders
+    for top, left in ((0, 0), (110, 300), (119, 10), (230, 311), (100, 0)):
+        hm = np.full((H, W), 29.0, np.float32)
+        hm[top:top + 9, left:left + 9] = 27.9
+        frames.append(hm)
+    hm = torch.from_numpy(np.stack(frames))
+    for i in range(0, hm.shape[0], 32):
+        part = hm[i:i + 32]
+        rgb, dg, mk, dep = _run(eng, part)
+        pc = canon_taxim.indentation_depth(part.numpy())
+        o = canon_taxim.render(part.numpy(), pc)
+        assert np.array_equal(dep, pc)
+        assert np.array_equal(mk, o["mask"])
+        assert np.array_equal(dg, o["deformed"])
+        assert np.array_equal(rgb, o["rgb"]), f"frames {np.unique(np.nonzero(rgb != o['rgb'])[0]) + i}"
+
+
 def test_explicit_press_equals_fused(eng, inputs):
     hm = inputs["config2_sub"].cuda()
     press = eng.indentation_depth(hm)

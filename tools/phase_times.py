@@ -7,8 +7,10 @@ from tacex_b200.calib import TaximTables
 from tacex_b200.engine import TactileEngine
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 74
+FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 t = TaximTables.load(ROOT + "/tests/golden/gsmini_tables_320x240.npz")
 eng = TactileEngine(t, max_envs=E)
+eng.set_debug_flags(FLAGS)
 hm = synth.bench_batch(E, n_unique=64).cuda()
 rgb = torch.empty((E, 240, 320, 3), device="cuda")
 for _ in range(3):
