@@ -2,6 +2,8 @@
 #include "tx_kernels.h"
 #include <new>
 #include <string>
+#include <algorithm>
+#include <map>
 #include <vector>
 
 using namespace tx;
@@ -13,8 +15,10 @@ struct tx_fem {
     std::string err;
     std::vector<double> mass;
     int *d_tets = nullptr, *d_attach = nullptr, *d_surf = nullptr;
-    double *d_Dm_inv = nullptr, *d_vol = nullptr, *d_mass = nullptr, *d_X = nullptr, *d_h9 = nullptr, *d_tsc = nullptr;
-    int *d_adj_off = nullptr, *d_adj = nullptr;
+    double *d_Dm_inv = nullptr, *d_vol = nullptr, *d_mass = nullptr, *d_X = nullptr, *d_tsc = nullptr, *d_valg = nullptr, *d_xt = nullptr;
+    int *d_adj_off = nullptr, *d_adj = nullptr, *d_edge_off = nullptr, *d_edge_adj = nullptr, *d_ell = nullptr;
+    int *d_attach_of = nullptr, *d_surf_of = nullptr;
+    int nE = 0, n_s = 0, nslots = 0;
     int grid = 0;
     // markers
     int M = 0;
@@ -48,8 +52,8 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
         return ffail(nullptr, TX_ERR_NO_DEVICE, "tx_fem_create: no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= ndev) return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: bad device index");
     if (c->V <= 0 || c->T <= 0 || c->substep <= 0) return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: bad sizes");
-    if (fem_smem_bytes(c->V, c->S) > 227 * 1024)
-        return ffail(nullptr, TX_ERR_UNSUPPORTED, "tx_fem_create: mesh too large for the shared-memory resident solver");
+    if (c->V > fem_threads())
+        return ffail(nullptr, TX_ERR_UNSUPPORTED, "tx_fem_create: more vertices than the one-row-per-thread solver supports (576)");
     tx_fem* f = new (std::nothrow) tx_fem();
     if (!f) return ffail(nullptr, TX_ERR_INVALID_ARG, "out of host memory");
     f->cfg = *c;
@@ -95,8 +99,82 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
     FEM_CUDA_C(cudaMalloc(&f->d_vol, sizeof(double) * c->T));
     FEM_CUDA_C(cudaMalloc(&f->d_mass, sizeof(double) * c->V));
     FEM_CUDA_C(cudaMalloc(&f->d_X, sizeof(double) * 3 * c->V));
-    FEM_CUDA_C(cudaMalloc(&f->d_h9, sizeof(double) * 45 * (size_t)c->T * f->grid));
-    FEM_CUDA_C(cudaMalloc(&f->d_tsc, sizeof(double) * 48 * (size_t)c->T * f->grid));
+    FEM_CUDA_C(cudaMalloc(&f->d_tsc, sizeof(double) * 102 * (size_t)c->T * f->grid));
+    FEM_CUDA_C(cudaMalloc(&f->d_xt, sizeof(double) * 3 * (size_t)c->V * f->grid));
+    {   // vertex graph: edges (i < j) numbered by (j - i, i) so that consecutive rows read consecutive blocks; edge ->
+        // (tet, pair slot, transpose) incidence in ascending tet order; ELL rows (one slot per distinct offset j - i when
+        // the mesh is structured, otherwise the neighbours in ascending order)
+        static const int PAIR[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+        std::map<std::pair<int, int>, std::vector<int>> inc; // key (offset, i)
+        for (int t = 0; t < c->T; ++t)
+            for (int ps = 0; ps < 6; ++ps) {
+                const int a = tets[4 * t + PAIR[ps][0]], b = tets[4 * t + PAIR[ps][1]];
+                if (a == b) { tx_fem_destroy(f); return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: degenerate tet"); }
+                const int i = a < b ? a : b, j = a < b ? b : a;
+                inc[{j - i, i}].push_back(t << 4 | ps << 1 | (a > b ? 1 : 0));
+            }
+        const int nE = (int)inc.size();
+        std::vector<int> eoff(nE + 1, 0), eadj, ei(nE), ej(nE);
+        std::vector<int> offsets; // distinct directed offsets
+        {
+            int e = 0;
+            for (auto& kv : inc) {
+                ei[e] = kv.first.second;
+                ej[e] = kv.first.second + kv.first.first;
+                for (int en : kv.second) eadj.push_back(en);
+                eoff[e + 1] = (int)eadj.size();
+                if (offsets.empty() || offsets.back() != kv.first.first) offsets.push_back(kv.first.first);
+                ++e;
+            }
+        }
+        const int TH = fem_threads();
+        std::vector<std::vector<int>> rows(c->V); // packed entries per row
+        int nslots = 0;
+        std::vector<int> ell;
+        if ((int)offsets.size() <= 16) { // structured: slot = rank of the directed offset (negative offsets first)
+            nslots = 2 * (int)offsets.size();
+            ell.assign((size_t)nslots * TH, -1);
+            for (int e = 0; e < nE; ++e) {
+                const int k = (int)(std::lower_bound(offsets.begin(), offsets.end(), ej[e] - ei[e]) - offsets.begin());
+                ell[(size_t)(offsets.size() + k) * TH + ei[e]] = ej[e] | (e << 13);            // row i, neighbour j
+                ell[(size_t)(offsets.size() - 1 - k) * TH + ej[e]] = ei[e] | 0x1000 | (e << 13); // row j, neighbour i (A^T)
+            }
+        } else {
+            for (int e = 0; e < nE; ++e) {
+                rows[ei[e]].push_back(ej[e] | (e << 13));
+                rows[ej[e]].push_back(ei[e] | 0x1000 | (e << 13));
+            }
+            for (auto& r : rows) nslots = std::max(nslots, (int)r.size());
+            ell.assign((size_t)nslots * TH, -1);
+            for (int i = 0; i < c->V; ++i) {
+                std::sort(rows[i].begin(), rows[i].end(), [](int x, int y) { return (x & 0xfff) < (y & 0xfff); });
+                for (size_t k = 0; k < rows[i].size(); ++k) ell[k * TH + i] = rows[i][k];
+            }
+        }
+        f->nE = nE;
+        f->nslots = nslots;
+        f->n_s = std::min(nE, fem_max_smem_edges(c->V));
+        std::vector<int> attach_of(c->V, -1), surf_of(c->V, -1);
+        for (int k = 0; k < c->A; ++k) {
+            if (attach[k] < 0 || attach[k] >= c->V) { tx_fem_destroy(f); return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: attach index out of range"); }
+            attach_of[attach[k]] = k;
+        }
+        for (int k = 0; k < c->S; ++k) {
+            if (surf[k] < 0 || surf[k] >= c->V) { tx_fem_destroy(f); return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: surface index out of range"); }
+            surf_of[surf[k]] = k;
+        }
+        FEM_CUDA_C(cudaMalloc(&f->d_edge_off, sizeof(int) * (nE + 1)));
+        FEM_CUDA_C(cudaMalloc(&f->d_edge_adj, sizeof(int) * eadj.size()));
+        FEM_CUDA_C(cudaMalloc(&f->d_ell, sizeof(int) * ell.size()));
+        FEM_CUDA_C(cudaMalloc(&f->d_attach_of, sizeof(int) * c->V));
+        FEM_CUDA_C(cudaMalloc(&f->d_surf_of, sizeof(int) * c->V));
+        FEM_CUDA_C(cudaMalloc(&f->d_valg, sizeof(double) * 9 * (size_t)std::max(nE - f->n_s, 1) * f->grid));
+        FEM_CUDA_C(cudaMemcpy(f->d_edge_off, eoff.data(), sizeof(int) * (nE + 1), cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_edge_adj, eadj.data(), sizeof(int) * eadj.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_ell, ell.data(), sizeof(int) * ell.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_attach_of, attach_of.data(), sizeof(int) * c->V, cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_surf_of, surf_of.data(), sizeof(int) * c->V, cudaMemcpyHostToDevice));
+    }
     {   // vertex -> (tet, local vertex) incidence in CSR form, ascending tet order
         std::vector<int> off(c->V + 1, 0), adj((size_t)4 * c->T);
         for (int t = 0; t < c->T; ++t)
@@ -132,7 +210,8 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     if (!f) return;
     cudaSetDevice(f->device);
     cudaFree(f->d_tets); cudaFree(f->d_attach); cudaFree(f->d_surf); cudaFree(f->d_Dm_inv); cudaFree(f->d_vol);
-    cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_h9); cudaFree(f->d_tsc); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
+    cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_tsc); cudaFree(f->d_valg); cudaFree(f->d_xt); cudaFree(f->d_edge_off); cudaFree(f->d_edge_adj);
+    cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
     cudaFree(f->d_tri); cudaFree(f->d_w);
     delete f;
 }
@@ -156,8 +235,12 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.N = N; a.V = c.V; a.T = c.T; a.A = c.A; a.S = c.S;
     a.tets = f->d_tets; a.Dm_inv = f->d_Dm_inv; a.vol = f->d_vol; a.mass = f->d_mass; a.attach = f->d_attach; a.surf = f->d_surf;
     a.x = x; a.v = v; a.x_prev = x_prev; a.aim = aim; a.ind_prev = ind_prev; a.ind_next = ind_next; a.stats = stats;
-    a.h9_scratch = f->d_h9;
     a.tet_scratch = f->d_tsc;
+    a.val_scratch = f->d_valg;
+    a.xt_scratch = f->d_xt;
+    a.nE = f->nE; a.n_s = f->n_s; a.nslots = f->nslots;
+    a.edge_off = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
+    a.attach_of = f->d_attach_of; a.surf_of = f->d_surf_of;
     a.adj_off = f->d_adj_off;
     a.adj = f->d_adj;
     a.dt = c.dt;

@@ -21,7 +21,7 @@
 
 namespace tx {
 
-constexpr int FEM_THREADS = 256;
+constexpr int FEM_THREADS = 576; // one thread per vertex row (V <= 576), 18 warps
 
 // ---- small dense helpers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double det3cm(const double* F)
@@ -289,6 +289,123 @@ __device__ void snh_hessian_spd_analytic(const double* F, double mu, double lamb
         }
 }
 
+// Per-tet gradient and 12x12 Hessian blocks straight from the analytic eigen-system (no 9x9 / 12x12 work matrices):
+// with dF = sum_v dx_v W_v^T, y_v = U^T dx_v and z_v = V^T W_v the rotated increment is d-hat = sum_v y_v z_v^T, so the
+// (va, vb) block of the projected Hessian is U S U^T with
+//   S[i][j] = Ap[i][j] z_va[i] z_vb[j]                                        (scaling block, clamped)
+//   S[i][i] += dd_ij z_va[j] z_vb[j],  S[j][j] += dd_ij z_va[i] z_vb[i]       (twist / flip pairs i < j, clamped)
+//   S[i][j] += od_ij z_va[j] z_vb[i],  S[j][i] += od_ij z_va[i] z_vb[j]
+// Output (structure of arrays over the tet index, stride T): rows 0..11 gradient, 12 + 9 v diagonal block of local vertex
+// v, 48 + 9 s off-diagonal block of the local pair s in (0,1) (0,2) (0,3) (1,2) (1,3) (2,3).
+__device__ void tet_contrib(const double* F, const double W[4][3], double mu, double lambda, double sc, double* to, int T)
+{
+    double V[3][3], U[3][3], sg[3];
+    {
+        const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
+        double w[3];
+        jacobi3(f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2], f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2],
+                f0[0] * f2[0] + f0[1] * f2[1] + f0[2] * f2[2], f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2],
+                f1[0] * f2[0] + f1[1] * f2[1] + f1[2] * f2[2], f2[0] * f2[0] + f2[1] * f2[1] + f2[2] * f2[2], w, V);
+#define SWAPC(i, j)                                                                                                    \
+    if (w[i] < w[j]) {                                                                                                \
+        double t_ = w[i]; w[i] = w[j]; w[j] = t_;                                                                     \
+        for (int r_ = 0; r_ < 3; ++r_) { t_ = V[r_][i]; V[r_][i] = V[r_][j]; V[r_][j] = t_; }                         \
+    }
+        SWAPC(0, 1) SWAPC(0, 2) SWAPC(1, 2)
+#undef SWAPC
+        const double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
+                            V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
+        if (detV < 0.0)
+            for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
+        double Fv[3][3]; // Fv[i] = F v_i
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Fv[i][r] = F[r] * V[0][i] + F[3 + r] * V[1][i] + F[6 + r] * V[2][i];
+        const double n0 = sqrt(Fv[0][0] * Fv[0][0] + Fv[0][1] * Fv[0][1] + Fv[0][2] * Fv[0][2]);
+        for (int r = 0; r < 3; ++r) U[r][0] = Fv[0][r] / n0;
+        const double d01 = U[0][0] * Fv[1][0] + U[1][0] * Fv[1][1] + U[2][0] * Fv[1][2];
+        const double t1[3] = {Fv[1][0] - d01 * U[0][0], Fv[1][1] - d01 * U[1][0], Fv[1][2] - d01 * U[2][0]};
+        const double n1 = sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+        for (int r = 0; r < 3; ++r) U[r][1] = t1[r] / n1;
+        U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+        U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+        U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sg[i] = U[0][i] * Fv[i][0] + U[1][i] * Fv[i][1] + U[2][i] * Fv[i][2];
+    }
+    const double J = sg[0] * sg[1] * sg[2];
+    const double c = lambda * (J - 1.0) - mu;
+    // gradient: dPsi/dF = mu F + c cof(F) = U diag(mu s_i + c s_j s_k) V^T, g_v = dPsi/dF W_v
+    {
+        const double dg[3] = {sc * (mu * sg[0] + c * sg[1] * sg[2]), sc * (mu * sg[1] + c * sg[0] * sg[2]), sc * (mu * sg[2] + c * sg[0] * sg[1])};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            double z[3];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) z[b] = dg[b] * (V[0][b] * W[v][0] + V[1][b] * W[v][1] + V[2][b] * W[v][2]);
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) to[(size_t)(3 * v + cc) * T] = U[cc][0] * z[0] + U[cc][1] * z[1] + U[cc][2] * z[2];
+        }
+    }
+    // clamped scaling block and twist / flip pairs
+    double Ap[3][3], dd[3], od[3]; // dd / od indexed by the third index k of the pair (i, j)
+    {
+        const double sw[3] = {sg[1] * sg[2], sg[0] * sg[2], sg[0] * sg[1]};
+        double aw[3], Q[3][3];
+        jacobi3(mu + lambda * sw[0] * sw[0], c * sg[2] + lambda * sw[0] * sw[1], c * sg[1] + lambda * sw[0] * sw[2],
+                mu + lambda * sw[1] * sw[1], c * sg[0] + lambda * sw[1] * sw[2], mu + lambda * sw[2] * sw[2], aw, Q);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) aw[k] = aw[k] < 0.0 ? 0.0 : aw[k] * sc;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Ap[i][j] = Q[i][0] * aw[0] * Q[j][0] + Q[i][1] * aw[1] * Q[j][1] + Q[i][2] * aw[2] * Q[j][2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double lt = mu + c * sg[k], lf = mu - c * sg[k];
+            const double ltp = lt < 0.0 ? 0.0 : lt, lfp = lf < 0.0 ? 0.0 : lf;
+            dd[k] = 0.5 * (ltp + lfp) * sc;
+            od[k] = 0.5 * (lfp - ltp) * sc;
+        }
+    }
+    double Z[4][3]; // z_v = V^T W_v
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Z[v][b] = V[0][b] * W[v][0] + V[1][b] * W[v][1] + V[2][b] * W[v][2];
+#pragma unroll
+    for (int vb = 0; vb < 4; ++vb)
+#pragma unroll
+        for (int va = 0; va <= vb; ++va) {
+            const double* za = Z[va];
+            const double* zb = Z[vb];
+            double S[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) S[i][j] = Ap[i][j] * za[i] * zb[j];
+            // pairs (0,1) k=2, (0,2) k=1, (1,2) k=0
+            S[0][0] += dd[2] * za[1] * zb[1] + dd[1] * za[2] * zb[2];
+            S[1][1] += dd[2] * za[0] * zb[0] + dd[0] * za[2] * zb[2];
+            S[2][2] += dd[1] * za[0] * zb[0] + dd[0] * za[1] * zb[1];
+            S[0][1] += od[2] * za[1] * zb[0]; S[1][0] += od[2] * za[0] * zb[1];
+            S[0][2] += od[1] * za[2] * zb[0]; S[2][0] += od[1] * za[0] * zb[2];
+            S[1][2] += od[0] * za[2] * zb[1]; S[2][1] += od[0] * za[1] * zb[2];
+            double US[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) US[i][j] = U[i][0] * S[0][j] + U[i][1] * S[1][j] + U[i][2] * S[2][j];
+            const int base = va == vb ? 12 + 9 * va : 48 + 9 * (va == 0 ? vb - 1 : (va == 1 ? vb + 1 : 5));
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    to[(size_t)(base + 3 * i + j) * T] = US[i][0] * U[j][0] + US[i][1] * U[j][1] + US[i][2] * U[j][2];
+        }
+}
+
 __device__ __forceinline__ void barrier_fn(double D, double d_hat, double kappa, double* B, double* dB, double* ddB)
 {
     const double D0 = d_hat * d_hat;
@@ -387,29 +504,28 @@ __device__ __forceinline__ void tet_F(const double* x, const int* e, const doubl
 }
 
 // ---- block reductions (deterministic: fixed tree over a fixed thread -> element mapping) -----------------------------
+// One __syncthreads per reduction: the per-warp partials are double-buffered (consecutive calls alternate buffers) and every
+// thread folds the NW partials itself in the same fixed order.
 struct Red {
-    double buf[FEM_THREADS / 32];
-    double result;
+    double buf[2][FEM_THREADS / 32];
 };
 
 template <int OP> // 0 sum, 1 min, 2 max
-__device__ double block_reduce(double v, Red* red)
+__device__ __forceinline__ double block_reduce(double v, Red* red, int& phase)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double t = __shfl_xor_sync(0xffffffffu, v, o);
         v = OP == 0 ? v + t : (OP == 1 ? fmin(v, t) : fmax(v, t));
     }
-    __syncthreads(); // protects red->result of a previous call
-    if ((threadIdx.x & 31) == 0) red->buf[threadIdx.x >> 5] = v;
+    double* b = red->buf[phase & 1];
+    phase ^= 1;
+    if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = red->buf[0];
-        for (int w = 1; w < FEM_THREADS / 32; ++w) s = OP == 0 ? s + red->buf[w] : (OP == 1 ? fmin(s, red->buf[w]) : fmax(s, red->buf[w]));
-        red->result = s;
-    }
-    __syncthreads();
-    return red->result;
+    double s = b[0];
+#pragma unroll
+    for (int w = 1; w < FEM_THREADS / 32; ++w) s = OP == 0 ? s + b[w] : (OP == 1 ? fmin(s, b[w]) : fmax(s, b[w]));
+    return s;
 }
 
 // symmetric packed index of a 9x9 matrix (upper triangle, row-major)
@@ -419,248 +535,240 @@ __device__ __forceinline__ int sym9(int i, int j)
     return a * 9 - a * (a - 1) / 2 + (b - a);
 }
 
+// symmetric 3x3 stored as (00, 01, 02, 11, 12, 22)
+__device__ __forceinline__ void sym3_mul(const double* m, double p0, double p1, double p2, double& y0, double& y1, double& y2)
+{
+    y0 = m[0] * p0 + m[1] * p1 + m[2] * p2;
+    y1 = m[1] * p0 + m[3] * p1 + m[4] * p2;
+    y2 = m[2] * p0 + m[4] * p1 + m[5] * p2;
+}
+
+// Shared memory: positions x and the PCG direction p (both read by other rows), reduction scratch, and as many off-diagonal
+// 3x3 blocks of the assembled Hessian as fit ([9][n_s], structure of arrays over the edge index); the remaining blocks
+// live in an L2-resident global scratch of the CTA. Everything that only its own row touches (gradient, diagonal block,
+// preconditioner, r / z / dx of PCG, line-search base) lives in the registers of the thread that owns the row.
 struct FemShared {
-    double* x; double* xt; double* dx; double* x0; double* r; double* z; double* p; double* Ap; double* G;
-    double* Dg;  // [V][9]  diagonal blocks, inverted in place for the preconditioner
-    double* Hc;  // [S][9]
+    double* x;   // [3V]
+    double* p;   // [3V]
+    double* val; // [9][n_s]
     Red* red;
 };
 
-__device__ double total_energy(const FemArgs& a, const FemShared& s, const double* x, const double* xprev_g,
-                               const double* aim_g, const FemIndenter& ind, double ratio, double* min_dist, double* h9_unused)
+// total incremental potential at the positions in s.x (thread `row` owns vertex `row`)
+__device__ double total_energy(const FemArgs& a, const FemShared& s, const double* xt_g,
+                               const double* __restrict__ xprev_g, const double* __restrict__ aim_g, const FemIndenter& ind,
+                               double ratio, double* min_dist, int& ph)
 {
     const double dt2 = a.dt * a.dt;
+    const int i = threadIdx.x;
     double E = 0.0, md = 1e300;
     bool bad = false;
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
+    if (i < a.V) {
+        const double xi[3] = {s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]};
+        const double m = a.mass[i];
         double q = 0;
-        for (int c = 0; c < 3; ++c) { const double d = x[3 * i + c] - s.xt[3 * i + c]; q += d * d; }
-        E += 0.5 * a.mass[i] * q;
+        for (int c = 0; c < 3; ++c) { const double d = xi[c] - xt_g[3 * i + c]; q += d * d; }
+        E += 0.5 * m * q;
+        const int ka = a.attach_of[i];
+        if (ka >= 0) {
+            double q2 = 0;
+            for (int c = 0; c < 3; ++c) {
+                const double xp = xprev_g[3 * i + c];
+                const double aimx = xp + (aim_g[3 * ka + c] - xp) * ratio;
+                const double d = xi[c] - aimx;
+                q2 += d * d;
+            }
+            E += 0.5 * a.attach_strength * m * q2;
+        }
+        if (a.surf_of[i] >= 0) {
+            double d, n[3], B;
+            indenter_sdf(ind, xi, &d, n, nullptr);
+            md = d;
+            if (d <= 0.0) bad = true;
+            else {
+                barrier_fn(d * d, a.d_hat, a.kappa * dt2, &B, nullptr, nullptr);
+                E += B;
+            }
+        }
     }
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         double W[4][3], F[9], e;
-        int ev[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
+        const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
+        const int ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
         tet_W(a.Dm_inv, t, a.T, W);
-        tet_F(x, ev, W, F);
+        tet_F(s.x, ev, W, F);
         snh(F, a.mu, a.lambda, &e, nullptr, nullptr);
         E += dt2 * a.vol[t] * e;
     }
-    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
-        const int i = a.attach[k];
-        double q = 0;
-        for (int c = 0; c < 3; ++c) {
-            const double xp = xprev_g[3 * i + c];
-            const double aimx = xp + (aim_g[3 * k + c] - xp) * ratio;
-            const double d = x[3 * i + c] - aimx;
-            q += d * d;
-        }
-        E += 0.5 * a.attach_strength * a.mass[i] * q;
-    }
-    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
-        const int i = a.surf[k];
-        double d, n[3], B;
-        indenter_sdf(ind, x + 3 * i, &d, n, nullptr);
-        md = fmin(md, d);
-        if (d <= 0.0) { bad = true; continue; }
-        barrier_fn(d * d, a.d_hat, a.kappa * dt2, &B, nullptr, nullptr);
-        E += B;
-    }
-    E = block_reduce<0>(E, s.red);
-    md = block_reduce<1>(md, s.red);
-    const double anybad = block_reduce<2>(bad ? 1.0 : 0.0, s.red);
+    E = block_reduce<0>(E, s.red, ph);
+    md = block_reduce<1>(md, s.red, ph);
+    const double anybad = block_reduce<2>(bad ? 1.0 : 0.0, s.red, ph);
     if (min_dist) *min_dist = md;
     return anybad > 0.0 ? INFINITY : E;
 }
 
-__device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xprev_g, const double* aim_g,
-                          const FemIndenter& ind, double ratio, double* h9 /*[T][45] scratch*/, double* tsc /*[T][48]*/)
+// Gradient g3 (row-local), diagonal block d6 (row-local, symmetric) and the off-diagonal blocks of the Hessian (s.val / valg)
+__device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt_g, const double* __restrict__ xprev_g,
+                          const double* __restrict__ aim_g, const FemIndenter& ind, double ratio, double* __restrict__ tsc /*[102][T]*/,
+                          double* valg, double g3[3], double d6[6])
 {
     const double dt2 = a.dt * a.dt;
-    for (int i = threadIdx.x; i < 3 * a.V; i += FEM_THREADS) s.G[i] = 0.0;
-    for (int i = threadIdx.x; i < 9 * a.V; i += FEM_THREADS) s.Dg[i] = 0.0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
-        for (int c = 0; c < 3; ++c) {
-            s.G[3 * i + c] = a.mass[i] * (s.x[3 * i + c] - s.xt[3 * i + c]);
-            s.Dg[9 * i + 4 * c] = a.mass[i];
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
-        int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
-        double W[4][3], F[9], dEdF[9], H[81];
-        tet_W(a.Dm_inv, t, a.T, W);
+    const int T = a.T;
+    // (1) per tet: gradient (12), the 4 diagonal and the 6 off-diagonal 3x3 blocks of W^T H9 W
+    for (int t = threadIdx.x; t < T; t += FEM_THREADS) {
+        const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
+        const int e[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+        double W[4][3], F[9];
+        tet_W(a.Dm_inv, t, T, W);
         tet_F(s.x, e, W, F);
-        snh(F, a.mu, a.lambda, nullptr, dEdF, H);
-        const double sc = dt2 * a.vol[t];
-        for (int i = 0; i < 9; ++i) dEdF[i] *= sc;
-        for (int i = 0; i < 81; ++i) H[i] *= sc;
-        if (!is_pd<9>(H)) snh_hessian_spd_analytic(F, a.mu, a.lambda, sc, H);
-        for (int i = 0; i < 9; ++i)
-            for (int j = i; j < 9; ++j) h9[(size_t)sym9(i, j) * a.T + t] = H[i * 9 + j];
-        double* to = tsc + t; // SoA [48][T]: rows 0..11 gradient, rows 12 + 9 v .. diagonal block of local vertex v
-        for (int v = 0; v < 4; ++v)
-            for (int c = 0; c < 3; ++c) {
-                double sum = 0;
-                for (int b = 0; b < 3; ++b) sum += dEdF[3 * b + c] * W[v][b];
-                to[(size_t)(3 * v + c) * a.T] = sum;
-            }
-        for (int v = 0; v < 4; ++v)
-            for (int c = 0; c < 3; ++c)
-                for (int cc = 0; cc < 3; ++cc) {
-                    double sum = 0;
-                    for (int b = 0; b < 3; ++b)
-                        for (int b2 = 0; b2 < 3; ++b2) sum += W[v][b] * H[(3 * b + c) * 9 + (3 * b2 + cc)] * W[v][b2];
-                    to[(size_t)(12 + 9 * v + 3 * c + cc) * a.T] = sum;
-                }
+        tet_contrib(F, W, a.mu, a.lambda, dt2 * a.vol[t], tsc + t, T);
     }
     __syncthreads();
-    // deterministic assembly: every vertex sums its incident tets in CSR order (no atomics -> bitwise reproducible)
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) {
-        double g3[3] = {s.G[3 * i], s.G[3 * i + 1], s.G[3 * i + 2]};
-        double d9[9];
-        for (int j = 0; j < 9; ++j) d9[j] = s.Dg[9 * i + j];
+    // (2) per vertex (row-local): kinetic + elastic (incident tets in CSR order: no atomics) + attachment + barrier
+    const int i = threadIdx.x;
+    g3[0] = g3[1] = g3[2] = 0.0;
+    for (int j = 0; j < 6; ++j) d6[j] = 0.0;
+    if (i < a.V) {
+        const double m = a.mass[i];
+        const double xi[3] = {s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]};
+        for (int c = 0; c < 3; ++c) g3[c] = m * (xi[c] - xt_g[3 * i + c]);
+        d6[0] = m; d6[3] = m; d6[5] = m;
         for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
             const int tv = a.adj[q];
             const double* to = tsc + (tv >> 2);
             const int v = tv & 3;
-            for (int c = 0; c < 3; ++c) g3[c] += to[(size_t)(3 * v + c) * a.T];
-            for (int j = 0; j < 9; ++j) d9[j] += to[(size_t)(12 + 9 * v + j) * a.T];
+            for (int c = 0; c < 3; ++c) g3[c] += to[(size_t)(3 * v + c) * T];
+            const double* tb = to + (size_t)(12 + 9 * v) * T;
+            d6[0] += tb[0]; d6[1] += tb[(size_t)1 * T]; d6[2] += tb[(size_t)2 * T];
+            d6[3] += tb[(size_t)4 * T]; d6[4] += tb[(size_t)5 * T]; d6[5] += tb[(size_t)8 * T];
         }
-        for (int c = 0; c < 3; ++c) s.G[3 * i + c] = g3[c];
-        for (int j = 0; j < 9; ++j) s.Dg[9 * i + j] = d9[j];
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
-        const int i = a.attach[k];
-        const double sm = a.attach_strength * a.mass[i];
-        for (int c = 0; c < 3; ++c) {
-            const double xp = xprev_g[3 * i + c];
-            const double aimx = xp + (aim_g[3 * k + c] - xp) * ratio;
-            s.G[3 * i + c] += sm * (s.x[3 * i + c] - aimx);
-            s.Dg[9 * i + 4 * c] += sm;
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
-        const int i = a.surf[k];
-        double d, n[3], Hd[9], dB, ddB, Hk[9];
-        for (int j = 0; j < 9; ++j) Hk[j] = 0.0;
-        indenter_sdf(ind, s.x + 3 * i, &d, n, Hd);
-        if ((d * d < a.d_hat * a.d_hat) && d > 0.0) {
-            barrier_fn(d * d, a.d_hat, a.kappa * dt2, nullptr, &dB, &ddB);
-            double dD[3];
-            for (int c = 0; c < 3; ++c) dD[c] = 2.0 * d * n[c];
-            for (int c = 0; c < 3; ++c) s.G[3 * i + c] += dB * dD[c];
-            for (int c = 0; c < 3; ++c)
-                for (int b = 0; b < 3; ++b) Hk[3 * c + b] = ddB * dD[c] * dD[b] + dB * 2.0 * (n[c] * n[b] + d * Hd[3 * c + b]);
-            spd_project<3>(Hk);
-            for (int j = 0; j < 9; ++j) s.Dg[9 * i + j] += Hk[j];
-        }
-        for (int j = 0; j < 9; ++j) s.Hc[9 * k + j] = Hk[j];
-    }
-    __syncthreads();
-}
-
-__device__ void apply_A(const FemArgs& a, const FemShared& s, const double* h9, double* tsc, const double* p, double* y)
-{
-    for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
-        int e[4] = {a.tets[4 * t], a.tets[4 * t + 1], a.tets[4 * t + 2], a.tets[4 * t + 3]};
-        double W[4][3], P[9], Q[9], Hs[45];
-        tet_W(a.Dm_inv, t, a.T, W);
-        tet_F(p, e, W, P);
-#pragma unroll
-        for (int i = 0; i < 45; ++i) Hs[i] = h9[(size_t)i * a.T + t];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            double q = 0;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) q += Hs[sym9(i, j)] * P[j];
-            Q[i] = q;
-        }
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-#pragma unroll
+        const int ka = a.attach_of[i];
+        if (ka >= 0) {
+            const double sm = a.attach_strength * m;
             for (int c = 0; c < 3; ++c) {
-                double q = 0;
-#pragma unroll
-                for (int b = 0; b < 3; ++b) q += Q[3 * b + c] * W[v][b];
-                tsc[(size_t)(3 * v + c) * a.T + t] = q;
+                const double xp = xprev_g[3 * i + c];
+                const double aimx = xp + (aim_g[3 * ka + c] - xp) * ratio;
+                g3[c] += sm * (xi[c] - aimx);
             }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) { // deterministic gather in CSR order
-        double y3[3];
-        for (int c = 0; c < 3; ++c) y3[c] = a.mass[i] * p[3 * i + c];
-        for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
-            const int tv = a.adj[q];
-            const double* to = tsc + (size_t)(3 * (tv & 3)) * a.T + (tv >> 2);
-            for (int c = 0; c < 3; ++c) y3[c] += to[(size_t)c * a.T];
+            d6[0] += sm; d6[3] += sm; d6[5] += sm;
         }
-        for (int c = 0; c < 3; ++c) y[3 * i + c] = y3[c];
+        if (a.surf_of[i] >= 0) {
+            double d, n[3], Hd[9], dB, ddB, Hk[9];
+            indenter_sdf(ind, xi, &d, n, Hd);
+            if ((d * d < a.d_hat * a.d_hat) && d > 0.0) {
+                barrier_fn(d * d, a.d_hat, a.kappa * dt2, nullptr, &dB, &ddB);
+                double dD[3];
+                for (int c = 0; c < 3; ++c) dD[c] = 2.0 * d * n[c];
+                for (int c = 0; c < 3; ++c) g3[c] += dB * dD[c];
+                for (int c = 0; c < 3; ++c)
+                    for (int b = 0; b < 3; ++b) Hk[3 * c + b] = ddB * dD[c] * dD[b] + dB * 2.0 * (n[c] * n[b] + d * Hd[3 * c + b]);
+                spd_project<3>(Hk);
+                d6[0] += Hk[0]; d6[1] += Hk[1]; d6[2] += Hk[2]; d6[3] += Hk[4]; d6[4] += Hk[5]; d6[5] += Hk[8];
+            }
+        }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < a.A; k += FEM_THREADS) {
-        const int i = a.attach[k];
-        for (int c = 0; c < 3; ++c) y[3 * i + c] += a.attach_strength * a.mass[i] * p[3 * i + c];
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
-        const int i = a.surf[k];
-        for (int c = 0; c < 3; ++c)
-            for (int b = 0; b < 3; ++b) y[3 * i + c] += s.Hc[9 * k + 3 * c + b] * p[3 * i + b];
+    // (3) per edge (i < j): block A_ij = sum over the incident tets, in CSR order
+    for (int e = threadIdx.x; e < a.nE; e += FEM_THREADS) {
+        double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = a.edge_off[e]; q < a.edge_off[e + 1]; ++q) {
+            const int en = a.edge_adj[q]; // tet << 4 | pair slot << 1 | transpose
+            const double* to = tsc + (size_t)(48 + 9 * ((en >> 1) & 7)) * T + (en >> 4);
+            if (en & 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) blk[3 * c + b] += to[(size_t)(3 * b + c) * T];
+            } else {
+#pragma unroll
+                for (int m = 0; m < 9; ++m) blk[m] += to[(size_t)m * T];
+            }
+        }
+        if (e < a.n_s) {
+#pragma unroll
+            for (int m = 0; m < 9; ++m) s.val[(size_t)m * a.n_s + e] = blk[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < 9; ++m) valg[(size_t)m * (a.nE - a.n_s) + (e - a.n_s)] = blk[m];
+        }
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void precond(const FemArgs& a, const FemShared& s, double* z, const double* r)
+// y = A p for the row of this thread: diagonal block + the off-diagonal blocks in ELL order (symmetric storage: the block of
+// edge (i, j), i < j, serves row i as is and row j transposed; both reads are coalesced when the edges are numbered by
+// (j - i, i), which tx_fem_create does)
+__device__ __forceinline__ void spmv_row(const FemArgs& a, const FemShared& s, const double* valg, const double d6[6],
+                                         double y[3])
 {
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS)
-        for (int c = 0; c < 3; ++c)
-            z[3 * i + c] = s.Dg[9 * i + 3 * c] * r[3 * i] + s.Dg[9 * i + 3 * c + 1] * r[3 * i + 1] + s.Dg[9 * i + 3 * c + 2] * r[3 * i + 2];
-    __syncthreads();
-}
-
-__device__ double dot_n(const FemShared& s, const double* u, const double* v, int n)
-{
-    double q = 0;
-    for (int i = threadIdx.x; i < n; i += FEM_THREADS) q += u[i] * v[i];
-    return block_reduce<0>(q, s.red);
-}
-
-// PCG, x0 = 0, b = s.G (already negated); solution in s.dx (linear_pcg.cu:45-140)
-__device__ int pcg(const FemArgs& a, const FemShared& s, const double* h9, double* tsc)
-{
-    const int n = 3 * a.V;
-    for (int i = threadIdx.x; i < a.V; i += FEM_THREADS) { // invert the diagonal blocks in place
-        double* M = s.Dg + 9 * i;
-        const double m0 = M[0], m1 = M[1], m2 = M[2], m3 = M[3], m4 = M[4], m5 = M[5], m6 = M[6], m7 = M[7], m8 = M[8];
-        const double det = m0 * (m4 * m8 - m5 * m7) - m1 * (m3 * m8 - m5 * m6) + m2 * (m3 * m7 - m4 * m6);
-        M[0] = (m4 * m8 - m5 * m7) / det; M[1] = (m2 * m7 - m1 * m8) / det; M[2] = (m1 * m5 - m2 * m4) / det;
-        M[3] = (m5 * m6 - m3 * m8) / det; M[4] = (m0 * m8 - m2 * m6) / det; M[5] = (m2 * m3 - m0 * m5) / det;
-        M[6] = (m3 * m7 - m4 * m6) / det; M[7] = (m1 * m6 - m0 * m7) / det; M[8] = (m0 * m4 - m1 * m3) / det;
+    const int i = threadIdx.x;
+    y[0] = y[1] = y[2] = 0.0;
+    if (i >= a.V) return;
+    sym3_mul(d6, s.p[3 * i], s.p[3 * i + 1], s.p[3 * i + 2], y[0], y[1], y[2]);
+    const int nEg = a.nE - a.n_s;
+#pragma unroll 2
+    for (int sl = 0; sl < a.nslots; ++sl) {
+        const int pk = __ldg(a.ell + (size_t)sl * FEM_THREADS + i);
+        if (pk < 0) continue;
+        const int j = pk & 0xfff, e = pk >> 13;
+        const double p0 = s.p[3 * j], p1 = s.p[3 * j + 1], p2 = s.p[3 * j + 2];
+        double m[9];
+        if (e < a.n_s) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) m[k] = s.val[(size_t)k * a.n_s + e];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) m[k] = valg[(size_t)k * nEg + (e - a.n_s)];
+        }
+        if (pk & 0x1000) { // this row is the j of edge (i', j): A^T
+            y[0] += m[0] * p0 + m[3] * p1 + m[6] * p2;
+            y[1] += m[1] * p0 + m[4] * p1 + m[7] * p2;
+            y[2] += m[2] * p0 + m[5] * p1 + m[8] * p2;
+        } else {
+            y[0] += m[0] * p0 + m[1] * p1 + m[2] * p2;
+            y[1] += m[3] * p0 + m[4] * p1 + m[5] * p2;
+            y[2] += m[6] * p0 + m[7] * p1 + m[8] * p2;
+        }
     }
-    for (int i = threadIdx.x; i < n; i += FEM_THREADS) { s.dx[i] = 0.0; s.r[i] = s.G[i]; }
-    __syncthreads();
-    precond(a, s, s.z, s.r);
-    for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.p[i] = s.z[i];
-    __syncthreads();
-    double rz = dot_n(s, s.r, s.z, n);
+}
+
+// PCG with the 3x3 block-Jacobi preconditioner (linear_pcg.cu:45-140, fem_diag_preconditioner.cu:112-164), x0 = 0,
+// b = -g3; solution in dx (row-local). Every vector except p is row-local (registers).
+__device__ int pcg(const FemArgs& a, const FemShared& s, const double* valg, const double g3[3], const double d6[6],
+                   double dx[3], int& ph)
+{
+    const int i = threadIdx.x;
+    const bool on = i < a.V;
+    double inv[6] = {0, 0, 0, 0, 0, 0};
+    if (on) { // inverse of the symmetric diagonal block
+        const double m0 = d6[0], m1 = d6[1], m2 = d6[2], m4 = d6[3], m5 = d6[4], m8 = d6[5];
+        const double c00 = m4 * m8 - m5 * m5, c01 = m2 * m5 - m1 * m8, c02 = m1 * m5 - m2 * m4;
+        const double det = m0 * c00 + m1 * c01 + m2 * c02;
+        inv[0] = c00 / det; inv[1] = c01 / det; inv[2] = c02 / det;
+        inv[3] = (m0 * m8 - m2 * m2) / det; inv[4] = (m1 * m2 - m0 * m5) / det; inv[5] = (m0 * m4 - m1 * m1) / det;
+    }
+    double r[3] = {-g3[0], -g3[1], -g3[2]}, z[3], pl[3], Ap[3];
+    dx[0] = dx[1] = dx[2] = 0.0;
+    sym3_mul(inv, r[0], r[1], r[2], z[0], z[1], z[2]);
+    for (int c = 0; c < 3; ++c) pl[c] = z[c];
+    if (on) { s.p[3 * i] = pl[0]; s.p[3 * i + 1] = pl[1]; s.p[3 * i + 2] = pl[2]; }
+    double rz = block_reduce<0>(on ? r[0] * z[0] + r[1] * z[1] + r[2] * z[2] : 0.0, s.red, ph); // also publishes p
     const double rz0 = fabs(rz);
     if (rz0 == 0.0) return 0;
     int k;
-    const int max_iter = a.pcg_max_iter_ratio * n;
+    const int max_iter = a.pcg_max_iter_ratio * 3 * a.V;
     for (k = 1; k < max_iter; ++k) {
-        apply_A(a, s, h9, tsc, s.p, s.Ap);
-        const double pAp = dot_n(s, s.p, s.Ap, n);
+        spmv_row(a, s, valg, d6, Ap);
+        const double pAp = block_reduce<0>(on ? pl[0] * Ap[0] + pl[1] * Ap[1] + pl[2] * Ap[2] : 0.0, s.red, ph);
         const double alpha = rz / pAp;
-        for (int i = threadIdx.x; i < n; i += FEM_THREADS) { s.dx[i] += alpha * s.p[i]; s.r[i] -= alpha * s.Ap[i]; }
-        __syncthreads();
-        precond(a, s, s.z, s.r);
-        const double rzn = dot_n(s, s.r, s.z, n);
+        for (int c = 0; c < 3; ++c) { dx[c] += alpha * pl[c]; r[c] -= alpha * Ap[c]; }
+        sym3_mul(inv, r[0], r[1], r[2], z[0], z[1], z[2]);
+        const double rzn = block_reduce<0>(on ? r[0] * z[0] + r[1] * z[1] + r[2] * z[2] : 0.0, s.red, ph);
         if (fabs(rzn) <= a.pcg_tol_rate * rz0) break;
         const double beta = rzn / rz;
-        for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.p[i] = s.z[i] + beta * s.p[i];
+        for (int c = 0; c < 3; ++c) pl[c] = z[c] + beta * pl[c];
+        // every thread is past its spmv_row (two reductions ago): p may be overwritten; the next reduction is one barrier
+        // too late for the next spmv_row, hence the explicit one
+        if (on) { s.p[3 * i] = pl[0]; s.p[3 * i + 1] = pl[1]; s.p[3 * i + 2] = pl[2]; }
         __syncthreads();
         rz = rzn;
     }
@@ -680,13 +788,14 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
     const int n = 3 * a.V;
     double* base = reinterpret_cast<double*>(smem_raw);
     FemShared s;
-    s.x = base; s.xt = s.x + n; s.dx = s.xt + n; s.x0 = s.dx + n; s.r = s.x0 + n; s.z = s.r + n; s.p = s.z + n; s.Ap = s.p + n;
-    s.G = s.Ap + n;
-    s.Dg = s.G + n;
-    s.Hc = s.Dg + 9 * a.V;
-    s.red = reinterpret_cast<Red*>(s.Hc + 9 * a.S);
-    double* h9 = a.h9_scratch + (size_t)blockIdx.x * a.T * 45;
-    double* tsc = a.tet_scratch + (size_t)blockIdx.x * a.T * 48;
+    s.x = base; s.p = s.x + n; s.val = s.p + n;
+    s.red = reinterpret_cast<Red*>(s.val + (size_t)9 * a.n_s);
+    double* tsc = a.tet_scratch + (size_t)blockIdx.x * a.T * 102;
+    double* valg = a.val_scratch + (size_t)blockIdx.x * 9 * (a.nE - a.n_s);
+    double* xt_g = a.xt_scratch + (size_t)blockIdx.x * n;
+    const int i = threadIdx.x;
+    const bool on = i < a.V;
+    int ph = 0;
 
     for (int env = blockIdx.x; env < a.N; env += gridDim.x) {
         double* xg = a.x + (size_t)env * n;
@@ -695,16 +804,17 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
         const double* aim_g = a.aim + (size_t)env * 3 * a.A;
         const FemIndenter ind_prev = a.ind_prev[env], ind_next = a.ind_next[env];
         // predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed
-        for (int i = threadIdx.x; i < n; i += FEM_THREADS) {
-            s.x[i] = xg[i];
-            s.xt[i] = xpg[i] + a.gravity[i % 3] * a.dt * a.dt + vg[i] * a.dt;
+        for (int k = threadIdx.x; k < n; k += FEM_THREADS) {
+            s.x[k] = xg[k];
+            xt_g[k] = xpg[k] + a.gravity[k % 3] * a.dt * a.dt + vg[k] * a.dt;
         }
         __syncthreads();
         const double abs_tol = a.velocity_tol * a.dt;
         double res0 = 0.0, ccd_alpha = 1.0, ind_s = 0.0, last_res = 0.0, min_dist = 0.0, energy = 0.0;
         double umax = 0.0;
-        for (int i = 0; i < 3; ++i) umax += (ind_next.c[i] - ind_prev.c[i]) * (ind_next.c[i] - ind_prev.c[i]);
+        for (int c = 0; c < 3; ++c) umax += (ind_next.c[c] - ind_prev.c[c]) * (ind_next.c[c] - ind_prev.c[c]);
         umax = sqrt(umax);
+        const bool is_surf = on && a.surf_of[i] >= 0;
         int it, pcg_total = 0, ls_total = 0, conv = 0;
         for (it = 0; it < a.newton_max_iter; ++it) {
             const double tt = ((double)it + 1.0) / (double)a.substep;
@@ -712,69 +822,70 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             if (ind_s < 1.0) { // advance the prescribed indenter by at most half of the current minimum gap
                 const FemIndenter cur = lerp_ind(ind_prev, ind_next, ind_s);
                 double md = 1e300;
-                for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
+                if (is_surf) {
                     double d, nn[3];
-                    indenter_sdf(cur, s.x + 3 * a.surf[k], &d, nn, nullptr);
-                    md = fmin(md, d);
+                    indenter_sdf(cur, s.x + 3 * i, &d, nn, nullptr);
+                    md = d;
                 }
-                md = block_reduce<1>(md, s.red);
+                md = block_reduce<1>(md, s.red, ph);
                 double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
                 if (ds < 0.0) ds = 0.0;
                 ind_s = ind_s + ds < 1.0 ? ind_s + ds : 1.0;
             }
             const FemIndenter ind = lerp_ind(ind_prev, ind_next, ind_s);
 
-            grad_hess(a, s, xpg, aim_g, ind, ratio, h9, tsc);
-            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.G[i] = -s.G[i];
-            __syncthreads();
-            pcg_total += pcg(a, s, h9, tsc);
+            double g3[3], d6[6], dx[3];
+            grad_hess(a, s, xt_g, xpg, aim_g, ind, ratio, tsc, valg, g3, d6);
+            pcg_total += pcg(a, s, valg, g3, d6, dx, ph);
 
-            double res = 0.0;
-            for (int i = threadIdx.x; i < n; i += FEM_THREADS) res = fmax(res, fabs(s.dx[i]));
-            res = block_reduce<2>(res, s.red);
+            double res = on ? fmax(fmax(fabs(dx[0]), fabs(dx[1])), fabs(dx[2])) : 0.0;
+            res = block_reduce<2>(res, s.red, ph);
             if (it == 0) res0 = res;
             const double rel = res == 0.0 ? 0.0 : res / res0;
             const bool converged = (res <= abs_tol) || (rel <= 0.001);
             last_res = res;
             if (it > 0 && converged && ccd_alpha >= 1.0 && ratio >= 1.0 && ind_s >= 1.0) { conv = 1; break; }
 
-            // line search (sim_engine_do_advance.cu:276-347)
-            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x0[i] = s.x[i];
-            __syncthreads();
+            // line search (sim_engine_do_advance.cu:276-347); x0 is row-local
+            double x0[3] = {0, 0, 0};
+            if (on) { x0[0] = s.x[3 * i]; x0[1] = s.x[3 * i + 1]; x0[2] = s.x[3 * i + 2]; }
             double alpha = 1.0;
-            for (int k = threadIdx.x; k < a.S; k += FEM_THREADS) {
-                const int i = a.surf[k];
+            if (is_surf) {
                 double d, nn[3];
-                indenter_sdf(ind, s.x0 + 3 * i, &d, nn, nullptr);
-                const double len = sqrt(s.dx[3 * i] * s.dx[3 * i] + s.dx[3 * i + 1] * s.dx[3 * i + 1] + s.dx[3 * i + 2] * s.dx[3 * i + 2]);
+                indenter_sdf(ind, x0, &d, nn, nullptr);
+                const double len = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
                 if (len > 0.0 && d < 2.0 * len + a.d_hat) alpha = fmin(alpha, 0.8 * d / len);
             }
-            alpha = block_reduce<1>(alpha, s.red);
+            alpha = block_reduce<1>(alpha, s.red, ph);
             ccd_alpha = alpha;
-            const double E0 = total_energy(a, s, s.x0, xpg, aim_g, ind, ratio, nullptr, nullptr);
-            for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x[i] = s.x0[i] + alpha * s.dx[i];
+            const double E0 = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, nullptr, ph);
+            __syncthreads(); // every thread has read s.x
+            if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
             __syncthreads();
-            double E = total_energy(a, s, s.x, xpg, aim_g, ind, ratio, &min_dist, nullptr);
+            double E = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, &min_dist, ph);
             if (!converged) {
                 int ls = 0;
                 while (ls < a.ls_max_iter) {
                     if (E <= E0) break;
                     alpha *= 0.5;
-                    for (int i = threadIdx.x; i < n; i += FEM_THREADS) s.x[i] = s.x0[i] + alpha * s.dx[i];
                     __syncthreads();
-                    E = total_energy(a, s, s.x, xpg, aim_g, ind, ratio, &min_dist, nullptr);
+                    if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
+                    __syncthreads();
+                    E = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, &min_dist, ph);
                     ++ls;
                     ++ls_total;
                 }
             }
             energy = E;
+            __syncthreads();
         }
         // update velocity (fem_bdf1_time_integrator.cu:58-77), write back
-        for (int i = threadIdx.x; i < n; i += FEM_THREADS) {
-            const double xn = s.x[i];
-            vg[i] = (xn - xpg[i]) * (1.0 / a.dt);
-            xpg[i] = xn;
-            xg[i] = xn;
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += FEM_THREADS) {
+            const double xn = s.x[k];
+            vg[k] = (xn - xpg[k]) * (1.0 / a.dt);
+            xpg[k] = xn;
+            xg[k] = xn;
         }
         if (threadIdx.x == 0 && a.stats) {
             FemStats st;
@@ -786,11 +897,20 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
     }
 }
 
-size_t fem_smem_bytes(int V, int S) { return sizeof(double) * (9 * 3 * (size_t)V + 9 * (size_t)V + 9 * (size_t)S) + sizeof(Red) + 64; }
+int fem_threads() { return FEM_THREADS; }
+
+// n_s = number of off-diagonal blocks kept in shared memory
+size_t fem_smem_bytes(int V, int n_s) { return sizeof(double) * (2 * 3 * (size_t)V + 9 * (size_t)n_s) + sizeof(Red) + 64; }
+
+int fem_max_smem_edges(int V)
+{
+    const long avail = 227L * 1024 - (long)fem_smem_bytes(V, 0);
+    return avail > 0 ? (int)(avail / 72) : 0;
+}
 
 cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st)
 {
-    const size_t smem = fem_smem_bytes(a.V, a.S);
+    const size_t smem = fem_smem_bytes(a.V, a.n_s);
     cudaError_t e = cudaFuncSetAttribute(fem_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fem_step_kernel<<<grid, FEM_THREADS, smem, st>>>(a);

@@ -75,10 +75,17 @@ struct FemArgs {
     const double* aim;     // [N][A][3]
     const FemIndenter* ind_prev; const FemIndenter* ind_next; // [N]
     FemStats* stats;       // [N] or nullptr
-    double* h9_scratch;    // [grid][T][45]
-    double* tet_scratch;   // [grid][T][48] per-tet contributions (12 gradient / operator outputs + 4 diagonal 3x3 blocks)
+    double* tet_scratch;   // [grid][102][T] per-tet contributions: 12 gradient, 4 diagonal and 6 off-diagonal 3x3 blocks
+    double* val_scratch;   // [grid][9][nE - n_s] off-diagonal blocks that do not fit in shared memory (L2-resident)
+    double* xt_scratch;    // [grid][3V] predicted positions
     const int* adj_off;    // [V+1] CSR of the vertex -> (tet, local vertex) incidence, entries = 4 * tet + local
     const int* adj;        // [4T]
+    int nE, n_s, nslots;   // edges (i < j) of the vertex graph, edges kept in shared memory, ELL width
+    const int* edge_off;   // [nE+1] CSR of the edge -> (tet, pair slot, transpose) incidence
+    const int* edge_adj;   // entries = tet << 4 | pair slot << 1 | transpose
+    const int* ell;        // [nslots][FEM threads] row -> (neighbour j | transposed << 12 | edge << 13), -1 = empty
+    const int* attach_of;  // [V] index into attach[] or -1
+    const int* surf_of;    // [V] index into surf[] or -1
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate;
     int newton_max_iter, pcg_max_iter_ratio, ls_max_iter, substep;
 };
@@ -93,7 +100,9 @@ struct FemMarkerArgs {
     double cam_R[9], cam_t[3], fx, fy, cx, cy;
 };
 
-size_t fem_smem_bytes(int V, int S);
+size_t fem_smem_bytes(int V, int n_s);
+int fem_max_smem_edges(int V);
+int fem_threads();
 cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
 
