@@ -195,6 +195,10 @@ int tx_fem_get_mass(const tx_fem* f, double* mass);
 int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* aim, const tx_fem_indenter* ind_prev,
                 const tx_fem_indenter* ind_next, int N, tx_fem_stats* stats);
 
+/* Profiling hook: cycles (device, [#SMs][6] int64) receives the per-CTA clock64 totals of the phases of the last env each
+ * CTA processed (assembly, PCG, line search, and within the assembly: tets, vertex rows, edges); NULL disables. */
+int tx_fem_debug_set_cycles(tx_fem* f, long long* cycles);
+
 /* FEM marker read-out. set: HOST pointers, tri [M][3] surface-triangle vertex ids and barycentric weights [M][3] per marker,
  * camera pose (cam_R row-major world = R * cam, cam_t) and pinhole intrinsics. run: x DEVICE [N][V][3] ->
  * markers DEVICE [N][2][M][2] ([:,0] rest, [:,1] current, (u, v) pixels). */

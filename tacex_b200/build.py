@@ -55,7 +55,10 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
             continue
         o = LIB_DIR / (s.stem + ".o")
         if force or not o.exists() or o.stat().st_mtime < max(p.stat().st_mtime for p in list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [s, PKG.parent / "include" / "tacex_b200.h"]):
-            cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-I", str(PKG.parent / "include"), "-c", str(s), "-o", str(o)]
+            # float32 bit-parity needs explicit FMAs only (Taxim / FOTS); the float64 gel solver is tolerance-checked and
+            # wants contraction (DFMA instead of DMUL + DADD halves the work of the FP64 pipe)
+            flags = [f for f in NVCC_FLAGS if not (src.startswith("fem_") and f == "-fmad=false")]
+            cmd = [nvcc_path(), *flags, "-ccbin", "/usr/bin/g++", "-I", str(PKG.parent / "include"), "-c", str(s), "-o", str(o)]
             r = subprocess.run(cmd, capture_output=True, text=True, env=env)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

@@ -3,6 +3,7 @@
 #include <new>
 #include <string>
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -19,6 +20,7 @@ struct tx_fem {
     int *d_adj_off = nullptr, *d_adj = nullptr, *d_edge_off = nullptr, *d_edge_adj = nullptr, *d_ell = nullptr;
     int *d_attach_of = nullptr, *d_surf_of = nullptr;
     int nE = 0, n_s = 0, nslots = 0;
+    long long* d_cycles = nullptr;
     int grid = 0;
     // markers
     int M = 0;
@@ -99,7 +101,7 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
     FEM_CUDA_C(cudaMalloc(&f->d_vol, sizeof(double) * c->T));
     FEM_CUDA_C(cudaMalloc(&f->d_mass, sizeof(double) * c->V));
     FEM_CUDA_C(cudaMalloc(&f->d_X, sizeof(double) * 3 * c->V));
-    FEM_CUDA_C(cudaMalloc(&f->d_tsc, sizeof(double) * 102 * (size_t)c->T * f->grid));
+    FEM_CUDA_C(cudaMalloc(&f->d_tsc, sizeof(double) * 4 * 30 * (size_t)fem_threads() * f->grid));
     FEM_CUDA_C(cudaMalloc(&f->d_xt, sizeof(double) * 3 * (size_t)c->V * f->grid));
     {   // vertex graph: edges (i < j) numbered by (j - i, i) so that consecutive rows read consecutive blocks; edge ->
         // (tet, pair slot, transpose) incidence in ascending tet order; ELL rows (one slot per distinct offset j - i when
@@ -163,13 +165,25 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
             if (surf[k] < 0 || surf[k] >= c->V) { tx_fem_destroy(f); return ffail(nullptr, TX_ERR_INVALID_ARG, "tx_fem_create: surface index out of range"); }
             surf_of[surf[k]] = k;
         }
-        FEM_CUDA_C(cudaMalloc(&f->d_edge_off, sizeof(int) * (nE + 1)));
+        std::vector<int> es;
+        {
+            const int nch = (c->T + TH - 1) / TH;
+            es.assign((size_t)(nch + 1) * nE, 0);
+            for (int e = 0; e < nE; ++e) {
+                int q = eoff[e];
+                for (int ck = 0; ck <= nch; ++ck) {
+                    while (q < eoff[e + 1] && (eadj[q] >> 4) < ck * TH) ++q;
+                    es[(size_t)ck * nE + e] = q;
+                }
+            }
+        }
+        FEM_CUDA_C(cudaMalloc(&f->d_edge_off, sizeof(int) * es.size()));
         FEM_CUDA_C(cudaMalloc(&f->d_edge_adj, sizeof(int) * eadj.size()));
         FEM_CUDA_C(cudaMalloc(&f->d_ell, sizeof(int) * ell.size()));
         FEM_CUDA_C(cudaMalloc(&f->d_attach_of, sizeof(int) * c->V));
         FEM_CUDA_C(cudaMalloc(&f->d_surf_of, sizeof(int) * c->V));
         FEM_CUDA_C(cudaMalloc(&f->d_valg, sizeof(double) * 9 * (size_t)std::max(nE - f->n_s, 1) * f->grid));
-        FEM_CUDA_C(cudaMemcpy(f->d_edge_off, eoff.data(), sizeof(int) * (nE + 1), cudaMemcpyHostToDevice));
+        FEM_CUDA_C(cudaMemcpy(f->d_edge_off, es.data(), sizeof(int) * es.size(), cudaMemcpyHostToDevice));
         FEM_CUDA_C(cudaMemcpy(f->d_edge_adj, eadj.data(), sizeof(int) * eadj.size(), cudaMemcpyHostToDevice));
         FEM_CUDA_C(cudaMemcpy(f->d_ell, ell.data(), sizeof(int) * ell.size(), cudaMemcpyHostToDevice));
         FEM_CUDA_C(cudaMemcpy(f->d_attach_of, attach_of.data(), sizeof(int) * c->V, cudaMemcpyHostToDevice));
@@ -185,7 +199,20 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
             for (int k = 0; k < 4; ++k) adj[cur[tets[4 * t + k]]++] = 4 * t + k;
         FEM_CUDA_C(cudaMalloc(&f->d_adj_off, sizeof(int) * (c->V + 1)));
         FEM_CUDA_C(cudaMalloc(&f->d_adj, sizeof(int) * 4 * c->T));
-        FEM_CUDA_C(cudaMemcpy(f->d_adj_off, off.data(), sizeof(int) * (c->V + 1), cudaMemcpyHostToDevice));
+        {   // per chunk of one-tet-per-thread: where the entries of every row start
+            const int TH = fem_threads(), nch = (c->T + TH - 1) / TH;
+            std::vector<int> rs((size_t)(nch + 1) * TH, 0);
+            for (int i = 0; i < c->V; ++i) {
+                int q = off[i];
+                for (int ck = 0; ck <= nch; ++ck) {
+                    while (q < off[i + 1] && (adj[q] >> 2) < ck * TH) ++q;
+                    rs[(size_t)ck * TH + i] = q;
+                }
+            }
+            FEM_CUDA_C(cudaFree(f->d_adj_off));
+            FEM_CUDA_C(cudaMalloc(&f->d_adj_off, sizeof(int) * rs.size()));
+            FEM_CUDA_C(cudaMemcpy(f->d_adj_off, rs.data(), sizeof(int) * rs.size(), cudaMemcpyHostToDevice));
+        }
         FEM_CUDA_C(cudaMemcpy(f->d_adj, adj.data(), sizeof(int) * 4 * c->T, cudaMemcpyHostToDevice));
     }
     FEM_CUDA_C(cudaMemcpy(f->d_tets, tets, sizeof(int) * 4 * c->T, cudaMemcpyHostToDevice));
@@ -239,9 +266,11 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.val_scratch = f->d_valg;
     a.xt_scratch = f->d_xt;
     a.nE = f->nE; a.n_s = f->n_s; a.nslots = f->nslots;
-    a.edge_off = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
+    a.edge_start = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
     a.attach_of = f->d_attach_of; a.surf_of = f->d_surf_of;
-    a.adj_off = f->d_adj_off;
+    a.dbg_cycles = f->d_cycles;
+    a.dbg_mode = getenv("TX_FEM_DBG_MODE") ? atoi(getenv("TX_FEM_DBG_MODE")) : 0;
+    a.row_start = f->d_adj_off;
     a.adj = f->d_adj;
     a.dt = c.dt;
     for (int i = 0; i < 3; ++i) a.gravity[i] = c.gravity[i];
@@ -250,6 +279,13 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.pcg_max_iter_ratio = c.pcg_max_iter_ratio; a.ls_max_iter = c.ls_max_iter; a.substep = c.substep;
     const int grid = N < f->grid ? N : f->grid;
     FEM_CUDA(f, launch_fem_step(a, grid, f->stream));
+    return TX_OK;
+}
+
+extern "C" int tx_fem_debug_set_cycles(tx_fem* f, long long* cycles)
+{
+    if (!f) return TX_ERR_INVALID_ARG;
+    f->d_cycles = cycles;
     return TX_OK;
 }
 

@@ -162,20 +162,48 @@ __device__ void snh(const double* F, double mu, double lambda, double* E, double
 // eigenpairs are the twist (1, -1)/sqrt2 : mu + c s_k and the flip (1, 1)/sqrt2 : mu - c s_k. Clamping those nine
 // eigenvalues and rotating back gives the same matrix as the numeric 9x9 eigen-decomposition the reference (and the CPU
 // checker) use, at a fraction of the cost and without spilling an 81-entry work matrix per thread.
+// Reciprocal / reciprocal square root from the hardware approximation (about 20 bits) + two Newton steps: full double
+// precision for normal arguments, a fraction of the cost of the IEEE division / sqrt subroutines (the solver is checked
+// against the CPU restatement by tolerance, not bit for bit).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double h = 0.5 * x;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y * fma(-h * y, y, 1.5);
+}
+
+// one Jacobi rotation annihilating a_pq: t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (a_qq - a_pp) / (2 a_pq),
+// evaluated as t = +-|b| / (|d| + sqrt(d^2 + b^2)) with d = a_qq - a_pp, b = 2 a_pq (no division by a_pq)
 __device__ __forceinline__ void jrot(double& app, double& aqq, double& apq, double& arp, double& arq, double& vp0,
                                      double& vq0, double& vp1, double& vq1, double& vp2, double& vq2)
 {
-    if (apq == 0.0) return;
-    const double theta = (aqq - app) / (2.0 * apq);
-    const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+    const double d = aqq - app, b = 2.0 * apq;
+    const double h2 = fma(d, d, b * b);
+    if (!(h2 > 1e-280)) return; // a_pq == 0 (or negligible at any scale)
+    const double h = h2 * fast_rsqrt(h2);
+    const bool pos = (d == 0.0) || ((d > 0.0) == (b > 0.0));
+    const double tm = fabs(b) * fast_rcp(fabs(d) + h);
+    const double t = pos ? tm : -tm;
+    const double c = fast_rsqrt(fma(t, t, 1.0)), s = t * c;
     const double app_n = app - t * apq, aqq_n = aqq + t * apq;
     const double arp_n = c * arp - s * arq, arq_n = s * arp + c * arq;
     app = app_n; aqq = aqq_n; apq = 0.0; arp = arp_n; arq = arq_n;
-    double a, b;
-    a = vp0; b = vq0; vp0 = c * a - s * b; vq0 = s * a + c * b;
-    a = vp1; b = vq1; vp1 = c * a - s * b; vq1 = s * a + c * b;
-    a = vp2; b = vq2; vp2 = c * a - s * b; vq2 = s * a + c * b;
+    double a, bq;
+    a = vp0; bq = vq0; vp0 = c * a - s * bq; vq0 = s * a + c * bq;
+    a = vp1; bq = vq1; vp1 = c * a - s * bq; vq1 = s * a + c * bq;
+    a = vp2; bq = vq2; vp2 = c * a - s * bq; vq2 = s * a + c * bq;
 }
 
 // eigen-decomposition of a symmetric 3x3 (a00 a01 a02 a11 a12 a22); eigenvectors are the COLUMNS of V (row-major v[r][c])
@@ -195,100 +223,6 @@ __device__ __forceinline__ void jacobi3(double a00, double a01, double a02, doub
     v[0][0] = v00; v[0][1] = v01; v[0][2] = v02; v[1][0] = v10; v[1][1] = v11; v[1][2] = v12; v[2][0] = v20; v[2][1] = v21; v[2][2] = v22;
 }
 
-// H (81, row-major over the column-major vec(F)) <- scale * SPD-projected SNH Hessian at F
-__device__ void snh_hessian_spd_analytic(const double* F, double mu, double lambda, double scale, double* H)
-{
-    // C = F^T F
-    double Cm[6];
-    {
-        const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
-        Cm[0] = f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2];
-        Cm[1] = f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2];
-        Cm[2] = f0[0] * f2[0] + f0[1] * f2[1] + f0[2] * f2[2];
-        Cm[3] = f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2];
-        Cm[4] = f1[0] * f2[0] + f1[1] * f2[1] + f1[2] * f2[2];
-        Cm[5] = f2[0] * f2[0] + f2[1] * f2[1] + f2[2] * f2[2];
-    }
-    double w[3], V[3][3];
-    jacobi3(Cm[0], Cm[1], Cm[2], Cm[3], Cm[4], Cm[5], w, V);
-    // sort columns by descending eigenvalue
-#define SWAPC(i, j)                                                                                                    \
-    if (w[i] < w[j]) {                                                                                                \
-        double t_ = w[i]; w[i] = w[j]; w[j] = t_;                                                                     \
-        for (int r_ = 0; r_ < 3; ++r_) { t_ = V[r_][i]; V[r_][i] = V[r_][j]; V[r_][j] = t_; }                         \
-    }
-    SWAPC(0, 1) SWAPC(0, 2) SWAPC(1, 2)
-#undef SWAPC
-    const double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
-                        V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
-    if (detV < 0.0)
-        for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
-    // U: u0 = F v0 / |.|, u1 = Gram-Schmidt(F v1), u2 = u0 x u1 ; signed singular values s_i = u_i . F v_i
-    double Fv[3][3]; // Fv[i] = F v_i
-    for (int i = 0; i < 3; ++i)
-        for (int r = 0; r < 3; ++r) Fv[i][r] = F[r] * V[0][i] + F[3 + r] * V[1][i] + F[6 + r] * V[2][i];
-    double U[3][3]; // columns u_i stored as U[r][i]
-    double n0 = sqrt(Fv[0][0] * Fv[0][0] + Fv[0][1] * Fv[0][1] + Fv[0][2] * Fv[0][2]);
-    for (int r = 0; r < 3; ++r) U[r][0] = Fv[0][r] / n0;
-    double d01 = U[0][0] * Fv[1][0] + U[1][0] * Fv[1][1] + U[2][0] * Fv[1][2];
-    double t1[3] = {Fv[1][0] - d01 * U[0][0], Fv[1][1] - d01 * U[1][0], Fv[1][2] - d01 * U[2][0]};
-    double n1 = sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
-    for (int r = 0; r < 3; ++r) U[r][1] = t1[r] / n1;
-    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
-    double sg[3];
-    for (int i = 0; i < 3; ++i) sg[i] = U[0][i] * Fv[i][0] + U[1][i] * Fv[i][1] + U[2][i] * Fv[i][2];
-    const double J = sg[0] * sg[1] * sg[2];
-    const double c = lambda * (J - 1.0) - mu;
-    // scaling block
-    const double sw[3] = {sg[1] * sg[2], sg[0] * sg[2], sg[0] * sg[1]};
-    double aw[3], Q[3][3];
-    jacobi3(mu + lambda * sw[0] * sw[0], c * sg[2] + lambda * sw[0] * sw[1], c * sg[1] + lambda * sw[0] * sw[2],
-            mu + lambda * sw[1] * sw[1], c * sg[0] + lambda * sw[1] * sw[2], mu + lambda * sw[2] * sw[2], aw, Q);
-    double Ap[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double q = 0;
-            for (int k = 0; k < 3; ++k) q += Q[i][k] * (aw[k] < 0.0 ? 0.0 : aw[k]) * Q[j][k];
-            Ap[i][j] = q * scale;
-        }
-    // rotated-frame Hessian Hh over indices (a, b) of d-hat, idx = 3 b + a (column-major like vec F)
-    double Hh[81];
-    for (int i = 0; i < 81; ++i) Hh[i] = 0.0;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) Hh[(4 * i) * 9 + 4 * j] = Ap[i][j]; // (i,i) <-> (j,j): idx 3i+i = 4i
-    for (int i = 0; i < 3; ++i)
-        for (int j = i + 1; j < 3; ++j) {
-            const int k = 3 - i - j;
-            const double lt = mu + c * sg[k], lf = mu - c * sg[k];
-            const double ltp = lt < 0.0 ? 0.0 : lt, lfp = lf < 0.0 ? 0.0 : lf;
-            const double dd = 0.5 * (ltp + lfp) * scale, od = 0.5 * (lfp - ltp) * scale;
-            const int pij = 3 * j + i, pji = 3 * i + j; // d_ij: row i, col j
-            Hh[pij * 9 + pij] = dd; Hh[pji * 9 + pji] = dd; Hh[pij * 9 + pji] = od; Hh[pji * 9 + pij] = od;
-        }
-    // rotate back: vec(dF) = T vec(d-hat), T[(3 j + i), (3 b + a)] = U[i][a] V[j][b];  H = T Hh T^T
-    double tmp[81]; // tmp = T Hh
-    for (int r = 0; r < 9; ++r) {
-        const int i = r % 3, j = r / 3;
-        for (int q2 = 0; q2 < 9; ++q2) {
-            double acc = 0;
-            for (int p2 = 0; p2 < 9; ++p2) {
-                const double h = Hh[p2 * 9 + q2];
-                if (h != 0.0) acc += U[i][p2 % 3] * V[j][p2 / 3] * h;
-            }
-            tmp[r * 9 + q2] = acc;
-        }
-    }
-    for (int r = 0; r < 9; ++r)
-        for (int r2 = 0; r2 < 9; ++r2) {
-            const int k = r2 % 3, l = r2 / 3;
-            double acc = 0;
-            for (int q2 = 0; q2 < 9; ++q2) acc += tmp[r * 9 + q2] * U[k][q2 % 3] * V[l][q2 / 3];
-            H[r * 9 + r2] = acc;
-        }
-}
-
 // Per-tet gradient and 12x12 Hessian blocks straight from the analytic eigen-system (no 9x9 / 12x12 work matrices):
 // with dF = sum_v dx_v W_v^T, y_v = U^T dx_v and z_v = V^T W_v the rotated increment is d-hat = sum_v y_v z_v^T, so the
 // (va, vb) block of the projected Hessian is U S U^T with
@@ -297,59 +231,85 @@ __device__ void snh_hessian_spd_analytic(const double* F, double mu, double lamb
 //   S[i][j] += od_ij z_va[j] z_vb[i],  S[j][i] += od_ij z_va[i] z_vb[j]
 // Output (structure of arrays over the tet index, stride T): rows 0..11 gradient, 12 + 9 v diagonal block of local vertex
 // v, 48 + 9 s off-diagonal block of the local pair s in (0,1) (0,2) (0,3) (1,2) (1,3) (2,3).
-__device__ void tet_contrib(const double* F, const double W[4][3], double mu, double lambda, double sc, double* to, int T)
+// Scratch layout (one chunk of FEM_THREADS tets, tet tl of the chunk): 32-byte units u at tsc[(u * FEM_THREADS + tl) * 4],
+// so that the tets of a warp write whole sectors side by side and a row / an edge reads whole sectors of one tet:
+//   3 v + 0, 1, 2      local vertex v: (g0 g1 g2 -) (d00 d01 d02 d11) (d12 d22 - -)
+//   12 + 3 s + 0, 1, 2 off-diagonal block of the local pair s: (b0 b1 b2 b3) (b4 b5 b6 b7) (b8 - - -)
+constexpr int FEM_UNITS = 30;
+__device__ __forceinline__ void st_unit(double* tsc_tl, int u, double a, double b, double c, double d)
 {
-    double V[3][3], U[3][3], sg[3];
+    double2* p = reinterpret_cast<double2*>(tsc_tl + (size_t)u * FEM_THREADS * 4);
+    p[0] = make_double2(a, b);
+    p[1] = make_double2(c, d);
+}
+__device__ __forceinline__ void ld_unit(const double* tsc_tl, int u, double o[4])
+{
+    const double2* p = reinterpret_cast<const double2*>(tsc_tl + (size_t)u * FEM_THREADS * 4);
+    const double2 a = p[0], b = p[1];
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+__device__ __noinline__ void tet_contrib(const double* F, const double W[4][3], double mu, double lambda, double sc, double* to)
+{
+    double U[3][3], sg[3];
+    double Z[4][3]; // z_v = V^T W_v (indexed dynamically by the pair loop below: lives in local memory on purpose)
     {
-        const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
-        double w[3];
-        jacobi3(f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2], f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2],
-                f0[0] * f2[0] + f0[1] * f2[1] + f0[2] * f2[2], f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2],
-                f1[0] * f2[0] + f1[1] * f2[1] + f1[2] * f2[2], f2[0] * f2[0] + f2[1] * f2[1] + f2[2] * f2[2], w, V);
+        double V[3][3];
+        {
+            const double *f0 = F, *f1 = F + 3, *f2 = F + 6;
+            double w[3];
+            jacobi3(f0[0] * f0[0] + f0[1] * f0[1] + f0[2] * f0[2], f0[0] * f1[0] + f0[1] * f1[1] + f0[2] * f1[2],
+                    f0[0] * f2[0] + f0[1] * f2[1] + f0[2] * f2[2], f1[0] * f1[0] + f1[1] * f1[1] + f1[2] * f1[2],
+                    f1[0] * f2[0] + f1[1] * f2[1] + f1[2] * f2[2], f2[0] * f2[0] + f2[1] * f2[1] + f2[2] * f2[2], w, V);
 #define SWAPC(i, j)                                                                                                    \
     if (w[i] < w[j]) {                                                                                                \
         double t_ = w[i]; w[i] = w[j]; w[j] = t_;                                                                     \
         for (int r_ = 0; r_ < 3; ++r_) { t_ = V[r_][i]; V[r_][i] = V[r_][j]; V[r_][j] = t_; }                         \
     }
-        SWAPC(0, 1) SWAPC(0, 2) SWAPC(1, 2)
+            SWAPC(0, 1) SWAPC(0, 2) SWAPC(1, 2)
 #undef SWAPC
+        }
         const double detV = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
                             V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
         if (detV < 0.0)
             for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
-        double Fv[3][3]; // Fv[i] = F v_i
+        {
+            double Fv[3][3]; // Fv[i] = F v_i
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int r = 0; r < 3; ++r) Fv[i][r] = F[r] * V[0][i] + F[3 + r] * V[1][i] + F[6 + r] * V[2][i];
-        const double n0 = sqrt(Fv[0][0] * Fv[0][0] + Fv[0][1] * Fv[0][1] + Fv[0][2] * Fv[0][2]);
-        for (int r = 0; r < 3; ++r) U[r][0] = Fv[0][r] / n0;
-        const double d01 = U[0][0] * Fv[1][0] + U[1][0] * Fv[1][1] + U[2][0] * Fv[1][2];
-        const double t1[3] = {Fv[1][0] - d01 * U[0][0], Fv[1][1] - d01 * U[1][0], Fv[1][2] - d01 * U[2][0]};
-        const double n1 = sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
-        for (int r = 0; r < 3; ++r) U[r][1] = t1[r] / n1;
-        U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
-        U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
-        U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+                for (int r = 0; r < 3; ++r) Fv[i][r] = F[r] * V[0][i] + F[3 + r] * V[1][i] + F[6 + r] * V[2][i];
+            const double n0 = fast_rsqrt(Fv[0][0] * Fv[0][0] + Fv[0][1] * Fv[0][1] + Fv[0][2] * Fv[0][2]);
+            for (int r = 0; r < 3; ++r) U[r][0] = Fv[0][r] * n0;
+            const double d01 = U[0][0] * Fv[1][0] + U[1][0] * Fv[1][1] + U[2][0] * Fv[1][2];
+            const double t1[3] = {Fv[1][0] - d01 * U[0][0], Fv[1][1] - d01 * U[1][0], Fv[1][2] - d01 * U[2][0]};
+            const double n1 = fast_rsqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+            for (int r = 0; r < 3; ++r) U[r][1] = t1[r] * n1;
+            U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+            U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+            U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) sg[i] = U[0][i] * Fv[i][0] + U[1][i] * Fv[i][1] + U[2][i] * Fv[i][2];
+            for (int i = 0; i < 3; ++i) sg[i] = U[0][i] * Fv[i][0] + U[1][i] * Fv[i][1] + U[2][i] * Fv[i][2];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) Z[v][b] = V[0][b] * W[v][0] + V[1][b] * W[v][1] + V[2][b] * W[v][2];
     }
     const double J = sg[0] * sg[1] * sg[2];
     const double c = lambda * (J - 1.0) - mu;
-    // gradient: dPsi/dF = mu F + c cof(F) = U diag(mu s_i + c s_j s_k) V^T, g_v = dPsi/dF W_v
+    // gradient: dPsi/dF = mu F + c cof(F) = U diag(mu s_i + c s_j s_k) V^T, g_v = dPsi/dF W_v = U (dg o z_v)
     {
         const double dg[3] = {sc * (mu * sg[0] + c * sg[1] * sg[2]), sc * (mu * sg[1] + c * sg[0] * sg[2]), sc * (mu * sg[2] + c * sg[0] * sg[1])};
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-            double z[3];
-#pragma unroll
-            for (int b = 0; b < 3; ++b) z[b] = dg[b] * (V[0][b] * W[v][0] + V[1][b] * W[v][1] + V[2][b] * W[v][2]);
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) to[(size_t)(3 * v + cc) * T] = U[cc][0] * z[0] + U[cc][1] * z[1] + U[cc][2] * z[2];
+            const double z0 = dg[0] * Z[v][0], z1 = dg[1] * Z[v][1], z2 = dg[2] * Z[v][2];
+            st_unit(to, 3 * v, U[0][0] * z0 + U[0][1] * z1 + U[0][2] * z2, U[1][0] * z0 + U[1][1] * z1 + U[1][2] * z2,
+                    U[2][0] * z0 + U[2][1] * z1 + U[2][2] * z2, 0.0);
         }
     }
-    // clamped scaling block and twist / flip pairs
-    double Ap[3][3], dd[3], od[3]; // dd / od indexed by the third index k of the pair (i, j)
+    // clamped scaling block (symmetric: a00 a01 a02 a11 a12 a22) and twist / flip pairs
+    double Ap[6], dd[3], od[3]; // dd / od indexed by the third index k of the pair (i, j)
     {
         const double sw[3] = {sg[1] * sg[2], sg[0] * sg[2], sg[0] * sg[1]};
         double aw[3], Q[3][3];
@@ -357,10 +317,12 @@ __device__ void tet_contrib(const double* F, const double W[4][3], double mu, do
                 mu + lambda * sw[1] * sw[1], c * sg[0] + lambda * sw[1] * sw[2], mu + lambda * sw[2] * sw[2], aw, Q);
 #pragma unroll
         for (int k = 0; k < 3; ++k) aw[k] = aw[k] < 0.0 ? 0.0 : aw[k] * sc;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) Ap[i][j] = Q[i][0] * aw[0] * Q[j][0] + Q[i][1] * aw[1] * Q[j][1] + Q[i][2] * aw[2] * Q[j][2];
+        Ap[0] = Q[0][0] * aw[0] * Q[0][0] + Q[0][1] * aw[1] * Q[0][1] + Q[0][2] * aw[2] * Q[0][2];
+        Ap[1] = Q[0][0] * aw[0] * Q[1][0] + Q[0][1] * aw[1] * Q[1][1] + Q[0][2] * aw[2] * Q[1][2];
+        Ap[2] = Q[0][0] * aw[0] * Q[2][0] + Q[0][1] * aw[1] * Q[2][1] + Q[0][2] * aw[2] * Q[2][2];
+        Ap[3] = Q[1][0] * aw[0] * Q[1][0] + Q[1][1] * aw[1] * Q[1][1] + Q[1][2] * aw[2] * Q[1][2];
+        Ap[4] = Q[1][0] * aw[0] * Q[2][0] + Q[1][1] * aw[1] * Q[2][1] + Q[1][2] * aw[2] * Q[2][2];
+        Ap[5] = Q[2][0] * aw[0] * Q[2][0] + Q[2][1] * aw[1] * Q[2][1] + Q[2][2] * aw[2] * Q[2][2];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const double lt = mu + c * sg[k], lf = mu - c * sg[k];
@@ -369,41 +331,40 @@ __device__ void tet_contrib(const double* F, const double W[4][3], double mu, do
             od[k] = 0.5 * (lfp - ltp) * sc;
         }
     }
-    double Z[4][3]; // z_v = V^T W_v
+    // the ten blocks, one at a time (a rolled loop keeps the live set small: U, Ap, dd, od + one block)
+#pragma unroll 1
+    for (int pr = 0; pr < 10; ++pr) {
+        // pr 0..3: diagonal blocks (v, v); 4..9: pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+        const int va = pr < 4 ? pr : (pr < 7 ? 0 : (pr < 9 ? 1 : 2));
+        const int vb = pr < 4 ? pr : (pr < 7 ? pr - 3 : (pr < 9 ? pr - 5 : 3));
+        const double a0 = Z[va][0], a1 = Z[va][1], a2 = Z[va][2];
+        const double b0 = Z[vb][0], b1 = Z[vb][1], b2 = Z[vb][2];
+        // S (pairs (0,1) k=2, (0,2) k=1, (1,2) k=0)
+        const double S00 = Ap[0] * a0 * b0 + dd[2] * a1 * b1 + dd[1] * a2 * b2;
+        const double S11 = Ap[3] * a1 * b1 + dd[2] * a0 * b0 + dd[0] * a2 * b2;
+        const double S22 = Ap[5] * a2 * b2 + dd[1] * a0 * b0 + dd[0] * a1 * b1;
+        const double S01 = Ap[1] * a0 * b1 + od[2] * a1 * b0, S10 = Ap[1] * a1 * b0 + od[2] * a0 * b1;
+        const double S02 = Ap[2] * a0 * b2 + od[1] * a2 * b0, S20 = Ap[2] * a2 * b0 + od[1] * a0 * b2;
+        const double S12 = Ap[4] * a1 * b2 + od[0] * a2 * b1, S21 = Ap[4] * a2 * b1 + od[0] * a1 * b2;
+        double T[3][3]; // U S
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) Z[v][b] = V[0][b] * W[v][0] + V[1][b] * W[v][1] + V[2][b] * W[v][2];
-#pragma unroll
-    for (int vb = 0; vb < 4; ++vb)
-#pragma unroll
-        for (int va = 0; va <= vb; ++va) {
-            const double* za = Z[va];
-            const double* zb = Z[vb];
-            double S[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) S[i][j] = Ap[i][j] * za[i] * zb[j];
-            // pairs (0,1) k=2, (0,2) k=1, (1,2) k=0
-            S[0][0] += dd[2] * za[1] * zb[1] + dd[1] * za[2] * zb[2];
-            S[1][1] += dd[2] * za[0] * zb[0] + dd[0] * za[2] * zb[2];
-            S[2][2] += dd[1] * za[0] * zb[0] + dd[0] * za[1] * zb[1];
-            S[0][1] += od[2] * za[1] * zb[0]; S[1][0] += od[2] * za[0] * zb[1];
-            S[0][2] += od[1] * za[2] * zb[0]; S[2][0] += od[1] * za[0] * zb[2];
-            S[1][2] += od[0] * za[2] * zb[1]; S[2][1] += od[0] * za[1] * zb[2];
-            double US[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) US[i][j] = U[i][0] * S[0][j] + U[i][1] * S[1][j] + U[i][2] * S[2][j];
-            const int base = va == vb ? 12 + 9 * va : 48 + 9 * (va == 0 ? vb - 1 : (va == 1 ? vb + 1 : 5));
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    to[(size_t)(base + 3 * i + j) * T] = US[i][0] * U[j][0] + US[i][1] * U[j][1] + US[i][2] * U[j][2];
+        for (int i = 0; i < 3; ++i) {
+            T[i][0] = U[i][0] * S00 + U[i][1] * S10 + U[i][2] * S20;
+            T[i][1] = U[i][0] * S01 + U[i][1] * S11 + U[i][2] * S21;
+            T[i][2] = U[i][0] * S02 + U[i][1] * S12 + U[i][2] * S22;
         }
+#define BIJ(i, j) (T[i][0] * U[j][0] + T[i][1] * U[j][1] + T[i][2] * U[j][2])
+        if (pr < 4) {
+            st_unit(to, 3 * pr + 1, BIJ(0, 0), BIJ(0, 1), BIJ(0, 2), BIJ(1, 1));
+            st_unit(to, 3 * pr + 2, BIJ(1, 2), BIJ(2, 2), 0.0, 0.0);
+        } else {
+            const int u = 12 + 3 * (pr - 4);
+            st_unit(to, u, BIJ(0, 0), BIJ(0, 1), BIJ(0, 2), BIJ(1, 0));
+            st_unit(to, u + 1, BIJ(1, 1), BIJ(1, 2), BIJ(2, 0), BIJ(2, 1));
+            st_unit(to, u + 2, BIJ(2, 2), 0.0, 0.0, 0.0);
+        }
+#undef BIJ
+    }
 }
 
 __device__ __forceinline__ void barrier_fn(double D, double d_hat, double kappa, double* B, double* dB, double* ddB)
@@ -522,9 +483,17 @@ __device__ __forceinline__ double block_reduce(double v, Red* red, int& phase)
     phase ^= 1;
     if ((threadIdx.x & 31) == 0) b[threadIdx.x >> 5] = v;
     __syncthreads();
-    double s = b[0];
+    // fixed pairwise tree over the NW partials (independent loads, depth log2 NW): identical in every thread
+    constexpr int NW = FEM_THREADS / 32;
+    double t[NW];
 #pragma unroll
-    for (int w = 1; w < FEM_THREADS / 32; ++w) s = OP == 0 ? s + b[w] : (OP == 1 ? fmin(s, b[w]) : fmax(s, b[w]));
+    for (int w = 0; w < NW; ++w) t[w] = b[w];
+#pragma unroll
+    for (int stride = 1; stride < NW; stride *= 2)
+#pragma unroll
+        for (int w = 0; w + stride < NW; w += 2 * stride)
+            t[w] = OP == 0 ? t[w] + t[w + stride] : (OP == 1 ? fmin(t[w], t[w + stride]) : fmax(t[w], t[w + stride]));
+    const double s = t[0];
     return s;
 }
 
@@ -607,41 +576,113 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
     return anybad > 0.0 ? INFINITY : E;
 }
 
-// Gradient g3 (row-local), diagonal block d6 (row-local, symmetric) and the off-diagonal blocks of the Hessian (s.val / valg)
+// Gradient g3 (row-local), diagonal block d6 (row-local, symmetric) and the off-diagonal blocks of the Hessian (s.val / valg).
+// The tets are processed in chunks of one tet per thread so that the per-tet scratch (102 doubles per tet) of all CTAs
+// stays L2-resident; rows and edges accumulate their incident tets chunk by chunk, in ascending tet order (no atomics).
 __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt_g, const double* __restrict__ xprev_g,
-                          const double* __restrict__ aim_g, const FemIndenter& ind, double ratio, double* __restrict__ tsc /*[102][T]*/,
-                          double* valg, double g3[3], double d6[6])
+                          const double* __restrict__ aim_g, const FemIndenter& ind, double ratio, double* __restrict__ tsc /*[102][TC]*/,
+                          double* valg, double g3[3], double d6[6], long long* cyc)
 {
+    long long tg0 = cyc ? clock64() : 0;
     const double dt2 = a.dt * a.dt;
-    const int T = a.T;
-    // (1) per tet: gradient (12), the 4 diagonal and the 6 off-diagonal 3x3 blocks of W^T H9 W
-    for (int t = threadIdx.x; t < T; t += FEM_THREADS) {
-        const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
-        const int e[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
-        double W[4][3], F[9];
-        tet_W(a.Dm_inv, t, T, W);
-        tet_F(s.x, e, W, F);
-        tet_contrib(F, W, a.mu, a.lambda, dt2 * a.vol[t], tsc + t, T);
-    }
-    __syncthreads();
-    // (2) per vertex (row-local): kinetic + elastic (incident tets in CSR order: no atomics) + attachment + barrier
+    constexpr int TC = FEM_THREADS;
     const int i = threadIdx.x;
+    const bool on = i < a.V;
+    double m = 0.0, xi[3] = {0, 0, 0};
     g3[0] = g3[1] = g3[2] = 0.0;
     for (int j = 0; j < 6; ++j) d6[j] = 0.0;
-    if (i < a.V) {
-        const double m = a.mass[i];
-        const double xi[3] = {s.x[3 * i], s.x[3 * i + 1], s.x[3 * i + 2]};
+    if (on) {
+        m = a.mass[i];
+        for (int c = 0; c < 3; ++c) xi[c] = s.x[3 * i + c];
         for (int c = 0; c < 3; ++c) g3[c] = m * (xi[c] - xt_g[3 * i + c]);
         d6[0] = m; d6[3] = m; d6[5] = m;
-        for (int q = a.adj_off[i]; q < a.adj_off[i + 1]; ++q) {
-            const int tv = a.adj[q];
-            const double* to = tsc + (tv >> 2);
-            const int v = tv & 3;
-            for (int c = 0; c < 3; ++c) g3[c] += to[(size_t)(3 * v + c) * T];
-            const double* tb = to + (size_t)(12 + 9 * v) * T;
-            d6[0] += tb[0]; d6[1] += tb[(size_t)1 * T]; d6[2] += tb[(size_t)2 * T];
-            d6[3] += tb[(size_t)4 * T]; d6[4] += tb[(size_t)5 * T]; d6[5] += tb[(size_t)8 * T];
+    }
+    for (int c0 = 0; c0 < a.T; c0 += TC) {
+        // (1) per tet: gradient (12), the 4 diagonal and the 6 off-diagonal 3x3 blocks
+        const int t = c0 + threadIdx.x;
+        if (t < a.T) {
+            const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
+            const int e[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+            double W[4][3], F[9];
+            tet_W(a.Dm_inv, t, a.T, W);
+            tet_F(s.x, e, W, F);
+            tet_contrib(F, W, a.mu, a.lambda, dt2 * a.vol[t], tsc + 4 * threadIdx.x);
         }
+        __syncthreads();
+        if (cyc) { cyc[0] += clock64() - tg0; tg0 = clock64(); }
+        // (2) per vertex (row-local): elastic gradient and diagonal block of the incident tets of this chunk; the entry
+        // lists are fetched four at a time so that the dependent index -> scratch loads overlap
+        const int ck = c0 / TC;
+        if (on) {
+            const int q1 = a.row_start[(size_t)(ck + 1) * FEM_THREADS + i];
+            for (int qb = a.row_start[(size_t)ck * FEM_THREADS + i]; qb < q1; qb += 4) {
+                int tvs[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) tvs[u] = qb + u < q1 ? a.adj[qb + u] : -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int tv = tvs[u];
+                    if (tv < 0) break;
+                    const double* to = tsc + 4 * ((tv >> 2) - c0);
+                    const int v = tv & 3;
+                    double u0[4], u1[4], u2[4];
+                    ld_unit(to, 3 * v, u0);
+                    ld_unit(to, 3 * v + 1, u1);
+                    ld_unit(to, 3 * v + 2, u2);
+                    g3[0] += u0[0]; g3[1] += u0[1]; g3[2] += u0[2];
+                    d6[0] += u1[0]; d6[1] += u1[1]; d6[2] += u1[2]; d6[3] += u1[3]; d6[4] += u2[0]; d6[5] += u2[1];
+                }
+            }
+        }
+        if (cyc) { cyc[1] += clock64() - tg0; tg0 = clock64(); }
+        // (3) per edge (i < j): block A_ij += the incident tets of this chunk
+        for (int e = threadIdx.x; e < a.nE; e += FEM_THREADS) {
+            double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            const int q0 = a.edge_start[(size_t)ck * a.nE + e], q1 = a.edge_start[(size_t)(ck + 1) * a.nE + e];
+            if (q0 == q1 && c0 != 0) continue;
+            for (int qb = q0; qb < q1; qb += 4) {
+                int ens[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ens[u] = qb + u < q1 ? a.edge_adj[qb + u] : -1; // tet << 4 | pair slot << 1 | transpose
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int en = ens[u];
+                    if (en < 0) break;
+                    const double* to = tsc + 4 * ((en >> 4) - c0);
+                    const int ps = (en >> 1) & 7;
+                    double b[9], u0[4], u1[4], u2[4];
+                    ld_unit(to, 12 + 3 * ps, u0);
+                    ld_unit(to, 13 + 3 * ps, u1);
+                    ld_unit(to, 14 + 3 * ps, u2);
+                    b[0] = u0[0]; b[1] = u0[1]; b[2] = u0[2]; b[3] = u0[3]; b[4] = u1[0]; b[5] = u1[1]; b[6] = u1[2]; b[7] = u1[3];
+                    b[8] = u2[0];
+                    if (en & 1) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int bb = 0; bb < 3; ++bb) blk[3 * c + bb] += b[3 * bb + c];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) blk[k] += b[k];
+                    }
+                }
+            }
+            if (e < a.n_s) {
+                double* dst = s.val + e;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dst[(size_t)k * a.n_s] = (c0 == 0 ? 0.0 : dst[(size_t)k * a.n_s]) + blk[k];
+            } else {
+                double* dst = valg + (e - a.n_s);
+                const int nEg = a.nE - a.n_s;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dst[(size_t)k * nEg] = (c0 == 0 ? 0.0 : dst[(size_t)k * nEg]) + blk[k];
+            }
+        }
+        __syncthreads(); // the next chunk overwrites the scratch
+        if (cyc) { cyc[2] += clock64() - tg0; tg0 = clock64(); }
+    }
+    // (4) attachment + barrier (row-local)
+    if (on) {
         const int ka = a.attach_of[i];
         if (ka >= 0) {
             const double sm = a.attach_strength * m;
@@ -667,36 +708,13 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
             }
         }
     }
-    // (3) per edge (i < j): block A_ij = sum over the incident tets, in CSR order
-    for (int e = threadIdx.x; e < a.nE; e += FEM_THREADS) {
-        double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int q = a.edge_off[e]; q < a.edge_off[e + 1]; ++q) {
-            const int en = a.edge_adj[q]; // tet << 4 | pair slot << 1 | transpose
-            const double* to = tsc + (size_t)(48 + 9 * ((en >> 1) & 7)) * T + (en >> 4);
-            if (en & 1) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) blk[3 * c + b] += to[(size_t)(3 * b + c) * T];
-            } else {
-#pragma unroll
-                for (int m = 0; m < 9; ++m) blk[m] += to[(size_t)m * T];
-            }
-        }
-        if (e < a.n_s) {
-#pragma unroll
-            for (int m = 0; m < 9; ++m) s.val[(size_t)m * a.n_s + e] = blk[m];
-        } else {
-#pragma unroll
-            for (int m = 0; m < 9; ++m) valg[(size_t)m * (a.nE - a.n_s) + (e - a.n_s)] = blk[m];
-        }
-    }
-    __syncthreads();
+    if (cyc) cyc[1] += clock64() - tg0;
 }
 
 // y = A p for the row of this thread: diagonal block + the off-diagonal blocks in ELL order (symmetric storage: the block of
 // edge (i, j), i < j, serves row i as is and row j transposed; both reads are coalesced when the edges are numbered by
-// (j - i, i), which tx_fem_create does)
+// (j - i, i), which tx_fem_create does). The ELL entries of the row are fetched up front (one L2 round trip per product).
+constexpr int FEM_SLOT_GROUP = 16;
 __device__ __forceinline__ void spmv_row(const FemArgs& a, const FemShared& s, const double* valg, const double d6[6],
                                          double y[3])
 {
@@ -705,28 +723,34 @@ __device__ __forceinline__ void spmv_row(const FemArgs& a, const FemShared& s, c
     if (i >= a.V) return;
     sym3_mul(d6, s.p[3 * i], s.p[3 * i + 1], s.p[3 * i + 2], y[0], y[1], y[2]);
     const int nEg = a.nE - a.n_s;
-#pragma unroll 2
-    for (int sl = 0; sl < a.nslots; ++sl) {
-        const int pk = __ldg(a.ell + (size_t)sl * FEM_THREADS + i);
-        if (pk < 0) continue;
-        const int j = pk & 0xfff, e = pk >> 13;
-        const double p0 = s.p[3 * j], p1 = s.p[3 * j + 1], p2 = s.p[3 * j + 2];
-        double m[9];
-        if (e < a.n_s) {
+    for (int sl0 = 0; sl0 < a.nslots; sl0 += FEM_SLOT_GROUP) {
+        int pks[FEM_SLOT_GROUP];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[k] = s.val[(size_t)k * a.n_s + e];
-        } else {
+        for (int u = 0; u < FEM_SLOT_GROUP; ++u)
+            pks[u] = sl0 + u < a.nslots ? __ldg(a.ell + (size_t)(sl0 + u) * FEM_THREADS + i) : -1;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[k] = valg[(size_t)k * nEg + (e - a.n_s)];
-        }
-        if (pk & 0x1000) { // this row is the j of edge (i', j): A^T
-            y[0] += m[0] * p0 + m[3] * p1 + m[6] * p2;
-            y[1] += m[1] * p0 + m[4] * p1 + m[7] * p2;
-            y[2] += m[2] * p0 + m[5] * p1 + m[8] * p2;
-        } else {
-            y[0] += m[0] * p0 + m[1] * p1 + m[2] * p2;
-            y[1] += m[3] * p0 + m[4] * p1 + m[5] * p2;
-            y[2] += m[6] * p0 + m[7] * p1 + m[8] * p2;
+        for (int u = 0; u < FEM_SLOT_GROUP; ++u) {
+            const int pk = pks[u];
+            if (pk < 0) continue;
+            const int j = pk & 0xfff, e = pk >> 13;
+            const double p0 = s.p[3 * j], p1 = s.p[3 * j + 1], p2 = s.p[3 * j + 2];
+            double m[9];
+            if (e < a.n_s) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) m[k] = s.val[(size_t)k * a.n_s + e];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) m[k] = valg[(size_t)k * nEg + (e - a.n_s)];
+            }
+            if (pk & 0x1000) { // this row is the j of edge (i', j): A^T
+                y[0] += m[0] * p0 + m[3] * p1 + m[6] * p2;
+                y[1] += m[1] * p0 + m[4] * p1 + m[7] * p2;
+                y[2] += m[2] * p0 + m[5] * p1 + m[8] * p2;
+            } else {
+                y[0] += m[0] * p0 + m[1] * p1 + m[2] * p2;
+                y[1] += m[3] * p0 + m[4] * p1 + m[5] * p2;
+                y[2] += m[6] * p0 + m[7] * p1 + m[8] * p2;
+            }
         }
     }
 }
@@ -734,8 +758,9 @@ __device__ __forceinline__ void spmv_row(const FemArgs& a, const FemShared& s, c
 // PCG with the 3x3 block-Jacobi preconditioner (linear_pcg.cu:45-140, fem_diag_preconditioner.cu:112-164), x0 = 0,
 // b = -g3; solution in dx (row-local). Every vector except p is row-local (registers).
 __device__ int pcg(const FemArgs& a, const FemShared& s, const double* valg, const double g3[3], const double d6[6],
-                   double dx[3], int& ph)
+                   double dx[3], int& ph, long long* cyc)
 {
+    long long tp0 = 0;
     const int i = threadIdx.x;
     const bool on = i < a.V;
     double inv[6] = {0, 0, 0, 0, 0, 0};
@@ -757,7 +782,9 @@ __device__ int pcg(const FemArgs& a, const FemShared& s, const double* valg, con
     int k;
     const int max_iter = a.pcg_max_iter_ratio * 3 * a.V;
     for (k = 1; k < max_iter; ++k) {
+        if (cyc) tp0 = clock64();
         spmv_row(a, s, valg, d6, Ap);
+        if (cyc) { cyc[0] += clock64() - tp0; tp0 = clock64(); }
         const double pAp = block_reduce<0>(on ? pl[0] * Ap[0] + pl[1] * Ap[1] + pl[2] * Ap[2] : 0.0, s.red, ph);
         const double alpha = rz / pAp;
         for (int c = 0; c < 3; ++c) { dx[c] += alpha * pl[c]; r[c] -= alpha * Ap[c]; }
@@ -771,6 +798,7 @@ __device__ int pcg(const FemArgs& a, const FemShared& s, const double* valg, con
         if (on) { s.p[3 * i] = pl[0]; s.p[3 * i + 1] = pl[1]; s.p[3 * i + 2] = pl[2]; }
         __syncthreads();
         rz = rzn;
+        if (cyc) cyc[1] += clock64() - tp0;
     }
     return k;
 }
@@ -790,12 +818,15 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
     FemShared s;
     s.x = base; s.p = s.x + n; s.val = s.p + n;
     s.red = reinterpret_cast<Red*>(s.val + (size_t)9 * a.n_s);
-    double* tsc = a.tet_scratch + (size_t)blockIdx.x * a.T * 102;
+    double* tsc = a.tet_scratch + (size_t)blockIdx.x * FEM_THREADS * 4 * FEM_UNITS;
     double* valg = a.val_scratch + (size_t)blockIdx.x * 9 * (a.nE - a.n_s);
     double* xt_g = a.xt_scratch + (size_t)blockIdx.x * n;
     const int i = threadIdx.x;
     const bool on = i < a.V;
     int ph = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0}, tc0 = 0;
+#define FEM_TIC() do { if (a.dbg_cycles) tc0 = clock64(); } while (0)
+#define FEM_TOC(k) do { if (a.dbg_cycles) cyc[k] += clock64() - tc0; } while (0)
 
     for (int env = blockIdx.x; env < a.N; env += gridDim.x) {
         double* xg = a.x + (size_t)env * n;
@@ -835,8 +866,13 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             const FemIndenter ind = lerp_ind(ind_prev, ind_next, ind_s);
 
             double g3[3], d6[6], dx[3];
-            grad_hess(a, s, xt_g, xpg, aim_g, ind, ratio, tsc, valg, g3, d6);
-            pcg_total += pcg(a, s, valg, g3, d6, dx, ph);
+            FEM_TIC();
+            grad_hess(a, s, xt_g, xpg, aim_g, ind, ratio, tsc, valg, g3, d6, (a.dbg_cycles && !a.dbg_mode) ? cyc + 3 : nullptr);
+            FEM_TOC(0);
+            FEM_TIC();
+            pcg_total += pcg(a, s, valg, g3, d6, dx, ph, (a.dbg_cycles && a.dbg_mode) ? cyc + 3 : nullptr);
+            FEM_TOC(1);
+            FEM_TIC();
 
             double res = on ? fmax(fmax(fabs(dx[0]), fabs(dx[1])), fabs(dx[2])) : 0.0;
             res = block_reduce<2>(res, s.red, ph);
@@ -878,6 +914,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             }
             energy = E;
             __syncthreads();
+            FEM_TOC(2);
         }
         // update velocity (fem_bdf1_time_integrator.cu:58-77), write back
         __syncthreads();
@@ -887,6 +924,8 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             xpg[k] = xn;
             xg[k] = xn;
         }
+        if (threadIdx.x == 0 && a.dbg_cycles)
+            for (int k = 0; k < 6; ++k) a.dbg_cycles[(size_t)blockIdx.x * 6 + k] = cyc[k];
         if (threadIdx.x == 0 && a.stats) {
             FemStats st;
             st.converged = conv; st.newton_iters = it; st.pcg_iters = pcg_total; st.ls_halvings = ls_total;

@@ -75,17 +75,19 @@ struct FemArgs {
     const double* aim;     // [N][A][3]
     const FemIndenter* ind_prev; const FemIndenter* ind_next; // [N]
     FemStats* stats;       // [N] or nullptr
-    double* tet_scratch;   // [grid][102][T] per-tet contributions: 12 gradient, 4 diagonal and 6 off-diagonal 3x3 blocks
+    double* tet_scratch;   // [grid][102][576] per-tet contributions of one chunk of tets (one tet per thread): 12 gradient, 4 diagonal and 6 off-diagonal 3x3 blocks
     double* val_scratch;   // [grid][9][nE - n_s] off-diagonal blocks that do not fit in shared memory (L2-resident)
     double* xt_scratch;    // [grid][3V] predicted positions
-    const int* adj_off;    // [V+1] CSR of the vertex -> (tet, local vertex) incidence, entries = 4 * tet + local
+    const int* row_start;  // [nchunks+1][576] per chunk of 576 tets: first entry of `adj` (ascending tets) of every row
     const int* adj;        // [4T]
     int nE, n_s, nslots;   // edges (i < j) of the vertex graph, edges kept in shared memory, ELL width
-    const int* edge_off;   // [nE+1] CSR of the edge -> (tet, pair slot, transpose) incidence
+    const int* edge_start; // [nchunks+1][nE] per chunk: first entry of `edge_adj` (ascending tets) of every edge
     const int* edge_adj;   // entries = tet << 4 | pair slot << 1 | transpose
     const int* ell;        // [nslots][FEM threads] row -> (neighbour j | transposed << 12 | edge << 13), -1 = empty
     const int* attach_of;  // [V] index into attach[] or -1
     const int* surf_of;    // [V] index into surf[] or -1
+    int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
+    long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate;
     int newton_max_iter, pcg_max_iter_ratio, ls_max_iter, substep;
 };

@@ -21,4 +21,11 @@ for s in range(steps):
     d = eng.decode_stats(st)
     nn = np.mean([q["newton_iters"] for q in d]); pc = np.mean([q["pcg_iters"] for q in d]); cv = np.mean([q["converged"] for q in d])
     print(f"step {s}: {e0.elapsed_time(e1):8.2f} ms  newton {nn:.2f}  pcg {pc:.1f}  converged {cv:.2f}  min_dist {min(q['min_dist'] for q in d):.2e}")
+cyc = torch.zeros((148, 6), dtype=torch.int64, device="cuda")
+eng.lib.tx_fem_debug_set_cycles(eng.h, cyc.data_ptr())
+st = eng.step(x, v, xp, aim, inds[steps - 1], inds[steps]); torch.cuda.synchronize()
+eng.lib.tx_fem_debug_set_cycles(eng.h, None)
+c = cyc.double().mean(0).tolist()
+per = N / 148
+print("cycles per gel-step (mean over CTAs): " + "  ".join(f"{n} {v / per:9.0f}" for n, v in zip(["assembly", "pcg", "linesearch", "asm:tets", "asm:rows", "asm:edges"], c)))
 print(f"-> {N / (e0.elapsed_time(e1) / 1e3):.0f} gel-steps/s at the last step")
