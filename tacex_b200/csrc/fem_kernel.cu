@@ -22,6 +22,7 @@
 namespace tx {
 
 constexpr int FEM_THREADS = 576; // one thread per vertex row (V <= 576), 18 warps
+constexpr int FEM_VAL_STRIDE = 2836; // shared-memory blocks: val[k][e], k < 9, e < n_s <= FEM_VAL_STRIDE (compile-time stride: immediate offsets)
 
 // ---- small dense helpers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double det3cm(const double* F)
@@ -670,7 +671,7 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
             if (e < a.n_s) {
                 double* dst = s.val + e;
 #pragma unroll
-                for (int k = 0; k < 9; ++k) dst[(size_t)k * a.n_s] = (c0 == 0 ? 0.0 : dst[(size_t)k * a.n_s]) + blk[k];
+                for (int k = 0; k < 9; ++k) dst[k * FEM_VAL_STRIDE] = (c0 == 0 ? 0.0 : dst[k * FEM_VAL_STRIDE]) + blk[k];
             } else {
                 double* dst = valg + (e - a.n_s);
                 const int nEg = a.nE - a.n_s;
@@ -737,7 +738,7 @@ __device__ __forceinline__ void spmv_row(const FemArgs& a, const FemShared& s, c
             double m[9];
             if (e < a.n_s) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) m[k] = s.val[(size_t)k * a.n_s + e];
+                for (int k = 0; k < 9; ++k) m[k] = s.val[k * FEM_VAL_STRIDE + e];
             } else {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) m[k] = valg[(size_t)k * nEg + (e - a.n_s)];
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
     double* base = reinterpret_cast<double*>(smem_raw);
     FemShared s;
     s.x = base; s.p = s.x + n; s.val = s.p + n;
-    s.red = reinterpret_cast<Red*>(s.val + (size_t)9 * a.n_s);
+    s.red = reinterpret_cast<Red*>(s.val + (size_t)9 * FEM_VAL_STRIDE);
     double* tsc = a.tet_scratch + (size_t)blockIdx.x * FEM_THREADS * 4 * FEM_UNITS;
     double* valg = a.val_scratch + (size_t)blockIdx.x * 9 * (a.nE - a.n_s);
     double* xt_g = a.xt_scratch + (size_t)blockIdx.x * n;
@@ -939,13 +940,9 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
 int fem_threads() { return FEM_THREADS; }
 
 // n_s = number of off-diagonal blocks kept in shared memory
-size_t fem_smem_bytes(int V, int n_s) { return sizeof(double) * (2 * 3 * (size_t)V + 9 * (size_t)n_s) + sizeof(Red) + 64; }
+size_t fem_smem_bytes(int V, int n_s) { (void)n_s; return sizeof(double) * (2 * 3 * (size_t)V + 9 * (size_t)FEM_VAL_STRIDE) + sizeof(Red) + 64; }
 
-int fem_max_smem_edges(int V)
-{
-    const long avail = 227L * 1024 - (long)fem_smem_bytes(V, 0);
-    return avail > 0 ? (int)(avail / 72) : 0;
-}
+int fem_max_smem_edges(int V) { (void)V; return FEM_VAL_STRIDE; }
 
 cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st)
 {

@@ -231,6 +231,35 @@ __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits,
         if (tk && tid == 0) tk[(slot)] = clock64();                                                                   \
     } while (0)
 
+// Flat part of the colour stage: the pixels outside the rectangle [ry0, ry1] x [xa, xb] (local rows / image columns) of
+// this CTA's half copy the precomputed flat RGB. The rectangle is known before the pyramid starts, so the copy is cut into
+// one slice per blur level and done by the warps that have no column in that level's vertical pass (they would idle).
+struct FlatCopy {
+    const float* src; // flat RGB of this half
+    float* dst;       // RGB output of this half
+    int ry0, ry1, xa, xb, total;
+    unsigned done;    // bit l: slice l has been copied
+};
+constexpr int FC_SLICES = 7;
+constexpr int FC_SLICE_QUADS = (HALF_H * (IMG_W / 4) + FC_SLICES - 1) / FC_SLICES;
+
+__device__ __forceinline__ void flat_copy_slice(const FlatCopy& fc, int slice, int first, int nthr)
+{
+    constexpr int QPR = IMG_W / 4;
+    const int q1 = min((slice + 1) * FC_SLICE_QUADS, HALF_H * QPR);
+#pragma unroll 2
+    for (int qd = slice * FC_SLICE_QUADS + first; qd < q1; qd += nthr) {
+        const int row = qd / QPR;
+        const int x0 = (qd - row * QPR) * 4;
+        if (fc.total > 0 && row >= fc.ry0 && row <= fc.ry1 && x0 >= fc.xa && x0 <= fc.xb) continue;
+        const size_t pix = (size_t)row * IMG_W + x0;
+        const float4* f4 = reinterpret_cast<const float4*>(fc.src + pix * 3);
+        float4* o4 = reinterpret_cast<float4*>(fc.dst + pix * 3);
+        const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
+        o4[0] = t0; o4[1] = t1; o4[2] = t2;
+    }
+}
+
 // Region = bounding box (image coordinates) outside of which the plane is exactly zero at the start of the level.
 struct Region {
     int r0, r1, c0, c1;
@@ -240,7 +269,7 @@ template <int L, int RAD, int R, bool FINAL>
 __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
                                            const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half,
                                            float m, float press, int tid, int warp, int lane, unsigned q, Region& rg,
-                                           cg::cluster_group& cluster, long long* tk, float depth_clip)
+                                           cg::cluster_group& cluster, long long* tk, float depth_clip, FlatCopy& fc)
 {
     const int base = (int)q * HALF_H;
     hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1));
@@ -254,6 +283,12 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
         const int ta = q == 0 ? ro0 : max(IMG_H - 1 - ro1, 0);
         const int tb = q == 0 ? min(ro1, HALF_H - 1) : min(IMG_H - 1 - ro0, HALF_H - 1);
         vpass<L, RAD, R>(plane, hb_local, tid, q, ca, cb - ca + 1, ta, tb);
+        // the warps without a column copy this level's slice of the flat RGB meanwhile
+        const int nv = tb < ta ? 0 : ((cb - ca + 1 + 31) & ~31);
+        if (nv < NTHREADS) {
+            if (tid >= nv) flat_copy_slice(fc, L, tid - nv, NTHREADS - nv);
+            fc.done |= 1u << L;
+        }
         rg.r0 = ro0; rg.r1 = ro1; rg.c0 = ca; rg.c1 = cb;
     }
     __syncthreads();
@@ -486,17 +521,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
 
     TX_TICK(3);
     const float depth_clip = DEPTH ? p.clip_max_m : 0.0f; // > 0: the input frame is a depth image in metres
+    const bool active = (p.gel != nullptr) || (press > 0.0f);
+    // rectangle of the pixels that can have a non-zero gradient: the contact box grown by the sum of the blur radii (the
+    // region after the last level) + 1 px for the central differences; the replicate-padded border rows / columns follow
+    // their inner neighbour. LOCAL rows / image columns, columns aligned to the 4-pixel quads; empty without contact.
+    FlatCopy fc;
+    fc.src = p.flat_rgb + (size_t)q * HALF_H * IMG_W * 3;
+    fc.dst = p.rgb + half_off * 3;
+    fc.ry0 = 0; fc.ry1 = -1; fc.xa = 0; fc.xb = -1; fc.done = 0u;
+    if (active && !(p.dbg & 4)) {
+        constexpr int GROW = 30 + 16 + 8 + 4 + 2 + 1 + 2;
+        const int base = (int)q * HALF_H;
+        const int fr0 = max(rg.r0 - GROW, 0), fr1 = min(rg.r1 + GROW, IMG_H - 1);
+        const int fc0 = max(rg.c0 - GROW, 0), fc1 = min(rg.c1 + GROW, IMG_W - 1);
+        const int a0 = fr0 - 1 <= 1 ? 0 : fr0 - 1;                     // row 0 samples row 1
+        const int a1 = fr1 + 1 >= IMG_H - 2 ? IMG_H - 1 : fr1 + 1;     // row 239 samples row 238
+        fc.ry0 = max(a0, base) - base;
+        fc.ry1 = min(a1, base + HALF_H - 1) - base;
+        fc.xa = fc0 - 1 <= 1 ? 0 : ((fc0 - 1) & ~3);                   // column 0 samples column 1
+        fc.xb = fc1 + 1 >= IMG_W - 2 ? IMG_W - 1 : ((fc1 + 1) | 3);    // column 319 samples column 318
+    }
+    {
+        const int nq_ = fc.xb >= fc.xa ? (fc.xb - fc.xa + 1) >> 2 : 0;
+        fc.total = fc.ry1 >= fc.ry0 ? nq_ * (fc.ry1 - fc.ry0 + 1) : 0;
+    }
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
-    const bool active = (p.gel != nullptr) || (press > 0.0f);
     if (active) {
-        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
-        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip);
+        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
     }
 
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
@@ -543,34 +601,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     //       of 32 scattered requests per load).
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
-    const float* flat_half = p.flat_rgb + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
     float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (15 x 2560 B = 38,400 B)
     constexpr int QPR = IMG_W / 4; // quads per row
-    int ry0 = 0, ry1 = -1, xa = 0, xb = -1; // rectangle in LOCAL rows / image columns (empty without contact)
-    if (active && !(p.dbg & 4)) {
-        const int base = (int)q * HALF_H;
-        const int a0 = rg.r0 - 1 <= 1 ? 0 : rg.r0 - 1;                     // row 0 samples row 1
-        const int a1 = rg.r1 + 1 >= IMG_H - 2 ? IMG_H - 1 : rg.r1 + 1;     // row 239 samples row 238
-        ry0 = max(a0, base) - base;
-        ry1 = min(a1, base + HALF_H - 1) - base;
-        xa = rg.c0 - 1 <= 1 ? 0 : ((rg.c0 - 1) & ~3);                      // column 0 samples column 1
-        xb = rg.c1 + 1 >= IMG_W - 2 ? IMG_W - 1 : ((rg.c1 + 1) | 3);       // column 319 samples column 318
-    }
+    const int ry0 = fc.ry0, xa = fc.xa, xb = fc.xb, total = fc.total;
     const int nq = xb >= xa ? (xb - xa + 1) >> 2 : 0;
-    const int total = ry1 >= ry0 ? nq * (ry1 - ry0 + 1) : 0;
-    // (1) flat copy of everything outside the rectangle
-#pragma unroll 2
-    for (int qd = tid; qd < HALF_H * QPR; qd += NTHREADS) {
-        const int row = qd / QPR;
-        const int x0 = (qd - row * QPR) * 4;
-        if (total > 0 && row >= ry0 && row <= ry1 && x0 >= xa && x0 <= xb) continue;
-        const size_t pix = (size_t)row * IMG_W + x0;
-        const float4* f4 = reinterpret_cast<const float4*>(flat_half + pix * 3);
-        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
-        const float4 t0 = __ldg(f4), t1 = __ldg(f4 + 1), t2 = __ldg(f4 + 2);
-        o4[0] = t0; o4[1] = t1; o4[2] = t2;
-    }
+    // (1) flat copy of everything outside the rectangle: the slices no idle warp has taken during the pyramid
+    for (int sl = 0; sl < FC_SLICES; ++sl)
+        if (!((fc.done >> sl) & 1u)) flat_copy_slice(fc, sl, tid, NTHREADS);
     // (2) the rectangle
 #pragma unroll 1
     for (int qb = warp * 32; qb < total; qb += NTHREADS) {
