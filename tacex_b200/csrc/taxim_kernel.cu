@@ -609,86 +609,94 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     // (1) flat copy of everything outside the rectangle: the slices no idle warp has taken during the pyramid
     for (int sl = 0; sl < FC_SLICES; ++sl)
         if (!((fc.done >> sl) & 1u)) flat_copy_slice(fc, sl, tid, NTHREADS);
-    // (2) the rectangle
-#pragma unroll 1
-    for (int qb = warp * 32; qb < total; qb += NTHREADS) {
-        const bool valid = qb + lane < total;
-        const int qd = valid ? qb + lane : total - 1;
-        const int rr = qd / nq;
-        const int row = ry0 + rr;
-        const int x0 = xa + (qd - rr * nq) * 4;
+    // (2) the rectangle: one pixel per lane, software-pipelined: the table records of the NEXT pixel set are requested
+    // (after its bins are known) before the current set is staged and evaluated, so the L2 round trip of the gather
+    // overlaps the arithmetic instead of serialising with it.
+    (void)nq; (void)QPR;
+    const int nw = xb >= xa ? xb - xa + 1 : 0;   // rectangle width in pixels
+    const int npx = total * 4;                   // pixels of the rectangle in this half
+    const int rec_of = lane / 5;                 // idx = e * 32 + lane: record (idx / 5), part (idx % 5), precomputed per e
+    int bin_next = 0, row_n = 0, x_n = 0;
+    float4 rec[5];
+    // lane-constant gather pattern
+    int g_rec[5], g_part[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+        const int idx = e * 32 + lane;
+        g_rec[e] = idx / 5;
+        g_part[e] = idx - g_rec[e] * 5;
+    }
+    (void)rec_of;
+    auto pixel_bin = [&](int pidx, int& row, int& x) -> int {
+        const int rr = pidx / nw;
+        row = ry0 + rr;
+        x = xa + (pidx - rr * nw);
         const int gy_ = (int)q * HALF_H + row; // image row
-        const size_t pix = (size_t)row * IMG_W + x0;
-        float4* o4 = reinterpret_cast<float4*>(rgb_half + pix * 3);
-        float gx[4], gy[4], s2[4];
-        {
-            // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
-            const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixels
-            const float* ctr = plane + yy * IMG_W;
-            const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1;
-            const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1;
-            const float4 cu = *reinterpret_cast<const float4*>(up + x0);
-            const float4 cd = *reinterpret_cast<const float4*>(dn + x0);
-            const float4 cc = *reinterpret_cast<const float4*>(ctr + x0);
-            const float c6[6] = {ctr[max(x0 - 1, 0)], cc.x, cc.y, cc.z, cc.w, ctr[min(x0 + 4, IMG_W - 1)]};
-            const float u4[4] = {cu.x, cu.y, cu.z, cu.w}, d4[4] = {cd.x, cd.y, cd.z, cd.w};
+        // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
+        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
+        const int xx = min(max(x, 1), IMG_W - 2);
+        const float* ctr = plane + yy * IMG_W + xx;
+        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1 + xx;
+        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1 + xx;
+        const float top = __fmul_rn(*up, p.inv_pixmm), bot = __fmul_rn(*dn, p.inv_pixmm);
+        const float lef = __fmul_rn(ctr[-1], p.inv_pixmm), rig = __fmul_rn(ctr[1], p.inv_pixmm);
+        const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
+        const float gy = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
+        const float s2 = __fmaf_rn(gx, gx, __fmul_rn(gy, gy));
+        // tt = sqrt(s2) is zero iff s2 is zero: a flat pixel (exact zero gradient) lands in bin (0, dir = 0)
+        const float tt = (p.dbg & 16) ? s2 : __fsqrt_rn(s2);
+        const float mag = (p.dbg & 16) ? tt : atanf_c(tt);
+        const float dir = (p.dbg & 16) ? gx : ((tt != 0.0f) ? atan2f_c(gx, gy) : 0.0f);
+        int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
+        int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
+        im = min(max(im, 0), p.nb - 1);
+        id = min(max(id, 0), p.nb - 1);
+        return (p.dbg & 32) ? 62 : im * p.nb + id; // record index into [nb][nb][20 floats]
+    };
+    auto request = [&](int bin) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float top = __fmul_rn(u4[i], p.inv_pixmm), bot = __fmul_rn(d4[i], p.inv_pixmm);
-                const float lef = __fmul_rn(c6[i], p.inv_pixmm), rig = __fmul_rn(c6[i + 2], p.inv_pixmm);
-                gx[i] = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
-                gy[i] = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
-            }
-            if (x0 == 0) { gx[0] = gx[1]; gy[0] = gy[1]; }         // column 0 samples column 1
-            if (x0 == IMG_W - 4) { gx[3] = gx[2]; gy[3] = gy[2]; } // column 319 samples column 318
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s2[i] = __fmaf_rn(gx[i], gx[i], __fmul_rn(gy[i], gy[i]));
+        for (int e = 0; e < 5; ++e) {
+            const int bsrc = __shfl_sync(0xffffffffu, bin, g_rec[e]);
+            rec[e] = __ldg(p.poly + (size_t)bsrc * 5 + g_part[e]);
         }
-        const float4* bg4 = reinterpret_cast<const float4*>(bg_half + pix * 3);
-        const float4 b0 = __ldg(bg4), b1 = __ldg(bg4 + 1), b2 = __ldg(bg4 + 2);
-        const float bgv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
-        int bin[4];
+    };
+    int pb = warp * 32;
+    if (pb < npx) {
+        bin_next = pixel_bin(min(pb + lane, npx - 1), row_n, x_n);
+        request(bin_next);
+    }
+#pragma unroll 1
+    for (; pb < npx; pb += NTHREADS) {
+        const bool valid = pb + lane < npx;
+        const int row = row_n, x = x_n;
+        // stage the current records (one 80-byte record per lane)
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // tt = sqrt(s2) is zero iff s2 is zero: a flat pixel (exact zero gradient) lands in bin (0, dir = 0)
-            const float tt = (p.dbg & 16) ? s2[i] : __fsqrt_rn(s2[i]);
-            const float mag = (p.dbg & 16) ? tt : atanf_c(tt);
-            const float dir = (p.dbg & 16) ? gx[i] : ((tt != 0.0f) ? atan2f_c(gx[i], gy[i]) : 0.0f);
-            int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
-            int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
-            im = min(max(im, 0), p.nb - 1);
-            id = min(max(id, 0), p.nb - 1);
-            bin[i] = im * p.nb + id; // record index into [nb][nb][20 floats]
-            if (p.dbg & 32) bin[i] = 62;
+        for (int e = 0; e < 5; ++e) reinterpret_cast<float4*>(stage)[e * 32 + lane] = rec[e];
+        // next set: bins, then its requests go out before this set is evaluated
+        const int pn = pb + NTHREADS;
+        if (pn < npx) {
+            bin_next = pixel_bin(min(pn + lane, npx - 1), row_n, x_n);
+            request(bin_next);
         }
-        float o[12];
+        __syncwarp();
+        float cf[20];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            const float4 t = reinterpret_cast<const float4*>(stage)[lane * 5 + e];
+            cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
+        }
+        const int gy_ = (int)q * HALF_H + row;
+        const size_t pix = (size_t)row * IMG_W + x;
+        const float* bgp = bg_half + pix * 3;
+        const float bgv[3] = {__ldg(bgp), __ldg(bgp + 1), __ldg(bgp + 2)};
         const float yf = __fmul_rn((float)gy_, p.fy);
-        const float f1 = __fmul_rn(yf, yf);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            // cooperative gather: float4 number idx = e * 32 + lane of the 32 x 5 float4 this warp needs
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < 5; ++e) {
-                const int idx = e * 32 + lane;
-                const int rec = idx / 5, part = idx - rec * 5;
-                const int bsrc = __shfl_sync(0xffffffffu, bin[i], rec);
-                reinterpret_cast<float4*>(stage)[idx] = __ldg(p.poly + (size_t)bsrc * 5 + part);
-            }
-            __syncwarp();
-            float cf[20];
-#pragma unroll
-            for (int e = 0; e < 5; ++e) {
-                const float4 t = reinterpret_cast<const float4*>(stage)[lane * 5 + e];
-                cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
-            }
-            const float xf = __fmul_rn((float)(x0 + i), p.fx);
-            poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), f1, __fmul_rn(xf, yf), bgv + 3 * i, o + 3 * i);
-        }
+        const float xf = __fmul_rn((float)x, p.fx);
+        float o[3];
+        poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), __fmul_rn(yf, yf), __fmul_rn(xf, yf), bgv, o);
         if (valid && (!(p.dbg & 1) || o[0] < -1.0f)) {
-            o4[0] = make_float4(o[0], o[1], o[2], o[3]);
-            o4[1] = make_float4(o[4], o[5], o[6], o[7]);
-            o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+            float* op = rgb_half + pix * 3;
+            op[0] = o[0]; op[1] = o[1]; op[2] = o[2];
         }
     }
     __syncthreads();
