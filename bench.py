@@ -125,7 +125,7 @@ def fem_cpu_port(n_gels: int = 64) -> tuple[float, int, str]:
     return 2 * n_gels / dt, canon.num_threads(), f"{n_gels} gels x 2 steps of the config-3 box press (float64 CPU restatement)"
 
 
-def fem_gpu(E: int, steps: int, dev) -> dict:
+def fem_gpu(E: int, steps: int, dev, tactile=None) -> dict:
     """Config 3 extra: batched gel FEM substep + FEM marker read-out for E gels (box indenter pressed 0 -> 1 mm in 30 steps)."""
     import numpy as np
     import torch
@@ -143,7 +143,7 @@ def fem_gpu(E: int, steps: int, dev) -> dict:
     x, v, xp = eng.new_state(E)
     aim = eng.rest_aim(E)
     ctr = lambda s: np.concatenate([offs, np.full((E, 1), z0 - 1e-3 * s / 30)], 1)  # noqa: E731
-    inds = [fem.indenter_array(1, ctr(s), half, device=dev) for s in range(steps + 3)]
+    inds = [fem.indenter_array(1, ctr(s), half, device=dev) for s in range(2 * steps + 3)]
     mk = torch.empty((E, 2, 128, 2), device=dev)
     for s in range(2):
         eng.step(x, v, xp, aim, inds[s], inds[s + 1], want_stats=False)
@@ -158,11 +158,31 @@ def fem_gpu(E: int, steps: int, dev) -> dict:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     d = eng.decode_stats(st)
-    return {"workload": f"{E} gels (572 verts / 2160 tets, float64): implicit-Euler IPC substep + FEM marker read-out",
+    full = None
+    if tactile is not None:
+        # config 3 as one step: gel FEM substep + FEM marker read-out + Taxim RGB from the recorded depth maps of the same envs
+        t_eng, hm, rgb, depth = tactile
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        f0.record()
+        for s in range(2 + steps, 2 + 2 * steps):
+            k = min(s, len(inds) - 2)
+            eng.step(x, v, xp, aim, inds[k], inds[k + 1], want_stats=False)
+            eng.markers(x, out=mk)
+            t_eng.render(hm[:E], None, out=rgb[:E], depth_out=depth[:E])
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / steps
+        full = {"workload": f"config 3: {E} envs, gel FEM substep + FEM markers + Taxim RGB 320x240 per step",
+                "frames_per_s": E / (fms / 1e3), "ms_per_step": fms}
+    out = {"workload": f"{E} gels (572 verts / 2160 tets, float64): implicit-Euler IPC substep + FEM marker read-out",
             "gel_steps_per_s": E / (ms / 1e3), "ms_per_step": ms,
             "newton_iters_mean": float(np.mean([q["newton_iters"] for q in d])),
             "pcg_iters_mean": float(np.mean([q["pcg_iters"] for q in d])),
             "compulsory_bytes_per_gel_step": 315136}
+    if full is not None:
+        out["config3_full_step"] = full
+    return out
 
 
 def run_reference(args) -> None:
@@ -313,7 +333,7 @@ def main() -> None:
     # ---- config 3 extra: the optional gel FEM substep, measured in the same run (not part of `value`) -------------
     fem_extra = None
     if not args.no_fem and world == 1:
-        fem_extra = fem_gpu(min(E, 4096), 3, dev)
+        fem_extra = fem_gpu(min(E, 4096), 3, dev, tactile=(eng, hm, rgb, depth))
 
     # ---- max over ranks ------------------------------------------------------------------------------------------
     t = torch.tensor([ms, kern_ms, e2e_s], device=dev, dtype=torch.float64)

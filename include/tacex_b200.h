@@ -120,6 +120,18 @@ int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N
 int tx_render_depth(tx_handle* h, const float* depth_m, float clip_max_m, int N, float* rgb, float* depth_out,
                     float* height_mm_out);
 
+/* Camera resolution != tactile resolution. The reference resizes the sensor camera's height map with torchvision's
+ * F.resize (bilinear, antialias) before rendering when the camera is coarser than the tactile image -- its RL tasks and
+ * the FEM preset run 32x32 / 32x24 cameras (ref: .../gpu_taxim/taxim_sim.py:88-89, .../fots/fots_marker_sim.py:121-127,
+ * tacex_assets/sensors/gelsight_mini/gsmini_taxim_fem_cfg.py:27,52). tx_set_camera_resolution precomputes the filter taps
+ * for [Hc][Wc] -> [H][W] (up-sampling only, Hc * Wc <= 9600); tx_render_camera then takes frames [N][Hc][Wc] -- height maps
+ * in mm, or (is_depth != 0) depth images in metres with inf -> clip_max_m as tx_render_depth -- resizes them in the load
+ * stage of the fused kernel and renders as tx_render does. press_mm == NULL: the indentation depth is computed from the
+ * CAMERA-resolution frame, as compute_indentation_depth does (ref: taxim_sim.py:115-131), and stored in depth_out. */
+int tx_set_camera_resolution(tx_handle* h, int Hc, int Wc);
+int tx_render_camera(tx_handle* h, const float* frames, int is_depth, float clip_max_m, const float* press_mm, int N,
+                     float* rgb, float* depth_out, float* deformed, uint8_t* mask);
+
 /* Replaces FOTSMarkerSimulator.marker_motion_simulation + MarkerMotion.marker_sim
  * (ref: .../fots/fots_marker_sim.py:114-184, .../fots/sim/marker_motion.py:78-120,144-219) using the gel
  * deformation recorded by the preceding tx_render of the SAME batch (no second blur pyramid).

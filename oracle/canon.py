@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(str(_LIB))
         _lib.canon_taxim_render.restype = C.c_int
         _lib.canon_num_threads.restype = C.c_int
+        _lib.canon_resize_bilinear.restype = C.c_int
     return _lib
 
 
@@ -87,9 +88,10 @@ class CanonTaxim:
         self.gelpad_height_m, self.gelpad_to_cam_min_m = gelpad_height_m, gelpad_to_cam_min_m
 
     def indentation_depth(self, hm_mm: np.ndarray) -> np.ndarray:
+        """Any frame shape [N][h][w]: the reference computes it on the camera-resolution height map (taxim_sim.py:115-131)."""
         hm = np.ascontiguousarray(hm_mm, np.float32)
         out = np.empty(hm.shape[0], np.float32)
-        lib().canon_indentation_depth(_p(hm, C.c_float), hm.shape[0], self.H, self.W, C.c_float(self.gelpad_height_m),
+        lib().canon_indentation_depth(_p(hm, C.c_float), hm.shape[0], hm.shape[1], hm.shape[2], C.c_float(self.gelpad_height_m),
                                       C.c_float(self.gelpad_to_cam_min_m), _p(out, C.c_float))
         return out
 
@@ -145,6 +147,17 @@ class CanonFots:
                               _p(mk, C.c_uint8), _p(pr, C.c_float), _p(th, C.c_float), N, _p(self.traj0, C.c_float),
                               _p(self.traj_len, C.c_int32), _p(out, C.c_float))
         return out
+
+
+def resize_bilinear(src: np.ndarray, out_hw: tuple[int, int]) -> np.ndarray:
+    """Canonical restatement of the reference's F.resize of the height map (taxim_sim.py:88-89): [N][Hi][Wi] -> [N][Ho][Wo]."""
+    s = np.ascontiguousarray(src, np.float32)
+    N, Hi, Wi = s.shape
+    out = np.empty((N, out_hw[0], out_hw[1]), np.float32)
+    rc = lib().canon_resize_bilinear(_p(s, C.c_float), N, Hi, Wi, out_hw[0], out_hw[1], _p(out, C.c_float))
+    if rc != 0:
+        raise ValueError("canon_resize_bilinear: unsupported scale")
+    return out
 
 
 def num_threads() -> int:

@@ -439,6 +439,77 @@ void canon_fots_step(const canon_fots_cfg* c, const int32_t* mx, const int32_t* 
     }
 }
 
+/* ---------------- camera resolution != tactile resolution: bilinear resize of the height map ----------------
+ * ref: TaximSimulator.optical_simulation, .../gpu_taxim/taxim_sim.py:88-89 (torchvision F.resize, bilinear, antialias) and
+ * FOTSMarkerSimulator, .../fots/fots_marker_sim.py:121-127. torch's antialiased bilinear filter (aten UpSampleKernel.cpp,
+ * _compute_indices_min_size_weights_aa): scale = in / out, centre = scale (i + 0.5), support = 1 when up-sampling (scale when
+ * down-sampling), taps xmin = max(int(centre - support + 0.5), 0) .. min(int(centre + support + 0.5), in) - 1 with triangle
+ * weights normalised to sum 1. Canonical choices: float32 weight arithmetic (as aten does for float32 images); at most
+ * CANON_RS_TAPS taps; each 1-D pass accumulates acc = w[0] x[0]; acc = fmaf(w[k], x[k], acc); horizontal pass first. */
+#define CANON_RS_TAPS 8
+int canon_resize_weights(int in_size, int out_size, int32_t* first /*[out]*/, int32_t* count /*[out]*/, float* w /*[out][CANON_RS_TAPS]*/)
+{
+    /* float32 arithmetic throughout, like aten computes the weights for float32 images */
+    const float scale = (float)in_size / (float)out_size;
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    for (int i = 0; i < out_size; ++i) {
+        const float center = scale * ((float)i + 0.5f);
+        long xmin = (long)(center - support + 0.5f);
+        if (xmin < 0) xmin = 0;
+        long xmax = (long)(center + support + 0.5f);
+        if (xmax > in_size) xmax = in_size;
+        const int n = (int)(xmax - xmin);
+        if (n < 1 || n > CANON_RS_TAPS) return -1;
+        float wd[CANON_RS_TAPS], tot = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            float x = ((float)(j + xmin) - center + 0.5f) * invscale;
+            if (x < 0) x = -x;
+            wd[j] = x < 1.0f ? 1.0f - x : 0.0f;
+            tot += wd[j];
+        }
+        first[i] = (int32_t)xmin;
+        count[i] = n;
+        for (int j = 0; j < CANON_RS_TAPS; ++j) w[i * CANON_RS_TAPS + j] = j < n ? wd[j] / tot : 0.0f;
+    }
+    return 0;
+}
+
+int canon_resize_bilinear(const float* src /*[N][Hi][Wi]*/, int N, int Hi, int Wi, int Ho, int Wo, float* dst /*[N][Ho][Wo]*/)
+{
+    int32_t *fx = malloc(sizeof(int32_t) * Wo), *cx = malloc(sizeof(int32_t) * Wo), *fy = malloc(sizeof(int32_t) * Ho), *cy = malloc(sizeof(int32_t) * Ho);
+    float *wx = malloc(sizeof(float) * Wo * CANON_RS_TAPS), *wy = malloc(sizeof(float) * Ho * CANON_RS_TAPS);
+    int rc = -1;
+    if (fx && cx && fy && cy && wx && wy && canon_resize_weights(Wi, Wo, fx, cx, wx) == 0 && canon_resize_weights(Hi, Ho, fy, cy, wy) == 0) {
+        rc = 0;
+#pragma omp parallel for schedule(static)
+        for (int n = 0; n < N; ++n) {
+            float* tmp = malloc(sizeof(float) * (size_t)Hi * Wo);
+            const float* s = src + (size_t)n * Hi * Wi;
+            float* d = dst + (size_t)n * Ho * Wo;
+            for (int y = 0; y < Hi; ++y)
+                for (int X = 0; X < Wo; ++X) {
+                    const float* sp = s + (size_t)y * Wi + fx[X];
+                    const float* w = wx + X * CANON_RS_TAPS;
+                    float acc = w[0] * sp[0];
+                    for (int j = 1; j < cx[X]; ++j) acc = fmaf(w[j], sp[j], acc);
+                    tmp[(size_t)y * Wo + X] = acc;
+                }
+            for (int Y = 0; Y < Ho; ++Y)
+                for (int X = 0; X < Wo; ++X) {
+                    const float* tp = tmp + (size_t)fy[Y] * Wo + X;
+                    const float* w = wy + Y * CANON_RS_TAPS;
+                    float acc = w[0] * tp[0];
+                    for (int j = 1; j < cy[Y]; ++j) acc = fmaf(w[j], tp[(size_t)j * Wo], acc);
+                    d[(size_t)Y * Wo + X] = acc;
+                }
+            free(tmp);
+        }
+    }
+    free(fx); free(cx); free(fy); free(cy); free(wx); free(wy);
+    return rc;
+}
+
 /* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs ask for all host threads explicitly */
 void canon_set_threads(int n)
 {

@@ -195,7 +195,7 @@ __device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, un
 // `list` holds the indices of the mask words with at least one bit set (built once per frame).
 __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits, const unsigned short* list, int nlist,
                                          const float* __restrict__ hm_half, const float* __restrict__ gel_half, float m,
-                                         float press, int warp, int lane, float depth_clip)
+                                         float press, int warp, int lane, float depth_clip, bool coherent)
 {
     for (int i0 = warp * 4; i0 < nlist; i0 += NWARPS * 4) {
         float v[4];
@@ -210,7 +210,7 @@ __device__ __forceinline__ void reimpose(float* plane, const unsigned* maskbits,
                 idx[u] = w * 32 + lane;
                 on[u] = (maskbits[w] >> lane) & 1u;
                 if (on[u]) {
-                    v[u] = __ldg(hm_half + idx[u]);
+                    v[u] = coherent ? hm_half[idx[u]] : __ldg(hm_half + idx[u]); // coherent: written by this kernel (resized map)
                     if (depth_clip > 0.0f) v[u] = __fmul_rn(isinf(v[u]) ? depth_clip : v[u], 1000.0f);
                 }
             }
@@ -239,6 +239,7 @@ struct FlatCopy {
     float* dst;       // RGB output of this half
     int ry0, ry1, xa, xb, total;
     unsigned done;    // bit l: slice l has been copied
+    bool coherent_src; // the re-imposition source was written by this kernel (resized camera frame): no read-only loads
 };
 constexpr int FC_SLICES = 7;
 constexpr int FC_SLICE_QUADS = (HALF_H * (IMG_W / 4) + FC_SLICES - 1) / FC_SLICES;
@@ -294,7 +295,7 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
     __syncthreads();
     TX_TICK(4 + 4 * L + 2);
     if (!FINAL) {
-        reimpose(plane, maskbits, mlist, nlist, hm_half, gel_half, m, press, warp, lane, depth_clip);
+        reimpose(plane, maskbits, mlist, nlist, hm_half, gel_half, m, press, warp, lane, depth_clip, fc.coherent_src);
         __syncthreads();
     }
     TX_TICK(4 + 4 * L + 3);
@@ -345,7 +346,9 @@ cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s)
 }
 
 // ---- the fused kernel -------------------------------------------------------------------------------------------
-template <bool DEPTH>
+// MODE bit 0: the input is the camera DEPTH image in metres (inf = no hit); bit 1: the input has the camera resolution
+// [Hc][Wc] != 240 x 320 and is resized (bilinear, torchvision F.resize semantics) in the load stage.
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_fused_kernel(const TaximArgs p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -361,7 +364,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     const int n = blockIdx.x >> 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t half_off = (size_t)n * IMG_H * IMG_W + (size_t)q * HALF_H * IMG_W;
-    const float* hm_half = p.hm + half_off;
+    constexpr bool DEPTH = (MODE & 1) != 0, LOWRES = (MODE & 2) != 0;
+    const float* hm_half = (LOWRES ? p.up_scratch : p.hm) + half_off; // full-resolution height map of this half (global)
     const float* gel_half = p.gel ? p.gel + (size_t)q * HALF_H * IMG_W : nullptr;
     float* hb0_remote = cluster.map_shared_rank(hb0, q ^ 1u);
     float* hb1_remote = cluster.map_shared_rank(hb1, q ^ 1u);
@@ -378,31 +382,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         misc->bbox[0] = IMG_H; misc->bbox[1] = -1; misc->bbox[2] = IMG_W; misc->bbox[3] = -1;
     }
     __syncthreads();
-    if (tid == 0) {
-        constexpr uint32_t CH = HALF_H * IMG_W * 4 / 4; // 4 chunks of 38,400 B
-        mbar_expect_tx(&misc->mbar, HALF_H * IMG_W * 4);
+    float m_cam = 0.0f; // LOWRES: minimum of the camera-resolution height map (what compute_indentation_depth sees)
+    if (!LOWRES) {
+        if (tid == 0) {
+            constexpr uint32_t CH = HALF_H * IMG_W * 4 / 4; // 4 chunks of 38,400 B
+            mbar_expect_tx(&misc->mbar, HALF_H * IMG_W * 4);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            bulk_g2s(reinterpret_cast<unsigned char*>(plane) + c * CH,
-                     reinterpret_cast<const unsigned char*>(hm_half) + c * CH, CH, &misc->mbar);
-    }
-    mbar_wait(&misc->mbar, 0);
-    TX_TICK(1);
-
-    // ---- optional fused GelSightSensor._get_height_map (ref: gelsight_sensor.py:581-593): depth [m] -> height map [mm] ----
-    if (DEPTH) {
-        float4* p4w = reinterpret_cast<float4*>(plane);
-        float4* o4w = p.hm_out ? reinterpret_cast<float4*>(p.hm_out + half_off) : nullptr;
-        for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) {
-            float4 t = p4w[i];
-            t.x = __fmul_rn(isinf(t.x) ? p.clip_max_m : t.x, 1000.0f);
-            t.y = __fmul_rn(isinf(t.y) ? p.clip_max_m : t.y, 1000.0f);
-            t.z = __fmul_rn(isinf(t.z) ? p.clip_max_m : t.z, 1000.0f);
-            t.w = __fmul_rn(isinf(t.w) ? p.clip_max_m : t.w, 1000.0f);
-            p4w[i] = t;
-            if (o4w) o4w[i] = t;
+            for (int c = 0; c < 4; ++c)
+                bulk_g2s(reinterpret_cast<unsigned char*>(plane) + c * CH,
+                         reinterpret_cast<const unsigned char*>(hm_half) + c * CH, CH, &misc->mbar);
         }
+        mbar_wait(&misc->mbar, 0);
+        TX_TICK(1);
+
+        // ---- optional fused GelSightSensor._get_height_map (ref: gelsight_sensor.py:581-593): depth [m] -> height map [mm] ----
+        if (DEPTH) {
+            float4* p4w = reinterpret_cast<float4*>(plane);
+            float4* o4w = p.hm_out ? reinterpret_cast<float4*>(p.hm_out + half_off) : nullptr;
+            for (int i = tid; i < HALF_H * IMG_W / 4; i += NTHREADS) {
+                float4 t = p4w[i];
+                t.x = __fmul_rn(isinf(t.x) ? p.clip_max_m : t.x, 1000.0f);
+                t.y = __fmul_rn(isinf(t.y) ? p.clip_max_m : t.y, 1000.0f);
+                t.z = __fmul_rn(isinf(t.z) ? p.clip_max_m : t.z, 1000.0f);
+                t.w = __fmul_rn(isinf(t.w) ? p.clip_max_m : t.w, 1000.0f);
+                p4w[i] = t;
+                if (o4w) o4w[i] = t;
+            }
+            __syncthreads();
+        }
+    } else {
+        // ---- camera resolution != tactile resolution (ref: taxim_sim.py:88-89, F.resize bilinear): the whole camera frame is
+        // staged in shared memory (hb0 is free until the first blur level), converted like _get_height_map when it is a depth
+        // image, and every pixel of this half is interpolated from it: horizontal taps first, then vertical, fmaf-accumulated
+        // exactly like aten's separable antialias kernel (the tables hold first tap + two weights per output index).
+        float* lo = hb0;
+        const int npx = p.Hc * p.Wc;
+        const float* src = p.hm + (size_t)n * npx;
+        float lmin = __int_as_float(0x7f800000);
+        for (int i = tid; i < npx; i += NTHREADS) {
+            float v = __ldg(src + i);
+            if (DEPTH) v = __fmul_rn(isinf(v) ? p.clip_max_m : v, 1000.0f);
+            lo[i] = v;
+            lmin = fminf(lmin, v);
+        }
+        lmin = warp_min(lmin);
+        if (lane == 0) misc->red_f[warp] = lmin;
         __syncthreads();
+        m_cam = misc->red_f[0];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) m_cam = fminf(m_cam, misc->red_f[w]);
+        float* up_half = p.up_scratch + half_off;
+        for (int idx = tid; idx < HALF_H * IMG_W; idx += NTHREADS) {
+            const int row = idx / IMG_W, X = idx - row * IMG_W;
+            const int Y = (int)q * HALF_H + row;
+            const int y0 = __ldg(p.rs_y0 + Y), x0 = __ldg(p.rs_x0 + X);
+            const float2 wy = __ldg(p.rs_wy + Y), wx = __ldg(p.rs_wx + X);
+            const int y1 = min(y0 + 1, p.Hc - 1), x1 = min(x0 + 1, p.Wc - 1);
+            const float t0 = __fmaf_rn(wx.y, lo[y0 * p.Wc + x1], __fmul_rn(wx.x, lo[y0 * p.Wc + x0]));
+            const float t1 = __fmaf_rn(wx.y, lo[y1 * p.Wc + x1], __fmul_rn(wx.x, lo[y1 * p.Wc + x0]));
+            const float v = __fmaf_rn(wy.y, t1, __fmul_rn(wy.x, t0));
+            plane[idx] = v;
+            up_half[idx] = v; // the masked re-imposition reads the resized map back (L2)
+        }
+        __syncthreads(); // also: red_f is reused by the frame minimum below
+        TX_TICK(1);
     }
 
     // ---- frame minimum (ref: taxim_torch.py:441, taxim_sim.py:116-117) ----------------------------------------
@@ -433,7 +476,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     if (p.press_in) {
         press = __ldg(p.press_in + n);
     } else {
-        float d = __fdiv_rn(m, 1000.0f);
+        float d = __fdiv_rn(LOWRES ? m_cam : m, 1000.0f);
         d = __fadd_rn(d, -p.gelpad_min);
         d = d < 0.0f ? 0.0f : d;
         press = (d <= p.gelpad_h) ? __fmul_rn(__fadd_rn(p.gelpad_h, -d), 1000.0f) : 0.0f;
@@ -520,7 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     if (p.gel != nullptr) { rg.r0 = 0; rg.r1 = IMG_H - 1; rg.c0 = 0; rg.c1 = IMG_W - 1; } // a gel map makes the plane dense
 
     TX_TICK(3);
-    const float depth_clip = DEPTH ? p.clip_max_m : 0.0f; // > 0: the input frame is a depth image in metres
+    const float depth_clip = (DEPTH && !LOWRES) ? p.clip_max_m : 0.0f; // > 0: the re-imposition source is a depth image in metres
     const bool active = (p.gel != nullptr) || (press > 0.0f);
     // rectangle of the pixels that can have a non-zero gradient: the contact box grown by the sum of the blur radii (the
     // region after the last level) + 1 px for the central differences; the replicate-padded border rows / columns follow
@@ -529,6 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     fc.src = p.flat_rgb + (size_t)q * HALF_H * IMG_W * 3;
     fc.dst = p.rgb + half_off * 3;
     fc.ry0 = 0; fc.ry1 = -1; fc.xa = 0; fc.xb = -1; fc.done = 0u;
+    fc.coherent_src = LOWRES;
     if (active && !(p.dbg & 4)) {
         constexpr int GROW = 30 + 16 + 8 + 4 + 2 + 1 + 2;
         const int base = (int)q * HALF_H;
@@ -707,18 +751,25 @@ cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(taxim_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(taxim_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(taxim_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(taxim_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (a.input_is_depth)
-        taxim_fused_kernel<true><<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
-    else
-        taxim_fused_kernel<false><<<dim3(2 * N), dim3(NTHREADS), SM_TOTAL, s>>>(a);
+    const int mode = (a.input_is_depth ? 1 : 0) | (a.Hc > 0 ? 2 : 0);
+    const dim3 grid(2 * N), block(NTHREADS);
+    switch (mode) {
+    case 0: taxim_fused_kernel<0><<<grid, block, SM_TOTAL, s>>>(a); break;
+    case 1: taxim_fused_kernel<1><<<grid, block, SM_TOTAL, s>>>(a); break;
+    case 2: taxim_fused_kernel<2><<<grid, block, SM_TOTAL, s>>>(a); break;
+    default: taxim_fused_kernel<3><<<grid, block, SM_TOTAL, s>>>(a); break;
+    }
     return cudaGetLastError();
 }
+
+int taxim_lowres_max_pixels() { return HB0_ROWS * IMG_W; }
 
 // ---- stand-alone indentation depth (ref: taxim_sim.py:115-131): one CTA per frame, HBM-bound -------------------
 __global__ void __launch_bounds__(256) indentation_depth_kernel(const float* __restrict__ hm, float* __restrict__ out,

@@ -46,6 +46,11 @@ struct tx_handle {
     std::vector<cudaEvent_t> ev_in, ev_done;
     long long* d_ticks = nullptr; // not owned
     int dbg = 0;
+    // camera resolution != tactile resolution (tx_set_camera_resolution)
+    int Hc = 0, Wc = 0;
+    int *d_rs_x0 = nullptr, *d_rs_y0 = nullptr;
+    float2 *d_rs_wx = nullptr, *d_rs_wy = nullptr;
+    float* d_up = nullptr;
 };
 
 static std::string g_create_err;
@@ -166,6 +171,7 @@ extern "C" void tx_destroy(tx_handle* h)
     cudaSetDevice(h->device);
     cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
+    cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
     cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
     cudaFree(h->d_traj_len); cudaFree(h->d_markers);
     for (auto e : h->ev_in) cudaEventDestroy(e);
@@ -256,7 +262,72 @@ extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N,
 }
 
 static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
-                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out);
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres = 0);
+
+// first tap + two weights per output index of torch's antialiased bilinear filter for up-sampling (support 1): float32
+// arithmetic like aten (UpSampleKernel.cpp, _compute_indices_min_size_weights_aa); returns false if more than two taps.
+static bool resize_table(int in_size, int out_size, std::vector<int>& first, std::vector<float2>& w)
+{
+    const float scale = (float)in_size / (float)out_size;
+    if (scale > 1.0f) return false; // down-sampling needs more taps than the fused load stage implements
+    first.resize(out_size);
+    w.resize(out_size);
+    for (int i = 0; i < out_size; ++i) {
+        const float center = scale * ((float)i + 0.5f);
+        long xmin = (long)(center - 1.0f + 0.5f);
+        if (xmin < 0) xmin = 0;
+        long xmax = (long)(center + 1.0f + 0.5f);
+        if (xmax > in_size) xmax = in_size;
+        const int n = (int)(xmax - xmin);
+        if (n < 1 || n > 2) return false;
+        float wd[2] = {0.0f, 0.0f}, tot = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            float x = ((float)(j + xmin) - center + 0.5f);
+            if (x < 0) x = -x;
+            wd[j] = x < 1.0f ? 1.0f - x : 0.0f;
+            tot += wd[j];
+        }
+        first[i] = (int)xmin;
+        w[i] = make_float2(wd[0] / tot, n > 1 ? wd[1] / tot : 0.0f);
+    }
+    return true;
+}
+
+extern "C" int tx_set_camera_resolution(tx_handle* h, int Hc, int Wc)
+{
+    if (!h || Hc <= 0 || Wc <= 0) return fail(h, TX_ERR_INVALID_ARG, "tx_set_camera_resolution: bad argument");
+    if (Hc > h->cfg.H || Wc > h->cfg.W || Hc * Wc > taxim_lowres_max_pixels() || (Hc == h->cfg.H && Wc == h->cfg.W))
+        return fail(h, TX_ERR_UNSUPPORTED, "tx_set_camera_resolution: only up-sampling of frames of at most 9600 pixels is fused");
+    std::vector<int> fx, fy;
+    std::vector<float2> wx, wy;
+    if (!resize_table(Wc, h->cfg.W, fx, wx) || !resize_table(Hc, h->cfg.H, fy, wy))
+        return fail(h, TX_ERR_UNSUPPORTED, "tx_set_camera_resolution: unsupported scale");
+    TX_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_rs_x0) {
+        TX_CUDA(h, cudaMalloc(&h->d_rs_x0, sizeof(int) * h->cfg.W));
+        TX_CUDA(h, cudaMalloc(&h->d_rs_y0, sizeof(int) * h->cfg.H));
+        TX_CUDA(h, cudaMalloc(&h->d_rs_wx, sizeof(float2) * h->cfg.W));
+        TX_CUDA(h, cudaMalloc(&h->d_rs_wy, sizeof(float2) * h->cfg.H));
+        TX_CUDA(h, cudaMalloc(&h->d_up, sizeof(float) * (size_t)h->cfg.max_envs * h->cfg.H * h->cfg.W));
+    }
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    TX_CUDA(h, cudaMemcpy(h->d_rs_x0, fx.data(), sizeof(int) * fx.size(), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_rs_y0, fy.data(), sizeof(int) * fy.size(), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_rs_wx, wx.data(), sizeof(float2) * wx.size(), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_rs_wy, wy.data(), sizeof(float2) * wy.size(), cudaMemcpyHostToDevice));
+    h->Hc = Hc;
+    h->Wc = Wc;
+    return TX_OK;
+}
+
+extern "C" int tx_render_camera(tx_handle* h, const float* frames, int is_depth, float clip_max_m, const float* press_mm, int N,
+                                float* rgb, float* depth_out, float* deformed, uint8_t* mask)
+{
+    if (!h) return TX_ERR_INVALID_ARG;
+    if (h->Hc <= 0) return fail(h, TX_ERR_STATE, "tx_render_camera: call tx_set_camera_resolution first");
+    if (is_depth && !(clip_max_m > 0.0f)) return fail(h, TX_ERR_INVALID_ARG, "tx_render_camera: clip_max_m must be positive");
+    return render_impl(h, frames, press_mm, N, rgb, depth_out, deformed, mask, is_depth ? 1 : 0, clip_max_m, nullptr, 1);
+}
 
 extern "C" int tx_render(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb,
                          float* depth_out, float* deformed, uint8_t* mask)
@@ -274,12 +345,12 @@ extern "C" int tx_render_depth(tx_handle* h, const float* depth_m, float clip_ma
 }
 
 static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
-                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out)
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres)
 {
     if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render: bad argument");
     if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
     if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
-    if (((uintptr_t)height_mm & 15u) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u)))
+    if ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u)))
         return fail(h, TX_ERR_INVALID_ARG, "tx_render: device buffers must be 16-byte aligned");
     if (N == 0) return TX_OK;
     TX_CUDA(h, cudaSetDevice(h->device));
@@ -289,6 +360,11 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     a.input_is_depth = input_is_depth;
     a.clip_max_m = clip_max_m;
     a.hm_out = hm_out;
+    if (lowres) {
+        a.Hc = h->Hc; a.Wc = h->Wc;
+        a.rs_x0 = h->d_rs_x0; a.rs_y0 = h->d_rs_y0; a.rs_wx = h->d_rs_wx; a.rs_wy = h->d_rs_wy;
+        a.up_scratch = h->d_up;
+    }
     fill_taxim_consts(h, a);
     a.rgb = rgb;
     a.depth_out = depth_out;

@@ -21,6 +21,13 @@ struct TaximArgs {
     int input_is_depth;    // 1: `hm` holds the camera depth image in metres (inf = no hit): mm = (isinf ? clip_max : d) * 1000
     float clip_max_m;      // far clipping plane of the sensor camera [m]
     float* hm_out;         // optional [N][240][320]: the height map in mm (what GelSightSensor publishes as 'height_map')
+    // camera resolution != tactile resolution (ref: taxim_sim.py:88-89): `hm` holds [N][Hc][Wc] frames, resized in the load stage
+    int Hc, Wc;            // 0, 0: `hm` is [N][240][320]
+    const int* rs_x0;      // [320] first horizontal tap
+    const float2* rs_wx;   // [320] the two horizontal weights
+    const int* rs_y0;      // [240] first vertical tap
+    const float2* rs_wy;   // [240] the two vertical weights
+    float* up_scratch;     // [N][240][320] resized height maps (read back by the masked re-imposition)
     const float* gel;      // [240][320] or nullptr (flat)
     const float4* poly;    // [nb][nb][20] (3 channels x 6 coefficients, padded)
     const float* bg_hwc;   // [240][320][3]
@@ -110,6 +117,7 @@ cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
 
 cudaError_t upload_taps(const float* host_taps, cudaStream_t s);
 int taxim_smem_bytes();
+int taxim_lowres_max_pixels();
 cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
 cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);

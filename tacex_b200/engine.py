@@ -152,6 +152,25 @@ class TactileEngine:
                                              _ptr(height_map_out)))
         return out
 
+    def set_camera_resolution(self, Hc: int, Wc: int) -> None:
+        """Sensor camera coarser than the tactile image (ref: taxim_sim.py:88-89): precompute the bilinear resize taps."""
+        self._check(self.lib.tx_set_camera_resolution(self.h, int(Hc), int(Wc)))
+        self.cam_hw = (int(Hc), int(Wc))
+
+    def render_camera(self, frames: torch.Tensor, is_depth: bool = False, clip_max_m: float = 0.0,
+                      press: torch.Tensor | None = None, out: torch.Tensor | None = None, depth_out: torch.Tensor | None = None,
+                      deformed_out: torch.Tensor | None = None, mask_out: torch.Tensor | None = None) -> torch.Tensor:
+        """RGB (N, H, W, 3) from camera-resolution frames (N, Hc, Wc): F.resize (bilinear) fused into the load stage."""
+        if frames.device != self.device or frames.dtype != torch.float32 or not frames.is_contiguous():
+            raise _lib.TxError("frames must be a contiguous float32 tensor on the engine's device")
+        if frames.dim() != 3 or tuple(frames.shape[1:]) != getattr(self, "cam_hw", None):
+            raise _lib.TxError("frames must have the shape given to set_camera_resolution")
+        N = frames.shape[0]
+        out = torch.empty((N, self.H, self.W, 3), device=self.device) if out is None else out
+        self._check(self.lib.tx_render_camera(self.h, _ptr(frames), int(bool(is_depth)), float(clip_max_m), _ptr(press), N,
+                                              _ptr(out), _ptr(depth_out), _ptr(deformed_out), _ptr(mask_out)))
+        return out
+
     def fots_markers(self, press: torch.Tensor, theta: torch.Tensor, traj0: torch.Tensor, traj_len: torch.Tensor,
                      out: torch.Tensor | None = None) -> torch.Tensor:
         N = press.shape[0]

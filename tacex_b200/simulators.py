@@ -175,15 +175,45 @@ class B200TaximSimulator(GelSightSimulator):
         self._sensor_depth_version = None
 
     # -- helpers ---------------------------------------------------------------------------------------------------
+    def _camera_mode(self, hm: torch.Tensor) -> bool:
+        """True when the sensor camera is coarser than the tactile image and the fused resize of the kernel's load stage
+        applies (ref: taxim_sim.py:88-89 F.resize; the RL tasks / the FEM preset run 32x32 / 32x24 cameras)."""
+        W, H = self.cfg.tactile_img_res
+        hc, wc = int(hm.shape[1]), int(hm.shape[2])
+        if (hc, wc) == (H, W):
+            return False
+        if hc <= H and wc <= W and hc * wc <= 9600:
+            if getattr(self.engine, "cam_hw", None) != (hc, wc):
+                self.engine.set_camera_resolution(hc, wc)
+            return True
+        return False
+
     def _height_map(self) -> torch.Tensor:
         hm = self.sensor._data.output["height_map"]
         W, H = self.cfg.tactile_img_res
         if (hm.shape[1], hm.shape[2]) != (H, W):
-            # camera resolution != tactile resolution: bilinear + antialias like torchvision's F.resize (taxim_sim.py:88-89)
+            # camera finer than the tactile image (down-sampling; not fused): torchvision's F.resize semantics (taxim_sim.py:88-89)
             hm = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0]
         if hm.device != self.engine.device:
             hm = hm.to(self.engine.device)
         return hm.contiguous()
+
+    def _render(self, press, depth_out=None):
+        raw = self.sensor._data.output["height_map"]
+        if self._camera_mode(raw):
+            cam = raw if raw.device == self.engine.device else raw.to(self.engine.device)
+            self.engine.render_camera(cam.contiguous(), press=press, out=self._rgb_target(), depth_out=depth_out)
+            return
+        hm = self._height_map()
+        if press is None and tuple(raw.shape[1:]) != tuple(hm.shape[1:]):
+            # the indentation depth belongs to the CAMERA-resolution map (taxim_sim.py:115-131), the render to the resized one
+            mn = raw.amin((1, 2)) / 1000.0 - self.cfg.gelpad_to_camera_min_distance
+            mn = torch.where(mn < 0, torch.zeros_like(mn), mn)
+            press = torch.where(mn <= self.cfg.gelpad_height, (self.cfg.gelpad_height - mn) * 1000.0, torch.zeros_like(mn))
+            press = press.to(self.engine.device, torch.float32).contiguous()
+            if depth_out is not None:
+                depth_out.copy_(press)
+        self.engine.render(hm, press, out=self._rgb_target(), depth_out=depth_out if press is None else None)
 
     def _rgb_target(self) -> torch.Tensor:
         """Render straight into the sensor-owned output tensor when it exists: ``output[:] = returned`` in the sensor
@@ -204,8 +234,7 @@ class B200TaximSimulator(GelSightSimulator):
     def compute_indentation_depth(self):
         """Indentation depth [mm] (ref: taxim_sim.py:115-131). Runs the FUSED kernel: the RGB frame of the same
         height map is produced in the same launch and reused by ``optical_simulation`` if nothing changed."""
-        hm = self._height_map()
-        self.engine.render(hm, None, out=self._rgb_target(), depth_out=self._indentation_depth)
+        self._render(None, depth_out=self._indentation_depth)
         self._stamp = (self._hm_stamp(), self._indentation_depth._version)
         return self._indentation_depth
 
@@ -225,8 +254,7 @@ class B200TaximSimulator(GelSightSimulator):
     def optical_simulation(self):
         """Tactile RGB (num_envs, H, W, 3) float32 in [0, 1] (ref: taxim_sim.py:80-113)."""
         if self._stamp != (self._hm_stamp(), self._indentation_depth._version):
-            hm = self._height_map()
-            self.engine.render(hm, self._indentation_depth, out=self._rgb_target())
+            self._render(self._indentation_depth)
             self._stamp = (self._hm_stamp(), self._indentation_depth._version)
         sd = getattr(self.sensor, "_indentation_depth", None)
         self._sensor_depth_version = sd._version if isinstance(sd, torch.Tensor) else None

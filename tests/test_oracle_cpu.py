@@ -140,3 +140,18 @@ def test_canonical_atan_accuracy():
     got = np.array([catan(v) for v in x[::50]])
     assert np.abs(got - ref[::50]).max() < 3e-7
     assert lib is not None
+
+
+def test_canonical_resize_is_bitwise_torch_antialias_bilinear():
+    """Row a3 (camera resolution != tactile resolution, ref: taxim_sim.py:88-89): the canonical C restatement of the resize
+    equals torch's antialiased bilinear interpolation (what torchvision's F.resize calls) BIT FOR BIT on the CPU."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import canon
+
+    rng = np.random.default_rng(0)
+    for hi, wi in [(24, 32), (32, 32), (48, 64), (60, 80), (120, 160), (17, 23)]:
+        x = rng.uniform(24, 29, (2, hi, wi)).astype(np.float32)
+        ref = F.interpolate(torch.from_numpy(x)[:, None], size=[240, 320], mode="bilinear", align_corners=False, antialias=True)[:, 0]
+        assert np.array_equal(canon.resize_bilinear(x, (240, 320)), ref.numpy()), (hi, wi)

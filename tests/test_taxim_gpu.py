@@ -102,6 +102,43 @@ def test_region_edges_vs_canonical_oracle(eng, canon_taxim):
         assert np.array_equal(rgb, o["rgb"]), f"frames {np.unique(np.nonzero(rgb != o['rgb'])[0]) + i}"
 
 
+@pytest.mark.parametrize("cam", [(24, 32), (32, 32), (60, 80)])
+def test_camera_resolution_fused_resize(tables, canon_taxim, cam):
+    """Row a3: sensor camera coarser than the tactile image (the FEM preset renders 32x24, the RL tasks 32x32). The resize
+    runs in the kernel's load stage; bit-exact against the oracle (canonical resize -- itself bitwise torch F.resize on the
+    CPU -- followed by the canonical render), with the indentation depth taken from the CAMERA-resolution map."""
+    from oracle import canon
+    from tacex_b200 import synth
+    from tacex_b200.engine import TactileEngine
+
+    hc, wc = cam
+    pitch = synth.PIXEL_PITCH_M_320 * W / wc
+    rng = np.random.default_rng(5)
+    depth = torch.stack([
+        synth.depth_map(0, 3e-3, float(rng.uniform(-4e-3, 4e-3)), float(rng.uniform(-3e-3, 3e-3)), 0.0, float(rng.uniform(2e-4, 1.5e-3)),
+                        H=hc, W=wc, pitch=pitch, contact=i != 3) for i in range(6)])
+    depth[5] = torch.where(depth[5] >= synth.CLIP_MAX_M, torch.full_like(depth[5], float("inf")), depth[5])  # RTX "no hit"
+    hm_lo = synth.height_map_mm(depth)
+    e = TactileEngine(tables, max_envs=8)
+    e.set_camera_resolution(hc, wc)
+    n = hm_lo.shape[0]
+    dg = torch.empty((n, H, W), device="cuda")
+    mk = torch.empty((n, H, W), device="cuda", dtype=torch.uint8)
+    dep = torch.empty(n, device="cuda")
+    rgb = e.render_camera(hm_lo.cuda().contiguous(), depth_out=dep, deformed_out=dg, mask_out=mk)
+    dep2 = torch.empty(n, device="cuda")
+    rgb2 = e.render_camera(depth.cuda().contiguous(), is_depth=True, clip_max_m=synth.CLIP_MAX_M, depth_out=dep2)
+    torch.cuda.synchronize()
+    pc = canon_taxim.indentation_depth(hm_lo.numpy())
+    o = canon_taxim.render(canon.resize_bilinear(hm_lo.numpy(), (H, W)), pc)
+    assert np.array_equal(dep.cpu().numpy(), pc) and np.array_equal(dep2.cpu().numpy(), pc)
+    assert np.array_equal(mk.cpu().numpy(), o["mask"])
+    assert np.array_equal(dg.cpu().numpy(), o["deformed"])
+    assert np.array_equal(rgb.cpu().numpy(), o["rgb"])
+    assert torch.equal(rgb, rgb2)
+    assert (pc > 0).sum() >= 4
+
+
 def test_explicit_press_equals_fused(eng, inputs):
     hm = inputs["config2_sub"].cuda()
     press = eng.indentation_depth(hm)
