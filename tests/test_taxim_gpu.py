@@ -286,6 +286,30 @@ def test_sensor_plugin_flow(tables, canon_taxim, inputs, golden):
     assert int(s.marker_motion_simulator.traj_len[1]) == 0 and int(s.marker_motion_simulator.traj_len[0]) == 3
 
 
+def test_sensor_plugin_flow_coarse_camera(tables, canon_taxim):
+    """The FEM preset's 32x24 sensor camera (ref: gsmini_taxim_fem_cfg.py:27,52) through the plug-in: the optical simulator
+    resizes inside the fused kernel; RGB / indentation depth / markers equal the oracle's resize + render + FOTS."""
+    from oracle import canon
+    from tacex_b200 import sensor, synth
+
+    cfg = sensor.gelsight_mini_cfg(str(GOLDEN / "gsmini_tables_320x240.npz"), num_envs=4)
+    cfg.sensor_camera_cfg.resolution = (32, 24)
+    s = sensor.GelSightSensor(cfg)
+    pitch = synth.PIXEL_PITCH_M_320 * 10
+    depth = torch.stack([synth.depth_map(0, 3e-3, 1e-3 * i, -5e-4 * i, 0.0, 4e-4 + 3e-4 * i, H=24, W=32, pitch=pitch) for i in range(4)])
+    s.set_camera_depth(depth.cuda())
+    s.update(0.0, force_recompute=True)
+    hm_lo = synth.height_map_mm(depth).numpy()
+    pc = canon_taxim.indentation_depth(hm_lo)
+    o = canon_taxim.render(canon.resize_bilinear(hm_lo, (H, W)), pc)
+    assert np.array_equal(s.indentation_depth.cpu().numpy(), pc) and (pc > 0).all()
+    assert np.array_equal(s.data.output["tactile_rgb"].cpu().numpy(), o["rgb"])
+    cf = canon.CanonFots(H, W, 9, 11, 15, 26)
+    mc = cf.step(o["deformed"], o["mask"], pc, np.zeros(4, np.float32))
+    assert np.abs(s.data.output["marker_motion"].cpu().numpy() - mc).max() <= 2e-4
+    assert tuple(s.data.output["height_map"].shape) == (4, 24, 32)
+
+
 def test_step_host_end_to_end(tables, canon_taxim, inputs):
     from tacex_b200.engine import TactileEngine
 
