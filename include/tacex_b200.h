@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TX_ABI_VERSION 1
+#define TX_ABI_VERSION 2
 #define TX_MAX_BLURS 8
 #define TX_MAX_TAPS 64
 #define TX_MAX_MARKERS 256
@@ -189,6 +189,9 @@ typedef struct {
     double velocity_tol, pcg_tol_rate;
     int pcg_max_iter_ratio, ls_max_iter, substep;
     int rest_volume_det; /* 1: elastic rest "volume" = det(Dm) as libuipc does; 0: det/6 */
+    double friction_mu;  /* Coulomb coefficient gel / indenter (lagged IPC friction, ref: contact_system/contact_models/
+                            ipc_vertex_half_plane_frictional_contact.cu; uipc_sim.py default friction ratio 0.5); 0 = off */
+    double eps_velocity; /* friction eps_velocity [m/s] (0.01) */
 } tx_fem_config;
 
 typedef struct tx_fem tx_fem;

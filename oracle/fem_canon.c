@@ -48,6 +48,8 @@ typedef struct {
     int pcg_max_iter_ratio;
     int ls_max_iter;
     int substep;
+    double friction_mu;   /* Coulomb coefficient of the gel / indenter pair (uipc_sim.py default_friction_ratio 0.5); 0 disables */
+    double eps_velocity;  /* friction.eps_velocity [m/s] (scene default 0.01) */
 } fem_cfg;
 
 typedef struct {
@@ -298,7 +300,70 @@ typedef struct {
     const double* x_tilde;
     double ratio;        /* animation substep ratio */
     fem_indenter ind;    /* current (interpolated) indenter */
+    fem_indenter ind0;   /* indenter at the start of the step (lagged friction) */
 } fem_ctx;
+
+/* ---- lagged Coulomb friction of a surface vertex against the prescribed indenter ---------------------------------------
+ * ref: contact_system/contact_models/ipc_vertex_half_plane_frictional_contact.cu:29-127,
+ *      ipc_vertex_half_plane_contact_function.h:62-151 (compute_tan_basis, PH_friction_energy / gradient_hessian),
+ *      codim_ipc_contact_function.h:16-128 (C1 clamp f0 / f1 / f2, 2x2 Hessian, normal_force).
+ * The normal force and the tangent frame are taken at the start-of-step position against the start-of-step indenter
+ * (lagged); the half-plane of the reference is static, here the tangential slip is measured RELATIVE to the prescribed
+ * translation of the indenter over the step. */
+static int friction_lagged(const fem_cfg* g, const fem_indenter* ind0, const double* xp, double* fn, double* e1, double* e2)
+{
+    double d, n[3], dB;
+    fem_indenter_sdf(ind0, xp, &d, n, 0);
+    if (!(d > 0.0) || !(d < g->d_hat)) return 0;
+    fem_barrier(d * d, g->d_hat, g->kappa * g->dt * g->dt, 0, &dB, 0);
+    *fn = -dB * 2.0 * d;
+    double t[3] = {1.0, 0.0, 0.0};
+    if (n[0] > 0.9) { t[0] = 0.0; t[2] = 1.0; }
+    double c[3] = {t[1] * n[2] - t[2] * n[1], t[2] * n[0] - t[0] * n[2], t[0] * n[1] - t[1] * n[0]};
+    const double l = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    for (int a = 0; a < 3; ++a) e1[a] = c[a] / l;
+    e2[0] = n[1] * e1[2] - n[2] * e1[1];
+    e2[1] = n[2] * e1[0] - n[0] * e1[2];
+    e2[2] = n[0] * e1[1] - n[1] * e1[0];
+    return 1;
+}
+
+/* energy, gradient (3) and Hessian (9, row-major) of mu fn f0(|u|), u = [e1 e2]^T rel, rel = (x - x_prev) - indenter shift */
+void fem_friction_terms(const fem_cfg* g, const fem_indenter* ind0, const fem_indenter* ind, const double* xp, const double* x,
+                        double* E, double* G, double* H)
+{
+    if (E) *E = 0.0;
+    if (G) memset(G, 0, sizeof(double) * 3);
+    if (H) memset(H, 0, sizeof(double) * 9);
+    double fn, e1[3], e2[3];
+    if (!(g->friction_mu > 0.0) || !friction_lagged(g, ind0, xp, &fn, e1, e2)) return;
+    double rel[3];
+    for (int a = 0; a < 3; ++a) rel[a] = (x[a] - xp[a]) - (ind->c[a] - ind0->c[a]);
+    const double u0 = e1[0] * rel[0] + e1[1] * rel[1] + e1[2] * rel[2];
+    const double u1 = e2[0] * rel[0] + e2[1] * rel[1] + e2[2] * rel[2];
+    const double x2 = u0 * u0 + u1 * u1, eps = g->eps_velocity * g->dt, y = sqrt(x2), mf = g->friction_mu * fn;
+    const int slip = x2 >= eps * eps;
+    if (E) *E = mf * (slip ? y : x2 * (-y / 3.0 + eps) / (eps * eps) + eps / 3.0);
+    const double f1 = slip ? 1.0 / y : (-y + 2.0 * eps) / (eps * eps);
+    if (G)
+        for (int a = 0; a < 3; ++a) G[a] = mf * f1 * (u0 * e1[a] + u1 * e2[a]);
+    if (H) {
+        double h00, h01, h11;
+        if (slip) {
+            const double s = mf * f1 / x2;
+            h00 = s * u1 * u1; h01 = -s * u1 * u0; h11 = s * u0 * u0;
+        } else if (x2 == 0.0) {
+            h00 = h11 = mf * f1; h01 = 0.0;
+        } else {
+            const double f2 = -1.0 / (eps * eps) / y; /* both eigenvalues (f1 - y / eps^2, f1) are positive: make_spd is the identity */
+            h00 = mf * (f2 * u0 * u0 + f1); h01 = mf * f2 * u0 * u1; h11 = mf * (f2 * u1 * u1 + f1);
+        }
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                H[3 * a + b] = h00 * e1[a] * e1[b] + h01 * (e1[a] * e2[b] + e2[a] * e1[b]) + h11 * e2[a] * e2[b];
+        fem_spd_project(3, H);
+    }
+}
 
 static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
 {
@@ -337,6 +402,13 @@ static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
         fem_barrier(d * d, g->d_hat, g->kappa * dt2, &B, 0, 0);
         E += B;
     }
+    if (g->friction_mu > 0.0)
+        for (int k = 0; k < g->S; ++k) {
+            int i = c->surf[k];
+            double Ef;
+            fem_friction_terms(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, &Ef, 0, 0);
+            E += Ef;
+        }
     if (min_dist) *min_dist = md;
     return E;
 }
@@ -397,14 +469,21 @@ static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, 
         double* Hk = Hc + 9 * k;
         memset(Hk, 0, sizeof(double) * 9);
         fem_indenter_sdf(&c->ind, x + 3 * i, &d, n, Hd);
-        if (!(d * d < g->d_hat * g->d_hat) || d <= 0.0) continue;
-        fem_barrier(d * d, g->d_hat, g->kappa * dt2, 0, &dB, &ddB);
-        double dD[3];
-        for (int a = 0; a < 3; ++a) dD[a] = 2.0 * d * n[a];
-        for (int a = 0; a < 3; ++a) G[3 * i + a] += dB * dD[a];
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) Hk[3 * a + b] = ddB * dD[a] * dD[b] + dB * 2.0 * (n[a] * n[b] + d * Hd[3 * a + b]);
-        fem_spd_project(3, Hk);
+        if ((d * d < g->d_hat * g->d_hat) && d > 0.0) {
+            fem_barrier(d * d, g->d_hat, g->kappa * dt2, 0, &dB, &ddB);
+            double dD[3];
+            for (int a = 0; a < 3; ++a) dD[a] = 2.0 * d * n[a];
+            for (int a = 0; a < 3; ++a) G[3 * i + a] += dB * dD[a];
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) Hk[3 * a + b] = ddB * dD[a] * dD[b] + dB * 2.0 * (n[a] * n[b] + d * Hd[3 * a + b]);
+            fem_spd_project(3, Hk);
+        }
+        if (g->friction_mu > 0.0) {
+            double Gf[3], Hf[9];
+            fem_friction_terms(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, 0, Gf, Hf);
+            for (int a = 0; a < 3; ++a) G[3 * i + a] += Gf[a];
+            for (int j = 0; j < 9; ++j) Hk[j] += Hf[j];
+        }
         for (int j = 0; j < 9; ++j) Dg[9 * i + j] += Hk[j];
     }
 }
@@ -524,6 +603,7 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     memset(&c, 0, sizeof(c));
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
     c.x_prev = x_prev; c.x_tilde = xt;
+    c.ind0 = *ind_prev;
     memset(st, 0, sizeof(*st));
 
     /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */
@@ -640,7 +720,7 @@ void fem_assemble_dense(const fem_cfg* g, const int32_t* tets, const double* Dm_
     fem_ctx c;
     memset(&c, 0, sizeof(c));
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
-    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind;
+    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind; c.ind0 = *ind;
     double* G = (double*)malloc(sizeof(double) * n);
     double* H9 = (double*)malloc(sizeof(double) * 81 * g->T);
     double* Dg = (double*)malloc(sizeof(double) * 9 * g->V);
@@ -667,7 +747,7 @@ int fem_pcg_solve(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, c
     fem_ctx c;
     memset(&c, 0, sizeof(c));
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
-    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind;
+    c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind; c.ind0 = *ind;
     double* buf = (double*)malloc(sizeof(double) * (6 * n + 81 * g->T + 18 * g->V + 9 * (g->S + 1)));
     double *G = buf, *r = G + n, *z = r + n, *p = z + n, *Ap = p + n, *H9 = Ap + n, *Dg = H9 + 81 * g->T, *Dinv = Dg + 9 * g->V,
            *Hc = Dinv + 9 * g->V;

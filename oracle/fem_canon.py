@@ -24,7 +24,7 @@ class FemCfg(C.Structure):
                 ("gravity", C.c_double * 3), ("mu", C.c_double), ("lam", C.c_double), ("attach_strength", C.c_double),
                 ("d_hat", C.c_double), ("kappa", C.c_double), ("newton_max_iter", C.c_int), ("velocity_tol", C.c_double),
                 ("pcg_tol_rate", C.c_double), ("pcg_max_iter_ratio", C.c_int), ("ls_max_iter", C.c_int),
-                ("substep", C.c_int)]
+                ("substep", C.c_int), ("friction_mu", C.c_double), ("eps_velocity", C.c_double)]
 
 
 class FemIndenter(C.Structure):
@@ -67,7 +67,8 @@ def make_indenter(kind: int, center, half, R=None) -> FemIndenter:
 
 class CanonFem:
     def __init__(self, mesh, youngs=1e4, poisson=0.49, density=1e3, dt=0.01, gravity=(0, 0, -9.8), attach_strength=1000.0,
-                 d_hat=5e-4, kappa=1e10, newton_max_iter=1024, velocity_tol=0.05, rest_volume_det=True, substep=1):
+                 d_hat=5e-4, kappa=1e10, newton_max_iter=1024, velocity_tol=0.05, rest_volume_det=True, substep=1,
+                 friction_mu=0.5, eps_velocity=0.01):
         from tacex_b200.gel_mesh import lame
 
         self.mesh = mesh
@@ -79,6 +80,7 @@ class CanonFem:
         g.mu, g.lam, g.attach_strength, g.d_hat, g.kappa = mu, lam, attach_strength, d_hat, kappa
         g.newton_max_iter, g.velocity_tol, g.pcg_tol_rate, g.pcg_max_iter_ratio, g.ls_max_iter, g.substep = (
             newton_max_iter, velocity_tol, 1e-3, 2, 8, substep)
+        g.friction_mu, g.eps_velocity = friction_mu, eps_velocity
         self.cfg = g
         self.X = np.ascontiguousarray(mesh.X, np.float64)
         self.tets = np.ascontiguousarray(mesh.tets, np.int32)

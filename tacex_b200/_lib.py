@@ -12,7 +12,7 @@ from pathlib import Path
 TX_MAX_BLURS = 8
 TX_MAX_TAPS = 64
 TX_MAX_MARKERS = 256
-TX_ABI_VERSION = 1
+TX_ABI_VERSION = 2
 
 import os
 
@@ -45,7 +45,7 @@ class TxFemConfig(C.Structure):
                 ("attach_strength", C.c_double), ("d_hat", C.c_double), ("kappa", C.c_double),
                 ("newton_max_iter", C.c_int), ("velocity_tol", C.c_double), ("pcg_tol_rate", C.c_double),
                 ("pcg_max_iter_ratio", C.c_int), ("ls_max_iter", C.c_int), ("substep", C.c_int),
-                ("rest_volume_det", C.c_int)]
+                ("rest_volume_det", C.c_int), ("friction_mu", C.c_double), ("eps_velocity", C.c_double)]
 
 
 class TxFemIndenter(C.Structure):

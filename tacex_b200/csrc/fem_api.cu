@@ -275,6 +275,7 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.dt = c.dt;
     for (int i = 0; i < 3; ++i) a.gravity[i] = c.gravity[i];
     a.mu = c.mu; a.lambda = c.lambda; a.attach_strength = c.attach_strength; a.d_hat = c.d_hat; a.kappa = c.kappa;
+    a.friction_mu = c.friction_mu; a.eps_velocity = c.eps_velocity;
     a.velocity_tol = c.velocity_tol; a.pcg_tol_rate = c.pcg_tol_rate; a.newton_max_iter = c.newton_max_iter;
     a.pcg_max_iter_ratio = c.pcg_max_iter_ratio; a.ls_max_iter = c.ls_max_iter; a.substep = c.substep;
     const int grid = N < f->grid ? N : f->grid;

@@ -465,6 +465,58 @@ __device__ __forceinline__ void tet_F(const double* x, const int* e, const doubl
         }
 }
 
+// ---- lagged Coulomb friction of a surface vertex against the prescribed indenter ------------------------------------------
+// ref: contact_system/contact_models/ipc_vertex_half_plane_frictional_contact.cu:29-127, ipc_vertex_half_plane_contact_function.h
+// :62-151, codim_ipc_contact_function.h:16-128. Normal force and tangent frame at the start-of-step position against the
+// start-of-step indenter (lagged); slip measured relative to the indenter's prescribed translation. E / G / H may be null.
+__device__ void friction_terms(const FemArgs& a, const FemIndenter& ind0, const FemIndenter& ind, const double* xp, const double* x,
+                               double* E, double* G, double* H6 /* symmetric 00 01 02 11 12 22 */)
+{
+    double d, n[3], dB;
+    indenter_sdf(ind0, xp, &d, n, nullptr);
+    if (!(d > 0.0) || !(d < a.d_hat)) return;
+    barrier_fn(d * d, a.d_hat, a.kappa * a.dt * a.dt, nullptr, &dB, nullptr);
+    const double mf = a.friction_mu * (-dB * 2.0 * d);
+    double t[3] = {1.0, 0.0, 0.0};
+    if (n[0] > 0.9) { t[0] = 0.0; t[2] = 1.0; }
+    const double c[3] = {t[1] * n[2] - t[2] * n[1], t[2] * n[0] - t[0] * n[2], t[0] * n[1] - t[1] * n[0]};
+    const double il = fast_rsqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const double e1[3] = {c[0] * il, c[1] * il, c[2] * il};
+    const double e2[3] = {n[1] * e1[2] - n[2] * e1[1], n[2] * e1[0] - n[0] * e1[2], n[0] * e1[1] - n[1] * e1[0]};
+    double rel[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rel[k] = (x[k] - xp[k]) - (ind.c[k] - ind0.c[k]);
+    const double u0 = e1[0] * rel[0] + e1[1] * rel[1] + e1[2] * rel[2];
+    const double u1 = e2[0] * rel[0] + e2[1] * rel[1] + e2[2] * rel[2];
+    const double x2 = u0 * u0 + u1 * u1, eps = a.eps_velocity * a.dt, y = sqrt(x2);
+    const bool slip = x2 >= eps * eps;
+    if (E) *E += mf * (slip ? y : x2 * (-y / 3.0 + eps) / (eps * eps) + eps / 3.0);
+    const double f1 = slip ? 1.0 / y : (-y + 2.0 * eps) / (eps * eps);
+    if (G) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) G[k] += mf * f1 * (u0 * e1[k] + u1 * e2[k]);
+    }
+    if (H6) {
+        double h00, h01, h11;
+        if (slip) {
+            const double s = mf * f1 / x2;
+            h00 = s * u1 * u1; h01 = -s * u1 * u0; h11 = s * u0 * u0;
+        } else if (x2 == 0.0) {
+            h00 = h11 = mf * f1; h01 = 0.0;
+        } else { // both eigenvalues (f1 - y / eps^2 and f1) are positive: make_spd is the identity
+            const double f2 = -1.0 / (eps * eps) / y;
+            h00 = mf * (f2 * u0 * u0 + f1); h01 = mf * f2 * u0 * u1; h11 = mf * (f2 * u1 * u1 + f1);
+        }
+        // J^T H2 J is positive semi-definite by construction (H2 is): the reference's 3x3 make_spd changes nothing
+        H6[0] += h00 * e1[0] * e1[0] + 2.0 * h01 * e1[0] * e2[0] + h11 * e2[0] * e2[0];
+        H6[1] += h00 * e1[0] * e1[1] + h01 * (e1[0] * e2[1] + e2[0] * e1[1]) + h11 * e2[0] * e2[1];
+        H6[2] += h00 * e1[0] * e1[2] + h01 * (e1[0] * e2[2] + e2[0] * e1[2]) + h11 * e2[0] * e2[2];
+        H6[3] += h00 * e1[1] * e1[1] + 2.0 * h01 * e1[1] * e2[1] + h11 * e2[1] * e2[1];
+        H6[4] += h00 * e1[1] * e1[2] + h01 * (e1[1] * e2[2] + e2[1] * e1[2]) + h11 * e2[1] * e2[2];
+        H6[5] += h00 * e1[2] * e1[2] + 2.0 * h01 * e1[2] * e2[2] + h11 * e2[2] * e2[2];
+    }
+}
+
 // ---- block reductions (deterministic: fixed tree over a fixed thread -> element mapping) -----------------------------
 // One __syncthreads per reduction: the per-warp partials are double-buffered (consecutive calls alternate buffers) and every
 // thread folds the NW partials itself in the same fixed order.
@@ -527,7 +579,7 @@ struct FemShared {
 // total incremental potential at the positions in s.x (thread `row` owns vertex `row`)
 __device__ double total_energy(const FemArgs& a, const FemShared& s, const double* xt_g,
                                const double* __restrict__ xprev_g, const double* __restrict__ aim_g, const FemIndenter& ind,
-                               double ratio, double* min_dist, int& ph)
+                               const FemIndenter& ind0, double ratio, double* min_dist, int& ph)
 {
     const double dt2 = a.dt * a.dt;
     const int i = threadIdx.x;
@@ -559,6 +611,10 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
                 barrier_fn(d * d, a.d_hat, a.kappa * dt2, &B, nullptr, nullptr);
                 E += B;
             }
+            if (a.friction_mu > 0.0) {
+                const double xp[3] = {xprev_g[3 * i], xprev_g[3 * i + 1], xprev_g[3 * i + 2]};
+                friction_terms(a, ind0, ind, xp, xi, &E, nullptr, nullptr);
+            }
         }
     }
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
@@ -581,8 +637,8 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
 // The tets are processed in chunks of one tet per thread so that the per-tet scratch (102 doubles per tet) of all CTAs
 // stays L2-resident; rows and edges accumulate their incident tets chunk by chunk, in ascending tet order (no atomics).
 __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt_g, const double* __restrict__ xprev_g,
-                          const double* __restrict__ aim_g, const FemIndenter& ind, double ratio, double* __restrict__ tsc /*[102][TC]*/,
-                          double* valg, double g3[3], double d6[6], long long* cyc)
+                          const double* __restrict__ aim_g, const FemIndenter& ind, const FemIndenter& ind0, double ratio,
+                          double* __restrict__ tsc, double* valg, double g3[3], double d6[6], long long* cyc)
 {
     long long tg0 = cyc ? clock64() : 0;
     const double dt2 = a.dt * a.dt;
@@ -706,6 +762,10 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
                     for (int b = 0; b < 3; ++b) Hk[3 * c + b] = ddB * dD[c] * dD[b] + dB * 2.0 * (n[c] * n[b] + d * Hd[3 * c + b]);
                 spd_project<3>(Hk);
                 d6[0] += Hk[0]; d6[1] += Hk[1]; d6[2] += Hk[2]; d6[3] += Hk[4]; d6[4] += Hk[5]; d6[5] += Hk[8];
+            }
+            if (a.friction_mu > 0.0) {
+                const double xp[3] = {xprev_g[3 * i], xprev_g[3 * i + 1], xprev_g[3 * i + 2]};
+                friction_terms(a, ind0, ind, xp, xi, nullptr, g3, d6);
             }
         }
     }
@@ -868,7 +928,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
 
             double g3[3], d6[6], dx[3];
             FEM_TIC();
-            grad_hess(a, s, xt_g, xpg, aim_g, ind, ratio, tsc, valg, g3, d6, (a.dbg_cycles && !a.dbg_mode) ? cyc + 3 : nullptr);
+            grad_hess(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, tsc, valg, g3, d6, (a.dbg_cycles && !a.dbg_mode) ? cyc + 3 : nullptr);
             FEM_TOC(0);
             FEM_TIC();
             pcg_total += pcg(a, s, valg, g3, d6, dx, ph, (a.dbg_cycles && a.dbg_mode) ? cyc + 3 : nullptr);
@@ -895,11 +955,11 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             }
             alpha = block_reduce<1>(alpha, s.red, ph);
             ccd_alpha = alpha;
-            const double E0 = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, nullptr, ph);
+            const double E0 = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, nullptr, ph);
             __syncthreads(); // every thread has read s.x
             if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
             __syncthreads();
-            double E = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, &min_dist, ph);
+            double E = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph);
             if (!converged) {
                 int ls = 0;
                 while (ls < a.ls_max_iter) {
@@ -908,7 +968,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                     __syncthreads();
                     if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
                     __syncthreads();
-                    E = total_energy(a, s, xt_g, xpg, aim_g, ind, ratio, &min_dist, ph);
+                    E = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph);
                     ++ls;
                     ++ls_total;
                 }

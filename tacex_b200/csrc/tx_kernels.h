@@ -95,7 +95,7 @@ struct FemArgs {
     const int* surf_of;    // [V] index into surf[] or -1
     int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
     long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
-    double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate;
+    double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate, friction_mu, eps_velocity;
     int newton_max_iter, pcg_max_iter_ratio, ls_max_iter, substep;
 };
 

@@ -37,6 +37,8 @@ class GelFemCfg:
     line_search_max_iter: int = 8
     animator_substep: int = 1
     rest_volume_det: bool = True     # reproduce libuipc's det(Dm) elastic rest "volume" 
+    friction_ratio: float = 0.5      # contact.default_friction_ratio (uipc_sim.py); 0 disables the lagged friction
+    friction_eps_velocity: float = 0.01  # contact.eps_velocity [m/s]
 
 
 def indenter_array(kind, centers, half, R=None, device="cuda") -> torch.Tensor:
@@ -76,6 +78,7 @@ class GelFemEngine:
         g.newton_max_iter, g.velocity_tol, g.pcg_tol_rate = c.newton_max_iter, c.newton_velocity_tol, c.pcg_tol_rate
         g.pcg_max_iter_ratio, g.ls_max_iter, g.substep = 2, c.line_search_max_iter, c.animator_substep
         g.rest_volume_det = int(c.rest_volume_det)
+        g.friction_mu, g.eps_velocity = c.friction_ratio, c.friction_eps_velocity
         self.g = g
         X = np.ascontiguousarray(mesh.X, np.float64)
         tets = np.ascontiguousarray(mesh.tets, np.int32)

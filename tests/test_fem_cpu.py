@@ -208,3 +208,44 @@ def test_press_keeps_gap_positive_and_is_monotone():
         tops.append(x[0][:, 2].max() - 0)  # track
     centre = np.argmin(np.abs(cf.X[:, 0]) + np.abs(cf.X[:, 1]) - cf.X[:, 2])
     assert x[0][centre, 2] < cf.X[centre, 2] - 3e-4  # the gel under the sphere moved down by > 0.3 mm
+
+
+def test_friction_terms_match_finite_differences():
+    """Lagged IPC friction of a surface vertex against the prescribed indenter (ref: ipc_vertex_half_plane_frictional_contact.cu,
+    codim_ipc_contact_function.h:16-128): gradient / Hessian vs finite differences of the energy in the static, the C1-clamped
+    and the sliding regime; zero when the vertex was outside d_hat at the start of the step; SPD Hessian."""
+    import ctypes as C
+
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh
+
+    cf = fc.CanonFem(gel_mesh.box_gel(cells=(2, 2, 1)), friction_mu=0.5, eps_velocity=0.01)
+    lib = fc.lib()
+    ind0 = fc.make_indenter(0, (0.0, 0.0, 0.0103), (3e-3, 0, 0))         # sphere 0.3 mm above the point below
+    ind1 = fc.make_indenter(0, (2e-5, -1e-5, 0.0102), (3e-3, 0, 0))       # moved during the step
+    xp = np.array([4e-4, -3e-4, 0.0070])
+    eps = cf.cfg.eps_velocity * cf.cfg.dt
+
+    def terms(x):
+        E = C.c_double()
+        G = np.zeros(3)
+        H = np.zeros(9)
+        lib.fem_friction_terms(C.byref(cf.cfg), C.byref(ind0), C.byref(ind1), fc._d(xp), fc._d(np.ascontiguousarray(x)), C.byref(E), fc._d(G), fc._d(H))
+        return E.value, G, H.reshape(3, 3)
+
+    for slip in (0.0, 0.3 * eps, 5 * eps):
+        x = xp + np.array([2e-5, -1e-5, -1e-4]) + slip * np.array([0.6, 0.8, 0.0])
+        E, G, H = terms(x)
+        assert E > 0 and np.all(np.linalg.eigvalsh(0.5 * (H + H.T)) >= -1e-9 * abs(H).max())
+        h = 1e-9
+        Gn = np.array([(terms(x + h * e)[0] - terms(x - h * e)[0]) / (2 * h) for e in np.eye(3)])
+        np.testing.assert_allclose(G, Gn, rtol=2e-5, atol=1e-7 * max(1.0, abs(G).max()))
+        if slip != 0.0:  # at zero slip the energy is only C1: the analytic Hessian is the one-sided limit
+            Hn = np.array([(terms(x + h * e)[1] - terms(x - h * e)[1]) / (2 * h) for e in np.eye(3)]).T
+            np.testing.assert_allclose(H, Hn, rtol=1e-3, atol=1e-4 * abs(H).max())
+    far = xp.copy()
+    far[2] = 0.0060  # more than d_hat away from the indenter at the start of the step: no lagged normal force
+    E = C.c_double(1.0)
+    G = np.ones(3)
+    lib.fem_friction_terms(C.byref(cf.cfg), C.byref(ind0), C.byref(ind1), fc._d(far), fc._d(far + 1e-4), C.byref(E), fc._d(G), None)
+    assert E.value == 0.0 and not G.any()

@@ -75,6 +75,44 @@ def test_press_30_steps_matches_cpu_restatement(kind, half):
     assert float((x[0] - eng.X).abs().max()) > 3e-4  # the gel really deformed
 
 
+def test_friction_shear_matches_cpu_restatement():
+    """Lagged IPC friction (default ratio 0.5): a sphere is pressed 0.6 mm into the gel, then dragged sideways. GPU and CPU
+    restatement agree step by step, and the dragged gel surface follows the indenter measurably more than without friction."""
+    from oracle import fem_canon as fc
+    from tacex_b200 import fem, gel_mesh
+
+    m = gel_mesh.box_gel()
+    eng = fem.GelFemEngine(m, fem.GelFemCfg(newton_velocity_tol=1e-3))
+    eng0 = fem.GelFemEngine(m, fem.GelFemCfg(newton_velocity_tol=1e-3, friction_ratio=0.0))
+    cf = fc.CanonFem(m, velocity_tol=1e-3)
+    r = 3e-3
+    z0 = 4.5e-3 + r + 4e-4
+
+    def ctr(s):  # 12 steps down, then 10 steps sideways (0.1 mm per step)
+        return [[0.0, 0.0, z0 - 1e-3 * min(s, 12) / 12]] if s <= 12 else [[1e-4 * (s - 12), 0.0, z0 - 1e-3]]
+
+    x, v, xp = eng.new_state(1)
+    x0, v0, xp0 = eng0.new_state(1)
+    xc, vc, xpc = cf.new_state(1)
+    aim, aimc = eng.rest_aim(1), cf.X[cf.attach][None]
+    worst = 0.0
+    for s in range(22):
+        a, b = fem.indenter_array(0, ctr(s), (r, 0, 0)), fem.indenter_array(0, ctr(s + 1), (r, 0, 0))
+        st = eng.step(x, v, xp, aim, a, b)
+        eng0.step(x0, v0, xp0, aim, a, b)
+        cst = cf.step(xc, vc, xpc, aimc, [fc.make_indenter(0, ctr(s)[0], (r, 0, 0))], [fc.make_indenter(0, ctr(s + 1)[0], (r, 0, 0))])
+        torch.cuda.synchronize()
+        worst = max(worst, np.abs(x.cpu().numpy() - xc).max())
+        assert eng.decode_stats(st)[0]["newton_iters"] == cst[0]["newton_iters"], s
+    print(f"friction shear: max |x_gpu - x_cpu| over 22 steps = {worst:.3e} m")
+    assert worst <= 1e-5
+    top = np.asarray(m.surf)
+    drag = float((x[0, top, 0] - eng.X[top, 0]).max())
+    drag0 = float((x0[0, top, 0] - eng0.X[top, 0]).max())
+    print(f"max surface drag in x: {drag:.3e} m with friction, {drag0:.3e} m without")
+    assert drag > drag0 + 2e-5
+
+
 def test_marker_readout_projection():
     from tacex_b200 import fem, gel_mesh
 
