@@ -30,6 +30,7 @@ FRAME_OUT_BYTES = H * W * 3 * 4       # float32 NHWC RGB
 MARKER_ROWS, MARKER_COLS = 7, 9       # 63 markers (BASELINE.json north_star; the reference default 11x9 is parity-tested)
 M = MARKER_ROWS * MARKER_COLS
 ALGO_BYTES_PER_FRAME = FRAME_IN_BYTES + FRAME_OUT_BYTES  # 1,228,800 B
+ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None  # before any NUMA binding
 METRIC = "tactile frames/sec (320x240 RGB+markers) @4096 envs, 1/2/4/8 B200"
 
 
@@ -69,6 +70,30 @@ class ClockSampler(threading.Thread):
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
                 "samples": len(self.samples)}
+
+
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Runs this rank on the CPU cores of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first touch), so that the end-to-end H2D / D2H copies do not cross the socket interconnect. Best effort."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+        return f"numa node {node} (no allowed cpu)"
+    except Exception as exc:
+        return f"numa: unbound ({type(exc).__name__})"
 
 
 def cpu_port_fps(n_frames: int, with_markers: bool = True) -> tuple[float, int, str]:
@@ -218,7 +243,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "none"], help="N>1: all-gather of the RGB observation")
+    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "nccl", "none"],
+                    help="N>1: float32 all-gather of the RGB observation: fp32 = NVLink peer copies into symmetric memory "
+                         "(falls back to NCCL), nccl = all_gather_into_tensor, none = observations stay sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fem", action="store_true", help="skip the extra gel-FEM measurement (config 3)")
     args = ap.parse_args()
@@ -232,7 +259,7 @@ def main() -> None:
     from tacex_b200 import synth
     from tacex_b200.calib import TaximTables
     from tacex_b200.engine import TactileEngine
-    from tacex_b200.shard import all_gather_obs
+    from tacex_b200.shard import PeerObsGather, all_gather_obs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -240,6 +267,7 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -259,10 +287,21 @@ def main() -> None:
     traj0 = torch.zeros((E, 4), device=dev)
     traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
     # N > 1: the observation all-gather of step t runs on a side stream while step t+1 computes (double-buffered RGB)
-    do_gather = world > 1 and args.obs_gather == "fp32"
+    do_gather = world > 1 and args.obs_gather in ("fp32", "nccl")
     rgb_buf = [rgb, torch.empty_like(rgb)] if do_gather else [rgb]
-    gathered = [torch.empty((world * E, H, W, 3), device=dev) for _ in range(2)] if do_gather else None
-    side = torch.cuda.Stream(device=dev) if do_gather else None
+    peer, gathered, gather_kind = None, None, "n/a"
+    if do_gather:
+        if args.obs_gather == "fp32":
+            try:
+                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2)
+                rgb_buf = [peer.local_block(0), peer.local_block(1)]  # the kernel renders straight into the gathered buffer
+                gather_kind = "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step"
+            except Exception as exc:  # symmetric memory unavailable on this box
+                print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+        if peer is None:
+            gathered = [torch.empty((world * E, H, W, 3), device=dev) for _ in range(2)]
+            gather_kind = "float32 NCCL all_gather_into_tensor of RGB, overlapped with the next step on a side stream"
+    side = torch.cuda.Stream(device=dev, priority=-1) if do_gather else None
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
     ev_free = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0}
@@ -278,7 +317,10 @@ def main() -> None:
             ev_done[i].record()
             with torch.cuda.stream(side):
                 side.wait_event(ev_done[i])
-                all_gather_obs(rgb_buf[i], gathered[i])
+                if peer is not None:
+                    peer.gather(rgb_buf[i], i)
+                else:
+                    all_gather_obs(rgb_buf[i], gathered[i])
                 ev_free[i].record()
 
     def barrier():
@@ -360,18 +402,20 @@ def main() -> None:
                             f"(config-1 distribution, 10% no contact); the optional gel FEM substep (config 3) is reported separately under fem_gel_substep",
                 "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"dp{world} (contiguous env shards)",
                 "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2)",
-                "obs_gather": ((args.obs_gather + " all-gather of RGB, overlapped with the next step on a side stream") if world > 1 else "n/a"),
+                "obs_gather": (gather_kind if do_gather else ("none (observations stay sharded)" if world > 1 else "n/a")),
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": "taxim_fused_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * E,
                          "peak_source": peak_src,
                          "note": "FP32-FMA bound (exact separable pyramid, 266 MAC/px): see DESIGN.md section 5"},
             "e2e": {"value": world * E / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": E * (FRAME_IN_BYTES + 4),
-                    "d2h_bytes_per_step": E * (FRAME_OUT_BYTES + 4 + M * 16), "api": "tx_step_host (C ABI, pinned host buffers)"},
+                    "d2h_bytes_per_step": E * (FRAME_OUT_BYTES + 4 + M * 16), "api": "tx_step_host (C ABI, pinned host buffers)", "host_binding": numa},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
+            if ALL_CPUS:
+                os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host thread, not just the GPU's NUMA node
             fps, cores, sample = cpu_port_fps(256)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         if fem_extra is not None:
