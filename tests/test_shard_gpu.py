@@ -1,0 +1,54 @@
+"""Multi-GPU test (needs >= 2 CUDA devices; skipped on a one-GPU box): the observation all-gather by NVLink peer copies into
+symmetric memory delivers, on every rank, exactly what a single process renders for all envs (shard invariance, bit for bit)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tacex_b200 import synth
+    from tacex_b200.calib import TaximTables
+    from tacex_b200.engine import TactileEngine
+    from tacex_b200.shard import PeerObsGather, env_shard
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    t = TaximTables.load(os.path.join(root, "tests", "golden", "gsmini_tables_320x240.npz"))
+    n = 8
+    hm = synth.height_map_mm(synth.config1(n, seed=5)["depth_m"])
+    a, b = env_shard(n, rank, world)
+    eng = TactileEngine(t, max_envs=n, device=f"cuda:{rank}")
+    g = PeerObsGather((b - a, 240, 320, 3), torch.float32, torch.device("cuda", rank), n_slots=2)
+    ok = True
+    for step in range(3):  # both slots, slot reuse
+        slot = step & 1
+        eng.render(hm[a:b].cuda(rank).contiguous(), None, out=g.local_block(slot))
+        full = g.gather(g.local_block(slot), slot)
+        ref = eng.render(hm.cuda(rank).contiguous(), None)
+        torch.cuda.synchronize()
+        ok = ok and torch.equal(full, ref)
+    q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_copy_all_gather_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    oks = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(oks) and all(p.exitcode == 0 for p in procs)
