@@ -64,57 +64,70 @@ int taxim_smem_bytes() { return SM_TOTAL; }
 // Lane i owns virtual columns v = 12*i + j - 32 (j = 0..11); virtual columns outside [0, 320) hold the reflected
 // pixels (torch 'reflect'), so the correlation is uniform over the warp. PUSH: also store the result row into the
 // peer CTA's halo buffer (row index = distance from the CTA boundary).
+// Only the rows [la, lb] (local) can hold non-zero values (exact zeros elsewhere: a blur of zeros is +0.0f bit for bit),
+// so only they are processed, interleaved over the warps; skipped rows inside the push range send zeros to the peer.
+// LPR = lanes per row. 32: the warp holds the whole row (384 virtual columns incl. the reflected ones). 16: the non-zero
+// columns [c0, c1] of the level's input, the blur radius on both sides and the alignment slack fit into 192 columns that do
+// not reach the reflected border, so every warp processes TWO rows at once (one per half warp) on the window that starts at
+// column `vbase`; the lanes wrap around inside their half, and everything a wrapped tap can reach is exactly zero, so the
+// result is bit-identical to the full-width evaluation (same tap order, zero terms leave the accumulator unchanged).
+template <int LPR>
 __device__ __forceinline__ void load_row12(const float* rp, int v0, bool interior, float (&x)[12])
 {
-    if (interior) { // lanes 3..28: three aligned 128-bit loads (conflict-free within each quarter warp)
+    if (interior) { // three aligned 128-bit loads (conflict-free within each quarter warp)
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
             const float4 t = *reinterpret_cast<const float4*>(rp + v0 + 4 * e);
             x[4 * e + 0] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
         }
-    } else { // the six edge lanes hold the reflected columns
+    } else if (LPR == 32) { // the six edge lanes hold the reflected columns
 #pragma unroll
         for (int j = 0; j < 12; ++j) {
             int v = v0 + j;
             v = v < 0 ? -v : (v > IMG_W - 1 ? 2 * (IMG_W - 1) - v : v);
             x[j] = rp[v];
         }
+    } else { // window past the end of the row: those columns only feed outputs that are never stored
+#pragma unroll
+        for (int j = 0; j < 12; ++j) x[j] = (v0 + j >= 0 && v0 + j < IMG_W) ? rp[v0 + j] : 0.0f;
     }
 }
 
-// Only the rows [la, lb] (local) can hold non-zero values (exact zeros elsewhere: a blur of zeros is +0.0f bit for bit),
-// so only they are processed, interleaved over the warps; skipped rows inside the push range send zeros to the peer.
-template <int L, int RAD>
-__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, int warp, int lane, unsigned q, int la, int lb)
+template <int L, int RAD, int LPR>
+__device__ __forceinline__ void hpass_rows(float* plane, float* hb_remote, int warp, int lane, unsigned q, int la, int lb, int vbase)
 {
     constexpr int D = (RAD + 11) / 12;
-    const int v0 = 12 * lane - 32;
-    const bool interior = (lane >= 3) && (lane <= 28);
-    // zero halo rows for the skipped rows of the push range (the halo buffers are reused across levels)
-    for (int i = tid; i < RAD * (IMG_W / 4); i += NTHREADS) {
-        const int dist = i / (IMG_W / 4);
-        const int row = q == 0 ? (HALF_H - 1 - dist) : dist;
-        if (row < la || row > lb)
-            reinterpret_cast<float4*>(hb_remote + dist * IMG_W)[i - dist * (IMG_W / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    constexpr int RPW = 32 / LPR; // rows per warp
+    const int sub = lane & (LPR - 1), half = lane / LPR;
+    const int v0 = vbase + 12 * sub;
+    const bool interior = LPR == 32 ? (lane >= 3) && (lane <= 28) : (v0 >= 0 && v0 + 11 < IMG_W);
     const int nact = lb - la + 1;
-    if (warp >= nact) return;
+    const int ngrp = (nact + RPW - 1) / RPW; // groups of RPW consecutive rows
+    if (warp >= ngrp) return;
     float xn[12];
-    load_row12(plane + (la + warp) * IMG_W, v0, interior, xn);
+    {
+        const int r0 = min(la + warp * RPW + half, lb);
+        load_row12<LPR>(plane + r0 * IMG_W, v0, interior, xn);
+    }
 #pragma unroll 1
-    for (int k = warp; k < nact; k += NWARPS) {
-        const int row = la + k;
+    for (int k = warp; k < ngrp; k += NWARPS) {
+        const int rowu = la + k * RPW + half;
+        const bool rvalid = rowu <= lb;
+        const int row = min(rowu, lb);
         float* rp = plane + row * IMG_W;
         float x[12], acc[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) { x[j] = xn[j]; acc[j] = 0.0f; }
-        if (k + NWARPS < nact) load_row12(rp + NWARPS * IMG_W, v0, interior, xn); // prefetch this warp's next row
+        if (k + NWARPS < ngrp) { // prefetch this warp's next row(s)
+            const int rn = min(la + (k + NWARPS) * RPW + half, lb);
+            load_row12<LPR>(plane + rn * IMG_W, v0, interior, xn);
+        }
 #pragma unroll
         for (int d = -D; d <= D; ++d) {
 #pragma unroll
             for (int j = 0; j < 12; ++j) {
                 if (12 * d + j >= -RAD && 12 * d + j - 11 <= RAD) {
-                    const float y = (d == 0) ? x[j] : __shfl_sync(0xffffffffu, x[j], (lane + d) & 31);
+                    const float y = (d == 0) ? x[j] : __shfl_sync(0xffffffffu, x[j], ((lane + d) & (LPR - 1)) | (lane & ~(LPR - 1)));
 #pragma unroll
                     for (int m = 0; m < 12; ++m) {
                         const int kk = 12 * d + j - m;
@@ -126,16 +139,39 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, i
         // the shuffles above are warp-synchronous: every lane has consumed the old row before anyone overwrites it
         const int dist = q == 0 ? (HALF_H - 1 - row) : row; // distance from the CTA boundary
         const bool push = dist < RAD;
+        if (rvalid) {
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int vb = v0 + 4 * e;
-            if (vb >= 0 && vb <= IMG_W - 4) {
-                const float4 t = make_float4(acc[4 * e + 0], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
-                *reinterpret_cast<float4*>(rp + vb) = t;
-                if (push) *reinterpret_cast<float4*>(hb_remote + dist * IMG_W + vb) = t;
+            for (int e = 0; e < 3; ++e) {
+                const int vb = v0 + 4 * e;
+                if (vb >= 0 && vb <= IMG_W - 4) {
+                    const float4 t = make_float4(acc[4 * e + 0], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+                    *reinterpret_cast<float4*>(rp + vb) = t;
+                    if (push) *reinterpret_cast<float4*>(hb_remote + dist * IMG_W + vb) = t;
+                }
             }
         }
     }
+}
+
+// c0 / c1: non-zero columns of the level's input (image coordinates)
+template <int L, int RAD>
+__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, int warp, int lane, unsigned q, int la, int lb,
+                                      int c0, int c1)
+{
+    // zero halo rows for the skipped rows of the push range (the halo buffers are reused across levels)
+    for (int i = tid; i < RAD * (IMG_W / 4); i += NTHREADS) {
+        const int dist = i / (IMG_W / 4);
+        const int row = q == 0 ? (HALF_H - 1 - dist) : dist;
+        if (row < la || row > lb)
+            reinterpret_cast<float4*>(hb_remote + dist * IMG_W)[i - dist * (IMG_W / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // Halo rows written by the narrow variant keep stale columns outside the window; the vertical pass of this level only
+    // reads the columns [c0 - RAD, c1 + RAD], which the window covers.
+    const bool narrow = c0 > RAD && c1 < IMG_W - 1 - RAD && (c1 - c0 + 1) + 2 * RAD + 8 <= 192;
+    if (narrow)
+        hpass_rows<L, RAD, 16>(plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
+    else
+        hpass_rows<L, RAD, 32>(plane, hb_remote, warp, lane, q, la, lb, -32);
 }
 
 // ---- vertical pass: thread per column, sliding register window, in place --------------------------------------
@@ -273,7 +309,7 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
                                            cg::cluster_group& cluster, long long* tk, float depth_clip, FlatCopy& fc)
 {
     const int base = (int)q * HALF_H;
-    hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1));
+    hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1), rg.c0, rg.c1);
     TX_TICK(4 + 4 * L + 0);
     cluster.sync(); // rows + pushed halo rows visible in both CTAs
     TX_TICK(4 + 4 * L + 1);
