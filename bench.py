@@ -243,9 +243,12 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "nccl", "none"],
-                    help="N>1: float32 all-gather of the RGB observation: fp32 = NVLink peer copies into symmetric memory "
-                         "(falls back to NCCL), nccl = all_gather_into_tensor, none = observations stay sharded")
+    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "fp32-rect", "fp32-ce", "nccl", "none"],
+                    help="N>1: float32 all-gather of the RGB observation into symmetric memory (falls back to NCCL). "
+                         "fp32-rect = NVLink peer stores of the non-flat rectangle of every frame + local completion from the flat "
+                         "image (bit-identical to gathering whole frames, about half the link bytes); fp32-ce = whole frames by "
+                         "copy-engine peer copies (no SM used); fp32 = fp32-ce for 2 GPUs (one peer: the link is not the limit), "
+                         "fp32-rect beyond; nccl = all_gather_into_tensor; none = observations stay sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fem", action="store_true", help="skip the extra gel-FEM measurement (config 3)")
     args = ap.parse_args()
@@ -287,15 +290,19 @@ def main() -> None:
     traj0 = torch.zeros((E, 4), device=dev)
     traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
     # N > 1: the observation all-gather of step t runs on a side stream while step t+1 computes (double-buffered RGB)
-    do_gather = world > 1 and args.obs_gather in ("fp32", "nccl")
+    do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl")
+    use_rects = args.obs_gather == "fp32-rect" or (args.obs_gather == "fp32" and world > 2)
     rgb_buf = [rgb, torch.empty_like(rgb)] if do_gather else [rgb]
     peer, gathered, gather_kind = None, None, "n/a"
     if do_gather:
-        if args.obs_gather == "fp32":
+        if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
             try:
-                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2)
+                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=use_rects)
                 rgb_buf = [peer.local_block(0), peer.local_block(1)]  # the kernel renders straight into the gathered buffer
-                gather_kind = "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step"
+                gather_kind = ("float32 all-gather of RGB, bit-identical to gathering whole frames: NVLink peer stores of every frame's "
+                               "non-flat rectangle into symmetric memory + local completion from the flat image, overlapped with the next step"
+                               if use_rects else
+                               "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step")
             except Exception as exc:  # symmetric memory unavailable on this box
                 print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
         if peer is None:
@@ -311,13 +318,17 @@ def main() -> None:
         state["i"] += 1
         if do_gather:
             torch.cuda.current_stream().wait_event(ev_free[i])  # the gather that read this buffer two steps ago is done
+        if peer is not None and use_rects:
+            eng.set_rect_output(peer.local_rects(i))
         eng.render(hm, None, out=rgb_buf[i], depth_out=depth)
         eng.fots_markers(depth, theta, traj0, traj_len, out=markers)
         if do_gather:
             ev_done[i].record()
             with torch.cuda.stream(side):
                 side.wait_event(ev_done[i])
-                if peer is not None:
+                if peer is not None and use_rects:
+                    peer.gather_rects(eng, i, side)
+                elif peer is not None:
                     peer.gather(rgb_buf[i], i)
                 else:
                     all_gather_obs(rgb_buf[i], gathered[i])
@@ -351,6 +362,7 @@ def main() -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    eng.set_rect_output(None)
     for _ in range(K):
         eng.render(hm, None, out=rgb, depth_out=depth)
     e1.record()

@@ -132,6 +132,22 @@ int tx_set_camera_resolution(tx_handle* h, int Hc, int Wc);
 int tx_render_camera(tx_handle* h, const float* frames, int is_depth, float clip_max_m, const float* press_mm, int N,
                      float* rgb, float* depth_out, float* deformed, uint8_t* mask);
 
+/* ---- multi-GPU: the single observation all-gather (the reference makes no collective call) ----------
+ * A frame differs from the flat image only inside a rectangle per half frame. tx_set_rect_output makes the following
+ * tx_render* calls record it: rect [N][2][4] int32 = (first row, last row -- local to the half --, first column, last column),
+ * last < first when empty. tx_obs_push (on `cuda_stream`, e.g. a side stream) stores the pixels of this rank's rectangles and
+ * the descriptors into the same block of every peer's gathered buffer: peer_rgb / peer_rect are HOST arrays of n_peers
+ * peer-mapped DEVICE pointers (symmetric memory, NVLink peer-to-peer stores). After a cross-rank barrier tx_obs_fill completes
+ * this rank's gathered buffer rgb_all [N_total][H][W][3]: everything outside the rectangles of the envs NOT in
+ * [skip_lo, skip_hi) (this rank's own, rendered in place) is copied from the flat image. prev_rect [N_total][2][4] (optional,
+ * inout, one per gathered buffer, initialised to (0, H/2-1, 0, W-1) per half) remembers what the buffer held after its last
+ * fill, so that only the part of the old rectangle the new one does not cover is restored. Result == gathering whole frames. */
+int tx_set_rect_output(tx_handle* h, int32_t* rect);
+int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* rect_local, int N, int n_peers, float* const* peer_rgb,
+                int32_t* const* peer_rect, void* cuda_stream);
+int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* prev_rect, int N_total, int skip_lo, int skip_hi,
+                void* cuda_stream);
+
 /* Replaces FOTSMarkerSimulator.marker_motion_simulation + MarkerMotion.marker_sim
  * (ref: .../fots/fots_marker_sim.py:114-184, .../fots/sim/marker_motion.py:78-120,144-219) using the gel
  * deformation recorded by the preceding tx_render of the SAME batch (no second blur pyramid).

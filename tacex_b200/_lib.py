@@ -66,7 +66,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
+    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers", "tx_fem_debug_set_cycles",
 ]
@@ -97,6 +97,11 @@ def load() -> C.CDLL:
     lib.tx_set_camera_resolution.restype = C.c_int
     lib.tx_render_camera.argtypes = [C.c_void_p, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, fp, u8p]
     lib.tx_render_camera.restype = C.c_int
+    lib.tx_set_rect_output.argtypes = [C.c_void_p, vp]
+    lib.tx_obs_push.argtypes = [C.c_void_p, fp, ip, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp]
+    lib.tx_obs_fill.argtypes = [C.c_void_p, fp, ip, ip, C.c_int, C.c_int, C.c_int, vp]
+    for name in ("tx_set_rect_output", "tx_obs_push", "tx_obs_fill"):
+        getattr(lib, name).restype = C.c_int
     lib.tx_render_depth.restype = C.c_int
     lib.tx_fots_markers.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, ip, fp]
     lib.tx_marker_grid.argtypes = [C.c_void_p, ip, ip]
@@ -118,7 +123,7 @@ def load() -> C.CDLL:
     lib.tx_fem_debug_set_cycles.restype = C.c_int
     for name in ("tx_fem_create", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers", "tx_fem_markers"):
         getattr(lib, name).restype = C.c_int
-    for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_fots_markers",
+    for name in ("tx_get_counters", "tx_upload_tables", "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_fots_markers",
                  "tx_marker_grid", "tx_step_host"):
         getattr(lib, name).restype = C.c_int
     _lib = lib

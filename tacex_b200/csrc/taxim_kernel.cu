@@ -625,6 +625,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         const int nq_ = fc.xb >= fc.xa ? (fc.xb - fc.xa + 1) >> 2 : 0;
         fc.total = fc.ry1 >= fc.ry0 ? nq_ * (fc.ry1 - fc.ry0 + 1) : 0;
     }
+    if (p.rect_out && tid == 0)
+        reinterpret_cast<int4*>(p.rect_out)[blockIdx.x] = fc.total > 0 ? make_int4(fc.ry0, fc.ry1, fc.xa, fc.xb) : make_int4(0, -1, 0, -1);
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     if (active) {
@@ -695,6 +697,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     (void)nq; (void)QPR;
     const int nw = xb >= xa ? xb - xa + 1 : 0;   // rectangle width in pixels
     const int npx = total * 4;                   // pixels of the rectangle in this half
+    const float inv_nw = nw > 0 ? 1.0f / (float)nw : 0.0f;
     const int rec_of = lane / 5;                 // idx = e * 32 + lane: record (idx / 5), part (idx % 5), precomputed per e
     int bin_next = 0, row_n = 0, x_n = 0;
     float4 rec[5];
@@ -708,7 +711,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     }
     (void)rec_of;
     auto pixel_bin = [&](int pidx, int& row, int& x) -> int {
-        const int rr = pidx / nw;
+        const int rr = __float2int_rz(__fmul_rn((float)pidx + 0.5f, inv_nw)); // == pidx / nw (pidx < 2^16, error << 0.5 / nw)
         row = ry0 + rr;
         x = xa + (pidx - rr * nw);
         const int gy_ = (int)q * HALF_H + row; // image row

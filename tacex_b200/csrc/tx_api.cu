@@ -51,6 +51,8 @@ struct tx_handle {
     int *d_rs_x0 = nullptr, *d_rs_y0 = nullptr;
     float2 *d_rs_wx = nullptr, *d_rs_wy = nullptr;
     float* d_up = nullptr;
+    int* d_rect = nullptr; // not owned: tx_set_rect_output
+    int n_sm = 148;
 };
 
 static std::string g_create_err;
@@ -116,6 +118,7 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
     h->device = device;
     h->stream = (cudaStream_t)cuda_stream;
     h->M = M;
+    h->n_sm = prop.multiProcessorCount;
 #define TX_CUDA_C(expr)                                                                                               \
     do {                                                                                                              \
         cudaError_t _e = (expr);                                                                                      \
@@ -381,10 +384,59 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     }
     a.ticks = h->d_ticks;
     a.dbg = h->dbg;
+    a.rect_out = h->d_rect;
     TX_CUDA(h, launch_taxim(a, N, h->stream));
     h->aux_valid_n = h->M > 0 ? N : 0;
     h->ctr.render_calls++;
     h->ctr.frames_rendered += (uint64_t)N;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_set_rect_output(tx_handle* h, int32_t* rect)
+{
+    if (!h) return TX_ERR_INVALID_ARG;
+    if (rect && ((uintptr_t)rect & 15u)) return fail(h, TX_ERR_INVALID_ARG, "tx_set_rect_output: buffer must be 16-byte aligned");
+    h->d_rect = rect;
+    return TX_OK;
+}
+
+extern "C" int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* rect_local, int N, int n_peers,
+                           float* const* peer_rgb, int32_t* const* peer_rect, void* cuda_stream)
+{
+    if (!h || !rgb_local || !rect_local || N < 0 || n_peers < 0 || n_peers > TX_MAX_PEERS || (n_peers > 0 && (!peer_rgb || !peer_rect)))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_obs_push: bad argument");
+    if (N == 0 || n_peers == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    ObsPushArgs a{};
+    a.rgb_local = rgb_local; a.rect_local = rect_local; a.N = N; a.n_peers = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_rgb[p] || !peer_rect[p]) return fail(h, TX_ERR_INVALID_ARG, "tx_obs_push: null peer pointer");
+        a.peer_rgb[p] = peer_rgb[p];
+        a.peer_rect[p] = peer_rect[p];
+    }
+    // The stores are posted writes bounded by the NVLink egress (900 GB/s per direction), not by the SMs: a few dozen CTAs keep
+    // the links busy, and every SM that hosts one is lost to the render kernel of the next step (its 128-register threads leave
+    // no room for a second CTA), so the grid stays small. TX_OBS_PUSH_CTAS overrides it for experiments.
+    int cap = 32;
+    if (const char* e = getenv("TX_OBS_PUSH_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
+    const int grid = 2 * N < cap ? 2 * N : cap;
+    TX_CUDA(h, launch_obs_push(a, grid, (cudaStream_t)cuda_stream));
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* prev_rect, int N_total, int skip_lo,
+                           int skip_hi, void* cuda_stream)
+{
+    if (!h || !rgb_all || !rect_all || N_total < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_obs_fill: bad argument");
+    if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_obs_fill: call tx_upload_tables first");
+    if (N_total == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    ObsFillArgs a{};
+    a.rgb_all = rgb_all; a.rect_all = rect_all; a.prev_rect = prev_rect; a.flat_rgb = h->d_flat; a.N_total = N_total; a.skip_lo = skip_lo; a.skip_hi = skip_hi;
+    const int grid = 2 * N_total < 8 * h->n_sm ? 2 * N_total : 8 * h->n_sm;
+    TX_CUDA(h, launch_obs_fill(a, grid, (cudaStream_t)cuda_stream));
     h->ctr.kernels_launched++;
     return TX_OK;
 }

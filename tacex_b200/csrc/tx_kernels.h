@@ -33,6 +33,8 @@ struct TaximArgs {
     const float* bg_hwc;   // [240][320][3]
     const float* flat_rgb; // [240][320][3] RGB of a flat (zero-gradient) pixel: clip(poly(bin(0, 0)) + background)
     float* rgb;            // [N][240][320][3]
+    int* rect_out;         // optional [N][2][4]: per half frame the rectangle (ry0, ry1 local rows, xa, xb columns) outside of
+                           // which the frame equals the flat RGB image (empty: ry1 < ry0); used by the multi-GPU gather
     float* depth_out;      // [N] or nullptr
     float* deformed_out;   // [N][240][320] or nullptr
     unsigned char* mask_out; // [N][240][320] or nullptr
@@ -48,6 +50,22 @@ struct TaximArgs {
     int nb;
     int dbg;          // profiling experiments only (0 in production): bit0 skip RGB stores, bit1 skip bg loads, bit2 force flat path
     long long* ticks; // optional [2N][40] phase clock stamps (profiling builds of the host call only)
+};
+
+constexpr int TX_MAX_PEERS = 15;
+struct ObsPushArgs {
+    const float* rgb_local;  // [N][240][320][3] this rank's frames
+    const int* rect_local;   // [N][2][4]
+    int N, n_peers;
+    float* peer_rgb[TX_MAX_PEERS];  // the same block inside every peer's gathered buffer (peer-mapped addresses)
+    int* peer_rect[TX_MAX_PEERS];
+};
+struct ObsFillArgs {
+    float* rgb_all;          // [N_total][240][320][3] this rank's gathered buffer
+    const int* rect_all;     // [N_total][2][4]
+    int* prev_rect;          // optional [N_total][2][4] inout: the rectangles this buffer held after its last fill
+    const float* flat_rgb;   // [240][320][3]
+    int N_total, skip_lo, skip_hi; // envs [skip_lo, skip_hi) are this rank's own
 };
 
 struct FotsArgs {
@@ -122,5 +140,7 @@ cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
 cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);
 cudaError_t launch_fots(const FotsArgs& a, int N, cudaStream_t s);
+cudaError_t launch_obs_push(const ObsPushArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_obs_fill(const ObsFillArgs& a, int grid, cudaStream_t s);
 
 } // namespace tx

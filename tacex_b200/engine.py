@@ -171,6 +171,27 @@ class TactileEngine:
                                               _ptr(out), _ptr(depth_out), _ptr(deformed_out), _ptr(mask_out)))
         return out
 
+    # -- multi-GPU observation gather ----------------------------------------------------------------------
+    def set_rect_output(self, rect: torch.Tensor | None) -> None:
+        """int32 (N, 2, 4) device tensor that the following renders fill with the per-half non-flat rectangle, or None."""
+        self._check(self.lib.tx_set_rect_output(self.h, _ptr(rect)))
+
+    def obs_push(self, rgb_local: torch.Tensor, rect_local: torch.Tensor, peer_rgb: list, peer_rect: list, stream) -> None:
+        import ctypes as C
+
+        n = len(peer_rgb)
+        pr = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_rgb])
+        pd = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_rect])
+        self._check(self.lib.tx_obs_push(self.h, _ptr(rgb_local), _ptr(rect_local), rgb_local.shape[0], n, pr, pd,
+                                         C.c_void_p(stream.cuda_stream)))
+
+    def obs_fill(self, rgb_all: torch.Tensor, rect_all: torch.Tensor, prev_rect: torch.Tensor | None, skip_lo: int, skip_hi: int,
+                 stream) -> None:
+        import ctypes as C
+
+        self._check(self.lib.tx_obs_fill(self.h, _ptr(rgb_all), _ptr(rect_all), _ptr(prev_rect), rgb_all.shape[0], int(skip_lo),
+                                         int(skip_hi), C.c_void_p(stream.cuda_stream)))
+
     def fots_markers(self, press: torch.Tensor, theta: torch.Tensor, traj0: torch.Tensor, traj_len: torch.Tensor,
                      out: torch.Tensor | None = None) -> torch.Tensor:
         N = press.shape[0]

@@ -39,19 +39,51 @@ class PeerObsGather:
     (2) everybody's pushes have landed. All calls are stream-ordered on the current stream; nothing synchronises the host.
     """
 
-    def __init__(self, local_shape, dtype, device, n_slots: int = 2):
+    def __init__(self, local_shape, dtype, device, n_slots: int = 2, with_rects: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.E = int(local_shape[0])
         full = (self.world * self.E,) + tuple(local_shape[1:])
         self.bufs, self.hdls, self.views = [], [], []
+        self.rects, self.rect_views, self.prev_rects = [], [], []
         for _ in range(n_slots):
             t = symm_mem.empty(full, dtype=dtype, device=device)
             h = symm_mem.rendezvous(t, dist.group.WORLD)
             self.bufs.append(t)
             self.hdls.append(h)
             self.views.append([h.get_buffer(p, full, dtype) for p in range(self.world)])
+            if with_rects:  # per half frame: the rectangle outside of which the frame equals the flat image
+                rshape = (self.world * self.E, 2, 4)
+                r = symm_mem.empty(rshape, dtype=torch.int32, device=device)
+                rh = symm_mem.rendezvous(r, dist.group.WORLD)
+                r.zero_()
+                self.rects.append(r)
+                self.rect_views.append([rh.get_buffer(p, rshape, torch.int32) for p in range(self.world)])
+                # what the buffer holds after its last fill (local): starts as "anything anywhere" = the whole half frame
+                hh, ww = int(local_shape[1]) // 2, int(local_shape[2])
+                self.prev_rects.append(torch.tensor([0, hh - 1, 0, ww - 1], dtype=torch.int32, device=device).repeat(rshape[0], 2, 1).contiguous())
+
+    def local_rects(self, slot: int) -> torch.Tensor:
+        lo = self.rank * self.E
+        return self.rects[slot][lo:lo + self.E]
+
+    def gather_rects(self, engine, slot: int, stream) -> torch.Tensor:
+        """The same all-gather with the link traffic reduced to the pixels that carry information: the frames of
+        ``local_block(slot)`` were rendered with ``engine.set_rect_output(local_rects(slot))``; their rectangles (and the
+        16-byte descriptors) are stored into every peer's buffer by one kernel (NVLink peer-to-peer stores), and after the
+        barrier every rank completes the remote envs of its own buffer from its flat image (only where the rectangle of the
+        previous fill of this slot is not covered by the new one). Bit-identical to ``gather``. ``stream`` must be the
+        current stream (the barriers are enqueued on it)."""
+        h, lo = self.hdls[slot], self.rank * self.E
+        peers = [(self.rank + k) % self.world for k in range(1, self.world)]
+        h.barrier(channel=0)  # every rank is done reading the previous content of this slot
+        engine.obs_push(self.local_block(slot), self.local_rects(slot),
+                        [self.views[slot][p][lo:lo + self.E] for p in peers],
+                        [self.rect_views[slot][p][lo:lo + self.E] for p in peers], stream)
+        h.barrier(channel=1)  # every rank's pushes into this slot have landed
+        engine.obs_fill(self.bufs[slot], self.rects[slot], self.prev_rects[slot], lo, lo + self.E, stream)
+        return self.bufs[slot]
 
     def local_block(self, slot: int) -> torch.Tensor:
         """This rank's block of its own gathered buffer: render straight into it and the self-copy disappears."""

@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode="copy"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -25,13 +25,29 @@ def _worker(rank, world, port, q):
     hm = synth.height_map_mm(synth.config1(n, seed=5)["depth_m"])
     a, b = env_shard(n, rank, world)
     eng = TactileEngine(t, max_envs=n, device=f"cuda:{rank}")
-    g = PeerObsGather((b - a, 240, 320, 3), torch.float32, torch.device("cuda", rank), n_slots=2)
+    g = PeerObsGather((b - a, 240, 320, 3), torch.float32, torch.device("cuda", rank), n_slots=2, with_rects=mode == "rects")
     ok = True
-    for step in range(3):  # both slots, slot reuse
+    if mode == "rects":
+        for buf in g.bufs:
+            buf.fill_(float("nan"))  # the first fill of a slot has to write every pixel outside the rectangles
+        torch.cuda.synchronize()
+        dist.barrier()
+    for step in range(5):  # both slots, slot reuse; in rectangle mode the contacts move between the steps
         slot = step & 1
-        eng.render(hm[a:b].cuda(rank).contiguous(), None, out=g.local_block(slot))
-        full = g.gather(g.local_block(slot), slot)
-        ref = eng.render(hm.cuda(rank).contiguous(), None)
+        if mode == "rects":
+            hm_s = torch.roll(hm, shifts=(7 * step, -11 * step), dims=(1, 2)) if step else hm
+            if step == 3:
+                hm_s = hm_s.clone()
+                hm_s[::2] = hm_s.max()  # every other env loses contact: its old rectangle must be restored completely
+            eng.set_rect_output(g.local_rects(slot))
+            eng.render(hm_s[a:b].cuda(rank).contiguous(), None, out=g.local_block(slot))
+            eng.set_rect_output(None)
+            full = g.gather_rects(eng, slot, torch.cuda.current_stream())
+        else:
+            hm_s = hm
+            eng.render(hm_s[a:b].cuda(rank).contiguous(), None, out=g.local_block(slot))
+            full = g.gather(g.local_block(slot), slot)
+        ref = eng.render(hm_s.cuda(rank).contiguous(), None)
         torch.cuda.synchronize()
         ok = ok and torch.equal(full, ref)
     q.put(bool(ok))
@@ -39,13 +55,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_peer_copy_all_gather_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["copy", "rects"])
+def test_peer_copy_all_gather_matches_single_gpu(mode):
+    """copy: whole frames through the copy engines; rects: only the non-flat rectangle of every half frame crosses the link
+    (tx_obs_push / tx_obs_fill), the rest is completed locally from the flat image -- both bit-identical to one GPU."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + (1 if mode == "rects" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     oks = [q.get(timeout=300) for _ in range(2)]
