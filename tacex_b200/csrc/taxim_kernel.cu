@@ -752,6 +752,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     for (; pb < npx; pb += NTHREADS) {
         const bool valid = pb + lane < npx;
         const int row = row_n, x = x_n;
+        // background of this pixel: requested first, used last (the loads cannot be hoisted across the warp barriers by the compiler)
+        const size_t pix = (size_t)row * IMG_W + x;
+        const float* bgp = bg_half + pix * 3;
+        const float bgv[3] = {__ldg(bgp), __ldg(bgp + 1), __ldg(bgp + 2)};
         // stage the current records (one 80-byte record per lane)
         __syncwarp();
 #pragma unroll
@@ -770,9 +774,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
         }
         const int gy_ = (int)q * HALF_H + row;
-        const size_t pix = (size_t)row * IMG_W + x;
-        const float* bgp = bg_half + pix * 3;
-        const float bgv[3] = {__ldg(bgp), __ldg(bgp + 1), __ldg(bgp + 2)};
         const float yf = __fmul_rn((float)gy_, p.fy);
         const float xf = __fmul_rn((float)x, p.fx);
         float o[3];

@@ -1,0 +1,33 @@
+"""Stall-reason samples per region of taxim_kernel.cu from `ncu --page source --print-source cuda,sass --csv` (CUDA view)."""
+import csv, sys, collections
+rows = list(csv.reader(open(sys.argv[1])))
+regions = [(96, 154, "hpass"), (181, 228, "vpass"), (232, 263, "reimpose"), (283, 298, "flatcopy"), (305, 338, "blur_level"),
+           (340, 356, "poly_rgb"), (388, 520, "prologue/min"), (521, 629, "mask pass"), (630, 683, "between"), (684, 900, "colour")]
+hdr = None; fname = ''
+agg = collections.defaultdict(lambda: collections.Counter()); inst = collections.Counter(); tot = 0
+lines = collections.Counter()
+for r in rows:
+    if len(r) == 2 and r[0] == 'File Path': fname = r[1].split('/')[-1]; continue
+    if r and r[0] == 'Line No': hdr = r; continue
+    if hdr and len(r) == len(hdr) and r[0].isdigit():
+        ln = int(r[0]); d = dict(zip(hdr, r))
+        reg = fname
+        if fname == 'taxim_kernel.cu':
+            reg = next((n for a, b, n in regions if a <= ln <= b), 'other')
+        try: smp = int(float(d['# Samples'])); ins = int(float(d['Instructions Executed']))
+        except ValueError: continue
+        inst[reg] += ins; tot += smp
+        for k, v in d.items():
+            if k.startswith('stall_') and 'Not Issued' not in k:
+                try: agg[reg][k] += int(float(v))
+                except ValueError: pass
+        lines[(fname, ln, r[1].strip()[:80])] += smp
+ti = sum(inst.values())
+print("total samples", tot, "inst", ti)
+for reg in sorted(agg, key=lambda k: -sum(agg[k].values())):
+    s = sum(agg[reg].values())
+    top = ", ".join(f"{k[6:]} {100*v/s:.0f}%" for k, v in agg[reg].most_common(5) if s)
+    print(f"{reg:28s} smp {100*s/tot:5.1f}%  inst {100*inst[reg]/ti:5.1f}%   {top}")
+if len(sys.argv) > 2:
+    for (f, ln, src), s in lines.most_common(int(sys.argv[2])):
+        print(f"{100*s/tot:5.1f}%  {f}:{ln}  {src}")
