@@ -50,7 +50,10 @@ typedef struct tx_handle tx_handle;
  *       .../fots/fots_marker_sim_cfg.py:15-75, .../fots/fots_marker_sim.py:77). */
 typedef struct {
     int abi_version;           /* TX_ABI_VERSION */
-    int H, W;                  /* tactile image shape (240, 320) */
+    int H, W;                  /* tactile image shape: (240, 320) runs the specialised 2-CTA kernel (with kernel sizes
+                                  61,33,17,9,5,3,5); any other shape with 3 <= H, W and H * W <= 19200 -- the reference's RL
+                                  tasks render 32 x 24 / 32 x 32 -- runs the arbitrary-resolution kernel: same results as the
+                                  reference at that shape, no marker grid, no fused camera resize */
     int max_envs;              /* upper bound of N for scratch allocation */
     int num_bins;              /* 125 */
     float pixmm;               /* 0.0295 (NOT rescaled with the resolution) */

@@ -337,24 +337,6 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
     TX_TICK(4 + 4 * L + 3);
 }
 
-// polynomial colour of one pixel: 3 channels x 6 coefficients (cf[6 ch + k], k over x^2, y^2, xy, x, y, 1), + background, clip
-__device__ __forceinline__ void poly_rgb(const float* cf, float xf, float yf, float f0, float f1, float f2, const float* bgv,
-                                         float* o)
-{
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float* pc = cf + 6 * ch;
-        float s = pc[5];
-        s = __fmaf_rn(pc[4], yf, s);
-        s = __fmaf_rn(pc[3], xf, s);
-        s = __fmaf_rn(pc[2], f2, s);
-        s = __fmaf_rn(pc[1], f1, s);
-        s = __fmaf_rn(pc[0], f0, s);
-        s = __fadd_rn(s, bgv[ch]);
-        o[ch] = fminf(fmaxf(s, 0.0f), 1.0f);
-    }
-}
-
 // RGB of a pixel with exactly zero gradient (mag = 0, dir = 0), for every pixel position: computed once per calibration
 // with the same operation sequence the fused kernel uses, so copying it is bit-identical to evaluating it
 __global__ void flat_rgb_kernel(const TaximArgs p, float* __restrict__ out)

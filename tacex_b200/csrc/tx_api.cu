@@ -52,6 +52,8 @@ struct tx_handle {
     float2 *d_rs_wx = nullptr, *d_rs_wy = nullptr;
     float* d_up = nullptr;
     int* d_rect = nullptr; // not owned: tx_set_rect_output
+    bool generic = false;  // shape / radii other than the specialised 240 x 320 kernel: taxim_generic_kernel
+    float* d_taps = nullptr; // generic: [n_blurs][2][TX_MAX_TAPS]
     int n_sm = 148;
 };
 
@@ -96,14 +98,26 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, TX_ERR_NO_DEVICE, "tx_create: no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= ndev) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: bad device index");
-    if (cfg->H != IMG_H || cfg->W != IMG_W)
-        return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: this build is specialised for 240 x 320 frames");
+    // The 2-CTA kernel is specialised for the GelSight Mini at 240 x 320 (kernel sizes 61,33,17,9,5,3,5); every other shape
+    // (the reference's RL tasks render 32 x 24 / 32 x 32 tactile images) runs the arbitrary-resolution kernel.
     static const int want[7] = {61, 33, 17, 9, 5, 3, 5};
-    if (cfg->n_blurs != 7) return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: expected 6 pyramid levels + final blur");
-    for (int l = 0; l < 7; ++l)
-        if (cfg->ksx[l] != want[l] || cfg->ksy[l] != want[l])
-            return fail(nullptr, TX_ERR_UNSUPPORTED,
-                        "tx_create: kernel sizes must be 61,33,17,9,5,3,5 (GelSight Mini at 320x240)");
+    bool generic = cfg->H != IMG_H || cfg->W != IMG_W || cfg->n_blurs != 7;
+    if (cfg->n_blurs < 1 || cfg->n_blurs > TX_MAX_BLURS) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: bad number of blur levels");
+    for (int l = 0; l < cfg->n_blurs; ++l) {
+        if (cfg->ksx[l] < 1 || cfg->ksy[l] < 1 || !(cfg->ksx[l] & 1) || !(cfg->ksy[l] & 1) || cfg->ksx[l] > TX_MAX_TAPS ||
+            cfg->ksy[l] > TX_MAX_TAPS)
+            return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: kernel sizes must be odd and at most TX_MAX_TAPS");
+        if (!generic && (cfg->ksx[l] != want[l] || cfg->ksy[l] != want[l])) generic = true;
+    }
+    if (generic) {
+        if (cfg->H < 3 || cfg->W < 3 || (long long)cfg->H * cfg->W > TXG_MAX_PIXELS)
+            return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: frames other than 240 x 320 must have 3 <= H, W and at most 19200 pixels");
+        for (int l = 0; l < cfg->n_blurs; ++l)
+            if ((cfg->ksx[l] - 1) / 2 >= cfg->W || (cfg->ksy[l] - 1) / 2 >= cfg->H)
+                return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: blur radius must be smaller than the frame (reflect padding)");
+        if (cfg->marker_rows * cfg->marker_cols != 0)
+            return fail(nullptr, TX_ERR_UNSUPPORTED, "tx_create: the FOTS marker model needs the 240 x 320 kernel");
+    }
     if (cfg->max_envs <= 0) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: max_envs must be positive");
     const int M = cfg->marker_rows * cfg->marker_cols;
     if (M < 0 || M > TX_MAX_MARKERS) return fail(nullptr, TX_ERR_INVALID_ARG, "tx_create: too many markers");
@@ -119,6 +133,7 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
     h->stream = (cudaStream_t)cuda_stream;
     h->M = M;
     h->n_sm = prop.multiProcessorCount;
+    h->generic = generic;
 #define TX_CUDA_C(expr)                                                                                               \
     do {                                                                                                              \
         cudaError_t _e = (expr);                                                                                      \
@@ -137,8 +152,13 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
                 t[((size_t)l * 2 + 0) * TX_MAX_TAPS + k] = k < cfg->ksx[l] ? cfg->taps_x[l][k] : 0.0f;
                 t[((size_t)l * 2 + 1) * TX_MAX_TAPS + k] = k < cfg->ksy[l] ? cfg->taps_y[l][k] : 0.0f;
             }
-        TX_CUDA_C(upload_taps(t.data(), h->stream));
-        TX_CUDA_C(cudaStreamSynchronize(h->stream));
+        if (generic) { // per-handle taps in global memory (the __constant__ copy belongs to the specialised kernel)
+            TX_CUDA_C(cudaMalloc(&h->d_taps, t.size() * sizeof(float)));
+            TX_CUDA_C(cudaMemcpy(h->d_taps, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            TX_CUDA_C(upload_taps(t.data(), h->stream));
+            TX_CUDA_C(cudaStreamSynchronize(h->stream));
+        }
     }
     if (M > 0) {
         std::vector<int32_t> ax, ay;
@@ -172,6 +192,7 @@ extern "C" void tx_destroy(tx_handle* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    cudaFree(h->d_taps);
     cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
@@ -220,8 +241,8 @@ extern "C" int tx_upload_tables(tx_handle* h, const float* poly_grad, const floa
         cudaFree(h->d_gel);
         h->d_gel = nullptr;
     }
-    if (!h->d_flat) TX_CUDA(h, cudaMalloc(&h->d_flat, sizeof(float) * H * W * 3));
-    {
+    if (!h->generic) {
+        if (!h->d_flat) TX_CUDA(h, cudaMalloc(&h->d_flat, sizeof(float) * H * W * 3));
         TaximArgs a{};
         fill_taxim_consts(h, a);
         TX_CUDA(h, launch_flat_rgb(a, h->d_flat, h->stream));
@@ -257,8 +278,12 @@ extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N,
     if (!h || !height_mm || !depth_mm || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_indentation_depth: bad argument");
     if (N == 0) return TX_OK;
     TX_CUDA(h, cudaSetDevice(h->device));
-    TX_CUDA(h, launch_indentation_depth(height_mm, depth_mm, N, h->cfg.gelpad_height_m, h->cfg.gelpad_to_cam_min_m,
-                                        h->stream));
+    if (h->generic)
+        TX_CUDA(h, launch_indentation_depth_generic(height_mm, depth_mm, N, h->cfg.H * h->cfg.W, h->cfg.gelpad_height_m,
+                                                    h->cfg.gelpad_to_cam_min_m, h->stream));
+    else
+        TX_CUDA(h, launch_indentation_depth(height_mm, depth_mm, N, h->cfg.gelpad_height_m, h->cfg.gelpad_to_cam_min_m,
+                                            h->stream));
     h->ctr.depth_calls++;
     h->ctr.kernels_launched++;
     return TX_OK;
@@ -299,6 +324,7 @@ static bool resize_table(int in_size, int out_size, std::vector<int>& first, std
 extern "C" int tx_set_camera_resolution(tx_handle* h, int Hc, int Wc)
 {
     if (!h || Hc <= 0 || Wc <= 0) return fail(h, TX_ERR_INVALID_ARG, "tx_set_camera_resolution: bad argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_set_camera_resolution: the fused resize belongs to the 240 x 320 kernel");
     if (Hc > h->cfg.H || Wc > h->cfg.W || Hc * Wc > taxim_lowres_max_pixels() || (Hc == h->cfg.H && Wc == h->cfg.W))
         return fail(h, TX_ERR_UNSUPPORTED, "tx_set_camera_resolution: only up-sampling of frames of at most 9600 pixels is fused");
     std::vector<int> fx, fy;
@@ -353,10 +379,29 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render: bad argument");
     if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
     if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
-    if ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u)))
+    if (!h->generic &&
+        ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u))))
         return fail(h, TX_ERR_INVALID_ARG, "tx_render: device buffers must be 16-byte aligned");
     if (N == 0) return TX_OK;
     TX_CUDA(h, cudaSetDevice(h->device));
+    if (h->generic) {
+        TaximArgs c{};
+        fill_taxim_consts(h, c);
+        TaximGenericArgs g{};
+        g.hm = height_mm; g.press_in = press_mm; g.gel = c.gel; g.poly = c.poly; g.bg_hwc = c.bg_hwc; g.taps = h->d_taps;
+        g.rgb = rgb; g.depth_out = depth_out; g.deformed_out = deformed; g.mask_out = mask; g.hm_out = hm_out;
+        g.H = h->cfg.H; g.W = h->cfg.W; g.n_blurs = h->cfg.n_blurs; g.nb = c.nb; g.input_is_depth = input_is_depth;
+        for (int l = 0; l < h->cfg.n_blurs; ++l) { g.ksx[l] = h->cfg.ksx[l]; g.ksy[l] = h->cfg.ksy[l]; }
+        g.clip_max_m = clip_max_m; g.inv_pixmm = c.inv_pixmm; g.sx = c.sx; g.sy = c.sy; g.fx = c.fx; g.fy = c.fy;
+        g.contact_scale = c.contact_scale; g.gelpad_h = c.gelpad_h; g.gelpad_min = c.gelpad_min;
+        g.inv_xbin = c.inv_xbin; g.inv_ybin = c.inv_ybin;
+        TX_CUDA(h, launch_taxim_generic(g, N, h->stream));
+        h->aux_valid_n = 0;
+        h->ctr.render_calls++;
+        h->ctr.frames_rendered += (uint64_t)N;
+        h->ctr.kernels_launched++;
+        return TX_OK;
+    }
     TaximArgs a{};
     a.hm = height_mm;
     a.press_in = press_mm;
@@ -509,7 +554,7 @@ extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const flo
         return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: markers need theta and a marker grid");
     if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: N exceeds max_envs");
     TX_CUDA(h, cudaSetDevice(h->device));
-    const size_t HW = (size_t)IMG_H * IMG_W;
+    const size_t HW = (size_t)h->cfg.H * h->cfg.W;
     if (h->host_cap < N) {
         cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
         cudaFree(h->d_traj_len); cudaFree(h->d_markers);

@@ -42,6 +42,24 @@ __device__ __forceinline__ float atan2f_c(float y, float x)
     return (x < 0.0f) ? __fadd_rn(z, adj) : z;
 }
 
+// polynomial colour of one pixel: 3 channels x 6 coefficients (cf[6 ch + k], k over x^2, y^2, xy, x, y, 1), + background, clip
+__device__ __forceinline__ void poly_rgb(const float* cf, float xf, float yf, float f0, float f1, float f2, const float* bgv,
+                                         float* o)
+{
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* pc = cf + 6 * ch;
+        float s = pc[5];
+        s = __fmaf_rn(pc[4], yf, s);
+        s = __fmaf_rn(pc[3], xf, s);
+        s = __fmaf_rn(pc[2], f2, s);
+        s = __fmaf_rn(pc[1], f1, s);
+        s = __fmaf_rn(pc[0], f0, s);
+        s = __fadd_rn(s, bgv[ch]);
+        o[ch] = fminf(fmaxf(s, 0.0f), 1.0f);
+    }
+}
+
 // ---- mbarrier + bulk async copy (TMA, 1-D) -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -52,6 +52,25 @@ struct TaximArgs {
     long long* ticks; // optional [2N][40] phase clock stamps (profiling builds of the host call only)
 };
 
+// arbitrary-resolution variant (taxim_generic_kernel.cu): one CTA per frame, two planes + a byte mask in shared memory
+constexpr int TXG_MAX_PIXELS = 160 * 120;
+struct TaximGenericArgs {
+    const float* hm;         // [N][H][W] height map (mm) or depth image (m, input_is_depth)
+    const float* press_in;   // [N] or nullptr (fused indentation depth)
+    const float* gel;        // [H][W] or nullptr
+    const float4* poly;      // [nb][nb][5 float4]
+    const float* bg_hwc;     // [H][W][3]
+    const float* taps;       // [n_blurs][2][TX_MAX_TAPS] (x, y) in global memory
+    float* rgb;              // [N][H][W][3]
+    float* depth_out;        // [N] or nullptr
+    float* deformed_out;     // [N][H][W] or nullptr
+    unsigned char* mask_out; // [N][H][W] or nullptr
+    float* hm_out;           // [N][H][W] or nullptr (input_is_depth only)
+    int H, W, n_blurs, nb, input_is_depth;
+    int ksx[8], ksy[8];
+    float clip_max_m, inv_pixmm, sx, sy, fx, fy, contact_scale, gelpad_h, gelpad_min, inv_xbin, inv_ybin;
+};
+
 constexpr int TX_MAX_PEERS = 15;
 struct ObsPushArgs {
     const float* rgb_local;  // [N][240][320][3] this rank's frames
@@ -140,6 +159,10 @@ cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
 cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);
 cudaError_t launch_fots(const FotsArgs& a, int N, cudaStream_t s);
+cudaError_t launch_taxim_generic(const TaximGenericArgs& a, int N, cudaStream_t s);
+int taxim_generic_smem_bytes(int H, int W);
+cudaError_t launch_indentation_depth_generic(const float* hm, float* out, int N, int npx, float gelpad_h, float gelpad_min,
+                                             cudaStream_t s);
 cudaError_t launch_obs_push(const ObsPushArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_obs_fill(const ObsFillArgs& a, int grid, cudaStream_t s);
 

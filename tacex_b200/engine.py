@@ -67,6 +67,9 @@ class TactileEngine:
                 cfg.taps_x[l][k] = v
             for k, v in enumerate(ky.tolist()):
                 cfg.taps_y[l][k] = v
+        # the 2-CTA kernel is specialised for 240 x 320 / kernel sizes 61,33,17,9,5,3,5; any other shape (the reference's RL tasks
+        # render 32 x 24 / 32 x 32 tactile images) runs the arbitrary-resolution kernel of the library: no FOTS aux, no fused resize
+        self.generic = (H, W) != (240, 320) or [(kx.numel(), ky.numel()) for kx, ky in taps] != [(k, k) for k in (61, 33, 17, 9, 5, 3, 5)]
         cfg.marker_rows, cfg.marker_cols = marker_rows, marker_cols
         cfg.marker_x0, cfg.marker_y0 = marker_x0, marker_y0
         cfg.fots_lambda[:] = fots_lambda

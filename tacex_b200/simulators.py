@@ -123,10 +123,16 @@ class FOTSMarkerSimulatorCfg(GelSightSimulatorCfg):
 
 
 def _load_tables(path: str, shape: tuple[int, int]) -> TaximTables:
+    """``calib_folder_path``: a calibration folder in the reference's format, a folder of pre-baked ``tables_{W}x{H}.npz`` files
+    (one per tactile resolution), or one pre-baked ``.npz``."""
     p = Path(path)
     if p.is_dir():
-        return TaximTables.from_calib_folder(p, shape)
-    return TaximTables.load(p)
+        baked = p / f"tables_{shape[1]}x{shape[0]}.npz"
+        return TaximTables.load(baked) if baked.exists() else TaximTables.from_calib_folder(p, shape)
+    t = TaximTables.load(p)
+    if tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{p} holds tables for {t.shape[1]}x{t.shape[0]}, tactile_img_res asks for {shape[1]}x{shape[0]}")
+    return t
 
 
 def _is_cuda(dev) -> bool:
@@ -156,7 +162,9 @@ class B200TaximSimulator(GelSightSimulator):
         rows = cols = 0
         x0 = y0 = 0.0
         mm2pix = 19.58
-        if mcfg is not None and hasattr(mcfg, "marker_params") and hasattr(mcfg, "mm_to_pixel"):
+        # the marker model shares the optical kernel's blur pyramid only at the GelSight Mini's 320 x 240; at any other tactile
+        # resolution (e.g. the RL tasks' 32 x 24) the FOTS simulator runs its own 320 x 240 engine, as the reference does
+        if (H, W) == (240, 320) and mcfg is not None and hasattr(mcfg, "marker_params") and hasattr(mcfg, "mm_to_pixel"):
             rows, cols = mcfg.marker_params.num_markers_row, mcfg.marker_params.num_markers_col
             x0, y0, mm2pix = mcfg.marker_params.x0, mcfg.marker_params.y0, mcfg.mm_to_pixel
         self.engine = TactileEngine(
@@ -182,7 +190,7 @@ class B200TaximSimulator(GelSightSimulator):
         hc, wc = int(hm.shape[1]), int(hm.shape[2])
         if (hc, wc) == (H, W):
             return False
-        if hc <= H and wc <= W and hc * wc <= 9600:
+        if not self.engine.generic and hc <= H and wc <= W and hc * wc <= 9600:
             if getattr(self.engine, "cam_hw", None) != (hc, wc):
                 self.engine.set_camera_resolution(hc, wc)
             return True
@@ -298,6 +306,19 @@ class B200FOTSMarkerSimulator(GelSightSimulator):
                 "Currently FOTS simulation approach has to be used in combination with GPU-Taxim as optical-simulator."
             )
         eng = self._taxim.engine
+        W, H = self.cfg.tactile_img_res
+        # The marker model works on the gel deformation at ITS tactile resolution (ref: fots_marker_sim.py:121-129). When the
+        # optical simulator renders at another one (the RL tasks: optical 32 x 24, markers 320 x 240, ref:
+        # ball_rolling_taxim_fots.py:321,331) the deformation cannot be shared and this simulator owns a second engine.
+        self._own_engine = (eng.H, eng.W) != (H, W)
+        if self._own_engine:
+            mp = self.cfg.marker_params
+            eng = TactileEngine(
+                _load_tables(self._taxim.cfg.calib_folder_path, (H, W)), max_envs=self._num_envs, device=eng.device,
+                marker_rows=mp.num_markers_row, marker_cols=mp.num_markers_col, marker_x0=mp.x0, marker_y0=mp.y0,
+                mm2pix=self.cfg.mm_to_pixel, gelpad_height_m=self._taxim.cfg.gelpad_height,
+                gelpad_to_cam_min_m=self._taxim.cfg.gelpad_to_camera_min_distance,
+            )
         if eng.M != self.cfg.marker_params.num_markers_row * self.cfg.marker_params.num_markers_col:
             raise RuntimeError("marker grid of the optical simulator's engine does not match marker_params")
         self.engine = eng
@@ -345,6 +366,8 @@ class B200FOTSMarkerSimulator(GelSightSimulator):
         # GelSightSensor made of the simulator's buffer (gelsight_sensor.py:361-365) -- tracked with tensor versions,
         # no host synchronisation. Otherwise recompute it for exactly (height_map, sensor._indentation_depth), as the
         # reference always does (fots_marker_sim.py:128-129).
+        if self._own_engine:
+            return self._markers_own_engine(press)
         reuse = (
             tx._stamp is not None
             and tx._stamp == (tx._hm_stamp(), tx._indentation_depth._version)
@@ -357,6 +380,30 @@ class B200FOTSMarkerSimulator(GelSightSimulator):
             tx._stamp = None  # the engine's recorded deformation no longer belongs to the optical simulator's frame
         self.theta = self._relative_yaw()
         self.engine.fots_markers(press, self.theta, self.traj0, self.traj_len, out=self.marker_data)
+        return self.marker_data
+
+    def _markers_own_engine(self, press: torch.Tensor) -> torch.Tensor:
+        """Marker resolution != optical resolution: the height map is resized to the marker resolution (F.resize, ref:
+        fots_marker_sim.py:121-122; fused into the kernel's load stage when the camera is coarser) and the deformation is
+        computed by this simulator's own engine for (height map, sensor._indentation_depth), as the reference always does."""
+        W, H = self.cfg.tactile_img_res
+        eng = self.engine
+        hm = self.sensor._data.output["height_map"]
+        hm = (hm if hm.device == eng.device else hm.to(eng.device)).contiguous()
+        if self._scratch_rgb is None:
+            self._scratch_rgb = torch.empty((self._num_envs, H, W, 3), device=eng.device)
+        hc, wc = int(hm.shape[1]), int(hm.shape[2])
+        if (hc, wc) == (H, W):
+            eng.render(hm, press, out=self._scratch_rgb)
+        elif hc <= H and wc <= W and hc * wc <= 9600:
+            if getattr(eng, "cam_hw", None) != (hc, wc):
+                eng.set_camera_resolution(hc, wc)
+            eng.render_camera(hm, press=press, out=self._scratch_rgb)
+        else:
+            hm = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0].contiguous()
+            eng.render(hm, press, out=self._scratch_rgb)
+        self.theta = self._relative_yaw()
+        eng.fots_markers(press, self.theta, self.traj0, self.traj_len, out=self.marker_data)
         return self.marker_data
 
     def reset(self):

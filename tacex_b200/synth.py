@@ -174,3 +174,23 @@ def bench_batch(n_envs: int, seed: int = 0, H: int = 240, W: int = 320, n_unique
     pool = height_map_mm(config1(min(n_unique, n_envs), seed, H, W)["depth_m"])
     reps = (n_envs + pool.shape[0] - 1) // pool.shape[0]
     return pool.repeat(reps, 1, 1)[:n_envs].contiguous()
+
+
+def lowres_batch(n_envs: int, H: int, W: int, seed: int = 3) -> torch.Tensor:
+    """Height maps [mm] at a coarse tactile resolution (the reference's RL tasks render 32 x 24 / 32 x 32 tactile images,
+    ref: tacex_tasks/.../ball_rolling_taxim_fots.py:306-321): the four indenter kinds with random pose, the pixel pitch scaled
+    so that the frame covers the same gel area as 320 x 240; every fifth env has no contact."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.rand(n_envs, generator=g, dtype=torch.float64)  # noqa: E731
+    kind = torch.randint(0, 4, (n_envs,), generator=g)
+    size = (1.5 + 2.5 * r()) * 1e-3
+    cx, cy = (r() * 8 - 4) * 1e-3, (r() * 6 - 3) * 1e-3
+    p = (0.2 + r() * 1.3) * 1e-3
+    yaw = (r() * 2 - 1) * math.pi
+    pitch = PIXEL_PITCH_M_320 * 320 / W
+    d = torch.stack([
+        depth_map(int(kind[i]), size[i].item(), cx[i].item(), cy[i].item(), yaw[i].item(), p[i].item(), H, W, pitch,
+                  contact=(i % 5 != 4))
+        for i in range(n_envs)
+    ])
+    return height_map_mm(d)
