@@ -46,6 +46,10 @@ constexpr int SM_MLIST = SM_MASK + HALF_H * (IMG_W / 32) * 4; // u16 indices of 
 constexpr int SM_MISC = SM_MLIST + HALF_H * (IMG_W / 32) * 2;
 constexpr int SM_TOTAL = SM_MISC + 512;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+// colour stage: the per-warp staging areas (640 floats each) start at hb0 and may run into the first rows of hb1 (contiguous),
+// so the 1-row halo of the central differences sits behind them
+constexpr int HALO1_OFF = 1024;
+static_assert(NWARPS * 640 <= HB0_ROWS * IMG_W + HALO1_OFF && HALO1_OFF + IMG_W <= HB1_ROWS * IMG_W, "staging area");
 
 struct Misc {
     uint64_t mbar;
@@ -506,7 +510,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     const float thr = __fmul_rn(-press, p.contact_scale);
     unsigned cnt = 0, srow = 0, scol = 0;
     constexpr int NWORDS = HALF_H * (IMG_W / 32);
-    static_assert(NWORDS % (NWARPS * 4) == 0, "h/mask pass unroll");
+    static_assert(NWORDS % 4 == 0, "h/mask pass unroll");
     // contact bounding box of this warp's words (warp-uniform registers; merged with 4 shared atomics per warp at the end)
     int bb_r0 = IMG_H, bb_r1 = -1, bb_c0 = IMG_W, bb_c1 = -1;
     for (int w0 = warp * 4; w0 < NWORDS; w0 += NWARPS * 4) {
@@ -624,7 +628,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
     {
         const int brow = q == 0 ? HALF_H - 1 : 0;
-        for (int x = tid; x < IMG_W; x += NTHREADS) hb1_remote[x] = plane[brow * IMG_W + x];
+        for (int x = tid; x < IMG_W; x += NTHREADS) hb1_remote[HALO1_OFF + x] = plane[brow * IMG_W + x];
     }
     if (p.deformed_out) {
         const float4* s4 = reinterpret_cast<const float4*>(plane);
@@ -701,8 +705,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
         const int xx = min(max(x, 1), IMG_W - 2);
         const float* ctr = plane + yy * IMG_W + xx;
-        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1 + xx;
-        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1 + xx;
+        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1 + HALO1_OFF + xx;
+        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1 + HALO1_OFF + xx;
         const float top = __fmul_rn(*up, p.inv_pixmm), bot = __fmul_rn(*dn, p.inv_pixmm);
         const float lef = __fmul_rn(ctr[-1], p.inv_pixmm), rig = __fmul_rn(ctr[1], p.inv_pixmm);
         const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);

@@ -10,9 +10,9 @@ constexpr int IMG_H = 240;
 constexpr int IMG_W = 320;
 constexpr int HALF_H = 120;   // rows owned by one CTA of the 2-CTA cluster
 #ifndef TX_NTHREADS
-#define TX_NTHREADS 480
+#define TX_NTHREADS 512
 #endif
-constexpr int NTHREADS = TX_NTHREADS; // 15 warps (12 warps = 384 is the other supported value)
+constexpr int NTHREADS = TX_NTHREADS; // 16 warps x 128 registers = the whole register file of the SM (480 / 384 also build)
 constexpr int NWARPS = NTHREADS / 32;
 
 struct TaximArgs {

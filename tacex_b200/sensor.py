@@ -220,6 +220,20 @@ class GelSightSensor:
             hm *= 1000
             return hm
 
+    def _get_camera_depth(self):
+        """Normalised uint8 depth image for debug visualisation (ref: gelsight_sensor.py:557-579), same arithmetic: mm, minus
+        the near plane, divided by the far plane, x 255, truncated to uint8; (N, H_cam, W_cam, 1)."""
+        if self._camera_depth is not None:
+            d = self._camera_depth.clone()
+            lo, hi = self.cfg.sensor_camera_cfg.clipping_range
+            d[torch.isinf(d)] = hi
+            d *= 1000.0
+            d -= lo * 1000
+            d /= hi * 1000
+            W, H = self.camera_resolution
+            self._data.output["camera_depth"] = (d * 255).type(dtype=torch.uint8).reshape((self._num_envs, H, W, 1))
+        return self._data.output.get("camera_depth")
+
     def _update_buffers_impl(self, env_ids):
         """ref: gelsight_sensor.py:342-378 -- same order: height map, indentation depth, RGB, markers."""
         self._frame[env_ids] += 1
@@ -234,6 +248,8 @@ class GelSightSensor:
         elif self.compute_indentation_depth_func is not None:
             self._get_height_map()
             self._indentation_depth[:] = self.compute_indentation_depth_func()
+        if "camera_depth" in self._data.output:
+            self._get_camera_depth()
         if (self.optical_simulator is not None) and ("tactile_rgb" in self.cfg.data_types):
             self._data.output["tactile_rgb"][:] = self.optical_simulator.optical_simulation()
         if (self.marker_motion_simulator is not None) and ("marker_motion" in self.cfg.data_types):
