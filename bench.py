@@ -249,6 +249,7 @@ def main() -> None:
                          "image (bit-identical to gathering whole frames, about half the link bytes); fp32-ce = whole frames by "
                          "copy-engine peer copies (no SM used); fp32 = fp32-ce for 2 GPUs (one peer: the link is not the limit), "
                          "fp32-rect beyond; nccl = all_gather_into_tensor; none = observations stay sharded")
+    ap.add_argument("--no-multicast", action="store_true", help="fp32-rect: one store per peer instead of NVSwitch multicast stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fem", action="store_true", help="skip the extra gel-FEM measurement (config 3)")
     args = ap.parse_args()
@@ -283,6 +284,10 @@ def main() -> None:
     hm_host = synth.bench_batch(E, seed=rank, n_unique=64).pin_memory()
     theta_host = torch.zeros(E).pin_memory()
     hm = hm_host.to(dev)
+    # consecutive steps see DIFFERENT depth maps for every env (the pool of unique maps shifted by a prime number of envs):
+    # nothing a step produces can be carried over from the previous one, and the rectangle transport of the observation
+    # gather has to restore the previous rectangles of each buffer (contacts that jump, the unfavourable case)
+    hm_sets = [hm, hm.roll(37, 0).contiguous(), hm.roll(74, 0).contiguous()]
     theta = theta_host.to(dev)
     depth = torch.empty(E, device=dev)
     rgb = torch.empty((E, H, W, 3), device=dev)
@@ -297,10 +302,12 @@ def main() -> None:
     if do_gather:
         if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
             try:
-                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=use_rects)
+                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=use_rects, multicast=not args.no_multicast)
                 rgb_buf = [peer.local_block(0), peer.local_block(1)]  # the kernel renders straight into the gathered buffer
                 gather_kind = ("float32 all-gather of RGB, bit-identical to gathering whole frames: NVLink peer stores of every frame's "
-                               "non-flat rectangle into symmetric memory + local completion from the flat image, overlapped with the next step"
+                               "non-flat rectangle into symmetric memory ("
+                               + ("NVSwitch multicast stores" if (use_rects and peer.mc_rgb[0]) else "one store per peer")
+                               + ") + local completion from the flat image, overlapped with the next step"
                                if use_rects else
                                "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step")
             except Exception as exc:  # symmetric memory unavailable on this box
@@ -320,7 +327,7 @@ def main() -> None:
             torch.cuda.current_stream().wait_event(ev_free[i])  # the gather that read this buffer two steps ago is done
         if peer is not None and use_rects:
             eng.set_rect_output(peer.local_rects(i))
-        eng.render(hm, None, out=rgb_buf[i], depth_out=depth)
+        eng.render(hm_sets[(state["i"] - 1) % 3], None, out=rgb_buf[i], depth_out=depth)
         eng.fots_markers(depth, theta, traj0, traj_len, out=markers)
         if do_gather:
             ev_done[i].record()
@@ -413,7 +420,7 @@ def main() -> None:
                 "workload": f"{E} envs/GPU x 320x240: indentation depth + Taxim RGB + FOTS {M}-marker motion, sphere indenters "
                             f"(config-1 distribution, 10% no contact); the optional gel FEM substep (config 3) is reported separately under fem_gel_substep",
                 "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"dp{world} (contiguous env shards)",
-                "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2)",
+                "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2); three input sets cycle, so every env sees a different depth map in consecutive steps",
                 "obs_gather": (gather_kind if do_gather else ("none (observations stay sharded)" if world > 1 else "n/a")),
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

@@ -140,14 +140,16 @@ int tx_render_camera(tx_handle* h, const float* frames, int is_depth, float clip
  * tx_render* calls record it: rect [N][2][4] int32 = (first row, last row -- local to the half --, first column, last column),
  * last < first when empty. tx_obs_push (on `cuda_stream`, e.g. a side stream) stores the pixels of this rank's rectangles and
  * the descriptors into the same block of every peer's gathered buffer: peer_rgb / peer_rect are HOST arrays of n_peers
- * peer-mapped DEVICE pointers (symmetric memory, NVLink peer-to-peer stores). After a cross-rank barrier tx_obs_fill completes
+ * peer-mapped DEVICE pointers (symmetric memory, NVLink peer-to-peer stores); mc_rgb / mc_rect (optional, both or none) are the
+ * addresses of the same block in the NVSwitch MULTICAST mapping of the buffers: one multimem.st per 16 bytes leaves the GPU and the
+ * switch replicates it to every peer (egress / (n_peers) of the unicast stores). After a cross-rank barrier tx_obs_fill completes
  * this rank's gathered buffer rgb_all [N_total][H][W][3]: everything outside the rectangles of the envs NOT in
  * [skip_lo, skip_hi) (this rank's own, rendered in place) is copied from the flat image. prev_rect [N_total][2][4] (optional,
  * inout, one per gathered buffer, initialised to (0, H/2-1, 0, W-1) per half) remembers what the buffer held after its last
  * fill, so that only the part of the old rectangle the new one does not cover is restored. Result == gathering whole frames. */
 int tx_set_rect_output(tx_handle* h, int32_t* rect);
 int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* rect_local, int N, int n_peers, float* const* peer_rgb,
-                int32_t* const* peer_rect, void* cuda_stream);
+                int32_t* const* peer_rect, float* mc_rgb, int32_t* mc_rect, void* cuda_stream);
 int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* prev_rect, int N_total, int skip_lo, int skip_hi,
                 void* cuda_stream);
 

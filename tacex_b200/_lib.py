@@ -98,7 +98,7 @@ def load() -> C.CDLL:
     lib.tx_render_camera.argtypes = [C.c_void_p, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, fp, u8p]
     lib.tx_render_camera.restype = C.c_int
     lib.tx_set_rect_output.argtypes = [C.c_void_p, vp]
-    lib.tx_obs_push.argtypes = [C.c_void_p, fp, ip, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp]
+    lib.tx_obs_push.argtypes = [C.c_void_p, fp, ip, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), fp, ip, vp]
     lib.tx_obs_fill.argtypes = [C.c_void_p, fp, ip, ip, C.c_int, C.c_int, C.c_int, vp]
     for name in ("tx_set_rect_output", "tx_obs_push", "tx_obs_fill"):
         getattr(lib, name).restype = C.c_int

@@ -16,6 +16,13 @@ namespace tx {
 constexpr int OG_THREADS = 512;
 constexpr int QPR = IMG_W / 4; // 4-pixel quads per row (48 bytes = 3 float4 each)
 
+// 16-byte store to a multicast address (NVLink SHARP / NVLS mapping of a symmetric allocation)
+__device__ __forceinline__ void mc_store(float* mc_addr, float4 v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(OG_THREADS) obs_push_kernel(const ObsPushArgs a)
 {
     constexpr int UNR = 4; // independent 16-byte loads in flight per thread (the grid is small: see tx_obs_push)
@@ -23,7 +30,11 @@ __global__ void __launch_bounds__(OG_THREADS) obs_push_kernel(const ObsPushArgs 
     for (int item = blockIdx.x; item < 2 * a.N; item += gridDim.x) {
         const int4 r = reinterpret_cast<const int4*>(a.rect_local)[item]; // ry0, ry1 (local rows of the half), xa, xb
         if (threadIdx.x == 0) {
-            for (int p = 0; p < a.n_peers; ++p) reinterpret_cast<int4*>(a.peer_rect[p])[item] = r;
+            if (a.mc_rect)
+                mc_store(reinterpret_cast<float*>(a.mc_rect) + (size_t)item * 4,
+                         make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.z), __int_as_float(r.w)));
+            else
+                for (int p = 0; p < a.n_peers; ++p) reinterpret_cast<int4*>(a.peer_rect[p])[item] = r;
         }
         if (r.y < r.x || r.w < r.z) continue;
         const int nf4 = (r.w - r.z + 1) * 3 / 4;              // float4 per row segment (the width is a multiple of 4 pixels)
@@ -40,12 +51,18 @@ __global__ void __launch_bounds__(OG_THREADS) obs_push_kernel(const ObsPushArgs 
                 off[u] = base + ((size_t)(r.x + rr) * IMG_W + r.z) * 3 + (size_t)(i - rr * nf4) * 4;
                 if (i < total) v[u] = __ldcs(reinterpret_cast<const float4*>(a.rgb_local + off[u]));
             }
-#pragma unroll 1
-            for (int p = 0; p < a.n_peers; ++p) {
-                float* dst = a.peer_rgb[p];
+            if (a.mc_rgb) { // one multicast store: the NVSwitch replicates it into every GPU's buffer (this GPU's included)
 #pragma unroll
                 for (int u = 0; u < UNR; ++u)
-                    if (i0 + u * OG_THREADS < total) *reinterpret_cast<float4*>(dst + off[u]) = v[u];
+                    if (i0 + u * OG_THREADS < total) mc_store(a.mc_rgb + off[u], v[u]);
+            } else {
+#pragma unroll 1
+                for (int p = 0; p < a.n_peers; ++p) {
+                    float* dst = a.peer_rgb[p];
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u)
+                        if (i0 + u * OG_THREADS < total) *reinterpret_cast<float4*>(dst + off[u]) = v[u];
+                }
             }
         }
     }

@@ -447,7 +447,7 @@ extern "C" int tx_set_rect_output(tx_handle* h, int32_t* rect)
 }
 
 extern "C" int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* rect_local, int N, int n_peers,
-                           float* const* peer_rgb, int32_t* const* peer_rect, void* cuda_stream)
+                           float* const* peer_rgb, int32_t* const* peer_rect, float* mc_rgb, int32_t* mc_rect, void* cuda_stream)
 {
     if (!h || !rgb_local || !rect_local || N < 0 || n_peers < 0 || n_peers > TX_MAX_PEERS || (n_peers > 0 && (!peer_rgb || !peer_rect)))
         return fail(h, TX_ERR_INVALID_ARG, "tx_obs_push: bad argument");
@@ -455,6 +455,8 @@ extern "C" int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* 
     TX_CUDA(h, cudaSetDevice(h->device));
     ObsPushArgs a{};
     a.rgb_local = rgb_local; a.rect_local = rect_local; a.N = N; a.n_peers = n_peers;
+    if ((mc_rgb != nullptr) != (mc_rect != nullptr)) return fail(h, TX_ERR_INVALID_ARG, "tx_obs_push: both multicast pointers or none");
+    a.mc_rgb = mc_rgb; a.mc_rect = mc_rect;
     for (int p = 0; p < n_peers; ++p) {
         if (!peer_rgb[p] || !peer_rect[p]) return fail(h, TX_ERR_INVALID_ARG, "tx_obs_push: null peer pointer");
         a.peer_rgb[p] = peer_rgb[p];

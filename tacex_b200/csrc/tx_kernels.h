@@ -78,6 +78,8 @@ struct ObsPushArgs {
     int N, n_peers;
     float* peer_rgb[TX_MAX_PEERS];  // the same block inside every peer's gathered buffer (peer-mapped addresses)
     int* peer_rect[TX_MAX_PEERS];
+    float* mc_rgb;  // optional: the same block through the NVSwitch MULTICAST mapping of the gathered buffers (multimem.st:
+    int* mc_rect;   // one store leaves the GPU, the switch replicates it to every peer); nullptr = one store per peer
 };
 struct ObsFillArgs {
     float* rgb_all;          // [N_total][240][320][3] this rank's gathered buffer

@@ -179,14 +179,15 @@ class TactileEngine:
         """int32 (N, 2, 4) device tensor that the following renders fill with the per-half non-flat rectangle, or None."""
         self._check(self.lib.tx_set_rect_output(self.h, _ptr(rect)))
 
-    def obs_push(self, rgb_local: torch.Tensor, rect_local: torch.Tensor, peer_rgb: list, peer_rect: list, stream) -> None:
+    def obs_push(self, rgb_local: torch.Tensor, rect_local: torch.Tensor, peer_rgb: list, peer_rect: list, stream,
+                 mc_rgb: int = 0, mc_rect: int = 0) -> None:
         import ctypes as C
 
         n = len(peer_rgb)
         pr = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_rgb])
         pd = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in peer_rect])
         self._check(self.lib.tx_obs_push(self.h, _ptr(rgb_local), _ptr(rect_local), rgb_local.shape[0], n, pr, pd,
-                                         C.c_void_p(stream.cuda_stream)))
+                                         mc_rgb or None, mc_rect or None, C.c_void_p(stream.cuda_stream)))
 
     def obs_fill(self, rgb_all: torch.Tensor, rect_all: torch.Tensor, prev_rect: torch.Tensor | None, skip_lo: int, skip_hi: int,
                  stream) -> None:

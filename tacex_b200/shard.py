@@ -39,7 +39,7 @@ class PeerObsGather:
     (2) everybody's pushes have landed. All calls are stream-ordered on the current stream; nothing synchronises the host.
     """
 
-    def __init__(self, local_shape, dtype, device, n_slots: int = 2, with_rects: bool = False):
+    def __init__(self, local_shape, dtype, device, n_slots: int = 2, with_rects: bool = False, multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
@@ -47,6 +47,10 @@ class PeerObsGather:
         full = (self.world * self.E,) + tuple(local_shape[1:])
         self.bufs, self.hdls, self.views = [], [], []
         self.rects, self.rect_views, self.prev_rects = [], [], []
+        self.mc_rgb, self.mc_rect = [], []  # multicast (NVSwitch) addresses of this rank's block, 0 when unavailable
+        frame_bytes = 4
+        for d in local_shape[1:]:
+            frame_bytes *= int(d)
         for _ in range(n_slots):
             t = symm_mem.empty(full, dtype=dtype, device=device)
             h = symm_mem.rendezvous(t, dist.group.WORLD)
@@ -60,6 +64,10 @@ class PeerObsGather:
                 r.zero_()
                 self.rects.append(r)
                 self.rect_views.append([rh.get_buffer(p, rshape, torch.int32) for p in range(self.world)])
+                mc_a, mc_b = (int(getattr(h, "multicast_ptr", 0) or 0), int(getattr(rh, "multicast_ptr", 0) or 0)) if multicast else (0, 0)
+                ok = mc_a != 0 and mc_b != 0
+                self.mc_rgb.append(mc_a + self.rank * self.E * frame_bytes if ok else 0)
+                self.mc_rect.append(mc_b + self.rank * self.E * 32 if ok else 0)
                 # what the buffer holds after its last fill (local): starts as "anything anywhere" = the whole half frame
                 hh, ww = int(local_shape[1]) // 2, int(local_shape[2])
                 self.prev_rects.append(torch.tensor([0, hh - 1, 0, ww - 1], dtype=torch.int32, device=device).repeat(rshape[0], 2, 1).contiguous())
@@ -80,7 +88,8 @@ class PeerObsGather:
         h.barrier(channel=0)  # every rank is done reading the previous content of this slot
         engine.obs_push(self.local_block(slot), self.local_rects(slot),
                         [self.views[slot][p][lo:lo + self.E] for p in peers],
-                        [self.rect_views[slot][p][lo:lo + self.E] for p in peers], stream)
+                        [self.rect_views[slot][p][lo:lo + self.E] for p in peers], stream,
+                        mc_rgb=self.mc_rgb[slot], mc_rect=self.mc_rect[slot])
         h.barrier(channel=1)  # every rank's pushes into this slot have landed
         engine.obs_fill(self.bufs[slot], self.rects[slot], self.prev_rects[slot], lo, lo + self.E, stream)
         return self.bufs[slot]

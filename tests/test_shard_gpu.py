@@ -25,16 +25,20 @@ def _worker(rank, world, port, q, mode="copy"):
     hm = synth.height_map_mm(synth.config1(n, seed=5)["depth_m"])
     a, b = env_shard(n, rank, world)
     eng = TactileEngine(t, max_envs=n, device=f"cuda:{rank}")
-    g = PeerObsGather((b - a, 240, 320, 3), torch.float32, torch.device("cuda", rank), n_slots=2, with_rects=mode == "rects")
+    rects = mode.startswith("rects")
+    g = PeerObsGather((b - a, 240, 320, 3), torch.float32, torch.device("cuda", rank), n_slots=2, with_rects=rects,
+                      multicast=mode == "rects")
+    if rects and rank == 0:
+        print(f"[{mode}] NVSwitch multicast stores: {'yes' if g.mc_rgb[0] else 'no (one store per peer)'}", flush=True)
     ok = True
-    if mode == "rects":
+    if rects:
         for buf in g.bufs:
             buf.fill_(float("nan"))  # the first fill of a slot has to write every pixel outside the rectangles
         torch.cuda.synchronize()
         dist.barrier()
     for step in range(5):  # both slots, slot reuse; in rectangle mode the contacts move between the steps
         slot = step & 1
-        if mode == "rects":
+        if rects:
             hm_s = torch.roll(hm, shifts=(7 * step, -11 * step), dims=(1, 2)) if step else hm
             if step == 3:
                 hm_s = hm_s.clone()
@@ -55,15 +59,17 @@ def _worker(rank, world, port, q, mode="copy"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["copy", "rects"])
+@pytest.mark.parametrize("mode", ["copy", "rects", "rects-unicast"])
 def test_peer_copy_all_gather_matches_single_gpu(mode):
     """copy: whole frames through the copy engines; rects: only the non-flat rectangle of every half frame crosses the link
-    (tx_obs_push / tx_obs_fill), the rest is completed locally from the flat image -- both bit-identical to one GPU."""
+    (tx_obs_push / tx_obs_fill; NVSwitch multicast stores when the symmetric allocation has a multicast mapping, else -- and
+    in the rects-unicast case -- one store per peer), the rest is completed locally from the flat image. All bit-identical to
+    one GPU."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300 + (1 if mode == "rects" else 0)
+    port = 29600 + os.getpid() % 300 + ["copy", "rects", "rects-unicast"].index(mode)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
