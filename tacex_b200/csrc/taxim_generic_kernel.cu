@@ -150,9 +150,12 @@ int taxim_generic_smem_bytes(int H, int W) { return H * W * 9 + 16; }
 
 cudaError_t launch_taxim_generic(const TaximGenericArgs& a, int N, cudaStream_t s)
 {
-    static int smem_set = 0;
+    static int smem_set_dev[64] = {}; // per (function, device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    int& smem_set = smem_set_dev[dev];
     const int smem = taxim_generic_smem_bytes(a.H, a.W);
-    if (smem > smem_set) {
+    if (smem > smem_set || dev == 63) {
         cudaError_t e = cudaFuncSetAttribute(taxim_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         smem_set = smem;

@@ -775,8 +775,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
 
 cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set_dev[64] = {}; // the attribute belongs to the (function, device) pair: one process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
+    bool& attr_set = attr_set_dev[dev];
+    if (!attr_set || dev == 63) {
         cudaError_t e = cudaFuncSetAttribute(taxim_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(taxim_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(taxim_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
