@@ -552,6 +552,7 @@ extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const flo
                             float* depth_host, float* markers_host)
 {
     if (!h || !height_mm_host || !rgb_host || N <= 0) return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: bad argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_step_host: the pipelined host entry point belongs to the 240 x 320 kernel");
     if (markers_host && (!theta_host || h->M <= 0))
         return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: markers need theta and a marker grid");
     if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_step_host: N exceeds max_envs");
