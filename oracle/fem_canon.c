@@ -303,6 +303,33 @@ typedef struct {
     fem_indenter ind0;   /* indenter at the start of the step (lagged friction) */
 } fem_ctx;
 
+/* ---- IPC barrier of a surface vertex against the prescribed indenter ---------------------------------------------------------
+ * ref: contact_system/contact_models/ipc_vertex_half_plane_contact_function.h:12-60 (PH_barrier_energy / gradient_hessian:
+ * B(D) with D the squared distance, G = dB/dD dD/dx, H = d2B/dD2 dD/dx dD/dx^T + dB/dD d2D/dx2), with the half-plane distance
+ * generalised to the signed distance d of the analytic indenter: D = d^2, dD/dx = 2 d n, d2D/dx2 = 2 (n n^T + d Hd). For a point
+ * under a flat face of a box this IS the reference's half-plane model (pinned by tests/test_fem_ref_pin_cpu.py).
+ * Returns 0 (and zero terms) outside the barrier's support; E / G / H (row-major, NOT projected) may be NULL. */
+int fem_vertex_barrier_terms(const fem_cfg* g, const fem_indenter* ind, const double* x, double* E, double* G, double* H)
+{
+    double d, n[3], Hd[9], B, dB, ddB;
+    if (E) *E = 0.0;
+    if (G) memset(G, 0, sizeof(double) * 3);
+    if (H) memset(H, 0, sizeof(double) * 9);
+    fem_indenter_sdf(ind, x, &d, n, Hd);
+    if (!((d * d < g->d_hat * g->d_hat) && d > 0.0)) return 0;
+    const double dt2 = g->dt * g->dt;
+    fem_barrier(d * d, g->d_hat, g->kappa * dt2, &B, &dB, &ddB);
+    if (E) *E = B;
+    double dD[3];
+    for (int a = 0; a < 3; ++a) dD[a] = 2.0 * d * n[a];
+    if (G)
+        for (int a = 0; a < 3; ++a) G[a] = dB * dD[a];
+    if (H)
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) H[3 * a + b] = ddB * dD[a] * dD[b] + dB * 2.0 * (n[a] * n[b] + d * Hd[3 * a + b]);
+    return 1;
+}
+
 /* ---- lagged Coulomb friction of a surface vertex against the prescribed indenter ---------------------------------------
  * ref: contact_system/contact_models/ipc_vertex_half_plane_frictional_contact.cu:29-127,
  *      ipc_vertex_half_plane_contact_function.h:62-151 (compute_tan_basis, PH_friction_energy / gradient_hessian),
@@ -465,17 +492,11 @@ static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, 
     }
     for (int k = 0; k < g->S; ++k) {
         int i = c->surf[k];
-        double d, n[3], Hd[9], dB, ddB;
         double* Hk = Hc + 9 * k;
         memset(Hk, 0, sizeof(double) * 9);
-        fem_indenter_sdf(&c->ind, x + 3 * i, &d, n, Hd);
-        if ((d * d < g->d_hat * g->d_hat) && d > 0.0) {
-            fem_barrier(d * d, g->d_hat, g->kappa * dt2, 0, &dB, &ddB);
-            double dD[3];
-            for (int a = 0; a < 3; ++a) dD[a] = 2.0 * d * n[a];
-            for (int a = 0; a < 3; ++a) G[3 * i + a] += dB * dD[a];
-            for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) Hk[3 * a + b] = ddB * dD[a] * dD[b] + dB * 2.0 * (n[a] * n[b] + d * Hd[3 * a + b]);
+        double Gb[3];
+        if (fem_vertex_barrier_terms(g, &c->ind, x + 3 * i, 0, Gb, Hk)) {
+            for (int a = 0; a < 3; ++a) G[3 * i + a] += Gb[a];
             fem_spd_project(3, Hk);
         }
         if (g->friction_mu > 0.0) {

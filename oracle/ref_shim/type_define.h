@@ -1,0 +1,26 @@
+// Stand-in for the reference's backends/cuda/type_define.h (which pulls muda + Eigen + uipc/common/type_define.h) -- TEST
+// INFRASTRUCTURE, see mini_eigen.h. Same names, float64 like the reference (uipc::Float = double).
+#pragma once
+#include "mini_eigen.h"
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+#define UIPC_GENERIC
+#define UIPC_DEVICE
+#define UIPC_HOST
+namespace uipc {
+using Float = double;
+using Vector2 = Eigen::Matrix<Float, 2, 1>;
+using Vector3 = Eigen::Matrix<Float, 3, 1>;
+using Matrix2x2 = Eigen::Matrix<Float, 2, 2>;
+using Matrix3x3 = Eigen::Matrix<Float, 3, 3>;
+template <class T, int M, int N>
+using Matrix = Eigen::Matrix<T, M, N>;
+template <class T, int N>
+using Vector = Eigen::Matrix<T, N, 1>;
+namespace backend::cuda {
+    using namespace uipc;
+    namespace distance {}
+}
+} // namespace uipc

@@ -1,0 +1,133 @@
+"""Pins the float64 FEM restatement (oracle/fem_canon.c) against the REFERENCE'S OWN SOURCE, compiled unmodified from where it
+lies under /root/reference (libuipc cuda backend; oracle/Makefile target `ref` -> oracle/_ref/libuipc_sym.so, see
+oracle/ref_sym.cpp): the stable Neo-Hookean energy / gradient / Hessian (sym/stable_neo_hookean_3d.inl), the IPC barrier
+(sym/codim_ipc_contact.inl), and the vertex-vs-half-plane normal and frictional contact (ipc_vertex_half_plane_contact_function.h,
+codim_ipc_contact_function.h) that the restatement generalises to analytic indenters: under a flat face of a box indenter the
+two models must coincide. Skipped where the library has not been built (it needs /root/reference; the GPU box has none)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import fem_canon as fc
+
+REF = Path(fc.__file__).resolve().parent / "_ref" / "libuipc_sym.so"
+pytestmark = pytest.mark.skipif(not REF.exists(), reason="oracle/_ref/libuipc_sym.so not built (make -C oracle ref; needs /root/reference)")
+
+DP = C.POINTER(C.c_double)
+
+
+def _d(a):
+    return a.ctypes.data_as(DP)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return C.CDLL(str(REF))
+
+
+@pytest.fixture(scope="module")
+def canon():
+    return fc.lib()
+
+
+def _rot(rng):
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+def test_stable_neo_hookean_matches_reference_source(ref, canon):
+    rng = np.random.default_rng(0)
+    mu, lam = 3355.7, 164429.5  # E = 10 kPa, nu = 0.49
+    for k in range(20):
+        F = (np.eye(3) + (0.05 if k < 10 else 0.6) * rng.standard_normal((3, 3))).T.reshape(-1).copy()
+        E1, g1, H1 = C.c_double(), np.empty(9), np.empty(81)
+        E2, g2, H2 = C.c_double(), np.empty(9), np.empty(81)
+        canon.fem_snh(_d(F), C.c_double(mu), C.c_double(lam), C.byref(E1), _d(g1), _d(H1))
+        ref.ref_snh(_d(F), C.c_double(mu), C.c_double(lam), C.byref(E2), _d(g2), _d(H2))
+        assert abs(E1.value - E2.value) <= 1e-12 * max(abs(E2.value), 1.0)
+        assert np.abs(g1 - g2).max() <= 1e-11 * np.abs(g2).max()
+        assert np.abs(H1 - H2).max() <= 1e-11 * np.abs(H2).max()
+
+
+def test_barrier_matches_reference_source(ref, canon):
+    d_hat, kappa = 5e-4, 1e10 * 1e-4
+    for d in np.geomspace(1e-7, d_hat * 0.999, 25):
+        B1, dB1, ddB1 = C.c_double(), C.c_double(), C.c_double()
+        B2, dB2, ddB2 = C.c_double(), C.c_double(), C.c_double()
+        canon.fem_barrier(C.c_double(d * d), C.c_double(d_hat), C.c_double(kappa), C.byref(B1), C.byref(dB1), C.byref(ddB1))
+        ref.ref_kappa_barrier(C.c_double(kappa), C.c_double(d * d), C.c_double(d_hat), C.c_double(0.0), C.byref(B2), C.byref(dB2),
+                              C.byref(ddB2))
+        for a, b in ((B1, B2), (dB1, dB2), (ddB1, ddB2)):
+            assert abs(a.value - b.value) <= 1e-9 * abs(b.value) + 1e-300
+
+
+def _cfg(friction_mu=0.5):
+    g = fc.FemCfg()
+    g.dt, g.d_hat, g.kappa, g.friction_mu, g.eps_velocity = 0.01, 5e-4, 1e10, friction_mu, 0.01
+    return g
+
+
+def _face_case(rng, rotated):
+    """A box indenter, a vertex under its bottom face at distance d < d_hat, and the reference's half-plane (P, N) of that face."""
+    Rm = _rot(rng) if rotated else np.eye(3)
+    c = rng.uniform(-1e-2, 1e-2, 3)
+    half = np.array([4e-3, 5e-3, 2e-3])
+    ind = fc.make_indenter(1, c, half, R=Rm)
+    N = -Rm[:, 2]
+    P = c - half[2] * Rm[:, 2]
+    d = rng.uniform(0.02, 0.95) * 5e-4
+    loc = np.array([rng.uniform(-0.8, 0.8) * half[0], rng.uniform(-0.8, 0.8) * half[1], -half[2] - d])
+    x = c + Rm @ loc
+    return ind, N.copy(), P.copy(), x.copy(), d
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_vertex_barrier_under_a_flat_face_is_the_reference_half_plane_model(ref, canon, rotated):
+    rng = np.random.default_rng(1)
+    g = _cfg()
+    kap = g.kappa * (g.dt * g.dt)
+    canon.fem_vertex_barrier_terms.restype = C.c_int
+    for _ in range(20):
+        ind, N, P, x, d = _face_case(rng, rotated)
+        E1, G1, H1 = C.c_double(), np.empty(3), np.empty(9)
+        assert canon.fem_vertex_barrier_terms(C.byref(g), C.byref(ind), _d(x), C.byref(E1), _d(G1), _d(H1)) == 1
+        E2, G2, H2 = C.c_double(), np.empty(3), np.empty(9)
+        ref.ref_ph_barrier(C.c_double(kap), C.c_double(g.d_hat), C.c_double(0.0), _d(x), _d(P), _d(N), C.byref(E2), _d(G2), _d(H2))
+        # the distance itself carries ~1e-16 / d of relative rounding (d down to 1e-5 m inside coordinates of 1e-2 m)
+        tol = 1e-8
+        assert abs(E1.value - E2.value) <= tol * abs(E2.value)
+        assert np.abs(G1 - G2).max() <= tol * np.abs(G2).max()
+        assert np.abs(H1 - H2).max() <= tol * np.abs(H2).max()
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_lagged_friction_under_a_flat_face_is_the_reference_half_plane_model(ref, canon, rotated):
+    rng = np.random.default_rng(2)
+    g = _cfg()
+    kap, eps = g.kappa * g.dt * g.dt, g.eps_velocity * g.dt
+    n_stick = n_slip = 0
+    for k in range(40):
+        ind, N, P, xp, d = _face_case(rng, rotated)
+        # stick (|u| < eps) and slip (|u| > eps) displacements, mostly tangential
+        scale = eps * (0.3 if k % 2 == 0 else 5.0)
+        x = xp + scale * rng.standard_normal(3) * np.array([1.0, 1.0, 0.05])
+        e1, e2 = np.empty(3), np.empty(3)
+        ref.ref_tan_basis(_d(N), _d(e1), _d(e2))
+        u2 = ((x - xp) @ e1) ** 2 + ((x - xp) @ e2) ** 2
+        n_stick += u2 < eps * eps
+        n_slip += u2 >= eps * eps
+        E1, G1, H1 = C.c_double(), np.empty(3), np.empty(9)
+        canon.fem_friction_terms(C.byref(g), C.byref(ind), C.byref(ind), _d(xp), _d(x), C.byref(E1), _d(G1), _d(H1))
+        E2, G2, H2 = C.c_double(), np.empty(3), np.empty(9)
+        ref.ref_ph_friction(C.c_double(kap), C.c_double(g.d_hat), C.c_double(0.0), C.c_double(g.friction_mu), C.c_double(eps),
+                            _d(xp), _d(x), _d(P), _d(N), C.byref(E2), _d(G2), _d(H2))
+        tol = 1e-8
+        assert E2.value > 0
+        assert abs(E1.value - E2.value) <= tol * abs(E2.value)
+        assert np.abs(G1 - G2).max() <= tol * np.abs(G2).max()
+        assert np.abs(H1 - H2).max() <= tol * np.abs(H2).max()
+    assert n_stick >= 5 and n_slip >= 5
