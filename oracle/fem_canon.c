@@ -22,11 +22,15 @@
  * Re-design stated in DESIGN.md: the indenter is a PRESCRIBED rigid analytic body (sphere / oriented box), so contact is
  * the reference's vertex-vs-implicit-surface barrier generalised from a half-plane to a signed-distance function, the
  * broad phase (LBVH) disappears, and the CCD step bound is the conservative-advancement bound of a 1-Lipschitz SDF.
- * Friction is not restated yet.
+ * Lagged friction against the prescribed indenter: see friction_lagged / fem_friction_terms below.
  *
- * PARITY UNPINNED: libuipc cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it has no CPU
- * backend) and its tests hold no golden positions for this path. This restatement is pinned only
- * by its own known-answer tests (finite differences, dense solves, eigh) under tests/.
+ * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
+ * has no CPU backend) and its tests hold no golden positions for this path: the SOLVER LOOP of this
+ * restatement (Newton, PCG, line search, CCD) is UNPINNED, checked only by known-answer tests (finite differences, dense solves,
+ * eigh). The per-element physics IS pinned against the reference's own source, compiled unmodified from /root/reference
+ * (oracle/ref_sym.cpp -> oracle/_ref/libuipc_sym.so): fem_snh, fem_barrier, fem_vertex_barrier_terms and fem_friction_terms
+ * agree with sym/stable_neo_hookean_3d.inl, sym/codim_ipc_contact.inl, ipc_vertex_half_plane_contact_function.h to 1e-8..1e-12
+ * (tests/test_fem_ref_pin_cpu.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this library.
  */

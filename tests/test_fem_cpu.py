@@ -1,4 +1,5 @@
-"""CPU suite for the gel FEM restatement (oracle/fem_canon.c). libuipc cannot run here (PARITY UNPINNED), so the
+"""CPU suite for the gel FEM restatement (oracle/fem_canon.c). libuipc cannot run here (solver loop UNPINNED; the per-element physics is pinned against the reference source in
+test_fem_ref_pin_cpu.py), so the
 restatement is pinned by known-answer tests: finite differences, numpy.linalg.eigh / solve (protocol P5)."""
 import ctypes as C
 
