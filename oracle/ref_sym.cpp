@@ -5,11 +5,14 @@
 //                                                                       C1-clamped friction f0 / f1 / f2, 2 x 2 Hessian, normal_force
 //   contact_system/contact_models/ipc_vertex_half_plane_contact_function.h   PH_barrier_* / PH_friction_* (vertex vs half-plane,
 //                                                                       sym/vertex_half_plane_distance.inl)
+//   (libuipc/include) uipc/constitution/conversion.h                    EP_to_lame, what ElasticModuli::youngs_poisson calls
+//                                                                       (src/constitution/elastic_moduli.cpp:20-27)
 // Eigen / muda are not in this image: oracle/ref_shim/ supplies a minimal stand-in (type_define.h, mini_eigen.h, a 2 x 2 evd) and
 // empty headers for the includes the compiled subset does not use. Built by oracle/Makefile into oracle/_ref/libuipc_sym.so (only
 // where /root/reference exists); used by tests/test_fem_ref_pin_cpu.py to pin oracle/fem_canon.c.
 #include <type_define.h>
 #include <contact_system/contact_models/ipc_vertex_half_plane_contact_function.h>
+#include <uipc/constitution/conversion.h> // frontend: Young's modulus / Poisson ratio -> Lame parameters (header-only)
 
 namespace ref_snh_ns {
 using namespace uipc;
@@ -92,6 +95,8 @@ void ref_ph_friction(double kappa, double d_hat, double thickness, double mu, do
         for (int j = 0; j < 3; ++j) H[3 * i + j] = h(i, j);
     }
 }
+
+void ref_ep_to_lame(double E, double nu, double* lambda, double* mu) { uipc::constitution::EP_to_lame(E, nu, *lambda, *mu); }
 
 void ref_tan_basis(const double* N, double* e1, double* e2)
 {

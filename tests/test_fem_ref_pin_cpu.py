@@ -131,3 +131,15 @@ def test_lagged_friction_under_a_flat_face_is_the_reference_half_plane_model(ref
         assert np.abs(G1 - G2).max() <= tol * np.abs(G2).max()
         assert np.abs(H1 - H2).max() <= tol * np.abs(H2).max()
     assert n_stick >= 5 and n_slip >= 5
+
+
+def test_lame_parameters_match_reference_frontend(ref):
+    """ElasticModuli::youngs_poisson(E * MPa, nu) of the gel object (ref: tacex_uipc/objects/uipc_object.py:453-455,
+    libuipc src/constitution/elastic_moduli.cpp:20-27 -> include/uipc/constitution/conversion.h EP_to_lame)."""
+    from tacex_b200.gel_mesh import lame
+
+    for E, nu in [(1e4, 0.49), (0.01e6, 0.49), (5e5, 0.3), (2e9, 0.0)]:
+        lam_r, mu_r = C.c_double(), C.c_double()
+        ref.ref_ep_to_lame(C.c_double(E), C.c_double(nu), C.byref(lam_r), C.byref(mu_r))
+        lam, mu = lame(E, nu)
+        assert abs(lam - lam_r.value) <= 1e-12 * max(abs(lam_r.value), 1.0) and abs(mu - mu_r.value) <= 1e-12 * mu_r.value
