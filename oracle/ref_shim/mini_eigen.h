@@ -22,6 +22,13 @@ struct DiagRef {
 };
 
 template <class T, int R, int C>
+struct ColRef { // assignable column of a matrix (m.col(j) = v)
+    Matrix<T, R, C>* m;
+    int j;
+    ColRef& operator=(const Matrix<T, R, 1>& v) { for (int i = 0; i < R; ++i) (*m)(i, j) = v.d[i]; return *this; }
+};
+
+template <class T, int R, int C>
 struct Matrix {
     T d[R * C];
     Matrix() { for (int i = 0; i < R * C; ++i) d[i] = T(0); }
@@ -65,6 +72,15 @@ struct Matrix {
                 m(i, j) = s;
             }
         return m;
+    }
+    ColRef<T, R, C> col(int j) { return ColRef<T, R, C>{this, j}; }
+    Matrix<T, R, 1> col(int j) const { Matrix<T, R, 1> v; for (int i = 0; i < R; ++i) v.d[i] = (*this)(i, j); return v; }
+    T determinant() const
+    {
+        static_assert(R == 3 && C == 3, "3 x 3");
+        const Matrix& a = *this;
+        return a(0, 0) * (a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1)) - a(0, 1) * (a(1, 0) * a(2, 2) - a(1, 2) * a(2, 0)) +
+               a(0, 2) * (a(1, 0) * a(2, 1) - a(1, 1) * a(2, 0));
     }
     DiagRef<T, R> diagonal() { static_assert(R == C, "square"); return DiagRef<T, R>{this}; }
     Matrix<T, R, R> asDiagonal() const { static_assert(C == 1, "vector"); Matrix<T, R, R> m; for (int i = 0; i < R; ++i) m(i, i) = d[i]; return m; }

@@ -15,6 +15,11 @@ using Vector2 = Eigen::Matrix<Float, 2, 1>;
 using Vector3 = Eigen::Matrix<Float, 3, 1>;
 using Matrix2x2 = Eigen::Matrix<Float, 2, 2>;
 using Matrix3x3 = Eigen::Matrix<Float, 3, 3>;
+using Vector9 = Eigen::Matrix<Float, 9, 1>;
+using Vector12 = Eigen::Matrix<Float, 12, 1>;
+using Matrix9x9 = Eigen::Matrix<Float, 9, 9>;
+using Matrix9x12 = Eigen::Matrix<Float, 9, 12>;
+using Matrix12x12 = Eigen::Matrix<Float, 12, 12>;
 template <class T, int M, int N>
 using Matrix = Eigen::Matrix<T, M, N>;
 template <class T, int N>

@@ -5,6 +5,7 @@
 //                                                                       C1-clamped friction f0 / f1 / f2, 2 x 2 Hessian, normal_force
 //   contact_system/contact_models/ipc_vertex_half_plane_contact_function.h   PH_barrier_* / PH_friction_* (vertex vs half-plane,
 //                                                                       sym/vertex_half_plane_distance.inl)
+//   finite_element/fem_utils.cu                                         Ds, Dm_inv, F = Ds Dm^-1, dFdx (9 x 12) of a tetrahedron
 //   (libuipc/include) uipc/constitution/conversion.h                    EP_to_lame, what ElasticModuli::youngs_poisson calls
 //                                                                       (src/constitution/elastic_moduli.cpp:20-27)
 // Eigen / muda are not in this image: oracle/ref_shim/ supplies a minimal stand-in (type_define.h, mini_eigen.h, a 2 x 2 evd) and
@@ -13,6 +14,13 @@
 #include <type_define.h>
 #include <contact_system/contact_models/ipc_vertex_half_plane_contact_function.h>
 #include <uipc/constitution/conversion.h> // frontend: Young's modulus / Poisson ratio -> Lame parameters (header-only)
+
+#include <finite_element/fem_utils.cu> // Ds, Dm_inv, F, dFdx (9 x 12): plain functions, host-compilable
+#include <cstdlib>
+namespace uipc::backend::cuda { // mentioned by fem_utils.cu's invariant helpers, never called by the pin tests
+Float ddot(const Matrix3x3&, const Matrix3x3&) { std::abort(); }
+void svd(const Matrix3x3&, Matrix3x3&, Vector3&, Matrix3x3&) noexcept { std::abort(); }
+} // namespace uipc::backend::cuda
 
 namespace ref_snh_ns {
 using namespace uipc;
@@ -97,6 +105,23 @@ void ref_ph_friction(double kappa, double d_hat, double thickness, double mu, do
 }
 
 void ref_ep_to_lame(double E, double nu, double* lambda, double* mu) { uipc::constitution::EP_to_lame(E, nu, *lambda, *mu); }
+
+// one tetrahedron: X / x = 4 rest / current vertices (12 doubles each); Dm^-1 row-major 3 x 3, F as column-major vec (the VecF
+// of the constitution), dFdx row-major 9 x 12 (rows: VecF, columns: the 12 vertex coordinates)
+void ref_tet(const double* X, const double* x, double* DmInv, double* vecF, double* dFdx)
+{
+    namespace fem = uipc::backend::cuda::fem;
+    const Matrix3x3 Di = fem::Dm_inv(v3(X), v3(X + 3), v3(X + 6), v3(X + 9));
+    const Matrix3x3 F = fem::F(v3(x), v3(x + 3), v3(x + 6), v3(x + 9), Di);
+    const Matrix9x12 P = fem::dFdx(Di);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            DmInv[3 * i + j] = Di(i, j);
+            vecF[3 * j + i] = F(i, j);
+        }
+    for (int i = 0; i < 9; ++i)
+        for (int j = 0; j < 12; ++j) dFdx[12 * i + j] = P(i, j);
+}
 
 void ref_tan_basis(const double* N, double* e1, double* e2)
 {

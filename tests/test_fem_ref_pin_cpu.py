@@ -143,3 +143,44 @@ def test_lame_parameters_match_reference_frontend(ref):
         ref.ref_ep_to_lame(C.c_double(E), C.c_double(nu), C.byref(lam_r), C.byref(mu_r))
         lam, mu = lame(E, nu)
         assert abs(lam - lam_r.value) <= 1e-12 * max(abs(lam_r.value), 1.0) and abs(mu - mu_r.value) <= 1e-12 * mu_r.value
+
+
+def test_per_tet_assembly_matches_reference_fem_utils_and_constitution(ref, canon):
+    """One tetrahedron: the Newton matrix and right-hand side of the restatement (inertia + dt^2 V dFdx^T spd(H9) dFdx, gradient
+    dt^2 V dFdx^T dE/dF) against the reference's own Ds / Dm_inv / F / dFdx (finite_element/fem_utils.cu) combined with its
+    stable Neo-Hookean gradient / Hessian (sym/stable_neo_hookean_3d.inl); make_spd (utils/make_spd.h: eigenvalue clamp) via
+    numpy.linalg.eigh."""
+    rng = np.random.default_rng(5)
+    mu, lam, dt = 3355.7, 164429.5, 0.01
+    for k in range(10):
+        X = np.array([[0, 0, 0], [2e-3, 0, 0], [0, 2e-3, 0], [0, 0, 1.5e-3]]) + 2e-4 * rng.standard_normal((4, 3))
+        if np.linalg.det((X[1:] - X[0]).T) < 0:
+            X[[1, 2]] = X[[2, 1]]
+        x = X + (2e-5 if k < 5 else 4e-4) * rng.standard_normal((4, 3))
+        tets = np.array([[0, 1, 2, 3]], np.int32)
+        g = fc.FemCfg()
+        g.V, g.T, g.A, g.S, g.dt, g.mu, g.lam = 4, 1, 0, 0, dt, mu, lam
+        g.d_hat, g.kappa, g.attach_strength, g.friction_mu, g.eps_velocity = 5e-4, 1e10, 0.0, 0.0, 0.01
+        Dm_inv, vol, mass = np.empty(9), np.empty(1), np.empty(4)
+        canon.fem_precompute(4, 1, _d(X), fc._i(tets), C.c_double(1e3), 1, _d(Dm_inv), _d(vol), _d(mass))
+        xt = x + 1e-6 * rng.standard_normal((4, 3))
+        A, b, E = np.zeros((12, 12)), np.zeros(12), C.c_double()
+        far = fc.make_indenter(0, (0, 0, 1.0), (1e-3, 0, 0))
+        none_i, none_d = np.zeros(1, np.int32), np.zeros(3)
+        canon.fem_assemble_dense(C.byref(g), fc._i(tets), _d(Dm_inv), _d(vol), _d(mass), fc._i(none_i), fc._i(none_i), _d(none_d),
+                                 C.byref(far), _d(x), _d(X), _d(xt), C.c_double(1.0), _d(A), _d(b), C.byref(E))
+        # reference side
+        Di, vf, P = np.empty(9), np.empty(9), np.empty(108)
+        ref.ref_tet(_d(np.ascontiguousarray(X.reshape(-1))), _d(np.ascontiguousarray(x.reshape(-1))), _d(Di), _d(vf), _d(P))
+        P = P.reshape(9, 12)
+        assert np.abs(np.sort(np.abs(Dm_inv)) - np.sort(np.abs(Di))).max() <= 1e-9 * np.abs(Di).max()  # same matrix (layout aside)
+        Er, gr, Hr = C.c_double(), np.empty(9), np.empty(81)
+        ref.ref_snh(_d(vf), C.c_double(mu), C.c_double(lam), C.byref(Er), _d(gr), _d(Hr))
+        w, Q = np.linalg.eigh(Hr.reshape(9, 9))
+        Hspd = (Q * np.maximum(w, 0.0)) @ Q.T
+        M = np.repeat(mass, 3)
+        s = dt * dt * vol[0]
+        G_ref = M * (x - xt).reshape(-1) + s * (P.T @ gr)
+        A_ref = np.diag(M) + s * (P.T @ Hspd @ P)
+        assert np.abs(-b - G_ref).max() <= 1e-9 * np.abs(G_ref).max()
+        assert np.abs(A - A_ref).max() <= 1e-9 * np.abs(A_ref).max()
