@@ -1,0 +1,61 @@
+"""Container-only tests (marker `refbox`): the canonical restatement against the reference EXECUTED here on inputs that are NOT
+part of the committed fixtures -- fresh seeds of the config-2 generator (four indenter kinds, random pose and yaw), a batch at a
+time as the reference runs them. Skipped where /root/reference does not exist (e.g. the GPU box)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import H, W
+
+pytestmark = pytest.mark.refbox
+
+
+@pytest.fixture(scope="module")
+def ref_taxim():
+    from oracle import ref_bootstrap as rb
+
+    if not rb.available():
+        pytest.skip("reference checkout not present on this machine")
+    torch.set_num_threads(1)  # the reference's FFT noise depends on the thread count
+    return rb, rb.load_taxim()
+
+
+@pytest.mark.parametrize("seed", [101, 202])
+def test_canonical_vs_executed_reference_on_fresh_inputs(ref_taxim, canon_taxim, seed):
+    from tacex_b200 import synth
+
+    rb, tx = ref_taxim
+    hm = synth.height_map_mm(synth.config2(12, seed=seed)["depth_m"])
+    press = rb.ref_indentation_depth(hm)
+    dg, mask = rb.ref_deformed_gel(tx, hm, press)
+    mag, _, im, idr = rb.ref_normals_bins(tx, dg)
+    rgb_ref = rb.ref_render(tx, hm, press).numpy()
+    assert np.array_equal(canon_taxim.indentation_depth(hm.numpy()), press.numpy())
+    o = canon_taxim.render(hm.numpy(), press.numpy())
+    assert np.abs(o["deformed"] - dg.numpy()).max() <= 1e-5                     # P1
+    assert (o["mask"].astype(bool) != mask.numpy()).sum() <= 4
+    well = (mag >= 1e-3).numpy()
+    agree = (o["idx_mag"] == im.numpy()) & (o["idx_dir"] == idr.numpy())
+    assert agree[well].mean() >= 0.99                                            # P2
+    d = np.abs(o["rgb"] - rgb_ref).max(-1)
+    assert d[agree].max() <= 1e-5
+    assert (d[well] <= 1e-3).mean() >= 0.99
+
+
+def test_fots_vs_executed_reference_on_fresh_inputs(ref_taxim, canon_taxim):
+    """Two trajectory samples of fresh config-2 envs through the reference's per-env loop around the unmodified MarkerMotion."""
+    from oracle import canon
+    from tacex_b200 import synth
+
+    rb, tx = ref_taxim
+    c2 = synth.config2(6, seed=303)
+    hm0, hm1 = synth.height_map_mm(c2["depth_m0"]), synth.height_map_mm(c2["depth_m"])
+    rf = rb.RefFots(tx, rows=9, cols=11, x0=15, y0=26)
+    cf = canon.CanonFots(H, W, 9, 11, 15, 26)
+    for hm, th in ((hm0, c2["theta0"]), (hm1, c2["theta"])):
+        press = rb.ref_indentation_depth(hm)
+        ref = rf.step(hm, press, th.numpy()).numpy()
+        o = canon_taxim.render(hm.numpy(), press.numpy(), want=("deformed", "mask"))
+        mine = cf.step(o["deformed"], o["mask"], press.numpy(), th.numpy().astype(np.float32))
+        assert np.abs(mine - ref).max() <= 1.958  # P4: 1e-4 m at 19.58 px/mm
+        assert np.abs(mine - ref).max() <= 1e-2   # observed: << 0.01 px
