@@ -273,6 +273,8 @@ def main() -> None:
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (stdout by default) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     E, K, Wm = args.envs, args.steps, max(args.warmup, 3)
