@@ -115,6 +115,45 @@ class CanonTaxim:
         return out
 
 
+class _ShadowCfg(C.Structure):
+    _fields_ = [("D", C.c_int), ("Hn", C.c_int), ("S", C.c_int), ("F", C.c_int), ("depth_0", C.c_float),
+                ("height_precision", C.c_float), ("discretize_precision", C.c_float), ("step_x", C.c_float), ("step_y", C.c_float),
+                ("dil", (C.c_int * 2) * 2), ("ks_sx", C.c_int), ("ks_sy", C.c_int)]
+
+
+def render_shadow(ct: "CanonTaxim", st, hm_mm: np.ndarray, press_mm: np.ndarray, want_boundary: bool = False,
+                  want_shadow_img: bool = False):
+    """Canonical Taxim render WITH shadows (ref: taxim_torch.py:260-346). ``st`` = tacex_b200.calib.ShadowTables."""
+    hm = np.ascontiguousarray(hm_mm, np.float32)
+    pr = np.ascontiguousarray(press_mm, np.float32)
+    N = hm.shape[0]
+    sc = _ShadowCfg()
+    sc.D, sc.Hn, sc.S = st.table.shape[1], st.table.shape[2], st.table.shape[3]
+    sc.F = st.fan_cos.shape[1]
+    sc.depth_0, sc.height_precision, sc.discretize_precision = st.depth_0, st.height_precision, st.discretize_precision
+    sc.step_x, sc.step_y = st.step_x, st.step_y
+    for r in range(2):
+        sc.dil[r][0], sc.dil[r][1] = st.dilate_rounds[r]
+    tx = np.ascontiguousarray(st.blur_taps[0], np.float32)
+    ty = np.ascontiguousarray(st.blur_taps[1], np.float32)
+    sc.ks_sx, sc.ks_sy = tx.size, ty.size
+    tab = np.ascontiguousarray(st.table, np.float32)
+    fc_, fs_ = np.ascontiguousarray(st.fan_cos, np.float32), np.ascontiguousarray(st.fan_sin, np.float32)
+    rgb = np.empty((N, ct.H, ct.W, 3), np.float32)
+    bnd = np.empty((N, ct.H, ct.W), np.uint8) if want_boundary else None
+    shi = np.empty((N, 3, ct.H, ct.W), np.float32) if want_shadow_img else None
+    lib().canon_taxim_render_shadow.restype = C.c_int
+    rc = lib().canon_taxim_render_shadow(C.byref(ct.cfg), _p(ct.taps, C.c_float), _p(ct.poly, C.c_float), _p(ct.bg, C.c_float),
+                                         _p(ct.gel, C.c_float), _p(hm, C.c_float), _p(pr, C.c_float), N, C.byref(sc),
+                                         _p(tab, C.c_float), _p(fc_, C.c_float), _p(fs_, C.c_float), _p(tx, C.c_float),
+                                         _p(ty, C.c_float), _p(rgb, C.c_float), _p(bnd, C.c_uint8), _p(shi, C.c_float))
+    if rc != 0:
+        raise MemoryError("canon_taxim_render_shadow failed")
+    if want_boundary or want_shadow_img:
+        return {"rgb": rgb, "boundary": bnd, "shadow_img": shi}
+    return rgb
+
+
 class CanonFots:
     """Canonical FOTS marker motion with the per-env trajectory state the reference keeps in python lists."""
 

@@ -30,14 +30,31 @@ def available() -> bool:
 
 
 _taxim = None
+SCATTER_CAPTURE: dict = {}
+
+
+def _torch_scatter_stand_in():
+    """torch_scatter is not in this image. The reference's shadow branch calls exactly one function of it,
+    ``scatter_min(src [C, K], index [K], dim_size=S, out=out [C, S])`` (taxim_torch.py:330-335); its published semantics
+    (out[c, index[k]] = min(out[c, index[k]], src[c, k])) are torch's own ``scatter_reduce_(..., 'amin')``."""
+    m = types.ModuleType("torch_scatter")
+
+    def scatter_min(src, index, dim=-1, out=None, dim_size=None):
+        idx = index.expand_as(src) if index.dim() < src.dim() else index
+        out.scatter_reduce_(-1, idx, src, reduce="amin", include_self=True)
+        SCATTER_CAPTURE["shadow_img_flat"] = out.clone()  # lets the tests see the reference's intermediate shadow image
+        return out, None
+
+    m.scatter_min = scatter_min
+    return m
 
 
 def load_taxim(device: str = "cpu"):
-    """``sim.Taxim(calib_folder=..., backend='torch')`` of the reference. torch_scatter is only used by the shadow
-    branch (taxim_torch.py:330), which every GelSight Mini preset disables, so an empty stub module suffices."""
+    """``sim.Taxim(calib_folder=..., backend='torch')`` of the reference. torch_scatter (absent here) is only used by the
+    shadow branch (taxim_torch.py:330): see _torch_scatter_stand_in."""
     global _taxim
     if _taxim is None:
-        sys.modules.setdefault("torch_scatter", types.ModuleType("torch_scatter"))
+        sys.modules.setdefault("torch_scatter", _torch_scatter_stand_in())
         if str(TAXIM_PKG) not in sys.path:
             sys.path.insert(0, str(TAXIM_PKG))
         import sim  # noqa: PLC0415  (the reference's gpu_taxim/sim package)
@@ -75,6 +92,11 @@ def ref_tables(tx, shape=(240, 320)) -> dict:
 def ref_render(tx, hm_mm: torch.Tensor, press_mm: torch.Tensor) -> torch.Tensor:
     """(N,H,W,3) exactly as TaximSimulator.optical_simulation returns it (taxim_sim.py:104-111)."""
     return tx.render_direct(hm_mm, with_shadow=False, press_depth=press_mm, orig_hm_fmt=False).movedim(1, 3).contiguous()
+
+
+def ref_render_shadow(tx, hm_mm: torch.Tensor, press_mm: torch.Tensor) -> torch.Tensor:
+    """(N,H,W,3) with_shadow=True (taxim_torch.py:260-346), otherwise as ref_render."""
+    return tx.render_direct(hm_mm, with_shadow=True, press_depth=press_mm, orig_hm_fmt=False).movedim(1, 3).contiguous()
 
 
 def ref_deformed_gel(tx, hm_mm: torch.Tensor, press_mm: torch.Tensor):

@@ -279,6 +279,196 @@ int canon_taxim_render(const canon_cfg* cfg, const float* taps, const float* pol
     return status;
 }
 
+/* ---------------- Taxim SHADOW branch (with_shadow = True; ref: taxim_torch.py:260-346) ----------------
+ * Restated on top of the same canonical deformation / normals / polynomial image as canon_taxim_render (the code below repeats
+ * that function's steps on purpose: the no-shadow checker stays untouched). Canonical choices: the ray-fan trigonometry comes in
+ * as float32 tables (the reference evaluates torch.cos / torch.sin of the same float32 angles at init), every coordinate is
+ * step * (s + 1) * cos -> + pixel -> truncation toward zero, all in float32 like the tensor expression; blurs are the direct
+ * separable correlation of canon_blur. */
+typedef struct {
+    int D, Hn, S, F;          /* directions (63), height entries (24), table row length (51), fan rays (4) */
+    float depth_0;            /* 0.4 */
+    float height_precision;   /* 0.1 */
+    float discretize_precision; /* 0.1 */
+    float step_x, step_y;     /* 0.625 */
+    int dil[2][2];            /* two dilation rounds: (ky, kx) */
+    int ks_sx, ks_sy;         /* shadow blur tap counts */
+} canon_shadow_cfg;
+
+/* conv2d(ones(ky, kx), padding='same') != 0 of a 0/1 image, zero padded; torch pads the extra element of an even kernel on the
+ * right / bottom: out[y][x] = OR over in[y - (ky-1)/2 .. + ky - 1][x - (kx-1)/2 .. + kx - 1] */
+static void dilate_same(const uint8_t* in, uint8_t* out, int H, int W, int ky, int kx)
+{
+    const int py = (ky - 1) / 2, px = (kx - 1) / 2;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            uint8_t v = 0;
+            for (int j = 0; j < ky && !v; ++j) {
+                const int yy = y - py + j;
+                if (yy < 0 || yy >= H) continue;
+                for (int i = 0; i < kx; ++i) {
+                    const int xx = x - px + i;
+                    if (xx >= 0 && xx < W && in[yy * W + xx]) { v = 1; break; }
+                }
+            }
+            out[y * W + x] = v;
+        }
+}
+
+int canon_taxim_render_shadow(const canon_cfg* cfg, const float* taps, const float* poly, const float* bg, const float* gel,
+                              const float* hm_mm, const float* press, int N, const canon_shadow_cfg* sc,
+                              const float* table /*[3][D][Hn][S]*/, const float* fan_cos /*[D][F]*/, const float* fan_sin,
+                              const float* staps_x, const float* staps_y, float* rgb /*[N][H][W][3]*/, uint8_t* boundary_out,
+                              float* shadow_out /*[N][3][H][W] or NULL: the scatter-min image, +inf where no shadow sample landed*/)
+{
+    const int H = cfg->H, W = cfg->W, HW = H * W, nb = cfg->num_bins;
+    int status = 0;
+#pragma omp parallel for schedule(dynamic)
+    for (int n = 0; n < N; ++n) {
+        float* h = (float*)malloc(sizeof(float) * HW);
+        float* j = (float*)malloc(sizeof(float) * HW);
+        float* b = (float*)malloc(sizeof(float) * HW);
+        float* t1 = (float*)malloc(sizeof(float) * HW);
+        float* t2 = (float*)malloc(sizeof(float) * HW);
+        uint8_t* mk = (uint8_t*)malloc(HW);
+        uint8_t* d1 = (uint8_t*)malloc(HW);
+        uint8_t* d2 = (uint8_t*)malloc(HW);
+        float* mag = (float*)malloc(sizeof(float) * HW);
+        float* dir = (float*)malloc(sizeof(float) * HW);
+        float* raw = (float*)malloc(sizeof(float) * 3 * HW);  /* polynomial image without background, [3][H][W] */
+        float* sh = (float*)malloc(sizeof(float) * 3 * HW);   /* shadow image */
+        float* dpx = (float*)malloc(sizeof(float) * HW);
+        if (!h || !j || !b || !t1 || !t2 || !mk || !d1 || !d2 || !mag || !dir || !raw || !sh || !dpx) {
+            status = -1;
+        } else {
+            const float* hm = hm_mm + (size_t)n * HW;
+            /* ---- deformation, identical to canon_taxim_render ---- */
+            float m = hm[0];
+            for (int i = 1; i < HW; ++i) m = fminf(m, hm[i]);
+            for (int i = 0; i < HW; ++i) h[i] = (hm[i] - m) - press[n];
+            float hmin = h[0];
+            for (int i = 1; i < HW; ++i) hmin = fminf(hmin, h[i]);
+            float thr = (-(-hmin)) * cfg->contact_scale;
+            for (int i = 0; i < HW; ++i) {
+                float g = gel ? gel[i] : 0.0f;
+                int contact = h[i] < 0.0f;
+                j[i] = fminf(h[i], g);
+                mk[i] = (uint8_t)(((j[i] - g) < thr) && contact);
+            }
+            memcpy(b, j, sizeof(float) * HW);
+            for (int l = 0; l < cfg->n_blurs; ++l) {
+                canon_blur(b, t1, t2, H, W, taps + cfg->off_x[l], cfg->ksx[l], taps + cfg->off_y[l], cfg->ksy[l]);
+                if (l < cfg->n_blurs - 1) {
+                    for (int i = 0; i < HW; ++i) b[i] = mk[i] ? j[i] : t2[i];
+                } else {
+                    memcpy(b, t2, sizeof(float) * HW);
+                }
+            }
+            /* ---- normals, identical to canon_taxim_render ---- */
+            const float inv_pixmm = 1.0f / cfg->pixmm;
+            const float sy = (float)H / cfg->calib_h, sx = (float)W / cfg->calib_w;
+            for (int i = 0; i < HW; ++i) t1[i] = b[i] * inv_pixmm;
+            for (int y = 1; y < H - 1; ++y)
+                for (int x = 1; x < W - 1; ++x) {
+                    float top = t1[(y - 1) * W + x], bot = t1[(y + 1) * W + x];
+                    float left = t1[y * W + x - 1], right = t1[y * W + x + 1];
+                    float gx = ((top - bot) * 0.5f) * sy;
+                    float gy = ((left - right) * 0.5f) * sx;
+                    float tt = sqrtf(fmaf(gx, gx, gy * gy));
+                    mag[y * W + x] = canon_atanf(tt);
+                    dir[y * W + x] = (tt != 0.0f) ? canon_atan2f(gx, gy) : 0.0f;
+                }
+            for (int y = 0; y < H; ++y) {
+                int yy = y < 1 ? 1 : (y > H - 2 ? H - 2 : y);
+                for (int x = 0; x < W; ++x) {
+                    int xx = x < 1 ? 1 : (x > W - 2 ? W - 2 : x);
+                    if (yy != y || xx != x) {
+                        mag[y * W + x] = mag[yy * W + xx];
+                        dir[y * W + x] = dir[yy * W + xx];
+                    }
+                }
+            }
+            /* ---- polynomial image WITHOUT background (ref: taxim_torch.py:248-253 sim_img_r) ---- */
+            const float inv_xbin = (float)(1.0 / (0.5 * M_PI / (nb - 1)));
+            const float inv_ybin = (float)(1.0 / (2.0 * M_PI / (nb - 1)));
+            const float pi_f = (float)M_PI;
+            const float fx = cfg->calib_w / (float)W, fy = cfg->calib_h / (float)H;
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    int i = y * W + x;
+                    int im = (int)floorf(mag[i] * inv_xbin);
+                    int id = (int)floorf((dir[i] + pi_f) * inv_ybin);
+                    if (im < 0) im = 0;
+                    if (im > nb - 1) im = nb - 1;
+                    if (id < 0) id = 0;
+                    if (id > nb - 1) id = nb - 1;
+                    float xf = (float)x * fx, yf = (float)y * fy;
+                    float f0 = xf * xf, f1 = yf * yf, f2 = xf * yf;
+                    for (int c = 0; c < 3; ++c) {
+                        const float* p = poly + (((size_t)c * nb + im) * nb + id) * 6;
+                        float s = p[5];
+                        s = fmaf(p[4], yf, s);
+                        s = fmaf(p[3], xf, s);
+                        s = fmaf(p[2], f2, s);
+                        s = fmaf(p[1], f1, s);
+                        s = fmaf(p[0], f0, s);
+                        raw[(size_t)c * HW + i] = s;
+                    }
+                }
+            /* ---- shadow attachment area: dilated mask minus mask (ref: taxim_torch.py:260-272) ---- */
+            dilate_same(mk, d1, H, W, sc->dil[0][0], sc->dil[0][1]);
+            dilate_same(d1, d2, H, W, sc->dil[1][0], sc->dil[1][1]);
+            for (int i = 0; i < HW; ++i) d2[i] = (uint8_t)(d2[i] && !mk[i]);
+            if (boundary_out) memcpy(boundary_out + (size_t)n * HW, d2, HW);
+            /* ---- cast the shadows (ref: taxim_torch.py:274-336) ---- */
+            for (int i = 0; i < 3 * HW; ++i) sh[i] = INFINITY;
+            for (int i = 0; i < HW; ++i) dpx[i] = b[i] / cfg->pixmm;
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    const int i = y * W + x;
+                    if (!d2[i]) continue;
+                    int nidx = (int)floorf((dir[i] + pi_f) / sc->discretize_precision);
+                    if (nidx < 0) nidx = 0;
+                    if (nidx > sc->D - 1) nidx = sc->D - 1;
+                    const float g = gel ? gel[i] : 0.0f;
+                    const float ch_px = (g - b[i]) / cfg->pixmm;
+                    int hidx = (int)floorf((ch_px * cfg->pixmm - sc->depth_0) / sc->height_precision) + 6;
+                    const int hmax = sc->Hn - 1;
+                    if (hidx < 0 || hidx >= hmax) hidx = hmax;
+                    for (int f = 0; f < sc->F; ++f) {
+                        const float cs = fan_cos[nidx * sc->F + f], sn = fan_sin[nidx * sc->F + f];
+                        for (int s = 0; s < sc->S; ++s) {
+                            const float kx_ = sc->step_x * (float)(s + 1), ky_ = sc->step_y * (float)(s + 1);
+                            const long cx = (long)((float)x + kx_ * cs);
+                            const long cy = (long)((float)y + ky_ * sn);
+                            if (cx < 0 || cx >= W || cy < 0 || cy >= H) continue;
+                            const int tgt = (int)cy * W + (int)cx;
+                            if (!(dpx[i] < dpx[tgt])) continue;
+                            for (int c = 0; c < 3; ++c) {
+                                const float v = table[(((size_t)c * sc->D + nidx) * sc->Hn + hidx) * sc->S + s];
+                                if (v < sh[(size_t)c * HW + tgt]) sh[(size_t)c * HW + tgt] = v;
+                            }
+                        }
+                    }
+                }
+            if (shadow_out) memcpy(shadow_out + (size_t)n * 3 * HW, sh, sizeof(float) * 3 * HW);
+            /* ---- min, shadow blur, + background, final blur, clip (ref: taxim_torch.py:337-346) ---- */
+            const int lf = cfg->n_blurs - 1;
+            for (int c = 0; c < 3; ++c) {
+                float* r = raw + (size_t)c * HW;
+                for (int i = 0; i < HW; ++i) r[i] = fminf(r[i], sh[(size_t)c * HW + i]);
+                canon_blur(r, t1, t2, H, W, staps_x, sc->ks_sx, staps_y, sc->ks_sy);
+                for (int i = 0; i < HW; ++i) t2[i] = t2[i] + bg[(size_t)c * HW + i];
+                canon_blur(t2, t1, r, H, W, taps + cfg->off_x[lf], cfg->ksx[lf], taps + cfg->off_y[lf], cfg->ksy[lf]);
+                for (int i = 0; i < HW; ++i) rgb[((size_t)n * HW + i) * 3 + c] = fminf(fmaxf(r[i], 0.0f), 1.0f);
+            }
+        }
+        free(h); free(j); free(b); free(t1); free(t2); free(mk); free(d1); free(d2); free(mag); free(dir); free(raw); free(sh);
+        free(dpx);
+    }
+    return status;
+}
+
 /* ---------------- FOTS marker motion (float64 like the NumPy reference) ---------------- */
 
 typedef struct {

@@ -184,3 +184,69 @@ class TaximTables:
     def bin_widths(self) -> tuple[float, float]:
         nb = self.params.num_bins
         return 0.5 * math.pi / (nb - 1), 2 * math.pi / (nb - 1)
+
+
+@dataclass
+class ShadowTables:
+    """Init-time data of the Taxim SHADOW branch (``with_shadow=True``; ref: taxim_torch.py:96-125, 260-346, taxim_impl.py:17-47).
+
+    Host-side preparation only: the tables are what a device implementation (and the CPU checker) consumes. The trigonometry of
+    the ray fan is evaluated HERE, once, in float32 with torch -- exactly the tensors the reference builds at init -- so that no
+    per-pixel ``cos`` / ``sin`` (whose last bit is library dependent) decides which pixel a shadow sample lands in.
+    """
+
+    table: np.ndarray        # (3, D, Hn, S) float32 / 255, RGB order, rows padded with +inf (the reference's `__shadow_table_padded`)
+    fan_cos: np.ndarray      # (D, F) float32: cos of direction + fan offset
+    fan_sin: np.ndarray      # (D, F) float32
+    depth_0: float           # 0.4 (taxim_torch.py:97)
+    height_precision: float
+    discretize_precision: float
+    step_x: float            # shadow_step(shape)[1] -- the reference multiplies the X coordinate by the H-relative value (quirk)
+    step_y: float            # shadow_step(shape)[0]
+    dilate_rounds: tuple     # ((ky, kx), (ky, kx)): box kernels of the two dilation rounds of the contact mask
+    blur_taps: tuple         # (x taps, y taps) of the shadow blur
+
+    @classmethod
+    def from_calib_folder(cls, folder: str | Path, shape: tuple[int, int] = (240, 320)) -> "ShadowTables":
+        folder = Path(folder)
+        with (folder / "params.json").open() as f:
+            sim = json.load(f)["simulator"]
+        data = np.load(str(folder / "shadowTable.npz"), allow_pickle=True)
+        direction = torch.from_numpy(data["shadowDirections"]).float()
+        fan_angle = float(sim["fan_angle"])
+        n_rays = int(fan_angle * 2 / float(sim["fan_precision"]))
+        fan = direction.unsqueeze(-1) + torch.linspace(-fan_angle, fan_angle, n_rays)
+        # BGR -> RGB flip; the reference also "appends an empty entry for heights outside the range", but the appended array has a
+        # zero-length height axis, so nothing is appended and out-of-range heights read the LAST REAL height entry (kept: quirk)
+        tab = np.flip(data["shadowTable"], axis=0)
+        n_max = max(len(e) for e in tab.reshape(-1))
+        padded = np.array([list(e) + [np.inf] * (n_max - len(e)) for e in tab.reshape(-1)], dtype=np.float32)
+        padded = (torch.from_numpy(padded).reshape(tab.shape + (-1,)) / 255).numpy()
+
+        def rel(name):  # `*_rel` parameters: (w value * W, h value * H)  (taxim_impl.py:33-47)
+            v = sim[name + "_rel"]
+            return v[0] * shape[1], v[1] * shape[0]
+
+        ks_total = np.round(np.array(rel("shadow_attachment_kernel_size")) * 2).astype(np.int_)
+        first = ks_total // 2
+        rounds = tuple(tuple(int(v) for v in np.flip(np.maximum(1, k))) for k in (first, ks_total - first))
+        step = rel("shadow_step")
+        sig = rel("shadow_blur_sigma")
+        return cls(padded, torch.cos(fan).numpy(), torch.sin(fan).numpy(), 0.4, float(sim["height_precision"]),
+                   float(sim["discretize_precision"]), float(step[1]), float(step[0]), rounds,
+                   (gaussian_taps(sig[0]).numpy(), gaussian_taps(sig[1]).numpy()))
+
+    # -- pre-baked tables ---------------------------------------------------------------------------------------
+    def save(self, path: str | Path) -> None:
+        np.savez_compressed(
+            str(path), table=self.table, fan_cos=self.fan_cos, fan_sin=self.fan_sin,
+            scalars=np.array([self.depth_0, self.height_precision, self.discretize_precision, self.step_x, self.step_y]),
+            dilate_rounds=np.array(self.dilate_rounds), taps_x=self.blur_taps[0], taps_y=self.blur_taps[1],
+        )
+
+    @classmethod
+    def load(cls, path: str | Path) -> "ShadowTables":
+        z = np.load(str(path), allow_pickle=False)
+        sc = [float(v) for v in z["scalars"]]
+        return cls(z["table"], z["fan_cos"], z["fan_sin"], sc[0], sc[1], sc[2], sc[3], sc[4],
+                   tuple(tuple(int(v) for v in r) for r in z["dilate_rounds"]), (z["taps_x"], z["taps_y"]))
