@@ -135,6 +135,25 @@ int tx_set_camera_resolution(tx_handle* h, int Hc, int Wc);
 int tx_render_camera(tx_handle* h, const float* frames, int is_depth, float clip_max_m, const float* press_mm, int N,
                      float* rgb, float* depth_out, float* deformed, uint8_t* mask);
 
+/* ---- shadow branch (TaximSimulatorCfg.with_shadow = True; ref: .../gpu_taxim/sim/taxim_torch.py:96-125, 260-346) ----------------
+ * tx_upload_shadow_tables takes the init-time data the reference prepares in TaximTorch.__init__ (HOST pointers): the padded
+ * shadow table [3][D][Hn][S] (RGB order, / 255, +inf padded), cos / sin of the ray-fan angles [D][F] (float32, evaluated by the
+ * host exactly like the reference's torch tensors), the scalars of params.json scaled to the image shape, the box kernels of the
+ * two mask-dilation rounds and the taps of the shadow blur. tx_render_shadow = tx_render + the shadow post-pass: the same
+ * arguments and results as tx_render(..., deformed = NULL, mask = NULL), RGB with shadows. 240 x 320 handles only. */
+typedef struct {
+    int D, Hn, S, F;                 /* 63 directions, 24 heights, 51 samples per ray, 4 fan rays */
+    float depth_0;                   /* 0.4 (taxim_torch.py:97) */
+    float height_precision;          /* 0.1 */
+    float discretize_precision;      /* 0.1 */
+    float step_x, step_y;            /* shadow_step(shape)[1], [0] (the reference swaps the two, taxim_torch.py:300-305) */
+    int dil[4];                      /* ky, kx of dilation round 0, then of round 1 (taxim_torch.py:261-270) */
+    int ks_sx, ks_sy;                /* tap counts of the shadow blur */
+    float taps_sx[TX_MAX_TAPS], taps_sy[TX_MAX_TAPS];
+} tx_shadow_config;
+int tx_upload_shadow_tables(tx_handle* h, const tx_shadow_config* cfg, const float* table, const float* fan_cos, const float* fan_sin);
+int tx_render_shadow(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out);
+
 /* ---- multi-GPU: the single observation all-gather (the reference makes no collective call) ----------
  * A frame differs from the flat image only inside a rectangle per half frame. tx_set_rect_output makes the following
  * tx_render* calls record it: rect [N][2][4] int32 = (first row, last row -- local to the half --, first column, last column),

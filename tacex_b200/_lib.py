@@ -34,6 +34,13 @@ class TxConfig(C.Structure):
     ]
 
 
+class TxShadowConfig(C.Structure):
+    _fields_ = [("D", C.c_int), ("Hn", C.c_int), ("S", C.c_int), ("F", C.c_int), ("depth_0", C.c_float),
+                ("height_precision", C.c_float), ("discretize_precision", C.c_float), ("step_x", C.c_float), ("step_y", C.c_float),
+                ("dil", C.c_int * 4), ("ks_sx", C.c_int), ("ks_sy", C.c_int),
+                ("taps_sx", C.c_float * TX_MAX_TAPS), ("taps_sy", C.c_float * TX_MAX_TAPS)]
+
+
 class TxCounters(C.Structure):
     _fields_ = [("render_calls", C.c_uint64), ("frames_rendered", C.c_uint64), ("fots_calls", C.c_uint64),
                 ("depth_calls", C.c_uint64), ("kernels_launched", C.c_uint64)]
@@ -66,7 +73,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
+    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers", "tx_fem_debug_set_cycles",
 ]
@@ -97,6 +104,10 @@ def load() -> C.CDLL:
     lib.tx_set_camera_resolution.restype = C.c_int
     lib.tx_render_camera.argtypes = [C.c_void_p, fp, C.c_int, C.c_float, fp, C.c_int, fp, fp, fp, u8p]
     lib.tx_render_camera.restype = C.c_int
+    lib.tx_upload_shadow_tables.argtypes = [C.c_void_p, C.POINTER(TxShadowConfig), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tx_upload_shadow_tables.restype = C.c_int
+    lib.tx_render_shadow.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp]
+    lib.tx_render_shadow.restype = C.c_int
     lib.tx_set_rect_output.argtypes = [C.c_void_p, vp]
     lib.tx_obs_push.argtypes = [C.c_void_p, fp, ip, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), fp, ip, vp]
     lib.tx_obs_fill.argtypes = [C.c_void_p, fp, ip, ip, C.c_int, C.c_int, C.c_int, vp]

@@ -52,6 +52,13 @@ struct tx_handle {
     float2 *d_rs_wx = nullptr, *d_rs_wy = nullptr;
     float* d_up = nullptr;
     int* d_rect = nullptr; // not owned: tx_set_rect_output
+    // shadow branch (tx_upload_shadow_tables / tx_render_shadow)
+    tx_shadow_config sh_cfg{};
+    bool have_shadow = false;
+    float *d_sh_table = nullptr, *d_sh_cos = nullptr, *d_sh_sin = nullptr, *d_sh_taps = nullptr; // taps: [4][TX_MAX_TAPS] sx, sy, fx, fy
+    float *d_sh_def = nullptr, *d_sh_img = nullptr, *d_sh_t1 = nullptr, *d_sh_t2 = nullptr;
+    unsigned char* d_sh_mask = nullptr;
+    int sh_chunk = 0;
     bool generic = false;  // shape / radii other than the specialised 240 x 320 kernel: taxim_generic_kernel
     float* d_taps = nullptr; // generic: [n_blurs][2][TX_MAX_TAPS]
     int n_sm = 148;
@@ -193,6 +200,8 @@ extern "C" void tx_destroy(tx_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_taps);
+    cudaFree(h->d_sh_table); cudaFree(h->d_sh_cos); cudaFree(h->d_sh_sin); cudaFree(h->d_sh_taps); cudaFree(h->d_sh_def);
+    cudaFree(h->d_sh_img); cudaFree(h->d_sh_t1); cudaFree(h->d_sh_t2); cudaFree(h->d_sh_mask);
     cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
@@ -435,6 +444,88 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     h->ctr.render_calls++;
     h->ctr.frames_rendered += (uint64_t)N;
     h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_upload_shadow_tables(tx_handle* h, const tx_shadow_config* c, const float* table, const float* fan_cos,
+                                       const float* fan_sin)
+{
+    if (!h || !c || !table || !fan_cos || !fan_sin) return fail(h, TX_ERR_INVALID_ARG, "tx_upload_shadow_tables: null argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_upload_shadow_tables: the shadow branch belongs to the 240 x 320 kernel");
+    if (c->D < 1 || c->Hn < 2 || c->S < 1 || c->F < 1 || c->ks_sx < 1 || c->ks_sy < 1 || !(c->ks_sx & 1) || !(c->ks_sy & 1) ||
+        c->ks_sx > TX_MAX_TAPS || c->ks_sy > TX_MAX_TAPS || !(c->height_precision > 0.0f) || !(c->discretize_precision > 0.0f))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_upload_shadow_tables: bad configuration");
+    for (int i = 0; i < 4; ++i)
+        if (c->dil[i] < 1 || c->dil[i] > 16) return fail(h, TX_ERR_INVALID_ARG, "tx_upload_shadow_tables: bad dilation kernel");
+    TX_CUDA(h, cudaSetDevice(h->device));
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_sh_table); cudaFree(h->d_sh_cos); cudaFree(h->d_sh_sin); cudaFree(h->d_sh_taps);
+    h->d_sh_table = h->d_sh_cos = h->d_sh_sin = h->d_sh_taps = nullptr;
+    h->have_shadow = false;
+    const size_t nt = (size_t)3 * c->D * c->Hn * c->S, nf = (size_t)c->D * c->F;
+    TX_CUDA(h, cudaMalloc(&h->d_sh_table, nt * sizeof(float)));
+    TX_CUDA(h, cudaMalloc(&h->d_sh_cos, nf * sizeof(float)));
+    TX_CUDA(h, cudaMalloc(&h->d_sh_sin, nf * sizeof(float)));
+    TX_CUDA(h, cudaMalloc(&h->d_sh_taps, sizeof(float) * 4 * TX_MAX_TAPS));
+    TX_CUDA(h, cudaMemcpy(h->d_sh_table, table, nt * sizeof(float), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_sh_cos, fan_cos, nf * sizeof(float), cudaMemcpyHostToDevice));
+    TX_CUDA(h, cudaMemcpy(h->d_sh_sin, fan_sin, nf * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> t((size_t)4 * TX_MAX_TAPS, 0.0f);
+    const int lf = h->cfg.n_blurs - 1; // the final blur of the deformation pyramid is also the last blur of the shadow branch
+    for (int k = 0; k < TX_MAX_TAPS; ++k) {
+        t[0 * TX_MAX_TAPS + k] = k < c->ks_sx ? c->taps_sx[k] : 0.0f;
+        t[1 * TX_MAX_TAPS + k] = k < c->ks_sy ? c->taps_sy[k] : 0.0f;
+        t[2 * TX_MAX_TAPS + k] = k < h->cfg.ksx[lf] ? h->cfg.taps_x[lf][k] : 0.0f;
+        t[3 * TX_MAX_TAPS + k] = k < h->cfg.ksy[lf] ? h->cfg.taps_y[lf][k] : 0.0f;
+    }
+    TX_CUDA(h, cudaMemcpy(h->d_sh_taps, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->sh_cfg = *c;
+    h->have_shadow = true;
+    return TX_OK;
+}
+
+extern "C" int tx_render_shadow(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out)
+{
+    if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render_shadow: bad argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_render_shadow: the shadow branch belongs to the 240 x 320 kernel");
+    if (!h->have_shadow) return fail(h, TX_ERR_NO_TABLES, "tx_render_shadow: call tx_upload_shadow_tables first");
+    if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render_shadow: N exceeds max_envs");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    const size_t HWp = (size_t)IMG_H * IMG_W;
+    if (!h->d_sh_def) { // scratch for one chunk of frames: deformed gel, mask, three [n][3][H][W] planes
+        const int chunk = h->cfg.max_envs < 256 ? h->cfg.max_envs : 256;
+        TX_CUDA(h, cudaMalloc(&h->d_sh_def, sizeof(float) * HWp * chunk));
+        TX_CUDA(h, cudaMalloc(&h->d_sh_mask, HWp * chunk));
+        TX_CUDA(h, cudaMalloc(&h->d_sh_img, sizeof(float) * 3 * HWp * chunk));
+        TX_CUDA(h, cudaMalloc(&h->d_sh_t1, sizeof(float) * 3 * HWp * chunk));
+        TX_CUDA(h, cudaMalloc(&h->d_sh_t2, sizeof(float) * 3 * HWp * chunk));
+        h->sh_chunk = chunk;
+    }
+    TaximArgs c{};
+    fill_taxim_consts(h, c);
+    const tx_shadow_config& sc = h->sh_cfg;
+    const int lf = h->cfg.n_blurs - 1;
+    for (int n0 = 0; n0 < N; n0 += h->sh_chunk) {
+        const int n = N - n0 < h->sh_chunk ? N - n0 : h->sh_chunk;
+        int rc = render_impl(h, height_mm + HWp * n0, press_mm ? press_mm + n0 : nullptr, n, rgb + HWp * 3 * n0,
+                             depth_out ? depth_out + n0 : nullptr, h->d_sh_def, h->d_sh_mask, 0, 0.0f, nullptr);
+        if (rc != TX_OK) return rc;
+        ShadowArgs a{};
+        a.deformed = h->d_sh_def; a.mask = h->d_sh_mask; a.gel = c.gel; a.poly = c.poly; a.shadow = h->d_sh_img;
+        a.table = h->d_sh_table; a.fan_cos = h->d_sh_cos; a.fan_sin = h->d_sh_sin;
+        a.D = sc.D; a.Hn = sc.Hn; a.S = sc.S; a.F = sc.F; a.nb = c.nb;
+        for (int i = 0; i < 4; ++i) a.dil[i] = sc.dil[i];
+        a.pixmm = h->cfg.pixmm; a.inv_pixmm = c.inv_pixmm; a.sx = c.sx; a.sy = c.sy; a.fx = c.fx; a.fy = c.fy;
+        a.inv_xbin = c.inv_xbin; a.inv_ybin = c.inv_ybin;
+        a.depth_0 = sc.depth_0; a.height_precision = sc.height_precision; a.discretize_precision = sc.discretize_precision;
+        a.step_x = sc.step_x; a.step_y = sc.step_y;
+        TX_CUDA(h, launch_shadow(a, n, h->d_sh_t1, h->d_sh_t2, rgb + HWp * 3 * n0, c.bg_hwc, h->d_sh_taps, sc.ks_sx,
+                                 h->d_sh_taps + TX_MAX_TAPS, sc.ks_sy, h->d_sh_taps + 2 * TX_MAX_TAPS, h->cfg.ksx[lf],
+                                 h->d_sh_taps + 3 * TX_MAX_TAPS, h->cfg.ksy[lf], h->stream));
+        h->ctr.kernels_launched += 7;
+    }
+    if (N > h->sh_chunk) h->aux_valid_n = 0; // the FOTS inputs recorded by the fused kernel only cover the last chunk
     return TX_OK;
 }
 

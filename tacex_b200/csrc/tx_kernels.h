@@ -71,6 +71,25 @@ struct TaximGenericArgs {
     float clip_max_m, inv_pixmm, sx, sy, fx, fy, contact_scale, gelpad_h, gelpad_min, inv_xbin, inv_ybin;
 };
 
+// shadow branch (taxim_shadow_kernel.cu)
+struct ShadowArgs {
+    const float* deformed;      // [n][240][320] deformed gel (mm), written by the fused kernel
+    const unsigned char* mask;  // [n][240][320] contact mask
+    const float* gel;           // [240][320] or nullptr
+    const float4* poly;         // [nb][nb][5 float4]
+    float* shadow;              // [n][3][240][320] scratch: scatter-min image, then min(polynomial colour, shadow)
+    const float* table;         // [3][D][Hn][S] shadow table (+inf padded)
+    const float* fan_cos;       // [D][F]
+    const float* fan_sin;       // [D][F]
+    int D, Hn, S, F, nb;
+    int dil[4];                 // ky0, kx0, ky1, kx1 of the two dilation rounds
+    float pixmm, inv_pixmm, sx, sy, fx, fy, inv_xbin, inv_ybin;
+    float depth_0, height_precision, discretize_precision, step_x, step_y;
+};
+cudaError_t launch_shadow(const ShadowArgs& a, int n, float* t1, float* t2, float* rgb, const float* bg_hwc, const float* taps_sx,
+                          int ks_sx, const float* taps_sy, int ks_sy, const float* taps_fx, int ks_fx, const float* taps_fy,
+                          int ks_fy, cudaStream_t s);
+
 constexpr int TX_MAX_PEERS = 15;
 struct ObsPushArgs {
     const float* rgb_local;  // [N][240][320][3] this rank's frames

@@ -174,6 +174,37 @@ class TactileEngine:
                                               _ptr(out), _ptr(depth_out), _ptr(deformed_out), _ptr(mask_out)))
         return out
 
+    # -- shadow branch (with_shadow=True) ------------------------------------------------------------------
+    def upload_shadow_tables(self, st) -> None:
+        """``st``: :class:`tacex_b200.calib.ShadowTables` (host, init time)."""
+        import numpy as np
+
+        c = _lib.TxShadowConfig()
+        c.D, c.Hn, c.S = (int(v) for v in st.table.shape[1:])
+        c.F = int(st.fan_cos.shape[1])
+        c.depth_0, c.height_precision, c.discretize_precision = st.depth_0, st.height_precision, st.discretize_precision
+        c.step_x, c.step_y = st.step_x, st.step_y
+        c.dil[:] = [int(st.dilate_rounds[0][0]), int(st.dilate_rounds[0][1]), int(st.dilate_rounds[1][0]), int(st.dilate_rounds[1][1])]
+        tx, ty = np.asarray(st.blur_taps[0], np.float32), np.asarray(st.blur_taps[1], np.float32)
+        if tx.size > _lib.TX_MAX_TAPS or ty.size > _lib.TX_MAX_TAPS:
+            raise _lib.TxError("shadow blur kernel too large")
+        c.ks_sx, c.ks_sy = int(tx.size), int(ty.size)
+        for k, v in enumerate(tx.tolist()):
+            c.taps_sx[k] = v
+        for k, v in enumerate(ty.tolist()):
+            c.taps_sy[k] = v
+        tab = np.ascontiguousarray(st.table, np.float32)
+        fc, fs = np.ascontiguousarray(st.fan_cos, np.float32), np.ascontiguousarray(st.fan_sin, np.float32)
+        self._check(self.lib.tx_upload_shadow_tables(self.h, C.byref(c), tab.ctypes.data, fc.ctypes.data, fs.ctypes.data))
+
+    def render_shadow(self, hm: torch.Tensor, press: torch.Tensor | None, out: torch.Tensor | None = None,
+                      depth_out: torch.Tensor | None = None) -> torch.Tensor:
+        """RGB (N, H, W, 3) with shadows (``render_direct(with_shadow=True)``); arguments as :meth:`render`."""
+        N = self._chk_hm(hm)
+        out = torch.empty((N, self.H, self.W, 3), device=self.device) if out is None else out
+        self._check(self.lib.tx_render_shadow(self.h, _ptr(hm), _ptr(press), N, _ptr(out), _ptr(depth_out)))
+        return out
+
     # -- multi-GPU observation gather (SURVEY 8e) ----------------------------------------------------------------------
     def set_rect_output(self, rect: torch.Tensor | None) -> None:
         """int32 (N, 2, 4) device tensor that the following renders fill with the per-half non-flat rectangle, or None."""
