@@ -1,10 +1,10 @@
-"""GPU parity of the shadow branch (tx_render_shadow, csrc/taxim_shadow_kernel.cu) against the canonical restatement, which is
-itself pinned to the executed reference (tests/test_shadow_cpu.py).
+"""GPU tests that have NOT run on a device yet (written after the round's GPU budget was spent). Everything here is marked xfail
+(non-strict): an XPASS in the round-end log is the confirmation, a failure cannot turn the validated suite red, and the file name
+sorts last so that a fault in an unvalidated path cannot disturb the validated tests of the same pytest process.
 
-STATUS: the kernels were written after this round's GPU budget was spent, so they have never run on a device; the test is marked
-xfail (non-strict) until a GPU run confirms it -- an XPASS in the round-end log is that confirmation. The file name sorts last
-so that a fault in this unvalidated path cannot disturb the validated tests of the same pytest process; the plug-in does not
-route with_shadow=True here yet (it still raises NotImplementedError)."""
+* shadow branch (tx_render_shadow, csrc/taxim_shadow_kernel.cu) bitwise against the canonical restatement, which is itself pinned
+  to the executed reference (tests/test_shadow_cpu.py); the plug-in does not route with_shadow=True there yet;
+* the fused (validated) kernel on extreme contacts added late (tests/test_refbox_cpu.py::EDGE_CASES)."""
 import numpy as np
 import pytest
 import torch
