@@ -154,18 +154,46 @@ class GelFemEngine:
         return out
 
 
-def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=128):
+def reference_marker_grid(interval_mm: float = 2.0625, translation_mm=(0.0, 0.0), rotation_rad: float = 0.0) -> np.ndarray:
+    """Marker positions [m], (K, 2), exactly as ``_gen_marker_grid`` lays them out in the CAMERA frame when all random ranges are
+    zero (ref: tactile_sensor_sapienipc_modified.py:189-247; pinned against the executed function in
+    tests/test_host_cpu.py): x from -ceil(8 / d) d to +ceil(16.5 / d) d, y from -ceil(6 / d) d to +ceil(6 / d) d -- the x range is
+    NOT symmetric (13 x 7 = 91 points from -8.25 mm to 16.5 mm for d = 2.0625 mm); markers outside the gel surface are dropped later
+    (``_gen_marker_weight``). Pass the result, shifted into the pad frame, to :func:`marker_grid_weights` as ``points_xy``."""
+    import math
+
+    d, (tx, ty) = float(interval_mm), translation_mm
+    x0 = -math.ceil((8 + tx) / d) * d + tx
+    x1 = math.ceil((16.5 - tx) / d) * d + tx
+    y0 = -math.ceil((6 + ty) / d) * d + ty
+    y1 = math.ceil((6 - ty) / d) * d + ty
+    mx = np.linspace(x0, x1, round((x1 - x0) / d) + 1, True)
+    my = np.linspace(y0, y1, round((y1 - y0) / d) + 1, True)
+    xy = np.array(np.meshgrid(mx, my)).reshape((2, -1)).T
+    rot = np.array([[math.cos(rotation_rad), -math.sin(rotation_rad)], [math.sin(rotation_rad), math.cos(rotation_rad)]])
+    return (xy @ rot.T) / 1000.0
+
+
+def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=128, points_xy: np.ndarray | None = None):
     """Marker grid on the gel's top surface and its barycentric weights (init time, host).
 
     Restates ``_gen_marker_grid`` / ``_gen_marker_weight`` of the reference's FEM marker sensor
     (tactile_sensor_sapienipc_modified.py:189-329) for the default configuration (all random ranges zero): a
     ``cols x rows`` grid with ``pitch`` spacing centred on the pad, markers outside the surface are dropped, the list
-    is padded to ``pad_to`` by repeating the last marker (mani_skill_sim_cfg.py:17,54)."""
+    is padded to ``pad_to`` by repeating the last marker (mani_skill_sim_cfg.py:17,54).
+
+    Placement: the reference lays the grid out in the CAMERA frame (:func:`reference_marker_grid`: x in [-8.25, 16.5] mm) and keeps
+    what falls on the gel surface; where the camera frame sits relative to the pad is fixed by the sensor's USD asset, which
+    cannot be read here. The default is therefore the full 13 x 7 grid centred on the pad; ``points_xy`` (K, 2) [m, pad frame]
+    overrides it, e.g. ``reference_marker_grid() - camera_origin_in_pad_frame``."""
     X = mesh.X
     tris = mesh.top_tris
-    xs = (np.arange(cols) - (cols - 1) / 2) * pitch
-    ys = (np.arange(rows) - (rows - 1) / 2) * pitch
-    pts = np.array([[x, y] for x in xs for y in ys])
+    if points_xy is not None:
+        pts = np.asarray(points_xy, np.float64).reshape(-1, 2)
+    else:
+        xs = (np.arange(cols) - (cols - 1) / 2) * pitch
+        ys = (np.arange(rows) - (rows - 1) / 2) * pitch
+        pts = np.array([[x, y] for x in xs for y in ys])
     out_tri, out_w = [], []
     A, B, Cc = X[tris[:, 0], :2], X[tris[:, 1], :2], X[tris[:, 2], :2]
     for p in pts:

@@ -121,3 +121,33 @@ def test_sensor_cfg_mirrors_reference_fields():
     assert cfg.marker_motion_sim_cfg.marker_params.num_markers == 99
     for f in ("calib_folder_path", "device", "with_shadow", "tactile_img_res", "gelpad_height", "gelpad_to_camera_min_distance"):
         assert hasattr(cfg.optical_sim_cfg, f)
+
+
+@pytest.mark.refbox
+def test_marker_grid_layout_against_the_executed_reference_function():
+    """`_gen_marker_grid` of the reference's FEM marker sensor (tactile_sensor_sapienipc_modified.py:189-247) is a method of a
+    class whose module needs Isaac Sim; the method itself only needs numpy / math, so its source is compiled from the reference
+    file (ast, nothing copied) and executed on a stand-in `self` with the preset's zero random ranges."""
+    import ast
+    import math
+    import types
+    from pathlib import Path
+
+    src = Path("/root/reference/source/tacex/tacex/simulation_approaches/fem_based/sim/tactile_sensor_sapienipc_modified.py")
+    if not src.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from tacex_b200.fem import reference_marker_grid
+
+    tree = ast.parse(src.read_text())
+    fn = next(n for c in tree.body if isinstance(c, ast.ClassDef) for n in c.body
+              if isinstance(n, ast.FunctionDef) and n.name == "_gen_marker_grid")
+    ns = {"np": np, "math": math}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), str(src), "exec"), ns)
+    for interval in (2.0625, 1.5, 3.0):
+        me = types.SimpleNamespace(marker_interval_range=(interval, interval), marker_rotation_range=0.0,
+                                   marker_translation_range=(0.0, 0.0), marker_pos_shift_range=(0.0, 0.0))
+        ref = ns["_gen_marker_grid"](me)
+        mine = reference_marker_grid(interval)
+        assert mine.shape == ref.shape and np.abs(mine - ref).max() <= 1e-15
+    g = reference_marker_grid()
+    assert g.shape == (91, 2) and abs(g[:, 0].min() + 8.25e-3) < 1e-12 and abs(g[:, 0].max() - 16.5e-3) < 1e-12
