@@ -151,3 +151,65 @@ def test_marker_grid_layout_against_the_executed_reference_function():
         assert mine.shape == ref.shape and np.abs(mine - ref).max() <= 1e-15
     g = reference_marker_grid()
     assert g.shape == (91, 2) and abs(g[:, 0].min() + 8.25e-3) < 1e-12 and abs(g[:, 0].max() - 16.5e-3) < 1e-12
+
+
+@pytest.mark.refbox
+def test_marker_weights_against_the_executed_reference_function():
+    """`_gen_marker_weight` (tactile_sensor_sapienipc_modified.py:249-329: hull test, 4 nearest face centres by ball tree, first
+    containing triangle, barycentric weights) executed from the reference file on the structured gel's top surface -- usdrt (the
+    Fabric mesh accessor, Isaac Sim) is replaced by a stand-in that hands out the same triangles -- against
+    fem.marker_grid_weights on the same points: the interpolated marker positions on a DEFORMED surface must coincide."""
+    import ast
+    import importlib.util
+    import types
+    from pathlib import Path
+
+    base = Path("/root/reference/source/tacex/tacex/simulation_approaches/fem_based/sim")
+    if not base.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from sklearn.neighbors import NearestNeighbors
+
+    from tacex_b200 import gel_mesh
+    from tacex_b200.fem import marker_grid_weights, reference_marker_grid
+
+    spec = importlib.util.spec_from_file_location("ref_geometry", str(base / "utils" / "geometry.py"))
+    geo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(geo)
+    tree = ast.parse((base / "tactile_sensor_sapienipc_modified.py").read_text())
+    fn = next(n for c in tree.body if isinstance(c, ast.ClassDef) for n in c.body
+              if isinstance(n, ast.FunctionDef) and n.name == "_gen_marker_weight")
+    m = gel_mesh.box_gel()
+    tris = np.asarray(m.top_tris)
+
+    class _Attr:
+        def Get(self):
+            return tris.reshape(-1).tolist()
+
+    class _Mesh:
+        def __init__(self, prim):
+            pass
+
+        def GetFaceVertexIndicesAttr(self):
+            return _Attr()
+
+    usdrt = types.SimpleNamespace(UsdGeom=types.SimpleNamespace(Mesh=_Mesh))
+    ns = {"np": np, "NearestNeighbors": NearestNeighbors, "in_hull": geo.in_hull, "usdrt": usdrt}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), str(base), "exec"), ns)
+    # camera frame := pad frame shifted so that the reference's asymmetric grid covers the pad (see DESIGN.md section 7)
+    X = np.asarray(m.X, np.float64)
+    shift = np.array([4.125e-3, 0.0])
+    pts_cam = reference_marker_grid()
+    surf_cam = X.copy()
+    surf_cam[:, :2] += shift
+    me = types.SimpleNamespace(init_surface_vertices_camera=torch.from_numpy(surf_cam), gelpad_obj=types.SimpleNamespace(fabric_prim=None))
+    idx_ref, w_ref = ns["_gen_marker_weight"](me, pts_cam.copy())
+    # same points in the pad frame through the product's host code (no padding: pad_to = number of valid markers)
+    pts_pad = pts_cam - shift
+    on = geo.in_hull(pts_cam, surf_cam[:, :2])
+    tri, w = marker_grid_weights(m, pad_to=int(on.sum()), points_xy=pts_pad[on])
+    assert idx_ref.shape[0] == tri.shape[0] == on.sum() and on.sum() >= 70  # 11 x 7 of the 13 x 7 points lie on this pad
+    rng = np.random.default_rng(0)
+    Xd = X + 2e-4 * rng.standard_normal(X.shape)  # a deformed surface
+    p_ref = (Xd[idx_ref] * w_ref[..., None]).sum(1)
+    p_me = (Xd[tri] * w[..., None]).sum(1)
+    assert np.abs(p_ref - p_me).max() <= 1e-9
