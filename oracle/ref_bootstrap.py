@@ -148,3 +148,45 @@ class RefFots:
                 mx, my = self.mm.init_marker_x_pos, self.mm.init_marker_y_pos
             out[env_id, 1] = torch.tensor(np.stack((mx, my), axis=-1).reshape(-1, 2))
         return out
+
+
+# ---- executing METHODS of reference classes whose modules need Isaac Sim ------------------------------------------------
+def ref_methods(path: Path, class_name: str, names: list[str], namespace: dict) -> dict:
+    """Compiles the named methods of ``class_name`` straight from the reference file (ast; nothing is copied into this repo) and
+    returns them as plain functions taking ``self`` first. The enclosing modules import omni / isaaclab at the top, so they
+    cannot be imported; the method bodies themselves only need what ``namespace`` supplies."""
+    import ast
+
+    tree = ast.parse(Path(path).read_text())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = dict(namespace)
+    exec(compile(ast.Module(body=fns, type_ignores=[]), str(path), "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
+class RefTaximSimulator:
+    """The reference's ``TaximSimulator.optical_simulation`` / ``compute_indentation_depth`` (taxim_sim.py:80-131) EXECUTED on a
+    stand-in ``self``: the real ``sim.Taxim`` instance, a dict as sensor output, the preset's cfg values."""
+
+    def __init__(self, tx, num_envs: int, tactile_img_res=(320, 240), gelpad_height=0.0045, min_dist=0.024, with_shadow=False):
+        import types
+
+        import torchvision.transforms.functional as F
+
+        self.m = ref_methods(REF_ROOT / "source/tacex/tacex/simulation_approaches/gpu_taxim/taxim_sim.py", "TaximSimulator",
+                             ["optical_simulation", "compute_indentation_depth"], {"torch": torch, "F": F, "np": np})
+        W, H = tactile_img_res
+        self.me = types.SimpleNamespace(
+            sensor=types.SimpleNamespace(_data=types.SimpleNamespace(output={})),
+            cfg=types.SimpleNamespace(tactile_img_res=tactile_img_res, with_shadow=with_shadow, gelpad_height=gelpad_height,
+                                      gelpad_to_camera_min_distance=min_dist),
+            _device="cpu", _taxim=tx, _indentation_depth=torch.zeros(num_envs), tactile_rgb_img=torch.zeros((num_envs, H, W, 3)),
+        )
+
+    def step(self, height_map_mm: torch.Tensor):
+        """-> (indentation depth [N], tactile RGB [N, H, W, 3]) in the reference's call order."""
+        self.me.sensor._data.output["height_map"] = height_map_mm
+        depth = self.m["compute_indentation_depth"](self.me).clone()
+        rgb = self.m["optical_simulation"](self.me).clone()
+        return depth, rgb

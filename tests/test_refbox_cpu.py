@@ -91,3 +91,38 @@ def test_edge_cases_vs_executed_reference(ref_taxim, canon_taxim, name):
     well = (mag >= 1e-3).numpy()
     agree = (o["idx_mag"] == im.numpy()) & (o["idx_dir"] == idr.numpy())
     assert well.sum() > 100 and agree[well].mean() >= 0.985
+
+
+@pytest.mark.parametrize("cam", [(240, 320), (24, 32), (60, 80)])
+def test_reference_simulator_methods_executed(ref_taxim, canon_taxim, cam):
+    """`TaximSimulator.compute_indentation_depth` + `optical_simulation` (taxim_sim.py:80-131) executed from the reference file on
+    a stand-in `self` -- including its `F.resize` of a coarser sensor camera (the FEM preset's 32 x 24) -- against the canonical
+    restatement fed with the canonical resize: indentation depth from the CAMERA-resolution map, P1/P2 on the render."""
+    from oracle import canon
+    from tacex_b200 import synth
+
+    rb, tx = ref_taxim
+    hc, wc = cam
+    pitch = synth.PIXEL_PITCH_M_320 * 320 / wc
+    depth_m = torch.stack([synth.depth_map(k % 4, (2.0 + 0.4 * k) * 1e-3, 1e-3 * k - 2e-3, 5e-4 * k, 0.3 * k, (3 + 2 * k) * 1e-4,
+                                           H=hc, W=wc, pitch=pitch) for k in range(4)])
+    hm = synth.height_map_mm(depth_m)
+    sim = rb.RefTaximSimulator(tx, 4)
+    press_ref, rgb_ref = sim.step(hm)
+    pc = canon_taxim.indentation_depth(hm.numpy())
+    assert np.abs(pc - press_ref.numpy()).max() <= 1e-6 and (pc > 0).all()
+    hm_full = hm.numpy() if cam == (H, W) else canon.resize_bilinear(hm.numpy(), (H, W))
+    o = canon_taxim.render(hm_full, pc)
+    # bins of the executed reference for the P2 protocol (recomputed through its own private methods on its own resize)
+    import torchvision.transforms.functional as F
+
+    hm_ref_full = hm if cam == (H, W) else F.resize(hm, (H, W))
+    assert np.abs(hm_full - hm_ref_full.numpy()).max() == 0.0  # canonical resize == torchvision F.resize, bitwise
+    dg, _ = rb.ref_deformed_gel(tx, hm_ref_full, press_ref)
+    mag, _, im, idr = rb.ref_normals_bins(tx, dg)
+    assert np.abs(o["deformed"] - dg.numpy()).max() <= 1e-5
+    well = (mag >= 1e-3).numpy()
+    agree = (o["idx_mag"] == im.numpy()) & (o["idx_dir"] == idr.numpy())
+    assert agree[well].mean() >= 0.985
+    d = np.abs(o["rgb"] - rgb_ref.numpy()).max(-1)
+    assert d[agree].max() <= 1e-5 and (d[well] <= 1e-3).mean() >= 0.985
