@@ -190,3 +190,49 @@ class RefTaximSimulator:
         depth = self.m["compute_indentation_depth"](self.me).clone()
         rgb = self.m["optical_simulation"](self.me).clone()
         return depth, rgb
+
+
+class RefFotsSimulatorMethod:
+    """The reference's ``FOTSMarkerSimulator.marker_motion_simulation`` (fots_marker_sim.py:114-184) EXECUTED from the file on a
+    stand-in ``self``. Isaac Lab's FrameTransformer / ``euler_xyz_from_quat`` (third party, absent) are replaced by a recorded
+    yaw per env: the stand-in hands the method a yaw-only quaternion and the published yaw formula atan2(2 (w z + x y),
+    1 - 2 (y^2 + z^2)). Used to check that ``RefFots`` above (the loop the golden markers were generated with) is that method."""
+
+    def __init__(self, tx, num_envs: int, rows=9, cols=11, x0=15, y0=26, mm2pix=19.58, W=320, H=240):
+        import types
+
+        import torchvision.transforms.functional as F
+
+        MarkerMotion = load_marker_motion_cls()
+        bg = tx._TaximTorch__get_background_img_cached((H, W)).movedim(0, 2).cpu().numpy()
+        mm = MarkerMotion(frame0_blur=bg, mm2pix=mm2pix, num_markers_col=cols, num_markers_row=rows, tactile_img_width=W,
+                          tactile_img_height=H, lamb=[0.00125, 0.00021, 0.00038], x0=x0, y0=y0)
+
+        def euler_xyz_from_quat(q):  # (K, 4) wxyz -> roll, pitch, yaw; only the yaw is used by the caller
+            w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+            yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+            return torch.zeros_like(yaw), torch.zeros_like(yaw), yaw
+
+        self.fn = ref_methods(REF_ROOT / "source/tacex/tacex/simulation_approaches/fots/fots_marker_sim.py", "FOTSMarkerSimulator",
+                              ["marker_motion_simulation"],
+                              {"torch": torch, "F": F, "np": np, "euler_xyz_from_quat": euler_xyz_from_quat})["marker_motion_simulation"]
+        init = np.stack((mm.init_marker_x_pos, mm.init_marker_y_pos), axis=-1).reshape(-1, 2)
+        md = torch.zeros((num_envs, 2, init.shape[0], 2))
+        md[:, 0] = torch.tensor(init)
+        ft = types.SimpleNamespace(update=lambda dt: None,
+                                   data=types.SimpleNamespace(target_pos_source=torch.zeros((num_envs, 1, 3)),
+                                                              target_quat_source=torch.zeros((num_envs, 1, 4))))
+        self.me = types.SimpleNamespace(
+            sensor=types.SimpleNamespace(_indentation_depth=None, _data=types.SimpleNamespace(output={"traj": [[] for _ in range(num_envs)]})),
+            cfg=types.SimpleNamespace(tactile_img_res=(W, H), mm_to_pixel=mm2pix), _device="cpu", _taxim=tx, marker_motion_sim=mm,
+            frame_transformer=ft, marker_data=md,
+        )
+
+    def step(self, hm_mm: torch.Tensor, press_mm: torch.Tensor, theta: np.ndarray) -> torch.Tensor:
+        th = torch.as_tensor(theta, dtype=torch.float32)
+        q = torch.zeros((th.shape[0], 1, 4))
+        q[:, 0, 0], q[:, 0, 3] = torch.cos(th / 2), torch.sin(th / 2)
+        self.me.frame_transformer.data.target_quat_source = q
+        self.me.sensor._indentation_depth = press_mm
+        self.me.sensor._data.output["height_map"] = hm_mm
+        return self.fn(self.me).clone()

@@ -126,3 +126,21 @@ def test_reference_simulator_methods_executed(ref_taxim, canon_taxim, cam):
     assert agree[well].mean() >= 0.985
     d = np.abs(o["rgb"] - rgb_ref.numpy()).max(-1)
     assert d[agree].max() <= 1e-5 and (d[well] <= 1e-3).mean() >= 0.985
+
+
+def test_fots_loop_restatement_is_the_executed_reference_method(ref_taxim):
+    """oracle/ref_bootstrap.RefFots (the per-env loop the committed marker fixtures were generated with) against
+    `FOTSMarkerSimulator.marker_motion_simulation` itself, executed from the reference file: two trajectory samples."""
+    from tacex_b200 import synth
+
+    rb, tx = ref_taxim
+    c2 = synth.config2(5, seed=505)
+    hm0, hm1 = synth.height_map_mm(c2["depth_m0"]), synth.height_map_mm(c2["depth_m"])
+    mine = rb.RefFots(tx, rows=9, cols=11, x0=15, y0=26)
+    ref = rb.RefFotsSimulatorMethod(tx, 5, rows=9, cols=11, x0=15, y0=26)
+    for hm, th in ((hm0, c2["theta0"]), (hm1, c2["theta"])):
+        press = rb.ref_indentation_depth(hm)
+        a = mine.step(hm, press, th.numpy()).numpy()
+        b = ref.step(hm, press, th.numpy()).numpy()
+        assert np.abs(a - b).max() <= 2e-3  # px; the yaw goes through a float32 quaternion in the stand-in
+        assert np.abs(a[:, 1] - a[:, 0]).max() > 0.5  # the markers do move
