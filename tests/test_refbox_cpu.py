@@ -144,3 +144,39 @@ def test_fots_loop_restatement_is_the_executed_reference_method(ref_taxim):
         b = ref.step(hm, press, th.numpy()).numpy()
         assert np.abs(a - b).max() <= 2e-3  # px; the yaw goes through a float32 quaternion in the stand-in
         assert np.abs(a[:, 1] - a[:, 0]).max() > 0.5  # the markers do move
+
+
+def test_sensor_depth_preprocessing_against_executed_reference_methods():
+    """`GelSightSensor._get_height_map` / `_get_camera_depth` (gelsight_sensor.py:557-593) executed from the reference file against
+    the same-named methods of the headless stand-in (tacex_b200/sensor.py), both on a stand-in `self` with CPU tensors."""
+    import types
+
+    from oracle import ref_bootstrap as rb
+
+    if not rb.available():
+        pytest.skip("reference checkout not present on this machine")
+    from tacex_b200 import sensor as mine
+
+    ref = rb.ref_methods(rb.REF_ROOT / "source/tacex/tacex/gelsight_sensor.py", "GelSightSensor", ["_get_height_map", "_get_camera_depth"],
+                         {"torch": torch})
+    g = torch.Generator().manual_seed(0)
+    n, hc, wc = 3, 24, 32
+    depth = 0.024 + 0.005 * torch.rand((n, hc, wc), generator=g)
+    depth[0, :3] = float("inf")  # no hit: the far clipping plane
+    cfg = types.SimpleNamespace(sensor_camera_cfg=types.SimpleNamespace(clipping_range=(0.024, 0.029)))
+
+    def stand_in():
+        return types.SimpleNamespace(cfg=cfg, _num_envs=n, camera_resolution=(wc, hc),
+                                     _data=types.SimpleNamespace(output={"height_map": torch.zeros((n, hc, wc)), "camera_depth": None}))
+
+    r = stand_in()
+    r.camera = types.SimpleNamespace(data=types.SimpleNamespace(output={"depth": depth.clone()[..., None]}))
+    hm_ref = ref["_get_height_map"](r).clone()
+    r.camera.data.output["depth"] = depth.clone()[..., None]
+    cd_ref = ref["_get_camera_depth"](r).clone()
+    m = stand_in()
+    m._camera_depth = depth.clone()
+    hm_mine = mine.GelSightSensor._get_height_map(m).clone()
+    cd_mine = mine.GelSightSensor._get_camera_depth(m).clone()
+    assert torch.equal(hm_mine, hm_ref)
+    assert cd_mine.dtype == torch.uint8 and cd_mine.shape == cd_ref.shape and torch.equal(cd_mine, cd_ref)
