@@ -165,6 +165,23 @@ def ref_methods(path: Path, class_name: str, names: list[str], namespace: dict) 
     return {n: ns[n] for n in names}
 
 
+def ref_class(path: Path, class_name: str, names: list[str], namespace: dict, base: type = object) -> type:
+    """Like :func:`ref_methods`, but returns a CLASS holding the named methods (derived from ``base``), for methods that call
+    ``super()``: instantiate it with ``cls.__new__(cls)`` and set the attributes the methods read."""
+    import ast
+
+    tree = ast.parse(Path(path).read_text())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    node = ast.ClassDef(name=class_name, bases=[ast.Name(id="_RefBase", ctx=ast.Load())], keywords=[], body=fns, decorator_list=[],
+                        type_params=[])
+    mod = ast.fix_missing_locations(ast.Module(body=[node], type_ignores=[]))
+    ns = dict(namespace)
+    ns["_RefBase"] = base
+    exec(compile(mod, str(path), "exec"), ns)
+    return ns[class_name]
+
+
 class RefTaximSimulator:
     """The reference's ``TaximSimulator.optical_simulation`` / ``compute_indentation_depth`` (taxim_sim.py:80-131) EXECUTED on a
     stand-in ``self``: the real ``sim.Taxim`` instance, a dict as sensor output, the preset's cfg values."""

@@ -180,3 +180,75 @@ def test_sensor_depth_preprocessing_against_executed_reference_methods():
     cd_mine = mine.GelSightSensor._get_camera_depth(m).clone()
     assert torch.equal(hm_mine, hm_ref)
     assert cd_mine.dtype == torch.uint8 and cd_mine.shape == cd_ref.shape and torch.equal(cd_mine, cd_ref)
+
+
+def test_sensor_update_and_reset_call_order_matches_the_executed_reference():
+    """`GelSightSensor._update_buffers_impl` / `reset` (gelsight_sensor.py:147-201, 342-378) executed from the reference file and
+    the stand-in's same-named methods, both driven with recording simulators: same calls on the plug-in interface, same order,
+    same buffers written."""
+    import types
+
+    from oracle import ref_bootstrap as rb
+
+    if not rb.available():
+        pytest.skip("reference checkout not present on this machine")
+    from tacex_b200 import sensor as mine
+
+    class SensorBaseStandIn:  # Isaac Lab's SensorBase.reset only resets timestamps
+        def reset(self, env_ids=None):
+            pass
+
+    RefSensor = rb.ref_class(rb.REF_ROOT / "source/tacex/tacex/gelsight_sensor.py", "GelSightSensor", ["_update_buffers_impl", "reset"],
+                             {"torch": torch, "Sequence": list}, base=SensorBaseStandIn)
+    ref = {"_update_buffers_impl": RefSensor._update_buffers_impl, "reset": RefSensor.reset}
+
+    def run(fns, is_ref):
+        log = []
+        n = 4
+
+        class Sim:
+            def __init__(self, name):
+                self.name = name
+
+            def optical_simulation(self):
+                log.append(f"{self.name}.optical_simulation")
+                return torch.full((n, 2, 2, 3), 0.5)
+
+            def marker_motion_simulation(self):
+                log.append(f"{self.name}.marker_motion_simulation")
+                return torch.full((n, 2, 3, 2), 7.0)
+
+            def compute_indentation_depth(self):
+                log.append(f"{self.name}.compute_indentation_depth")
+                return torch.arange(n, dtype=torch.float32)
+
+            def reset(self):
+                log.append(f"{self.name}.reset")
+
+        opt, mrk = Sim("optical"), Sim("marker")
+        me = RefSensor.__new__(RefSensor) if is_ref else types.SimpleNamespace()
+        me.__dict__.update(dict(
+            cfg=types.SimpleNamespace(data_types=["tactile_rgb", "marker_motion", "height_map"], compute_indentation_depth_class="optical_sim",
+                                      sensor_camera_cfg=types.SimpleNamespace(clipping_range=(0.024, 0.029))),
+            camera=None, _camera_depth=None, _timestamp=0.0, _num_envs=n, _frame=torch.zeros(n, dtype=torch.long),
+            _ALL_INDICES=torch.arange(n), _indentation_depth=torch.zeros(n), optical_simulator=opt, marker_motion_simulator=mrk,
+            compute_indentation_depth_func=opt.compute_indentation_depth,
+            _data=types.SimpleNamespace(output={"tactile_rgb": torch.zeros((n, 2, 2, 3)), "marker_motion": torch.zeros((n, 2, 3, 2)),
+                                                "height_map": torch.ones((n, 2, 2))}),
+        ))
+        me._get_height_map = lambda: log.append("_get_height_map")
+        me._get_camera_depth = lambda: log.append("_get_camera_depth")
+        fns["_update_buffers_impl"](me, me._ALL_INDICES)
+        snap = (me._indentation_depth.clone(), me._data.output["tactile_rgb"].clone(), me._data.output["marker_motion"].clone(),
+                me._frame.clone())
+        log.append("--reset--")
+        fns["reset"](me, torch.tensor([1]))
+        return log, snap, me
+
+    log_r, snap_r, me_r = run(ref, True)
+    log_m, snap_m, me_m = run({"_update_buffers_impl": mine.GelSightSensor._update_buffers_impl, "reset": mine.GelSightSensor.reset}, False)
+    assert log_m == log_r, f"\\nreference: {log_r}\\nstand-in:  {log_m}"
+    for a, b in zip(snap_m, snap_r):
+        assert torch.equal(a, b)
+    assert torch.equal(me_m._indentation_depth, me_r._indentation_depth) and torch.equal(me_m._frame, me_r._frame)
+    assert torch.equal(me_m._data.output["height_map"], me_r._data.output["height_map"])
