@@ -252,3 +252,53 @@ def test_sensor_update_and_reset_call_order_matches_the_executed_reference():
         assert torch.equal(a, b)
     assert torch.equal(me_m._indentation_depth, me_r._indentation_depth) and torch.equal(me_m._frame, me_r._frame)
     assert torch.equal(me_m._data.output["height_map"], me_r._data.output["height_map"])
+
+
+def test_fem_defaults_are_the_reference_cfg_defaults():
+    """GelFemCfg against the literal defaults of the reference's cfg classes, read from the reference files with ast (the modules
+    need Isaac Lab's @configclass): UipcSimCfg (uipc_sim.py:32-131), UipcObjectCfg (uipc_object.py:59,79,84), the d_hat of the
+    ball-rolling UIPC task (ball_rolling_tactile_rgb_uipc.py:223)."""
+    import ast
+    from pathlib import Path
+
+    root = Path("/root/reference/source")
+    if not root.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from tacex_b200.fem import GelFemCfg
+
+    def defaults(path, cls_path):
+        node = ast.parse(Path(path).read_text())
+        for name in cls_path:
+            node = next(n for n in ast.walk(node) if isinstance(n, ast.ClassDef) and n.name == name)
+        out = {}
+        for n in node.body:
+            if isinstance(n, ast.AnnAssign) and n.value is not None:
+                try:
+                    out[n.target.id] = ast.literal_eval(n.value)
+                except ValueError:
+                    try:  # simple arithmetic like 0.1 / 1.0
+                        out[n.target.id] = eval(compile(ast.Expression(n.value), "<cfg>", "eval"), {"__builtins__": {}})
+                    except Exception:
+                        pass
+        return out
+
+    sim = root / "tacex_uipc/tacex_uipc/sim/uipc_sim.py"
+    top, newton = defaults(sim, ["UipcSimCfg"]), defaults(sim, ["UipcSimCfg", "Newton"])
+    lin, ls, con = defaults(sim, ["UipcSimCfg", "LinearSystem"]), defaults(sim, ["UipcSimCfg", "LineSearch"]), defaults(sim, ["UipcSimCfg", "Contact"])
+    c = GelFemCfg()
+    assert c.dt == top["dt"] and tuple(c.gravity) == tuple(top["gravity"])
+    assert c.newton_max_iter == newton["max_iter"] and c.newton_velocity_tol == newton["velocity_tol"]
+    assert c.pcg_tol_rate == lin["tol_rate"] and lin["solver"] == "linear_pcg"
+    assert c.line_search_max_iter == ls["max_iter"]
+    assert c.friction_ratio == con["default_friction_ratio"] and c.friction_eps_velocity == con["eps_velocity"]
+    assert c.contact_resistance == con["default_contact_resistance"] * 1e9  # GPa
+    obj = root / "tacex_uipc/tacex_uipc/objects/uipc_object.py"
+    src = Path(obj).read_text()
+    tree = ast.parse(src)
+    vals = {n.target.id: ast.literal_eval(n.value) for n in ast.walk(tree)
+            if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name) and n.value is not None
+            and n.target.id in ("mass_density", "youngs_modulus", "poisson_rate") and isinstance(n.value, ast.Constant)}
+    assert c.mass_density == vals["mass_density"] and c.poisson_rate == vals["poisson_rate"]
+    assert c.youngs_modulus == vals["youngs_modulus"] * 1e6  # MPa (uipc_object.py:453: youngs * MPa)
+    task = (root / "tacex_tasks/tacex_tasks/ball_rolling_tactile/ball_rolling_tactile_rgb_uipc.py").read_text()
+    assert "d_hat=0.0005" in task and c.d_hat == 0.0005
