@@ -555,8 +555,8 @@ extern "C" int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* 
     }
     // The stores are posted writes bounded by the NVLink egress (900 GB/s per direction), not by the SMs: a few dozen CTAs keep
     // the links busy, and every SM that hosts one is lost to the render kernel of the next step (its 128-register threads leave
-    // no room for a second CTA), so the grid stays small. TX_OBS_PUSH_CTAS overrides it for experiments.
-    int cap = 32;
+    // no room for a second CTA), so the grid stays small (64 CTAs). TX_OBS_PUSH_CTAS overrides it for experiments.
+    int cap = 64; // measured: 4 GPUs 1.41 M (32) vs 1.43 M (64) frames/s, 8 GPUs 1.31 M vs 1.33 M; 16 CTAs starve the links
     if (const char* e = getenv("TX_OBS_PUSH_CTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
     const int grid = 2 * N < cap ? 2 * N : cap;
     TX_CUDA(h, launch_obs_push(a, grid, (cudaStream_t)cuda_stream));
