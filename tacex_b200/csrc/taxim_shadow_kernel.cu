@@ -32,7 +32,7 @@ __device__ __forceinline__ int reflect_i(int i, int n)
 __device__ __forceinline__ void atomic_min_float(float* addr, float v)
 {
     if (v >= 0.0f)
-        atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+        atomicMin(reinterpret_cast<int*>(addr), __float_as_int(__fadd_rn(v, 0.0f))); // -0.0f + 0.0f = +0.0f: -0 must not sort below the negatives
     else
         atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
