@@ -15,6 +15,8 @@ Select them with ``cfg.simulation_approach_class = B200TaximSimulator`` (see INT
 
 from __future__ import annotations
 
+import os
+
 from abc import ABC, abstractmethod
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -152,10 +154,13 @@ class B200TaximSimulator(GelSightSimulator):
         self._device = self.sensor.device if self.cfg.device is None else self.cfg.device
         if not _is_cuda(self._device):
             raise RuntimeError("B200TaximSimulator runs on a CUDA (sm_100a) device only; there is no CPU path")
-        if self.cfg.with_shadow:
-            raise NotImplementedError("with_shadow=True is not implemented (every GelSight Mini preset disables it)")
         self._num_envs = self.sensor._num_envs
         W, H = self.cfg.tactile_img_res
+        if self.cfg.with_shadow and ((H, W) != (240, 320) or os.environ.get("TACEX_B200_UNVALIDATED_SHADOW") != "1"):
+            # every GelSight Mini preset disables the shadows. The device version of the shadow branch (tx_render_shadow) exists
+            # but has not been validated on a GPU yet: it is strictly opt-in.
+            raise NotImplementedError("with_shadow=True: the shadow kernels are not validated yet; set "
+                                      "TACEX_B200_UNVALIDATED_SHADOW=1 to use them at 320x240 anyway")
         self.img_res = self.cfg.tactile_img_res
         tables = _load_tables(self.cfg.calib_folder_path, (H, W))
         mcfg = getattr(self.sensor.cfg, "marker_motion_sim_cfg", None)
@@ -172,6 +177,13 @@ class B200TaximSimulator(GelSightSimulator):
             marker_y0=y0, mm2pix=mm2pix, gelpad_height_m=self.cfg.gelpad_height,
             gelpad_to_cam_min_m=self.cfg.gelpad_to_camera_min_distance,
         )
+        if self.cfg.with_shadow:
+            from .calib import ShadowTables
+
+            p = Path(self.cfg.calib_folder_path)
+            baked = p / f"shadow_tables_{W}x{H}.npz" if p.is_dir() else None
+            self.engine.upload_shadow_tables(ShadowTables.load(baked) if baked is not None and baked.exists()
+                                             else ShadowTables.from_calib_folder(p, (H, W)))
         dev = self.engine.device
         self._indentation_depth = torch.zeros((self._num_envs,), device=dev)
         self._own_rgb = torch.zeros((self._num_envs, H, W, 3), device=dev)
@@ -208,7 +220,7 @@ class B200TaximSimulator(GelSightSimulator):
 
     def _render(self, press, depth_out=None):
         raw = self.sensor._data.output["height_map"]
-        if self._camera_mode(raw):
+        if not self.cfg.with_shadow and self._camera_mode(raw):
             cam = raw if raw.device == self.engine.device else raw.to(self.engine.device)
             self.engine.render_camera(cam.contiguous(), press=press, out=self._rgb_target(), depth_out=depth_out)
             return
@@ -221,6 +233,9 @@ class B200TaximSimulator(GelSightSimulator):
             press = press.to(self.engine.device, torch.float32).contiguous()
             if depth_out is not None:
                 depth_out.copy_(press)
+        if self.cfg.with_shadow:
+            self.engine.render_shadow(hm, press, out=self._rgb_target(), depth_out=depth_out if press is None else None)
+            return
         self.engine.render(hm, press, out=self._rgb_target(), depth_out=depth_out if press is None else None)
 
     def _rgb_target(self) -> torch.Tensor:
@@ -252,6 +267,8 @@ class B200TaximSimulator(GelSightSimulator):
         sensor's ``height_map`` output in place and returns the indentation depth."""
         hm = self.sensor._data.output["height_map"]
         W, H = self.cfg.tactile_img_res
+        if self.cfg.with_shadow:
+            return None  # the shadow post-pass has no fused depth entry point: the sensor takes the reference's call order
         if tuple(depth_m.shape[1:]) != (H, W) or hm.shape != depth_m.shape or not hm.is_contiguous() or hm.device != self.engine.device:
             return None
         self.engine.render_depth(depth_m.contiguous(), clip_max_m, out=self._rgb_target(), depth_out=self._indentation_depth,
