@@ -213,3 +213,26 @@ def test_marker_weights_against_the_executed_reference_function():
     p_ref = (Xd[idx_ref] * w_ref[..., None]).sum(1)
     p_me = (Xd[tri] * w[..., None]).sum(1)
     assert np.abs(p_ref - p_me).max() <= 1e-9
+
+
+def test_reference_arm_under_torchrun_prints_one_json_line_from_rank_0():
+    """bench.py --impl reference launched like the driver launches it for N > 1: rank 0 alone runs and prints ONE JSON line with
+    the contract's keys, the other rank exits 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    port = 29800 + os.getpid() % 150
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["n_gpus"] == 2
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
