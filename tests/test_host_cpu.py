@@ -236,3 +236,19 @@ def test_reference_arm_under_torchrun_prints_one_json_line_from_rank_0():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["n_gpus"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_has_no_cpu_path_for_the_product_arm():
+    """Without a CUDA device the product arm of bench.py must fail loudly instead of timing anything on the CPU."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=str(root))
+    assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout) and not any(l.startswith("{") for l in r.stdout.splitlines())
