@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(SH_THREADS) shadow_blur_v_kernel(const float* 
     }
 }
 
+#ifndef TX_EMULATE // the host emulation of tools/emu drives the kernels itself (no <<< >>> there)
 cudaError_t launch_shadow(const ShadowArgs& a, int n, float* t1, float* t2, float* rgb, const float* bg_hwc, const float* taps_sx,
                           int ks_sx, const float* taps_sy, int ks_sy, const float* taps_fx, int ks_fx, const float* taps_fy,
                           int ks_fy, cudaStream_t s)
@@ -204,5 +205,6 @@ cudaError_t launch_shadow(const ShadowArgs& a, int n, float* t1, float* t2, floa
     shadow_blur_v_kernel<1><<<gpl, SH_THREADS, 0, s>>>(t1, rgb, taps_fy, ks_fy, bg_hwc);
     return cudaGetLastError();
 }
+#endif
 
 } // namespace tx

@@ -86,3 +86,56 @@ def test_shadow_tables_and_fresh_inputs_vs_executed_reference(canon_taxim, shado
     dg, _ = rb.ref_deformed_gel(tx, hm, press)
     _, _, im, idr = rb.ref_normals_bins(tx, dg)
     _check(canon_taxim, st, hm.numpy(), press.numpy(), rgb, im.numpy(), idr.numpy(), sh)
+
+
+def test_shadow_kernel_source_emulated_on_the_host_matches_the_restatement(tables, canon_taxim, shadow_tables):
+    """No GPU has run csrc/taxim_shadow_kernel.cu yet. Its kernels are plain per-pixel code, so the SAME SOURCE FILE is compiled
+    for the host (tools/emu: a stand-in <cuda_runtime.h> maps every intrinsic to the identical IEEE-754 operation) and driven
+    thread by thread on the deformed gel + mask of the canonical restatement (with which the fused GPU kernel is bit-identical).
+    The result must equal canon_taxim_render_shadow bit for bit. This checks the kernels' logic (indexing, dilation, ray casting,
+    integer-atomic float minimum, blur order), not the GPU execution -- that is tests/test_zz_unvalidated_gpu.py."""
+    import ctypes as C
+    import subprocess
+    from pathlib import Path
+
+    from oracle import canon
+    from oracle import make_golden_shadow as mg
+    from tacex_b200 import synth
+
+    root = Path(__file__).resolve().parent.parent
+    so = root / "tools" / "emu" / "_build" / "libshadow_emu.so"
+    srcs = [root / "tools/emu/shadow_emu.cpp", root / "tools/emu/include/cuda_runtime.h", root / "tacex_b200/csrc/taxim_shadow_kernel.cu",
+            root / "tacex_b200/csrc/tx_common.cuh", root / "tacex_b200/csrc/tx_kernels.h"]
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
+        so.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-w", f"-I{root / 'tools/emu/include'}",
+                        "-o", str(so), str(srcs[0])], check=True, capture_output=True)
+    emu = C.CDLL(str(so))
+    st = shadow_tables
+    hm = torch.cat([mg.inputs()[:2], synth.golden_config1(H, W)[3:5]]).numpy()  # config 0, a config-2 env, a sphere, an env without contact
+    n = hm.shape[0]
+    press = canon_taxim.indentation_depth(hm)
+    base = canon_taxim.render(hm, press, want=("deformed", "mask"))
+    ref = canon.render_shadow(canon_taxim, st, hm, press)
+    # device layouts of tx_upload_tables: poly [nb][nb][3 * 6 padded to 20], background [H][W][3]
+    nb = tables.params.num_bins
+    poly20 = np.zeros((nb, nb, 20), np.float32)
+    poly20[:, :, :18] = tables.poly_grad.numpy().transpose(1, 2, 0, 3).reshape(nb, nb, 18)
+    bg_hwc = np.ascontiguousarray(tables.background.numpy().transpose(1, 2, 0))
+    taps = tables.params.blur_taps((H, W))
+    tfx, tfy = (np.ascontiguousarray(t.numpy(), np.float32) for t in taps[-1])
+    tsx, tsy = (np.ascontiguousarray(t, np.float32) for t in st.blur_taps)
+    dil = np.array([st.dilate_rounds[0][0], st.dilate_rounds[0][1], st.dilate_rounds[1][0], st.dilate_rounds[1][1]], np.int32)
+    tab = np.ascontiguousarray(st.table, np.float32)
+    fcos, fsin = np.ascontiguousarray(st.fan_cos, np.float32), np.ascontiguousarray(st.fan_sin, np.float32)
+    deformed = np.ascontiguousarray(base["deformed"], np.float32)
+    mask = np.ascontiguousarray(base["mask"], np.uint8)
+    rgb = np.empty((n, H, W, 3), np.float32)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    f32 = C.c_float
+    emu.emu_shadow(fp(deformed), mask.ctypes.data_as(C.POINTER(C.c_uint8)), None, fp(poly20), fp(bg_hwc), fp(tab), fp(fcos), fp(fsin),
+                   tab.shape[1], tab.shape[2], tab.shape[3], fcos.shape[1], nb, dil.ctypes.data_as(C.POINTER(C.c_int)),
+                   f32(tables.params.pixmm), f32(tables.params.calib_h), f32(tables.params.calib_w), f32(st.depth_0),
+                   f32(st.height_precision), f32(st.discretize_precision), f32(st.step_x), f32(st.step_y), fp(tsx), tsx.size, fp(tsy),
+                   tsy.size, fp(tfx), tfx.size, fp(tfy), tfy.size, n, fp(rgb))
+    assert np.array_equal(rgb, ref), f"max |d| = {np.abs(rgb - ref).max()}"
