@@ -121,37 +121,105 @@ def cpu_port_fps(n_frames: int, with_markers: bool = True) -> tuple[float, int, 
     return n_frames / dt, canon.num_threads(), f"{n_frames} frames of the same workload (config-1 sphere presses), one pass"
 
 
-def fem_cpu_port(n_gels: int = 64) -> tuple[float, int, str]:
-    """Gel FEM substep on the host cores with the float64 CPU restatement (libuipc itself has no CPU backend)."""
+BLUR_RADII = (30, 16, 8, 4, 2, 1, 2)
+
+
+def fp32_lane_ops_per_frame(hm_pool) -> float:
+    """FP32 lane-operations (FMA / FADD / FMUL on one float) the exact separable pyramid NEEDS for these frames given the
+    kernel's exact-zero skipping: per level, rows x columns that can be non-zero x (2R+1) taps for the horizontal pass and the
+    same for the vertical pass (R adds of the symmetric pairs + R+1 multiply-adds), the region growing by R per level.
+    A dense frame (gel map or full-frame contact) costs 266 x 76,800 = 20.4 M; the colour stage is not counted."""
     import numpy as np
 
-    from oracle import fem_canon as fc
-    from tacex_b200 import gel_mesh
+    hm = hm_pool.numpy() if hasattr(hm_pool, "numpy") else np.asarray(hm_pool)
+    tot = 0.0
+    for f in hm:
+        m = f.min()
+        d = max(m / 1000.0 - 0.024, 0.0)
+        press = (0.0045 - d) * 1000.0 if d <= 0.0045 else 0.0
+        c = (f - m - press) < 0
+        if press <= 0 or not c.any():
+            continue
+        ys, xs = np.nonzero(c)
+        r0, r1, c0, c1 = ys.min(), ys.max(), xs.min(), xs.max()
+        for R in BLUR_RADII:
+            h, w = r1 - r0 + 1, c1 - c0 + 1
+            c0, c1 = max(c0 - R, 0), min(c1 + R, W - 1)
+            tot += h * (c1 - c0 + 1) * (2 * R + 1)            # horizontal pass: input rows x output columns
+            r0, r1 = max(r0 - R, 0), min(r1 + R, H - 1)
+            tot += (r1 - r0 + 1) * (c1 - c0 + 1) * (2 * R + 1)  # vertical pass: output rows x columns
+    return tot / len(hm)
+
+
+def fem_cpu_port(n_gels: int = 128, n_steps: int = 4) -> tuple[float, int, str]:
+    """Gel FEM substep on the host cores with the float64 CPU restatement (libuipc itself has no CPU backend): the config-3
+    box edge / corner press, steps 21..24 of 30 after an untimed run-in of the same gels."""
+    import numpy as np
 
     from oracle import canon as _canon
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh, synth
 
     _canon.use_all_threads()
     m = gel_mesh.box_gel()
     cf = fc.CanonFem(m)
-    rng = np.random.default_rng(2)
-    offs = rng.uniform(-1, 1, (n_gels, 2)) * np.array([6e-3, 8e-3])
-    half = (2e-3, 3e-3, 1e-3)
-    z0 = 4.5e-3 + half[2] + 4e-4
+    c3 = synth.config3_box(n_gels, seed=2, step=0)
+    R = c3["R"].numpy()
+    half = np.asarray(c3["half"])
+    low = np.abs(R[:, 2, :] * half[None]).sum(1)
     x, v, xp = cf.new_state(n_gels)
     aim = cf.X[cf.attach][None].repeat(n_gels, 0)
-    mk = lambda s: [fc.make_indenter(1, (o[0], o[1], z0 - 1e-3 * s / 30), half) for o in offs]  # noqa: E731
-    cf.step(x, v, xp, aim, mk(0), mk(1))
+    mk = lambda s: [fc.make_indenter(1, (c3["cx"][i].item(), c3["cy"][i].item(), 4.5e-3 + low[i] + 4e-4 - 1e-3 * s / 30), half, R[i])  # noqa: E731
+                    for i in range(n_gels)]
+    first = 21
+    for s in range(0, first, 3):  # coarse run-in (3 press steps per solver step) so that the timed steps see real contact
+        cf.step(x, v, xp, aim, mk(s), mk(s + 3))
     t0 = time.perf_counter()
-    for s in (1, 2):
+    for s in range(first, first + n_steps):
         cf.step(x, v, xp, aim, mk(s), mk(s + 1))
     dt = time.perf_counter() - t0
-    from oracle import canon
+    return (n_steps * n_gels / dt, _canon.num_threads(),
+            f"{n_gels} gels x {n_steps} steps (steps {first}..{first + n_steps - 1} of 30) of the config-3 box edge / corner press "
+            f"(float64 CPU restatement, OpenMP over gels)")
 
-    return 2 * n_gels / dt, canon.num_threads(), f"{n_gels} gels x 2 steps of the config-3 box press (float64 CPU restatement)"
+
+class Config3:
+    """BASELINE config 3 inputs: a rigid 4 x 6 x 2 mm box pressed with an EDGE / a CORNER 0 -> 1 mm into the gel over 30 steps
+    (seed 2 for the pose jitter) -- the SAME poses as FEM indenters (tx_fem_indenter) and as recorded depth maps of the sensor
+    camera (the reference renders the tactile image from the camera's depth image of the indenter, not from the FEM state).
+    ``n_unique`` poses tiled to E envs (every env still runs the full path). Timed steps = the deepest part of the press."""
+
+    def __init__(self, E: int, dev, seed: int = 2, n_unique: int = 64, first: int = 24, last: int = 30):
+        import numpy as np
+        import torch
+
+        from tacex_b200 import fem, synth
+
+        self.E, self.dev, self.first, self.last = E, dev, first, last
+        k = min(n_unique, E)
+        c3 = synth.config3_box(k, seed=seed, step=0)
+        R = c3["R"].numpy()
+        half = np.asarray(c3["half"])
+        low = np.abs(R[:, 2, :] * half[None]).sum(1)  # lowest corner below the box centre
+        reps = (E + k - 1) // k
+        tile = lambda a: np.concatenate([a] * reps, 0)[:E]  # noqa: E731
+        self.idx = torch.arange(E, device=dev) % k
+        top = 4.5e-3
+        self.inds, self.hm_pool = [], {}
+        for s in range(last + 1):
+            ctr = np.stack([c3["cx"].numpy(), c3["cy"].numpy(), top + low + 4e-4 - 1e-3 * s / 30], 1)
+            self.inds.append(fem.indenter_array(1, tile(ctr), half, tile(R), device=dev))
+        for s in range(first, last + 1):
+            self.hm_pool[s] = synth.height_map_mm(synth.config3_box(k, seed=seed, step=s)["depth_m"]).to(dev)
+
+    def height_maps(self, s: int):
+        return self.hm_pool[min(max(s, self.first), self.last)][self.idx].contiguous()
 
 
-def fem_gpu(E: int, steps: int, dev, tactile=None) -> dict:
-    """Config 3 extra: batched gel FEM substep + FEM marker read-out for E gels (box indenter pressed 0 -> 1 mm in 30 steps)."""
+def fem_gpu(E: int, dev, tactile=None) -> dict:
+    """Config 3: batched gel FEM substep + FEM marker read-out for E gels, and the full config-3 step (FEM substep + FEM markers
+    + Taxim RGB from the recorded depth maps of the SAME box poses). Steps 0..23 of the 30-step press run untimed; the timed
+    steps are 24..29 (deepest contact)."""
     import numpy as np
     import torch
 
@@ -161,79 +229,227 @@ def fem_gpu(E: int, steps: int, dev, tactile=None) -> dict:
     eng = fem.GelFemEngine(m, device=dev)
     tri, w = fem.marker_grid_weights(m)
     eng.set_markers(tri, w)
-    rng = np.random.default_rng(2)
-    offs = rng.uniform(-1, 1, (E, 2)) * np.array([6e-3, 8e-3])
-    half = (2e-3, 3e-3, 1e-3)
-    z0 = 4.5e-3 + half[2] + 4e-4
+    c3 = Config3(E, dev)
     x, v, xp = eng.new_state(E)
     aim = eng.rest_aim(E)
-    ctr = lambda s: np.concatenate([offs, np.full((E, 1), z0 - 1e-3 * s / 30)], 1)  # noqa: E731
-    inds = [fem.indenter_array(1, ctr(s), half, device=dev) for s in range(2 * steps + 3)]
     mk = torch.empty((E, 2, 128, 2), device=dev)
-    for s in range(2):
-        eng.step(x, v, xp, aim, inds[s], inds[s + 1], want_stats=False)
+    for s in range(c3.first - 3):
+        eng.step(x, v, xp, aim, c3.inds[s], c3.inds[s + 1], want_stats=False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     st = None
-    for s in range(2, 2 + steps):
-        st = eng.step(x, v, xp, aim, inds[s], inds[s + 1], want_stats=True)
+    for s in range(c3.first - 3, c3.first):
+        st = eng.step(x, v, xp, aim, c3.inds[s], c3.inds[s + 1], want_stats=True)
         eng.markers(x, out=mk)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms = e0.elapsed_time(e1) / 3
     d = eng.decode_stats(st)
-    full = None
+    out = {"workload": f"{E} gels (572 verts / 2160 tets, float64): implicit-Euler IPC substep + FEM marker read-out, config-3 box "
+                       f"edge / corner press (steps {c3.first - 3}..{c3.first - 1} of 30)",
+           "gel_steps_per_s": E / (ms / 1e3), "ms_per_step": ms,
+           "newton_iters_mean": float(np.mean([q["newton_iters"] for q in d])),
+           "pcg_iters_mean": float(np.mean([q["pcg_iters"] for q in d])),
+           "compulsory_bytes_per_gel_step": 315136,
+           "hbm_frac_on_compulsory_bytes": 315136 * E / (ms / 1e3) / 1e9 / _peaks()[0]}
     if tactile is not None:
-        # config 3 as one step: gel FEM substep + FEM marker read-out + Taxim RGB from the recorded depth maps of the same envs
-        t_eng, hm, rgb, depth = tactile
+        t_eng, rgb, depth = tactile
+        hms = [c3.height_maps(s + 1) for s in range(c3.first, c3.last)]
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         f0.record()
-        for s in range(2 + steps, 2 + 2 * steps):
-            k = min(s, len(inds) - 2)
-            eng.step(x, v, xp, aim, inds[k], inds[k + 1], want_stats=False)
+        for j, s in enumerate(range(c3.first, c3.last)):
+            eng.step(x, v, xp, aim, c3.inds[s], c3.inds[s + 1], want_stats=False)
             eng.markers(x, out=mk)
-            t_eng.render(hm[:E], None, out=rgb[:E], depth_out=depth[:E])
+            t_eng.render(hms[j], None, out=rgb[:E], depth_out=depth[:E])
         f1.record()
         torch.cuda.synchronize()
-        fms = f0.elapsed_time(f1) / steps
-        full = {"workload": f"config 3: {E} envs, gel FEM substep + FEM markers + Taxim RGB 320x240 per step",
-                "frames_per_s": E / (fms / 1e3), "ms_per_step": fms}
-    out = {"workload": f"{E} gels (572 verts / 2160 tets, float64): implicit-Euler IPC substep + FEM marker read-out",
-            "gel_steps_per_s": E / (ms / 1e3), "ms_per_step": ms,
-            "newton_iters_mean": float(np.mean([q["newton_iters"] for q in d])),
-            "pcg_iters_mean": float(np.mean([q["pcg_iters"] for q in d])),
-            "compulsory_bytes_per_gel_step": 315136}
-    if full is not None:
-        out["config3_full_step"] = full
+        fms = f0.elapsed_time(f1) / (c3.last - c3.first)
+        out["config3_full_step"] = {
+            "workload": f"config 3: {E} envs, gel FEM substep + FEM markers + Taxim RGB 320x240 from the depth maps of the same box "
+                        f"poses, steps {c3.first}..{c3.last - 1} of the 30-step press",
+            "frames_per_s": E / (fms / 1e3), "ms_per_step": fms}
     return out
 
 
+REF_BATCH = 32  # envs per reference call: the batch size at which the reference's CPU path is fastest
+
+
+def cpu_reference_fps(reps: int, warmup: int = 1) -> tuple[float, int, str] | None:
+    """The UNMODIFIED reference (TaximTorch.render_direct + indentation depth + the per-env MarkerMotion loop, staged under the
+    git-ignored baseline/_ref/ by baseline/stage_ref.py) on all host cores, on a bounded sample of the same workload.
+    None when the staged copy is absent (then the oracle's C port is timed instead)."""
+    from baseline import ref_arm
+
+    if not ref_arm.available():
+        return None
+    from tacex_b200 import synth
+
+    hm = synth.bench_batch(64, n_unique=64)
+    fps, threads = ref_arm.time_cpu(hm, REF_BATCH, reps, warmup=warmup, with_markers=True)
+    return fps, threads, (f"{reps} sensor updates of {REF_BATCH} envs each (config-1 sphere presses): the reference's own TaximTorch.render_direct "
+                          f"+ compute_indentation_depth + per-env MarkerMotion.marker_sim loop, torch CPU, {threads} threads")
+
+
 def run_reference(args) -> None:
-    """--impl reference: the reference's algorithm on the host cores. The reference's own implementation is Python
-    (torch + NumPy) inside /root/reference, which does not exist on the GPU box, so the timed code is the oracle's
-    C port of it (kind = "port"), with all host threads it can use (OpenMP over frames)."""
+    """--impl reference: the reference's OWN implementation of the path on the host cores -- the unmodified TaximTorch /
+    MarkerMotion code staged under baseline/_ref/ (kind = "reference"), with all host threads torch can use. Each step is a
+    bounded sample (one sensor update of 32 envs). Falls back to the oracle's C port (kind = "port") only if the staged copy
+    is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = 256
-    vals = []
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_port_fps(64)
-    for _ in range(max(1, min(args.steps, 5))):
-        fps, cores, sample = cpu_port_fps(n)
-        vals.append(fps)
-    v = statistics.median(vals)
+    K = max(1, min(args.steps, 20))
+    Wm = max(1, min(args.warmup, 3))
+    r = cpu_reference_fps(K, warmup=Wm)
+    if r is not None:
+        v, cores, sample = r
+        kind, n = "reference", REF_BATCH
+    else:
+        for _ in range(Wm):
+            cpu_port_fps(64)
+        n = 256
+        vals = [cpu_port_fps(n)[0] for _ in range(min(K, 5))]
+        K = len(vals)
+        v = statistics.median(vals)
+        _, cores, sample = cpu_port_fps(8)
+        kind = "port"
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": 1, "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": K,
+        "warmup": Wm, "ms_per_step": 1000.0 * n / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n}-frame bounded sample per step of: {args.envs} envs x 320x240, Taxim RGB + FOTS {M}-marker motion"},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{n}-env bounded sample per step of: {args.envs} envs x 320x240, indentation depth + Taxim RGB + FOTS {M}-marker motion, "
+                               f"sphere indenters (config-1 distribution)"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+class StepRunner:
+    """One rank's step loop: [gel FEM substep + FEM markers] + fused Taxim render + FOTS markers for E envs, and (N > 1) the
+    all-gather of the float32 RGB observation on a side stream, overlapped with the next step (double-buffered)."""
+
+    def __init__(self, args, eng, E, dev, world, rank, hm_sets, fem_ctx=None):
+        import torch
+
+        from tacex_b200.shard import PeerObsGather
+
+        self.args, self.eng, self.E, self.dev, self.world, self.rank = args, eng, E, dev, world, rank
+        self.hm_sets, self.fem = hm_sets, fem_ctx
+        self.theta = torch.zeros(E, device=dev)
+        self.depth = torch.empty(E, device=dev)
+        rgb = torch.empty((E, H, W, 3), device=dev)
+        self.markers = torch.empty((E, 2, M, 2), device=dev)
+        self.traj0 = torch.zeros((E, 4), device=dev)
+        self.traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
+        self.do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl")
+        self.use_rects = args.obs_gather == "fp32-rect" or (args.obs_gather == "fp32" and world > 2)
+        self.rgb_buf = [rgb, torch.empty_like(rgb)] if self.do_gather else [rgb]
+        self.peer, self.gathered, self.gather_kind = None, None, "n/a"
+        if self.do_gather:
+            if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
+                try:
+                    self.peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=self.use_rects,
+                                              multicast=not args.no_multicast)
+                    self.rgb_buf = [self.peer.local_block(0), self.peer.local_block(1)]  # render straight into the gathered buffer
+                    self.gather_kind = (
+                        "float32 all-gather of RGB, bit-identical to gathering whole frames: NVLink peer stores of every frame's "
+                        "non-flat rectangle into symmetric memory ("
+                        + ("NVSwitch multicast stores" if (self.use_rects and self.peer.mc_rgb[0]) else "one store per peer")
+                        + ") + local completion from the flat image, overlapped with the next step"
+                        if self.use_rects else
+                        "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step")
+                except Exception as exc:  # symmetric memory unavailable on this box
+                    print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+            if self.peer is None:
+                self.gathered = [torch.empty((world * E, H, W, 3), device=dev) for _ in range(2)]
+                self.gather_kind = "float32 NCCL all_gather_into_tensor of RGB, overlapped with the next step on a side stream"
+        self.side = torch.cuda.Stream(device=dev, priority=-1) if self.do_gather else None
+        self.ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self.last = (0, 0)  # (slot, input-set index) of the last step
+
+    def step(self):
+        import torch
+
+        from tacex_b200.shard import all_gather_obs
+
+        i = (self.i & 1) if self.do_gather else 0
+        k = self.i % len(self.hm_sets)
+        self.i += 1
+        self.last = (i, k)
+        if self.do_gather:
+            torch.cuda.current_stream().wait_event(self.ev_free[i])  # the gather that read this buffer two steps ago is done
+        if self.fem is not None:
+            self.fem.step()
+        if self.peer is not None and self.use_rects:
+            self.eng.set_rect_output(self.peer.local_rects(i))
+        self.eng.render(self.hm_sets[k], None, out=self.rgb_buf[i], depth_out=self.depth)
+        self.eng.fots_markers(self.depth, self.theta, self.traj0, self.traj_len, out=self.markers)
+        if self.do_gather:
+            self.ev_done[i].record()
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.ev_done[i])
+                if self.peer is not None and self.use_rects:
+                    self.peer.gather_rects(self.eng, i, self.side)
+                elif self.peer is not None:
+                    self.peer.gather(self.rgb_buf[i], i)
+                else:
+                    all_gather_obs(self.rgb_buf[i], self.gathered[i])
+                self.ev_free[i].record()
+
+    def finish(self):
+        import torch
+
+        if self.do_gather:
+            torch.cuda.current_stream().wait_stream(self.side)  # the last gathers finish inside the timed region
+        self.eng.set_rect_output(None)
+
+    def verify_gather(self, remote_sets_fn) -> bool | None:
+        """After a step: re-render the block of ONE remote rank locally from that rank's (deterministic) inputs and compare it,
+        bit for bit, with what the gather delivered into this rank's buffer."""
+        import torch
+
+        if not self.do_gather:
+            return None
+        torch.cuda.synchronize()
+        slot, k = self.last
+        r = (self.rank + 1) % self.world
+        full = self.peer.bufs[slot] if self.peer is not None else self.gathered[slot]
+        ref = torch.empty((self.E, H, W, 3), device=self.dev)
+        self.eng.set_rect_output(None)
+        self.eng.render(remote_sets_fn(r)[k], None, out=ref)
+        torch.cuda.synchronize()
+        own = torch.equal(full[self.rank * self.E:(self.rank + 1) * self.E], self.rgb_buf[slot])
+        return bool(own and torch.equal(full[r * self.E:(r + 1) * self.E], ref))
+
+
+class FemCtx:
+    """Gel FEM substep + FEM marker read-out of E gels walking through the config-3 press (used by the config-4 step)."""
+
+    def __init__(self, E, dev, c3):
+        import torch
+
+        from tacex_b200 import fem, gel_mesh
+
+        m = gel_mesh.box_gel()
+        self.eng = fem.GelFemEngine(m, device=dev)
+        tri, w = fem.marker_grid_weights(m)
+        self.eng.set_markers(tri, w)
+        self.c3 = c3
+        self.x, self.v, self.xp = self.eng.new_state(E)
+        self.aim = self.eng.rest_aim(E)
+        self.mk = torch.empty((E, 2, 128, 2), device=dev)
+        self.s = 0
+
+    def step(self):
+        s = min(self.s, len(self.c3.inds) - 2)
+        self.eng.step(self.x, self.v, self.xp, self.aim, self.c3.inds[s], self.c3.inds[s + 1], want_stats=False)
+        self.eng.markers(self.x, out=self.mk)
+        self.s += 1
 
 
 def main() -> None:
@@ -251,7 +467,9 @@ def main() -> None:
                          "fp32-rect beyond; nccl = all_gather_into_tensor; none = observations stay sharded")
     ap.add_argument("--no-multicast", action="store_true", help="fp32-rect: one store per peer instead of NVSwitch multicast stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fem", action="store_true", help="skip the extra gel-FEM measurement (config 3)")
+    ap.add_argument("--no-fem", action="store_true", help="skip the gel-FEM measurements (config 3 / config 4)")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_dense / reference_cuda (the contract keys stay)")
+    ap.add_argument("--config4-envs", type=int, default=1024, help="envs per GPU of the config-4 step (8192 = 8 x 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -263,7 +481,6 @@ def main() -> None:
     from tacex_b200 import synth
     from tacex_b200.calib import TaximTables
     from tacex_b200.engine import TactileEngine
-    from tacex_b200.shard import PeerObsGather, all_gather_obs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -283,65 +500,19 @@ def main() -> None:
     eng = TactileEngine(tables, max_envs=E, device=dev, marker_rows=MARKER_ROWS, marker_cols=MARKER_COLS)
 
     # ---- synthetic "recorded" depth maps: the shard of envs [rank*E, (rank+1)*E) ---------------------------------
-    hm_host = synth.bench_batch(E, seed=rank, n_unique=64).pin_memory()
-    theta_host = torch.zeros(E).pin_memory()
-    hm = hm_host.to(dev)
     # consecutive steps see DIFFERENT depth maps for every env (the pool of unique maps shifted by a prime number of envs):
     # nothing a step produces can be carried over from the previous one, and the rectangle transport of the observation
     # gather has to restore the previous rectangles of each buffer (contacts that jump, the unfavourable case)
-    hm_sets = [hm, hm.roll(37, 0).contiguous(), hm.roll(74, 0).contiguous()]
-    theta = theta_host.to(dev)
-    depth = torch.empty(E, device=dev)
-    rgb = torch.empty((E, H, W, 3), device=dev)
-    markers = torch.empty((E, 2, M, 2), device=dev)
-    traj0 = torch.zeros((E, 4), device=dev)
-    traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
-    # N > 1: the observation all-gather of step t runs on a side stream while step t+1 computes (double-buffered RGB)
-    do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl")
-    use_rects = args.obs_gather == "fp32-rect" or (args.obs_gather == "fp32" and world > 2)
-    rgb_buf = [rgb, torch.empty_like(rgb)] if do_gather else [rgb]
-    peer, gathered, gather_kind = None, None, "n/a"
-    if do_gather:
-        if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
-            try:
-                peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=use_rects, multicast=not args.no_multicast)
-                rgb_buf = [peer.local_block(0), peer.local_block(1)]  # the kernel renders straight into the gathered buffer
-                gather_kind = ("float32 all-gather of RGB, bit-identical to gathering whole frames: NVLink peer stores of every frame's "
-                               "non-flat rectangle into symmetric memory ("
-                               + ("NVSwitch multicast stores" if (use_rects and peer.mc_rgb[0]) else "one store per peer")
-                               + ") + local completion from the flat image, overlapped with the next step"
-                               if use_rects else
-                               "float32 all-gather of RGB by NVLink peer copies into symmetric memory (copy engines), overlapped with the next step")
-            except Exception as exc:  # symmetric memory unavailable on this box
-                print(f"[bench] symmetric-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
-        if peer is None:
-            gathered = [torch.empty((world * E, H, W, 3), device=dev) for _ in range(2)]
-            gather_kind = "float32 NCCL all_gather_into_tensor of RGB, overlapped with the next step on a side stream"
-    side = torch.cuda.Stream(device=dev, priority=-1) if do_gather else None
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0}
+    def sets_of(r: int, host=None):
+        h = synth.bench_batch(E, seed=r, n_unique=64) if host is None else host
+        d = h.to(dev)
+        return [d, d.roll(37, 0).contiguous(), d.roll(74, 0).contiguous()]
 
-    def step():
-        i = (state["i"] & 1) if do_gather else 0
-        state["i"] += 1
-        if do_gather:
-            torch.cuda.current_stream().wait_event(ev_free[i])  # the gather that read this buffer two steps ago is done
-        if peer is not None and use_rects:
-            eng.set_rect_output(peer.local_rects(i))
-        eng.render(hm_sets[(state["i"] - 1) % 3], None, out=rgb_buf[i], depth_out=depth)
-        eng.fots_markers(depth, theta, traj0, traj_len, out=markers)
-        if do_gather:
-            ev_done[i].record()
-            with torch.cuda.stream(side):
-                side.wait_event(ev_done[i])
-                if peer is not None and use_rects:
-                    peer.gather_rects(eng, i, side)
-                elif peer is not None:
-                    peer.gather(rgb_buf[i], i)
-                else:
-                    all_gather_obs(rgb_buf[i], gathered[i])
-                ev_free[i].record()
+    hm_host = synth.bench_batch(E, seed=rank, n_unique=64).pin_memory()
+    theta_host = torch.zeros(E).pin_memory()
+    hm_sets = sets_of(rank, hm_host)
+    hm = hm_sets[0]
+    run = StepRunner(args, eng, E, dev, world, rank, hm_sets)
 
     def barrier():
         torch.cuda.synchronize()
@@ -349,34 +520,73 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(runner, k_steps, w_steps):
+        for _ in range(w_steps):
+            runner.step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(k_steps):
+            runner.step()
+        runner.finish()
+        b.record()
+        barrier()
+        return a.elapsed_time(b)
+
     for _ in range(Wm):
-        step()
+        run.step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     c0 = eng.counters()["kernels_launched"]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        step()
-    if do_gather:
-        torch.cuda.current_stream().wait_stream(side)  # the last gathers finish inside the timed region
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms = timed(run, K, 0)
     launches = eng.counters()["kernels_launched"] - c0
+    gk = gather_kind_of(world, args, run)
+    gather_ok = None
+    if run.do_gather:
+        run.step()
+        run.finish()
+        barrier()
+        gather_ok = run.verify_gather(lambda r: sets_of(r))
+        barrier()
 
     # ---- dominant kernel alone (roofline.achieved): K launches of the fused Taxim kernel --------------------------
+    rgb, depth = run.rgb_buf[0], run.depth
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    eng.set_rect_output(None)
     for _ in range(K):
         eng.render(hm, None, out=rgb, depth_out=depth)
     e1.record()
     torch.cuda.synchronize()
     kern_ms = e0.elapsed_time(e1) / K
+
+    # ---- the same step on DENSE contacts (exact-zero skipping gains nothing there) and on the config-3 box presses ----
+    extras = {}
+    if not args.no_extras:
+        for name, pool, what in (
+            ("value_dense", synth.dense_batch(E, seed=4 + rank, n_unique=16),
+             "dense contacts: flat punches / large spheres / large tilted boxes covering 30-45 % of the frame, no env without contact"),
+            ("value_config3_box", synth.height_map_mm(synth.config3_box(64, seed=2 + rank, step=30)["depth_m"]).repeat((E + 63) // 64, 1, 1)[:E].contiguous(),
+             "config-3 depth maps: 4 x 6 x 2 mm box pressed 1 mm with an edge / a corner"),
+        ):
+            d = pool.to(dev)
+            sets = [d, d.roll(5, 0).contiguous(), d.roll(11, 0).contiguous()]
+            for _ in range(3):
+                eng.render(sets[0], None, out=rgb, depth_out=depth)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for j in range(K):
+                eng.render(sets[j % 3], None, out=rgb, depth_out=depth)
+                eng.fots_markers(depth, run.theta, run.traj0, run.traj_len, out=run.markers)
+            b.record()
+            torch.cuda.synchronize()
+            dms = a.elapsed_time(b) / K
+            extras[name] = {"value": E / (dms / 1e3), "unit": "frames/s per GPU", "ms_per_step": dms, "workload": what,
+                            "fp32_lane_ops_per_frame": fp32_lane_ops_per_frame(pool[:64])}
+            del d, sets
 
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) --------------
     rgb_host = torch.empty((E, H, W, 3)).pin_memory()
@@ -392,62 +602,141 @@ def main() -> None:
     e2e_s = (time.perf_counter() - t0) / Ke
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    del rgb_host
 
-    # ---- config 3 extra: the optional gel FEM substep, measured in the same run (not part of `value`) -------------
-    fem_extra = None
-    if not args.no_fem and world == 1:
-        fem_extra = fem_gpu(min(E, 4096), 3, dev, tactile=(eng, hm, rgb, depth))
+    # ---- config 3 (one GPU: FEM substep alone + full step) and config 4 (every N: E4 envs per GPU, gel FEM substep + FEM markers
+    #      + Taxim RGB + FOTS markers + observation gather; 8 x 1024 = the north star's 8192 envs) ------------------------
+    fem_extra, config4 = None, None
+    if not args.no_fem:
+        if world == 1:
+            fem_extra = fem_gpu(min(E, 4096), dev, tactile=(eng, rgb, depth))
+        E4 = min(args.config4_envs, E)
+        c3 = Config3(E4, dev, seed=2 + rank)
+        eng4 = TactileEngine(tables, max_envs=E4, device=dev, marker_rows=MARKER_ROWS, marker_cols=MARKER_COLS)
+        K4 = c3.last - c3.first  # 6 timed steps = press steps 24..29; the depth map of step s is the pose at its END (s + 1)
+        maps_of = lambda c: [c.height_maps(s + 1) for s in range(c.first, c.last)]  # noqa: E731
+        run4 = StepRunner(args, eng4, E4, dev, world, rank, maps_of(c3), fem_ctx=FemCtx(E4, dev, c3))
+        for _ in range(c3.first - K4):   # untimed run-in of the press (FEM only), then K4 full warm-up steps
+            run4.fem.step()
+        ms4 = timed(run4, K4, K4)
+        ok4 = None
+        if run4.do_gather:
+            ok4 = run4.verify_gather(lambda r: maps_of(Config3(E4, dev, seed=2 + r)))
+            f4 = torch.tensor([1.0 if ok4 else 0.0], device=dev)
+            dist.all_reduce(f4, op=dist.ReduceOp.MIN)
+            ok4 = bool(f4.item())
+        t4 = torch.tensor([ms4], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        ms4 = float(t4.item())
+        config4 = {"workload": f"config 4: {world} x {E4} envs, per step: gel FEM substep (config-3 box edge / corner press, steps "
+                               f"{c3.first}..{c3.last - 1} of 30) + FEM marker read-out + Taxim RGB 320x240 + FOTS {M}-marker motion"
+                               + (" + observation all-gather" if run4.do_gather else ""),
+                   "frames_per_s": world * E4 * K4 / (ms4 / 1e3), "ms_per_step": ms4 / K4, "global_envs": world * E4,
+                   "obs_gather": run4.gather_kind if run4.do_gather else "n/a", "gather_verified": ok4}
+
+    # ---- the reference's own CUDA path on this GPU, rank 0 of a 1-GPU run only ------------
+    reference_cuda = None
+    if not args.no_extras and world == 1:
+        try:
+            from baseline import ref_arm
+
+            if ref_arm.available():
+                del run
+                torch.cuda.empty_cache()
+                reference_cuda = {"what": "the UNMODIFIED reference TaximTorch.render_direct(with_shadow=False) + NHWC copy with device='cuda' "
+                                          "on this GPU, same depth maps, CUDA-event timed (RGB only, no markers)",
+                                  "batches": ref_arm.time_cuda(hm, (256, 1024, 4096))}
+        except Exception as exc:
+            reference_cuda = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
     # ---- max over ranks ------------------------------------------------------------------------------------------
-    t = torch.tensor([ms, kern_ms, e2e_s], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, kern_ms, e2e_s, 0.0 if gather_ok is False else 1.0], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, kern_ms, e2e_s = t.tolist()
+        dist.all_reduce(t[:3], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[3:], op=dist.ReduceOp.MIN)
+    ms, kern_ms, e2e_s, gok = t.tolist()
 
     if rank == 0:
         peak, peak_src = _peaks()
         frames = world * E * K
         value = frames / (ms / 1e3)
         ach = ALGO_BYTES_PER_FRAME * E / (kern_ms / 1e3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
-            traffic = tj.get("dram_bytes_per_frame", 0) * E if tj.get("dram_bytes_per_frame") else None
+            if tj.get("dram_bytes_per_frame"):
+                traffic = tj["dram_bytes_per_frame"] * E
+                traffic_src = tj.get("source", "profiles/traffic.json")
+        clocks = sampler.summary()
+        clk = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+        ops = fp32_lane_ops_per_frame(hm_host[:64])
+        lanes = ops * E / (kern_ms / 1e3) / (148 * clk)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": f"{E} envs/GPU x 320x240: indentation depth + Taxim RGB + FOTS {M}-marker motion, sphere indenters "
-                            f"(config-1 distribution, 10% no contact); the optional gel FEM substep (config 3) is reported separately under fem_gel_substep",
+                            f"(config-1 distribution, 10% no contact); dense contacts under value_dense, the gel FEM substep (config 3) under "
+                            f"fem_gel_substep, config 4 (FEM + RGB + markers + gather) under config4",
                 "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"dp{world} (contiguous env shards)",
                 "l2_policy": f"inputs larger than L2 ({E * FRAME_IN_BYTES / 1e6:.0f} MB in + {E * FRAME_OUT_BYTES / 1e6:.0f} MB out per step vs 126 MB L2); three input sets cycle, so every env sees a different depth map in consecutive steps",
-                "obs_gather": (gather_kind if do_gather else ("none (observations stay sharded)" if world > 1 else "n/a")),
+                "obs_gather": gk,
             },
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "kernel": "taxim_fused_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * E,
                          "peak_source": peak_src,
-                         "note": "FP32-FMA bound (exact separable pyramid, 266 MAC/px): see DESIGN.md section 5"},
+                         "fp32": {"what": "second ceiling (SURVEY 8d): FP32 lane-ops the exact separable pyramid needs for these frames "
+                                          "(zero-skipped regions excluded, colour stage not counted) per clock and SM",
+                                  "lane_ops_per_frame": ops, "dense_lane_ops_per_frame": 266 * H * W,
+                                  "achieved_lanes_per_clk_sm": lanes, "peak_lanes_per_clk_sm": 128, "measured_peak_lanes_per_clk_sm": 125,
+                                  "frac": lanes / 125, "sm_clock_mhz": clk / 1e6},
+                         "note": "HBM is the nominal bound; the exact pyramid (266 lane-ops/px) caps a dense evaluation at ~30% of it: see DESIGN.md section 4.1"},
             "e2e": {"value": world * E / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": E * (FRAME_IN_BYTES + 4),
-                    "d2h_bytes_per_step": E * (FRAME_OUT_BYTES + 4 + M * 16), "api": "tx_step_host (C ABI, pinned host buffers)", "host_binding": numa},
+                    "d2h_bytes_per_step": E * (FRAME_OUT_BYTES + 4 + M * 16), "api": "tx_step_host (C ABI, pinned host buffers)", "host_binding": numa,
+                    "pcie_gbs_d2h": E * (FRAME_OUT_BYTES + 4 + M * 16) / e2e_s / 1e9},
             "gpu_launches": launches,
-            "clocks": sampler.summary(),
+            "clocks": clocks,
         }
+        if world > 1:
+            line["gather_verified"] = (bool(gok) if gather_ok is not None else None)
+        line.update(extras)
+        if reference_cuda is not None:
+            line["reference_cuda"] = reference_cuda
         if not args.no_cpu_baseline:
             if ALL_CPUS:
                 os.sched_setaffinity(0, ALL_CPUS)  # the CPU baseline uses every host thread, not just the GPU's NUMA node
-            fps, cores, sample = cpu_port_fps(256)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            r = cpu_reference_fps(20, warmup=1)
+            if r is not None:
+                fps, cores, sample = r
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample}
+                pf, pc, ps = cpu_port_fps(256)
+                line["cpu_baseline"]["oracle_port"] = {"value": pf, "unit": "frames/s", "cores": pc, "kind": "port", "sample": ps}
+            else:
+                fps, cores, sample = cpu_port_fps(256)
+                line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         if fem_extra is not None:
             line["fem_gel_substep"] = fem_extra
             if not args.no_cpu_baseline:
-                g, cores, sample = fem_cpu_port(64)
+                g, cores, sample = fem_cpu_port()
                 line["fem_gel_substep"]["cpu_baseline"] = {"value": g, "unit": "gel-steps/s", "cores": cores, "kind": "port",
                                                            "sample": sample}
+        if config4 is not None:
+            line["config4"] = config4
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gather_kind_of(world, args, run) -> str:
+    if world == 1:
+        return "n/a"
+    if run is not None and run.do_gather:
+        return run.gather_kind
+    return "none (observations stay sharded)"
 
 
 if __name__ == "__main__":

@@ -27,13 +27,9 @@ namespace cg = cooperative_groups;
 
 namespace tx {
 
-__constant__ float c_taps[TX_MAX_BLURS][2][TX_MAX_TAPS];
-
-cudaError_t upload_taps(const float* host_taps /*[TX_MAX_BLURS][2][TX_MAX_TAPS]*/, cudaStream_t s)
-{
-    return cudaMemcpyToSymbolAsync(c_taps, host_taps, sizeof(float) * TX_MAX_BLURS * 2 * TX_MAX_TAPS, 0,
-                                   cudaMemcpyHostToDevice, s);
-}
+// The blur taps travel as a __grid_constant__ kernel parameter (constant bank 0, read as immediate-offset operands of the
+// FMAs exactly like a __constant__ array), so every handle -- every calibration -- brings its own and two handles of one
+// process can never see each other's taps.
 
 // ---- shared memory carve-up ---------------------------------------------------------------------------------
 constexpr int HB0_ROWS = 30; // even levels (radius 30, 8, 2, 2)
@@ -98,7 +94,7 @@ __device__ __forceinline__ void load_row12(const float* rp, int v0, bool interio
 }
 
 template <int L, int RAD, int LPR>
-__device__ __forceinline__ void hpass_rows(float* plane, float* hb_remote, int warp, int lane, unsigned q, int la, int lb, int vbase)
+__device__ __forceinline__ void hpass_rows(const TaximTaps& c_taps, float* plane, float* hb_remote, int warp, int lane, unsigned q, int la, int lb, int vbase)
 {
     constexpr int D = (RAD + 11) / 12;
     constexpr int RPW = 32 / LPR; // rows per warp
@@ -135,7 +131,7 @@ __device__ __forceinline__ void hpass_rows(float* plane, float* hb_remote, int w
 #pragma unroll
                     for (int m = 0; m < 12; ++m) {
                         const int kk = 12 * d + j - m;
-                        if (kk >= -RAD && kk <= RAD) acc[m] = __fmaf_rn(c_taps[L][0][kk + RAD], y, acc[m]);
+                        if (kk >= -RAD && kk <= RAD) acc[m] = __fmaf_rn(c_taps.t[L][0][kk + RAD], y, acc[m]);
                     }
                 }
             }
@@ -159,7 +155,7 @@ __device__ __forceinline__ void hpass_rows(float* plane, float* hb_remote, int w
 
 // c0 / c1: non-zero columns of the level's input (image coordinates)
 template <int L, int RAD>
-__device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, int warp, int lane, unsigned q, int la, int lb,
+__device__ __forceinline__ void hpass(const TaximTaps& c_taps, float* plane, float* hb_remote, int tid, int warp, int lane, unsigned q, int la, int lb,
                                       int c0, int c1)
 {
     // zero halo rows for the skipped rows of the push range (the halo buffers are reused across levels)
@@ -173,9 +169,9 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, i
     // reads the columns [c0 - RAD, c1 + RAD], which the window covers.
     const bool narrow = c0 > RAD && c1 < IMG_W - 1 - RAD && (c1 - c0 + 1) + 2 * RAD + 8 <= 192;
     if (narrow)
-        hpass_rows<L, RAD, 16>(plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
+        hpass_rows<L, RAD, 16>(c_taps, plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
     else
-        hpass_rows<L, RAD, 32>(plane, hb_remote, warp, lane, q, la, lb, -32);
+        hpass_rows<L, RAD, 32>(c_taps, plane, hb_remote, warp, lane, q, la, lb, -32);
 }
 
 // ---- vertical pass: thread per column, sliding register window, in place --------------------------------------
@@ -183,7 +179,7 @@ __device__ __forceinline__ void hpass(float* plane, float* hb_remote, int tid, i
 // q = 1: t = 119 - local row, marching up). Positions < 0 are the reflected rows, positions >= 120 come from
 // the halo buffer (rows of the peer CTA by distance from the boundary).
 template <int L, int RAD, int R>
-__device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, unsigned q, int ca, int ncols, int ta, int tb)
+__device__ __forceinline__ void vpass(const TaximTaps& c_taps, float* plane, const float* hb, int tid, unsigned q, int ca, int ncols, int ta, int tb)
 {
     // only columns [ca, ca + ncols) and positions [ta, tb] can become non-zero; everything else stays exactly +0.0f
     if (tid >= ncols || tb < ta) return;
@@ -206,12 +202,12 @@ __device__ __forceinline__ void vpass(float* plane, const float* hb, int tid, un
         float acc[R];
         // centre-outward, symmetric pair summed first: independent of the marching direction
 #pragma unroll
-        for (int m = 0; m < R; ++m) acc[m] = __fmul_rn(c_taps[L][1][RAD], win[m + RAD]);
+        for (int m = 0; m < R; ++m) acc[m] = __fmul_rn(c_taps.t[L][1][RAD], win[m + RAD]);
 #pragma unroll
         for (int d = 1; d <= RAD; ++d) {
 #pragma unroll
             for (int m = 0; m < R; ++m)
-                acc[m] = __fmaf_rn(c_taps[L][1][RAD + d], __fadd_rn(win[m + RAD - d], win[m + RAD + d]), acc[m]);
+                acc[m] = __fmaf_rn(c_taps.t[L][1][RAD + d], __fadd_rn(win[m + RAD - d], win[m + RAD + d]), acc[m]);
         }
         float* po = p0 + (b * R) * S;
 #pragma unroll
@@ -307,13 +303,13 @@ struct Region {
 };
 
 template <int L, int RAD, int R, bool FINAL>
-__device__ __forceinline__ void blur_level(float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
+__device__ __forceinline__ void blur_level(const TaximTaps& c_taps, float* plane, float* hb_local, float* hb_remote, const unsigned* maskbits,
                                            const unsigned short* mlist, int nlist, const float* hm_half, const float* gel_half,
                                            float m, float press, int tid, int warp, int lane, unsigned q, Region& rg,
                                            cg::cluster_group& cluster, long long* tk, float depth_clip, FlatCopy& fc)
 {
     const int base = (int)q * HALF_H;
-    hpass<L, RAD>(plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1), rg.c0, rg.c1);
+    hpass<L, RAD>(c_taps, plane, hb_remote, tid, warp, lane, q, max(rg.r0 - base, 0), min(rg.r1 - base, HALF_H - 1), rg.c0, rg.c1);
     TX_TICK(4 + 4 * L + 0);
     cluster.sync(); // rows + pushed halo rows visible in both CTAs
     TX_TICK(4 + 4 * L + 1);
@@ -323,7 +319,7 @@ __device__ __forceinline__ void blur_level(float* plane, float* hb_local, float*
         // position t counts from the image edge of this half: q = 0: t = image row; q = 1: t = 239 - image row
         const int ta = q == 0 ? ro0 : max(IMG_H - 1 - ro1, 0);
         const int tb = q == 0 ? min(ro1, HALF_H - 1) : min(IMG_H - 1 - ro0, HALF_H - 1);
-        vpass<L, RAD, R>(plane, hb_local, tid, q, ca, cb - ca + 1, ta, tb);
+        vpass<L, RAD, R>(c_taps, plane, hb_local, tid, q, ca, cb - ca + 1, ta, tb);
         // the warps without a column copy this level's slice of the flat RGB meanwhile
         const int nv = tb < ta ? 0 : ((cb - ca + 1 + 31) & ~31);
         if (nv < NTHREADS) {
@@ -371,7 +367,7 @@ cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s)
 // MODE bit 0: the input is the camera DEPTH image in metres (inf = no hit); bit 1: the input has the camera resolution
 // [Hc][Wc] != 240 x 320 and is resized (bilinear, torchvision F.resize semantics) in the load stage.
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_fused_kernel(const TaximArgs p)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_fused_kernel(const __grid_constant__ TaximArgs p, const __grid_constant__ TaximTaps c_taps)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float* plane = reinterpret_cast<float*>(smem + SM_PLANE);
@@ -616,13 +612,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     if (active) {
-        blur_level<0, 30, 12, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<1, 16, 24, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<2, 8, 24, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<3, 4, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<4, 2, 30, false>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<5, 1, 30, false>(plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
-        blur_level<6, 2, 30, true>(plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<0, 30, 12, false>(c_taps, plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<1, 16, 24, false>(c_taps, plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<2, 8, 24, false>(c_taps, plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<3, 4, 30, false>(c_taps, plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<4, 2, 30, false>(c_taps, plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<5, 1, 30, false>(c_taps, plane, hb1, hb1_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
+        blur_level<6, 2, 30, true>(c_taps, plane, hb0, hb0_remote, maskbits, mlist, nlist, hm_half, gel_half, m, press, tid, warp, lane, q, rg, cluster, tk, depth_clip, fc);
     }
 
     // ---- 1-row halo for the central differences, optional outputs ---------------------------------------------
@@ -773,7 +769,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     TX_TICK(33);
 }
 
-cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
+cudaError_t launch_taxim(const TaximArgs& a, const TaximTaps& taps, int N, cudaStream_t s)
 {
     static bool attr_set_dev[64] = {}; // the attribute belongs to the (function, device) pair: one process may drive several GPUs
     int dev = 0;
@@ -790,10 +786,10 @@ cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s)
     const int mode = (a.input_is_depth ? 1 : 0) | (a.Hc > 0 ? 2 : 0);
     const dim3 grid(2 * N), block(NTHREADS);
     switch (mode) {
-    case 0: taxim_fused_kernel<0><<<grid, block, SM_TOTAL, s>>>(a); break;
-    case 1: taxim_fused_kernel<1><<<grid, block, SM_TOTAL, s>>>(a); break;
-    case 2: taxim_fused_kernel<2><<<grid, block, SM_TOTAL, s>>>(a); break;
-    default: taxim_fused_kernel<3><<<grid, block, SM_TOTAL, s>>>(a); break;
+    case 0: taxim_fused_kernel<0><<<grid, block, SM_TOTAL, s>>>(a, taps); break;
+    case 1: taxim_fused_kernel<1><<<grid, block, SM_TOTAL, s>>>(a, taps); break;
+    case 2: taxim_fused_kernel<2><<<grid, block, SM_TOTAL, s>>>(a, taps); break;
+    default: taxim_fused_kernel<3><<<grid, block, SM_TOTAL, s>>>(a, taps); break;
     }
     return cudaGetLastError();
 }

@@ -61,6 +61,7 @@ struct tx_handle {
     int sh_chunk = 0;
     bool generic = false;  // shape / radii other than the specialised 240 x 320 kernel: taxim_generic_kernel
     float* d_taps = nullptr; // generic: [n_blurs][2][TX_MAX_TAPS]
+    TaximTaps taps{};        // specialised kernel: this handle's taps, passed as a kernel parameter with every launch
     int n_sm = 148;
 };
 
@@ -151,7 +152,7 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
         }                                                                                                             \
     } while (0)
     TX_CUDA_C(cudaSetDevice(device));
-    // taps -> __constant__ memory, [blur][0 = x, 1 = y][tap]
+    // taps, [blur][0 = x, 1 = y][tap]: per handle (global memory for the generic kernel, a kernel parameter otherwise)
     {
         std::vector<float> t((size_t)TX_MAX_BLURS * 2 * TX_MAX_TAPS, 0.0f);
         for (int l = 0; l < cfg->n_blurs; ++l)
@@ -163,8 +164,9 @@ extern "C" int tx_create(const tx_config* cfg, int device, void* cuda_stream, tx
             TX_CUDA_C(cudaMalloc(&h->d_taps, t.size() * sizeof(float)));
             TX_CUDA_C(cudaMemcpy(h->d_taps, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
         } else {
-            TX_CUDA_C(upload_taps(t.data(), h->stream));
-            TX_CUDA_C(cudaStreamSynchronize(h->stream));
+            for (int l = 0; l < TX_FUSED_BLURS; ++l)
+                for (int ax = 0; ax < 2; ++ax)
+                    memcpy(h->taps.t[l][ax], &t[((size_t)l * 2 + ax) * TX_MAX_TAPS], sizeof(float) * TX_MAX_TAPS);
         }
     }
     if (M > 0) {
@@ -299,7 +301,8 @@ extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N,
 }
 
 static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
-                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres = 0);
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres = 0,
+                       int env0 = 0);
 
 // first tap + two weights per output index of torch's antialiased bilinear filter for up-sampling (support 1): float32
 // arithmetic like aten (UpSampleKernel.cpp, _compute_indices_min_size_weights_aa); returns false if more than two taps.
@@ -383,11 +386,13 @@ extern "C" int tx_render_depth(tx_handle* h, const float* depth_m, float clip_ma
 }
 
 static int render_impl(tx_handle* h, const float* height_mm, const float* press_mm, int N, float* rgb, float* depth_out,
-                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres)
+                       float* deformed, uint8_t* mask, int input_is_depth, float clip_max_m, float* hm_out, int lowres, int env0)
 {
+    // env0: the frames are envs [env0, env0 + N) of a batch rendered in chunks (tx_render_shadow, tx_step_host): the per-env
+    // records of the FOTS model and the gather rectangles land at their batch position, so the whole batch stays valid
     if (!h || !height_mm || !rgb || N < 0) return fail(h, TX_ERR_INVALID_ARG, "tx_render: bad argument");
     if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
-    if (N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
+    if (N > h->cfg.max_envs || env0 < 0 || env0 + N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
     if (!h->generic &&
         ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u))))
         return fail(h, TX_ERR_INVALID_ARG, "tx_render: device buffers must be 16-byte aligned");
@@ -428,19 +433,19 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     a.deformed_out = deformed;
     a.mask_out = mask;
     if (h->M > 0) {
-        a.aux_sums = h->d_aux_sums;
-        a.aux_bmax = h->d_aux_bmax;
-        a.aux_b = h->d_aux_b;
-        a.aux_m = h->d_aux_m;
+        a.aux_sums = h->d_aux_sums + (size_t)env0 * 8;
+        a.aux_bmax = h->d_aux_bmax + (size_t)env0 * 2;
+        a.aux_b = h->d_aux_b + (size_t)env0 * h->M;
+        a.aux_m = h->d_aux_m + (size_t)env0 * h->M;
         a.mk_x = h->d_mx;
         a.mk_y = h->d_my;
         a.M = h->M;
     }
     a.ticks = h->d_ticks;
     a.dbg = h->dbg;
-    a.rect_out = h->d_rect;
-    TX_CUDA(h, launch_taxim(a, N, h->stream));
-    h->aux_valid_n = h->M > 0 ? N : 0;
+    a.rect_out = h->d_rect ? h->d_rect + (size_t)env0 * 8 : nullptr;
+    TX_CUDA(h, launch_taxim(a, h->taps, N, h->stream));
+    h->aux_valid_n = h->M > 0 ? env0 + N : 0;
     h->ctr.render_calls++;
     h->ctr.frames_rendered += (uint64_t)N;
     h->ctr.kernels_launched++;
@@ -509,7 +514,7 @@ extern "C" int tx_render_shadow(tx_handle* h, const float* height_mm, const floa
     for (int n0 = 0; n0 < N; n0 += h->sh_chunk) {
         const int n = N - n0 < h->sh_chunk ? N - n0 : h->sh_chunk;
         int rc = render_impl(h, height_mm + HWp * n0, press_mm ? press_mm + n0 : nullptr, n, rgb + HWp * 3 * n0,
-                             depth_out ? depth_out + n0 : nullptr, h->d_sh_def, h->d_sh_mask, 0, 0.0f, nullptr);
+                             depth_out ? depth_out + n0 : nullptr, h->d_sh_def, h->d_sh_mask, 0, 0.0f, nullptr, 0, n0);
         if (rc != TX_OK) return rc;
         ShadowArgs a{};
         a.deformed = h->d_sh_def; a.mask = h->d_sh_mask; a.gel = c.gel; a.poly = c.poly; a.shadow = h->d_sh_img;
@@ -525,7 +530,6 @@ extern "C" int tx_render_shadow(tx_handle* h, const float* height_mm, const floa
                                  h->d_sh_taps + 3 * TX_MAX_TAPS, h->cfg.ksy[lf], h->stream));
         h->ctr.kernels_launched += 7;
     }
-    if (N > h->sh_chunk) h->aux_valid_n = 0; // the FOTS inputs recorded by the fused kernel only cover the last chunk
     return TX_OK;
 }
 
@@ -682,6 +686,9 @@ extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const flo
         h->ev_in.push_back(a);
         h->ev_done.push_back(b);
     }
+    int* const saved_rect = h->d_rect; // the gather rectangles belong to device-resident batches, not to the chunked host path
+    h->d_rect = nullptr;
+    struct RestoreRect { tx_handle* h; int* r; ~RestoreRect() { h->d_rect = r; } } restore_rect{h, saved_rect};
     // the copy streams must not run ahead of work already queued on the caller's stream
     TX_CUDA(h, cudaEventRecord(h->ev_done[0], h->stream));
     TX_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done[0], 0));

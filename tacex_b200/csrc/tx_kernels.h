@@ -52,6 +52,12 @@ struct TaximArgs {
     long long* ticks; // optional [2N][40] phase clock stamps (profiling builds of the host call only)
 };
 
+// blur taps of the specialised 240 x 320 kernel: [level][0 = x, 1 = y][tap], a kernel parameter (per handle)
+constexpr int TX_FUSED_BLURS = 7;
+struct TaximTaps {
+    float t[TX_FUSED_BLURS][2][TX_MAX_TAPS];
+};
+
 // arbitrary-resolution variant (taxim_generic_kernel.cu): one CTA per frame, two planes + a byte mask in shared memory
 constexpr int TXG_MAX_PIXELS = 160 * 120;
 struct TaximGenericArgs {
@@ -173,10 +179,9 @@ int fem_threads();
 cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
 
-cudaError_t upload_taps(const float* host_taps, cudaStream_t s);
 int taxim_smem_bytes();
 int taxim_lowres_max_pixels();
-cudaError_t launch_taxim(const TaximArgs& a, int N, cudaStream_t s);
+cudaError_t launch_taxim(const TaximArgs& a, const TaximTaps& taps, int N, cudaStream_t s);
 cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);
 cudaError_t launch_fots(const FotsArgs& a, int N, cudaStream_t s);

@@ -156,11 +156,9 @@ class B200TaximSimulator(GelSightSimulator):
             raise RuntimeError("B200TaximSimulator runs on a CUDA (sm_100a) device only; there is no CPU path")
         self._num_envs = self.sensor._num_envs
         W, H = self.cfg.tactile_img_res
-        if self.cfg.with_shadow and ((H, W) != (240, 320) or os.environ.get("TACEX_B200_UNVALIDATED_SHADOW") != "1"):
-            # every GelSight Mini preset disables the shadows. The device version of the shadow branch (tx_render_shadow) exists
-            # but has not been validated on a GPU yet: it is strictly opt-in.
-            raise NotImplementedError("with_shadow=True: the shadow kernels are not validated yet; set "
-                                      "TACEX_B200_UNVALIDATED_SHADOW=1 to use them at 320x240 anyway")
+        if self.cfg.with_shadow and (H, W) != (240, 320):
+            # the shadow branch (tx_render_shadow, bit-exact vs the canonical restatement on a B200) belongs to the 240 x 320 kernel
+            raise NotImplementedError("with_shadow=True is implemented for tactile_img_res=(320, 240) only")
         self.img_res = self.cfg.tactile_img_res
         tables = _load_tables(self.cfg.calib_folder_path, (H, W))
         mcfg = getattr(self.sensor.cfg, "marker_motion_sim_cfg", None)

@@ -194,3 +194,81 @@ def lowres_batch(n_envs: int, H: int, W: int, seed: int = 3) -> torch.Tensor:
         for i in range(n_envs)
     ])
     return height_map_mm(d)
+
+
+def box_depth_map(half_m, cx_m: float, cy_m: float, R, press_m: float, H: int = 240, W: int = 320,
+                  pitch: float = PIXEL_PITCH_M_320) -> torch.Tensor:
+    """Camera depth image [m] of a rigid BOX (half extents ``half_m``, rotation ``R`` 3x3, world z up towards the camera...
+    the camera looks at the box's lower surface) whose lowest point is pressed ``press_m`` into the gel: per pixel the entry
+    point of the vertical ray into the rotated box (slab test), relative to the box's lowest point."""
+    X, Y = _grid(H, W, pitch)
+    R = torch.as_tensor(R, dtype=torch.float64)
+    h = torch.as_tensor(half_m, dtype=torch.float64)
+    # ray o + t * ez in the box frame: o' = R^T (o - c), d' = R^T ez = third row of R
+    ox, oy = X - cx_m, Y - cy_m
+    t_in = torch.full_like(X, -float("inf"))
+    t_out = torch.full_like(X, float("inf"))
+    for k in range(3):
+        o_k = R[0, k] * ox + R[1, k] * oy  # (R^T o)_k with o_z = 0
+        d_k = R[2, k]
+        if abs(float(d_k)) < 1e-12:
+            inside = o_k.abs() <= h[k]
+            t_in = torch.where(inside, t_in, torch.full_like(X, float("inf")))
+            continue
+        ta, tb = (-h[k] - o_k) / d_k, (h[k] - o_k) / d_k
+        t_in = torch.maximum(t_in, torch.minimum(ta, tb))
+        t_out = torch.minimum(t_out, torch.maximum(ta, tb))
+    hit = t_in <= t_out
+    low = -float((R[2, :].abs() * h).sum())  # z of the lowest corner relative to the centre
+    z = torch.where(hit, t_in - low, torch.full_like(X, float("inf")))
+    return torch.clamp(GEL_SURFACE_M - press_m + z, max=CLIP_MAX_M).to(torch.float32)
+
+
+def _rot(yaw: float, tilt_y: float = 0.0, tilt_x: float = 0.0) -> torch.Tensor:
+    c, s = math.cos(yaw), math.sin(yaw)
+    Rz = torch.tensor([[c, -s, 0], [s, c, 0], [0, 0, 1.0]], dtype=torch.float64)
+    c, s = math.cos(tilt_y), math.sin(tilt_y)
+    Ry = torch.tensor([[c, 0, s], [0, 1, 0], [-s, 0, c]], dtype=torch.float64)
+    c, s = math.cos(tilt_x), math.sin(tilt_x)
+    Rx = torch.tensor([[1, 0, 0], [0, c, -s], [0, s, c]], dtype=torch.float64)
+    return Rz @ Ry @ Rx
+
+
+def config3_box(n_envs: int, seed: int = 2, step: int = 30, H: int = 240, W: int = 320) -> dict:
+    """Depth maps of BASELINE config 3: a rigid 4 x 6 x 2 mm box pressed with an EDGE (even envs) or a CORNER (odd envs) into the
+    gel, 0 -> 1 mm over 30 steps (``step`` selects the sample), seed 2 for the pose jitter."""
+    g = torch.Generator().manual_seed(seed)
+    r = lambda: torch.rand(n_envs, generator=g, dtype=torch.float64)  # noqa: E731
+    cx, cy = (r() * 2 - 1) * 6e-3, (r() * 2 - 1) * 4e-3
+    yaw = (r() * 2 - 1) * math.pi
+    jit = (r() * 2 - 1) * math.radians(5.0)
+    half = (2e-3, 3e-3, 1e-3)
+    d, Rs = [], []
+    for i in range(n_envs):
+        R = _rot(yaw[i].item(), math.radians(20.0) + jit[i].item(), 0.0 if i % 2 == 0 else math.radians(15.0))
+        Rs.append(R)
+        d.append(box_depth_map(half, cx[i].item(), cy[i].item(), R, 1e-3 * step / 30, H, W))
+    return {"depth_m": torch.stack(d), "R": torch.stack(Rs), "cx": cx, "cy": cy, "half": half}
+
+
+def dense_batch(n_envs: int, seed: int = 4, H: int = 240, W: int = 320, n_unique: int = 16) -> torch.Tensor:
+    """Height maps [mm] of DENSE contacts (the unfavourable case for the kernel's exact-zero skipping): flat punches covering
+    about a third of the frame (10 x 8 mm boxes, any yaw), large spheres (r = 12 mm, 1.2-1.5 mm press), and config-3 edge /
+    corner presses of a large box; no env without contact. ``n_unique`` maps tiled to ``n_envs``."""
+    g = torch.Generator().manual_seed(seed)
+    k = min(n_unique, n_envs)
+    u = torch.rand((k, 5), generator=g, dtype=torch.float64)
+    d = []
+    for i in range(k):
+        cx, cy = (u[i, 0].item() * 2 - 1) * 2e-3, (u[i, 1].item() * 2 - 1) * 1.5e-3
+        yaw = (u[i, 2].item() * 2 - 1) * math.pi
+        p = (1.2 + 0.3 * u[i, 3].item()) * 1e-3
+        if i % 3 == 0:
+            d.append(box_depth_map((5e-3, 4e-3, 1e-3), cx, cy, _rot(yaw), p, H, W))
+        elif i % 3 == 1:
+            d.append(depth_map(0, 12e-3, cx, cy, 0.0, p, H, W))
+        else:
+            d.append(box_depth_map((6e-3, 5e-3, 2e-3), cx, cy, _rot(yaw, math.radians(4.0), math.radians(3.0 * (i % 2))), p, H, W))
+    pool = height_map_mm(torch.stack(d))
+    reps = (n_envs + k - 1) // k
+    return pool.repeat(reps, 1, 1)[:n_envs].contiguous()

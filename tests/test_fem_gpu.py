@@ -135,3 +135,77 @@ def test_marker_readout_projection():
     assert np.array_equal(mk[0, 0], mk[0, 1]) and np.array_equal(mk[2], mk[0])
     du = mk[1, 1, :, 0] - mk[1, 0, :, 0]
     assert np.allclose(du, 340 * 1e-3 / pc[:, 2], atol=1e-3)  # 1 mm at 24 mm -> ~14 px
+
+
+def _mixed_press_batch(N, seed=7):
+    """Mixed contacts for the persistent-CTA test: spheres of several radii, boxes with a yaw, boxes tilted onto an EDGE and
+    onto a CORNER, random in-plane offsets up to the pad's edge; steps 0..5 press 0.6 mm down, then a sideways drag (friction)."""
+    rng = np.random.default_rng(seed)
+    kind = rng.integers(0, 4, N)  # 0 sphere, 1 yawed box, 2 box on an edge, 3 box on a corner
+    offs = rng.uniform(-1, 1, (N, 2)) * np.array([7e-3, 9e-3])
+    yaw = rng.uniform(-np.pi, np.pi, N)
+    rad = rng.uniform(2e-3, 4e-3, N)
+    Rs, halfs, low, types = [], [], [], []
+    for i in range(N):
+        c, s = np.cos(yaw[i]), np.sin(yaw[i])
+        Rz = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+        if kind[i] == 0:
+            R, h, lo, t = np.eye(3), (rad[i], 0.0, 0.0), rad[i], 0
+        else:
+            h, t = (2e-3, 3e-3, 1e-3), 1
+            if kind[i] == 1:
+                R = Rz
+            elif kind[i] == 2:  # rotate about the box's y axis by 45 deg: an edge points down
+                a = np.pi / 4
+                R = Rz @ np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+            else:  # corner down
+                a, b = np.pi / 5, np.pi / 6
+                Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+                Rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+                R = Rz @ Ry @ Rx
+            # lowest point of the rotated box below its centre
+            lo = float(np.abs(R[2, :] * np.asarray(h)).sum())
+        Rs.append(R); halfs.append(h); low.append(lo); types.append(t)
+    return np.asarray(types), offs, np.asarray(Rs), np.asarray(halfs), np.asarray(low)
+
+
+def test_persistent_cta_loop_600_gels_mixed_contacts_matches_cpu_restatement():
+    """The kernel is persistent (grid = #SMs, every CTA walks ~4 gels here, ~28 at the benchmark's 4096): shared-memory operator
+    reuse, per-CTA scratch reuse and the indenter / statistics state across CONSECUTIVE gels of one CTA are compared with the
+    float64 CPU restatement for 600 gels with mixed sphere / yawed-box / edge / corner presses and a friction drag, 8 steps."""
+    from tacex_b200 import fem
+
+    N = 600
+    m, eng, cf, fc = _setup((10, 12, 3), 1e-3, N)
+    types, offs, Rs, halfs, low = _mixed_press_batch(N)
+    top = 4.5e-3
+
+    def ctr(s):
+        z = top + low + 4e-4 - 6e-4 * min(s, 6) / 6
+        dx = 1e-4 * max(s - 6, 0)
+        return np.stack([offs[:, 0] + dx, offs[:, 1], z], 1)
+
+    x, v, xp = eng.new_state(N)
+    aim = eng.rest_aim(N)
+    xc, vc, xpc = cf.new_state(N)
+    aimc = cf.X[cf.attach][None].repeat(N, 0)
+    mk = lambda s: [fc.make_indenter(int(types[i]), ctr(s)[i], halfs[i], Rs[i]) for i in range(N)]  # noqa: E731
+    worst = 0.0
+    n_mismatch = 0
+    for s in range(8):
+        a = fem.indenter_array(types, ctr(s), halfs, Rs)
+        b = fem.indenter_array(types, ctr(s + 1), halfs, Rs)
+        st = eng.step(x, v, xp, aim, a, b)
+        cst = cf.step(xc, vc, xpc, aimc, mk(s), mk(s + 1))
+        torch.cuda.synchronize()
+        d = np.abs(x.cpu().numpy() - xc).reshape(N, -1).max(1)
+        worst = max(worst, float(d.max()))
+        gs = eng.decode_stats(st)
+        assert d.max() <= 1e-5, f"step {s}: gel {int(d.argmax())} differs by {d.max():.3e} m"
+        n_mismatch += sum(int(gs[i]["newton_iters"] != cst[i]["newton_iters"]) for i in range(N))
+        assert all(q["min_dist"] > 0 and np.isfinite(q["energy"]) for q in gs)
+    print(f"600 gels x 8 steps: max |x_gpu - x_cpu| = {worst:.3e} m, Newton-count mismatches {n_mismatch} of {8 * N}")
+    assert n_mismatch == 0
+    # the contacts really happened: most gels deformed by more than 0.1 mm
+    moved = (x - eng.X[None]).abs().amax((1, 2))
+    assert float((moved > 1e-4).float().mean()) > 0.8

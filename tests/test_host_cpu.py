@@ -234,7 +234,8 @@ def test_reference_arm_under_torchrun_prints_one_json_line_from_rank_0():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["n_gpus"] == 2
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    staged = (root / "baseline" / "_ref" / "gpu_taxim" / "sim" / "taxim_torch.py").exists()
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

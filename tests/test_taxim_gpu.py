@@ -322,3 +322,110 @@ def test_step_host_end_to_end(tables, canon_taxim, inputs):
     pc = canon_taxim.indentation_depth(hm.numpy())
     o = canon_taxim.render(hm.numpy(), pc)
     assert np.array_equal(dep.numpy(), pc) and np.array_equal(rgb.numpy(), o["rgb"])
+
+
+def test_extreme_contacts_bitwise_vs_canonical(tables, canon_taxim):
+    """The fused kernel on the extreme contacts of tests/test_refbox_cpu.py::EDGE_CASES (a third of the frame in contact, image
+    corner, 0.01 mm and 4.4 mm presses, a few pixels of contact)."""
+    from tacex_b200 import synth
+    from tacex_b200.engine import TactileEngine
+    from test_refbox_cpu import EDGE_CASES
+
+    hm = synth.height_map_mm(torch.stack([synth.depth_map(*v) for v in EDGE_CASES.values()]))
+    n = hm.shape[0]
+    eng = TactileEngine(tables, max_envs=n, marker_rows=9, marker_cols=11)
+    depth = torch.empty(n, device="cuda")
+    deformed = torch.empty((n, H, W), device="cuda")
+    mask = torch.empty((n, H, W), device="cuda", dtype=torch.uint8)
+    rgb = eng.render(hm.cuda(), None, depth_out=depth, deformed_out=deformed, mask_out=mask)
+    torch.cuda.synchronize()
+    press = canon_taxim.indentation_depth(hm.numpy())
+    o = canon_taxim.render(hm.numpy(), press)
+    assert np.array_equal(depth.cpu().numpy(), press)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), o["mask"].astype(bool))
+    assert np.array_equal(deformed.cpu().numpy(), o["deformed"])
+    assert np.array_equal(rgb.cpu().numpy(), o["rgb"])
+
+
+def _render_all(eng, hm, chunk=None):
+    n = hm.shape[0]
+    hmd = hm.cuda()
+    rgb = torch.empty((n, H, W, 3), device="cuda")
+    dg = torch.empty((n, H, W), device="cuda")
+    mk = torch.empty((n, H, W), device="cuda", dtype=torch.uint8)
+    dep = torch.empty(n, device="cuda")
+    eng.render(hmd, None, out=rgb, depth_out=dep, deformed_out=dg, mask_out=mk)
+    torch.cuda.synchronize()
+    return rgb, dg, mk, dep
+
+
+def test_config1_256_envs_bitwise_vs_canonical_oracle(tables, canon_taxim):
+    """BASELINE config 1 at its full size (256 envs, seed 0): every frame array_equal to the canonical oracle."""
+    from tacex_b200 import synth
+    from tacex_b200.engine import TactileEngine
+
+    hm = synth.height_map_mm(synth.config1(256, seed=0)["depth_m"])
+    eng = TactileEngine(tables, max_envs=256)
+    rgb, dg, mk, dep = _render_all(eng, hm)
+    pc = canon_taxim.indentation_depth(hm.numpy())
+    o = canon_taxim.render(hm.numpy(), pc)
+    assert np.array_equal(dep.cpu().numpy(), pc)
+    assert np.array_equal(mk.cpu().numpy(), o["mask"])
+    assert np.array_equal(dg.cpu().numpy(), o["deformed"])
+    assert np.array_equal(rgb.cpu().numpy(), o["rgb"])
+
+
+def test_config2_1024_envs_bitwise_vs_canonical_oracle(tables, canon_taxim):
+    """BASELINE config 2 at its full size (1024 envs, seed 1, all four indenter kinds, moving yaw): RGB + FOTS markers of both
+    trajectory samples against the canonical oracle (RGB / deformed gel / mask bit-exact, markers <= 2e-4 px)."""
+    from oracle import canon
+    from tacex_b200 import synth
+    from tacex_b200.engine import TactileEngine
+
+    n = 1024
+    c2 = synth.config2(n, seed=1)
+    assert set(c2["kind"].tolist()) == {0, 1, 2, 3}
+    eng = TactileEngine(tables, max_envs=n, marker_rows=7, marker_cols=9)
+    cf = canon.CanonFots(H, W, 7, 9, 15, 26)
+    traj0 = torch.zeros((n, 4), device="cuda")
+    tl = torch.zeros(n, device="cuda", dtype=torch.int32)
+    canon.use_all_threads()
+    for key, th in (("depth_m0", "theta0"), ("depth_m", "theta")):
+        hm = synth.height_map_mm(c2[key])
+        rgb, dg, mk, dep = _render_all(eng, hm)
+        mkr = eng.fots_markers(dep, c2[th].cuda(), traj0, tl)
+        torch.cuda.synchronize()
+        pc = canon_taxim.indentation_depth(hm.numpy())
+        o = canon_taxim.render(hm.numpy(), pc)
+        assert np.array_equal(dep.cpu().numpy(), pc)
+        assert np.array_equal(mk.cpu().numpy(), o["mask"])
+        assert np.array_equal(dg.cpu().numpy(), o["deformed"])
+        assert np.array_equal(rgb.cpu().numpy(), o["rgb"])
+        mc = cf.step(o["deformed"], o["mask"], pc, c2[th].numpy())
+        assert np.abs(mkr.cpu().numpy() - mc).max() <= 2e-4
+
+
+def test_4096_env_launch_strided_sample_vs_canonical_oracle(tables, canon_taxim):
+    """One launch at the benchmark's batch size (4096 envs, the bench's own input pool incl. dense box contacts): a strided
+    sample of 64 frames spread over the whole grid is array_equal to the canonical oracle, and every frame equals the frame
+    of the same depth map elsewhere in the batch (batch-position invariance over all 4096)."""
+    from tacex_b200 import synth
+    from tacex_b200.engine import TactileEngine
+
+    n = 4096
+    pool = torch.cat([synth.bench_batch(48, seed=0, n_unique=48), synth.dense_batch(16, seed=4)])
+    hm = pool.repeat(n // 64, 1, 1).contiguous()
+    eng = TactileEngine(tables, max_envs=n)
+    rgb = torch.empty((n, H, W, 3), device="cuda")
+    dep = torch.empty(n, device="cuda")
+    eng.render(hm.cuda(), None, out=rgb, depth_out=dep)
+    torch.cuda.synchronize()
+    idx = torch.arange(0, n, 65)[:64]  # 65 = 64 + 1: walks through the pool AND through the grid
+    sub = hm[idx]
+    pc = canon_taxim.indentation_depth(sub.numpy())
+    o = canon_taxim.render(sub.numpy(), pc, want=("rgb",))
+    assert np.array_equal(dep[idx.cuda()].cpu().numpy(), pc)
+    assert np.array_equal(rgb[idx.cuda()].cpu().numpy(), o["rgb"])
+    first = rgb[:64]
+    for r in range(1, n // 64):
+        assert torch.equal(rgb[64 * r: 64 * (r + 1)], first), f"replica {r} differs"
