@@ -11,7 +11,8 @@ FLAGS = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 t = TaximTables.load(ROOT + "/tests/golden/gsmini_tables_320x240.npz")
 eng = TactileEngine(t, max_envs=E)
 eng.set_debug_flags(FLAGS)
-hm = synth.bench_batch(E, n_unique=64).cuda()
+KIND = sys.argv[3] if len(sys.argv) > 3 else "sparse"
+hm = (synth.dense_batch(E, n_unique=16) if KIND == "dense" else synth.bench_batch(E, n_unique=64)).cuda()
 rgb = torch.empty((E, 240, 320, 3), device="cuda")
 for _ in range(3):
     eng.render(hm, None, out=rgb)
