@@ -74,6 +74,35 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: list[str], source: str = "taxim_kernel.cu") -> Path:
+    """Experiment builds (tools/kbench.py): recompiles ONE kernel source with extra -D flags and links it with the other
+    objects of the regular build into tacex_b200/lib/libtacex_b200_<name>.so (selected with TACEX_B200_LIB)."""
+    build_lib()
+    env = dict(os.environ)
+    env.pop("CC", None), env.pop("CXX", None)
+    s = CSRC / source
+    o = LIB_DIR / f"{s.stem}.{name}.o"
+    flags = [f for f in NVCC_FLAGS if not (source.startswith("fem_") and f == "-fmad=false")]
+    cmd = [nvcc_path(), *flags, *[f"-D{d}" for d in defines], "-ccbin", "/usr/bin/g++", "-I", str(PKG.parent / "include"), "-c", str(s), "-o", str(o)]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    (LIB_DIR / f"{s.stem}.{name}.ptxas.txt").write_text(r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"nvcc failed on {source} ({name})")
+    objs = [str(LIB_DIR / (Path(x).stem + ".o")) for x in SOURCES if x != source] + [str(o)]
+    out = LIB_DIR / f"libtacex_b200_{name}.so"
+    r = subprocess.run([nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", str(out), *objs, "-lcudart"],
+                       capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+        sys.exit(0)
     p = build_lib(force="--force" in sys.argv, verbose=True)
     print(p)

@@ -45,7 +45,11 @@ static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 // colour stage: the per-warp staging areas (640 floats each) start at hb0 and may run into the first rows of hb1 (contiguous),
 // so the 1-row halo of the central differences sits behind them
 constexpr int HALO1_OFF = 1024;
-static_assert(NWARPS * 640 <= HB0_ROWS * IMG_W + HALO1_OFF && HALO1_OFF + IMG_W <= HB1_ROWS * IMG_W, "staging area");
+constexpr int IOST_OFF = HALO1_OFF + IMG_W; // per-warp background / RGB staging (192 floats each) behind the halo row
+static_assert(NWARPS * 640 <= HB0_ROWS * IMG_W + HALO1_OFF && IOST_OFF + NWARPS * 192 <= HB1_ROWS * IMG_W, "staging area");
+#ifndef TX_REC_F4
+#define TX_REC_F4 8 // float4 per polynomial record in device memory: 8 = padded to one 128-byte line (5 are used)
+#endif
 
 struct Misc {
     uint64_t mbar;
@@ -71,43 +75,44 @@ int taxim_smem_bytes() { return SM_TOTAL; }
 // not reach the reflected border, so every warp processes TWO rows at once (one per half warp) on the window that starts at
 // column `vbase`; the lanes wrap around inside their half, and everything a wrapped tap can reach is exactly zero, so the
 // result is bit-identical to the full-width evaluation (same tap order, zero terms leave the accumulator unchanged).
-template <int LPR>
-__device__ __forceinline__ void load_row12(const float* rp, int v0, bool interior, float (&x)[12])
+// J = columns per lane (12 or 8), REFLECT = the window is the whole row incl. its reflected border (LPR = 32, J = 12 only).
+template <int LPR, int J, bool REFLECT>
+__device__ __forceinline__ void load_row(const float* rp, int v0, bool interior, float (&x)[J])
 {
-    if (interior) { // three aligned 128-bit loads (conflict-free within each quarter warp)
+    if (interior) { // aligned 128-bit loads (conflict-free within each quarter warp)
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
+        for (int e = 0; e < J / 4; ++e) {
             const float4 t = *reinterpret_cast<const float4*>(rp + v0 + 4 * e);
             x[4 * e + 0] = t.x; x[4 * e + 1] = t.y; x[4 * e + 2] = t.z; x[4 * e + 3] = t.w;
         }
-    } else if (LPR == 32) { // the six edge lanes hold the reflected columns
+    } else if (REFLECT) { // the six edge lanes hold the reflected columns
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
+        for (int j = 0; j < J; ++j) {
             int v = v0 + j;
             v = v < 0 ? -v : (v > IMG_W - 1 ? 2 * (IMG_W - 1) - v : v);
             x[j] = rp[v];
         }
-    } else { // window past the end of the row: those columns only feed outputs that are never stored
+    } else { // window past the end of the row: those columns are zero / only feed outputs that are never stored
 #pragma unroll
-        for (int j = 0; j < 12; ++j) x[j] = (v0 + j >= 0 && v0 + j < IMG_W) ? rp[v0 + j] : 0.0f;
+        for (int j = 0; j < J; ++j) x[j] = (v0 + j >= 0 && v0 + j < IMG_W) ? rp[v0 + j] : 0.0f;
     }
 }
 
-template <int L, int RAD, int LPR>
+template <int L, int RAD, int LPR, int J, bool REFLECT>
 __device__ __forceinline__ void hpass_rows(const TaximTaps& c_taps, float* plane, float* hb_remote, int warp, int lane, unsigned q, int la, int lb, int vbase)
 {
-    constexpr int D = (RAD + 11) / 12;
+    constexpr int D = (RAD + J - 1) / J;
     constexpr int RPW = 32 / LPR; // rows per warp
     const int sub = lane & (LPR - 1), half = lane / LPR;
-    const int v0 = vbase + 12 * sub;
-    const bool interior = LPR == 32 ? (lane >= 3) && (lane <= 28) : (v0 >= 0 && v0 + 11 < IMG_W);
+    const int v0 = vbase + J * sub;
+    const bool interior = v0 >= 0 && v0 + J - 1 < IMG_W;
     const int nact = lb - la + 1;
     const int ngrp = (nact + RPW - 1) / RPW; // groups of RPW consecutive rows
     if (warp >= ngrp) return;
-    float xn[12];
+    float xn[J];
     {
         const int r0 = min(la + warp * RPW + half, lb);
-        load_row12<LPR>(plane + r0 * IMG_W, v0, interior, xn);
+        load_row<LPR, J, REFLECT>(plane + r0 * IMG_W, v0, interior, xn);
     }
 #pragma unroll 1
     for (int k = warp; k < ngrp; k += NWARPS) {
@@ -115,22 +120,22 @@ __device__ __forceinline__ void hpass_rows(const TaximTaps& c_taps, float* plane
         const bool rvalid = rowu <= lb;
         const int row = min(rowu, lb);
         float* rp = plane + row * IMG_W;
-        float x[12], acc[12];
+        float x[J], acc[J];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) { x[j] = xn[j]; acc[j] = 0.0f; }
+        for (int j = 0; j < J; ++j) { x[j] = xn[j]; acc[j] = 0.0f; }
         if (k + NWARPS < ngrp) { // prefetch this warp's next row(s)
             const int rn = min(la + (k + NWARPS) * RPW + half, lb);
-            load_row12<LPR>(plane + rn * IMG_W, v0, interior, xn);
+            load_row<LPR, J, REFLECT>(plane + rn * IMG_W, v0, interior, xn);
         }
 #pragma unroll
         for (int d = -D; d <= D; ++d) {
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                if (12 * d + j >= -RAD && 12 * d + j - 11 <= RAD) {
+            for (int j = 0; j < J; ++j) {
+                if (J * d + j >= -RAD && J * d + j - (J - 1) <= RAD) {
                     const float y = (d == 0) ? x[j] : __shfl_sync(0xffffffffu, x[j], ((lane + d) & (LPR - 1)) | (lane & ~(LPR - 1)));
 #pragma unroll
-                    for (int m = 0; m < 12; ++m) {
-                        const int kk = 12 * d + j - m;
+                    for (int m = 0; m < J; ++m) {
+                        const int kk = J * d + j - m;
                         if (kk >= -RAD && kk <= RAD) acc[m] = __fmaf_rn(c_taps.t[L][0][kk + RAD], y, acc[m]);
                     }
                 }
@@ -141,7 +146,7 @@ __device__ __forceinline__ void hpass_rows(const TaximTaps& c_taps, float* plane
         const bool push = dist < RAD;
         if (rvalid) {
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
+            for (int e = 0; e < J / 4; ++e) {
                 const int vb = v0 + 4 * e;
                 if (vb >= 0 && vb <= IMG_W - 4) {
                     const float4 t = make_float4(acc[4 * e + 0], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
@@ -165,13 +170,21 @@ __device__ __forceinline__ void hpass(const TaximTaps& c_taps, float* plane, flo
         if (row < la || row > lb)
             reinterpret_cast<float4*>(hb_remote + dist * IMG_W)[i - dist * (IMG_W / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // Halo rows written by the narrow variant keep stale columns outside the window; the vertical pass of this level only
-    // reads the columns [c0 - RAD, c1 + RAD], which the window covers.
-    const bool narrow = c0 > RAD && c1 < IMG_W - 1 - RAD && (c1 - c0 + 1) + 2 * RAD + 8 <= 192;
-    if (narrow)
-        hpass_rows<L, RAD, 16>(c_taps, plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
+    // Windowed variants: when the non-zero columns [c0, c1] stay more than RAD away from both image borders, no reflected tap can
+    // reach a non-zero value, so the row is evaluated on a window that starts at `vbase` with zeros outside the image -- no
+    // reflected loads (which cost the six edge lanes a divergent scalar path), and fewer columns:
+    //   192 columns (16 lanes x 12): two rows per warp;   256 columns (32 lanes x 8).
+    // Halo rows written by a windowed variant keep stale columns outside the window; the vertical pass of this level only
+    // reads the columns [c0 - RAD, c1 + RAD], which the window covers. Bit-identical to the full-width evaluation (same tap
+    // order, zero terms leave the accumulator unchanged).
+    const bool inner = c0 > RAD && c1 < IMG_W - 1 - RAD;
+    const int need = (c1 - c0 + 1) + 2 * RAD + 4; // columns from the 4-aligned window start to c1 + RAD
+    if (inner && need + 4 <= 192)
+        hpass_rows<L, RAD, 16, 12, false>(c_taps, plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
+    else if (inner && need <= 256)
+        hpass_rows<L, RAD, 32, 8, false>(c_taps, plane, hb_remote, warp, lane, q, la, lb, (c0 - RAD) & ~3);
     else
-        hpass_rows<L, RAD, 32>(c_taps, plane, hb_remote, warp, lane, q, la, lb, -32);
+        hpass_rows<L, RAD, 32, 12, true>(c_taps, plane, hb_remote, warp, lane, q, la, lb, -32);
 }
 
 // ---- vertical pass: thread per column, sliding register window, in place --------------------------------------
@@ -345,7 +358,7 @@ __global__ void flat_rgb_kernel(const TaximArgs p, float* __restrict__ out)
     if (i >= IMG_H * IMG_W) return;
     const float PI_F = 3.14159265358979323846f;
     const int id_flat = min(max((int)floorf(__fmul_rn(__fadd_rn(0.0f, PI_F), p.inv_ybin)), 0), p.nb - 1);
-    const float4* pf = p.poly + (size_t)id_flat * 5;
+    const float4* pf = p.poly + (size_t)id_flat * TX_REC_F4;
     const float4 a0 = __ldg(pf), a1 = __ldg(pf + 1), a2 = __ldg(pf + 2), a3 = __ldg(pf + 3), a4 = __ldg(pf + 4);
     const float cf[20] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y,
                           a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
@@ -505,46 +518,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     // min over the frame of ((hm - m) - press) is exactly -press, so pressing_depth_mm == press.
     const float thr = __fmul_rn(-press, p.contact_scale);
     unsigned cnt = 0, srow = 0, scol = 0;
-    constexpr int NWORDS = HALF_H * (IMG_W / 32);
-    static_assert(NWORDS % 4 == 0, "h/mask pass unroll");
-    // contact bounding box of this warp's words (warp-uniform registers; merged with 4 shared atomics per warp at the end)
+    // One warp iteration = 128 consecutive pixels (4 mask words): every lane owns 4 pixels as one float4 (128-bit shared-memory
+    // accesses), the 4-bit mask nibbles of the 8 lanes of a word are merged with three shuffles. The contact bounding box and
+    // the FOTS sums are kept in per-lane registers and reduced once per warp at the end.
+    constexpr int NSEG = HALF_H * IMG_W / 128;
     int bb_r0 = IMG_H, bb_r1 = -1, bb_c0 = IMG_W, bb_c1 = -1;
-    for (int w0 = warp * 4; w0 < NWORDS; w0 += NWARPS * 4) {
-        float pv[4], gv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = (w0 + u) * 32 + lane;
-            pv[u] = plane[idx];
-            gv[u] = gel_half ? __ldg(gel_half + idx) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int w = w0 + u;
-            const int idx = w * 32 + lane;
-            const float h = __fadd_rn(__fadd_rn(pv[u], -m), -press);
-            const bool contact = h < 0.0f;
-            const float j = fminf(h, gv[u]);
-            const bool mk = (__fadd_rn(j, -gv[u]) < thr) && contact;
-            plane[idx] = j;
-            const unsigned bits = __ballot_sync(0xffffffffu, mk);
-            const unsigned cbits = __ballot_sync(0xffffffffu, contact);
-            if (lane == 0) maskbits[w] = bits;
-            if (cbits) { // grow the contact bounding box (the joined map is non-zero exactly where h < 0)
-                const int rrow = (int)(q * HALF_H) + w / (IMG_W / 32), cb0 = (w % (IMG_W / 32)) * 32;
+    {
+        float4* plane4 = reinterpret_cast<float4*>(plane);
+        const float4* gel4 = gel_half ? reinterpret_cast<const float4*>(gel_half) : nullptr;
+        const int sub = lane & 7, grp = lane >> 3;
+#pragma unroll 2
+        for (int sg = warp; sg < NSEG; sg += NWARPS) {
+            const int i4 = sg * 32 + lane;
+            const float4 pv = plane4[i4];
+            const float4 gv = gel4 ? __ldg(gel4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int w = sg * 4 + grp;                 // mask word of this lane's pixels
+            const int lrow = w / (IMG_W / 32);          // local row
+            const int x0 = (w - lrow * (IMG_W / 32)) * 32 + sub * 4;
+            const float hx = __fadd_rn(__fadd_rn(pv.x, -m), -press), hy = __fadd_rn(__fadd_rn(pv.y, -m), -press);
+            const float hz = __fadd_rn(__fadd_rn(pv.z, -m), -press), hw = __fadd_rn(__fadd_rn(pv.w, -m), -press);
+            const float4 j = make_float4(fminf(hx, gv.x), fminf(hy, gv.y), fminf(hz, gv.z), fminf(hw, gv.w));
+            plane4[i4] = j;
+            const unsigned c0 = hx < 0.0f, c1 = hy < 0.0f, c2 = hz < 0.0f, c3 = hw < 0.0f;
+            const unsigned m0 = (__fadd_rn(j.x, -gv.x) < thr) & c0, m1 = (__fadd_rn(j.y, -gv.y) < thr) & c1;
+            const unsigned m2 = (__fadd_rn(j.z, -gv.z) < thr) & c2, m3 = (__fadd_rn(j.w, -gv.w) < thr) & c3;
+            const unsigned nb = m0 | (m1 << 1) | (m2 << 2) | (m3 << 3);
+            const unsigned cn = c0 | (c1 << 1) | (c2 << 2) | (c3 << 3);
+            unsigned wb = nb << (4 * sub);
+            wb |= __shfl_xor_sync(0xffffffffu, wb, 1);
+            wb |= __shfl_xor_sync(0xffffffffu, wb, 2);
+            wb |= __shfl_xor_sync(0xffffffffu, wb, 4);
+            const bool leader = sub == 0;
+            if (leader) maskbits[w] = wb;
+            const unsigned bal = __ballot_sync(0xffffffffu, leader && wb != 0u);
+            if (bal) { // append the non-empty words to the list (one shared atomic per warp iteration)
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&misc->nlist, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (leader && wb != 0u) mlist[pos + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)w;
+            }
+            if (cn) { // contact bounding box (the joined map is non-zero exactly where h < 0)
+                const int rrow = (int)(q * HALF_H) + lrow;
                 bb_r0 = min(bb_r0, rrow);
                 bb_r1 = max(bb_r1, rrow);
-                bb_c0 = min(bb_c0, cb0 + __ffs(cbits) - 1);
-                bb_c1 = max(bb_c1, cb0 + 31 - __clz(cbits));
+                bb_c0 = min(bb_c0, x0 + __ffs(cn) - 1);
+                bb_c1 = max(bb_c1, x0 + 31 - __clz(cn));
             }
-            if (bits) {
-                if (lane == 0) mlist[atomicAdd(&misc->nlist, 1)] = (unsigned short)w;
-                if (mk) { // row / column from the word index (one word = 32 consecutive columns of one row)
-                    cnt += 1u;
-                    srow += (unsigned)(q * HALF_H) + (unsigned)w / (IMG_W / 32);
-                    scol += ((unsigned)w % (IMG_W / 32)) * 32u + (unsigned)lane;
-                }
+            if (nb) {
+                const unsigned k = __popc(nb);
+                cnt += k;
+                srow += k * ((unsigned)(q * HALF_H) + (unsigned)lrow);
+                scol += k * (unsigned)x0 + m1 + 2u * m2 + 3u * m3;
             }
-            if (p.mask_out) p.mask_out[half_off + idx] = mk ? 1 : 0;
+            if (p.mask_out)
+                *reinterpret_cast<uchar4*>(p.mask_out + half_off + (size_t)i4 * 4) = make_uchar4(m0, m1, m2, m3);
+        }
+    }
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bb_r0 = min(bb_r0, __shfl_xor_sync(0xffffffffu, bb_r0, o));
+            bb_r1 = max(bb_r1, __shfl_xor_sync(0xffffffffu, bb_r1, o));
+            bb_c0 = min(bb_c0, __shfl_xor_sync(0xffffffffu, bb_c0, o));
+            bb_c1 = max(bb_c1, __shfl_xor_sync(0xffffffffu, bb_c1, o));
         }
     }
     if (lane == 0 && bb_r1 >= 0) {
@@ -656,97 +692,94 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     TX_TICK(32);
 
     // ---- normals -> bins -> polynomial -> + background -> clip -> NHWC (ref: taxim_torch.py:475-503, 243-258) ---
-    // One thread per 4 consecutive pixels of a row, 128-bit loads / stores. The deformed gel is exactly zero outside the
-    // region `rg`, so only the pixels of the rectangle rg + 1 px (central differences; the replicate-padded border rows /
-    // columns follow their inner neighbour) can have a non-zero gradient:
+    // The deformed gel is exactly zero outside the region `rg`, so only the pixels of the rectangle rg + 1 px (central
+    // differences; the replicate-padded border rows / columns follow their inner neighbour) can have a non-zero gradient:
     //   (1) outside the rectangle: copy the precomputed flat RGB (bit-identical to evaluating it);
-    //   (2) inside: threads are mapped densely onto the rectangle; canonical atan / atan2, bins, and a cooperative gather
-    //       of the 80-byte table records through a per-warp staging area (5 lanes read one record contiguously instead
-    //       of 32 scattered requests per load).
+    //   (2) inside: one warp per block of 32 consecutive pixels of a rectangle row, one pixel per lane: canonical atan / atan2,
+    //       bins, then the polynomial record of every pixel is gathered COOPERATIVELY (5 lanes read one record contiguously;
+    //       the records are padded to one 128-byte line each) into a per-warp staging area; the background and the RGB output
+    //       of the block -- 384 contiguous bytes each -- move as 24 x 128-bit accesses through a small staging area instead
+    //       of 3 x 32 scalar accesses with a 12-byte stride; the gather of the NEXT block is requested before the current
+    //       block is evaluated (software pipeline).
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
-    float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (15 x 2560 B = 38,400 B)
-    constexpr int QPR = IMG_W / 4; // quads per row
-    const int ry0 = fc.ry0, xa = fc.xa, xb = fc.xb, total = fc.total;
-    const int nq = xb >= xa ? (xb - xa + 1) >> 2 : 0;
+    float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (16 x 2560 B = 40,960 B)
+    float* iost = hb1 + IOST_OFF + warp * 192; // per warp: 96 floats of background + 96 floats of RGB
+    const float* halo1 = hb1 + HALO1_OFF;
+    const int ry0 = fc.ry0, ry1 = fc.ry1, xa = fc.xa, xb = fc.xb;
     // (1) flat copy of everything outside the rectangle: the slices no idle warp has taken during the pyramid
     for (int sl = 0; sl < FC_SLICES; ++sl)
         if (!((fc.done >> sl) & 1u)) flat_copy_slice(fc, sl, tid, NTHREADS);
-    // (2) the rectangle: one pixel per lane, software-pipelined: the table records of the NEXT pixel set are requested
-    // (after its bins are known) before the current set is staged and evaluated, so the L2 round trip of the gather
-    // overlaps the arithmetic instead of serialising with it.
-    (void)nq; (void)QPR;
-    const int nw = xb >= xa ? xb - xa + 1 : 0;   // rectangle width in pixels
-    const int npx = total * 4;                   // pixels of the rectangle in this half
-    const float inv_nw = nw > 0 ? 1.0f / (float)nw : 0.0f;
-    const int rec_of = lane / 5;                 // idx = e * 32 + lane: record (idx / 5), part (idx % 5), precomputed per e
-    int bin_next = 0, row_n = 0, x_n = 0;
-    float4 rec[5];
-    // lane-constant gather pattern
-    int g_rec[5], g_part[5];
+    // (2) the rectangle
+    const int nw = (fc.total > 0 && xb >= xa) ? xb - xa + 1 : 0; // rectangle width in pixels (multiple of 4)
+    const int nbr = (nw + 31) >> 5;                               // 32-pixel blocks per rectangle row
+    const int nblk = nw > 0 ? nbr * (ry1 - ry0 + 1) : 0;
+    const float inv_nbr = nbr > 0 ? 1.0f / (float)nbr : 0.0f;
+    float4 rec[5], bg4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int g_rec[5], g_part[5]; // lane-constant gather pattern: float4 index e * 32 + lane = record (idx / 5), part (idx % 5)
 #pragma unroll
     for (int e = 0; e < 5; ++e) {
         const int idx = e * 32 + lane;
         g_rec[e] = idx / 5;
         g_part[e] = idx - g_rec[e] * 5;
     }
-    (void)rec_of;
-    auto pixel_bin = [&](int pidx, int& row, int& x) -> int {
-        const int rr = __float2int_rz(__fmul_rn((float)pidx + 0.5f, inv_nw)); // == pidx / nw (pidx < 2^16, error << 0.5 / nw)
+    int row_n = 0, xs_n = 0;
+    auto block_bin = [&](int bi, int& row, int& xs) -> int {
+        const int rr = __float2int_rz(__fmul_rn((float)bi + 0.5f, inv_nbr)); // == bi / nbr (bi < 2^12, error << 0.5 / nbr)
         row = ry0 + rr;
-        x = xa + (pidx - rr * nw);
+        xs = xa + 32 * (bi - rr * nbr);
+        const int x = min(xs + lane, xb);
         const int gy_ = (int)q * HALF_H + row; // image row
         // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
         const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
         const int xx = min(max(x, 1), IMG_W - 2);
         const float* ctr = plane + yy * IMG_W + xx;
-        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : hb1 + HALO1_OFF + xx;
-        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : hb1 + HALO1_OFF + xx;
+        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : halo1 + xx;
+        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : halo1 + xx;
         const float top = __fmul_rn(*up, p.inv_pixmm), bot = __fmul_rn(*dn, p.inv_pixmm);
         const float lef = __fmul_rn(ctr[-1], p.inv_pixmm), rig = __fmul_rn(ctr[1], p.inv_pixmm);
         const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
         const float gy = __fmul_rn(__fmul_rn(__fadd_rn(lef, -rig), 0.5f), p.sx);
         const float s2 = __fmaf_rn(gx, gx, __fmul_rn(gy, gy));
         // tt = sqrt(s2) is zero iff s2 is zero: a flat pixel (exact zero gradient) lands in bin (0, dir = 0)
-        const float tt = (p.dbg & 16) ? s2 : __fsqrt_rn(s2);
-        const float mag = (p.dbg & 16) ? tt : atanf_c(tt);
-        const float dir = (p.dbg & 16) ? gx : ((tt != 0.0f) ? atan2f_c(gx, gy) : 0.0f);
+        const float tt = __fsqrt_rn(s2);
+        const float mag = atanf_c(tt);
+        const float dir = (tt != 0.0f) ? atan2f_c(gx, gy) : 0.0f;
         int im = (int)floorf(__fmul_rn(mag, p.inv_xbin));
         int id = (int)floorf(__fmul_rn(__fadd_rn(dir, PI_F), p.inv_ybin));
         im = min(max(im, 0), p.nb - 1);
         id = min(max(id, 0), p.nb - 1);
-        return (p.dbg & 32) ? 62 : im * p.nb + id; // record index into [nb][nb][20 floats]
+        return im * p.nb + id; // record index
     };
-    auto request = [&](int bin) {
+    auto request = [&](int bin, int row, int xs) {
 #pragma unroll
         for (int e = 0; e < 5; ++e) {
             const int bsrc = __shfl_sync(0xffffffffu, bin, g_rec[e]);
-            rec[e] = __ldg(p.poly + (size_t)bsrc * 5 + g_part[e]);
+            rec[e] = __ldg(p.poly + (size_t)bsrc * TX_REC_F4 + g_part[e]);
         }
+        // background of the block: 3 * nval contiguous floats, 128-bit loads by the first lanes
+        const int nval = min(32, xb - xs + 1);
+        if (4 * lane < 3 * nval) bg4 = __ldg(reinterpret_cast<const float4*>(bg_half + ((size_t)row * IMG_W + xs) * 3) + lane);
     };
-    int pb = warp * 32;
-    if (pb < npx) {
-        bin_next = pixel_bin(min(pb + lane, npx - 1), row_n, x_n);
-        request(bin_next);
+    int bi = warp;
+    if (bi < nblk) {
+        const int b = block_bin(bi, row_n, xs_n);
+        request(b, row_n, xs_n);
     }
 #pragma unroll 1
-    for (; pb < npx; pb += NTHREADS) {
-        const bool valid = pb + lane < npx;
-        const int row = row_n, x = x_n;
-        // background of this pixel: requested first, used last (the loads cannot be hoisted across the warp barriers by the compiler)
-        const size_t pix = (size_t)row * IMG_W + x;
-        const float* bgp = bg_half + pix * 3;
-        const float bgv[3] = {__ldg(bgp), __ldg(bgp + 1), __ldg(bgp + 2)};
-        // stage the current records (one 80-byte record per lane)
+    for (; bi < nblk; bi += NWARPS) {
+        const int row = row_n, xs = xs_n;
+        const int nval = min(32, xb - xs + 1);
         __syncwarp();
+        // stage the current records (one 80-byte record per lane) and the background of the block
 #pragma unroll
         for (int e = 0; e < 5; ++e) reinterpret_cast<float4*>(stage)[e * 32 + lane] = rec[e];
-        // next set: bins, then its requests go out before this set is evaluated
-        const int pn = pb + NTHREADS;
-        if (pn < npx) {
-            bin_next = pixel_bin(min(pn + lane, npx - 1), row_n, x_n);
-            request(bin_next);
+        if (4 * lane < 3 * nval) reinterpret_cast<float4*>(iost)[lane] = bg4;
+        // next block: bins, then its requests go out before this block is evaluated
+        if (bi + NWARPS < nblk) {
+            const int b = block_bin(bi + NWARPS, row_n, xs_n);
+            request(b, row_n, xs_n);
         }
         __syncwarp();
         float cf[20];
@@ -755,15 +788,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             const float4 t = reinterpret_cast<const float4*>(stage)[lane * 5 + e];
             cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
         }
-        const int gy_ = (int)q * HALF_H + row;
-        const float yf = __fmul_rn((float)gy_, p.fy);
-        const float xf = __fmul_rn((float)x, p.fx);
+        const float bgv[3] = {iost[3 * lane], iost[3 * lane + 1], iost[3 * lane + 2]};
+        const float yf = __fmul_rn((float)((int)q * HALF_H + row), p.fy);
+        const float xf = __fmul_rn((float)(xs + lane), p.fx);
         float o[3];
         poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), __fmul_rn(yf, yf), __fmul_rn(xf, yf), bgv, o);
-        if (valid && (!(p.dbg & 1) || o[0] < -1.0f)) {
-            float* op = rgb_half + pix * 3;
-            op[0] = o[0]; op[1] = o[1]; op[2] = o[2];
-        }
+        iost[96 + 3 * lane] = o[0]; iost[96 + 3 * lane + 1] = o[1]; iost[96 + 3 * lane + 2] = o[2];
+        __syncwarp();
+        if (4 * lane < 3 * nval)
+            reinterpret_cast<float4*>(rgb_half + ((size_t)row * IMG_W + xs) * 3)[lane] = reinterpret_cast<const float4*>(iost + 96)[lane];
     }
     __syncthreads();
     TX_TICK(33);
@@ -795,6 +828,7 @@ cudaError_t launch_taxim(const TaximArgs& a, const TaximTaps& taps, int N, cudaS
 }
 
 int taxim_lowres_max_pixels() { return HB0_ROWS * IMG_W; }
+int taxim_record_f4() { return TX_REC_F4; }
 
 // ---- stand-alone indentation depth (ref: taxim_sim.py:115-131): one CTA per frame, HBM-bound -------------------
 __global__ void __launch_bounds__(256) indentation_depth_kernel(const float* __restrict__ hm, float* __restrict__ out,

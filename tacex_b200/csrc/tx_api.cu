@@ -18,7 +18,8 @@ struct tx_handle {
     tx_counters ctr{};
     bool have_tables = false;
     // device tables
-    float4* d_poly = nullptr; // [nb][nb][20]
+    float4* d_poly = nullptr; // [nb][nb][20]  (generic / shadow kernels)
+    float4* d_poly128 = nullptr; // [nb][nb][32] the same records padded to one 128-byte line each (fused 240 x 320 kernel)
     float* d_bg = nullptr;    // [H][W][3]
     float* d_gel = nullptr;   // [H][W] or nullptr
     float* d_flat = nullptr;  // [H][W][3] flat-pixel RGB
@@ -204,7 +205,7 @@ extern "C" void tx_destroy(tx_handle* h)
     cudaFree(h->d_taps);
     cudaFree(h->d_sh_table); cudaFree(h->d_sh_cos); cudaFree(h->d_sh_sin); cudaFree(h->d_sh_taps); cudaFree(h->d_sh_def);
     cudaFree(h->d_sh_img); cudaFree(h->d_sh_t1); cudaFree(h->d_sh_t2); cudaFree(h->d_sh_mask);
-    cudaFree(h->d_poly); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
+    cudaFree(h->d_poly); cudaFree(h->d_poly128); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
     cudaFree(h->d_hm); cudaFree(h->d_rgb); cudaFree(h->d_depth); cudaFree(h->d_theta); cudaFree(h->d_traj0);
@@ -244,6 +245,12 @@ extern "C" int tx_upload_tables(tx_handle* h, const float* poly_grad, const floa
     if (!h->d_poly) TX_CUDA(h, cudaMalloc(&h->d_poly, poly.size() * sizeof(float)));
     if (!h->d_bg) TX_CUDA(h, cudaMalloc(&h->d_bg, bg.size() * sizeof(float)));
     TX_CUDA(h, cudaMemcpy(h->d_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (!h->generic) {
+        std::vector<float> p128((size_t)nb * nb * 32, 0.0f);
+        for (size_t r = 0; r < (size_t)nb * nb; ++r) memcpy(&p128[r * 32], &poly[r * 20], 20 * sizeof(float));
+        if (!h->d_poly128) TX_CUDA(h, cudaMalloc(&h->d_poly128, p128.size() * sizeof(float)));
+        TX_CUDA(h, cudaMemcpy(h->d_poly128, p128.data(), p128.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     TX_CUDA(h, cudaMemcpy(h->d_bg, bg.data(), bg.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (gel_map) {
         if (!h->d_gel) TX_CUDA(h, cudaMalloc(&h->d_gel, sizeof(float) * H * W));
@@ -256,6 +263,7 @@ extern "C" int tx_upload_tables(tx_handle* h, const float* poly_grad, const floa
         if (!h->d_flat) TX_CUDA(h, cudaMalloc(&h->d_flat, sizeof(float) * H * W * 3));
         TaximArgs a{};
         fill_taxim_consts(h, a);
+        a.poly = taxim_record_f4() == 8 ? h->d_poly128 : h->d_poly;
         TX_CUDA(h, launch_flat_rgb(a, h->d_flat, h->stream));
         TX_CUDA(h, cudaStreamSynchronize(h->stream));
         h->ctr.kernels_launched++;
@@ -394,7 +402,8 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     if (!h->have_tables) return fail(h, TX_ERR_NO_TABLES, "tx_render: call tx_upload_tables first");
     if (N > h->cfg.max_envs || env0 < 0 || env0 + N > h->cfg.max_envs) return fail(h, TX_ERR_INVALID_ARG, "tx_render: N exceeds max_envs");
     if (!h->generic &&
-        ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u))))
+        ((!lowres && ((uintptr_t)height_mm & 15u)) || ((uintptr_t)rgb & 15u) || (deformed && ((uintptr_t)deformed & 15u)) ||
+         (mask && ((uintptr_t)mask & 3u))))
         return fail(h, TX_ERR_INVALID_ARG, "tx_render: device buffers must be 16-byte aligned");
     if (N == 0) return TX_OK;
     TX_CUDA(h, cudaSetDevice(h->device));
@@ -428,6 +437,7 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
         a.up_scratch = h->d_up;
     }
     fill_taxim_consts(h, a);
+    a.poly = taxim_record_f4() == 8 ? h->d_poly128 : h->d_poly; // one 128-byte line per record
     a.rgb = rgb;
     a.depth_out = depth_out;
     a.deformed_out = deformed;

@@ -29,7 +29,7 @@ struct TaximArgs {
     const float2* rs_wy;   // [240] the two vertical weights
     float* up_scratch;     // [N][240][320] resized height maps (read back by the masked re-imposition)
     const float* gel;      // [240][320] or nullptr (flat)
-    const float4* poly;    // [nb][nb][20] (3 channels x 6 coefficients, padded)
+    const float4* poly;    // [nb][nb][32]: 3 channels x 6 coefficients, every record padded to one 128-byte line
     const float* bg_hwc;   // [240][320][3]
     const float* flat_rgb; // [240][320][3] RGB of a flat (zero-gradient) pixel: clip(poly(bin(0, 0)) + background)
     float* rgb;            // [N][240][320][3]
@@ -181,6 +181,7 @@ cudaError_t launch_fem_markers(const FemMarkerArgs& m, int N, cudaStream_t st);
 
 int taxim_smem_bytes();
 int taxim_lowres_max_pixels();
+int taxim_record_f4(); // float4 stride of the polynomial records the fused kernel expects (8 = one 128-byte line, 5 = packed)
 cudaError_t launch_taxim(const TaximArgs& a, const TaximTaps& taps, int N, cudaStream_t s);
 cudaError_t launch_flat_rgb(const TaximArgs& a, float* flat_rgb, cudaStream_t s);
 cudaError_t launch_indentation_depth(const float* hm, float* out, int N, float gelpad_h, float gelpad_min, cudaStream_t s);

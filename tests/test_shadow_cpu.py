@@ -8,7 +8,7 @@
   clip) agrees to 1e-5 wherever the 7 x 7 neighbourhood a pixel's two blurs reach holds no pixel whose gradient bin the
   reference's FFT noise decided differently (SURVEY section 0-4);
 * container only (marker refbox): the init-time tables against the reference's tensors, and fresh inputs.
-No product kernel consumes this yet: the plug-in still raises NotImplementedError for with_shadow=True."""
+The device kernels (tx_render_shadow) are compared bit for bit with this restatement in tests/test_shadow_gpu.py."""
 import numpy as np
 import pytest
 import torch

@@ -1,8 +1,8 @@
 """Stall-reason samples per region of taxim_kernel.cu from `ncu --page source --print-source cuda,sass --csv` (CUDA view)."""
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
-regions = [(96, 154, "hpass"), (181, 228, "vpass"), (232, 263, "reimpose"), (283, 298, "flatcopy"), (305, 338, "blur_level"),
-           (340, 356, "poly_rgb"), (388, 520, "prologue/min"), (521, 629, "mask pass"), (630, 683, "between"), (684, 900, "colour")]
+regions = [(78, 160, "hpass"), (161, 180, "hpass-wrap"), (185, 233, "vpass"), (236, 275, "reimpose"), (278, 304, "flatcopy"), (310, 345, "blur_level"),
+           (347, 370, "flat_rgb"), (375, 508, "prologue/min"), (509, 639, "mask pass"), (640, 685, "between"), (686, 800, "colour")]
 hdr = None; fname = ''
 agg = collections.defaultdict(lambda: collections.Counter()); inst = collections.Counter(); tot = 0
 lines = collections.Counter()
