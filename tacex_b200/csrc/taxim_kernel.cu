@@ -762,24 +762,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         const int nval = min(32, xb - xs + 1);
         if (4 * lane < 3 * nval) bg4 = __ldg(reinterpret_cast<const float4*>(bg_half + ((size_t)row * IMG_W + xs) * 3) + lane);
     };
+    // Software pipeline, three blocks deep: iteration i stages the records of block i (requested one iteration ago), requests
+    // the records of block i + 1 (its bins were computed one iteration ago), computes the bins of block i + 2 -- the long
+    // dependent sqrt / atan / atan2 chain, which covers the L2 round trip of the request -- and evaluates block i.
     int bi = warp;
+    int row_c = 0, xs_c = 0;     // block i (records in flight / staged)
+    int bin_n = 0;               // block i + 1 (bins known)
     if (bi < nblk) {
-        const int b = block_bin(bi, row_n, xs_n);
-        request(b, row_n, xs_n);
+        const int b = block_bin(bi, row_c, xs_c);
+        request(b, row_c, xs_c);
+        if (bi + NWARPS < nblk) bin_n = block_bin(bi + NWARPS, row_n, xs_n);
     }
 #pragma unroll 1
     for (; bi < nblk; bi += NWARPS) {
-        const int row = row_n, xs = xs_n;
+        const int row = row_c, xs = xs_c;
         const int nval = min(32, xb - xs + 1);
         __syncwarp();
         // stage the current records (one 80-byte record per lane) and the background of the block
 #pragma unroll
         for (int e = 0; e < 5; ++e) reinterpret_cast<float4*>(stage)[e * 32 + lane] = rec[e];
         if (4 * lane < 3 * nval) reinterpret_cast<float4*>(iost)[lane] = bg4;
-        // next block: bins, then its requests go out before this block is evaluated
+        // block i + 1: its requests go out now; block i + 2: bins
         if (bi + NWARPS < nblk) {
-            const int b = block_bin(bi + NWARPS, row_n, xs_n);
-            request(b, row_n, xs_n);
+            row_c = row_n; xs_c = xs_n;
+            request(bin_n, row_c, xs_c);
+            if (bi + 2 * NWARPS < nblk) bin_n = block_bin(bi + 2 * NWARPS, row_n, xs_n);
         }
         __syncwarp();
         float cf[20];
