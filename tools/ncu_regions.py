@@ -1,8 +1,8 @@
 """Stall-reason samples per region of taxim_kernel.cu from `ncu --page source --print-source cuda,sass --csv` (CUDA view)."""
 import csv, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
-regions = [(78, 160, "hpass"), (161, 180, "hpass-wrap"), (185, 233, "vpass"), (236, 275, "reimpose"), (278, 304, "flatcopy"), (310, 345, "blur_level"),
-           (347, 370, "flat_rgb"), (375, 508, "prologue/min"), (509, 639, "mask pass"), (640, 685, "between"), (686, 800, "colour")]
+regions = [(78, 162, "hpass"), (163, 190, "hpass-wrap"), (196, 244, "vpass_static"), (245, 301, "vpass"), (302, 340, "reimpose"), (341, 388, "flatcopy"), (389, 430, "blur_level"),
+           (431, 454, "flat_rgb"), (455, 592, "prologue/min"), (593, 723, "box/split/restage"), (724, 827, "mask pass"), (828, 883, "between"), (884, 1028, "colour")]
 hdr = None; fname = ''
 agg = collections.defaultdict(lambda: collections.Counter()); inst = collections.Counter(); tot = 0
 lines = collections.Counter()
