@@ -182,6 +182,20 @@ int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* 
 int tx_fots_markers(tx_handle* h, const float* press_mm, const float* theta, int N, float* traj0, int32_t* traj_len,
                     float* markers);
 
+/* Replaces FOTSMarkerSimulator.draw_markers and the per-env marker-overlay loop of the reference's RL task
+ * (ref: .../fots/fots_marker_sim.py:346-384; source/tacex_tasks/tacex_tasks/ball_rolling_tactile/ball_rolling_taxim_fots.py:918-937),
+ * batched over envs in one launch.
+ *   tx_set_marker_patches: HOST pointer, [10][10][12][12] uint8 = patch_array[:, :, w] of the reference's generate_patch_array()
+ *                          for the marker size in use (w = floor((marker_size - 1.5) * 10) = 15 for the default size 3)
+ *   markers        [N][2][M][2] as tx_fots_markers returns them ([:,1] = current positions are drawn, in order)
+ *   rgb_in         [N][H][W][3] float32 or NULL; apply != 0: rgb = ((rgb * 255) * (marker / 255)) / 255 (the reference's order)
+ *   rgb_out        optional [N][H][W][3] float32 (may alias rgb_in)
+ *   marker_img_out optional [N][H][W] uint8   the marker image draw_markers returns
+ *   rgb_u8_out     optional [N][H][W][3] uint8 round(rgb * 255): the observation at a quarter of the bytes (extension) */
+int tx_set_marker_patches(tx_handle* h, const uint8_t* patches);
+int tx_marker_overlay(tx_handle* h, const float* markers, int N, int M, const float* rgb_in, int apply, float* rgb_out,
+                      uint8_t* marker_img_out, uint8_t* rgb_u8_out);
+
 /* Initial marker grid (host pointers, M ints each). ref: marker_motion.py:58-76 */
 int tx_marker_grid(const tx_handle* h, int32_t* mx, int32_t* my);
 

@@ -216,3 +216,33 @@ def use_all_threads() -> int:
     except Exception:
         pass
     return num_threads()
+
+
+# ---- marker image / marker overlay (ref: fots_marker_sim.py:346-384, ball_rolling_taxim_fots.py:918-937) ------------------
+def marker_image(markers_xy: np.ndarray, patch_w: np.ndarray, H: int = 240, W: int = 320) -> np.ndarray:
+    """Restatement of ``FOTSMarkerSimulator.draw_markers``: (M, 2) float32 marker positions (x, y) -> (H, W) uint8. ``patch_w`` is
+    ``generate_patch_array()['patch_array'][:, :, w]`` (10, 10, 12, 12) for the marker size in use."""
+    import math
+
+    canvas = np.full((H + 24, W + 24), 255, np.uint8)
+    uv = np.asarray(markers_xy, np.float32).astype(np.float64) + 0.5
+    for k in range(uv.shape[0]):
+        u, v = uv[k, 0] + 12, uv[k, 1] + 12
+        pu = math.floor((u - math.floor(u)) * 10)
+        pv = math.floor((v - math.floor(v)) * 10)
+        cu, cv = math.floor(u) - 6, math.floor(v) - 6
+        if canvas.shape[1] - 12 > cu >= 0 and canvas.shape[0] - 12 > cv >= 0:
+            canvas[cv:cv + 12, cu:cu + 12] = patch_w[pu, pv]
+    return canvas[12:-12, 12:-12]
+
+
+def marker_overlay(rgb: np.ndarray, marker_img: np.ndarray) -> np.ndarray:
+    """The RL task's overlay arithmetic in float32: ((rgb * 255) * (marker / 255)) / 255 per channel."""
+    r = np.asarray(rgb, np.float32)
+    w = (marker_img.astype(np.float32) / np.float32(255.0))[..., None]
+    return ((r * np.float32(255.0)) * w) / np.float32(255.0)
+
+
+def rgb_to_u8(rgb: np.ndarray) -> np.ndarray:
+    """round-half-even(rgb * 255) clamped to [0, 255] (the extension output of tx_marker_overlay)."""
+    return np.clip(np.rint(np.asarray(rgb, np.float32) * np.float32(255.0)), 0, 255).astype(np.uint8)

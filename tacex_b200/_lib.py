@@ -73,7 +73,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
+    "tx_indentation_depth", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_set_marker_patches", "tx_marker_overlay", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers", "tx_fem_debug_set_cycles",
 ]
@@ -115,6 +115,10 @@ def load() -> C.CDLL:
         getattr(lib, name).restype = C.c_int
     lib.tx_render_depth.restype = C.c_int
     lib.tx_fots_markers.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, ip, fp]
+    lib.tx_set_marker_patches.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tx_set_marker_patches.restype = C.c_int
+    lib.tx_marker_overlay.argtypes = [C.c_void_p, fp, C.c_int, C.c_int, fp, C.c_int, fp, u8p, u8p]
+    lib.tx_marker_overlay.restype = C.c_int
     lib.tx_marker_grid.argtypes = [C.c_void_p, ip, ip]
     lib.tx_step_host.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp, fp]
     lib.tx_debug_set_ticks.argtypes = [C.c_void_p, C.c_void_p]

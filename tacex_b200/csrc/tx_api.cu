@@ -19,6 +19,7 @@ struct tx_handle {
     bool have_tables = false;
     // device tables
     float4* d_poly = nullptr; // [nb][nb][20]  (generic / shadow kernels)
+    unsigned char* d_patch = nullptr; // [10][10][12][12] marker dot patches (tx_set_marker_patches)
     float4* d_poly128 = nullptr; // [nb][nb][32] the same records padded to one 128-byte line each (fused 240 x 320 kernel)
     float* d_bg = nullptr;    // [H][W][3]
     float* d_gel = nullptr;   // [H][W] or nullptr
@@ -205,6 +206,7 @@ extern "C" void tx_destroy(tx_handle* h)
     cudaFree(h->d_taps);
     cudaFree(h->d_sh_table); cudaFree(h->d_sh_cos); cudaFree(h->d_sh_sin); cudaFree(h->d_sh_taps); cudaFree(h->d_sh_def);
     cudaFree(h->d_sh_img); cudaFree(h->d_sh_t1); cudaFree(h->d_sh_t2); cudaFree(h->d_sh_mask);
+    cudaFree(h->d_patch);
     cudaFree(h->d_poly); cudaFree(h->d_poly128); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
@@ -625,6 +627,36 @@ extern "C" int tx_fots_markers(tx_handle* h, const float* press_mm, const float*
     f.theta_max = h->cfg.theta_max_rad;
     TX_CUDA(h, launch_fots(f, N, h->stream));
     h->ctr.fots_calls++;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_set_marker_patches(tx_handle* h, const uint8_t* patches)
+{
+    if (!h || !patches) return fail(h, TX_ERR_INVALID_ARG, "tx_set_marker_patches: null argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_set_marker_patches: the marker overlay belongs to the 240 x 320 kernel");
+    TX_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_patch) TX_CUDA(h, cudaMalloc(&h->d_patch, 10 * 10 * 12 * 12));
+    TX_CUDA(h, cudaStreamSynchronize(h->stream));
+    TX_CUDA(h, cudaMemcpy(h->d_patch, patches, 10 * 10 * 12 * 12, cudaMemcpyHostToDevice));
+    return TX_OK;
+}
+
+extern "C" int tx_marker_overlay(tx_handle* h, const float* markers, int N, int M, const float* rgb_in, int apply, float* rgb_out,
+                                 uint8_t* marker_img_out, uint8_t* rgb_u8_out)
+{
+    if (!h || N < 0 || M < 0 || M > TX_MAX_MARKERS) return fail(h, TX_ERR_INVALID_ARG, "tx_marker_overlay: bad argument");
+    if (h->generic) return fail(h, TX_ERR_UNSUPPORTED, "tx_marker_overlay: the marker overlay belongs to the 240 x 320 kernel");
+    if ((apply || marker_img_out) && (!markers || !h->d_patch))
+        return fail(h, TX_ERR_STATE, "tx_marker_overlay: markers and tx_set_marker_patches are needed for the marker image");
+    if ((rgb_out || rgb_u8_out) && !rgb_in) return fail(h, TX_ERR_INVALID_ARG, "tx_marker_overlay: rgb_in is needed for an RGB output");
+    if (!rgb_out && !rgb_u8_out && !marker_img_out) return fail(h, TX_ERR_INVALID_ARG, "tx_marker_overlay: no output requested");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    OverlayArgs a{};
+    a.markers = markers; a.patch = h->d_patch; a.rgb_in = rgb_in; a.rgb = rgb_out; a.marker_img = marker_img_out; a.rgb_u8 = rgb_u8_out;
+    a.M = (apply || marker_img_out) ? M : 0; a.apply = apply ? 1 : 0;
+    TX_CUDA(h, launch_marker_overlay(a, N, h->stream));
     h->ctr.kernels_launched++;
     return TX_OK;
 }

@@ -130,6 +130,18 @@ struct FotsArgs {
     double lamb0, lamb1, lamb2, mm2pix, shear_max, theta_max;
 };
 
+// marker image / marker overlay (overlay_kernel.cu)
+struct OverlayArgs {
+    const float* markers;      // [N][2][M][2]
+    const unsigned char* patch; // [10][10][12][12] anti-aliased dot patches of the chosen marker size (device)
+    const float* rgb_in;       // [N][240][320][3] or nullptr
+    float* rgb;                // [N][240][320][3] or nullptr (may alias rgb_in)
+    unsigned char* marker_img; // [N][240][320] or nullptr
+    unsigned char* rgb_u8;     // [N][240][320][3] or nullptr
+    int M, apply;              // apply = 0: rgb / rgb_u8 without the marker modulation (plain uint8 conversion)
+};
+cudaError_t launch_marker_overlay(const OverlayArgs& a, int N, cudaStream_t s);
+
 // ---- gel FEM ---------------------------------------------------------------------------------------------------------
 typedef tx_fem_indenter FemIndenter;
 typedef tx_fem_stats FemStats;

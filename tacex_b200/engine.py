@@ -234,6 +234,30 @@ class TactileEngine:
         self._check(self.lib.tx_fots_markers(self.h, _ptr(press), _ptr(theta), N, _ptr(traj0), _ptr(traj_len), _ptr(out)))
         return out
 
+    # -- marker image / marker overlay (ref: fots_marker_sim.py:346-384, ball_rolling_taxim_fots.py:918-937) --------------
+    def set_marker_patches(self, patches) -> None:
+        """``patches``: uint8 (10, 10, 12, 12) = ``generate_patch_array()['patch_array'][:, :, w]`` of the reference for the marker
+        size in use (w = 15 for the default marker_size = 3); a NumPy array or CPU tensor."""
+        import numpy as np
+
+        pa = np.ascontiguousarray(np.asarray(patches), np.uint8)
+        if pa.shape != (10, 10, 12, 12):
+            raise _lib.TxError("marker patches must have shape (10, 10, 12, 12)")
+        self._check(self.lib.tx_set_marker_patches(self.h, pa.ctypes.data))
+
+    def marker_overlay(self, markers: torch.Tensor | None, rgb: torch.Tensor | None = None, apply: bool = True,
+                       rgb_out: torch.Tensor | None = None, marker_img_out: torch.Tensor | None = None,
+                       rgb_u8_out: torch.Tensor | None = None) -> None:
+        """One launch for all envs: marker image (``draw_markers``), RGB modulated by it (the RL task's overlay loop) and / or
+        the uint8 observation. ``rgb_out`` may be ``rgb`` itself (in place)."""
+        for t, dt in ((markers, torch.float32), (rgb, torch.float32), (rgb_out, torch.float32), (marker_img_out, torch.uint8), (rgb_u8_out, torch.uint8)):
+            if t is not None and (t.device != self.device or t.dtype != dt or not t.is_contiguous()):
+                raise _lib.TxError("marker_overlay: tensors must be contiguous, on the engine's device, float32 / uint8 as documented")
+        N = (markers if markers is not None else rgb).shape[0]
+        M = markers.shape[2] if markers is not None else 0
+        self._check(self.lib.tx_marker_overlay(self.h, _ptr(markers), N, M, _ptr(rgb), int(bool(apply)), _ptr(rgb_out),
+                                               _ptr(marker_img_out), _ptr(rgb_u8_out)))
+
     def set_phase_ticks(self, ticks: torch.Tensor | None) -> None:
         """Profiling: int64 device tensor (2*N, 40) receiving per-CTA phase clock stamps, or None to disable."""
         self._check(self.lib.tx_debug_set_ticks(self.h, _ptr(ticks)))

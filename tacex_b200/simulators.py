@@ -353,9 +353,49 @@ class B200FOTSMarkerSimulator(GelSightSimulator):
         self.sensor._data.output["traj"] = self.traj0
         self.theta = torch.zeros((self._num_envs,), device=dev)
         self._scratch_rgb = None
+        # marker dot patches for draw_markers / the marker overlay (ref: fots_marker_sim.py:112, generate_patch_array()): the slice
+        # for the reference's default marker_size = 3, produced by executing the reference (oracle/make_golden_overlay.py)
+        self._marker_img = None
+        self._patches_ready = False
+        baked = Path(__file__).resolve().parent / "data" / "marker_patches_size3.npy"
+        if (H, W) == (240, 320) and not eng.generic and baked.exists():
+            import numpy as np
+
+            eng.set_marker_patches(np.load(baked))
+            self._patches_ready = True
         if self.frame_transformer is not None:
             self.frame_transformer._initialize_impl()
             self.frame_transformer._is_initialized = True
+
+    # -- marker image / overlay (ref: fots_marker_sim.py:346-384; ball_rolling_taxim_fots.py:918-937) -----------------------
+    def set_patch_array(self, patch_array_dict: dict, marker_size: float = 3) -> None:
+        """Use the dot patches of the reference's ``generate_patch_array()`` for another marker size."""
+        import math
+
+        w = math.floor((marker_size - patch_array_dict["base_circle_radius"]) * patch_array_dict["super_resolution_ratio"])
+        self.engine.set_marker_patches(patch_array_dict["patch_array"][:, :, w])
+        self._patches_ready = True
+
+    def draw_markers_batch(self, marker_data: torch.Tensor | None = None) -> torch.Tensor:
+        """The marker image of EVERY env in one launch: (num_envs, H, W) uint8, what ``draw_markers(marker_data[i, 1])`` returns
+        per env in the reference."""
+        if not self._patches_ready:
+            raise RuntimeError("marker patches are not set (320 x 240 only): call set_patch_array(generate_patch_array())")
+        md = self.marker_data if marker_data is None else marker_data.to(self.engine.device, torch.float32).contiguous()
+        if self._marker_img is None or self._marker_img.shape[0] != md.shape[0]:
+            self._marker_img = torch.empty((md.shape[0], self.engine.H, self.engine.W), dtype=torch.uint8, device=self.engine.device)
+        self.engine.marker_overlay(md, marker_img_out=self._marker_img)
+        return self._marker_img
+
+    def overlay_markers(self, tactile_rgb: torch.Tensor, marker_data: torch.Tensor | None = None, rgb_u8_out: torch.Tensor | None = None) -> torch.Tensor:
+        """``tactile_rgb`` (num_envs, 240, 320, 3) float32 modulated IN PLACE by the marker image of every env -- the RL task's
+        per-env loop (draw_markers -> tensor -> ``rgb * 255 * (marker / 255) / 255``) as one launch; optionally also the uint8
+        observation."""
+        if not self._patches_ready:
+            raise RuntimeError("marker patches are not set (320 x 240 only): call set_patch_array(generate_patch_array())")
+        md = self.marker_data if marker_data is None else marker_data.to(self.engine.device, torch.float32).contiguous()
+        self.engine.marker_overlay(md, tactile_rgb, apply=True, rgb_out=tactile_rgb, rgb_u8_out=rgb_u8_out)
+        return tactile_rgb
 
     def _relative_yaw(self) -> torch.Tensor:
         """Yaw of the indenter relative to the sensor (ref: fots_marker_sim.py:147-159 via FrameTransformer);
