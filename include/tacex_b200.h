@@ -274,6 +274,11 @@ int tx_fem_debug_set_cycles(tx_fem* f, long long* cycles);
 int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const double* weights, const double* cam_R, const double* cam_t,
                        double fx, double fy, double cx, double cy);
 int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers);
+/* Tail of gen_marker_flow (ref: tactile_sensor_sapienipc_modified.py:404-408): normalize != 0 maps the pixel coordinates to
+ * uv / (img_w / 2) - 1; zero_all != 0: no marker survived the reference's uv mask (:382-387), the flow is all zeros. The mask
+ * itself and the padding to num_markers only depend on the REST positions: the host applies them to (tri, weights) once
+ * (tacex_b200/fem.py::reference_marker_tail) before tx_fem_set_markers. */
+int tx_fem_set_marker_output(tx_fem* f, int normalize, double img_w, int zero_all);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,8 @@ struct tx_fem {
     int* d_tri = nullptr;
     double* d_w = nullptr;
     double cam_R[9], cam_t[3], fx = 0, fy = 0, cx = 0, cy = 0;
+    int normalize = 0, zero_all = 0;
+    double half_w = 160.0;
 };
 
 static std::string g_fem_err;
@@ -308,6 +310,15 @@ extern "C" int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const do
     return TX_OK;
 }
 
+extern "C" int tx_fem_set_marker_output(tx_fem* f, int normalize, double img_w, int zero_all)
+{
+    if (!f || !(img_w > 0.0)) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_marker_output: bad argument");
+    f->normalize = normalize ? 1 : 0;
+    f->half_w = img_w / 2.0;
+    f->zero_all = zero_all ? 1 : 0;
+    return TX_OK;
+}
+
 extern "C" int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers)
 {
     if (!f || !x || !markers || N < 0) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_markers: bad argument");
@@ -319,6 +330,7 @@ extern "C" int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers)
     for (int i = 0; i < 9; ++i) m.cam_R[i] = f->cam_R[i];
     for (int i = 0; i < 3; ++i) m.cam_t[i] = f->cam_t[i];
     m.fx = f->fx; m.fy = f->fy; m.cx = f->cx; m.cy = f->cy;
+    m.normalize = f->normalize; m.half_w = f->half_w; m.zero_all = f->zero_all;
     FEM_CUDA(f, launch_fem_markers(m, N, f->stream));
     return TX_OK;
 }

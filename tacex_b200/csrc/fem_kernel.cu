@@ -1033,8 +1033,14 @@ __global__ void fem_marker_kernel(const FemMarkerArgs m)
                 pc[c] = m.cam_R[0 * 3 + c] * (pw[0] - m.cam_t[0]) + m.cam_R[1 * 3 + c] * (pw[1] - m.cam_t[1]) + m.cam_R[2 * 3 + c] * (pw[2] - m.cam_t[2]);
             const double u = m.fx * pc[0] / pc[2] + m.cx, vv = m.fy * pc[1] / pc[2] + m.cy;
             float* o = out + (size_t)which * m.M * 2;
-            o[0] = (float)u;
-            o[1] = (float)vv;
+            // the reference projects in float32 (Isaac Lab project_points) and post-processes in float64 (NumPy)
+            float uf = (float)u, vf = (float)vv;
+            if (m.normalize) {
+                uf = (float)((double)uf / m.half_w - 1.0);
+                vf = (float)((double)vf / m.half_w - 1.0);
+            }
+            o[0] = m.zero_all ? 0.0f : uf;
+            o[1] = m.zero_all ? 0.0f : vf;
         }
     }
 }

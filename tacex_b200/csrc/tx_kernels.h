@@ -183,6 +183,9 @@ struct FemMarkerArgs {
     const double* x;       // [N][V][3]
     float* out;            // [N][2][M][2]
     double cam_R[9], cam_t[3], fx, fy, cx, cy;
+    int normalize;         // ret /= img_w / 2; ret -= 1 (gen_marker_flow's `normalize`)
+    double half_w;
+    int zero_all;          // no marker survived the reference's uv mask: the flow is all zeros
 };
 
 size_t fem_smem_bytes(int V, int n_s);

@@ -137,9 +137,22 @@ class GelFemEngine:
         return [{k: getattr(s, k) for k, _ in _lib.TxFemStats._fields_} for s in arr]
 
     # -- FEM marker read-out (ManiSkill-ViTac style) ---------------------------------------------------------------------
-    def set_markers(self, tri: np.ndarray, weights: np.ndarray, cam_R=None, cam_t=(0.0, 0.0, 0.0285), intrinsics=(340.0, 325.0, 160.0, 125.0)):
+    def set_markers(self, tri: np.ndarray, weights: np.ndarray, cam_R=None, cam_t=(0.0, 0.0, 0.0285), intrinsics=(340.0, 325.0, 160.0, 125.0),
+                    reference_tail: bool = False, num_markers: int = 128, img_hw=(240, 320), normalize: bool = False):
+        """``reference_tail``: ``tri`` / ``weights`` hold the UNPADDED markers that lie on the surface; apply the rest of
+        ``gen_marker_flow`` -- uv mask on the initial positions (Q12), compaction, padding to ``num_markers`` -- once here
+        (it only depends on the rest positions) and ``normalize`` in the kernel."""
         tri = np.ascontiguousarray(tri, np.int32)
         w = np.ascontiguousarray(weights, np.float64)
+        zero_all = False
+        if reference_tail:
+            P = (np.asarray(self.mesh.X, np.float64)[tri] * w[..., None]).sum(1)
+            sel = reference_marker_tail(project_uv(P, cam_R, cam_t, intrinsics), num_markers, img_hw)
+            if sel.size == 0:
+                zero_all = True
+                sel = np.zeros(num_markers, np.int64)
+            tri, w = np.ascontiguousarray(tri[sel]), np.ascontiguousarray(w[sel])
+        self._check(self.lib.tx_fem_set_marker_output(self.h, int(bool(normalize)), float(img_hw[1]), int(zero_all)))
         R = np.ascontiguousarray(np.diag([1.0, -1.0, -1.0]) if cam_R is None else cam_R, np.float64)
         t = np.ascontiguousarray(cam_t, np.float64)
         fx, fy, cx, cy = intrinsics
@@ -211,6 +224,34 @@ def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=
     while len(out_tri) < pad_to:
         out_tri.append(out_tri[-1]); out_w.append(out_w[-1])
     return np.asarray(out_tri[:pad_to], np.int32), np.asarray(out_w[:pad_to], np.float64)
+
+
+def project_uv(P_world: np.ndarray, cam_R=None, cam_t=(0.0, 0.0, 0.0285), intrinsics=(340.0, 325.0, 160.0, 125.0)) -> np.ndarray:
+    """Pinhole projection of world points (K, 3) exactly as ``fem_marker_kernel`` does it (float64, rounded to float32)."""
+    R = np.diag([1.0, -1.0, -1.0]) if cam_R is None else np.asarray(cam_R, np.float64)
+    pc = (np.asarray(P_world, np.float64) - np.asarray(cam_t, np.float64)) @ R
+    fx, fy, cx, cy = intrinsics
+    return np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], -1).astype(np.float32)
+
+
+def reference_marker_tail(init_uv: np.ndarray, num_markers: int = 128, img_hw=(240, 320)) -> np.ndarray:
+    """Which markers ``gen_marker_flow`` returns, in which order (ref: tactile_sensor_sapienipc_modified.py:382-402, with the
+    preset's zero lose-tracking probability / noise): the uv mask on the INITIAL positions -- ``5 < u < H`` and ``5 < v < W``:
+    u is compared with the image HEIGHT and v with the WIDTH, the reference's axes are swapped, reproduced
+    --, compaction in order, then padding to ``num_markers`` by repeating the last survivor. Returns the (num_markers,) index
+    array into the unmasked marker list; no survivor -> an empty array (the reference itself raises there, :405; the product returns
+    an all-zero flow). More survivors than
+    ``num_markers`` makes the reference draw a RANDOM subset (np.random.choice): not reproducible, raises."""
+    H, W = img_hw
+    uv = np.asarray(init_uv)
+    keep = np.nonzero((uv[:, 0] > 5) & (uv[:, 0] < H) & (uv[:, 1] > 5) & (uv[:, 1] < W))[0]
+    if keep.size == 0:
+        return keep
+    if keep.size >= num_markers:
+        if keep.size == num_markers:
+            raise ValueError("the reference returns a random permutation when exactly num_markers markers survive")
+        raise ValueError("more surviving markers than num_markers: the reference draws a random subset")
+    return np.concatenate([keep, np.full(num_markers - keep.size, keep[-1])])
 
 
 class GelPadSim:
