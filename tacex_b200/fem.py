@@ -122,8 +122,19 @@ class GelFemEngine:
     def rest_aim(self, N: int) -> torch.Tensor:
         return self.X[torch.from_numpy(self.mesh.attach.astype(np.int64)).to(self.device)][None].repeat(N, 1, 1).contiguous()
 
+    def _chk_state(self, **tensors) -> None:
+        for name, t in tensors.items():
+            if not isinstance(t, torch.Tensor) or t.dtype != torch.float64 or t.device != self.device or not t.is_contiguous():
+                raise _lib.TxError(f"{name} must be a contiguous float64 tensor on {self.device}")
+
     def step(self, x, v, x_prev, aim, ind_prev: torch.Tensor, ind_next: torch.Tensor, want_stats: bool = True):
+        self._chk_state(x=x, v=v, x_prev=x_prev, aim=aim)
         N = x.shape[0]
+        if tuple(x.shape) != (N, self.V, 3) or v.shape != x.shape or x_prev.shape != x.shape or aim.shape[0] != N:
+            raise _lib.TxError("state tensors must have shape (N, V, 3), aim (N, A, 3)")
+        for ind in (ind_prev, ind_next):
+            if ind.dtype != torch.uint8 or ind.device != self.device or ind.numel() != N * C.sizeof(_lib.TxFemIndenter):
+                raise _lib.TxError("indenter arrays must be packed tx_fem_indenter records (fem.indenter_array) on the engine's device")
         st = torch.zeros((N, C.sizeof(_lib.TxFemStats)), dtype=torch.uint8, device=self.device) if want_stats else None
         self._check(self.lib.tx_fem_step(self.h, x.data_ptr(), v.data_ptr(), x_prev.data_ptr(), aim.data_ptr(),
                                          ind_prev.data_ptr(), ind_next.data_ptr(), N, None if st is None else st.data_ptr()))
@@ -161,6 +172,7 @@ class GelFemEngine:
         self.M = len(tri)
 
     def markers(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        self._chk_state(x=x)
         N = x.shape[0]
         out = torch.empty((N, 2, self.M, 2), device=self.device) if out is None else out
         self._check(self.lib.tx_fem_markers(self.h, x.data_ptr(), N, out.data_ptr()))

@@ -499,6 +499,10 @@ class ManiSkillSimulatorCfg(GelSightSimulatorCfg):
     camera_params: tuple = (340, 325, 160, 125, 0.0)
     tactile_img_res: tuple = (320, 240)
     marker_params: ManiSkillMarkerParams = field(default_factory=ManiSkillMarkerParams)
+    # not a reference field: where the sensor camera's optical axis meets the pad, in the pad frame [m]. The reference lays its
+    # marker grid out in the CAMERA frame (x in [-8.25, 16.5] mm) and reads the camera pose from the sensor's USD asset; headless
+    # it has to be stated. None = the legacy layout (a full 13 x 7 grid centred on the pad, no uv mask).
+    camera_origin_in_pad_frame: tuple | None = None
 
     def __post_init__(self):
         if self.simulation_approach_class is None:
@@ -530,9 +534,24 @@ class B200ManiSkillSimulator(GelSightSimulator):
                                     *self.cfg.marker_pos_shift_range, self.cfg.marker_random_noise,
                                     self.cfg.marker_lose_tracking_probability)):
             raise NotImplementedError("randomised marker grids are not implemented (all ranges are 0 in the reference presets)")
-        tri, w = marker_grid_weights(gel.mesh, pitch=self.cfg.marker_interval_range[0] * 1e-3, pad_to=self.cfg.marker_flow_size)
         fx, fy, cx, cy = self.cfg.camera_params[:4]
-        gel.engine.set_markers(tri, w, intrinsics=(fx, fy, cx, cy))
+        W, H = self.cfg.tactile_img_res
+        if self.cfg.camera_origin_in_pad_frame is None:
+            tri, w = marker_grid_weights(gel.mesh, pitch=self.cfg.marker_interval_range[0] * 1e-3, pad_to=self.cfg.marker_flow_size)
+            gel.engine.set_markers(tri, w, intrinsics=(fx, fy, cx, cy), normalize=self.cfg.normalize, img_hw=(H, W))
+        else:
+            # the reference's layout: its camera-frame grid (_gen_marker_grid), the markers that fall on the gel surface
+            # (_gen_marker_weight), then the uv mask / padding / normalize of gen_marker_flow
+            from .fem import reference_marker_grid
+
+            origin = np.asarray(self.cfg.camera_origin_in_pad_frame, np.float64)[:2]
+            pts = reference_marker_grid(self.cfg.marker_interval_range[0]) - origin
+            X = np.asarray(gel.mesh.X, np.float64)
+            lo, hi = X[:, :2].min(0), X[:, :2].max(0)
+            on = ((pts >= lo - 1e-12) & (pts <= hi + 1e-12)).all(1)
+            tri, w = marker_grid_weights(gel.mesh, pad_to=int(on.sum()), points_xy=pts[on])
+            gel.engine.set_markers(tri, w, cam_t=(origin[0], origin[1], 0.0285), intrinsics=(fx, fy, cx, cy), reference_tail=True,
+                                   num_markers=self.cfg.marker_flow_size, img_hw=(H, W), normalize=self.cfg.normalize)
         self.marker_data = torch.zeros((self._num_envs, 2, self.cfg.marker_flow_size, 2), device=gel.engine.device)
         self._indentation_depth = torch.zeros((self._num_envs,), device=gel.engine.device)
 
