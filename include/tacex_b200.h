@@ -280,6 +280,18 @@ int tx_fem_markers(tx_fem* f, const double* x, int N, float* markers);
  * (tacex_b200/fem.py::reference_marker_tail) before tx_fem_set_markers. */
 int tx_fem_set_marker_output(tx_fem* f, int normalize, double img_w, int zero_all);
 
+/* FEM gel surface -> sensor height map for every env in one launch (the reference reads the height map of a UIPC scene from the RTX
+ * depth camera and leaves the soft-body route as a TODO, ref: source/tacex/tacex/gelsight_sensor.py:581-598).
+ *   tx_fem_set_surface: HOST pointer, tris [n_tris][3] vertex ids of the gel's top surface
+ *   tx_fem_heightmap:   x DEVICE [N][V][3] -> height_mm DEVICE [N][H][W] float32: distance from the camera plane (z = cam_z_m in
+ *                       the pad frame, below the pad: -0.024) up to the deformed surface along the optical axis, in mm, clipped to
+ *                       [0, far_mm]; the image
+ *                       is an orthographic grid of pitch_m centred at (origin_x, origin_y) of the pad frame (the optical
+ *                       model's convention). Pixels no triangle covers hold far_mm. The result feeds tx_render directly. */
+int tx_fem_set_surface(tx_fem* f, int n_tris, const int32_t* tris);
+int tx_fem_heightmap(tx_fem* f, const double* x, int N, float* height_mm, int H, int W, double pitch_m, double origin_x, double origin_y,
+                     double cam_z_m, float far_mm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libtacex_b200.so"
-SOURCES = ["taxim_kernel.cu", "taxim_generic_kernel.cu", "taxim_shadow_kernel.cu", "fots_kernel.cu", "overlay_kernel.cu", "obs_gather_kernel.cu", "fem_kernel.cu", "tx_api.cu", "fem_api.cu"]
+SOURCES = ["taxim_kernel.cu", "taxim_generic_kernel.cu", "taxim_shadow_kernel.cu", "fots_kernel.cu", "overlay_kernel.cu", "raster_kernel.cu", "obs_gather_kernel.cu", "fem_kernel.cu", "tx_api.cu", "fem_api.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -29,6 +29,9 @@ struct tx_fem {
     double cam_R[9], cam_t[3], fx = 0, fy = 0, cx = 0, cy = 0;
     int normalize = 0, zero_all = 0;
     double half_w = 160.0;
+    // top-surface triangles for the height-map rasteriser
+    int n_top = 0;
+    int* d_top = nullptr;
 };
 
 static std::string g_fem_err;
@@ -241,7 +244,7 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     cudaFree(f->d_tets); cudaFree(f->d_attach); cudaFree(f->d_surf); cudaFree(f->d_Dm_inv); cudaFree(f->d_vol);
     cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_tsc); cudaFree(f->d_valg); cudaFree(f->d_xt); cudaFree(f->d_edge_off); cudaFree(f->d_edge_adj);
     cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
-    cudaFree(f->d_tri); cudaFree(f->d_w);
+    cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top);
     delete f;
 }
 
@@ -307,6 +310,35 @@ extern "C" int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const do
     for (int i = 0; i < 9; ++i) f->cam_R[i] = cam_R[i];
     for (int i = 0; i < 3; ++i) f->cam_t[i] = cam_t[i];
     f->fx = fx; f->fy = fy; f->cx = cx; f->cy = cy;
+    return TX_OK;
+}
+
+extern "C" int tx_fem_set_surface(tx_fem* f, int n_tris, const int32_t* tris)
+{
+    if (!f || n_tris <= 0 || !tris) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_surface: bad argument");
+    for (int i = 0; i < 3 * n_tris; ++i)
+        if (tris[i] < 0 || tris[i] >= f->cfg.V) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_surface: vertex index out of range");
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    cudaFree(f->d_top);
+    f->d_top = nullptr;
+    FEM_CUDA(f, cudaMalloc(&f->d_top, sizeof(int) * 3 * n_tris));
+    FEM_CUDA(f, cudaMemcpy(f->d_top, tris, sizeof(int) * 3 * n_tris, cudaMemcpyHostToDevice));
+    f->n_top = n_tris;
+    return TX_OK;
+}
+
+extern "C" int tx_fem_heightmap(tx_fem* f, const double* x, int N, float* height_mm, int H, int W, double pitch_m, double origin_x,
+                                double origin_y, double cam_z_m, float far_mm)
+{
+    if (!f || !x || !height_mm || N < 0 || H <= 0 || W <= 0 || !(pitch_m > 0.0) || !(far_mm > 0.0f))
+        return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_heightmap: bad argument");
+    if (f->n_top <= 0) return ffail(f, TX_ERR_STATE, "tx_fem_heightmap: call tx_fem_set_surface first");
+    if (N == 0) return TX_OK;
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    RasterArgs a{};
+    a.x = x; a.tris = f->d_top; a.hm = height_mm; a.V = f->cfg.V; a.n_tris = f->n_top; a.H = H; a.W = W;
+    a.pitch = pitch_m; a.ox = origin_x; a.oy = origin_y; a.cam_z = cam_z_m; a.far_mm = far_mm;
+    FEM_CUDA(f, launch_heightmap(a, N, f->stream));
     return TX_OK;
 }
 

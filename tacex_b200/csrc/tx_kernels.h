@@ -188,6 +188,18 @@ struct FemMarkerArgs {
     int zero_all;          // no marker survived the reference's uv mask: the flow is all zeros
 };
 
+// FEM gel surface -> height map (raster_kernel.cu)
+struct RasterArgs {
+    const double* x;     // [N][V][3] FEM positions
+    const int* tris;     // [n_tris][3] top-surface triangles
+    float* hm;           // [N][H][W] height map, mm
+    int V, n_tris, H, W;
+    double pitch, ox, oy; // pixel pitch [m], pad-frame position of the image centre
+    double cam_z;        // z of the camera plane in the pad frame [m]
+    float far_mm;        // far clipping plane [mm] (pixels no triangle covers)
+};
+cudaError_t launch_heightmap(const RasterArgs& a, int N, cudaStream_t s);
+
 size_t fem_smem_bytes(int V, int n_s);
 int fem_max_smem_edges(int V);
 int fem_threads();

@@ -171,6 +171,27 @@ class GelFemEngine:
                                                 fx, fy, cx, cy))
         self.M = len(tri)
 
+    # -- gel surface -> height map (the reference's TODO at gelsight_sensor.py:594-598) ---------------------------
+    def height_map(self, x: torch.Tensor, out: torch.Tensor | None = None, shape=(240, 320), pitch_m: float = 0.0295e-3 * 640 / 320,
+                   origin_xy=(0.0, 0.0), cam_z_m: float = -0.024, far_mm: float = 29.0) -> torch.Tensor:
+        """(N, H, W) float32 height map [mm] rasterised from the deformed top surface of every gel: the distance from the camera
+        plane to the surface along the optical axis, clipped to the far plane. The camera looks up through the pad from
+        ``cam_z_m`` = -24 mm (``gelpad_to_camera_min_distance`` below the pad's bottom, GelSight Mini preset): the undeformed
+        surface reads 28.5 mm, a 1 mm indentation 27.5 mm -- the values the depth camera reports for the indenter there.
+        Feeds ``TactileEngine.render`` directly."""
+        self._chk_state(x=x)
+        if not getattr(self, "_surface_set", False):
+            tt = np.ascontiguousarray(self.mesh.top_tris, np.int32)
+            self._check(self.lib.tx_fem_set_surface(self.h, len(tt), tt.ctypes.data))
+            self._surface_set = True
+        N, (H, W) = x.shape[0], shape
+        out = torch.empty((N, H, W), device=self.device) if out is None else out
+        if out.dtype != torch.float32 or out.device != self.device or not out.is_contiguous() or tuple(out.shape) != (N, H, W):
+            raise _lib.TxError("height map output must be a contiguous float32 (N, H, W) tensor on the engine's device")
+        self._check(self.lib.tx_fem_heightmap(self.h, x.data_ptr(), N, out.data_ptr(), H, W, float(pitch_m), float(origin_xy[0]),
+                                              float(origin_xy[1]), float(cam_z_m), float(far_mm)))
+        return out
+
     def markers(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         self._chk_state(x=x)
         N = x.shape[0]
