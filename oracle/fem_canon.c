@@ -556,6 +556,9 @@ static void inv3(const double* M, double* R)
     R[6] = (M[3] * M[7] - M[4] * M[6]) / det; R[7] = (M[1] * M[6] - M[0] * M[7]) / det; R[8] = (M[0] * M[4] - M[1] * M[3]) / det;
 }
 
+/* test hook: the block-Jacobi inverse of the restatement (pinned against muda's AnalyticalInverse, tests/test_fem_ref_pin_cpu.py) */
+void canon_inv3(const double* M, double* R) { inv3(M, R); }
+
 /* PCG with 3x3 block-Jacobi, x0 = 0, stop when |r.z| <= tol_rate * |r0.z0| (linear_pcg.cu:45-140) */
 static int pcg(const fem_ctx* c, const double* H9, const double* Hc, const double* Dg, const double* b, double* xs,
                double* r, double* z, double* p, double* Ap, double* Dinv)

@@ -34,6 +34,8 @@ struct Matrix {
     Matrix() { for (int i = 0; i < R * C; ++i) d[i] = T(0); }
     Matrix(T a, T b) { static_assert(R * C == 2, "size"); d[0] = a; d[1] = b; }
     Matrix(T a, T b, T c) { static_assert(R * C == 3, "size"); d[0] = a; d[1] = b; d[2] = c; }
+    T* data() { return d; }
+    const T* data() const { return d; }
     T& operator()(int i, int j) { return d[j * R + i]; }
     const T& operator()(int i, int j) const { return d[j * R + i]; }
     T& operator()(int i) { return d[i]; }

@@ -8,6 +8,9 @@
 //   finite_element/fem_utils.cu                                         Ds, Dm_inv, F = Ds Dm^-1, dFdx (9 x 12) of a tetrahedron
 //   (libuipc/include) uipc/constitution/conversion.h                    EP_to_lame, what ElasticModuli::youngs_poisson calls
 //                                                                       (src/constitution/elastic_moduli.cpp:20-27)
+//   (libuipc/external/muda) muda/ext/eigen/inverse/analytic_inverse.h   the 3 x 3 inverse of the block-Jacobi preconditioner
+//                                                                       (finite_element/fem_diag_preconditioner.cu:142-148 calls
+//                                                                       muda::eigen::inverse -> AnalyticalInverse for 3 x 3)
 // Eigen / muda are not in this image: oracle/ref_shim/ supplies a minimal stand-in (type_define.h, mini_eigen.h, a 2 x 2 evd) and
 // empty headers for the includes the compiled subset does not use. Built by oracle/Makefile into oracle/_ref/libuipc_sym.so (only
 // where /root/reference exists); used by tests/test_fem_ref_pin_cpu.py to pin oracle/fem_canon.c.
@@ -17,6 +20,7 @@
 
 #include <finite_element/fem_utils.cu> // Ds, Dm_inv, F, dFdx (9 x 12): plain functions, host-compilable
 #include <cstdlib>
+#include <muda/ext/eigen/inverse/analytic_inverse.h> // the real muda file (found through -I$(MUDA_SRC)), host-compilable
 namespace uipc::backend::cuda { // mentioned by fem_utils.cu's invariant helpers, never called by the pin tests
 Float ddot(const Matrix3x3&, const Matrix3x3&) { std::abort(); }
 void svd(const Matrix3x3&, Matrix3x3&, Vector3&, Matrix3x3&) noexcept { std::abort(); }
@@ -131,3 +135,11 @@ void ref_tan_basis(const double* N, double* e1, double* e2)
 }
 
 } // extern "C"
+
+extern "C" void ref_inverse3(const double* m_colmajor, double* out_colmajor)
+{
+    Eigen::Matrix<double, 3, 3> a;
+    for (int i = 0; i < 9; ++i) a.data()[i] = m_colmajor[i];
+    const Eigen::Matrix<double, 3, 3> r = muda::eigen::AnalyticalInverse{}(a);
+    for (int i = 0; i < 9; ++i) out_colmajor[i] = r.data()[i];
+}

@@ -184,3 +184,23 @@ def test_per_tet_assembly_matches_reference_fem_utils_and_constitution(ref, cano
         A_ref = np.diag(M) + s * (P.T @ Hspd @ P)
         assert np.abs(-b - G_ref).max() <= 1e-9 * np.abs(G_ref).max()
         assert np.abs(A - A_ref).max() <= 1e-9 * np.abs(A_ref).max()
+
+
+def test_block_jacobi_inverse_matches_muda_analytic_inverse(ref, canon):
+    """The 3 x 3 inverse of the block-Jacobi preconditioner: the reference calls muda::eigen::inverse, i.e. muda's AnalyticalInverse
+    (fem_diag_preconditioner.cu:142-148; external/muda/src/muda/ext/eigen/inverse/analytic_inverse.h, compiled unmodified), the
+    restatement its own adjugate formula (fem_canon.c::inv3). SPD diagonal blocks as the assembly produces them (mass + stiffness,
+    condition numbers up to ~1e6)."""
+    rng = np.random.default_rng(5)
+    for k in range(200):
+        q = _rot(rng)
+        ev = 10.0 ** rng.uniform(-6, 0, 3) * (1.0 if k % 2 else 1e4)
+        A = (q * ev) @ q.T
+        A = 0.5 * (A + A.T)
+        r_ref, r_me = np.empty(9), np.empty(9)
+        ref.ref_inverse3(_d(np.ascontiguousarray(A.T.reshape(-1))), _d(r_ref))  # column-major in, column-major out
+        canon.canon_inv3(_d(np.ascontiguousarray(A.reshape(-1))), _d(r_me))     # row-major (symmetric: the same)
+        R_ref, R_me = r_ref.reshape(3, 3).T, r_me.reshape(3, 3)
+        scale = np.abs(R_ref).max()
+        assert np.abs(R_ref - R_me).max() <= 1e-9 * scale
+        assert np.abs(R_me @ A - np.eye(3)).max() <= 1e-6
