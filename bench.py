@@ -489,6 +489,11 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa_node(local)
+    # stdout carries exactly ONE JSON line: everything a library prints to file descriptor 1 while the bench runs (NCCL's version
+    # banner, for one) goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own banner / debug output (stdout by default) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -726,7 +731,8 @@ def main() -> None:
                                                            "sample": sample}
         if config4 is not None:
             line["config4"] = config4
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
