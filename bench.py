@@ -344,11 +344,17 @@ class StepRunner:
         self.markers = torch.empty((E, 2, M, 2), device=dev)
         self.traj0 = torch.zeros((E, 4), device=dev)
         self.traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
-        self.do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl")
+        self.do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl", "u8")
+        self.u8 = world > 1 and args.obs_gather == "u8"
         self.use_rects = args.obs_gather == "fp32-rect" or (args.obs_gather == "fp32" and world > 2)
         self.rgb_buf = [rgb, torch.empty_like(rgb)] if self.do_gather else [rgb]
         self.peer, self.gathered, self.gather_kind = None, None, "n/a"
-        if self.do_gather:
+        if self.u8:
+            self.peer = PeerObsGather(rgb.shape, torch.uint8, dev, n_slots=2, with_rects=False, multicast=False)
+            self.rgb_buf = [rgb, rgb]  # float32 frames stay local; the uint8 copy is what travels
+            self.gather_kind = ("uint8 all-gather of RGB (round(rgb * 255), one extra conversion kernel per step) by NVLink peer copies into "
+                                "symmetric memory (copy engines), overlapped with the next step")
+        elif self.do_gather:
             if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
                 try:
                     self.peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=self.use_rects,
@@ -389,11 +395,15 @@ class StepRunner:
             self.eng.set_rect_output(self.peer.local_rects(i))
         self.eng.render(self.hm_sets[k], None, out=self.rgb_buf[i], depth_out=self.depth)
         self.eng.fots_markers(self.depth, self.theta, self.traj0, self.traj_len, out=self.markers)
+        if self.u8:
+            self.eng.marker_overlay(None, self.rgb_buf[i], apply=False, rgb_u8_out=self.peer.local_block(i))
         if self.do_gather:
             self.ev_done[i].record()
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.ev_done[i])
-                if self.peer is not None and self.use_rects:
+                if self.u8:
+                    self.peer.gather(self.peer.local_block(i), i)
+                elif self.peer is not None and self.use_rects:
                     self.peer.gather_rects(self.eng, i, self.side)
                 elif self.peer is not None:
                     self.peer.gather(self.rgb_buf[i], i)
@@ -422,6 +432,11 @@ class StepRunner:
         ref = torch.empty((self.E, H, W, 3), device=self.dev)
         self.eng.set_rect_output(None)
         self.eng.render(remote_sets_fn(r)[k], None, out=ref)
+        if self.u8:
+            ref8 = torch.empty((self.E, H, W, 3), device=self.dev, dtype=torch.uint8)
+            self.eng.marker_overlay(None, ref, apply=False, rgb_u8_out=ref8)
+            torch.cuda.synchronize()
+            return bool(torch.equal(full[r * self.E:(r + 1) * self.E], ref8))
         torch.cuda.synchronize()
         own = torch.equal(full[self.rank * self.E:(self.rank + 1) * self.E], self.rgb_buf[slot])
         return bool(own and torch.equal(full[r * self.E:(r + 1) * self.E], ref))
@@ -459,12 +474,14 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "fp32-rect", "fp32-ce", "nccl", "none"],
+    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "fp32-rect", "fp32-ce", "nccl", "u8", "none"],
                     help="N>1: float32 all-gather of the RGB observation into symmetric memory (falls back to NCCL). "
                          "fp32-rect = NVLink peer stores of the non-flat rectangle of every frame + local completion from the flat "
                          "image (bit-identical to gathering whole frames, about half the link bytes); fp32-ce = whole frames by "
                          "copy-engine peer copies (no SM used); fp32 = fp32-ce for 2 GPUs (one peer: the link is not the limit), "
-                         "fp32-rect beyond; nccl = all_gather_into_tensor; none = observations stay sharded")
+                         "fp32-rect beyond; nccl = all_gather_into_tensor; u8 = the observation converted to uint8 by one extra "
+                         "kernel (tx_marker_overlay) and gathered by copy-engine peer copies: a quarter of the link bytes (reported "
+                         "alongside the mandated float32 gather, SURVEY 8e); none = observations stay sharded")
     ap.add_argument("--no-multicast", action="store_true", help="fp32-rect: one store per peer instead of NVSwitch multicast stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fem", action="store_true", help="skip the gel-FEM measurements (config 3 / config 4)")

@@ -10,6 +10,7 @@
 // One CTA per env; the canvas lives in shared memory; optional uint8 outputs (the marker image itself, and the overlaid RGB
 // rounded to uint8 -- 4 x fewer bytes for the observation transport).
 #include "tx_kernels.h"
+#include <stdint.h>
 
 namespace tx {
 
@@ -61,8 +62,31 @@ __global__ void __launch_bounds__(OV_THREADS) marker_overlay_kernel(const Overla
     }
 }
 
+// plain float32 -> uint8 conversion of the observation (no marker image): elementwise, 16 floats per thread and iteration
+__global__ void __launch_bounds__(256) rgb_to_u8_kernel(const float4* __restrict__ in, uint4* __restrict__ out, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = __ldg(in + 4 * i + k);
+            const unsigned b0 = (unsigned)__float2int_rn(fminf(fmaxf(__fmul_rn(v.x, 255.0f), 0.0f), 255.0f));
+            const unsigned b1 = (unsigned)__float2int_rn(fminf(fmaxf(__fmul_rn(v.y, 255.0f), 0.0f), 255.0f));
+            const unsigned b2 = (unsigned)__float2int_rn(fminf(fmaxf(__fmul_rn(v.z, 255.0f), 0.0f), 255.0f));
+            const unsigned b3 = (unsigned)__float2int_rn(fminf(fmaxf(__fmul_rn(v.w, 255.0f), 0.0f), 255.0f));
+            w[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 cudaError_t launch_marker_overlay(const OverlayArgs& a, int N, cudaStream_t s)
 {
+    if (a.M == 0 && !a.apply && !a.marker_img && !a.rgb && a.rgb_u8 && !((uintptr_t)a.rgb_in & 15u) && !((uintptr_t)a.rgb_u8 & 15u)) {
+        const size_t n16 = (size_t)N * IMG_H * IMG_W * 3 / 16;
+        rgb_to_u8_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(a.rgb_in), reinterpret_cast<uint4*>(a.rgb_u8), n16);
+        return cudaGetLastError();
+    }
     static bool attr_dev[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;
