@@ -289,6 +289,13 @@ int tx_fem_set_marker_output(tx_fem* f, int normalize, double img_w, int zero_al
  *                       is an orthographic grid of pitch_m centred at (origin_x, origin_y) of the pad frame (the optical
  *                       model's convention). Pixels no triangle covers hold far_mm. The result feeds tx_render directly. */
 int tx_fem_set_surface(tx_fem* f, int n_tris, const int32_t* tris);
+
+/* Isaac x UIPC attachment, per-step part (ref: source/tacex_uipc/tacex_uipc/sim/uipc_attachments.py:388-428 _compute_aim_positions +
+ * the animator callback :364-386): aim positions of the attached vertices = R(quat) * offset + pos of the rigid body (sensor case) they
+ * hang on, for every env in one launch. pose DEVICE [N][7] float32 (x y z, quaternion w x y z), offsets DEVICE float32 [A][3] (shared)
+ * or [N][A][3] (per_env_offsets != 0): the attachment points in the body frame (host, once: tacex_b200/fem.py::
+ * compute_attachment_data, ref :247-350), aim DEVICE [N][A][3] float64 = the `aim` argument of tx_fem_step. */
+int tx_fem_attachment_aim(tx_fem* f, const float* pose, const float* offsets, int N, int per_env_offsets, double* aim);
 int tx_fem_heightmap(tx_fem* f, const double* x, int N, float* height_mm, int H, int W, double pitch_m, double origin_x, double origin_y,
                      double cam_z_m, float far_mm);
 

@@ -313,6 +313,16 @@ extern "C" int tx_fem_set_markers(tx_fem* f, int M, const int32_t* tri, const do
     return TX_OK;
 }
 
+extern "C" int tx_fem_attachment_aim(tx_fem* f, const float* pose, const float* offsets, int N, int per_env_offsets, double* aim)
+{
+    if (!f || !pose || !offsets || !aim || N < 0) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_attachment_aim: bad argument");
+    if (f->cfg.A <= 0) return ffail(f, TX_ERR_STATE, "tx_fem_attachment_aim: the mesh has no attached vertices");
+    if (N == 0) return TX_OK;
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    FEM_CUDA(f, launch_attachment_aim(pose, offsets, N, f->cfg.A, per_env_offsets ? 1 : 0, aim, f->stream));
+    return TX_OK;
+}
+
 extern "C" int tx_fem_set_surface(tx_fem* f, int n_tris, const int32_t* tris)
 {
     if (!f || n_tris <= 0 || !tris) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_surface: bad argument");

@@ -59,6 +59,45 @@ __global__ void __launch_bounds__(128) heightmap_raster_kernel(const RasterArgs 
     }
 }
 
+// ---- Isaac x UIPC attachment: per-step aim positions of the attached gel vertices -----------------------------------------------
+// ref: source/tacex_uipc/tacex_uipc/sim/uipc_attachments.py:388-428 (_compute_aim_positions): aim = transform_points(offsets, pos, quat)
+// = R(quat) offset + pos in float32 (Isaac Lab's matrix_from_quat: two_s = 2 / |q|^2, the pytorch3d formula), handed to the solver
+// as float64. The reference does this for ONE body with a torch -> NumPy -> python-callback round trip per step; here one launch
+// serves every env. pose [N][7] = position xyz + quaternion wxyz (what the reference slices from the PhysX view).
+__global__ void __launch_bounds__(128) attachment_aim_kernel(const float* __restrict__ pose, const float* __restrict__ offsets, int A,
+                                                             int per_env_offsets, double* __restrict__ aim)
+{
+    const int env = blockIdx.x;
+    const float* p = pose + (size_t)env * 7;
+    const float r = p[3], i = p[4], j = p[5], k = p[6];
+    const float two_s = __fdiv_rn(2.0f, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(i, i)), __fmul_rn(j, j)), __fmul_rn(k, k)));
+    float R[9];
+    R[0] = __fadd_rn(1.0f, -__fmul_rn(two_s, __fadd_rn(__fmul_rn(j, j), __fmul_rn(k, k))));
+    R[1] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, j), -__fmul_rn(k, r)));
+    R[2] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, k), __fmul_rn(j, r)));
+    R[3] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, j), __fmul_rn(k, r)));
+    R[4] = __fadd_rn(1.0f, -__fmul_rn(two_s, __fadd_rn(__fmul_rn(i, i), __fmul_rn(k, k))));
+    R[5] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(j, k), -__fmul_rn(i, r)));
+    R[6] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(i, k), -__fmul_rn(j, r)));
+    R[7] = __fmul_rn(two_s, __fadd_rn(__fmul_rn(j, k), __fmul_rn(i, r)));
+    R[8] = __fadd_rn(1.0f, -__fmul_rn(two_s, __fadd_rn(__fmul_rn(i, i), __fmul_rn(j, j))));
+    const float* off = offsets + (per_env_offsets ? (size_t)env * A * 3 : 0);
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const float ox = off[3 * a], oy = off[3 * a + 1], oz = off[3 * a + 2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3 * c], ox), __fmul_rn(R[3 * c + 1], oy)), __fmul_rn(R[3 * c + 2], oz)), p[c]);
+            aim[((size_t)env * A + a) * 3 + c] = (double)v;
+        }
+    }
+}
+
+cudaError_t launch_attachment_aim(const float* pose, const float* offsets, int N, int A, int per_env_offsets, double* aim, cudaStream_t s)
+{
+    attachment_aim_kernel<<<N, 128, 0, s>>>(pose, offsets, A, per_env_offsets, aim);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_heightmap(const RasterArgs& a, int N, cudaStream_t s)
 {
     const size_t n = (size_t)N * a.H * a.W;

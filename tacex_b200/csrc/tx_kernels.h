@@ -199,6 +199,7 @@ struct RasterArgs {
     float far_mm;        // far clipping plane [mm] (pixels no triangle covers)
 };
 cudaError_t launch_heightmap(const RasterArgs& a, int N, cudaStream_t s);
+cudaError_t launch_attachment_aim(const float* pose, const float* offsets, int N, int A, int per_env_offsets, double* aim, cudaStream_t s);
 
 size_t fem_smem_bytes(int V, int n_s);
 int fem_max_smem_edges(int V);

@@ -171,6 +171,22 @@ class GelFemEngine:
                                                 fx, fy, cx, cy))
         self.M = len(tri)
 
+    # -- Isaac x UIPC attachment, per-step aim positions (ref: uipc_attachments.py:388-428) -----------------------------------
+    def attachment_aim(self, pose: torch.Tensor, offsets: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """aim (N, A, 3) float64 = R(quat) offsets + pos for every env: ``pose`` (N, 7) float32 (xyz + quaternion wxyz of the body
+        the gel hangs on), ``offsets`` (A, 3) or (N, A, 3) float32 body-frame attachment points (:func:`compute_attachment_data`)."""
+        for t in (pose, offsets):
+            if t.dtype != torch.float32 or t.device != self.device or not t.is_contiguous():
+                raise _lib.TxError("pose / offsets must be contiguous float32 tensors on the engine's device")
+        N = pose.shape[0]
+        per_env = offsets.dim() == 3
+        if tuple(pose.shape) != (N, 7) or tuple(offsets.shape[-2:]) != (self.A, 3) or (per_env and offsets.shape[0] != N):
+            raise _lib.TxError("pose must be (N, 7), offsets (A, 3) or (N, A, 3) with A = the mesh's attached vertices")
+        out = torch.empty((N, self.A, 3), dtype=torch.float64, device=self.device) if out is None else out
+        self._chk_state(aim=out)
+        self._check(self.lib.tx_fem_attachment_aim(self.h, pose.data_ptr(), offsets.data_ptr(), N, int(per_env), out.data_ptr()))
+        return out
+
     # -- gel surface -> height map (SURVEY 8f-1; the reference's TODO at gelsight_sensor.py:594-598) ---------------------------
     def height_map(self, x: torch.Tensor, out: torch.Tensor | None = None, shape=(240, 320), pitch_m: float = 0.0295e-3 * 640 / 320,
                    origin_xy=(0.0, 0.0), cam_z_m: float = -0.024, far_mm: float = 29.0) -> torch.Tensor:
@@ -257,6 +273,39 @@ def marker_grid_weights(mesh: GelMesh, pitch=2.0625e-3, rows=7, cols=13, pad_to=
     while len(out_tri) < pad_to:
         out_tri.append(out_tri[-1]); out_w.append(out_w[-1])
     return np.asarray(out_tri[:pad_to], np.int32), np.asarray(out_w[:pad_to], np.float64)
+
+
+def quat_rotate_inverse_f32(q_wxyz: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Isaac Lab's ``quat_apply_inverse`` in float32 (ref call: uipc_attachments.py:322-325): v - 2 w (q x v) + 2 q x (q x v)."""
+    q = np.asarray(q_wxyz, np.float32)
+    v = np.asarray(v, np.float32)
+    w, xyz = q[0], q[1:]
+    t = np.cross(xyz, v).astype(np.float32) * np.float32(2.0)
+    return (v - w * t + np.cross(xyz, t).astype(np.float32)).astype(np.float32)
+
+
+def compute_attachment_data(tet_points: np.ndarray, body_pos, body_quat_wxyz, body_half_extents, sphere_radius: float = 5e-4,
+                            max_dist: float = 1e-5):
+    """Which gel vertices hang on the rigid body (the sensor case) and where they sit in its frame -- the init-time half of
+    ``UipcIsaacAttachments`` (ref: uipc_attachments.py:247-350). The reference asks PhysX whether a sphere of ``sphere_radius``
+    swept by ``max_dist`` around each vertex touches the body's collider; headless the collider is the body's BOX (centre
+    ``body_pos``, orientation ``body_quat_wxyz``, ``body_half_extents``): a vertex is attached iff its distance to the box is at
+    most ``sphere_radius + max_dist``. Returns (offsets (A, 3) float32 in the body frame = quat_apply_inverse(q, v - pos) as the
+    reference computes them, idx (A,) int32)."""
+    P = np.asarray(tet_points, np.float64)
+    pos = np.asarray(body_pos, np.float64)
+    q = np.asarray(body_quat_wxyz, np.float64)
+    w, x, y, z = q / np.linalg.norm(q)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    local = (P - pos) @ R  # R^T (p - pos)
+    d = np.abs(local) - np.asarray(body_half_extents, np.float64)
+    dist = np.linalg.norm(np.maximum(d, 0.0), axis=1) + np.minimum(d.max(1), 0.0)
+    idx = np.nonzero(dist <= sphere_radius + max_dist)[0].astype(np.int32)
+    offs = np.stack([quat_rotate_inverse_f32(np.asarray(body_quat_wxyz, np.float32), (P[i] - pos).astype(np.float32)) for i in idx]) \
+        if idx.size else np.zeros((0, 3), np.float32)
+    return offs.astype(np.float32), idx
 
 
 def project_uv(P_world: np.ndarray, cam_R=None, cam_t=(0.0, 0.0, 0.0285), intrinsics=(340.0, 325.0, 160.0, 125.0)) -> np.ndarray:
