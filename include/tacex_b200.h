@@ -102,6 +102,10 @@ int tx_upload_tables(tx_handle* h, const float* poly_grad, const float* backgrou
 /* Replaces TaximSimulator.compute_indentation_depth (ref: .../gpu_taxim/taxim_sim.py:115-131).
  *   height_mm [N][H][W] -> depth_mm [N] */
 int tx_indentation_depth(tx_handle* h, const float* height_mm, int N, float* depth_mm);
+/* The same for height maps at the CAMERA resolution (any number of pixels per frame): the reference computes the indentation depth
+ * from the camera-resolution map even when the optical model runs on a resized one (taxim_sim.py:115-131 reads
+ * sensor._data.output["height_map"]). IEEE division by 1000, like the reference on the CPU. */
+int tx_indentation_depth_frames(tx_handle* h, const float* frames_mm, int N, int pixels_per_frame, float* depth_mm);
 
 /* Replaces TaximTorch.render_direct(with_shadow=False, press_depth=...) + the NHWC copy
  * (ref: .../gpu_taxim/sim/taxim_torch.py:174-195, 225-258, 432-503; .../gpu_taxim/taxim_sim.py:104-111).
@@ -181,6 +185,13 @@ int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* 
  *   markers  [N][2][M][2]   [:,0] initial, [:,1] current marker (x, y) in pixels */
 int tx_fots_markers(tx_handle* h, const float* press_mm, const float* theta, int N, float* traj0, int32_t* traj_len,
                     float* markers);
+
+/* Replaces the F.resize of TaximSimulator.optical_simulation / FOTSMarkerSimulator.marker_motion_simulation when the sensor camera
+ * is FINER than the tactile image (ref: .../gpu_taxim/taxim_sim.py:88-89, .../fots/fots_marker_sim.py:121-122): torchvision's
+ * antialiased bilinear resize, bit-identical to torch.nn.functional.interpolate(mode="bilinear", antialias=True).
+ *   src [N][Hi][Wi] -> dst [N][H][W] (the handle's tactile shape); scales that need more than 8 taps per axis: TX_ERR_UNSUPPORTED.
+ * (A camera COARSER than the tactile image is resized inside the render kernel: tx_set_camera_resolution / tx_render_camera.) */
+int tx_resize(tx_handle* h, const float* src, int N, int Hi, int Wi, float* dst);
 
 /* Replaces FOTSMarkerSimulator.draw_markers and the per-env marker-overlay loop of the reference's RL task
  * (ref: .../fots/fots_marker_sim.py:346-384; source/tacex_tasks/tacex_tasks/ball_rolling_tactile/ball_rolling_taxim_fots.py:918-937),

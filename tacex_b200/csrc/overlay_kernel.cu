@@ -99,4 +99,33 @@ cudaError_t launch_marker_overlay(const OverlayArgs& a, int N, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ---- antialiased bilinear resize of the height map (camera FINER than the tactile image) -----------------------------------------
+// ref: TaximSimulator.optical_simulation, taxim_sim.py:88-89 (torchvision F.resize = aten's separable antialias kernel): float32
+// weights (host, tx_api.cu), horizontal pass then vertical pass, each acc = w[0] x[0]; acc = fmaf(w[k], x[k], acc). One thread per
+// output pixel evaluates the (at most 8 x 8) taps directly -- every intermediate row value is computed with exactly the arithmetic of
+// the two-pass form, so the result is bit-identical to it (and to torch) without a temporary plane in HBM.
+__global__ void __launch_bounds__(256) resize_aa_kernel(const ResizeArgs a)
+{
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y, n = blockIdx.z;
+    if (X >= a.Wo) return;
+    const int fx = __ldg(a.fx + X), cx = __ldg(a.cx + X), fy = __ldg(a.fy + Y), cy = __ldg(a.cy + Y);
+    const float* wx = a.wx + X * TX_RS_TAPS;
+    const float* wy = a.wy + Y * TX_RS_TAPS;
+    const float* s = a.src + ((size_t)n * a.Hi + fy) * a.Wi + fx;
+    float acc = 0.0f;
+    for (int j = 0; j < cy; ++j) {
+        const float* sp = s + (size_t)j * a.Wi;
+        float t = __fmul_rn(__ldg(wx), __ldg(sp));
+        for (int k = 1; k < cx; ++k) t = __fmaf_rn(__ldg(wx + k), __ldg(sp + k), t);
+        acc = j == 0 ? __fmul_rn(__ldg(wy), t) : __fmaf_rn(__ldg(wy + j), t, acc);
+    }
+    a.dst[((size_t)n * a.Ho + Y) * a.Wo + X] = acc;
+}
+
+cudaError_t launch_resize_aa(const ResizeArgs& a, int N, cudaStream_t s)
+{
+    resize_aa_kernel<<<dim3((a.Wo + 255) / 256, a.Ho, N), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 } // namespace tx

@@ -19,6 +19,9 @@ struct tx_handle {
     bool have_tables = false;
     // device tables
     float4* d_poly = nullptr; // [nb][nb][20]  (generic / shadow kernels)
+    int rs_Hi = 0, rs_Wi = 0;          // tx_resize: tables of the last source shape
+    int* d_rsa_i = nullptr;
+    float* d_rsa_w = nullptr;
     unsigned char* d_patch = nullptr; // [10][10][12][12] marker dot patches (tx_set_marker_patches)
     float4* d_poly128 = nullptr; // [nb][nb][32] the same records padded to one 128-byte line each (fused 240 x 320 kernel)
     float* d_bg = nullptr;    // [H][W][3]
@@ -206,7 +209,7 @@ extern "C" void tx_destroy(tx_handle* h)
     cudaFree(h->d_taps);
     cudaFree(h->d_sh_table); cudaFree(h->d_sh_cos); cudaFree(h->d_sh_sin); cudaFree(h->d_sh_taps); cudaFree(h->d_sh_def);
     cudaFree(h->d_sh_img); cudaFree(h->d_sh_t1); cudaFree(h->d_sh_t2); cudaFree(h->d_sh_mask);
-    cudaFree(h->d_patch);
+    cudaFree(h->d_patch); cudaFree(h->d_rsa_i); cudaFree(h->d_rsa_w);
     cudaFree(h->d_poly); cudaFree(h->d_poly128); cudaFree(h->d_bg); cudaFree(h->d_gel); cudaFree(h->d_flat); cudaFree(h->d_mx); cudaFree(h->d_my);
     cudaFree(h->d_aux_sums); cudaFree(h->d_aux_bmax); cudaFree(h->d_aux_b); cudaFree(h->d_aux_m);
     cudaFree(h->d_rs_x0); cudaFree(h->d_rs_y0); cudaFree(h->d_rs_wx); cudaFree(h->d_rs_wy); cudaFree(h->d_up);
@@ -305,6 +308,19 @@ extern "C" int tx_indentation_depth(tx_handle* h, const float* height_mm, int N,
     else
         TX_CUDA(h, launch_indentation_depth(height_mm, depth_mm, N, h->cfg.gelpad_height_m, h->cfg.gelpad_to_cam_min_m,
                                             h->stream));
+    h->ctr.depth_calls++;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+extern "C" int tx_indentation_depth_frames(tx_handle* h, const float* frames_mm, int N, int pixels_per_frame, float* depth_mm)
+{
+    if (!h || !frames_mm || !depth_mm || N < 0 || pixels_per_frame <= 0)
+        return fail(h, TX_ERR_INVALID_ARG, "tx_indentation_depth_frames: bad argument");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    TX_CUDA(h, launch_indentation_depth_generic(frames_mm, depth_mm, N, pixels_per_frame, h->cfg.gelpad_height_m,
+                                                h->cfg.gelpad_to_cam_min_m, h->stream));
     h->ctr.depth_calls++;
     h->ctr.kernels_launched++;
     return TX_OK;
@@ -627,6 +643,69 @@ extern "C" int tx_fots_markers(tx_handle* h, const float* press_mm, const float*
     f.theta_max = h->cfg.theta_max_rad;
     TX_CUDA(h, launch_fots(f, N, h->stream));
     h->ctr.fots_calls++;
+    h->ctr.kernels_launched++;
+    return TX_OK;
+}
+
+// aten's antialias weights for one axis (UpSampleKernel.cpp, _compute_indices_min_size_weights_aa; float32 arithmetic), any scale
+// with at most TX_RS_TAPS taps (down-sampling by up to 3.5 x)
+static bool resize_table_aa(int in_size, int out_size, std::vector<int>& first, std::vector<int>& count, std::vector<float>& w)
+{
+    const float scale = (float)in_size / (float)out_size;
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    first.resize(out_size); count.resize(out_size); w.assign((size_t)out_size * TX_RS_TAPS, 0.0f);
+    for (int i = 0; i < out_size; ++i) {
+        const float center = scale * ((float)i + 0.5f);
+        long xmin = (long)(center - support + 0.5f);
+        if (xmin < 0) xmin = 0;
+        long xmax = (long)(center + support + 0.5f);
+        if (xmax > in_size) xmax = in_size;
+        const int n = (int)(xmax - xmin);
+        if (n < 1 || n > TX_RS_TAPS) return false;
+        float wd[TX_RS_TAPS], tot = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            float x = ((float)(j + xmin) - center + 0.5f) * invscale;
+            if (x < 0) x = -x;
+            wd[j] = x < 1.0f ? 1.0f - x : 0.0f;
+            tot += wd[j];
+        }
+        first[i] = (int)xmin;
+        count[i] = n;
+        for (int j = 0; j < n; ++j) w[(size_t)i * TX_RS_TAPS + j] = wd[j] / tot;
+    }
+    return true;
+}
+
+extern "C" int tx_resize(tx_handle* h, const float* src, int N, int Hi, int Wi, float* dst)
+{
+    if (!h || !src || !dst || N < 0 || Hi <= 0 || Wi <= 0) return fail(h, TX_ERR_INVALID_ARG, "tx_resize: bad argument");
+    if (N == 0) return TX_OK;
+    TX_CUDA(h, cudaSetDevice(h->device));
+    const int Ho = h->cfg.H, Wo = h->cfg.W;
+    if (h->rs_Hi != Hi || h->rs_Wi != Wi) {
+        std::vector<int> fx, cx, fy, cy;
+        std::vector<float> wx, wy;
+        if (!resize_table_aa(Wi, Wo, fx, cx, wx) || !resize_table_aa(Hi, Ho, fy, cy, wy))
+            return fail(h, TX_ERR_UNSUPPORTED, "tx_resize: scale needs more than 8 taps per axis");
+        TX_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_rsa_i); cudaFree(h->d_rsa_w);
+        h->d_rsa_i = nullptr; h->d_rsa_w = nullptr;
+        TX_CUDA(h, cudaMalloc(&h->d_rsa_i, sizeof(int) * 2 * (Wo + Ho)));
+        TX_CUDA(h, cudaMalloc(&h->d_rsa_w, sizeof(float) * TX_RS_TAPS * (Wo + Ho)));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_i, fx.data(), sizeof(int) * Wo, cudaMemcpyHostToDevice));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_i + Wo, cx.data(), sizeof(int) * Wo, cudaMemcpyHostToDevice));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_i + 2 * Wo, fy.data(), sizeof(int) * Ho, cudaMemcpyHostToDevice));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_i + 2 * Wo + Ho, cy.data(), sizeof(int) * Ho, cudaMemcpyHostToDevice));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_w, wx.data(), sizeof(float) * TX_RS_TAPS * Wo, cudaMemcpyHostToDevice));
+        TX_CUDA(h, cudaMemcpy(h->d_rsa_w + (size_t)TX_RS_TAPS * Wo, wy.data(), sizeof(float) * TX_RS_TAPS * Ho, cudaMemcpyHostToDevice));
+        h->rs_Hi = Hi; h->rs_Wi = Wi;
+    }
+    ResizeArgs a{};
+    a.src = src; a.dst = dst; a.Hi = Hi; a.Wi = Wi; a.Ho = Ho; a.Wo = Wo;
+    a.fx = h->d_rsa_i; a.cx = h->d_rsa_i + Wo; a.fy = h->d_rsa_i + 2 * Wo; a.cy = h->d_rsa_i + 2 * Wo + Ho;
+    a.wx = h->d_rsa_w; a.wy = h->d_rsa_w + (size_t)TX_RS_TAPS * Wo;
+    TX_CUDA(h, launch_resize_aa(a, N, h->stream));
     h->ctr.kernels_launched++;
     return TX_OK;
 }

@@ -142,6 +142,17 @@ struct OverlayArgs {
 };
 cudaError_t launch_marker_overlay(const OverlayArgs& a, int N, cudaStream_t s);
 
+// antialiased bilinear resize (overlay_kernel.cu)
+constexpr int TX_RS_TAPS = 8;
+struct ResizeArgs {
+    const float* src; // [N][Hi][Wi]
+    float* dst;       // [N][Ho][Wo]
+    int Hi, Wi, Ho, Wo;
+    const int *fx, *cx, *fy, *cy; // first tap / tap count per output column / row
+    const float *wx, *wy;         // [Wo][8] / [Ho][8] normalised weights
+};
+cudaError_t launch_resize_aa(const ResizeArgs& a, int N, cudaStream_t s);
+
 // ---- gel FEM ---------------------------------------------------------------------------------------------------------
 typedef tx_fem_indenter FemIndenter;
 typedef tx_fem_stats FemStats;

@@ -130,6 +130,15 @@ class TactileEngine:
         self._check(self.lib.tx_indentation_depth(self.h, _ptr(hm), N, _ptr(out)))
         return out
 
+    def indentation_depth_frames(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Indentation depth [mm] of height maps at ANY resolution (N, Hc, Wc): what the reference computes from the camera map."""
+        if frames.device != self.device or frames.dtype != torch.float32 or not frames.is_contiguous() or frames.dim() != 3:
+            raise _lib.TxError("frames must be a contiguous float32 (N, Hc, Wc) tensor on the engine's device")
+        N = frames.shape[0]
+        out = torch.empty(N, device=self.device) if out is None else out
+        self._check(self.lib.tx_indentation_depth_frames(self.h, _ptr(frames), N, int(frames.shape[1] * frames.shape[2]), _ptr(out)))
+        return out
+
     def render(
         self,
         hm: torch.Tensor,
@@ -232,6 +241,16 @@ class TactileEngine:
         N = press.shape[0]
         out = torch.empty((N, 2, self.M, 2), device=self.device) if out is None else out
         self._check(self.lib.tx_fots_markers(self.h, _ptr(press), _ptr(theta), N, _ptr(traj0), _ptr(traj_len), _ptr(out)))
+        return out
+
+    def resize(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Antialiased bilinear resize (N, Hi, Wi) -> (N, H, W): torchvision's ``F.resize`` of the reference for a camera finer than
+        the tactile image, bit-identical to ``torch.nn.functional.interpolate(mode="bilinear", antialias=True)``."""
+        if frames.device != self.device or frames.dtype != torch.float32 or not frames.is_contiguous() or frames.dim() != 3:
+            raise _lib.TxError("frames must be a contiguous float32 (N, Hi, Wi) tensor on the engine's device")
+        N = frames.shape[0]
+        out = torch.empty((N, self.H, self.W), device=self.device) if out is None else out
+        self._check(self.lib.tx_resize(self.h, _ptr(frames), N, int(frames.shape[1]), int(frames.shape[2]), _ptr(out)))
         return out
 
     # -- marker image / marker overlay (ref: fots_marker_sim.py:346-384, ball_rolling_taxim_fots.py:918-937) --------------

@@ -26,6 +26,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from .calib import TaximTables
 from .engine import TactileEngine
 
@@ -209,11 +210,15 @@ class B200TaximSimulator(GelSightSimulator):
     def _height_map(self) -> torch.Tensor:
         hm = self.sensor._data.output["height_map"]
         W, H = self.cfg.tactile_img_res
-        if (hm.shape[1], hm.shape[2]) != (H, W):
-            # camera finer than the tactile image (down-sampling; not fused): torchvision's F.resize semantics (taxim_sim.py:88-89)
-            hm = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0]
         if hm.device != self.engine.device:
             hm = hm.to(self.engine.device)
+        if (hm.shape[1], hm.shape[2]) != (H, W):
+            # camera finer than the tactile image (down-sampling): torchvision's F.resize semantics (taxim_sim.py:88-89) by the
+            # library's own antialias kernel; torch only for scales beyond its 8 taps per axis
+            try:
+                return self.engine.resize(hm.contiguous().float())
+            except _lib.TxError:
+                hm = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0]
         return hm.contiguous()
 
     def _render(self, press, depth_out=None):
@@ -225,10 +230,8 @@ class B200TaximSimulator(GelSightSimulator):
         hm = self._height_map()
         if press is None and tuple(raw.shape[1:]) != tuple(hm.shape[1:]):
             # the indentation depth belongs to the CAMERA-resolution map (taxim_sim.py:115-131), the render to the resized one
-            mn = raw.amin((1, 2)) / 1000.0 - self.cfg.gelpad_to_camera_min_distance
-            mn = torch.where(mn < 0, torch.zeros_like(mn), mn)
-            press = torch.where(mn <= self.cfg.gelpad_height, (self.cfg.gelpad_height - mn) * 1000.0, torch.zeros_like(mn))
-            press = press.to(self.engine.device, torch.float32).contiguous()
+            cam = raw if raw.device == self.engine.device else raw.to(self.engine.device)
+            press = self.engine.indentation_depth_frames(cam.contiguous().float())
             if depth_out is not None:
                 depth_out.copy_(press)
         if self.cfg.with_shadow:

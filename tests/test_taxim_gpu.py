@@ -429,3 +429,37 @@ def test_4096_env_launch_strided_sample_vs_canonical_oracle(tables, canon_taxim)
     first = rgb[:64]
     for r in range(1, n // 64):
         assert torch.equal(rgb[64 * r: 64 * (r + 1)], first), f"replica {r} differs"
+
+
+@pytest.mark.parametrize("cam", [(480, 640), (300, 400), (360, 480)])
+def test_downsampling_resize_bitwise_torch_antialias(tables, canon_taxim, cam):
+    """Sensor camera FINER than the tactile image (ref: taxim_sim.py:88-89 F.resize): tx_resize is bit-identical to torch's
+    antialiased bilinear interpolate (= the canonical resize of the oracle), and the plug-in renders the resized map."""
+    import torch.nn.functional as F
+
+    from oracle import canon
+    from tacex_b200 import sensor, synth
+    from tacex_b200.engine import TactileEngine
+
+    Hc, Wc = cam
+    pitch = synth.PIXEL_PITCH_M_320 * 320 / Wc
+    depth = torch.stack([synth.depth_map(k % 4, 2.5e-3, 1e-3 * k, -5e-4 * k, 0.3 * k, 4e-4 + 2e-4 * k, H=Hc, W=Wc, pitch=pitch) for k in range(3)])
+    hm = synth.height_map_mm(depth)
+    eng = TactileEngine(tables, max_envs=3)
+    got = eng.resize(hm.cuda())
+    torch.cuda.synchronize()
+    ref_t = F.interpolate(hm[:, None], size=[H, W], mode="bilinear", align_corners=False, antialias=True)[:, 0]
+    assert torch.equal(got.cpu(), ref_t)
+    assert np.array_equal(got.cpu().numpy(), canon.resize_bilinear(hm.numpy(), (H, W)))
+    # through the plug-in: camera 2x finer than the tactile image
+    cfg = sensor.gelsight_mini_cfg(str(GOLDEN / "gsmini_tables_320x240.npz"), num_envs=3, with_markers=False)
+    cfg.sensor_camera_cfg.resolution = (Wc, Hc)
+    s = sensor.GelSightSensor(cfg)
+    k0 = s.optical_simulator.engine.counters()["kernels_launched"]
+    s.set_camera_depth(depth.cuda())
+    s.update(0.0, force_recompute=True)
+    hm_small = ref_t.numpy()
+    pc = canon_taxim.indentation_depth(hm.numpy())  # the indentation depth belongs to the CAMERA-resolution map
+    o = canon_taxim.render(hm_small, pc, want=("rgb",))
+    assert np.array_equal(s.data.output["tactile_rgb"].cpu().numpy(), o["rgb"])
+    assert s.optical_simulator.engine.counters()["kernels_launched"] - k0 >= 2  # resize kernel + fused render: no torch fallback
