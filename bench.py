@@ -344,9 +344,10 @@ class StepRunner:
         self.markers = torch.empty((E, 2, M, 2), device=dev)
         self.traj0 = torch.zeros((E, 4), device=dev)
         self.traj_len = torch.zeros(E, device=dev, dtype=torch.int32)
-        self.do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-rect", "fp32-ce", "nccl", "u8")
+        self.do_gather = world > 1 and args.obs_gather in ("fp32", "fp32-fused", "fp32-rect", "fp32-ce", "nccl", "u8")
         self.u8 = world > 1 and args.obs_gather == "u8"
-        self.use_rects = args.obs_gather == "fp32-rect" or (args.obs_gather == "fp32" and world > 2)
+        self.use_rects = args.obs_gather in ("fp32-rect", "fp32-fused", "fp32")
+        self.fused = False
         self.rgb_buf = [rgb, torch.empty_like(rgb)] if self.do_gather else [rgb]
         self.peer, self.gathered, self.gather_kind = None, None, "n/a"
         if self.u8:
@@ -355,12 +356,21 @@ class StepRunner:
             self.gather_kind = ("uint8 all-gather of RGB (round(rgb * 255), one extra conversion kernel per step) by NVLink peer copies into "
                                 "symmetric memory (copy engines), overlapped with the next step")
         elif self.do_gather:
-            if args.obs_gather in ("fp32", "fp32-rect", "fp32-ce"):
+            if args.obs_gather in ("fp32", "fp32-fused", "fp32-rect", "fp32-ce"):
                 try:
                     self.peer = PeerObsGather(rgb.shape, rgb.dtype, dev, n_slots=2, with_rects=self.use_rects,
                                               multicast=not args.no_multicast)
                     self.rgb_buf = [self.peer.local_block(0), self.peer.local_block(1)]  # render straight into the gathered buffer
+                    self.fused = self.use_rects and args.obs_gather in ("fp32", "fp32-fused") and self.peer.fused_available()
+                    if args.obs_gather == "fp32" and not self.fused and world == 2:
+                        # no multicast mapping: with one peer the link is not the limit and the copy engines win over the
+                        # rectangle push kernel (no SM taken)
+                        self.use_rects = False
                     self.gather_kind = (
+                        "float32 all-gather of RGB, bit-identical to gathering whole frames, FUSED into the render kernel: its epilogue "
+                        "stores every frame's non-flat rectangle through the NVSwitch multicast mapping of the symmetric buffers "
+                        "(multimem.st), the flat remainder is completed locally after a cross-rank barrier"
+                        if self.fused else
                         "float32 all-gather of RGB, bit-identical to gathering whole frames: NVLink peer stores of every frame's "
                         "non-flat rectangle into symmetric memory ("
                         + ("NVSwitch multicast stores" if (self.use_rects and self.peer.mc_rgb[0]) else "one store per peer")
@@ -391,7 +401,9 @@ class StepRunner:
             torch.cuda.current_stream().wait_event(self.ev_free[i])  # the gather that read this buffer two steps ago is done
         if self.fem is not None:
             self.fem.step()
-        if self.peer is not None and self.use_rects:
+        if self.fused:
+            self.peer.begin_fused(self.eng, i)  # barrier: every rank is done with the slot; multicast output on
+        elif self.peer is not None and self.use_rects:
             self.eng.set_rect_output(self.peer.local_rects(i))
         self.eng.render(self.hm_sets[k], None, out=self.rgb_buf[i], depth_out=self.depth)
         self.eng.fots_markers(self.depth, self.theta, self.traj0, self.traj_len, out=self.markers)
@@ -403,6 +415,8 @@ class StepRunner:
                 self.side.wait_event(self.ev_done[i])
                 if self.u8:
                     self.peer.gather(self.peer.local_block(i), i)
+                elif self.fused:
+                    self.peer.finish_fused(self.eng, i, self.side)
                 elif self.peer is not None and self.use_rects:
                     self.peer.gather_rects(self.eng, i, self.side)
                 elif self.peer is not None:
@@ -417,6 +431,7 @@ class StepRunner:
         if self.do_gather:
             torch.cuda.current_stream().wait_stream(self.side)  # the last gathers finish inside the timed region
         self.eng.set_rect_output(None)
+        self.eng.set_multicast_output(0, 0)
 
     def verify_gather(self, remote_sets_fn) -> bool | None:
         """After a step: re-render the block of ONE remote rank locally from that rank's (deterministic) inputs and compare it,
@@ -474,12 +489,13 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "fp32-rect", "fp32-ce", "nccl", "u8", "none"],
+    ap.add_argument("--obs-gather", default="fp32", choices=["fp32", "fp32-fused", "fp32-rect", "fp32-ce", "nccl", "u8", "none"],
                     help="N>1: float32 all-gather of the RGB observation into symmetric memory (falls back to NCCL). "
                          "fp32-rect = NVLink peer stores of the non-flat rectangle of every frame + local completion from the flat "
                          "image (bit-identical to gathering whole frames, about half the link bytes); fp32-ce = whole frames by "
-                         "copy-engine peer copies (no SM used); fp32 = fp32-ce for 2 GPUs (one peer: the link is not the limit), "
-                         "fp32-rect beyond; nccl = all_gather_into_tensor; u8 = the observation converted to uint8 by one extra "
+                         "copy-engine peer copies (no SM used); fp32 = fp32-fused when the allocation has an NVSwitch multicast mapping (the "
+                         "render kernel's epilogue stores every frame's rectangle through it: compute + collective in one kernel), "
+                         "else fp32-ce for 2 GPUs / fp32-rect beyond; nccl = all_gather_into_tensor; u8 = the observation converted to uint8 by one extra "
                          "kernel (tx_marker_overlay) and gathered by copy-engine peer copies: a quarter of the link bytes (reported "
                          "alongside the mandated float32 gather, SURVEY 8e); none = observations stay sharded")
     ap.add_argument("--no-multicast", action="store_true", help="fp32-rect: one store per peer instead of NVSwitch multicast stores")

@@ -171,6 +171,12 @@ int tx_render_shadow(tx_handle* h, const float* height_mm, const float* press_mm
  * inout, one per gathered buffer, initialised to (0, H/2-1, 0, W-1) per half) remembers what the buffer held after its last
  * fill, so that only the part of the old rectangle the new one does not cover is restored. Result == gathering whole frames. */
 int tx_set_rect_output(tx_handle* h, int32_t* rect);
+/* Fused observation all-gather: the following tx_render calls (with tx_set_rect_output active, whole batch, not the chunked host
+ * path) store the evaluated rectangle of every frame and its descriptor through the NVSwitch MULTICAST mapping of this rank's block of
+ * the gathered buffers (multimem.st from the render kernel's epilogue: compute and collective in one kernel, no second pass over
+ * the pixels, no SM taken by a push kernel). mc_rgb / mc_rect: multicast addresses of [N][H][W][3] float32 / [N][2][4] int32, or NULL,
+ * NULL to switch back. The flat remainder of each remote frame is completed locally by tx_obs_fill after a cross-rank barrier. */
+int tx_set_multicast_output(tx_handle* h, float* mc_rgb, int32_t* mc_rect);
 int tx_obs_push(tx_handle* h, const float* rgb_local, const int32_t* rect_local, int N, int n_peers, float* const* peer_rgb,
                 int32_t* const* peer_rect, float* mc_rgb, int32_t* mc_rect, void* cuda_stream);
 int tx_obs_fill(tx_handle* h, float* rgb_all, const int32_t* rect_all, int32_t* prev_rect, int N_total, int skip_lo, int skip_hi,

@@ -73,7 +73,7 @@ _lib = None
 # every symbol include/tacex_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
-    "tx_indentation_depth", "tx_indentation_depth_frames", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_set_marker_patches", "tx_marker_overlay", "tx_resize", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
+    "tx_indentation_depth", "tx_indentation_depth_frames", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_set_multicast_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_set_marker_patches", "tx_marker_overlay", "tx_resize", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
     "tx_fem_markers", "tx_fem_set_marker_output", "tx_fem_set_surface", "tx_fem_heightmap", "tx_fem_attachment_aim", "tx_fem_debug_set_cycles",
 ]
@@ -111,6 +111,8 @@ def load() -> C.CDLL:
     lib.tx_render_shadow.argtypes = [C.c_void_p, fp, fp, C.c_int, fp, fp]
     lib.tx_render_shadow.restype = C.c_int
     lib.tx_set_rect_output.argtypes = [C.c_void_p, vp]
+    lib.tx_set_multicast_output.argtypes = [C.c_void_p, fp, ip]
+    lib.tx_set_multicast_output.restype = C.c_int
     lib.tx_obs_push.argtypes = [C.c_void_p, fp, ip, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), fp, ip, vp]
     lib.tx_obs_fill.argtypes = [C.c_void_p, fp, ip, ip, C.c_int, C.c_int, C.c_int, vp]
     for name in ("tx_set_rect_output", "tx_obs_push", "tx_obs_fill"):

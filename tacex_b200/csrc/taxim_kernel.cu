@@ -643,8 +643,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         const int nq_ = fc.xb >= fc.xa ? (fc.xb - fc.xa + 1) >> 2 : 0;
         fc.total = fc.ry1 >= fc.ry0 ? nq_ * (fc.ry1 - fc.ry0 + 1) : 0;
     }
-    if (p.rect_out && tid == 0)
-        reinterpret_cast<int4*>(p.rect_out)[blockIdx.x] = fc.total > 0 ? make_int4(fc.ry0, fc.ry1, fc.xa, fc.xb) : make_int4(0, -1, 0, -1);
+    if (p.rect_out && tid == 0) {
+        const int4 rd = fc.total > 0 ? make_int4(fc.ry0, fc.ry1, fc.xa, fc.xb) : make_int4(0, -1, 0, -1);
+        reinterpret_cast<int4*>(p.rect_out)[blockIdx.x] = rd;
+        if (p.rect_mc) // the descriptor travels with the pixels: every GPU learns which part of the frame it has to complete itself
+            multimem_st_f4(reinterpret_cast<float*>(p.rect_mc) + 4 * (size_t)blockIdx.x,
+                           make_float4(__int_as_float(rd.x), __int_as_float(rd.y), __int_as_float(rd.z), __int_as_float(rd.w)));
+    }
     // ---- Gaussian pyramid with masked re-imposition + final blur (ref: taxim_torch.py:463-471) -----------------
     // Without contact and with a flat gel map the joined map is identically zero: every blur returns exact zeros.
     if (active) {
@@ -704,6 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     const float PI_F = 3.14159265358979323846f;
     const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
     float* rgb_half = p.rgb + half_off * 3;
+    float* rgb_mc_half = p.rgb_mc ? p.rgb_mc + half_off * 3 : nullptr;
     float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (16 x 2560 B = 40,960 B)
     float* iost = hb1 + IOST_OFF + warp * 192; // per warp: 96 floats of background + 96 floats of RGB
     const float* halo1 = hb1 + HALO1_OFF;
@@ -802,8 +808,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), __fmul_rn(yf, yf), __fmul_rn(xf, yf), bgv, o);
         iost[96 + 3 * lane] = o[0]; iost[96 + 3 * lane + 1] = o[1]; iost[96 + 3 * lane + 2] = o[2];
         __syncwarp();
-        if (4 * lane < 3 * nval)
-            reinterpret_cast<float4*>(rgb_half + ((size_t)row * IMG_W + xs) * 3)[lane] = reinterpret_cast<const float4*>(iost + 96)[lane];
+        if (4 * lane < 3 * nval) {
+            const float4 v = reinterpret_cast<const float4*>(iost + 96)[lane];
+            const size_t off = ((size_t)row * IMG_W + xs) * 3 + 4 * lane;
+            if (rgb_mc_half) multimem_st_f4(rgb_mc_half + off, v); // fused all-gather: into every GPU's buffer (this one included)
+            else *reinterpret_cast<float4*>(rgb_half + off) = v;
+        }
     }
     __syncthreads();
     TX_TICK(33);

@@ -57,6 +57,8 @@ struct tx_handle {
     float2 *d_rs_wx = nullptr, *d_rs_wy = nullptr;
     float* d_up = nullptr;
     int* d_rect = nullptr; // not owned: tx_set_rect_output
+    float* mc_rgb = nullptr; // not owned: tx_set_multicast_output
+    int* mc_rect = nullptr;
     // shadow branch (tx_upload_shadow_tables / tx_render_shadow)
     tx_shadow_config sh_cfg{};
     bool have_shadow = false;
@@ -472,6 +474,7 @@ static int render_impl(tx_handle* h, const float* height_mm, const float* press_
     a.ticks = h->d_ticks;
     a.dbg = h->dbg;
     a.rect_out = h->d_rect ? h->d_rect + (size_t)env0 * 8 : nullptr;
+    if (h->mc_rgb && h->d_rect && env0 == 0) { a.rgb_mc = h->mc_rgb; a.rect_mc = h->mc_rect; }
     TX_CUDA(h, launch_taxim(a, h->taps, N, h->stream));
     h->aux_valid_n = h->M > 0 ? env0 + N : 0;
     h->ctr.render_calls++;
@@ -566,6 +569,18 @@ extern "C" int tx_set_rect_output(tx_handle* h, int32_t* rect)
     if (!h) return TX_ERR_INVALID_ARG;
     if (rect && ((uintptr_t)rect & 15u)) return fail(h, TX_ERR_INVALID_ARG, "tx_set_rect_output: buffer must be 16-byte aligned");
     h->d_rect = rect;
+    return TX_OK;
+}
+
+extern "C" int tx_set_multicast_output(tx_handle* h, float* mc_rgb, int32_t* mc_rect)
+{
+    if (!h) return TX_ERR_INVALID_ARG;
+    if ((mc_rgb != nullptr) != (mc_rect != nullptr)) return fail(h, TX_ERR_INVALID_ARG, "tx_set_multicast_output: both pointers or none");
+    if (mc_rgb && (((uintptr_t)mc_rgb & 15u) || ((uintptr_t)mc_rect & 15u)))
+        return fail(h, TX_ERR_INVALID_ARG, "tx_set_multicast_output: pointers must be 16-byte aligned");
+    if (h->generic && mc_rgb) return fail(h, TX_ERR_UNSUPPORTED, "tx_set_multicast_output: belongs to the 240 x 320 kernel");
+    h->mc_rgb = mc_rgb;
+    h->mc_rect = mc_rect;
     return TX_OK;
 }
 
@@ -810,6 +825,7 @@ extern "C" int tx_step_host(tx_handle* h, const float* height_mm_host, const flo
     int* const saved_rect = h->d_rect; // the gather rectangles belong to device-resident batches, not to the chunked host path
     h->d_rect = nullptr;
     struct RestoreRect { tx_handle* h; int* r; ~RestoreRect() { h->d_rect = r; } } restore_rect{h, saved_rect};
+    // (the fused multicast output needs the rectangles: it is off with them)
     // the copy streams must not run ahead of work already queued on the caller's stream
     TX_CUDA(h, cudaEventRecord(h->ev_done[0], h->stream));
     TX_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done[0], 0));

@@ -134,6 +134,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// 16-byte store to a multicast address (NVLink SHARP / NVLS mapping of a symmetric allocation): the switch replicates it
+__device__ __forceinline__ void multimem_st_f4(float* mc_addr, float4 v)
+{
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 // ---- warp reductions ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_min(float v)
 {

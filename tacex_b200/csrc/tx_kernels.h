@@ -35,6 +35,11 @@ struct TaximArgs {
     float* rgb;            // [N][240][320][3]
     int* rect_out;         // optional [N][2][4]: per half frame the rectangle (ry0, ry1 local rows, xa, xb columns) outside of
                            // which the frame equals the flat RGB image (empty: ry1 < ry0); used by the multi-GPU gather
+    // fused observation all-gather (multi-GPU): NVSwitch MULTICAST mappings of this rank's block of the gathered buffers. When set,
+    // the evaluated rectangle and the rectangle descriptors are stored through them (multimem.st: one store leaves the GPU, the
+    // switch replicates it into every GPU's buffer, this one included) instead of into rgb / rect_out; the flat part stays local.
+    float* rgb_mc;         // [N][240][320][3] or nullptr
+    int* rect_mc;          // [N][2][4] or nullptr
     float* depth_out;      // [N] or nullptr
     float* deformed_out;   // [N][240][320] or nullptr
     unsigned char* mask_out; // [N][240][320] or nullptr

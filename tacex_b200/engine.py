@@ -219,6 +219,11 @@ class TactileEngine:
         """int32 (N, 2, 4) device tensor that the following renders fill with the per-half non-flat rectangle, or None."""
         self._check(self.lib.tx_set_rect_output(self.h, _ptr(rect)))
 
+    def set_multicast_output(self, mc_rgb: int = 0, mc_rect: int = 0) -> None:
+        """Multicast addresses (ints; 0, 0 = off) of this rank's block of the gathered RGB / rectangle buffers: the following renders
+        store their rectangles through them (fused all-gather, needs ``set_rect_output``)."""
+        self._check(self.lib.tx_set_multicast_output(self.h, mc_rgb or None, mc_rect or None))
+
     def obs_push(self, rgb_local: torch.Tensor, rect_local: torch.Tensor, peer_rgb: list, peer_rect: list, stream,
                  mc_rgb: int = 0, mc_rect: int = 0) -> None:
         import ctypes as C

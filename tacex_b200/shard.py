@@ -94,6 +94,25 @@ class PeerObsGather:
         engine.obs_fill(self.bufs[slot], self.rects[slot], self.prev_rects[slot], lo, lo + self.E, stream)
         return self.bufs[slot]
 
+    def fused_available(self, slot: int = 0) -> bool:
+        return bool(self.rects) and bool(self.mc_rgb[slot])
+
+    def begin_fused(self, engine, slot: int) -> None:
+        """Fused all-gather, step 1 (current stream, BEFORE the render of this slot): every rank is done reading the slot's previous
+        content (barrier), then the engine is pointed at the multicast mapping of this rank's block: the render kernel's epilogue
+        stores every frame's rectangle + descriptor into ALL GPUs' buffers while it computes."""
+        self.hdls[slot].barrier(channel=0)
+        engine.set_rect_output(self.local_rects(slot))
+        engine.set_multicast_output(self.mc_rgb[slot], self.mc_rect[slot])
+
+    def finish_fused(self, engine, slot: int, stream) -> torch.Tensor:
+        """Fused all-gather, step 2 (``stream`` = current stream, after the render): every rank's stores have landed (barrier), then
+        the remote frames of this rank's copy are completed from its flat image. Bit-identical to ``gather``."""
+        lo = self.rank * self.E
+        self.hdls[slot].barrier(channel=1)
+        engine.obs_fill(self.bufs[slot], self.rects[slot], self.prev_rects[slot], lo, lo + self.E, stream)
+        return self.bufs[slot]
+
     def local_block(self, slot: int) -> torch.Tensor:
         """This rank's block of its own gathered buffer: render straight into it and the self-copy disappears."""
         lo = self.rank * self.E
