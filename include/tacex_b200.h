@@ -237,7 +237,7 @@ int tx_step_host(tx_handle* h, const float* height_mm_host, const float* theta_h
  * (ref: source/tacex/tacex/simulation_approaches/fem_based/mani_skill_sim.py:82-86). All state is float64 like libuipc. */
 
 typedef struct {
-    int type;    /* 0 sphere, 1 oriented box */
+    int type;    /* 0 sphere, 1 oriented box, 2 the triangle mesh of tx_fem_set_indenter_mesh (pose c, R; h unused) */
     double c[3]; /* centre, world frame [m] */
     double R[9]; /* rotation, row-major, world = R * local */
     double h[3]; /* box half extents, or h[0] = sphere radius */
@@ -283,6 +283,13 @@ int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* a
 
 /* Profiling hook: cycles (device, [#SMs][6] int64) receives the per-CTA clock64 totals of the phases of the last env each
  * CTA processed (assembly, PCG, line search, and within the assembly: tets, vertex rows, edges); NULL disables. */
+/* Prescribed rigid TRIANGLE-MESH indenter (indenter type 2): tri_local HOST [n_tris][3][3] float64, triangle vertices in the indenter's
+ * own frame [m]; one mesh per handle, posed per gel by tx_fem_indenter.c / .R. Every (gel surface vertex, triangle) candidate inside
+ * d_hat gets the reference's point-triangle barrier with closest-feature classification (ref: libuipc
+ * utils/distance/distance_flagged.h:248-350, contact_system/contact_models/ipc_simplex_normal_contact.cu:270-342,
+ * collision_detection/filters/lbvh_simplex_trajectory_filter.cu:600-690), restricted to the gel vertex (the indenter is prescribed).
+ * n_tris = 0 removes the mesh. */
+int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri_local);
 int tx_fem_debug_set_cycles(tx_fem* f, long long* cycles);
 
 /* FEM marker read-out. set: HOST pointers, tri [M][3] surface-triangle vertex ids and barycentric weights [M][3] per marker,

@@ -23,6 +23,16 @@
  * the reference's vertex-vs-implicit-surface barrier generalised from a half-plane to a signed-distance function, the
  * broad phase (LBVH) disappears, and the CCD step bound is the conservative-advancement bound of a 1-Lipschitz SDF.
  * Lagged friction against the prescribed indenter: see friction_lagged / fem_friction_terms below.
+ * Third indenter kind (type 2): a prescribed rigid TRIANGLE MESH. Every (gel surface vertex, indenter triangle) candidate is treated
+ * as the reference treats a point-triangle candidate: closest-feature classification, squared distance of the PT / PE / PP case,
+ * one barrier per candidate inside d_hat, make_spd per candidate
+ *   ref: .../utils/distance/distance_flagged.h:248-350 (point_triangle_distance_flag), :527-562, :650-700, :813-868,
+ *        .../collision_detection/filters/lbvh_simplex_trajectory_filter.cu:600-690 (narrow phase: no de-duplication of the PE / PP
+ *        cases two triangles share), .../contact_system/contact_models/ipc_simplex_normal_contact.cu:270-342 (PT barrier + make_spd)
+ * restricted to the degrees of freedom of the gel vertex (the indenter is prescribed). fem_pt_distance is PINNED against the
+ * reference's distance_flagged.h compiled here (oracle/ref_dist.cpp -> oracle/_ref/libuipc_dist.so, tests/test_fem_ref_pin_cpu.py).
+ * Not restated: triangle(gel)-point(indenter) and edge-edge candidates, LBVH (every triangle is tested against its box), ACCD (the
+ * conservative-advancement bound of a 1-Lipschitz distance is kept).
  *
  * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
  * has no CPU backend) and its tests hold no golden positions for this path: the SOLVER LOOP of this
@@ -195,10 +205,139 @@ void fem_barrier(double D, double d_hat, double kappa, double* B, double* dB, do
     if (ddB) *ddB = -kappa * (2.0 * lg + 4.0 * t / D - t * t / (D * D));
 }
 
-/* signed distance of a world point to the indenter, unit normal n = grad d, Hd = hessian of d (row-major) */
+
+/* ---- prescribed triangle-mesh indenter (type 2) ------------------------------------------------------------------------------- */
+static double* g_mesh_tri = 0;  /* [n][9] local-frame triangles */
+static double* g_mesh_box = 0;  /* [n][6] lo / hi */
+static int g_mesh_n = 0;
+void fem_set_indenter_mesh(const double* tri, int n)
+{
+    free(g_mesh_tri); free(g_mesh_box);
+    g_mesh_tri = (double*)malloc(sizeof(double) * 9 * (n > 0 ? n : 1));
+    g_mesh_box = (double*)malloc(sizeof(double) * 6 * (n > 0 ? n : 1));
+    g_mesh_n = n;
+    memcpy(g_mesh_tri, tri, sizeof(double) * 9 * n);
+    for (int t = 0; t < n; ++t)
+        for (int a = 0; a < 3; ++a) {
+            double lo = tri[9 * t + a], hi = lo;
+            for (int v = 1; v < 3; ++v) {
+                const double c = tri[9 * t + 3 * v + a];
+                if (c < lo) lo = c;
+                if (c > hi) hi = c;
+            }
+            g_mesh_box[6 * t + a] = lo;
+            g_mesh_box[6 * t + 3 + a] = hi;
+        }
+}
+
+/* Closest feature of the triangle (t0, t1, t2) to the point p, squared distance D, dD/dp (3) and d2D/dp2 (9, row-major).
+ * Returns the kind: 0 face, 1 / 2 / 3 edge t0t1 / t1t2 / t2t0, 4 / 5 / 6 vertex t0 / t1 / t2. Decision order of the reference's
+ * point_triangle_distance_flag (distance_flagged.h:248-350): per edge the coordinate a along the edge (0..1) and the sign of the
+ * coordinate b along (edge x normal), i.e. outside of that edge; first edge with 0 < a < 1 and b >= 0, else the vertex tests
+ * (a_k <= 0 and a_{k-1} >= 1), else the face. The squared distances are those of point_point / point_edge / point_triangle
+ * (details/point_point.inl:3-9, point_edge.inl:5-13, point_triangle.inl:658-668); the derivatives are their p-blocks in closed form. */
+int fem_pt_distance(const double* p, const double* t0, const double* t1, const double* t2, double* D, double* g, double* H)
+{
+    const double* T[3] = {t0, t1, t2};
+    double e01[3], e02[3], n[3];
+    for (int a = 0; a < 3; ++a) { e01[a] = t1[a] - t0[a]; e02[a] = t2[a] - t0[a]; }
+    n[0] = e01[1] * e02[2] - e01[2] * e02[1];
+    n[1] = e01[2] * e02[0] - e01[0] * e02[2];
+    n[2] = e01[0] * e02[1] - e01[1] * e02[0];
+    double av[3], bv[3];
+    int kind = -1;
+    for (int k = 0; k < 3; ++k) {
+        const double *s = T[k], *t = T[(k + 1) % 3];
+        double e[3], q[3], m[3];
+        for (int a = 0; a < 3; ++a) { e[a] = t[a] - s[a]; q[a] = p[a] - s[a]; }
+        m[0] = e[1] * n[2] - e[2] * n[1];
+        m[1] = e[2] * n[0] - e[0] * n[2];
+        m[2] = e[0] * n[1] - e[1] * n[0];
+        av[k] = (e[0] * q[0] + e[1] * q[1] + e[2] * q[2]) / (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        bv[k] = (m[0] * q[0] + m[1] * q[1] + m[2] * q[2]) / (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        if (av[k] > 0.0 && av[k] < 1.0 && bv[k] >= 0.0) { kind = 1 + k; break; }
+    }
+    if (kind < 0) {
+        if (av[0] <= 0.0 && av[2] >= 1.0) kind = 4;
+        else if (av[1] <= 0.0 && av[0] >= 1.0) kind = 5;
+        else if (av[2] <= 0.0 && av[1] >= 1.0) kind = 6;
+        else kind = 0;
+    }
+    if (H) memset(H, 0, sizeof(double) * 9);
+    if (kind >= 4) {
+        const double* v = T[kind - 4];
+        double r[3] = {p[0] - v[0], p[1] - v[1], p[2] - v[2]};
+        *D = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        if (g) for (int a = 0; a < 3; ++a) g[a] = 2.0 * r[a];
+        if (H) H[0] = H[4] = H[8] = 2.0;
+    } else if (kind >= 1) {
+        const double *s = T[kind - 1], *t = T[kind % 3];
+        double u[3], q[3];
+        for (int a = 0; a < 3; ++a) { u[a] = t[a] - s[a]; q[a] = p[a] - s[a]; }
+        const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], qu = q[0] * u[0] + q[1] * u[1] + q[2] * u[2];
+        double c[3] = {q[1] * u[2] - q[2] * u[1], q[2] * u[0] - q[0] * u[2], q[0] * u[1] - q[1] * u[0]};
+        *D = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / uu;
+        if (g) for (int a = 0; a < 3; ++a) g[a] = 2.0 * (q[a] - qu / uu * u[a]);
+        if (H)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) H[3 * a + b] = 2.0 * ((a == b ? 1.0 : 0.0) - u[a] * u[b] / uu);
+    } else {
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double sd = n[0] * (p[0] - t0[0]) + n[1] * (p[1] - t0[1]) + n[2] * (p[2] - t0[2]);
+        *D = sd * sd / nn;
+        if (g) for (int a = 0; a < 3; ++a) g[a] = 2.0 * sd / nn * n[a];
+        if (H)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) H[3 * a + b] = 2.0 * n[a] * n[b] / nn;
+    }
+    return kind;
+}
+
+static double box_dist2(const double* box, const double* p)
+{
+    double s = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        const double d = p[a] < box[a] ? box[a] - p[a] : (p[a] > box[3 + a] ? p[a] - box[3 + a] : 0.0);
+        s += d * d;
+    }
+    return s;
+}
+
+/* world point -> local frame of the indenter (R^T (x - c)) */
+static void to_local(const fem_indenter* I, const double* x, double* p)
+{
+    double q[3];
+    for (int i = 0; i < 3; ++i) q[i] = x[i] - I->c[i];
+    for (int i = 0; i < 3; ++i) p[i] = I->R[0 * 3 + i] * q[0] + I->R[1 * 3 + i] * q[1] + I->R[2 * 3 + i] * q[2];
+}
+
+/* nearest point of the mesh: unsigned distance d and direction n (world) from it to x; triangles whose box is farther than the
+   best distance so far are skipped (the "broad phase" of a few hundred static triangles) */
+static void mesh_nearest(const fem_indenter* I, const double* x, double* d, double* n)
+{
+    double p[3], best = 1e300, gb[3] = {0, 0, 1};
+    to_local(I, x, p);
+    for (int t = 0; t < g_mesh_n; ++t) {
+        if (!(box_dist2(g_mesh_box + 6 * t, p) < best)) continue;
+        double D, g[3];
+        fem_pt_distance(p, g_mesh_tri + 9 * t, g_mesh_tri + 9 * t + 3, g_mesh_tri + 9 * t + 6, &D, g, 0);
+        if (D < best) { best = D; memcpy(gb, g, sizeof(gb)); }
+    }
+    *d = sqrt(best);
+    const double l = sqrt(gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
+    for (int i = 0; i < 3; ++i)
+        n[i] = l > 0.0 ? (I->R[i * 3 + 0] * gb[0] + I->R[i * 3 + 1] * gb[1] + I->R[i * 3 + 2] * gb[2]) / l : (i == 2 ? 1.0 : 0.0);
+}
+
+/* signed distance of a world point to the indenter, unit normal n = grad d, Hd = hessian of d (row-major; analytic kinds only) */
 void fem_indenter_sdf(const fem_indenter* I, const double* x, double* d, double* n, double* Hd)
 {
     double p[3], q[3];
+    if (I->type == 2) { /* triangle mesh: UNSIGNED distance (an IPC trajectory never crosses the surface) */
+        mesh_nearest(I, x, d, n);
+        if (Hd) memset(Hd, 0, sizeof(double) * 9);
+        return;
+    }
     for (int i = 0; i < 3; ++i) q[i] = x[i] - I->c[i];
     for (int i = 0; i < 3; ++i) p[i] = I->R[0 * 3 + i] * q[0] + I->R[1 * 3 + i] * q[1] + I->R[2 * 3 + i] * q[2]; /* R^T q */
     double nl[3] = {0, 0, 0}, Hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -307,6 +446,43 @@ typedef struct {
     fem_indenter ind0;   /* indenter at the start of the step (lagged friction) */
 } fem_ctx;
 
+/* triangle-mesh indenter: one barrier per (vertex, triangle) candidate inside d_hat, each candidate's Hessian block made positive
+ * semi-definite on its own (ipc_simplex_normal_contact.cu:270-342: PT_barrier_gradient_hessian + make_spd), summed. H is returned
+ * ALREADY projected (a sum of PSD blocks). */
+static int mesh_barrier_terms(const fem_cfg* g, const fem_indenter* I, const double* x, double* E, double* G, double* H)
+{
+    double p[3], Gl[3] = {0, 0, 0}, Hl[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, Es = 0.0;
+    const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
+    int active = 0;
+    to_local(I, x, p);
+    for (int t = 0; t < g_mesh_n; ++t) {
+        if (!(box_dist2(g_mesh_box + 6 * t, p) < D0)) continue;
+        double D, gd[3], Hd[9], B, dB, ddB, Hp[9];
+        fem_pt_distance(p, g_mesh_tri + 9 * t, g_mesh_tri + 9 * t + 3, g_mesh_tri + 9 * t + 6, &D, gd, Hd);
+        if (!(D < D0) || !(D > 0.0)) continue;
+        fem_barrier(D, g->d_hat, kdt2, &B, &dB, &ddB);
+        active = 1;
+        Es += B;
+        for (int a = 0; a < 3; ++a) Gl[a] += dB * gd[a];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Hp[3 * a + b] = ddB * gd[a] * gd[b] + dB * Hd[3 * a + b];
+        fem_spd_project(3, Hp);
+        for (int j = 0; j < 9; ++j) Hl[j] += Hp[j];
+    }
+    if (!active) return 0;
+    if (E) *E = Es;
+    if (G)
+        for (int i = 0; i < 3; ++i) G[i] = I->R[i * 3 + 0] * Gl[0] + I->R[i * 3 + 1] * Gl[1] + I->R[i * 3 + 2] * Gl[2];
+    if (H) { /* R Hl R^T */
+        double T[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) T[3 * i + j] = I->R[i * 3 + 0] * Hl[0 * 3 + j] + I->R[i * 3 + 1] * Hl[1 * 3 + j] + I->R[i * 3 + 2] * Hl[2 * 3 + j];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) H[3 * i + j] = T[3 * i + 0] * I->R[j * 3 + 0] + T[3 * i + 1] * I->R[j * 3 + 1] + T[3 * i + 2] * I->R[j * 3 + 2];
+    }
+    return 1;
+}
+
 /* ---- IPC barrier of a surface vertex against the prescribed indenter ---------------------------------------------------------
  * ref: contact_system/contact_models/ipc_vertex_half_plane_contact_function.h:12-60 (PH_barrier_energy / gradient_hessian:
  * B(D) with D the squared distance, G = dB/dD dD/dx, H = d2B/dD2 dD/dx dD/dx^T + dB/dD d2D/dx2), with the half-plane distance
@@ -319,6 +495,7 @@ int fem_vertex_barrier_terms(const fem_cfg* g, const fem_indenter* ind, const do
     if (E) *E = 0.0;
     if (G) memset(G, 0, sizeof(double) * 3);
     if (H) memset(H, 0, sizeof(double) * 9);
+    if (ind->type == 2) return mesh_barrier_terms(g, ind, x, E, G, H);
     fem_indenter_sdf(ind, x, &d, n, Hd);
     if (!((d * d < g->d_hat * g->d_hat) && d > 0.0)) return 0;
     const double dt2 = g->dt * g->dt;
@@ -344,10 +521,20 @@ int fem_vertex_barrier_terms(const fem_cfg* g, const fem_indenter* ind, const do
 static int friction_lagged(const fem_cfg* g, const fem_indenter* ind0, const double* xp, double* fn, double* e1, double* e2)
 {
     double d, n[3], dB;
-    fem_indenter_sdf(ind0, xp, &d, n, 0);
-    if (!(d > 0.0) || !(d < g->d_hat)) return 0;
-    fem_barrier(d * d, g->d_hat, g->kappa * g->dt * g->dt, 0, &dB, 0);
-    *fn = -dB * 2.0 * d;
+    if (ind0->type == 2) {
+        /* triangle mesh: ONE lagged contact per vertex -- the resultant of the candidates' normal forces (its magnitude and
+           direction); equal to the reference's per-candidate friction when a single candidate is active */
+        double Gb[3];
+        if (!mesh_barrier_terms(g, ind0, xp, 0, Gb, 0)) return 0;
+        *fn = sqrt(Gb[0] * Gb[0] + Gb[1] * Gb[1] + Gb[2] * Gb[2]);
+        if (!(*fn > 0.0)) return 0;
+        for (int a = 0; a < 3; ++a) n[a] = -Gb[a] / *fn;
+    } else {
+        fem_indenter_sdf(ind0, xp, &d, n, 0);
+        if (!(d > 0.0) || !(d < g->d_hat)) return 0;
+        fem_barrier(d * d, g->d_hat, g->kappa * g->dt * g->dt, 0, &dB, 0);
+        *fn = -dB * 2.0 * d;
+    }
     double t[3] = {1.0, 0.0, 0.0};
     if (n[0] > 0.9) { t[0] = 0.0; t[2] = 1.0; }
     double c[3] = {t[1] * n[2] - t[2] * n[1], t[2] * n[0] - t[0] * n[2], t[0] * n[1] - t[1] * n[0]};
@@ -430,8 +617,14 @@ static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
         fem_indenter_sdf(&c->ind, x + 3 * i, &d, n, 0);
         if (d < md) md = d;
         if (d <= 0.0) { E = INFINITY; continue; }
-        fem_barrier(d * d, g->d_hat, g->kappa * dt2, &B, 0, 0);
-        E += B;
+        if (c->ind.type == 2) {
+            B = 0.0;
+            mesh_barrier_terms(g, &c->ind, x + 3 * i, &B, 0, 0);
+            E += B;
+        } else {
+            fem_barrier(d * d, g->d_hat, g->kappa * dt2, &B, 0, 0);
+            E += B;
+        }
     }
     if (g->friction_mu > 0.0)
         for (int k = 0; k < g->S; ++k) {

@@ -96,6 +96,12 @@ class CanonFem:
         x = np.tile(self.X[None], (N, 1, 1)).copy()
         return x, np.zeros_like(x), x.copy()
 
+    @staticmethod
+    def set_indenter_mesh(tri_local) -> None:
+        """Triangles (n, 3, 3) float64 of the prescribed mesh indenter (type 2) in its own frame; process-wide like the C global."""
+        t = np.ascontiguousarray(tri_local, np.float64).reshape(-1, 9)
+        lib().fem_set_indenter_mesh(_d(t), C.c_int(len(t)))
+
     def step(self, x, v, x_prev, aim, ind_prev, ind_next):
         """x, v, x_prev: (N, V, 3) float64 updated in place; aim (N, A, 3); indenters: lists of FemIndenter."""
         N = x.shape[0]

@@ -18,6 +18,9 @@ struct DiagRef {
         Matrix<T, N, N>* m;
         Arr& operator+=(T s) { for (int i = 0; i < N; ++i) (*m)(i, i) += s; return *this; }
     };
+    void setConstant(T s) { for (int i = 0; i < N; ++i) (*m)(i, i) = s; }
+    struct Unused {
+    };
     Arr array() { return Arr{m}; }
 };
 
@@ -28,12 +31,59 @@ struct ColRef { // assignable column of a matrix (m.col(j) = v)
     ColRef& operator=(const Matrix<T, R, 1>& v) { for (int i = 0; i < R; ++i) (*m)(i, j) = v.d[i]; return *this; }
 };
 
+
+// ---- assignable views used by the reference's distance headers (utils/distance/distance_flagged.h) -------------------------------
+template <class T, int R, int C, int N>
+struct SegRef { // v.segment<N>(i) / v.head<N>() of a vector
+    Matrix<T, R, C>* m;
+    int i0;
+    SegRef& operator=(const SegRef& o) { for (int i = 0; i < N; ++i) m->d[i0 + i] = o.m->d[o.i0 + i]; return *this; }
+    template <int R2, int C2>
+    SegRef& operator=(const SegRef<T, R2, C2, N>& o) { for (int i = 0; i < N; ++i) m->d[i0 + i] = o.m->d[o.i0 + i]; return *this; }
+    SegRef& operator=(const Matrix<T, N, 1>& v) { for (int i = 0; i < N; ++i) m->d[i0 + i] = v.d[i]; return *this; }
+    Matrix<T, N, 1> operator-() const { Matrix<T, N, 1> v; for (int i = 0; i < N; ++i) v.d[i] = -m->d[i0 + i]; return v; }
+    operator Matrix<T, N, 1>() const { Matrix<T, N, 1> v; for (int i = 0; i < N; ++i) v.d[i] = m->d[i0 + i]; return v; }
+};
+template <class T, int R, int C, int BR, int BC>
+struct BlockRef { // m.block<BR, BC>(i, j)
+    Matrix<T, R, C>* m;
+    int i0, j0;
+    template <int R2, int C2>
+    BlockRef& operator=(const BlockRef<T, R2, C2, BR, BC>& o)
+    {
+        for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) (*m)(i0 + i, j0 + j) = (*o.m)(o.i0 + i, o.j0 + j);
+        return *this;
+    }
+    BlockRef& operator=(const BlockRef& o)
+    {
+        for (int i = 0; i < BR; ++i) for (int j = 0; j < BC; ++j) (*m)(i0 + i, j0 + j) = (*o.m)(o.i0 + i, o.j0 + j);
+        return *this;
+    }
+};
+template <class T, int R, int C>
+struct RowRef { // m.row(i): assignable from a row or a column vector, cross product with a 3-vector
+    Matrix<T, R, C>* m;
+    int i;
+    RowRef& operator=(const Matrix<T, 1, C>& v) { for (int j = 0; j < C; ++j) (*m)(i, j) = v.d[j]; return *this; }
+    RowRef& operator=(const Matrix<T, C, 1>& v) { for (int j = 0; j < C; ++j) (*m)(i, j) = v.d[j]; return *this; }
+    operator Matrix<T, C, 1>() const { Matrix<T, C, 1> v; for (int j = 0; j < C; ++j) v.d[j] = (*m)(i, j); return v; }
+    Matrix<T, C, 1> cross(const Matrix<T, C, 1>& o) const { return Matrix<T, C, 1>(*this).cross(o); }
+    Matrix<T, C, 1> cross(const RowRef& o) const { return Matrix<T, C, 1>(*this).cross(Matrix<T, C, 1>(o)); }
+};
+
 template <class T, int R, int C>
 struct Matrix {
     T d[R * C];
     Matrix() { for (int i = 0; i < R * C; ++i) d[i] = T(0); }
     Matrix(T a, T b) { static_assert(R * C == 2, "size"); d[0] = a; d[1] = b; }
     Matrix(T a, T b, T c) { static_assert(R * C == 3, "size"); d[0] = a; d[1] = b; d[2] = c; }
+    Matrix(T a, T b, T c, T e) { static_assert(R * C == 4, "size"); d[0] = a; d[1] = b; d[2] = c; d[3] = e; }
+    void setZero() { for (int i = 0; i < R * C; ++i) d[i] = T(0); }
+    void setConstant(T v) { for (int i = 0; i < R * C; ++i) d[i] = v; }
+    template <int N> SegRef<T, R, C, N> segment(int i0) { return SegRef<T, R, C, N>{this, i0}; }
+    template <int N> SegRef<T, R, C, N> head() { return SegRef<T, R, C, N>{this, 0}; }
+    template <int BR, int BC> BlockRef<T, R, C, BR, BC> block(int i0, int j0) { return BlockRef<T, R, C, BR, BC>{this, i0, j0}; }
+    RowRef<T, R, C> row(int i) { return RowRef<T, R, C>{this, i}; }
     T* data() { return d; }
     const T* data() const { return d; }
     T& operator()(int i, int j) { return d[j * R + i]; }
@@ -58,6 +108,7 @@ struct Matrix {
         return Matrix(d[1] * o.d[2] - d[2] * o.d[1], d[2] * o.d[0] - d[0] * o.d[2], d[0] * o.d[1] - d[1] * o.d[0]);
     }
     Matrix operator+(const Matrix& o) const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i] + o.d[i]; return m; }
+    Matrix operator/(T s) const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i] / s; return m; }
     Matrix operator-(const Matrix& o) const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i] - o.d[i]; return m; }
     Matrix operator-() const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = -d[i]; return m; }
     Matrix operator*(T s) const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i] * s; return m; }

@@ -11,6 +11,10 @@
 #define UIPC_HOST
 namespace uipc {
 using Float = double;
+using IndexT = int;
+using Vector2i = Eigen::Matrix<IndexT, 2, 1>;
+using Vector3i = Eigen::Matrix<IndexT, 3, 1>;
+using Vector4i = Eigen::Matrix<IndexT, 4, 1>;
 using Vector2 = Eigen::Matrix<Float, 2, 1>;
 using Vector3 = Eigen::Matrix<Float, 3, 1>;
 using Matrix2x2 = Eigen::Matrix<Float, 2, 2>;

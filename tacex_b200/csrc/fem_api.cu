@@ -32,6 +32,9 @@ struct tx_fem {
     // top-surface triangles for the height-map rasteriser
     int n_top = 0;
     int* d_top = nullptr;
+    // prescribed triangle-mesh indenter (tx_fem_set_indenter_mesh)
+    int mesh_n = 0;
+    double *d_mesh_tri = nullptr, *d_mesh_box = nullptr;
 };
 
 static std::string g_fem_err;
@@ -244,7 +247,7 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     cudaFree(f->d_tets); cudaFree(f->d_attach); cudaFree(f->d_surf); cudaFree(f->d_Dm_inv); cudaFree(f->d_vol);
     cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_tsc); cudaFree(f->d_valg); cudaFree(f->d_xt); cudaFree(f->d_edge_off); cudaFree(f->d_edge_adj);
     cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
-    cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top);
+    cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top); cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box);
     delete f;
 }
 
@@ -273,6 +276,7 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.nE = f->nE; a.n_s = f->n_s; a.nslots = f->nslots;
     a.edge_start = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
     a.attach_of = f->d_attach_of; a.surf_of = f->d_surf_of;
+    a.mesh_tri = f->d_mesh_tri; a.mesh_box = f->d_mesh_box; a.mesh_n = f->mesh_n;
     a.dbg_cycles = f->d_cycles;
     a.dbg_mode = getenv("TX_FEM_DBG_MODE") ? atoi(getenv("TX_FEM_DBG_MODE")) : 0;
     a.row_start = f->d_adj_off;
@@ -285,6 +289,41 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.pcg_max_iter_ratio = c.pcg_max_iter_ratio; a.ls_max_iter = c.ls_max_iter; a.substep = c.substep;
     const int grid = N < f->grid ? N : f->grid;
     FEM_CUDA(f, launch_fem_step(a, grid, f->stream));
+    return TX_OK;
+}
+
+extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri_local)
+{
+    if (!f || n_tris < 0 || (n_tris > 0 && !tri_local)) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_indenter_mesh: bad argument");
+    if (n_tris > 4096) return ffail(f, TX_ERR_UNSUPPORTED, "tx_fem_set_indenter_mesh: more than 4096 triangles (every triangle is box-tested per vertex)");
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    FEM_CUDA(f, cudaStreamSynchronize(f->stream)); // a step in flight may still read the old mesh
+    cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box);
+    f->d_mesh_tri = f->d_mesh_box = nullptr;
+    f->mesh_n = 0;
+    if (n_tris == 0) return TX_OK;
+    std::vector<double> box((size_t)6 * n_tris);
+    for (int t = 0; t < n_tris; ++t) {
+        const double* tr = tri_local + (size_t)9 * t;
+        const double e1[3] = {tr[3] - tr[0], tr[4] - tr[1], tr[5] - tr[2]}, e2[3] = {tr[6] - tr[0], tr[7] - tr[1], tr[8] - tr[2]};
+        const double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+        if (!(nx * nx + ny * ny + nz * nz > 0.0)) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_indenter_mesh: degenerate triangle");
+        for (int a = 0; a < 3; ++a) {
+            double lo = tr[a], hi = tr[a];
+            for (int v = 1; v < 3; ++v) {
+                const double c = tr[3 * v + a];
+                lo = c < lo ? c : lo;
+                hi = c > hi ? c : hi;
+            }
+            box[(size_t)6 * t + a] = lo;
+            box[(size_t)6 * t + 3 + a] = hi;
+        }
+    }
+    FEM_CUDA(f, cudaMalloc(&f->d_mesh_tri, sizeof(double) * 9 * n_tris));
+    FEM_CUDA(f, cudaMalloc(&f->d_mesh_box, sizeof(double) * 6 * n_tris));
+    FEM_CUDA(f, cudaMemcpy(f->d_mesh_tri, tri_local, sizeof(double) * 9 * n_tris, cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_mesh_box, box.data(), sizeof(double) * 6 * n_tris, cudaMemcpyHostToDevice));
+    f->mesh_n = n_tris;
     return TX_OK;
 }
 

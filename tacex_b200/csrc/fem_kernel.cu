@@ -378,8 +378,163 @@ __device__ __forceinline__ void barrier_fn(double D, double d_hat, double kappa,
     if (ddB) *ddB = -kappa * (2.0 * lg + 4.0 * t / D - t * t / (D * D));
 }
 
-__device__ void indenter_sdf(const FemIndenter& I, const double* x, double* d, double* n, double* Hd)
+
+// ---- prescribed triangle-mesh indenter (type 2) ----------------------------------------------------------------------------
+// Every (gel surface vertex, indenter triangle) candidate is treated as the reference treats a point-triangle candidate: closest
+// feature (distance_flagged.h:248-350, same decision order), squared distance of the PT / PE / PP case (details/point_*.inl), one
+// barrier per candidate inside d_hat (ipc_simplex_normal_contact.cu:270-342; no de-duplication of shared edges / vertices,
+// lbvh_simplex_trajectory_filter.cu:600-690), restricted to the gel vertex's degrees of freedom. dD/dp = 2 (p - closest point) in
+// all three cases, and each candidate's make_spd'ed block has the closed form max(0, B'' + B' / (2 D)) g g^T (pinned against the
+// reference's Hessian in tests/test_fem_ref_pin_cpu.py), so neither d2D/dp2 nor an eigen-decomposition is needed here.
+// The triangles are static in the indenter's frame and shared by all gels (L1 / L2 resident, every lane of a warp reads the same
+// triangle: a broadcast); the broad phase is a box test per triangle.
+__device__ __forceinline__ double pt_distance2(const double* __restrict__ tr, const double p[3], double g[3])
 {
+    const double e01[3] = {tr[3] - tr[0], tr[4] - tr[1], tr[5] - tr[2]}, e02[3] = {tr[6] - tr[0], tr[7] - tr[1], tr[8] - tr[2]};
+    const double n[3] = {e01[1] * e02[2] - e01[2] * e02[1], e01[2] * e02[0] - e01[0] * e02[2], e01[0] * e02[1] - e01[1] * e02[0]};
+    double av[3];
+    int kind = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (kind >= 0) continue;
+        const double* s = tr + 3 * k;
+        const double* t = tr + 3 * ((k + 1) % 3);
+        const double e[3] = {t[0] - s[0], t[1] - s[1], t[2] - s[2]}, q[3] = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};
+        const double m[3] = {e[1] * n[2] - e[2] * n[1], e[2] * n[0] - e[0] * n[2], e[0] * n[1] - e[1] * n[0]};
+        av[k] = (e[0] * q[0] + e[1] * q[1] + e[2] * q[2]) / (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        const double b = (m[0] * q[0] + m[1] * q[1] + m[2] * q[2]) / (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        if (av[k] > 0.0 && av[k] < 1.0 && b >= 0.0) kind = 1 + k;
+    }
+    if (kind < 0) {
+        if (av[0] <= 0.0 && av[2] >= 1.0) kind = 4;
+        else if (av[1] <= 0.0 && av[0] >= 1.0) kind = 5;
+        else if (av[2] <= 0.0 && av[1] >= 1.0) kind = 6;
+        else kind = 0;
+    }
+    double D;
+    if (kind >= 4) {
+        const double* v = tr + 3 * (kind - 4);
+        const double r[3] = {p[0] - v[0], p[1] - v[1], p[2] - v[2]};
+        D = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        g[0] = 2.0 * r[0]; g[1] = 2.0 * r[1]; g[2] = 2.0 * r[2];
+    } else if (kind >= 1) {
+        const double* s = tr + 3 * (kind - 1);
+        const double* t = tr + 3 * (kind % 3);
+        const double u[3] = {t[0] - s[0], t[1] - s[1], t[2] - s[2]}, q[3] = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};
+        const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], qu = q[0] * u[0] + q[1] * u[1] + q[2] * u[2];
+        const double c[3] = {q[1] * u[2] - q[2] * u[1], q[2] * u[0] - q[0] * u[2], q[0] * u[1] - q[1] * u[0]};
+        D = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / uu;
+        const double f = qu / uu;
+        g[0] = 2.0 * (q[0] - f * u[0]); g[1] = 2.0 * (q[1] - f * u[1]); g[2] = 2.0 * (q[2] - f * u[2]);
+    } else {
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double sd = n[0] * (p[0] - tr[0]) + n[1] * (p[1] - tr[1]) + n[2] * (p[2] - tr[2]);
+        D = sd * sd / nn;
+        const double f = 2.0 * sd / nn;
+        g[0] = f * n[0]; g[1] = f * n[1]; g[2] = f * n[2];
+    }
+    return D;
+}
+
+// One pass over the triangles: nearest distance d + direction n (world), and -- when kdt2 > 0 -- the summed barrier energy, gradient
+// (world) and projected Hessian block (world, symmetric 00 01 02 11 12 22) of the candidates inside d_hat. Returns whether any
+// candidate is active. E / G / H6 are ACCUMULATED into.
+// Out-of-line, and every input BY VALUE: a reference to the kernel's parameter struct or to an indenter held in registers would force
+// both onto the local-memory stack of the (register-tight) step kernel for all indenter kinds.
+struct MeshRef { const double* tri; const double* box; int n; double d_hat; };
+struct MeshOut { double d, n[3], E, G[3], H6[6]; };
+__device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0, double3 r1, double3 r2, double3 xw, double kdt2, MeshOut* o)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double q[3] = {xw.x - c.x, xw.y - c.y, xw.z - c.z};
+    double p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = R[0 * 3 + i] * q[0] + R[1 * 3 + i] * q[1] + R[2 * 3 + i] * q[2];
+    const double D0 = m.d_hat * m.d_hat, Dcull = kdt2 > 0.0 ? D0 : 0.0;
+    double best = 1e300, gb[3] = {0.0, 0.0, 1.0};
+    double Es = 0.0, Gl[3] = {0.0, 0.0, 0.0}, Hl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    bool active = false;
+    for (int t = 0; t < m.n; ++t) {
+        const double* bx = m.box + 6 * t;
+        double bd = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double lo = bx[c], hi = bx[3 + c];
+            const double dd = p[c] < lo ? lo - p[c] : (p[c] > hi ? p[c] - hi : 0.0);
+            bd += dd * dd;
+        }
+        if (!(bd < best) && !(bd < Dcull)) continue;
+        double g[3];
+        const double D = pt_distance2(m.tri + 9 * t, p, g);
+        if (D < best) { best = D; gb[0] = g[0]; gb[1] = g[1]; gb[2] = g[2]; }
+        if (kdt2 > 0.0 && D < D0 && D > 0.0) {
+            double B, dB, ddB;
+            barrier_fn(D, m.d_hat, kdt2, &B, &dB, &ddB);
+            active = true;
+            Es += B;
+            Gl[0] += dB * g[0]; Gl[1] += dB * g[1]; Gl[2] += dB * g[2];
+            const double w = ddB + dB / (2.0 * D);
+            if (w > 0.0) {
+                Hl[0] += w * g[0] * g[0]; Hl[1] += w * g[0] * g[1]; Hl[2] += w * g[0] * g[2];
+                Hl[3] += w * g[1] * g[1]; Hl[4] += w * g[1] * g[2]; Hl[5] += w * g[2] * g[2];
+            }
+        }
+    }
+    o->d = sqrt(best);
+    {
+        const double l = sqrt(gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            o->n[i] = l > 0.0 ? (R[i * 3 + 0] * gb[0] + R[i * 3 + 1] * gb[1] + R[i * 3 + 2] * gb[2]) / l : (i == 2 ? 1.0 : 0.0);
+    }
+    o->E = Es;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o->G[i] = R[i * 3 + 0] * Gl[0] + R[i * 3 + 1] * Gl[1] + R[i * 3 + 2] * Gl[2];
+    { // R Hl R^T
+        const double Hf[9] = {Hl[0], Hl[1], Hl[2], Hl[1], Hl[3], Hl[4], Hl[2], Hl[4], Hl[5]};
+        double T[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) T[3 * i + j] = R[i * 3 + 0] * Hf[j] + R[i * 3 + 1] * Hf[3 + j] + R[i * 3 + 2] * Hf[6 + j];
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = i; j < 3; ++j, ++k) o->H6[k] = T[3 * i + 0] * R[j * 3 + 0] + T[3 * i + 1] * R[j * 3 + 1] + T[3 * i + 2] * R[j * 3 + 2];
+    }
+    return active;
+}
+
+// inlined front end: nearest distance d + direction n (world) and -- when kdt2 > 0 -- energy / gradient / projected block ACCUMULATED
+// into E / G / H6 (any may be null). Returns whether a candidate is active.
+__device__ __forceinline__ bool mesh_contact(const FemArgs& a, const FemIndenter& I, const double* x, double kdt2, double* d, double* n,
+                                             double* E, double* G, double* H6)
+{
+    MeshOut o;
+    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat};
+    const bool active = mesh_contact_impl(m, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]),
+                                          make_double3(I.R[3], I.R[4], I.R[5]), make_double3(I.R[6], I.R[7], I.R[8]),
+                                          make_double3(x[0], x[1], x[2]), kdt2, &o);
+    if (d) *d = o.d;
+    if (n) { n[0] = o.n[0]; n[1] = o.n[1]; n[2] = o.n[2]; }
+    if (!active) return false;
+    if (E) *E += o.E;
+    if (G) { G[0] += o.G[0]; G[1] += o.G[1]; G[2] += o.G[2]; }
+    if (H6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) H6[k] += o.H6[k];
+    }
+    return true;
+}
+
+template <bool MESH>
+__device__ void indenter_sdf(const FemArgs& a, const FemIndenter& I, const double* x, double* d, double* n, double* Hd)
+{
+    if (MESH && I.type == 2) { // triangle mesh: UNSIGNED distance (Hd is not defined: the barrier goes through mesh_contact)
+        mesh_contact(a, I, x, 0.0, d, n, nullptr, nullptr, nullptr);
+        return;
+    }
     double p[3], q[3];
     for (int i = 0; i < 3; ++i) q[i] = x[i] - I.c[i];
     for (int i = 0; i < 3; ++i) p[i] = I.R[0 * 3 + i] * q[0] + I.R[1 * 3 + i] * q[1] + I.R[2 * 3 + i] * q[2];
@@ -469,14 +624,38 @@ __device__ __forceinline__ void tet_F(const double* x, const int* e, const doubl
 // ref: contact_system/contact_models/ipc_vertex_half_plane_frictional_contact.cu:29-127, ipc_vertex_half_plane_contact_function.h
 // :62-151, codim_ipc_contact_function.h:16-128. Normal force and tangent frame at the start-of-step position against the
 // start-of-step indenter (lagged); slip measured relative to the indenter's prescribed translation. E / G / H may be null.
+// Lagged contact of a vertex against the mesh indenter: ONE per vertex, the resultant of the candidates' normal forces at the
+// start-of-step position. It does not change during the step, so the row's thread computes it once (a pass over the triangles).
+struct FrLag { double fn, n[3]; };
+__device__ __forceinline__ FrLag mesh_friction_lag(const FemArgs& a, const FemIndenter& ind0, const double* xp)
+{
+    FrLag l{0.0, {0.0, 0.0, 1.0}};
+    double Gb[3] = {0.0, 0.0, 0.0};
+    if (!mesh_contact(a, ind0, xp, a.kappa * a.dt * a.dt, nullptr, nullptr, nullptr, Gb, nullptr)) return l;
+    const double fn = sqrt(Gb[0] * Gb[0] + Gb[1] * Gb[1] + Gb[2] * Gb[2]);
+    if (!(fn > 0.0)) return l;
+    l.fn = fn;
+    l.n[0] = -Gb[0] / fn; l.n[1] = -Gb[1] / fn; l.n[2] = -Gb[2] / fn;
+    return l;
+}
+
+template <bool MESH>
 __device__ void friction_terms(const FemArgs& a, const FemIndenter& ind0, const FemIndenter& ind, const double* xp, const double* x,
-                               double* E, double* G, double* H6 /* symmetric 00 01 02 11 12 22 */)
+                               double* E, double* G, double* H6 /* symmetric 00 01 02 11 12 22 */, const FrLag& lag)
 {
     double d, n[3], dB;
-    indenter_sdf(ind0, xp, &d, n, nullptr);
-    if (!(d > 0.0) || !(d < a.d_hat)) return;
-    barrier_fn(d * d, a.d_hat, a.kappa * a.dt * a.dt, nullptr, &dB, nullptr);
-    const double mf = a.friction_mu * (-dB * 2.0 * d);
+    double fn;
+    if (MESH && ind0.type == 2) {
+        if (!(lag.fn > 0.0)) return;
+        fn = lag.fn;
+        n[0] = lag.n[0]; n[1] = lag.n[1]; n[2] = lag.n[2];
+    } else {
+        indenter_sdf<MESH>(a, ind0, xp, &d, n, nullptr);
+        if (!(d > 0.0) || !(d < a.d_hat)) return;
+        barrier_fn(d * d, a.d_hat, a.kappa * a.dt * a.dt, nullptr, &dB, nullptr);
+        fn = -dB * 2.0 * d;
+    }
+    const double mf = a.friction_mu * fn;
     double t[3] = {1.0, 0.0, 0.0};
     if (n[0] > 0.9) { t[0] = 0.0; t[2] = 1.0; }
     const double c[3] = {t[1] * n[2] - t[2] * n[1], t[2] * n[0] - t[0] * n[2], t[0] * n[1] - t[1] * n[0]};
@@ -577,9 +756,10 @@ struct FemShared {
 };
 
 // total incremental potential at the positions in s.x (thread `row` owns vertex `row`)
+template <bool MESH>
 __device__ double total_energy(const FemArgs& a, const FemShared& s, const double* xt_g,
                                const double* __restrict__ xprev_g, const double* __restrict__ aim_g, const FemIndenter& ind,
-                               const FemIndenter& ind0, double ratio, double* min_dist, int& ph)
+                               const FemIndenter& ind0, double ratio, double* min_dist, int& ph, const FrLag& lag)
 {
     const double dt2 = a.dt * a.dt;
     const int i = threadIdx.x;
@@ -604,16 +784,22 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
         }
         if (a.surf_of[i] >= 0) {
             double d, n[3], B;
-            indenter_sdf(ind, xi, &d, n, nullptr);
+            if (MESH && ind.type == 2) {
+                mesh_contact(a, ind, xi, a.kappa * dt2, &d, nullptr, &E, nullptr, nullptr);
+                md = d;
+                if (d <= 0.0) bad = true;
+            } else {
+            indenter_sdf<MESH>(a, ind, xi, &d, n, nullptr);
             md = d;
             if (d <= 0.0) bad = true;
             else {
                 barrier_fn(d * d, a.d_hat, a.kappa * dt2, &B, nullptr, nullptr);
                 E += B;
             }
+            }
             if (a.friction_mu > 0.0) {
                 const double xp[3] = {xprev_g[3 * i], xprev_g[3 * i + 1], xprev_g[3 * i + 2]};
-                friction_terms(a, ind0, ind, xp, xi, &E, nullptr, nullptr);
+                friction_terms<MESH>(a, ind0, ind, xp, xi, &E, nullptr, nullptr, lag);
             }
         }
     }
@@ -636,9 +822,10 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
 // Gradient g3 (row-local), diagonal block d6 (row-local, symmetric) and the off-diagonal blocks of the Hessian (s.val / valg).
 // The tets are processed in chunks of one tet per thread so that the per-tet scratch (102 doubles per tet) of all CTAs
 // stays L2-resident; rows and edges accumulate their incident tets chunk by chunk, in ascending tet order (no atomics).
+template <bool MESH>
 __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt_g, const double* __restrict__ xprev_g,
                           const double* __restrict__ aim_g, const FemIndenter& ind, const FemIndenter& ind0, double ratio,
-                          double* __restrict__ tsc, double* valg, double g3[3], double d6[6], long long* cyc)
+                          double* __restrict__ tsc, double* valg, double g3[3], double d6[6], long long* cyc, const FrLag& lag)
 {
     long long tg0 = cyc ? clock64() : 0;
     const double dt2 = a.dt * a.dt;
@@ -752,7 +939,11 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
         }
         if (a.surf_of[i] >= 0) {
             double d, n[3], Hd[9], dB, ddB, Hk[9];
-            indenter_sdf(ind, xi, &d, n, Hd);
+            if (MESH && ind.type == 2) {
+                mesh_contact(a, ind, xi, a.kappa * dt2, nullptr, nullptr, nullptr, g3, d6);
+                d = -1.0;
+            } else
+                indenter_sdf<MESH>(a, ind, xi, &d, n, Hd);
             if ((d * d < a.d_hat * a.d_hat) && d > 0.0) {
                 barrier_fn(d * d, a.d_hat, a.kappa * dt2, nullptr, &dB, &ddB);
                 double dD[3];
@@ -765,7 +956,7 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
             }
             if (a.friction_mu > 0.0) {
                 const double xp[3] = {xprev_g[3 * i], xprev_g[3 * i + 1], xprev_g[3 * i + 2]};
-                friction_terms(a, ind0, ind, xp, xi, nullptr, g3, d6);
+                friction_terms<MESH>(a, ind0, ind, xp, xi, nullptr, g3, d6, lag);
             }
         }
     }
@@ -871,6 +1062,8 @@ __device__ __forceinline__ FemIndenter lerp_ind(const FemIndenter& a, const FemI
     return o;
 }
 
+// MESH = false is the kernel of the analytic indenters alone (the out-of-line mesh call would cost it registers and spills)
+template <bool MESH>
 __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -907,6 +1100,11 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
         for (int c = 0; c < 3; ++c) umax += (ind_next.c[c] - ind_prev.c[c]) * (ind_next.c[c] - ind_prev.c[c]);
         umax = sqrt(umax);
         const bool is_surf = on && a.surf_of[i] >= 0;
+        FrLag lag{0.0, {0.0, 0.0, 1.0}};
+        if (MESH && ind_prev.type == 2 && is_surf && a.friction_mu > 0.0) {
+            const double xp3[3] = {xpg[3 * i], xpg[3 * i + 1], xpg[3 * i + 2]};
+            lag = mesh_friction_lag(a, ind_prev, xp3);
+        }
         int it, pcg_total = 0, ls_total = 0, conv = 0;
         for (it = 0; it < a.newton_max_iter; ++it) {
             const double tt = ((double)it + 1.0) / (double)a.substep;
@@ -916,7 +1114,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                 double md = 1e300;
                 if (is_surf) {
                     double d, nn[3];
-                    indenter_sdf(cur, s.x + 3 * i, &d, nn, nullptr);
+                    indenter_sdf<MESH>(a, cur, s.x + 3 * i, &d, nn, nullptr);
                     md = d;
                 }
                 md = block_reduce<1>(md, s.red, ph);
@@ -928,7 +1126,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
 
             double g3[3], d6[6], dx[3];
             FEM_TIC();
-            grad_hess(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, tsc, valg, g3, d6, (a.dbg_cycles && !a.dbg_mode) ? cyc + 3 : nullptr);
+            grad_hess<MESH>(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, tsc, valg, g3, d6, (a.dbg_cycles && !a.dbg_mode) ? cyc + 3 : nullptr, lag);
             FEM_TOC(0);
             FEM_TIC();
             pcg_total += pcg(a, s, valg, g3, d6, dx, ph, (a.dbg_cycles && a.dbg_mode) ? cyc + 3 : nullptr);
@@ -949,17 +1147,17 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             double alpha = 1.0;
             if (is_surf) {
                 double d, nn[3];
-                indenter_sdf(ind, x0, &d, nn, nullptr);
+                indenter_sdf<MESH>(a, ind, x0, &d, nn, nullptr);
                 const double len = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
                 if (len > 0.0 && d < 2.0 * len + a.d_hat) alpha = fmin(alpha, 0.8 * d / len);
             }
             alpha = block_reduce<1>(alpha, s.red, ph);
             ccd_alpha = alpha;
-            const double E0 = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, nullptr, ph);
+            const double E0 = total_energy<MESH>(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, nullptr, ph, lag);
             __syncthreads(); // every thread has read s.x
             if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
             __syncthreads();
-            double E = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph);
+            double E = total_energy<MESH>(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph, lag);
             if (!converged) {
                 int ls = 0;
                 while (ls < a.ls_max_iter) {
@@ -968,7 +1166,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                     __syncthreads();
                     if (on) for (int c = 0; c < 3; ++c) s.x[3 * i + c] = x0[c] + alpha * dx[c];
                     __syncthreads();
-                    E = total_energy(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph);
+                    E = total_energy<MESH>(a, s, xt_g, xpg, aim_g, ind, ind_prev, ratio, &min_dist, ph, lag);
                     ++ls;
                     ++ls_total;
                 }
@@ -1007,9 +1205,15 @@ int fem_max_smem_edges(int V) { (void)V; return FEM_VAL_STRIDE; }
 cudaError_t launch_fem_step(const FemArgs& a, int grid, cudaStream_t st)
 {
     const size_t smem = fem_smem_bytes(a.V, a.n_s);
-    cudaError_t e = cudaFuncSetAttribute(fem_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fem_step_kernel<<<grid, FEM_THREADS, smem, st>>>(a);
+    if (a.mesh_n > 0) { // a triangle-mesh indenter is set (tx_fem_set_indenter_mesh): the kernel that knows indenter type 2
+        cudaError_t e = cudaFuncSetAttribute(fem_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        fem_step_kernel<true><<<grid, FEM_THREADS, smem, st>>>(a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(fem_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        fem_step_kernel<false><<<grid, FEM_THREADS, smem, st>>>(a);
+    }
     return cudaGetLastError();
 }
 

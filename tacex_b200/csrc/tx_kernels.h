@@ -185,6 +185,9 @@ struct FemArgs {
     const int* ell;        // [nslots][FEM threads] row -> (neighbour j | transposed << 12 | edge << 13), -1 = empty
     const int* attach_of;  // [V] index into attach[] or -1
     const int* surf_of;    // [V] index into surf[] or -1
+    const double* mesh_tri; // [mesh_n][9] triangles of the prescribed mesh indenter (type 2) in its local frame, or nullptr
+    const double* mesh_box; // [mesh_n][6] their boxes (lo, hi)
+    int mesh_n;
     int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
     long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate, friction_mu, eps_velocity;

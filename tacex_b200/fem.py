@@ -140,6 +140,17 @@ class GelFemEngine:
                                          ind_prev.data_ptr(), ind_next.data_ptr(), N, None if st is None else st.data_ptr()))
         return st
 
+    def set_indenter_mesh(self, tri_local: np.ndarray | None) -> None:
+        """Triangles (n, 3, 3) float64 [m] of the prescribed rigid mesh indenter in its own frame (indenter type 2 of
+        ``indenter_array``; pose = centre + rotation per gel); ``None`` removes it. One mesh per engine."""
+        if tri_local is None:
+            self._check(self.lib.tx_fem_set_indenter_mesh(self.h, 0, None))
+            return
+        t = np.ascontiguousarray(tri_local, np.float64)
+        if t.ndim != 3 or t.shape[1:] != (3, 3):
+            raise _lib.TxError("tri_local must have shape (n, 3, 3)")
+        self._check(self.lib.tx_fem_set_indenter_mesh(self.h, len(t), t.ctypes.data))
+
     @staticmethod
     def decode_stats(st: torch.Tensor) -> list[dict]:
         raw = st.cpu().numpy().tobytes()

@@ -56,6 +56,35 @@ def indenter_profile(kind: int, X: torch.Tensor, Y: torch.Tensor, size: float) -
     raise ValueError(f"unknown indenter kind {kind}")
 
 
+def indenter_mesh(kind: int, size: float, segments: int = 24):
+    """Closed triangle mesh (n, 3, 3) float64 [m] of the config-2 indenters for the gel FEM path (``tx_fem_set_indenter_mesh``), in the
+    indenter's own frame: lowest point at the origin, body towards +z -- the same shapes as ``indenter_profile``: kind 1 flat
+    cylinder (radius ``size``, height ``size``), 2 wedge (90 deg edge along y, half width ``size``, half length 2 ``size``),
+    3 cone (60 deg apex, base radius ``size``)."""
+    import numpy as np
+
+    tris = []
+    ang = np.linspace(0.0, 2.0 * np.pi, segments + 1)
+    ring = lambda r, z: np.stack([r * np.cos(ang), r * np.sin(ang), np.full_like(ang, z)], 1)  # noqa: E731
+    if kind == 1:
+        lo, hi, c0, c1 = ring(size, 0.0), ring(size, size), np.zeros(3), np.array([0.0, 0.0, size])
+        for k in range(segments):
+            tris += [[c0, lo[k + 1], lo[k]], [lo[k], lo[k + 1], hi[k + 1]], [lo[k], hi[k + 1], hi[k]], [c1, hi[k], hi[k + 1]]]
+    elif kind == 2:
+        s, l = size, 2.0 * size
+        e0, e1 = np.array([0.0, -l, 0.0]), np.array([0.0, l, 0.0])
+        a0, a1, b0, b1 = np.array([-s, -l, s]), np.array([-s, l, s]), np.array([s, -l, s]), np.array([s, l, s])
+        tris += [[e0, e1, a1], [e0, a1, a0], [e0, b0, b1], [e0, b1, e1], [e0, a0, b0], [e1, b1, a1], [a0, a1, b1], [a0, b1, b0]]
+    elif kind == 3:
+        h = size / math.tan(math.radians(30.0))
+        hi, apex, c1 = ring(size, h), np.zeros(3), np.array([0.0, 0.0, h])
+        for k in range(segments):
+            tris += [[apex, hi[k + 1], hi[k]], [c1, hi[k], hi[k + 1]]]
+    else:
+        raise ValueError(f"no mesh for indenter kind {kind} (the sphere is analytic)")
+    return np.asarray(tris, np.float64)
+
+
 def depth_map(
     kind: int,
     size_m: float,

@@ -250,3 +250,43 @@ def test_friction_terms_match_finite_differences():
     G = np.ones(3)
     lib.fem_friction_terms(C.byref(cf.cfg), C.byref(ind0), C.byref(ind1), fc._d(far), fc._d(far + 1e-4), C.byref(E), fc._d(G), None)
     assert E.value == 0.0 and not G.any()
+
+
+def test_triangle_mesh_indenter_of_the_restatement():
+    """Mesh indenter (type 2) of the CPU restatement: (a) a box given as 12 triangles presses the gel like the analytic box SDF
+    (same barrier wherever a single face candidate is active; near the face diagonals two candidates are, as in the reference,
+    which makes the mesh contact slightly stiffer), (b) a 90 deg wedge mesh converges every step and no gel surface vertex ends
+    up inside it."""
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh, synth
+
+    m = gel_mesh.box_gel()
+    cf = fc.CanonFem(m, velocity_tol=1e-3)
+    h = (2e-3, 3e-3, 1e-3)
+    v = np.array([[sx * h[0], sy * h[1], sz * h[2]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    box = np.array([[v[a], v[b], v[c]] for a, b, c, d in quads] + [[v[a], v[c], v[d]] for a, b, c, d in quads])
+    aim = cf.X[cf.attach][None]
+    z0 = 4.5e-3 + h[2] + 4e-4
+    ctr = lambda s: [1e-3, 0.5e-3, z0 - 1e-3 * s / 6]  # noqa: E731
+    fc.CanonFem.set_indenter_mesh(box)
+    xa, va, xpa = cf.new_state(1)
+    xb, vb, xpb = cf.new_state(1)
+    for s in range(6):
+        sa = cf.step(xa, va, xpa, aim, [fc.make_indenter(2, ctr(s), (0, 0, 0))], [fc.make_indenter(2, ctr(s + 1), (0, 0, 0))])
+        sb = cf.step(xb, vb, xpb, aim, [fc.make_indenter(1, ctr(s), h)], [fc.make_indenter(1, ctr(s + 1), h)])
+        assert sa[0]["converged"] == 1 and sb[0]["converged"] == 1
+    disp = np.abs(xb - cf.X).max()
+    assert disp > 5e-4 and np.abs(xa - xb).max() < 0.02 * disp
+
+    size = 3e-3
+    fc.CanonFem.set_indenter_mesh(synth.indenter_mesh(2, size))
+    x, vv, xp = cf.new_state(1)
+    z0 = 4.5e-3 + 4e-4
+    for s in range(8):
+        st = cf.step(x, vv, xp, aim, [fc.make_indenter(2, [1e-3, 0.0, z0 - 1e-3 * s / 8], (0, 0, 0))],
+                     [fc.make_indenter(2, [1e-3, 0.0, z0 - 1e-3 * (s + 1) / 8], (0, 0, 0))])
+        assert st[0]["converged"] == 1 and st[0]["min_dist"] > 0
+    p = x[0, cf.surf] - np.array([1e-3, 0.0, z0 - 1e-3])  # surface vertices in the wedge's frame
+    inside = (np.abs(p[:, 0]) < size) & (np.abs(p[:, 1]) < 2 * size) & (p[:, 2] > np.abs(p[:, 0])) & (p[:, 2] < size)
+    assert not inside.any() and np.abs(x - cf.X).max() > 1e-4

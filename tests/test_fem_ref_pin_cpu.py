@@ -204,3 +204,79 @@ def test_block_jacobi_inverse_matches_muda_analytic_inverse(ref, canon):
         scale = np.abs(R_ref).max()
         assert np.abs(R_ref - R_me).max() <= 1e-9 * scale
         assert np.abs(R_me @ A - np.eye(3)).max() <= 1e-6
+
+
+# ---- closest-feature distances (triangle-mesh indenter) ---------------------------------------------------------------------------
+REF_DIST = REF.parent / "libuipc_dist.so"
+# reference flag (p, t0, t1, t2) -> kind of oracle/fem_canon.c::fem_pt_distance
+_KIND = {(1, 1, 1, 1): 0, (1, 1, 1, 0): 1, (1, 0, 1, 1): 2, (1, 1, 0, 1): 3, (1, 1, 0, 0): 4, (1, 0, 1, 0): 5, (1, 0, 0, 1): 6}
+
+
+@pytest.mark.skipif(not REF_DIST.exists(), reason="oracle/_ref/libuipc_dist.so not built (make -C oracle ref; needs /root/reference)")
+def test_point_triangle_closest_feature_and_distance_derivatives_match_reference_source(canon):
+    """fem_pt_distance vs the reference's point_triangle_distance_flag + flagged distance / gradient / Hessian
+    (utils/distance/distance_flagged.h compiled from where it lies): the same closest feature for points all around random, thin and
+    obtuse triangles, the same squared distance, and the p-block of the 12-gradient / 12 x 12 Hessian."""
+    rd = C.CDLL(str(REF_DIST))
+    canon.fem_pt_distance.restype = C.c_int
+    rng = np.random.default_rng(7)
+    IP = C.POINTER(C.c_int)
+    seen = set()
+    n_checked = 0
+    for k in range(4000):
+        t = rng.standard_normal((3, 3)) * (1e-3 if k % 2 else 1.0)
+        if k % 5 == 0:  # thin / obtuse triangle
+            t[2] = t[0] + (t[1] - t[0]) * rng.uniform(-0.5, 1.5) + 0.05 * rng.standard_normal(3) * np.linalg.norm(t[1] - t[0])
+        e = np.linalg.norm(t[1] - t[0])
+        # points spread over all seven regions: barycentric combination with weights outside [0, 1] + an offset along the normal
+        w = rng.uniform(-1.0, 2.0, 3)
+        w /= w.sum() if abs(w.sum()) > 0.2 else 1.0
+        nrm = np.cross(t[1] - t[0], t[2] - t[0])
+        p = w @ t + rng.uniform(-1, 1) * e * nrm / np.linalg.norm(nrm)
+        t0, t1, t2 = (np.ascontiguousarray(t[i]) for i in range(3))
+        p = np.ascontiguousarray(p)
+        flag = np.zeros(4, np.int32)
+        D2, G2, H2 = C.c_double(), np.zeros(12), np.zeros(144)
+        rd.ref_pt(_d(p), _d(t0), _d(t1), _d(t2), flag.ctypes.data_as(IP), C.byref(D2), _d(G2), _d(H2))
+        D1, G1, H1 = C.c_double(), np.zeros(3), np.zeros(9)
+        kind = canon.fem_pt_distance(_d(p), _d(t0), _d(t1), _d(t2), C.byref(D1), _d(G1), _d(H1))
+        assert kind == _KIND[tuple(int(f) for f in flag)], (k, kind, flag)
+        seen.add(kind)
+        sc = max(D2.value, 1e-300)
+        assert abs(D1.value - D2.value) <= 1e-10 * sc
+        assert np.abs(G1 - G2[:3]).max() <= 1e-9 * max(np.abs(G2[:3]).max(), np.sqrt(sc) * 1e-3)
+        Hp = H2.reshape(12, 12)[:3, :3]
+        assert np.abs(H1.reshape(3, 3) - Hp).max() <= 1e-8 * 2.0, (k, kind)
+        n_checked += 1
+    assert seen == set(range(7)) and n_checked == 4000
+
+
+@pytest.mark.skipif(not REF_DIST.exists(), reason="oracle/_ref/libuipc_dist.so not built")
+def test_per_candidate_barrier_block_projection_has_the_closed_form_the_kernel_uses(canon):
+    """The CUDA kernel projects each candidate's 3 x 3 barrier block analytically: max(0, B'' + B' / (2 D)) g g^T. Checked against
+    make_spd (numeric eigen-decomposition) of B'' g g^T + B' H_D built from the REFERENCE's gradient / Hessian p-blocks."""
+    rd = C.CDLL(str(REF_DIST))
+    rng = np.random.default_rng(11)
+    IP = C.POINTER(C.c_int)
+    d_hat, kappa = 5e-4, 1e10 * 1e-4
+    for k in range(300):
+        t = rng.standard_normal((3, 3)) * 2e-3
+        w = rng.uniform(-0.6, 1.6, 3)
+        w /= w.sum() if abs(w.sum()) > 0.2 else 1.0
+        nrm = np.cross(t[1] - t[0], t[2] - t[0])
+        p = np.ascontiguousarray(w @ t + rng.uniform(0.02, 0.98) * d_hat * nrm / np.linalg.norm(nrm))
+        flag = np.zeros(4, np.int32)
+        D2, G2, H2 = C.c_double(), np.zeros(12), np.zeros(144)
+        rd.ref_pt(_d(p), _d(np.ascontiguousarray(t[0])), _d(np.ascontiguousarray(t[1])), _d(np.ascontiguousarray(t[2])),
+                  flag.ctypes.data_as(IP), C.byref(D2), _d(G2), _d(H2))
+        D = D2.value
+        if not (0 < D < d_hat * d_hat):
+            continue
+        B, dB, ddB = C.c_double(), C.c_double(), C.c_double()
+        canon.fem_barrier(C.c_double(D), C.c_double(d_hat), C.c_double(kappa), C.byref(B), C.byref(dB), C.byref(ddB))
+        g = G2[:3]
+        H = ddB.value * np.outer(g, g) + dB.value * H2.reshape(12, 12)[:3, :3]
+        wv, V = np.linalg.eigh(0.5 * (H + H.T))
+        Hproj = (V * np.maximum(wv, 0)) @ V.T
+        closed = max(0.0, ddB.value + dB.value / (2 * D)) * np.outer(g, g)
+        assert np.abs(Hproj - closed).max() <= 1e-9 * max(np.abs(Hproj).max(), 1e-30)

@@ -1,4 +1,7 @@
-"""Timing of the batched gel FEM substep (config 3: box indenter pressed 0 -> 1 mm over 30 steps)."""
+"""Timing of the batched gel FEM substep (config 3: box indenter pressed 0 -> 1 mm over 30 steps).
+
+    python tools/fem_time.py [N] [steps] [mesh_kind]     mesh_kind 1 / 2 / 3: the config-2 cylinder / wedge / cone as a prescribed triangle mesh
+"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +16,14 @@ half = (2e-3, 3e-3, 1e-3)
 z0 = 4.5e-3 + half[2] + 4e-4
 x, v, xp = eng.new_state(N); aim = eng.rest_aim(N)
 ctr = lambda s: np.concatenate([offs, np.full((N, 1), z0 - 1e-3 * s / 30)], 1)
-inds = [fem.indenter_array(1, ctr(s), half) for s in range(steps + 1)]
+mesh_kind = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if mesh_kind:
+    from tacex_b200 import synth
+    eng.set_indenter_mesh(synth.indenter_mesh(mesh_kind, 3e-3))
+    z0 = 4.5e-3 + 4e-4
+    inds = [fem.indenter_array(2, ctr(s), (0, 0, 0)) for s in range(steps + 1)]
+else:
+    inds = [fem.indenter_array(1, ctr(s), half) for s in range(steps + 1)]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 tot_newton = 0; tot_pcg = 0
 for s in range(steps):
