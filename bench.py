@@ -653,7 +653,16 @@ def main() -> None:
         eng4 = TactileEngine(tables, max_envs=E4, device=dev, marker_rows=MARKER_ROWS, marker_cols=MARKER_COLS)
         K4 = c3.last - c3.first  # 6 timed steps = press steps 24..29; the depth map of step s is the pose at its END (s + 1)
         maps_of = lambda c: [c.height_maps(s + 1) for s in range(c.first, c.last)]  # noqa: E731
-        run4 = StepRunner(args, eng4, E4, dev, world, rank, maps_of(c3), fem_ctx=FemCtx(E4, dev, c3))
+        args4 = args
+        if world > 2 and args.obs_gather == "fp32":
+            # With the FEM substep in the step the SEPARATE rectangle push wins beyond two GPUs: it runs on the side stream under the
+            # next step's FEM kernel, while the fused epilogue stores stall the (short) render on the link instead
+            # (8 GPUs, 8 x 1024 envs: 678 k vs 642 k frames/s, profiles/r02_bench_n8_fp32.json vs r02_bench_n8_fp32_fused.json)
+            import copy
+
+            args4 = copy.copy(args)
+            args4.obs_gather = "fp32-rect"
+        run4 = StepRunner(args4, eng4, E4, dev, world, rank, maps_of(c3), fem_ctx=FemCtx(E4, dev, c3))
         for _ in range(c3.first - K4):   # untimed run-in of the press (FEM only), then K4 full warm-up steps
             run4.fem.step()
         ms4 = timed(run4, K4, K4)

@@ -31,8 +31,8 @@
  *        cases two triangles share), .../contact_system/contact_models/ipc_simplex_normal_contact.cu:270-342 (PT barrier + make_spd)
  * restricted to the degrees of freedom of the gel vertex (the indenter is prescribed). fem_pt_distance is PINNED against the
  * reference's distance_flagged.h compiled here (oracle/ref_dist.cpp -> oracle/_ref/libuipc_dist.so, tests/test_fem_ref_pin_cpu.py).
- * Not restated: triangle(gel)-point(indenter) and edge-edge candidates, LBVH (every triangle is tested against its box), ACCD (the
- * conservative-advancement bound of a 1-Lipschitz distance is kept).
+ * The CCD step bound of the mesh path is the reference's ACCD per (vertex, triangle) pair (fem_pt_accd, pinned against ccd.inl).
+ * Not restated: triangle(gel)-point(indenter) and edge-edge candidates, LBVH (every triangle is tested against its box).
  *
  * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
  * has no CPU backend) and its tests hold no golden positions for this path: the SOLVER LOOP of this
@@ -327,6 +327,74 @@ static void mesh_nearest(const fem_indenter* I, const double* x, double* d, doub
     const double l = sqrt(gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
     for (int i = 0; i < 3; ++i)
         n[i] = l > 0.0 ? (I->R[i * 3 + 0] * gb[0] + I->R[i * 3 + 1] * gb[1] + I->R[i * 3 + 2] * gb[2]) / l : (i == 2 ? 1.0 : 0.0);
+}
+
+
+/* Additive CCD of a point against a triangle, all four points moving linearly over the step (p + t dp, ...): the reference's
+ * point_triangle_ccd (utils/distance/details/ccd.inl:200-262; Codim-IPC's ACCD): the common translation is removed, the motion is
+ * advanced by the conservative bound (1 - eta) (d^2 - xi^2) / ((d + xi) L) until the gap has shrunk to eta times its initial value;
+ * returns 1 and the time of impact *toc when that happens before the incoming *toc, else 0. PINNED against the compiled reference
+ * on muda's vertex-face fixtures (tests/test_fem_ref_pin_cpu.py). */
+int fem_pt_accd(const double* p_, const double* t0_, const double* t1_, const double* t2_, const double* dp_, const double* dt0_,
+                const double* dt1_, const double* dt2_, double eta, double thickness, int max_iter, double* toc)
+{
+    double p[3], t0[3], t1[3], t2[3], dp[3], dt0[3], dt1[3], dt2[3];
+    for (int a = 0; a < 3; ++a) {
+        const double mov = (dt0_[a] + dt1_[a] + dt2_[a] + dp_[a]) / 4;
+        p[a] = p_[a]; t0[a] = t0_[a]; t1[a] = t1_[a]; t2[a] = t2_[a];
+        dp[a] = dp_[a] - mov; dt0[a] = dt0_[a] - mov; dt1[a] = dt1_[a] - mov; dt2[a] = dt2_[a] - mov;
+    }
+    const double m0 = dt0[0] * dt0[0] + dt0[1] * dt0[1] + dt0[2] * dt0[2], m1 = dt1[0] * dt1[0] + dt1[1] * dt1[1] + dt1[2] * dt1[2],
+                 m2 = dt2[0] * dt2[0] + dt2[1] * dt2[1] + dt2[2] * dt2[2];
+    const double mm = m0 > m1 ? (m0 > m2 ? m0 : m2) : (m1 > m2 ? m1 : m2);
+    const double L = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) + sqrt(mm);
+    if (L <= 0.0) return 0;
+    double d2, d;
+    fem_pt_distance(p, t0, t1, t2, &d2, 0, 0);
+    d = sqrt(d2);
+    const double xi2 = thickness * thickness, gap = eta * (d2 - xi2) / (d + thickness), toc_prev = *toc;
+    *toc = 0.0;
+    for (;;) {
+        if (max_iter >= 0 && --max_iter < 0) return 1;
+        const double lb = (1 - eta) * (d2 - xi2) / ((d + thickness) * L);
+        for (int a = 0; a < 3; ++a) { p[a] += lb * dp[a]; t0[a] += lb * dt0[a]; t1[a] += lb * dt1[a]; t2[a] += lb * dt2[a]; }
+        fem_pt_distance(p, t0, t1, t2, &d2, 0, 0);
+        d = sqrt(d2);
+        if (*toc != 0.0 && (d2 - xi2) / (d + thickness) < gap) break;
+        *toc += lb;
+        if (*toc > toc_prev) return 0;
+    }
+    return 1;
+}
+
+/* CCD step bound of the gel surface against the prescribed mesh indenter (it does not move during a Newton iteration): ACCD of every
+ * (vertex, triangle) pair that passes the reference's broad phase -- the box of the swept point against the triangle's box inflated
+ * by d_hat (ccd.inl:90-122) --, eta = 0.1, at most 1000 iterations, time horizon 1.1, step = min(1, min toc)
+ * (collision_detection/filters/lbvh_simplex_trajectory_filter.cu:892-1080, global_trajectory_filter.cu:76-98). */
+static double mesh_ccd_alpha(const fem_cfg* g, const fem_indenter* I, const double* x0, const double* dx, const int32_t* surf, int S)
+{
+    const double zero[3] = {0, 0, 0};
+    double alpha = 1.0;
+    for (int k = 0; k < S; ++k) {
+        const int i = surf[k];
+        double p[3], dp[3];
+        to_local(I, x0 + 3 * i, p);
+        for (int a = 0; a < 3; ++a) dp[a] = I->R[0 * 3 + a] * dx[3 * i] + I->R[1 * 3 + a] * dx[3 * i + 1] + I->R[2 * 3 + a] * dx[3 * i + 2];
+        for (int t = 0; t < g_mesh_n; ++t) {
+            const double* bx = g_mesh_box + 6 * t;
+            int far = 0;
+            for (int a = 0; a < 3; ++a) {
+                const double lo = dp[a] < 0 ? p[a] + dp[a] : p[a], hi = dp[a] < 0 ? p[a] : p[a] + dp[a];
+                if (lo - bx[3 + a] > g->d_hat || bx[a] - hi > g->d_hat) far = 1;
+            }
+            if (far) continue;
+            double toc = 1.1;
+            if (fem_pt_accd(p, g_mesh_tri + 9 * t, g_mesh_tri + 9 * t + 3, g_mesh_tri + 9 * t + 6, dp, zero, zero, zero, 0.1, 0.0, 1000, &toc)
+                && toc < alpha)
+                alpha = toc;
+        }
+    }
+    return alpha;
 }
 
 /* signed distance of a world point to the indenter, unit normal n = grad d, Hd = hessian of d (row-major; analytic kinds only) */
@@ -872,8 +940,10 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
         /* line search (sim_engine_do_advance.cu:276-347) */
         memcpy(x0, x, sizeof(double) * n);
         double alpha = 1.0;
-        /* CCD against the indenter: conservative advancement, keep 20 % of the gap (cf. eta = 0.1 ACCD) */
-        for (int k = 0; k < g->S; ++k) {
+        /* CCD against the indenter: conservative advancement, keep 20 % of the gap (cf. eta = 0.1 ACCD); the triangle mesh gets the
+           reference's ACCD per (vertex, triangle) pair */
+        if (c.ind.type == 2) alpha = mesh_ccd_alpha(g, &c.ind, x0, dx, surf, g->S);
+        else for (int k = 0; k < g->S; ++k) {
             int i = surf[k];
             double d, nn[3];
             fem_indenter_sdf(&c.ind, x0 + 3 * i, &d, nn, 0);

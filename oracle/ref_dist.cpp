@@ -3,6 +3,7 @@
 //   utils/distance/distance_flagged.h        point_triangle_distance_flag / point_edge_distance_flag / edge_edge_distance_flag and the
 //                                            flagged squared distances, gradients (12) and Hessians (12 x 12)
 //   utils/distance/{point_point,point_edge,point_triangle,edge_edge}.h + details/*.inl
+//   utils/distance/ccd.h + details/ccd.inl   point_triangle_ccd (additive CCD)
 // They are what the reference's narrow phase and barrier call for every point-triangle / edge-edge candidate
 // (collision_detection/filters/lbvh_simplex_trajectory_filter.cu:600-690, contact_system/contact_models/ipc_simplex_normal_contact.cu:270-342).
 // Eigen / muda are not in this image: oracle/ref_shim/ supplies the minimal stand-in. Built by oracle/Makefile into
@@ -14,6 +15,8 @@
 // does not). oracle/Makefile therefore pipes distance_flagged.h through ONE sed expression that inserts the keyword into a temporary
 // file outside the repo (deleted after the compile) -- every other reference file is read where it lies.
 #include REF_DISTANCE_FLAGGED_H
+#include <algorithm>
+#include <utils/distance/ccd.h> // + details/ccd.inl (ACCD); instantiated below: point_triangle_ccd only
 
 using namespace uipc;
 namespace D = uipc::backend::cuda::distance;
@@ -66,6 +69,13 @@ void ref_ee(const double* a0, const double* a1, const double* b0, const double* 
         G[i] = g(i);
         for (int j = 0; j < 12; ++j) H[12 * i + j] = h(i, j);
     }
+}
+
+// additive CCD of a point against a triangle, all four moving (positions + displacements over the step); returns hit, *toc in/out
+int ref_pt_ccd(const double* p, const double* t0, const double* t1, const double* t2, const double* dp, const double* dt0,
+               const double* dt1, const double* dt2, double eta, double thickness, int max_iter, double* toc)
+{
+    return D::point_triangle_ccd(v3(p), v3(t0), v3(t1), v3(t2), v3(dp), v3(dt0), v3(dt1), v3(dt2), eta, thickness, max_iter, *toc) ? 1 : 0;
 }
 
 } // extern "C"

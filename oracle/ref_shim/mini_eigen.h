@@ -114,6 +114,7 @@ struct Matrix {
     Matrix operator*(T s) const { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = d[i] * s; return m; }
     Matrix& operator*=(T s) { for (int i = 0; i < R * C; ++i) d[i] *= s; return *this; }
     Matrix& operator+=(const Matrix& o) { for (int i = 0; i < R * C; ++i) d[i] += o.d[i]; return *this; }
+    Matrix& operator-=(const Matrix& o) { for (int i = 0; i < R * C; ++i) d[i] -= o.d[i]; return *this; }
     template <int K>
     Matrix<T, R, K> operator*(const Matrix<T, C, K>& o) const
     {
@@ -144,5 +145,17 @@ inline Matrix<T, R, C> operator*(T s, const Matrix<T, R, C>& m) { return m * s; 
 
 template <class T, int N>
 using Vector = Matrix<T, N, 1>;
+
+// the little of Eigen::Array that utils/distance/details/ccd.inl touches (coefficient list + maxCoeff)
+template <class T, int R, int C>
+struct Array {
+    T d[R * C];
+    Array(T a, T b, T c) : d{a, b, c} { static_assert(R * C == 3, "size"); }
+    Array(T a, T b, T c, T e) : d{a, b, c, e} { static_assert(R * C == 4, "size"); }
+    T maxCoeff() const { T m = d[0]; for (int i = 1; i < R * C; ++i) m = d[i] > m ? d[i] : m; return m; }
+    T minCoeff() const { T m = d[0]; for (int i = 1; i < R * C; ++i) m = d[i] < m ? d[i] : m; return m; }
+};
+template <class T> using Array3 = Array<T, 3, 1>;
+template <class T> using Array4 = Array<T, 4, 1>;
 
 } // namespace Eigen

@@ -528,6 +528,75 @@ __device__ __forceinline__ bool mesh_contact(const FemArgs& a, const FemIndenter
     return true;
 }
 
+// CCD step bound of ONE gel vertex against the (static during a Newton iteration) mesh indenter: the reference's additive CCD per
+// (vertex, triangle) pair (utils/distance/details/ccd.inl:200-262: common translation removed, advance by the conservative bound until
+// the gap has shrunk to eta = 0.1 of its initial value; at most 1000 iterations, horizon 1.1) behind its broad phase (box of the swept
+// point vs the triangle's box inflated by d_hat, ccd.inl:90-122). Returns min(1, min toc). Same arithmetic as oracle/fem_canon.c
+// fem_pt_accd, which is pinned against the compiled reference.
+__device__ __noinline__ double mesh_ccd_impl(MeshRef m, double3 c, double3 r0, double3 r1, double3 r2, double3 xw, double3 dxw)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double q[3] = {xw.x - c.x, xw.y - c.y, xw.z - c.z}, dw[3] = {dxw.x, dxw.y, dxw.z};
+    double p0[3], dp0[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        p0[i] = R[0 * 3 + i] * q[0] + R[1 * 3 + i] * q[1] + R[2 * 3 + i] * q[2];
+        dp0[i] = R[0 * 3 + i] * dw[0] + R[1 * 3 + i] * dw[1] + R[2 * 3 + i] * dw[2];
+    }
+    const double eta = 0.1;
+    double alpha = 1.0;
+    for (int t = 0; t < m.n; ++t) {
+        const double* bx = m.box + 6 * t;
+        bool far = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double lo = dp0[a] < 0 ? p0[a] + dp0[a] : p0[a], hi = dp0[a] < 0 ? p0[a] : p0[a] + dp0[a];
+            if (lo - bx[3 + a] > m.d_hat || bx[a] - hi > m.d_hat) far = true;
+        }
+        if (far) continue;
+        double p[3], tr[9], dp[3], dt[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double mov = (0.0 + 0.0 + 0.0 + dp0[a]) / 4;
+            p[a] = p0[a];
+            dp[a] = dp0[a] - mov;
+            dt[a] = 0.0 - mov;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) tr[k] = m.tri[9 * t + k];
+        const double mm = dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2];
+        const double L = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) + sqrt(mm);
+        if (L <= 0.0) continue;
+        double g[3];
+        double d2 = pt_distance2(tr, p, g), d = sqrt(d2);
+        const double gap = eta * d2 / d, toc_prev = 1.1;
+        double toc = 0.0;
+        bool hit = true;
+        for (int it = 1000;;) {
+            if (--it < 0) break;
+            const double lb = (1 - eta) * d2 / (d * L);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                p[a] += lb * dp[a];
+                tr[a] += lb * dt[a]; tr[3 + a] += lb * dt[a]; tr[6 + a] += lb * dt[a];
+            }
+            d2 = pt_distance2(tr, p, g);
+            d = sqrt(d2);
+            if (toc != 0.0 && d2 / d < gap) break;
+            toc += lb;
+            if (toc > toc_prev) { hit = false; break; }
+        }
+        if (hit && toc < alpha) alpha = toc;
+    }
+    return alpha;
+}
+__device__ __forceinline__ double mesh_ccd(const FemArgs& a, const FemIndenter& I, const double* x0, const double* dx)
+{
+    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat};
+    return mesh_ccd_impl(m, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
+                         make_double3(I.R[6], I.R[7], I.R[8]), make_double3(x0[0], x0[1], x0[2]), make_double3(dx[0], dx[1], dx[2]));
+}
+
 template <bool MESH>
 __device__ void indenter_sdf(const FemArgs& a, const FemIndenter& I, const double* x, double* d, double* n, double* Hd)
 {
@@ -1145,7 +1214,9 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             double x0[3] = {0, 0, 0};
             if (on) { x0[0] = s.x[3 * i]; x0[1] = s.x[3 * i + 1]; x0[2] = s.x[3 * i + 2]; }
             double alpha = 1.0;
-            if (is_surf) {
+            if (MESH && ind.type == 2) {
+                if (is_surf) alpha = mesh_ccd(a, ind, x0, dx); // the reference's ACCD per (vertex, triangle) pair
+            } else if (is_surf) {
                 double d, nn[3];
                 indenter_sdf<MESH>(a, ind, x0, &d, nn, nullptr);
                 const double len = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);

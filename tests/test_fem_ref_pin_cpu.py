@@ -280,3 +280,61 @@ def test_per_candidate_barrier_block_projection_has_the_closed_form_the_kernel_u
         Hproj = (V * np.maximum(wv, 0)) @ V.T
         closed = max(0.0, ddB.value + dB.value / (2 * D)) * np.outer(g, g)
         assert np.abs(Hproj - closed).max() <= 1e-9 * max(np.abs(Hproj).max(), 1e-30)
+
+
+MUDA_VF = Path("/root/reference/source/tacex_uipc/libuipc/external/muda/test/data/unit-tests/vertex-face")
+
+
+def _vf_queries():
+    """muda's vertex-face CCD fixtures (rational coordinates num / den per axis + ground truth; 8 rows per query: the vertex and the
+    three face vertices at t = 0, then at t = 1)."""
+    out = []
+    for f in sorted(MUDA_VF.glob("*.csv")):
+        rows = np.loadtxt(f, delimiter=",", dtype=np.float64)
+        pts = np.stack([rows[:, 0] / rows[:, 1], rows[:, 2] / rows[:, 3], rows[:, 4] / rows[:, 5]], 1).reshape(-1, 8, 3)
+        truth = rows[:, 6].reshape(-1, 8)[:, 0].astype(bool)
+        out += [(q, bool(t)) for q, t in zip(pts, truth)]
+    return out
+
+
+@pytest.mark.skipif(not (REF_DIST.exists() and MUDA_VF.exists()), reason="needs oracle/_ref/libuipc_dist.so and the reference tree")
+def test_additive_ccd_matches_reference_source_on_mudas_vertex_face_fixtures(canon):
+    """fem_pt_accd vs the reference's point_triangle_ccd (utils/distance/details/ccd.inl compiled from where it lies) on the 250
+    vertex-face queries muda ships with ground truth: the same hit / miss decision and time of impact for every query, no collision
+    of the ground truth is missed by either (ACCD is conservative), and the same again for random sweeps against a static triangle
+    (the form the mesh-indenter path of the gel solver uses)."""
+    rd = C.CDLL(str(REF_DIST))
+    canon.fem_pt_accd.restype = C.c_int
+    qs = _vf_queries()
+    assert len(qs) == 250
+    n_hit = n_truth = 0
+
+    def both(p, t0, t1, t2, dp, d0, d1, d2, horizon):
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (p, t0, t1, t2, dp, d0, d1, d2)]
+        ta, tb = C.c_double(horizon), C.c_double(horizon)
+        ha = canon.fem_pt_accd(*[_d(a) for a in arrs], C.c_double(0.1), C.c_double(0.0), 1000, C.byref(ta))
+        hb = rd.ref_pt_ccd(*[_d(a) for a in arrs], C.c_double(0.1), C.c_double(0.0), 1000, C.byref(tb))
+        return ha, ta.value, hb, tb.value
+
+    for q, truth in qs:
+        d0 = np.linalg.norm(np.cross(q[2] - q[1], q[3] - q[1]))
+        if d0 == 0.0:
+            continue  # degenerate face: the closest-feature classification divides by the squared normal in both versions
+        ha, ta, hb, tb = both(q[0], q[1], q[2], q[3], q[4] - q[0], q[5] - q[1], q[6] - q[2], q[7] - q[3], 1.0)
+        assert ha == hb and (ta == tb or abs(ta - tb) <= 1e-12 * max(abs(tb), 1e-300) or (np.isnan(ta) and np.isnan(tb))), (q, ta, tb)
+        n_hit += ha
+        n_truth += truth
+        if truth:
+            assert ha == 1, q  # conservative: a true collision is never reported as a miss
+    assert n_truth > 20 and n_hit >= n_truth
+    rng = np.random.default_rng(3)
+    z = np.zeros(3)
+    hits = 0
+    for k in range(500):
+        t = rng.standard_normal((3, 3)) * 2e-3
+        p = t.mean(0) + rng.standard_normal(3) * 2e-3
+        dp = (t.mean(0) - p) * rng.uniform(0.2, 2.5) + rng.standard_normal(3) * 5e-4
+        ha, ta, hb, tb = both(p, t[0], t[1], t[2], dp, z, z, z, 1.1)
+        assert ha == hb and abs(ta - tb) <= 1e-12 * max(abs(tb), 1e-300), (k, ta, tb)
+        hits += ha
+    assert 100 < hits < 500
