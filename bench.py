@@ -626,6 +626,34 @@ def main() -> None:
                             "fp32_lane_ops_per_frame": fp32_lane_ops_per_frame(pool[:64])}
             del d, sets
 
+        # config 2: 1024 envs, sphere / flat cylinder / 90 deg wedge / 60 deg cone with random pose and in-plane yaw, RGB +
+        # FOTS markers along a trajectory: first contact (x0, y0, theta0), then sheared by U(-0.5, 0.5) mm and twisted by U(-30, 30) deg
+        E2 = min(1024, E)
+        c2 = synth.config2(min(128, E2), seed=1 + rank)
+        rep = (E2 + c2["depth_m"].shape[0] - 1) // c2["depth_m"].shape[0]
+        tile = lambda t: t.repeat(rep, *([1] * (t.dim() - 1)))[:E2].contiguous().to(dev)  # noqa: E731
+        hm_a, hm_b = tile(synth.height_map_mm(c2["depth_m0"])), tile(synth.height_map_mm(c2["depth_m"]))
+        th_a, th_b = tile(c2["theta0"]), tile(c2["theta"])
+        rgb2, dep2, mk2 = rgb[:E2], depth[:E2], run.markers[:E2]
+        tr2, tl2 = torch.zeros((E2, 4), device=dev), torch.zeros(E2, device=dev, dtype=torch.int32)
+        for j in range(4):
+            eng.render(hm_b if j % 2 else hm_a, None, out=rgb2, depth_out=dep2)
+            eng.fots_markers(dep2, th_b if j % 2 else th_a, tr2, tl2, out=mk2)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for j in range(2 * K):
+            eng.render(hm_b if j % 2 else hm_a, None, out=rgb2, depth_out=dep2)
+            eng.fots_markers(dep2, th_b if j % 2 else th_a, tr2, tl2, out=mk2)
+        b.record()
+        torch.cuda.synchronize()
+        dms = a.elapsed_time(b) / (2 * K)
+        extras["value_config2"] = {"value": E2 / (dms / 1e3), "unit": "frames/s per GPU", "ms_per_step": dms, "envs": E2,
+                                   "workload": "config 2: 1024 envs, random primitive indenters (sphere / flat cylinder / 90 deg wedge / 60 deg cone), "
+                                               f"random pose + yaw, RGB + FOTS {M}-marker motion along a shear / twist trajectory (steps alternate between "
+                                               "the first-contact and the moved pose); 128 unique maps tiled"}
+        del hm_a, hm_b
+
     # ---- end to end through the C ABI with HOST buffers (H2D + kernels + D2H inside the timed region) --------------
     rgb_host = torch.empty((E, H, W, 3)).pin_memory()
     depth_host = torch.empty(E).pin_memory()

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_fem_gpu.py -m gpu -x -q -s > gpurun_out/r02y_fem_pytest.log 2>&1; tail -8 gpurun_out/r02y_fem_pytest.log
+timeout 300 python tools/fem_time.py 4096 12 2 > gpurun_out/r02y_fem_time_wedge.log 2>&1; tail -3 gpurun_out/r02y_fem_time_wedge.log
+timeout 300 python tools/fem_time.py 4096 12 3 > gpurun_out/r02y_fem_time_cone.log 2>&1; tail -3 gpurun_out/r02y_fem_time_cone.log
