@@ -20,6 +20,7 @@ struct tx_fem {
     int *d_adj_off = nullptr, *d_adj = nullptr, *d_edge_off = nullptr, *d_edge_adj = nullptr, *d_ell = nullptr;
     int *d_attach_of = nullptr, *d_surf_of = nullptr;
     int nE = 0, n_s = 0, nslots = 0;
+    int chunk = 0; // tets per assembly chunk (<= threads): sets the per-CTA scratch footprint in L2
     long long* d_cycles = nullptr;
     int grid = 0;
     // markers
@@ -37,6 +38,8 @@ struct tx_fem {
     double *d_mesh_tri = nullptr, *d_mesh_box = nullptr;
 };
 
+// Default assembly chunk (see fem_kernel.cu, grad_hess): measured on the B200, profiles/r02_fem_chunk.txt
+static constexpr int FEM_DEFAULT_CHUNK = 576;
 static std::string g_fem_err;
 static int ffail(tx_fem* f, int code, const std::string& m)
 {
@@ -69,6 +72,12 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
     f->cfg = *c;
     f->device = device;
     f->stream = (cudaStream_t)cuda_stream;
+    {   // tets per assembly chunk: a multiple of 32 in [32, threads]; TX_FEM_CHUNK overrides the default for experiments
+        int ch = FEM_DEFAULT_CHUNK;
+        if (const char* ev = getenv("TX_FEM_CHUNK")) ch = atoi(ev);
+        ch = (ch / 32) * 32;
+        f->chunk = ch < 32 ? 32 : (ch > fem_threads() ? fem_threads() : ch);
+    }
     // precompute Dm^-1, elastic rest volume, lumped mass (ref: finite_element_method.cu:957-982, 721-744)
     std::vector<double> Dmi((size_t)9 * c->T), vol(c->T);
     f->mass.assign(c->V, 0.0);
@@ -175,12 +184,12 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
         }
         std::vector<int> es;
         {
-            const int nch = (c->T + TH - 1) / TH;
+            const int TCH = f->chunk, nch = (c->T + TCH - 1) / TCH;
             es.assign((size_t)(nch + 1) * nE, 0);
             for (int e = 0; e < nE; ++e) {
                 int q = eoff[e];
                 for (int ck = 0; ck <= nch; ++ck) {
-                    while (q < eoff[e + 1] && (eadj[q] >> 4) < ck * TH) ++q;
+                    while (q < eoff[e + 1] && (eadj[q] >> 4) < ck * TCH) ++q;
                     es[(size_t)ck * nE + e] = q;
                 }
             }
@@ -208,12 +217,12 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
         FEM_CUDA_C(cudaMalloc(&f->d_adj_off, sizeof(int) * (c->V + 1)));
         FEM_CUDA_C(cudaMalloc(&f->d_adj, sizeof(int) * 4 * c->T));
         {   // per chunk of one-tet-per-thread: where the entries of every row start
-            const int TH = fem_threads(), nch = (c->T + TH - 1) / TH;
+            const int TH = fem_threads(), TCH = f->chunk, nch = (c->T + TCH - 1) / TCH;
             std::vector<int> rs((size_t)(nch + 1) * TH, 0);
             for (int i = 0; i < c->V; ++i) {
                 int q = off[i];
                 for (int ck = 0; ck <= nch; ++ck) {
-                    while (q < off[i + 1] && (adj[q] >> 2) < ck * TH) ++q;
+                    while (q < off[i + 1] && (adj[q] >> 2) < ck * TCH) ++q;
                     rs[(size_t)ck * TH + i] = q;
                 }
             }
@@ -273,7 +282,7 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.tet_scratch = f->d_tsc;
     a.val_scratch = f->d_valg;
     a.xt_scratch = f->d_xt;
-    a.nE = f->nE; a.n_s = f->n_s; a.nslots = f->nslots;
+    a.nE = f->nE; a.n_s = f->n_s; a.nslots = f->nslots; a.chunk = f->chunk;
     a.edge_start = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
     a.attach_of = f->d_attach_of; a.surf_of = f->d_surf_of;
     a.mesh_tri = f->d_mesh_tri; a.mesh_box = f->d_mesh_box; a.mesh_n = f->mesh_n;

@@ -898,7 +898,7 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
 {
     long long tg0 = cyc ? clock64() : 0;
     const double dt2 = a.dt * a.dt;
-    constexpr int TC = FEM_THREADS;
+    const int TC = a.chunk; // tets per chunk: one tet per thread of the first TC threads
     const int i = threadIdx.x;
     const bool on = i < a.V;
     double m = 0.0, xi[3] = {0, 0, 0};
@@ -913,7 +913,7 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
     for (int c0 = 0; c0 < a.T; c0 += TC) {
         // (1) per tet: gradient (12), the 4 diagonal and the 6 off-diagonal 3x3 blocks
         const int t = c0 + threadIdx.x;
-        if (t < a.T) {
+        if (threadIdx.x < TC && t < a.T) {
             const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
             const int e[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
             double W[4][3], F[9];

@@ -180,6 +180,7 @@ struct FemArgs {
     const int* row_start;  // [nchunks+1][576] per chunk of 576 tets: first entry of `adj` (ascending tets) of every row
     const int* adj;        // [4T]
     int nE, n_s, nslots;   // edges (i < j) of the vertex graph, edges kept in shared memory, ELL width
+    int chunk;             // tets per assembly chunk (<= FEM threads, multiple of 32): row_start / edge_start are built for it
     const int* edge_start; // [nchunks+1][nE] per chunk: first entry of `edge_adj` (ascending tets) of every edge
     const int* edge_adj;   // entries = tet << 4 | pair slot << 1 | transpose
     const int* ell;        // [nslots][FEM threads] row -> (neighbour j | transposed << 12 | edge << 13), -1 = empty
