@@ -627,6 +627,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     fc.dst = p.rgb + half_off * 3;
     fc.ry0 = 0; fc.ry1 = -1; fc.xa = 0; fc.xb = -1; fc.done = 0u;
     fc.coherent_src = LOWRES;
+    int rect_a0 = 0, rect_a1 = -1; // IMAGE rows of the frame's rectangle (both halves): the colour stage is shared between the CTAs
     if (active && !(p.dbg & 4)) {
         constexpr int GROW = 30 + 16 + 8 + 4 + 2 + 1 + 2;
         const int base = (int)q * HALF_H;
@@ -636,6 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         const int a1 = fr1 + 1 >= IMG_H - 2 ? IMG_H - 1 : fr1 + 1;     // row 239 samples row 238
         fc.ry0 = max(a0, base) - base;
         fc.ry1 = min(a1, base + HALF_H - 1) - base;
+        rect_a0 = a0; rect_a1 = a1;
         fc.xa = fc0 - 1 <= 1 ? 0 : ((fc0 - 1) & ~3);                   // column 0 samples column 1
         fc.xb = fc1 + 1 >= IMG_W - 2 ? IMG_W - 1 : ((fc1 + 1) | 3);    // column 319 samples column 318
     }
@@ -707,21 +709,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
     //       of 3 x 32 scalar accesses with a 12-byte stride; the gather of the NEXT block is requested before the current
     //       block is evaluated (software pipeline).
     const float PI_F = 3.14159265358979323846f;
-    const float* bg_half = p.bg_hwc + (size_t)q * HALF_H * IMG_W * 3;
-    float* rgb_half = p.rgb + half_off * 3;
-    float* rgb_mc_half = p.rgb_mc ? p.rgb_mc + half_off * 3 : nullptr;
     float* stage = hb0 + warp * (32 * 20); // 32 records x 20 floats per warp; hb0 is free now (16 x 2560 B = 40,960 B)
     float* iost = hb1 + IOST_OFF + warp * 192; // per warp: 96 floats of background + 96 floats of RGB
     const float* halo1 = hb1 + HALO1_OFF;
-    const int ry0 = fc.ry0, ry1 = fc.ry1, xa = fc.xa, xb = fc.xb;
+    const int xa = fc.xa, xb = fc.xb;
     // (1) flat copy of everything outside the rectangle: the slices no idle warp has taken during the pyramid
     for (int sl = 0; sl < FC_SLICES; ++sl)
         if (!((fc.done >> sl) & 1u)) flat_copy_slice(fc, sl, tid, NTHREADS);
-    // (2) the rectangle
-    const int nw = (fc.total > 0 && xb >= xa) ? xb - xa + 1 : 0; // rectangle width in pixels (multiple of 4)
-    const int nbr = (nw + 31) >> 5;                               // 32-pixel blocks per rectangle row
-    const int nblk = nw > 0 ? nbr * (ry1 - ry0 + 1) : 0;
+    // (2) the rectangle. Its rows are split between the two halves as the contact happens to lie (typically 60 / 40), so the
+    // 32-pixel blocks of BOTH halves are numbered through (half 0 first) and each CTA evaluates one half of the blocks: the CTA
+    // whose half holds less of the rectangle takes rows of its peer, reading the peer's final plane through distributed shared
+    // memory (4 loads per pixel against ~250 instructions). Same arithmetic per pixel whoever evaluates it: bit-identical.
+    const float* plane_peer = cluster.map_shared_rank(plane, q ^ 1u);
+    const int nw = (fc.total > 0 || rect_a1 >= rect_a0) && xb >= xa ? xb - xa + 1 : 0; // rectangle width in pixels (multiple of 4)
+    const int nbr = (nw + 31) >> 5;                                                     // 32-pixel blocks per rectangle row
+    const int r0_lo = rect_a0, r0_hi = min(rect_a1, HALF_H - 1);                         // image rows of the rectangle in half 0
+    const int r1_lo = max(rect_a0, HALF_H), r1_hi = rect_a1;                             // ... in half 1
+    const int rows0 = nw > 0 ? max(r0_hi - r0_lo + 1, 0) : 0, rows1 = nw > 0 ? max(r1_hi - r1_lo + 1, 0) : 0;
+    const int nblk0 = nbr * rows0, nblk_all = nbr * (rows0 + rows1);
+#ifdef TX_NO_COLOUR_BALANCE
+    const int g_begin = q ? nblk0 : 0, g_end = q ? nblk_all : nblk0; // every CTA its own half (A/B reference)
+#else
+    const int g_split = (nblk_all + 1) >> 1;
+    const int g_begin = q ? g_split : 0, g_end = q ? nblk_all : g_split;
+#endif
     const float inv_nbr = nbr > 0 ? 1.0f / (float)nbr : 0.0f;
+    const float* bg_img = p.bg_hwc;
+    float* rgb_img = p.rgb + (size_t)n * IMG_H * IMG_W * 3;
+    float* rgb_mc_img = p.rgb_mc ? p.rgb_mc + (size_t)n * IMG_H * IMG_W * 3 : nullptr;
     float4 rec[5], bg4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int g_rec[5], g_part[5]; // lane-constant gather pattern: float4 index e * 32 + lane = record (idx / 5), part (idx % 5)
 #pragma unroll
@@ -731,18 +746,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         g_part[e] = idx - g_rec[e] * 5;
     }
     int row_n = 0, xs_n = 0;
+    // `row` is the IMAGE row from here on
     auto block_bin = [&](int bi, int& row, int& xs) -> int {
-        const int rr = __float2int_rz(__fmul_rn((float)bi + 0.5f, inv_nbr)); // == bi / nbr (bi < 2^12, error << 0.5 / nbr)
-        row = ry0 + rr;
-        xs = xa + 32 * (bi - rr * nbr);
+        const int h = bi >= nblk0 ? 1 : 0;          // half the block lies in
+        const int li = bi - h * nblk0;
+        const int rr = __float2int_rz(__fmul_rn((float)li + 0.5f, inv_nbr)); // == li / nbr (li < 2^12, error << 0.5 / nbr)
+        row = (h ? r1_lo : r0_lo) + rr;
+        xs = xa + 32 * (li - rr * nbr);
         const int x = min(xs + lane, xb);
-        const int gy_ = (int)q * HALF_H + row; // image row
         // replicate padding of the gradient maps: border pixels take the nearest interior pixel's (mag, dir)
-        const int yy = min(max(gy_, 1), IMG_H - 2) - (int)q * HALF_H; // local row of the sampled pixel
+        const int yy = min(max(row, 1), IMG_H - 2) - h * HALF_H; // local row (in half h) of the sampled pixel
         const int xx = min(max(x, 1), IMG_W - 2);
-        const float* ctr = plane + yy * IMG_W + xx;
-        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : halo1 + xx;
-        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : halo1 + xx;
+        const bool mine = (unsigned)h == q;
+        const float* ctr = (mine ? plane : plane_peer) + yy * IMG_W + xx;
+        // the row across the boundary between the halves: the peer's boundary row (halo1) for a pixel of this CTA's half, this
+        // CTA's own boundary row for a pixel of the peer's half
+        const float* across = mine ? halo1 + xx : plane + (q == 0 ? HALF_H - 1 : 0) * IMG_W + xx;
+        const float* up = (yy - 1 >= 0) ? ctr - IMG_W : across;
+        const float* dn = (yy + 1 < HALF_H) ? ctr + IMG_W : across;
         const float top = __fmul_rn(*up, p.inv_pixmm), bot = __fmul_rn(*dn, p.inv_pixmm);
         const float lef = __fmul_rn(ctr[-1], p.inv_pixmm), rig = __fmul_rn(ctr[1], p.inv_pixmm);
         const float gx = __fmul_rn(__fmul_rn(__fadd_rn(top, -bot), 0.5f), p.sy);
@@ -766,21 +787,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         }
         // background of the block: 3 * nval contiguous floats, 128-bit loads by the first lanes
         const int nval = min(32, xb - xs + 1);
-        if (4 * lane < 3 * nval) bg4 = __ldg(reinterpret_cast<const float4*>(bg_half + ((size_t)row * IMG_W + xs) * 3) + lane);
+        if (4 * lane < 3 * nval) bg4 = __ldg(reinterpret_cast<const float4*>(bg_img + ((size_t)row * IMG_W + xs) * 3) + lane);
     };
     // Software pipeline, three blocks deep: iteration i stages the records of block i (requested one iteration ago), requests
     // the records of block i + 1 (its bins were computed one iteration ago), computes the bins of block i + 2 -- the long
     // dependent sqrt / atan / atan2 chain, which covers the L2 round trip of the request -- and evaluates block i.
-    int bi = warp;
+    int bi = g_begin + warp;
     int row_c = 0, xs_c = 0;     // block i (records in flight / staged)
     int bin_n = 0;               // block i + 1 (bins known)
-    if (bi < nblk) {
+    if (bi < g_end) {
         const int b = block_bin(bi, row_c, xs_c);
         request(b, row_c, xs_c);
-        if (bi + NWARPS < nblk) bin_n = block_bin(bi + NWARPS, row_n, xs_n);
+        if (bi + NWARPS < g_end) bin_n = block_bin(bi + NWARPS, row_n, xs_n);
     }
 #pragma unroll 1
-    for (; bi < nblk; bi += NWARPS) {
+    for (; bi < g_end; bi += NWARPS) {
         const int row = row_c, xs = xs_c;
         const int nval = min(32, xb - xs + 1);
         __syncwarp();
@@ -789,10 +810,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         for (int e = 0; e < 5; ++e) reinterpret_cast<float4*>(stage)[e * 32 + lane] = rec[e];
         if (4 * lane < 3 * nval) reinterpret_cast<float4*>(iost)[lane] = bg4;
         // block i + 1: its requests go out now; block i + 2: bins
-        if (bi + NWARPS < nblk) {
+        if (bi + NWARPS < g_end) {
             row_c = row_n; xs_c = xs_n;
             request(bin_n, row_c, xs_c);
-            if (bi + 2 * NWARPS < nblk) bin_n = block_bin(bi + 2 * NWARPS, row_n, xs_n);
+            if (bi + 2 * NWARPS < g_end) bin_n = block_bin(bi + 2 * NWARPS, row_n, xs_n);
         }
         __syncwarp();
         float cf[20];
@@ -802,7 +823,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             cf[4 * e] = t.x; cf[4 * e + 1] = t.y; cf[4 * e + 2] = t.z; cf[4 * e + 3] = t.w;
         }
         const float bgv[3] = {iost[3 * lane], iost[3 * lane + 1], iost[3 * lane + 2]};
-        const float yf = __fmul_rn((float)((int)q * HALF_H + row), p.fy);
+        const float yf = __fmul_rn((float)row, p.fy);
         const float xf = __fmul_rn((float)(xs + lane), p.fx);
         float o[3];
         poly_rgb(cf, xf, yf, __fmul_rn(xf, xf), __fmul_rn(yf, yf), __fmul_rn(xf, yf), bgv, o);
@@ -811,11 +832,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
         if (4 * lane < 3 * nval) {
             const float4 v = reinterpret_cast<const float4*>(iost + 96)[lane];
             const size_t off = ((size_t)row * IMG_W + xs) * 3 + 4 * lane;
-            if (rgb_mc_half) multimem_st_f4(rgb_mc_half + off, v); // fused all-gather: into every GPU's buffer (this one included)
-            else *reinterpret_cast<float4*>(rgb_half + off) = v;
+            if (rgb_mc_img) multimem_st_f4(rgb_mc_img + off, v); // fused all-gather: into every GPU's buffer (this one included)
+            else *reinterpret_cast<float4*>(rgb_img + off) = v;
         }
     }
-    __syncthreads();
+    cluster.sync(); // the peer may still be reading this CTA's plane
     TX_TICK(33);
 }
 

@@ -290,3 +290,56 @@ def test_triangle_mesh_indenter_of_the_restatement():
     p = x[0, cf.surf] - np.array([1e-3, 0.0, z0 - 1e-3])  # surface vertices in the wedge's frame
     inside = (np.abs(p[:, 0]) < size) & (np.abs(p[:, 1]) < 2 * size) & (p[:, 2] > np.abs(p[:, 0])) & (p[:, 2] < size)
     assert not inside.any() and np.abs(x - cf.X).max() > 1e-4
+
+
+def test_step_driver_converges_to_the_stationary_point_an_independent_dense_newton_finds():
+    """The Newton / PCG / line-search / CCD driver of the restatement (the part no reference source can pin) against an INDEPENDENT
+    solver of the same incremental potential: plain Newton iterations with numpy's dense LU on the assembled system and energy
+    backtracking. A sphere resting inside the barrier zone of the gel (with gravity, attachment and friction terms active): the
+    step must end where the dense Newton iteration ends -- to within its own stopping rule (relative Newton tolerance 1e-3) --, and the
+    gradient there must have dropped accordingly."""
+    m, cf = _small()
+    g = cf.cfg
+    n = 3 * g.V
+    ind = fc.make_indenter(0, (0.5e-3, -0.3e-3, 4.5e-3 + 3e-3 + 3e-4), (3e-3, 0, 0))  # 0.3 mm above the gel: inside d_hat = 0.5 mm
+    aim = cf.X[cf.attach].copy()
+    xp = cf.X.copy()
+    xt = cf.X + np.array(list(g.gravity)) * g.dt * g.dt
+
+    def eval_(xx, want_A=True):
+        A = np.zeros((n, n)); b = np.zeros(n); E = C.c_double()
+        fc.lib().fem_assemble_dense(C.byref(g), fc._i(cf.tets), fc._d(cf.Dm_inv), fc._d(cf.vol), fc._d(cf.mass), fc._i(cf.attach),
+                                    fc._i(cf.surf), fc._d(aim), C.byref(ind), fc._d(np.ascontiguousarray(xx)), fc._d(xp), fc._d(xt),
+                                    C.c_double(1.0), fc._d(A), fc._d(b), C.byref(E))
+        return E.value, b, A
+
+    x = cf.X.copy()
+    for it in range(60):
+        E0, b, A = eval_(x)
+        dx = np.linalg.solve(A, b).reshape(x.shape)
+        a = 1.0
+        while True:
+            E1 = eval_(x + a * dx)[0]
+            if np.isfinite(E1) and E1 <= E0:
+                break
+            a *= 0.5
+            assert a > 1e-12
+        x = x + a * dx
+        if np.abs(dx).max() < 5e-12:  # quadratic convergence reaches the rounding floor (~1e-12 m) after two or three iterations
+            break
+    assert it < 10
+    old = (g.velocity_tol, g.pcg_tol_rate)
+    g.velocity_tol, g.pcg_tol_rate = 1e-9, 1e-14
+    try:
+        xs, vs, xps = cf.new_state(1)
+        st = cf.step(xs, vs, xps, aim[None], [ind], [ind])
+    finally:
+        g.velocity_tol, g.pcg_tol_rate = old
+    assert st[0]["converged"] == 1
+    disp = np.abs(x - cf.X).max()
+    assert disp > 5e-6  # the barrier (and gravity) really moved the gel
+    # the driver stops at |dx| <= 1e-3 |dx of the first iteration| (the reference's relative Newton tolerance, max_translation_checker.cu:25-50)
+    assert np.abs(xs[0] - x).max() <= 1.5e-3 * disp, (np.abs(xs[0] - x).max(), disp)
+    _, b_end, _ = eval_(xs[0])
+    _, b0, _ = eval_(cf.X)
+    assert np.abs(b_end).max() <= 5e-3 * np.abs(b0).max()
