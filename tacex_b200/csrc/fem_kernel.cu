@@ -600,8 +600,13 @@ __device__ __forceinline__ double mesh_ccd(const FemArgs& a, const FemIndenter& 
 template <bool MESH>
 __device__ void indenter_sdf(const FemArgs& a, const FemIndenter& I, const double* x, double* d, double* n, double* Hd)
 {
-    if (MESH && I.type == 2) { // triangle mesh: UNSIGNED distance (Hd is not defined: the barrier goes through mesh_contact)
-        mesh_contact(a, I, x, 0.0, d, n, nullptr, nullptr, nullptr);
+    if (I.type == 2) {
+        if (MESH) { // triangle mesh: UNSIGNED distance (Hd is not defined: the barrier goes through mesh_contact)
+            mesh_contact(a, I, x, 0.0, d, n, nullptr, nullptr, nullptr);
+        } else { // no mesh has been set: a type-2 indenter is no indenter
+            *d = 1e150; n[0] = 0.0; n[1] = 0.0; n[2] = 1.0;
+            if (Hd) for (int k = 0; k < 9; ++k) Hd[k] = 0.0;
+        }
         return;
     }
     double p[3], q[3];

@@ -836,7 +836,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
             else *reinterpret_cast<float4*>(rgb_img + off) = v;
         }
     }
-    cluster.sync(); // the peer may still be reading this CTA's plane
+    // a CTA that took blocks of the other half may still be reading its peer's plane: nobody leaves before both are done (the
+    // decision is the same in both CTAs: it only depends on the frame's rectangle)
+    if (g_end - g_begin != (q ? nblk_all - nblk0 : nblk0)) cluster.sync();
+    else __syncthreads();
     TX_TICK(33);
 }
 

@@ -262,3 +262,22 @@ def test_triangle_mesh_indenter_matches_cpu_restatement(kind):
     assert float((x - eng.X).abs().max()) > 2e-4  # the gels really deformed
     # a handle without a mesh keeps running the analytic kernel; removing the mesh switches back
     eng.set_indenter_mesh(None)
+
+
+def test_mesh_indenter_argument_checks():
+    from tacex_b200 import _lib
+
+    m, eng, cf, fc = _setup((10, 12, 3), 1e-3, 1)
+    with pytest.raises(_lib.TxError):
+        eng.set_indenter_mesh(np.zeros((4, 3, 2)))  # wrong shape
+    with pytest.raises(_lib.TxError):
+        eng.set_indenter_mesh(np.zeros((1, 3, 3)))  # degenerate triangle
+    eng.set_indenter_mesh(np.array([[[0, 0, 0], [1e-3, 0, 0], [0, 1e-3, 0]]], float))
+    eng.set_indenter_mesh(None)
+    # a type-2 indenter without a mesh is "no indenter": the step runs and nothing touches the gel
+    from tacex_b200 import fem
+
+    x, v, xp = eng.new_state(1)
+    far = fem.indenter_array(2, [[0, 0, 4.5e-3 + 1e-4]], (0, 0, 0))
+    st = eng.decode_stats(eng.step(x, v, xp, eng.rest_aim(1), far, far))
+    assert st[0]["converged"] == 1 and float((x[0] - eng.X).abs().max()) < 5e-5
