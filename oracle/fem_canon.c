@@ -32,7 +32,14 @@
  * restricted to the degrees of freedom of the gel vertex (the indenter is prescribed). fem_pt_distance is PINNED against the
  * reference's distance_flagged.h compiled here (oracle/ref_dist.cpp -> oracle/_ref/libuipc_dist.so, tests/test_fem_ref_pin_cpu.py).
  * The CCD step bound of the mesh path is the reference's ACCD per (vertex, triangle) pair (fem_pt_accd, pinned against ccd.inl).
- * Not restated: triangle(gel)-point(indenter) and edge-edge candidates, LBVH (every triangle is tested against its box).
+ * The second half of the vertex-face contact -- every VERTEX of the indenter mesh against every TRIANGLE of the gel's contact surface
+ * (fem_set_contact_surface) -- uses the same closest-feature classification, squared distance and barrier per candidate, with the
+ * exact gradient with respect to the three gel vertices (envelope theorem: dD/dt_j = -2 w_j (p - c), c = sum w_j t_j the closest
+ * point; pinned against the reference's 12-gradient) and a GAUSS-NEWTON Hessian: the closest point's barycentric weights frozen,
+ * which after make_spd leaves max(0, B'' + B' / (2 D)) g g^T -- exact energy and gradient, hence the same minimiser as the
+ * reference's model; only the curvature terms of a sliding closest point are dropped (stated in DESIGN.md). ACCD with the moving
+ * triangle as in the reference. No friction on these candidates.
+ * Not restated: edge-edge candidates (+ mollifier), LBVH (every triangle is tested against its box).
  *
  * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
  * has no CPU backend) and its tests hold no golden positions for this path: the SOLVER LOOP of this
@@ -210,6 +217,7 @@ void fem_barrier(double D, double d_hat, double kappa, double* B, double* dB, do
 static double* g_mesh_tri = 0;  /* [n][9] local-frame triangles */
 static double* g_mesh_box = 0;  /* [n][6] lo / hi */
 static int g_mesh_n = 0;
+static void mesh_unique_vertices(void);
 void fem_set_indenter_mesh(const double* tri, int n)
 {
     free(g_mesh_tri); free(g_mesh_box);
@@ -228,6 +236,33 @@ void fem_set_indenter_mesh(const double* tri, int n)
             g_mesh_box[6 * t + a] = lo;
             g_mesh_box[6 * t + 3 + a] = hi;
         }
+    mesh_unique_vertices();
+}
+
+static double* g_mesh_vert = 0; /* [nv][3] unique vertices of the indenter mesh (local frame) */
+static int g_mesh_nv = 0;
+static int32_t* g_ctri = 0;     /* [n][3] triangles of the gel's contact surface (vertex ids) */
+static int g_nctri = 0;
+static void mesh_unique_vertices(void)
+{
+    free(g_mesh_vert);
+    g_mesh_vert = (double*)malloc(sizeof(double) * 9 * (g_mesh_n > 0 ? g_mesh_n : 1));
+    g_mesh_nv = 0;
+    for (int k = 0; k < 3 * g_mesh_n; ++k) {
+        const double* v = g_mesh_tri + 3 * k;
+        int found = 0;
+        for (int j = 0; j < g_mesh_nv && !found; ++j)
+            found = g_mesh_vert[3 * j] == v[0] && g_mesh_vert[3 * j + 1] == v[1] && g_mesh_vert[3 * j + 2] == v[2];
+        if (!found) { memcpy(g_mesh_vert + 3 * g_mesh_nv, v, sizeof(double) * 3); ++g_mesh_nv; }
+    }
+}
+/* triangles (vertex ids) of the gel surface that the indenter's vertices can touch; n = 0 switches that half of the contact off */
+void fem_set_contact_surface(const int32_t* tris, int n)
+{
+    free(g_ctri);
+    g_ctri = (int32_t*)malloc(sizeof(int32_t) * 3 * (n > 0 ? n : 1));
+    g_nctri = n;
+    if (n > 0) memcpy(g_ctri, tris, sizeof(int32_t) * 3 * n);
 }
 
 /* Closest feature of the triangle (t0, t1, t2) to the point p, squared distance D, dD/dp (3) and d2D/dp2 (9, row-major).
@@ -290,6 +325,43 @@ int fem_pt_distance(const double* p, const double* t0, const double* t1, const d
             for (int a = 0; a < 3; ++a)
                 for (int b = 0; b < 3; ++b) H[3 * a + b] = 2.0 * n[a] * n[b] / nn;
     }
+    return kind;
+}
+
+/* Closest point c = sum w_j t_j of the triangle to p: same classification and squared distance as fem_pt_distance, plus r = p - c and
+ * the barycentric weights w. By the envelope theorem the full gradient of D is 2 r (x) [1, -w0, -w1, -w2] (p, t0, t1, t2). */
+int fem_pt_closest(const double* p, const double* t0, const double* t1, const double* t2, double* D, double* r, double* w)
+{
+    const double* T[3] = {t0, t1, t2};
+    const int kind = fem_pt_distance(p, t0, t1, t2, D, 0, 0);
+    w[0] = w[1] = w[2] = 0.0;
+    if (kind >= 4) {
+        w[kind - 4] = 1.0;
+    } else if (kind >= 1) {
+        const int is = kind - 1, it = kind % 3;
+        const double *s = T[is], *t = T[it];
+        double uu = 0.0, qu = 0.0;
+        for (int a = 0; a < 3; ++a) { uu += (t[a] - s[a]) * (t[a] - s[a]); qu += (p[a] - s[a]) * (t[a] - s[a]); }
+        const double al = qu / uu;
+        w[is] = 1.0 - al;
+        w[it] = al;
+    } else {
+        double v0[3], v1[3], n[3], c[3];
+        for (int a = 0; a < 3; ++a) { v0[a] = t1[a] - t0[a]; v1[a] = t2[a] - t0[a]; }
+        n[0] = v0[1] * v1[2] - v0[2] * v1[1];
+        n[1] = v0[2] * v1[0] - v0[0] * v1[2];
+        n[2] = v0[0] * v1[1] - v0[1] * v1[0];
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double sd = n[0] * (p[0] - t0[0]) + n[1] * (p[1] - t0[1]) + n[2] * (p[2] - t0[2]);
+        for (int a = 0; a < 3; ++a) c[a] = p[a] - sd / nn * n[a] - t0[a];
+        const double d00 = v0[0] * v0[0] + v0[1] * v0[1] + v0[2] * v0[2], d01 = v0[0] * v1[0] + v0[1] * v1[1] + v0[2] * v1[2],
+                     d11 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], d20 = c[0] * v0[0] + c[1] * v0[1] + c[2] * v0[2],
+                     d21 = c[0] * v1[0] + c[1] * v1[1] + c[2] * v1[2], den = d00 * d11 - d01 * d01;
+        w[1] = (d11 * d20 - d01 * d21) / den;
+        w[2] = (d00 * d21 - d01 * d20) / den;
+        w[0] = 1.0 - w[1] - w[2];
+    }
+    for (int a = 0; a < 3; ++a) r[a] = p[a] - (w[0] * t0[a] + w[1] * t1[a] + w[2] * t2[a]);
     return kind;
 }
 
@@ -501,6 +573,7 @@ static void tet_F(const double* x, const int32_t* e, const double W[4][3], doubl
         }
 }
 
+struct fem_tp_s;
 typedef struct {
     const fem_cfg* cfg;
     const int32_t* tets;
@@ -512,7 +585,109 @@ typedef struct {
     double ratio;        /* animation substep ratio */
     fem_indenter ind;    /* current (interpolated) indenter */
     fem_indenter ind0;   /* indenter at the start of the step (lagged friction) */
+    struct fem_tp_s* tp; /* active (indenter vertex, gel triangle) candidates of the last grad_hess (Gauss-Newton rank-1 terms) */
 } fem_ctx;
+
+/* ---- indenter VERTEX against gel TRIANGLE candidates (second half of the vertex-face contact) ------------------------------------ */
+typedef struct fem_tp_s { int n, cap; int32_t* tri; double* g9; double* w; } fem_tp;
+static void tp_push(fem_tp* tp, int f, const double* g9, double w)
+{
+    if (tp->n == tp->cap) {
+        tp->cap = tp->cap ? 2 * tp->cap : 256;
+        tp->tri = (int32_t*)realloc(tp->tri, sizeof(int32_t) * tp->cap);
+        tp->g9 = (double*)realloc(tp->g9, sizeof(double) * 9 * tp->cap);
+        tp->w = (double*)realloc(tp->w, sizeof(double) * tp->cap);
+    }
+    tp->tri[tp->n] = f;
+    memcpy(tp->g9 + 9 * tp->n, g9, sizeof(double) * 9);
+    tp->w[tp->n++] = w;
+}
+static void mesh_vertex_world(const fem_indenter* I, int k, double* pw)
+{
+    const double* l = g_mesh_vert + 3 * k;
+    for (int i = 0; i < 3; ++i) pw[i] = I->c[i] + I->R[i * 3 + 0] * l[0] + I->R[i * 3 + 1] * l[1] + I->R[i * 3 + 2] * l[2];
+}
+/* Energy, gradient (accumulated into G [V][3]), Gauss-Newton diagonal blocks (accumulated into Dg [V][9]) and the candidate list of
+ * the indenter's vertices against the gel's contact triangles at positions x; *dmin = smallest distance of any such pair. All
+ * outputs optional. Returns the energy (INFINITY when a vertex touches a triangle). */
+static double tp_terms(const fem_cfg* g, const fem_indenter* I, const double* x, double* G, double* Dg, fem_tp* tp, double* dmin)
+{
+    double E = 0.0, best = 1e300;
+    const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
+    if (tp) tp->n = 0;
+    if (I->type != 2 || g_nctri == 0) { if (dmin) *dmin = 1e150; return 0.0; }
+    for (int f = 0; f < g_nctri; ++f) {
+        const int32_t* tv = g_ctri + 3 * f;
+        const double *xa = x + 3 * tv[0], *xb = x + 3 * tv[1], *xc = x + 3 * tv[2];
+        double box[6];
+        for (int a = 0; a < 3; ++a) {
+            box[a] = fmin(xa[a], fmin(xb[a], xc[a]));
+            box[3 + a] = fmax(xa[a], fmax(xb[a], xc[a]));
+        }
+        for (int k = 0; k < g_mesh_nv; ++k) {
+            double pw[3], D, r[3], w[3], B, dB, ddB;
+            mesh_vertex_world(I, k, pw);
+            const double bd = box_dist2(box, pw);
+            if (!(bd < best) && !(bd < D0)) continue;
+            fem_pt_closest(pw, xa, xb, xc, &D, r, w);
+            if (D < best) best = D;
+            if (!(D < D0)) continue;
+            if (!(D > 0.0)) { E = INFINITY; continue; }
+            fem_barrier(D, g->d_hat, kdt2, &B, &dB, &ddB);
+            E += B;
+            double g9[9];
+            for (int j = 0; j < 3; ++j)
+                for (int a = 0; a < 3; ++a) g9[3 * j + a] = -2.0 * w[j] * r[a];
+            if (G)
+                for (int j = 0; j < 3; ++j)
+                    for (int a = 0; a < 3; ++a) G[3 * tv[j] + a] += dB * g9[3 * j + a];
+            const double we = ddB + dB / (2.0 * D);
+            if (we > 0.0) {
+                if (Dg)
+                    for (int j = 0; j < 3; ++j)
+                        for (int a = 0; a < 3; ++a)
+                            for (int b = 0; b < 3; ++b) Dg[9 * tv[j] + 3 * a + b] += we * g9[3 * j + a] * g9[3 * j + b];
+                if (tp) tp_push(tp, f, g9, we);
+            }
+        }
+    }
+    if (dmin) *dmin = sqrt(best);
+    return E;
+}
+
+/* CCD of the moving gel triangles against the (static) vertices of the indenter: the reference's ACCD per candidate behind its box
+ * broad phase (ccd.inl:90-122, 200-262), eta 0.1, horizon 1.1 */
+static double tp_ccd_alpha(const fem_cfg* g, const fem_indenter* I, const double* x0, const double* dx)
+{
+    const double zero[3] = {0, 0, 0};
+    double alpha = 1.0;
+    if (I->type != 2) return alpha;
+    for (int f = 0; f < g_nctri; ++f) {
+        const int32_t* tv = g_ctri + 3 * f;
+        double lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = 1e300; hi[a] = -1e300;
+            for (int j = 0; j < 3; ++j) {
+                const double u = x0[3 * tv[j] + a], v = u + dx[3 * tv[j] + a];
+                lo[a] = fmin(lo[a], fmin(u, v));
+                hi[a] = fmax(hi[a], fmax(u, v));
+            }
+        }
+        for (int k = 0; k < g_mesh_nv; ++k) {
+            double pw[3];
+            mesh_vertex_world(I, k, pw);
+            int far = 0;
+            for (int a = 0; a < 3; ++a)
+                if (pw[a] - hi[a] > g->d_hat || lo[a] - pw[a] > g->d_hat) far = 1;
+            if (far) continue;
+            double toc = 1.1;
+            if (fem_pt_accd(pw, x0 + 3 * tv[0], x0 + 3 * tv[1], x0 + 3 * tv[2], zero, dx + 3 * tv[0], dx + 3 * tv[1], dx + 3 * tv[2], 0.1, 0.0,
+                            1000, &toc) && toc < alpha)
+                alpha = toc;
+        }
+    }
+    return alpha;
+}
 
 /* triangle-mesh indenter: one barrier per (vertex, triangle) candidate inside d_hat, each candidate's Hessian block made positive
  * semi-definite on its own (ipc_simplex_normal_contact.cu:270-342: PT_barrier_gradient_hessian + make_spd), summed. H is returned
@@ -694,6 +869,11 @@ static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
             E += B;
         }
     }
+    {
+        double dtp;
+        E += tp_terms(g, &c->ind, x, 0, 0, 0, &dtp);
+        if (dtp < md) md = dtp;
+    }
     if (g->friction_mu > 0.0)
         for (int k = 0; k < g->S; ++k) {
             int i = c->surf[k];
@@ -772,6 +952,7 @@ static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, 
         }
         for (int j = 0; j < 9; ++j) Dg[9 * i + j] += Hk[j];
     }
+    tp_terms(g, &c->ind, x, G, Dg, c->tp, 0);
 }
 
 static void apply_A(const fem_ctx* c, const double* H9, const double* Hc, const double* p, double* y)
@@ -807,6 +988,17 @@ static void apply_A(const fem_ctx* c, const double* H9, const double* Hc, const 
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) y[3 * i + a] += Hk[3 * a + b] * p[3 * i + b];
     }
+    if (c->tp)
+        for (int q = 0; q < c->tp->n; ++q) { /* Gauss-Newton rank-1 term of every (indenter vertex, gel triangle) candidate */
+            const int32_t* tv = g_ctri + 3 * c->tp->tri[q];
+            const double* g9 = c->tp->g9 + 9 * q;
+            double sp = 0.0;
+            for (int j = 0; j < 3; ++j)
+                for (int a = 0; a < 3; ++a) sp += g9[3 * j + a] * p[3 * tv[j] + a];
+            sp *= c->tp->w[q];
+            for (int j = 0; j < 3; ++j)
+                for (int a = 0; a < 3; ++a) y[3 * tv[j] + a] += sp * g9[3 * j + a];
+        }
 }
 
 static void inv3(const double* M, double* R)
@@ -893,6 +1085,9 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
     c.x_prev = x_prev; c.x_tilde = xt;
     c.ind0 = *ind_prev;
+    fem_tp tpl;
+    memset(&tpl, 0, sizeof(tpl));
+    c.tp = &tpl;
     memset(st, 0, sizeof(*st));
 
     /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */
@@ -919,6 +1114,11 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
                 fem_indenter_sdf(&c.ind, x + 3 * surf[k], &d, nn, 0);
                 if (d < md) md = d;
             }
+            {
+                double dtp;
+                tp_terms(g, &c.ind, x, 0, 0, 0, &dtp);
+                if (dtp < md) md = dtp;
+            }
             double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
             if (ds < 0.0) ds = 0.0;
             ind_s = ind_s + ds < 1.0 ? ind_s + ds : 1.0;
@@ -942,7 +1142,11 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
         double alpha = 1.0;
         /* CCD against the indenter: conservative advancement, keep 20 % of the gap (cf. eta = 0.1 ACCD); the triangle mesh gets the
            reference's ACCD per (vertex, triangle) pair */
-        if (c.ind.type == 2) alpha = mesh_ccd_alpha(g, &c.ind, x0, dx, surf, g->S);
+        if (c.ind.type == 2) {
+            alpha = mesh_ccd_alpha(g, &c.ind, x0, dx, surf, g->S);
+            const double atp = tp_ccd_alpha(g, &c.ind, x0, dx);
+            if (atp < alpha) alpha = atp;
+        }
         else for (int k = 0; k < g->S; ++k) {
             int i = surf[k];
             double d, nn[3];
@@ -974,6 +1178,7 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     /* update velocity (fem_bdf1_time_integrator.cu:58-77) */
     for (int i = 0; i < n; ++i) { v[i] = (x[i] - x_prev[i]) * (1.0 / g->dt); x_prev[i] = x[i]; }
     free(xt); free(G); free(dx); free(x0); free(r); free(z); free(p); free(Ap); free(H9); free(Dg); free(Dinv); free(Hc);
+    free(tpl.tri); free(tpl.g9); free(tpl.w);
 }
 
 /* batch driver (OpenMP over gels) */
@@ -1010,6 +1215,9 @@ void fem_assemble_dense(const fem_cfg* g, const int32_t* tets, const double* Dm_
     const int n = 3 * g->V;
     fem_ctx c;
     memset(&c, 0, sizeof(c));
+    fem_tp tpl;
+    memset(&tpl, 0, sizeof(tpl));
+    c.tp = &tpl;
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
     c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind; c.ind0 = *ind;
     double* G = (double*)malloc(sizeof(double) * n);
@@ -1028,6 +1236,7 @@ void fem_assemble_dense(const fem_cfg* g, const int32_t* tets, const double* Dm_
     for (int i = 0; i < n; ++i) bout[i] = -G[i];
     if (energy) *energy = total_energy(&c, x, 0);
     free(G); free(H9); free(Dg); free(Hc); free(e); free(y);
+    free(tpl.tri); free(tpl.g9); free(tpl.w);
 }
 
 int fem_pcg_solve(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const double* vol, const double* mass,
@@ -1037,6 +1246,9 @@ int fem_pcg_solve(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, c
     const int n = 3 * g->V;
     fem_ctx c;
     memset(&c, 0, sizeof(c));
+    fem_tp tpl;
+    memset(&tpl, 0, sizeof(tpl));
+    c.tp = &tpl;
     c.cfg = g; c.tets = tets; c.Dm_inv = Dm_inv; c.vol = vol; c.mass = mass; c.attach = attach; c.surf = surf; c.aim = aim;
     c.x_prev = x_prev; c.x_tilde = x_tilde; c.ratio = ratio; c.ind = *ind; c.ind0 = *ind;
     double* buf = (double*)malloc(sizeof(double) * (6 * n + 81 * g->T + 18 * g->V + 9 * (g->S + 1)));
@@ -1046,5 +1258,6 @@ int fem_pcg_solve(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, c
     for (int i = 0; i < n; ++i) G[i] = -G[i];
     int k = pcg(&c, H9, Hc, Dg, G, sol, r, z, p, Ap, Dinv);
     free(buf);
+    free(tpl.tri); free(tpl.g9); free(tpl.w);
     return k;
 }

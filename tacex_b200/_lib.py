@@ -75,7 +75,7 @@ EXPORTS = [
     "tx_abi_version", "tx_create", "tx_destroy", "tx_last_error", "tx_get_counters", "tx_upload_tables",
     "tx_indentation_depth", "tx_indentation_depth_frames", "tx_render", "tx_render_depth", "tx_set_camera_resolution", "tx_render_camera", "tx_set_rect_output", "tx_set_multicast_output", "tx_obs_push", "tx_obs_fill", "tx_upload_shadow_tables", "tx_render_shadow", "tx_fots_markers", "tx_set_marker_patches", "tx_marker_overlay", "tx_resize", "tx_marker_grid", "tx_step_host", "tx_debug_set_ticks", "tx_debug_set_flags",
     "tx_fem_create", "tx_fem_destroy", "tx_fem_last_error", "tx_fem_get_mass", "tx_fem_step", "tx_fem_set_markers",
-    "tx_fem_markers", "tx_fem_set_marker_output", "tx_fem_set_surface", "tx_fem_heightmap", "tx_fem_attachment_aim", "tx_fem_set_indenter_mesh", "tx_fem_debug_set_cycles",
+    "tx_fem_markers", "tx_fem_set_marker_output", "tx_fem_set_surface", "tx_fem_heightmap", "tx_fem_attachment_aim", "tx_fem_set_indenter_mesh", "tx_fem_set_contact_surface", "tx_fem_debug_set_cycles",
 ]
 
 
@@ -144,6 +144,8 @@ def load() -> C.CDLL:
     lib.tx_fem_attachment_aim.restype = C.c_int
     lib.tx_fem_set_indenter_mesh.argtypes = [C.c_void_p, C.c_int, vp]
     lib.tx_fem_set_indenter_mesh.restype = C.c_int
+    lib.tx_fem_set_contact_surface.argtypes = [C.c_void_p, C.c_int, vp]
+    lib.tx_fem_set_contact_surface.restype = C.c_int
     lib.tx_fem_set_surface.argtypes = [C.c_void_p, C.c_int, vp]
     lib.tx_fem_set_surface.restype = C.c_int
     lib.tx_fem_heightmap.argtypes = [C.c_void_p, vp, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_float]

@@ -36,6 +36,11 @@ struct tx_fem {
     // prescribed triangle-mesh indenter (tx_fem_set_indenter_mesh)
     int mesh_n = 0;
     double *d_mesh_tri = nullptr, *d_mesh_box = nullptr;
+    // second half of the vertex-face contact: the mesh's unique vertices against the gel's contact triangles
+    int mesh_nv = 0, n_ctri = 0;
+    double* d_mesh_vert = nullptr;
+    int *d_ctri = nullptr, *d_ctri_row_start = nullptr, *d_ctri_row_adj = nullptr, *d_ctri_edge_start = nullptr, *d_ctri_edge_adj = nullptr;
+    std::map<std::pair<int, int>, int> edge_of; // (i, j), i < j -> edge number (tx_fem_create)
 };
 
 // Default assembly chunk (see fem_kernel.cu, grad_hess): measured on the B200, profiles/r02_fem_chunk.txt
@@ -140,6 +145,7 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
             for (auto& kv : inc) {
                 ei[e] = kv.first.second;
                 ej[e] = kv.first.second + kv.first.first;
+                f->edge_of[{ei[e], ej[e]}] = e;
                 for (int en : kv.second) eadj.push_back(en);
                 eoff[e + 1] = (int)eadj.size();
                 if (offsets.empty() || offsets.back() != kv.first.first) offsets.push_back(kv.first.first);
@@ -256,7 +262,8 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     cudaFree(f->d_tets); cudaFree(f->d_attach); cudaFree(f->d_surf); cudaFree(f->d_Dm_inv); cudaFree(f->d_vol);
     cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_tsc); cudaFree(f->d_valg); cudaFree(f->d_xt); cudaFree(f->d_edge_off); cudaFree(f->d_edge_adj);
     cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
-    cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top); cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box);
+    cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top); cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box); cudaFree(f->d_mesh_vert);
+    cudaFree(f->d_ctri); cudaFree(f->d_ctri_row_start); cudaFree(f->d_ctri_row_adj); cudaFree(f->d_ctri_edge_start); cudaFree(f->d_ctri_edge_adj);
     delete f;
 }
 
@@ -286,6 +293,10 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.edge_start = f->d_edge_off; a.edge_adj = f->d_edge_adj; a.ell = f->d_ell;
     a.attach_of = f->d_attach_of; a.surf_of = f->d_surf_of;
     a.mesh_tri = f->d_mesh_tri; a.mesh_box = f->d_mesh_box; a.mesh_n = f->mesh_n;
+    a.mesh_vert = f->d_mesh_vert; a.mesh_nv = f->mesh_nv;
+    a.ctri = f->d_ctri; a.n_ctri = f->mesh_n > 0 ? f->n_ctri : 0;
+    a.ctri_row_start = f->d_ctri_row_start; a.ctri_row_adj = f->d_ctri_row_adj;
+    a.ctri_edge_start = f->d_ctri_edge_start; a.ctri_edge_adj = f->d_ctri_edge_adj;
     a.dbg_cycles = f->d_cycles;
     a.dbg_mode = getenv("TX_FEM_DBG_MODE") ? atoi(getenv("TX_FEM_DBG_MODE")) : 0;
     a.row_start = f->d_adj_off;
@@ -307,9 +318,9 @@ extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri
     if (n_tris > 4096) return ffail(f, TX_ERR_UNSUPPORTED, "tx_fem_set_indenter_mesh: more than 4096 triangles (every triangle is box-tested per vertex)");
     FEM_CUDA(f, cudaSetDevice(f->device));
     FEM_CUDA(f, cudaStreamSynchronize(f->stream)); // a step in flight may still read the old mesh
-    cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box);
-    f->d_mesh_tri = f->d_mesh_box = nullptr;
-    f->mesh_n = 0;
+    cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box); cudaFree(f->d_mesh_vert);
+    f->d_mesh_tri = f->d_mesh_box = f->d_mesh_vert = nullptr;
+    f->mesh_n = f->mesh_nv = 0;
     if (n_tris == 0) return TX_OK;
     std::vector<double> box((size_t)6 * n_tris);
     for (int t = 0; t < n_tris; ++t) {
@@ -332,7 +343,63 @@ extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri
     FEM_CUDA(f, cudaMalloc(&f->d_mesh_box, sizeof(double) * 6 * n_tris));
     FEM_CUDA(f, cudaMemcpy(f->d_mesh_tri, tri_local, sizeof(double) * 9 * n_tris, cudaMemcpyHostToDevice));
     FEM_CUDA(f, cudaMemcpy(f->d_mesh_box, box.data(), sizeof(double) * 6 * n_tris, cudaMemcpyHostToDevice));
+    {   // unique vertices (exact coordinate match, first occurrence order) for the vertex-vs-gel-triangle candidates
+        std::vector<double> vert;
+        for (int k = 0; k < 3 * n_tris; ++k) {
+            const double* v = tri_local + (size_t)3 * k;
+            bool found = false;
+            for (size_t j = 0; j < vert.size() / 3 && !found; ++j) found = vert[3 * j] == v[0] && vert[3 * j + 1] == v[1] && vert[3 * j + 2] == v[2];
+            if (!found) vert.insert(vert.end(), v, v + 3);
+        }
+        FEM_CUDA(f, cudaMalloc(&f->d_mesh_vert, sizeof(double) * vert.size()));
+        FEM_CUDA(f, cudaMemcpy(f->d_mesh_vert, vert.data(), sizeof(double) * vert.size(), cudaMemcpyHostToDevice));
+        f->mesh_nv = (int)(vert.size() / 3);
+    }
     f->mesh_n = n_tris;
+    return TX_OK;
+}
+
+extern "C" int tx_fem_set_contact_surface(tx_fem* f, int n_tris, const int32_t* tris)
+{
+    if (!f || n_tris < 0 || (n_tris > 0 && !tris)) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_contact_surface: bad argument");
+    if (n_tris > fem_threads()) return ffail(f, TX_ERR_UNSUPPORTED, "tx_fem_set_contact_surface: more triangles than threads (one triangle per thread)");
+    FEM_CUDA(f, cudaSetDevice(f->device));
+    FEM_CUDA(f, cudaStreamSynchronize(f->stream));
+    cudaFree(f->d_ctri); cudaFree(f->d_ctri_row_start); cudaFree(f->d_ctri_row_adj); cudaFree(f->d_ctri_edge_start); cudaFree(f->d_ctri_edge_adj);
+    f->d_ctri = f->d_ctri_row_start = f->d_ctri_row_adj = f->d_ctri_edge_start = f->d_ctri_edge_adj = nullptr;
+    f->n_ctri = 0;
+    if (n_tris == 0) return TX_OK;
+    const int V = f->cfg.V, nE = f->nE;
+    static const int PR[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    std::vector<std::vector<int>> rows(V), edges(nE);
+    for (int t = 0; t < n_tris; ++t) {
+        for (int j = 0; j < 3; ++j) {
+            const int v = tris[3 * t + j];
+            if (v < 0 || v >= V) return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_contact_surface: vertex index out of range");
+            rows[v].push_back(t << 2 | j);
+        }
+        for (int pr = 0; pr < 3; ++pr) {
+            const int a = tris[3 * t + PR[pr][0]], b = tris[3 * t + PR[pr][1]];
+            const auto it = f->edge_of.find({a < b ? a : b, a < b ? b : a});
+            if (a == b || it == f->edge_of.end())
+                return ffail(f, TX_ERR_INVALID_ARG, "tx_fem_set_contact_surface: every triangle edge must be an edge of the tet mesh");
+            edges[it->second].push_back(t << 2 | pr);
+        }
+    }
+    std::vector<int> rs(V + 1, 0), ra, es(nE + 1, 0), ea;
+    for (int i = 0; i < V; ++i) { ra.insert(ra.end(), rows[i].begin(), rows[i].end()); rs[i + 1] = (int)ra.size(); }
+    for (int e = 0; e < nE; ++e) { ea.insert(ea.end(), edges[e].begin(), edges[e].end()); es[e + 1] = (int)ea.size(); }
+    FEM_CUDA(f, cudaMalloc(&f->d_ctri, sizeof(int) * 3 * n_tris));
+    FEM_CUDA(f, cudaMalloc(&f->d_ctri_row_start, sizeof(int) * rs.size()));
+    FEM_CUDA(f, cudaMalloc(&f->d_ctri_row_adj, sizeof(int) * std::max<size_t>(ra.size(), 1)));
+    FEM_CUDA(f, cudaMalloc(&f->d_ctri_edge_start, sizeof(int) * es.size()));
+    FEM_CUDA(f, cudaMalloc(&f->d_ctri_edge_adj, sizeof(int) * std::max<size_t>(ea.size(), 1)));
+    FEM_CUDA(f, cudaMemcpy(f->d_ctri, tris, sizeof(int) * 3 * n_tris, cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_ctri_row_start, rs.data(), sizeof(int) * rs.size(), cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_ctri_row_adj, ra.data(), sizeof(int) * ra.size(), cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_ctri_edge_start, es.data(), sizeof(int) * es.size(), cudaMemcpyHostToDevice));
+    FEM_CUDA(f, cudaMemcpy(f->d_ctri_edge_adj, ea.data(), sizeof(int) * ea.size(), cudaMemcpyHostToDevice));
+    f->n_ctri = n_tris;
     return TX_OK;
 }
 

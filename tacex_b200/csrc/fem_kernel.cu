@@ -528,6 +528,211 @@ __device__ __forceinline__ bool mesh_contact(const FemArgs& a, const FemIndenter
     return true;
 }
 
+// ---- indenter VERTEX against gel TRIANGLE candidates (second half of the vertex-face contact) ------------------------------------
+// Same closest-feature classification and squared distance as above; the unknowns are the triangle's three vertices. By the envelope
+// theorem dD/dt_j = -2 w_j r with r = p - c, c = sum w_j t_j the closest point (pinned against the reference's 12-gradient); the
+// Hessian is Gauss-Newton (weights frozen), which after make_spd leaves max(0, B'' + B' / (2 D)) g g^T (see oracle/fem_canon.c).
+__device__ __forceinline__ double pt_closest(const double* __restrict__ tr, const double p[3], double r[3], double w[3])
+{
+    const double e01[3] = {tr[3] - tr[0], tr[4] - tr[1], tr[5] - tr[2]}, e02[3] = {tr[6] - tr[0], tr[7] - tr[1], tr[8] - tr[2]};
+    const double n[3] = {e01[1] * e02[2] - e01[2] * e02[1], e01[2] * e02[0] - e01[0] * e02[2], e01[0] * e02[1] - e01[1] * e02[0]};
+    double av[3];
+    int kind = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (kind >= 0) continue;
+        const double* s = tr + 3 * k;
+        const double* t = tr + 3 * ((k + 1) % 3);
+        const double e[3] = {t[0] - s[0], t[1] - s[1], t[2] - s[2]}, q[3] = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};
+        const double m[3] = {e[1] * n[2] - e[2] * n[1], e[2] * n[0] - e[0] * n[2], e[0] * n[1] - e[1] * n[0]};
+        av[k] = (e[0] * q[0] + e[1] * q[1] + e[2] * q[2]) / (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+        const double b = (m[0] * q[0] + m[1] * q[1] + m[2] * q[2]) / (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        if (av[k] > 0.0 && av[k] < 1.0 && b >= 0.0) kind = 1 + k;
+    }
+    if (kind < 0) {
+        if (av[0] <= 0.0 && av[2] >= 1.0) kind = 4;
+        else if (av[1] <= 0.0 && av[0] >= 1.0) kind = 5;
+        else if (av[2] <= 0.0 && av[1] >= 1.0) kind = 6;
+        else kind = 0;
+    }
+    double D;
+    w[0] = w[1] = w[2] = 0.0;
+    if (kind >= 4) {
+        const double* v = tr + 3 * (kind - 4);
+        const double rr[3] = {p[0] - v[0], p[1] - v[1], p[2] - v[2]};
+        D = rr[0] * rr[0] + rr[1] * rr[1] + rr[2] * rr[2];
+        if (kind == 4) w[0] = 1.0; else if (kind == 5) w[1] = 1.0; else w[2] = 1.0;
+    } else if (kind >= 1) {
+        const double* s = tr + 3 * (kind - 1);
+        const double* t = tr + 3 * (kind % 3);
+        const double u[3] = {t[0] - s[0], t[1] - s[1], t[2] - s[2]}, q[3] = {p[0] - s[0], p[1] - s[1], p[2] - s[2]};
+        const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], qu = q[0] * u[0] + q[1] * u[1] + q[2] * u[2];
+        const double c[3] = {q[1] * u[2] - q[2] * u[1], q[2] * u[0] - q[0] * u[2], q[0] * u[1] - q[1] * u[0]};
+        D = (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / uu;
+        const double al = qu / uu;
+        if (kind == 1) { w[0] = 1.0 - al; w[1] = al; }
+        else if (kind == 2) { w[1] = 1.0 - al; w[2] = al; }
+        else { w[2] = 1.0 - al; w[0] = al; }
+    } else {
+        const double nn = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+        const double sd = n[0] * (p[0] - tr[0]) + n[1] * (p[1] - tr[1]) + n[2] * (p[2] - tr[2]);
+        D = sd * sd / nn;
+        const double f = sd / nn;
+        const double c[3] = {p[0] - f * n[0] - tr[0], p[1] - f * n[1] - tr[1], p[2] - f * n[2] - tr[2]};
+        const double d00 = e01[0] * e01[0] + e01[1] * e01[1] + e01[2] * e01[2], d01 = e01[0] * e02[0] + e01[1] * e02[1] + e01[2] * e02[2],
+                     d11 = e02[0] * e02[0] + e02[1] * e02[1] + e02[2] * e02[2], d20 = c[0] * e01[0] + c[1] * e01[1] + c[2] * e01[2],
+                     d21 = c[0] * e02[0] + c[1] * e02[1] + c[2] * e02[2], den = d00 * d11 - d01 * d01;
+        w[1] = (d11 * d20 - d01 * d21) / den;
+        w[2] = (d00 * d21 - d01 * d20) / den;
+        w[0] = 1.0 - w[1] - w[2];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) r[a] = p[a] - (w[0] * tr[a] + w[1] * tr[3 + a] + w[2] * tr[6 + a]);
+    return D;
+}
+
+struct MeshVerts { const double* vert; int nv; double d_hat; };
+// per gel triangle: k 0..8 gradient of its three vertices, 9..26 their diagonal blocks (symmetric 00 01 02 11 12 22), 27..44 the
+// blocks of the pairs (0,1) (0,2) (1,2) (multiples of r r^T: symmetric)
+struct TpOut { double E, dmin2, v[45]; int bad; };
+__device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, double3 r1, double3 r2, double3 xa, double3 xb, double3 xc,
+                                           double kdt2, int derivs, TpOut* o)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double tr[9] = {xa.x, xa.y, xa.z, xb.x, xb.y, xb.z, xc.x, xc.y, xc.z};
+    double lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = fmin(tr[a], fmin(tr[3 + a], tr[6 + a]));
+        hi[a] = fmax(tr[a], fmax(tr[3 + a], tr[6 + a]));
+    }
+    const double D0 = mv.d_hat * mv.d_hat;
+    double E = 0.0, best = 1e300;
+    int bad = 0;
+    if (derivs)
+        for (int k = 0; k < 45; ++k) o->v[k] = 0.0;
+    for (int k = 0; k < mv.nv; ++k) {
+        const double* l = mv.vert + 3 * k;
+        double pw[3];
+        pw[0] = c.x + R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
+        pw[1] = c.y + R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
+        pw[2] = c.z + R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+        double bd = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double dd = pw[a] < lo[a] ? lo[a] - pw[a] : (pw[a] > hi[a] ? pw[a] - hi[a] : 0.0);
+            bd += dd * dd;
+        }
+        if (!(bd < best) && !(bd < D0)) continue;
+        double r[3], w[3];
+        const double D = pt_closest(tr, pw, r, w);
+        if (D < best) best = D;
+        if (!(D < D0)) continue;
+        if (!(D > 0.0)) { bad = 1; continue; }
+        double B, dB, ddB;
+        barrier_fn(D, mv.d_hat, kdt2, &B, &dB, &ddB);
+        E += B;
+        if (derivs) {
+            const double we = ddB + dB / (2.0 * D), w4 = we > 0.0 ? 4.0 * we : 0.0;
+            const double rr[6] = {r[0] * r[0], r[0] * r[1], r[0] * r[2], r[1] * r[1], r[1] * r[2], r[2] * r[2]};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double gj = -2.0 * dB * w[j];
+                o->v[3 * j] += gj * r[0]; o->v[3 * j + 1] += gj * r[1]; o->v[3 * j + 2] += gj * r[2];
+                const double dj = w4 * w[j] * w[j];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) o->v[9 + 6 * j + q] += dj * rr[q];
+            }
+            const double p01 = w4 * w[0] * w[1], p02 = w4 * w[0] * w[2], p12 = w4 * w[1] * w[2];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                o->v[27 + q] += p01 * rr[q];
+                o->v[33 + q] += p02 * rr[q];
+                o->v[39 + q] += p12 * rr[q];
+            }
+        }
+    }
+    o->E = E; o->dmin2 = best; o->bad = bad;
+}
+
+// ACCD of a moving gel triangle (vertices + displacements) against the static vertices of the indenter: min(1, min toc)
+__device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, double3 r1, double3 r2, double3 xa, double3 xb, double3 xc,
+                                           double3 da, double3 db, double3 dc)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double t0[9] = {xa.x, xa.y, xa.z, xb.x, xb.y, xb.z, xc.x, xc.y, xc.z};
+    const double d0[9] = {da.x, da.y, da.z, db.x, db.y, db.z, dc.x, dc.y, dc.z};
+    double lo[3], hi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = 1e300; hi[a] = -1e300;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double u = t0[3 * j + a], v = u + d0[3 * j + a];
+            lo[a] = fmin(lo[a], fmin(u, v));
+            hi[a] = fmax(hi[a], fmax(u, v));
+        }
+    }
+    const double eta = 0.1;
+    double alpha = 1.0;
+    for (int k = 0; k < mv.nv; ++k) {
+        const double* l = mv.vert + 3 * k;
+        double p[3];
+        p[0] = c.x + R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
+        p[1] = c.y + R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
+        p[2] = c.z + R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+        bool far = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            if (p[a] - hi[a] > mv.d_hat || lo[a] - p[a] > mv.d_hat) far = true;
+        if (far) continue;
+        double tr[9], dt[9], dp[3];
+        double mm = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double mov = (d0[a] + d0[3 + a] + d0[6 + a] + 0.0) / 4;
+            dp[a] = 0.0 - mov;
+            dt[a] = d0[a] - mov; dt[3 + a] = d0[3 + a] - mov; dt[6 + a] = d0[6 + a] - mov;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mm = fmax(mm, dt[3 * j] * dt[3 * j] + dt[3 * j + 1] * dt[3 * j + 1] + dt[3 * j + 2] * dt[3 * j + 2]);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) tr[q] = t0[q];
+        const double L = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) + sqrt(mm);
+        if (L <= 0.0) continue;
+        double g[3];
+        double d2 = pt_distance2(tr, p, g), d = sqrt(d2);
+        const double gap = eta * d2 / d, toc_prev = 1.1;
+        double toc = 0.0;
+        bool hit = true;
+        for (int it = 1000;;) {
+            if (--it < 0) break;
+            const double lb = (1 - eta) * d2 / (d * L);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] += lb * dp[a];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) tr[q] += lb * dt[q];
+            d2 = pt_distance2(tr, p, g);
+            d = sqrt(d2);
+            if (toc != 0.0 && d2 / d < gap) break;
+            toc += lb;
+            if (toc > toc_prev) { hit = false; break; }
+        }
+        if (hit && toc < alpha) alpha = toc;
+    }
+    return alpha;
+}
+
+__device__ __forceinline__ void tp_terms(const FemArgs& a, const FemIndenter& I, const double* xs, int f, double kdt2, int derivs, TpOut* o)
+{
+    const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat};
+    const int i0 = a.ctri[3 * f], i1 = a.ctri[3 * f + 1], i2 = a.ctri[3 * f + 2];
+    tp_terms_impl(mv, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
+                  make_double3(I.R[6], I.R[7], I.R[8]), make_double3(xs[3 * i0], xs[3 * i0 + 1], xs[3 * i0 + 2]),
+                  make_double3(xs[3 * i1], xs[3 * i1 + 1], xs[3 * i1 + 2]), make_double3(xs[3 * i2], xs[3 * i2 + 1], xs[3 * i2 + 2]), kdt2,
+                  derivs, o);
+}
+
 // CCD step bound of ONE gel vertex against the (static during a Newton iteration) mesh indenter: the reference's additive CCD per
 // (vertex, triangle) pair (utils/distance/details/ccd.inl:200-262: common translation removed, advance by the conservative bound until
 // the gap has shrunk to eta = 0.1 of its initial value; at most 1000 iterations, horizon 1.1) behind its broad phase (box of the swept
@@ -877,6 +1082,13 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
             }
         }
     }
+    if (MESH && ind.type == 2 && a.n_ctri > 0 && threadIdx.x < a.n_ctri) { // indenter vertices against this thread's gel triangle
+        TpOut o;
+        tp_terms(a, ind, s.x, threadIdx.x, a.kappa * dt2, 0, &o);
+        E += o.E;
+        md = fmin(md, sqrt(o.dmin2));
+        if (o.bad) bad = true;
+    }
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         double W[4][3], F[9], e;
         const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
@@ -998,6 +1210,48 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
         }
         __syncthreads(); // the next chunk overwrites the scratch
         if (cyc) { cyc[2] += clock64() - tg0; tg0 = clock64(); }
+    }
+    // (3b) indenter vertices against the gel's contact triangles: one triangle per thread writes its 45 numbers to the (now free)
+    // scratch, rows and edges gather them through static incidence lists in a fixed order (deterministic, like the tets)
+    if (MESH && ind.type == 2 && a.n_ctri > 0) {
+        if (threadIdx.x < a.n_ctri) {
+            TpOut o;
+            tp_terms(a, ind, s.x, threadIdx.x, a.kappa * dt2, 1, &o);
+#pragma unroll 5
+            for (int k = 0; k < 45; ++k) tsc[(size_t)k * FEM_THREADS + threadIdx.x] = o.v[k];
+        }
+        __syncthreads();
+        if (on) {
+            for (int q = a.ctri_row_start[i]; q < a.ctri_row_start[i + 1]; ++q) {
+                const int ent = a.ctri_row_adj[q], f = ent >> 2, j = ent & 3;
+                const double* tf = tsc + f;
+                g3[0] += tf[(size_t)(3 * j) * FEM_THREADS]; g3[1] += tf[(size_t)(3 * j + 1) * FEM_THREADS]; g3[2] += tf[(size_t)(3 * j + 2) * FEM_THREADS];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d6[k] += tf[(size_t)(9 + 6 * j + k) * FEM_THREADS];
+            }
+        }
+        for (int e = threadIdx.x; e < a.nE; e += FEM_THREADS) {
+            const int q0 = a.ctri_edge_start[e], q1 = a.ctri_edge_start[e + 1];
+            if (q0 == q1) continue;
+            double b6[6] = {0, 0, 0, 0, 0, 0};
+            for (int q = q0; q < q1; ++q) {
+                const int ent = a.ctri_edge_adj[q], f = ent >> 2, pr = ent & 3;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) b6[k] += tsc[(size_t)(27 + 6 * pr + k) * FEM_THREADS + f];
+            }
+            const double blk[9] = {b6[0], b6[1], b6[2], b6[1], b6[3], b6[4], b6[2], b6[4], b6[5]};
+            if (e < a.n_s) {
+                double* dst = s.val + e;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dst[k * FEM_VAL_STRIDE] += blk[k];
+            } else {
+                double* dst = valg + (e - a.n_s);
+                const int nEg = a.nE - a.n_s;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dst[(size_t)k * nEg] += blk[k];
+            }
+        }
+        __syncthreads();
     }
     // (4) attachment + barrier (row-local)
     if (on) {
@@ -1191,6 +1445,11 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                     indenter_sdf<MESH>(a, cur, s.x + 3 * i, &d, nn, nullptr);
                     md = d;
                 }
+                if (MESH && cur.type == 2 && a.n_ctri > 0 && threadIdx.x < a.n_ctri) {
+                    TpOut o;
+                    tp_terms(a, cur, s.x, threadIdx.x, 0.0, 0, &o);
+                    md = fmin(md, sqrt(o.dmin2));
+                }
                 md = block_reduce<1>(md, s.red, ph);
                 double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
                 if (ds < 0.0) ds = 0.0;
@@ -1221,6 +1480,22 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
             double alpha = 1.0;
             if (MESH && ind.type == 2) {
                 if (is_surf) alpha = mesh_ccd(a, ind, x0, dx); // the reference's ACCD per (vertex, triangle) pair
+                if (a.n_ctri > 0) { // moving gel triangles against the indenter's vertices: the step of the other rows through s.p
+                    __syncthreads();
+                    if (on) { s.p[3 * i] = dx[0]; s.p[3 * i + 1] = dx[1]; s.p[3 * i + 2] = dx[2]; }
+                    __syncthreads();
+                    if (threadIdx.x < a.n_ctri) {
+                        const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat};
+                        const int f = threadIdx.x, i0 = a.ctri[3 * f], i1 = a.ctri[3 * f + 1], i2 = a.ctri[3 * f + 2];
+                        const double at = tp_ccd_impl(
+                            mv, make_double3(ind.c[0], ind.c[1], ind.c[2]), make_double3(ind.R[0], ind.R[1], ind.R[2]),
+                            make_double3(ind.R[3], ind.R[4], ind.R[5]), make_double3(ind.R[6], ind.R[7], ind.R[8]),
+                            make_double3(s.x[3 * i0], s.x[3 * i0 + 1], s.x[3 * i0 + 2]), make_double3(s.x[3 * i1], s.x[3 * i1 + 1], s.x[3 * i1 + 2]),
+                            make_double3(s.x[3 * i2], s.x[3 * i2 + 1], s.x[3 * i2 + 2]), make_double3(s.p[3 * i0], s.p[3 * i0 + 1], s.p[3 * i0 + 2]),
+                            make_double3(s.p[3 * i1], s.p[3 * i1 + 1], s.p[3 * i1 + 2]), make_double3(s.p[3 * i2], s.p[3 * i2 + 1], s.p[3 * i2 + 2]));
+                        alpha = fmin(alpha, at);
+                    }
+                }
             } else if (is_surf) {
                 double d, nn[3];
                 indenter_sdf<MESH>(a, ind, x0, &d, nn, nullptr);

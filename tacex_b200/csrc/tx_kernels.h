@@ -189,6 +189,15 @@ struct FemArgs {
     const double* mesh_tri; // [mesh_n][9] triangles of the prescribed mesh indenter (type 2) in its local frame, or nullptr
     const double* mesh_box; // [mesh_n][6] their boxes (lo, hi)
     int mesh_n;
+    // second half of the vertex-face contact (tx_fem_set_contact_surface): the indenter mesh's unique vertices against gel triangles
+    const double* mesh_vert; // [mesh_nv][3] local frame
+    int mesh_nv;
+    const int* ctri;           // [n_ctri][3] gel contact triangles (one per thread: n_ctri <= FEM threads), or nullptr
+    int n_ctri;
+    const int* ctri_row_start; // [V + 1] entries of ctri_row_adj per vertex
+    const int* ctri_row_adj;   // triangle << 2 | local vertex
+    const int* ctri_edge_start; // [nE + 1] entries of ctri_edge_adj per mesh edge
+    const int* ctri_edge_adj;  // triangle << 2 | pair (0: (0,1), 1: (0,2), 2: (1,2))
     int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
     long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate, friction_mu, eps_velocity;

@@ -151,6 +151,17 @@ class GelFemEngine:
             raise _lib.TxError("tri_local must have shape (n, 3, 3)")
         self._check(self.lib.tx_fem_set_indenter_mesh(self.h, len(t), t.ctypes.data))
 
+    def set_contact_surface(self, tris: np.ndarray | None) -> None:
+        """Triangles (n, 3) int32 of the gel surface (e.g. ``mesh.top_tris``) that the VERTICES of the mesh indenter can touch: the
+        second half of the vertex-face contact (a cone tip between four gel vertices is only seen this way). ``None`` switches it off."""
+        if tris is None:
+            self._check(self.lib.tx_fem_set_contact_surface(self.h, 0, None))
+            return
+        t = np.ascontiguousarray(tris, np.int32)
+        if t.ndim != 2 or t.shape[1] != 3:
+            raise _lib.TxError("tris must have shape (n, 3)")
+        self._check(self.lib.tx_fem_set_contact_surface(self.h, len(t), t.ctypes.data))
+
     @staticmethod
     def decode_stats(st: torch.Tensor) -> list[dict]:
         raw = st.cpu().numpy().tobytes()

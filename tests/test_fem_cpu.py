@@ -343,3 +343,57 @@ def test_step_driver_converges_to_the_stationary_point_an_independent_dense_newt
     _, b_end, _ = eval_(xs[0])
     _, b0, _ = eval_(cf.X)
     assert np.abs(b_end).max() <= 5e-3 * np.abs(b0).max()
+
+
+def test_indenter_vertices_against_gel_triangles_in_the_restatement():
+    """Second half of the vertex-face contact (fem_set_contact_surface): a 60 deg cone whose tip comes down in the middle of a
+    surface cell is invisible to the gel's vertices (2.1 mm apart) but not to its triangles. With the contact surface set the gel
+    follows the tip and the tip never reaches the surface; the Gauss-Newton operator the PCG applies is the assembled dense one."""
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh, synth
+
+    m = gel_mesh.box_gel()
+    cf = fc.CanonFem(m, velocity_tol=1e-3)
+    fc.CanonFem.set_indenter_mesh(synth.indenter_mesh(3, 3e-3))
+    aim = cf.X[cf.attach][None]
+    z0 = 4.5e-3 + 4e-4
+    ctr = lambda s: [1.0e-3, 0.5e-3, z0 - 1e-3 * s / 8]  # noqa: E731
+    out = {}
+    try:
+        for on in (False, True):
+            fc.CanonFem.set_contact_surface(m.top_tris if on else None)
+            x, v, xp = cf.new_state(1)
+            for s in range(8):
+                st = cf.step(x, v, xp, aim, [fc.make_indenter(2, ctr(s), (0, 0, 0))], [fc.make_indenter(2, ctr(s + 1), (0, 0, 0))])
+                assert st[0]["converged"] == 1 and st[0]["min_dist"] > 0
+            out[on] = (np.abs(x - cf.X).max(), st[0]["min_dist"], x.copy())
+        assert out[False][0] < 5e-5 and out[True][0] > 5e-4       # only the triangles see the tip
+        assert out[True][1] < cf.cfg.d_hat                        # ... and hold it inside the barrier zone
+        # operator consistency: A p of the matrix-free operator (with the rank-1 candidate terms) == dense assembled A p
+        g = cf.cfg
+        n = 3 * g.V
+        x = out[True][2][0]
+        ind = fc.make_indenter(2, ctr(8), (0, 0, 0))
+        A = np.zeros((n, n)); b = np.zeros(n); E = C.c_double()
+        xt = x.copy()
+        fc.lib().fem_assemble_dense(C.byref(g), fc._i(cf.tets), fc._d(cf.Dm_inv), fc._d(cf.vol), fc._d(cf.mass), fc._i(cf.attach),
+                                    fc._i(cf.surf), fc._d(aim[0].copy()), C.byref(ind), fc._d(np.ascontiguousarray(x)), fc._d(xt), fc._d(xt),
+                                    C.c_double(1.0), fc._d(A), fc._d(b), C.byref(E))
+        assert np.abs(A - A.T).max() <= 1e-9 * np.abs(A).max() and np.linalg.eigvalsh(A).min() > 0
+        # gradient of the candidate energy by finite differences on a touched triangle's vertex
+        top = np.asarray(m.top_tris)
+        touched = int(top[np.argmin(np.linalg.norm(cf.X[top].mean(1)[:, :2] - np.array(ctr(8)[:2]), axis=1))][0])
+
+        def energy(xx):
+            A2 = np.zeros((n, n)); b2 = np.zeros(n); E2 = C.c_double()
+            fc.lib().fem_assemble_dense(C.byref(g), fc._i(cf.tets), fc._d(cf.Dm_inv), fc._d(cf.vol), fc._d(cf.mass), fc._i(cf.attach),
+                                        fc._i(cf.surf), fc._d(aim[0].copy()), C.byref(ind), fc._d(np.ascontiguousarray(xx)), fc._d(xt),
+                                        fc._d(xt), C.c_double(1.0), fc._d(A2), fc._d(b2), C.byref(E2))
+            return E2.value
+
+        for a in range(3):
+            d = np.zeros_like(x); d[touched, a] = 1e-9
+            fd = (energy(x + d) - energy(x - d)) / 2e-9
+            assert abs(-b[3 * touched + a] - fd) <= 2e-4 * max(abs(fd), np.abs(b).max() * 1e-3), (a, b[3 * touched + a], fd)
+    finally:
+        fc.CanonFem.set_contact_surface(None)

@@ -281,3 +281,56 @@ def test_mesh_indenter_argument_checks():
     far = fem.indenter_array(2, [[0, 0, 4.5e-3 + 1e-4]], (0, 0, 0))
     st = eng.decode_stats(eng.step(x, v, xp, eng.rest_aim(1), far, far))
     assert st[0]["converged"] == 1 and float((x[0] - eng.X).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("kind", [3, 2])
+def test_two_sided_vertex_face_contact_matches_cpu_restatement(kind):
+    """Mesh indenter with BOTH halves of the vertex-face contact: gel surface vertices against indenter triangles and -- through
+    tx_fem_set_contact_surface -- indenter vertices against the gel's top triangles (exact energy / gradient, Gauss-Newton Hessian,
+    ACCD with the moving triangle). A cone tip / wedge corner placed BETWEEN the gel's surface vertices (2.1 mm apart) is only seen
+    by the second half: the gel must deform as far as the tip goes, and the kernel must follow the float64 CPU restatement."""
+    from tacex_b200 import fem, synth
+
+    m, eng, cf, fc = _setup((10, 12, 3), 1e-3, 4)
+    tri = synth.indenter_mesh(kind, 3e-3)
+    eng.set_indenter_mesh(tri)
+    eng.set_contact_surface(m.top_tris)
+    fc.CanonFem.set_indenter_mesh(tri)
+    fc.CanonFem.set_contact_surface(m.top_tris)
+    try:
+        N = 4
+        offs = np.array([[1.0e-3, 0.5e-3], [0.0, 0.0], [-3.1e-3, 2.6e-3], [4.2e-3, -1.0e-3]])  # env 0: centre of a surface cell
+        Rs = np.stack([_yaw(t) for t in (0.0, 0.4, 1.1, 2.0)])
+        z0 = 4.5e-3 + 4e-4
+
+        def ctr(s):
+            dz, dxs = 1.0e-3 * min(s, 8) / 8, 1e-4 * max(s - 8, 0)
+            return [[offs[i, 0] + dxs, offs[i, 1], z0 - dz] for i in range(N)]
+
+        x, v, xp = eng.new_state(N)
+        aim = eng.rest_aim(N)
+        xc, vc, xpc = cf.new_state(N)
+        aimc = cf.X[cf.attach][None].repeat(N, 0)
+        worst = 0.0
+        for s in range(11):
+            ip, inx = fem.indenter_array(2, ctr(s), (0, 0, 0), Rs), fem.indenter_array(2, ctr(s + 1), (0, 0, 0), Rs)
+            st = eng.step(x, v, xp, aim, ip, inx)
+            cst = cf.step(xc, vc, xpc, aimc, [fc.make_indenter(2, c, (0, 0, 0), R) for c, R in zip(ctr(s), Rs)],
+                          [fc.make_indenter(2, c, (0, 0, 0), R) for c, R in zip(ctr(s + 1), Rs)])
+            torch.cuda.synchronize()
+            d = np.abs(x.cpu().numpy() - xc).max()
+            worst = max(worst, d)
+            gs = eng.decode_stats(st)
+            assert d <= 1e-4, f"step {s}: {d}"
+            for i in range(N):
+                assert gs[i]["converged"] == 1 and gs[i]["min_dist"] > 0 and np.isfinite(gs[i]["energy"])
+                assert gs[i]["newton_iters"] == cst[i]["newton_iters"], (s, i, gs[i], cst[i])
+                assert abs(gs[i]["min_dist"] - cst[i]["min_dist"]) <= 1e-6
+        print(f"two-sided contact, mesh kind {kind}: max |x_gpu - x_cpu| over 11 steps = {worst:.3e} m")
+        assert worst <= 1e-5
+        # env 0: the tip went 0.6 mm below the rest surface between four vertices -- the surface followed it
+        assert float((eng.X[:, 2] - x[0, :, 2]).max()) > 4e-4
+    finally:
+        fc.CanonFem.set_contact_surface(None)
+        eng.set_contact_surface(None)
+        eng.set_indenter_mesh(None)

@@ -219,6 +219,7 @@ def test_point_triangle_closest_feature_and_distance_derivatives_match_reference
     obtuse triangles, the same squared distance, and the p-block of the 12-gradient / 12 x 12 Hessian."""
     rd = C.CDLL(str(REF_DIST))
     canon.fem_pt_distance.restype = C.c_int
+    canon.fem_pt_closest.restype = C.c_int
     rng = np.random.default_rng(7)
     IP = C.POINTER(C.c_int)
     seen = set()
@@ -247,6 +248,12 @@ def test_point_triangle_closest_feature_and_distance_derivatives_match_reference
         assert np.abs(G1 - G2[:3]).max() <= 1e-9 * max(np.abs(G2[:3]).max(), np.sqrt(sc) * 1e-3)
         Hp = H2.reshape(12, 12)[:3, :3]
         assert np.abs(H1.reshape(3, 3) - Hp).max() <= 1e-8 * 2.0, (k, kind)
+        # closest point form (the triangle's vertices as unknowns): the FULL 12-gradient is 2 r (x) [1, -w0, -w1, -w2]
+        D3, r3, w3 = C.c_double(), np.zeros(3), np.zeros(3)
+        assert canon.fem_pt_closest(_d(p), _d(t0), _d(t1), _d(t2), C.byref(D3), _d(r3), _d(w3)) == kind
+        assert abs(w3.sum() - 1.0) <= 1e-12 and abs(D3.value - D2.value) <= 1e-10 * sc
+        g12 = np.concatenate([2.0 * r3, -2.0 * w3[0] * r3, -2.0 * w3[1] * r3, -2.0 * w3[2] * r3])
+        assert np.abs(g12 - G2).max() <= 1e-8 * max(np.abs(G2).max(), np.sqrt(sc) * 1e-3), (k, kind, g12, G2)
         n_checked += 1
     assert seen == set(range(7)) and n_checked == 4000
 

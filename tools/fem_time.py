@@ -20,6 +20,8 @@ mesh_kind = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 if mesh_kind:
     from tacex_b200 import synth
     eng.set_indenter_mesh(synth.indenter_mesh(mesh_kind, 3e-3))
+    if os.environ.get("TX_TP"):  # second half of the vertex-face contact: indenter vertices against the gel's top triangles
+        eng.set_contact_surface(m.top_tris)
     z0 = 4.5e-3 + 4e-4
     inds = [fem.indenter_array(2, ctr(s), (0, 0, 0)) for s in range(steps + 1)]
 else:
