@@ -270,6 +270,37 @@ def fem_gpu(E: int, dev, tactile=None) -> dict:
             "workload": f"config 3: {E} envs, gel FEM substep + FEM markers + Taxim RGB 320x240 from the depth maps of the same box "
                         f"poses, steps {c3.first}..{c3.last - 1} of the 30-step press",
             "frames_per_s": E / (fms / 1e3), "ms_per_step": fms}
+    # config-2 indenters through the FEM path: wedge / cone as prescribed triangle meshes, vertex-face contact in both directions
+    from tacex_b200 import synth
+
+    out["mesh_indenters"] = {}
+    Em = min(E, 1024)
+    rng = np.random.default_rng(7)
+    offs = np.concatenate([rng.uniform(-1, 1, (Em, 2)) * np.array([6e-3, 8e-3]), np.zeros((Em, 1))], 1)
+    eng.set_contact_surface(m.top_tris)
+    for kind, name in ((2, "wedge"), (3, "cone")):
+        eng.set_indenter_mesh(synth.indenter_mesh(kind, 3e-3))
+        xm, vm, xpm = eng.new_state(Em)
+        aim_m = eng.rest_aim(Em)
+        pose = lambda sidx: fem.indenter_array(2, offs + np.array([0.0, 0.0, 4.5e-3 + 4e-4 - 1e-3 * sidx / 10]), (0, 0, 0), device=dev)  # noqa: E731
+        inds = [pose(sidx) for sidx in range(11)]
+        for sidx in range(7):
+            eng.step(xm, vm, xpm, aim_m, inds[sidx], inds[sidx + 1], want_stats=False)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for sidx in range(7, 10):
+            stm = eng.step(xm, vm, xpm, aim_m, inds[sidx], inds[sidx + 1], want_stats=True)
+        g1.record()
+        torch.cuda.synchronize()
+        dm = eng.decode_stats(stm)
+        out["mesh_indenters"][name] = {"gel_steps_per_s": Em / (g0.elapsed_time(g1) / 3 / 1e3), "ms_per_step": g0.elapsed_time(g1) / 3, "gels": Em,
+                                       "converged": float(np.mean([q["converged"] for q in dm])),
+                                       "newton_iters_mean": float(np.mean([q["newton_iters"] for q in dm]))}
+    out["mesh_indenters"]["workload"] = ("config-2 wedge / 60 deg cone as prescribed triangle meshes pressed 0 -> 1 mm over 10 steps (timed: steps 7..9), gel "
+                                         "vertices vs indenter triangles + indenter vertices vs the gel's 240 top triangles, ACCD")
+    eng.set_indenter_mesh(None)
+    eng.set_contact_surface(None)
     return out
 
 

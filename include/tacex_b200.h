@@ -290,8 +290,9 @@ int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* a
  * collision_detection/filters/lbvh_simplex_trajectory_filter.cu:600-690), restricted to the gel vertex (the indenter is prescribed).
  * n_tris = 0 removes the mesh. */
 int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri_local);
-/* Second half of the vertex-face contact with a mesh indenter: tris HOST [n_tris][3] vertex ids of the gel surface that the
- * indenter's VERTICES can touch (every triangle edge must be an edge of the tet mesh; n_tris <= 576, one triangle per thread; 0
+/* Second half of the vertex-face contact + the EDGE-EDGE candidates with a mesh indenter: tris HOST [n_tris][3] vertex ids of the gel
+ * surface that the indenter's VERTICES (against the triangles) and EDGES (against the triangles' unique edges, mollified as the
+ * reference: utils/distance/edge_edge_mollifier.h, distance_flagged.h:352-487, ccd.inl:267-354) can touch (every triangle edge must be an edge of the tet mesh; n_tris <= 576, one triangle per thread; 0
  * switches it off). Same classification / squared distance / barrier per candidate as above with the three gel vertices as the
  * unknowns: exact energy and gradient (the reference's 12-gradient), Gauss-Newton Hessian (closest point frozen), the reference's
  * additive CCD with the moving triangle (utils/distance/details/ccd.inl:200-262). */

@@ -38,8 +38,11 @@
  * point; pinned against the reference's 12-gradient) and a GAUSS-NEWTON Hessian: the closest point's barycentric weights frozen,
  * which after make_spd leaves max(0, B'' + B' / (2 D)) g g^T -- exact energy and gradient, hence the same minimiser as the
  * reference's model; only the curvature terms of a sliding closest point are dropped (stated in DESIGN.md). ACCD with the moving
- * triangle as in the reference. No friction on these candidates.
- * Not restated: edge-edge candidates (+ mollifier), LBVH (every triangle is tested against its box).
+ * triangle as in the reference. The EDGE-EDGE candidates (gel surface edges against the indenter's edges) are treated the same way:
+ * the reference's classification (edge_edge_distance_flag), the squared distance of the EE / PE / PP case, the mollifier of nearly
+ * parallel edges on the interior case, the edge-edge ACCD -- fem_ee_closest / fem_ee_mollifier / fem_ee_accd, all pinned. No
+ * friction on these two candidate families.
+ * Not restated: LBVH (every primitive pair is tested against its box).
  *
  * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
  * has no CPU backend) and its tests hold no golden positions for this path: the SOLVER LOOP of this
@@ -243,6 +246,11 @@ static double* g_mesh_vert = 0; /* [nv][3] unique vertices of the indenter mesh 
 static int g_mesh_nv = 0;
 static int32_t* g_ctri = 0;     /* [n][3] triangles of the gel's contact surface (vertex ids) */
 static int g_nctri = 0;
+static int32_t* g_cedge = 0;    /* [n][2] unique edges of those triangles */
+static double* g_cedge_len2 = 0; /* their squared REST lengths (mollifier threshold) */
+static int g_ncedge = 0;
+static int32_t* g_mesh_edge = 0; /* [n][2] unique edges of the indenter mesh (ids into g_mesh_vert) */
+static int g_mesh_ne = 0;
 static void mesh_unique_vertices(void)
 {
     free(g_mesh_vert);
@@ -255,14 +263,47 @@ static void mesh_unique_vertices(void)
             found = g_mesh_vert[3 * j] == v[0] && g_mesh_vert[3 * j + 1] == v[1] && g_mesh_vert[3 * j + 2] == v[2];
         if (!found) { memcpy(g_mesh_vert + 3 * g_mesh_nv, v, sizeof(double) * 3); ++g_mesh_nv; }
     }
+    /* unique edges by vertex id, first occurrence order */
+    free(g_mesh_edge);
+    g_mesh_edge = (int32_t*)malloc(sizeof(int32_t) * 6 * (g_mesh_n > 0 ? g_mesh_n : 1));
+    g_mesh_ne = 0;
+    for (int t = 0; t < g_mesh_n; ++t) {
+        int id[3];
+        for (int k = 0; k < 3; ++k) {
+            const double* v = g_mesh_tri + 9 * t + 3 * k;
+            id[k] = 0;
+            while (!(g_mesh_vert[3 * id[k]] == v[0] && g_mesh_vert[3 * id[k] + 1] == v[1] && g_mesh_vert[3 * id[k] + 2] == v[2])) ++id[k];
+        }
+        for (int k = 0; k < 3; ++k) {
+            const int a = id[k] < id[(k + 1) % 3] ? id[k] : id[(k + 1) % 3], b = id[k] < id[(k + 1) % 3] ? id[(k + 1) % 3] : id[k];
+            int found = 0;
+            for (int j = 0; j < g_mesh_ne && !found; ++j) found = g_mesh_edge[2 * j] == a && g_mesh_edge[2 * j + 1] == b;
+            if (!found) { g_mesh_edge[2 * g_mesh_ne] = a; g_mesh_edge[2 * g_mesh_ne + 1] = b; ++g_mesh_ne; }
+        }
+    }
 }
 /* triangles (vertex ids) of the gel surface that the indenter's vertices can touch; n = 0 switches that half of the contact off */
-void fem_set_contact_surface(const int32_t* tris, int n)
+void fem_set_contact_surface(const int32_t* tris, int n, const double* X_rest)
 {
-    free(g_ctri);
+    free(g_ctri); free(g_cedge); free(g_cedge_len2);
     g_ctri = (int32_t*)malloc(sizeof(int32_t) * 3 * (n > 0 ? n : 1));
+    g_cedge = (int32_t*)malloc(sizeof(int32_t) * 6 * (n > 0 ? n : 1));
+    g_cedge_len2 = (double*)malloc(sizeof(double) * 3 * (n > 0 ? n : 1));
     g_nctri = n;
+    g_ncedge = 0;
     if (n > 0) memcpy(g_ctri, tris, sizeof(int32_t) * 3 * n);
+    for (int t = 0; t < n; ++t) /* unique edges (i < j), first occurrence order over the triangles' pairs (0,1) (0,2) (1,2) */
+        for (int pr = 0; pr < 3; ++pr) {
+            const int p0 = tris[3 * t + (pr == 2 ? 1 : 0)], p1 = tris[3 * t + (pr == 0 ? 1 : 2)];
+            const int a = p0 < p1 ? p0 : p1, b = p0 < p1 ? p1 : p0;
+            int found = 0;
+            for (int j = 0; j < g_ncedge && !found; ++j) found = g_cedge[2 * j] == a && g_cedge[2 * j + 1] == b;
+            if (found) continue;
+            g_cedge[2 * g_ncedge] = a; g_cedge[2 * g_ncedge + 1] = b;
+            double l2 = 0.0;
+            for (int k = 0; k < 3; ++k) l2 += (X_rest[3 * a + k] - X_rest[3 * b + k]) * (X_rest[3 * a + k] - X_rest[3 * b + k]);
+            g_cedge_len2[g_ncedge++] = l2;
+        }
 }
 
 /* Closest feature of the triangle (t0, t1, t2) to the point p, squared distance D, dD/dp (3) and d2D/dp2 (9, row-major).
@@ -588,17 +629,157 @@ typedef struct {
     struct fem_tp_s* tp; /* active (indenter vertex, gel triangle) candidates of the last grad_hess (Gauss-Newton rank-1 terms) */
 } fem_ctx;
 
+/* ---- edge-edge candidates ---------------------------------------------------------------------------------------------------- */
+/* Closest points of the segments a = (a0, a1) and b = (b0, b1): decision order of the reference's edge_edge_distance_flag
+ * (distance_flagged.h:352-487: clamp s, then the nearly-parallel rule, then clamp t), squared distance of the resulting EE / PE / PP
+ * case (details/edge_edge.inl:706-715, point_edge.inl:5-13, point_point.inl:3-9), parameters s, t of the closest points and
+ * r = ca - cb. Full gradient by the envelope theorem: 2 r (x) [(1 - s), s, -(1 - t), -t]. Returns the flag bits (a0, a1, b0, b1) as
+ * 8 f0 + 4 f1 + 2 f2 + f3 (15 = edge-edge interior, the only case the mollifier applies to). */
+int fem_ee_closest(const double* a0, const double* a1, const double* b0, const double* b1, double* D, double* r, double* sp, double* tp)
+{
+    double u[3], v[3], w[3];
+    for (int k = 0; k < 3; ++k) { u[k] = a1[k] - a0[k]; v[k] = b1[k] - b0[k]; w[k] = a0[k] - b0[k]; }
+    const double a = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], b = u[0] * v[0] + u[1] * v[1] + u[2] * v[2],
+                 c = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = u[0] * w[0] + u[1] * w[1] + u[2] * w[2],
+                 e = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+    const double Dn = a * c - b * b;
+    double tD = Dn, tN;
+    const double sN = b * e - c * d;
+    const double x[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    int F = 15;
+    if (sN <= 0.0) { tN = e; tD = c; F = 8 | 2 | 1; }
+    else if (sN >= Dn) { tN = e + b; tD = c; F = 4 | 2 | 1; }
+    else {
+        tN = a * e - b * d;
+        if (tN > 0.0 && tN < tD && ((x[0] * w[0] + x[1] * w[1] + x[2] * w[2]) == 0.0 || xx < 1.0e-20 * a * c)) {
+            if (sN < Dn / 2) { tN = e; tD = c; F = 8 | 2 | 1; }
+            else { tN = e + b; tD = c; F = 4 | 2 | 1; }
+        }
+    }
+    if (tN <= 0.0) {
+        if (-d <= 0.0) F = 8 | 2;
+        else if (-d >= a) F = 4 | 2;
+        else F = 8 | 4 | 2;
+    } else if (tN >= tD) {
+        if ((-d + b) <= 0.0) F = 8 | 1;
+        else if ((-d + b) >= a) F = 4 | 1;
+        else F = 8 | 4 | 1;
+    }
+    double s_, t_;
+    switch (F) {
+    case 15: s_ = sN / Dn; t_ = tN / Dn; break;
+    case 8 | 2 | 1: s_ = 0.0; t_ = e / c; break;
+    case 4 | 2 | 1: s_ = 1.0; t_ = (e + b) / c; break;
+    case 8 | 4 | 2: t_ = 0.0; s_ = -d / a; break;
+    case 8 | 4 | 1: t_ = 1.0; s_ = (-d + b) / a; break;
+    case 8 | 2: s_ = 0.0; t_ = 0.0; break;
+    case 4 | 2: s_ = 1.0; t_ = 0.0; break;
+    case 8 | 1: s_ = 0.0; t_ = 1.0; break;
+    default: s_ = 1.0; t_ = 1.0; break; /* 4 | 1 */
+    }
+    for (int k = 0; k < 3; ++k) r[k] = (a0[k] + s_ * u[k]) - (b0[k] + t_ * v[k]);
+    if (F == 15) {
+        const double q = -(w[0] * x[0] + w[1] * x[1] + w[2] * x[2]); /* (b0 - a0) . (u x v) */
+        *D = q * q / xx;
+    } else if (F == (8 | 2) || F == (4 | 2) || F == (8 | 1) || F == (4 | 1)) {
+        *D = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    } else { /* point - edge */
+        const double* P = F == (8 | 2 | 1) ? a0 : (F == (4 | 2 | 1) ? a1 : (F == (8 | 4 | 2) ? b0 : b1));
+        const double *E0 = (F & 8) && (F & 4) ? a0 : b0, *E1 = (F & 8) && (F & 4) ? a1 : b1;
+        double p0[3], p1[3], ed[3];
+        for (int k = 0; k < 3; ++k) { p0[k] = E0[k] - P[k]; p1[k] = E1[k] - P[k]; ed[k] = E1[k] - E0[k]; }
+        const double cr[3] = {p0[1] * p1[2] - p0[2] * p1[1], p0[2] * p1[0] - p0[0] * p1[2], p0[0] * p1[1] - p0[1] * p1[0]};
+        *D = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) / (ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]);
+    }
+    *sp = s_; *tp = t_;
+    return F;
+}
+
+/* mollifier of nearly parallel edges (utils/distance/details/edge_edge_mollifier.inl:333-345, 347-378): e_k(c) with c = |u x v|^2 and
+ * the threshold eps_x = 1e-3 |u_rest|^2 |v_rest|^2; *de = d e_k / d c (0 outside the mollified range), gc = dc / d(a0, a1, b0, b1) */
+double fem_ee_mollifier(const double* a0, const double* a1, const double* b0, const double* b1, double eps_x, double* de, double* gc)
+{
+    double u[3], v[3];
+    for (int k = 0; k < 3; ++k) { u[k] = a1[k] - a0[k]; v[k] = b1[k] - b0[k]; }
+    const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], uv = u[0] * v[0] + u[1] * v[1] + u[2] * v[2],
+                 vv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const double x[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double c = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    if (gc)
+        for (int k = 0; k < 3; ++k) { /* d|u x v|^2/du = 2 (vv u - uv v), d/dv = 2 (uu v - uv u) */
+            const double du = 2.0 * (vv * u[k] - uv * v[k]), dv = 2.0 * (uu * v[k] - uv * u[k]);
+            gc[k] = -du; gc[3 + k] = du; gc[6 + k] = -dv; gc[9 + k] = dv;
+        }
+    if (c < eps_x) {
+        const double q = c / eps_x;
+        if (de) *de = 2.0 / eps_x * (-q + 1.0);
+        return (-q + 2.0) * q;
+    }
+    if (de) *de = 0.0;
+    return 1.0;
+}
+
+/* additive CCD of two edges (ccd.inl:267-354): as fem_pt_accd with the edge-edge distance; when that distance vanishes (far away,
+ * nearly parallel) the smallest end-point distance stands in, as in the reference */
+static double ee_dist2_ccd(const double* a0, const double* a1, const double* b0, const double* b1)
+{
+    double D, r[3], s_, t_;
+    fem_ee_closest(a0, a1, b0, b1, &D, r, &s_, &t_);
+    if (D <= 0.0) {
+        const double* P[2] = {a0, a1};
+        const double* Q[2] = {b0, b1};
+        D = 1e300;
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                double q = 0.0;
+                for (int k = 0; k < 3; ++k) q += (P[i][k] - Q[j][k]) * (P[i][k] - Q[j][k]);
+                if (q < D) D = q;
+            }
+    }
+    return D;
+}
+int fem_ee_accd(const double* a0_, const double* a1_, const double* b0_, const double* b1_, const double* da0_, const double* da1_,
+                const double* db0_, const double* db1_, double eta, double thickness, int max_iter, double* toc)
+{
+    double a0[3], a1[3], b0[3], b1[3], da0[3], da1[3], db0[3], db1[3];
+    for (int k = 0; k < 3; ++k) {
+        const double mov = (da0_[k] + da1_[k] + db0_[k] + db1_[k]) / 4;
+        a0[k] = a0_[k]; a1[k] = a1_[k]; b0[k] = b0_[k]; b1[k] = b1_[k];
+        da0[k] = da0_[k] - mov; da1[k] = da1_[k] - mov; db0[k] = db0_[k] - mov; db1[k] = db1_[k] - mov;
+    }
+    const double na0 = da0[0] * da0[0] + da0[1] * da0[1] + da0[2] * da0[2], na1 = da1[0] * da1[0] + da1[1] * da1[1] + da1[2] * da1[2],
+                 nb0 = db0[0] * db0[0] + db0[1] * db0[1] + db0[2] * db0[2], nb1 = db1[0] * db1[0] + db1[1] * db1[1] + db1[2] * db1[2];
+    const double L = sqrt(na0 > na1 ? na0 : na1) + sqrt(nb0 > nb1 ? nb0 : nb1);
+    if (L == 0.0) return 0;
+    const double xi2 = thickness * thickness;
+    double d2 = ee_dist2_ccd(a0, a1, b0, b1), d = sqrt(d2);
+    const double gap = eta * (d2 - xi2) / (d + thickness), toc_prev = *toc;
+    *toc = 0.0;
+    for (;;) {
+        if (max_iter >= 0 && --max_iter < 0) return 1;
+        const double lb = (1 - eta) * (d2 - xi2) / ((d + thickness) * L);
+        for (int k = 0; k < 3; ++k) { a0[k] += lb * da0[k]; a1[k] += lb * da1[k]; b0[k] += lb * db0[k]; b1[k] += lb * db1[k]; }
+        d2 = ee_dist2_ccd(a0, a1, b0, b1);
+        d = sqrt(d2);
+        if (*toc != 0.0 && (d2 - xi2) / (d + thickness) < gap) break;
+        *toc += lb;
+        if (*toc > toc_prev) return 0;
+    }
+    return 1;
+}
+
 /* ---- indenter VERTEX against gel TRIANGLE candidates (second half of the vertex-face contact) ------------------------------------ */
-typedef struct fem_tp_s { int n, cap; int32_t* tri; double* g9; double* w; } fem_tp;
-static void tp_push(fem_tp* tp, int f, const double* g9, double w)
+typedef struct fem_tp_s { int n, cap; int32_t* tri; double* g9; double* w; } fem_tp; /* tri: [cap][3] gel vertex ids (-1 = unused) */
+static void tp_push(fem_tp* tp, const int32_t* vid, const double* g9, double w)
 {
     if (tp->n == tp->cap) {
         tp->cap = tp->cap ? 2 * tp->cap : 256;
-        tp->tri = (int32_t*)realloc(tp->tri, sizeof(int32_t) * tp->cap);
+        tp->tri = (int32_t*)realloc(tp->tri, sizeof(int32_t) * 3 * tp->cap);
         tp->g9 = (double*)realloc(tp->g9, sizeof(double) * 9 * tp->cap);
         tp->w = (double*)realloc(tp->w, sizeof(double) * tp->cap);
     }
-    tp->tri[tp->n] = f;
+    memcpy(tp->tri + 3 * tp->n, vid, sizeof(int32_t) * 3);
     memcpy(tp->g9 + 9 * tp->n, g9, sizeof(double) * 9);
     tp->w[tp->n++] = w;
 }
@@ -614,7 +795,6 @@ static double tp_terms(const fem_cfg* g, const fem_indenter* I, const double* x,
 {
     double E = 0.0, best = 1e300;
     const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
-    if (tp) tp->n = 0;
     if (I->type != 2 || g_nctri == 0) { if (dmin) *dmin = 1e150; return 0.0; }
     for (int f = 0; f < g_nctri; ++f) {
         const int32_t* tv = g_ctri + 3 * f;
@@ -647,12 +827,95 @@ static double tp_terms(const fem_cfg* g, const fem_indenter* I, const double* x,
                     for (int j = 0; j < 3; ++j)
                         for (int a = 0; a < 3; ++a)
                             for (int b = 0; b < 3; ++b) Dg[9 * tv[j] + 3 * a + b] += we * g9[3 * j + a] * g9[3 * j + b];
-                if (tp) tp_push(tp, f, g9, we);
+                if (tp) tp_push(tp, tv, g9, we);
             }
         }
     }
     if (dmin) *dmin = sqrt(best);
     return E;
+}
+
+/* gel contact EDGES against the indenter's EDGES: closest-feature case, squared distance and barrier per candidate as the reference
+ * (mollified for the edge-edge interior case only, codim_ipc_simplex_normal_contact_function.h:176-290; the PE / PP cases of an
+ * edge-edge candidate are plain barriers, lbvh_simplex_trajectory_filter.cu:693-790); exact energy and gradient with respect to the
+ * gel edge's two vertices, Gauss-Newton Hessian e_k max(0, B'' + B' / (2 D)) gD gD^T (mollifier curvature dropped). */
+static double ee_terms(const fem_cfg* g, const fem_indenter* I, const double* x, double* G, double* Dg, fem_tp* tp, double* dmin)
+{
+    double E = 0.0, best = 1e300;
+    const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
+    if (I->type != 2 || g_ncedge == 0) { if (dmin) *dmin = 1e150; return 0.0; }
+    for (int ce = 0; ce < g_ncedge; ++ce) {
+        const int32_t vid[3] = {g_cedge[2 * ce], g_cedge[2 * ce + 1], -1};
+        const double *a0 = x + 3 * vid[0], *a1 = x + 3 * vid[1];
+        double box[6];
+        for (int k = 0; k < 3; ++k) { box[k] = fmin(a0[k], a1[k]); box[3 + k] = fmax(a0[k], a1[k]); }
+        for (int me = 0; me < g_mesh_ne; ++me) {
+            double b0[3], b1[3], bb[6];
+            mesh_vertex_world(I, g_mesh_edge[2 * me], b0);
+            mesh_vertex_world(I, g_mesh_edge[2 * me + 1], b1);
+            double bd = 0.0, vv = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                bb[k] = fmin(b0[k], b1[k]); bb[3 + k] = fmax(b0[k], b1[k]);
+                const double gap = bb[k] > box[3 + k] ? bb[k] - box[3 + k] : (box[k] > bb[3 + k] ? box[k] - bb[3 + k] : 0.0);
+                bd += gap * gap;
+                vv += (b1[k] - b0[k]) * (b1[k] - b0[k]);
+            }
+            if (!(bd < best) && !(bd < D0)) continue;
+            double D, r[3], s_, t_, B, dB, ddB;
+            const int F = fem_ee_closest(a0, a1, b0, b1, &D, r, &s_, &t_);
+            if (D < best) best = D;
+            if (!(D < D0)) continue;
+            if (!(D > 0.0)) { E = INFINITY; continue; }
+            fem_barrier(D, g->d_hat, kdt2, &B, &dB, &ddB);
+            double ek = 1.0, dek = 0.0, gc[12];
+            if (F == 15) ek = fem_ee_mollifier(a0, a1, b0, b1, 1.0e-3 * g_cedge_len2[ce] * vv, &dek, gc);
+            E += ek * B;
+            double g9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 3; ++k) { g9[k] = 2.0 * (1.0 - s_) * r[k]; g9[3 + k] = 2.0 * s_ * r[k]; }
+            if (G)
+                for (int j = 0; j < 2; ++j)
+                    for (int k = 0; k < 3; ++k)
+                        G[3 * vid[j] + k] += ek * dB * g9[3 * j + k] + (F == 15 ? B * dek * gc[3 * j + k] : 0.0);
+            const double we = ek * (ddB + dB / (2.0 * D));
+            if (we > 0.0) {
+                if (Dg)
+                    for (int j = 0; j < 2; ++j)
+                        for (int k = 0; k < 3; ++k)
+                            for (int l = 0; l < 3; ++l) Dg[9 * vid[j] + 3 * k + l] += we * g9[3 * j + k] * g9[3 * j + l];
+                if (tp) tp_push(tp, vid, g9, we);
+            }
+        }
+    }
+    if (dmin) *dmin = sqrt(best);
+    return E;
+}
+
+static double ee_ccd_alpha(const fem_cfg* g, const fem_indenter* I, const double* x0, const double* dx)
+{
+    const double zero[3] = {0, 0, 0};
+    double alpha = 1.0;
+    if (I->type != 2) return alpha;
+    for (int ce = 0; ce < g_ncedge; ++ce) {
+        const int i0 = g_cedge[2 * ce], i1 = g_cedge[2 * ce + 1];
+        double lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+            const double u0 = x0[3 * i0 + k], u1 = u0 + dx[3 * i0 + k], w0 = x0[3 * i1 + k], w1 = w0 + dx[3 * i1 + k];
+            lo[k] = fmin(fmin(u0, u1), fmin(w0, w1));
+            hi[k] = fmax(fmax(u0, u1), fmax(w0, w1));
+        }
+        for (int me = 0; me < g_mesh_ne; ++me) {
+            double b0[3], b1[3];
+            mesh_vertex_world(I, g_mesh_edge[2 * me], b0);
+            mesh_vertex_world(I, g_mesh_edge[2 * me + 1], b1);
+            int far = 0;
+            for (int k = 0; k < 3; ++k)
+                if (fmin(b0[k], b1[k]) - hi[k] > g->d_hat || lo[k] - fmax(b0[k], b1[k]) > g->d_hat) far = 1;
+            if (far) continue;
+            double toc = 1.1;
+            if (fem_ee_accd(x0 + 3 * i0, x0 + 3 * i1, b0, b1, dx + 3 * i0, dx + 3 * i1, zero, zero, 0.1, 0.0, 1000, &toc) && toc < alpha) alpha = toc;
+        }
+    }
+    return alpha;
 }
 
 /* CCD of the moving gel triangles against the (static) vertices of the indenter: the reference's ACCD per candidate behind its box
@@ -873,6 +1136,8 @@ static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
         double dtp;
         E += tp_terms(g, &c->ind, x, 0, 0, 0, &dtp);
         if (dtp < md) md = dtp;
+        E += ee_terms(g, &c->ind, x, 0, 0, 0, &dtp);
+        if (dtp < md) md = dtp;
     }
     if (g->friction_mu > 0.0)
         for (int k = 0; k < g->S; ++k) {
@@ -952,7 +1217,9 @@ static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, 
         }
         for (int j = 0; j < 9; ++j) Dg[9 * i + j] += Hk[j];
     }
+    if (c->tp) c->tp->n = 0;
     tp_terms(g, &c->ind, x, G, Dg, c->tp, 0);
+    ee_terms(g, &c->ind, x, G, Dg, c->tp, 0);
 }
 
 static void apply_A(const fem_ctx* c, const double* H9, const double* Hc, const double* p, double* y)
@@ -990,13 +1257,13 @@ static void apply_A(const fem_ctx* c, const double* H9, const double* Hc, const 
     }
     if (c->tp)
         for (int q = 0; q < c->tp->n; ++q) { /* Gauss-Newton rank-1 term of every (indenter vertex, gel triangle) candidate */
-            const int32_t* tv = g_ctri + 3 * c->tp->tri[q];
+            const int32_t* tv = c->tp->tri + 3 * q;
             const double* g9 = c->tp->g9 + 9 * q;
             double sp = 0.0;
-            for (int j = 0; j < 3; ++j)
+            for (int j = 0; j < 3 && tv[j] >= 0; ++j)
                 for (int a = 0; a < 3; ++a) sp += g9[3 * j + a] * p[3 * tv[j] + a];
             sp *= c->tp->w[q];
-            for (int j = 0; j < 3; ++j)
+            for (int j = 0; j < 3 && tv[j] >= 0; ++j)
                 for (int a = 0; a < 3; ++a) y[3 * tv[j] + a] += sp * g9[3 * j + a];
         }
 }
@@ -1118,6 +1385,8 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
                 double dtp;
                 tp_terms(g, &c.ind, x, 0, 0, 0, &dtp);
                 if (dtp < md) md = dtp;
+                ee_terms(g, &c.ind, x, 0, 0, 0, &dtp);
+                if (dtp < md) md = dtp;
             }
             double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
             if (ds < 0.0) ds = 0.0;
@@ -1146,6 +1415,8 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
             alpha = mesh_ccd_alpha(g, &c.ind, x0, dx, surf, g->S);
             const double atp = tp_ccd_alpha(g, &c.ind, x0, dx);
             if (atp < alpha) alpha = atp;
+            const double aee = ee_ccd_alpha(g, &c.ind, x0, dx);
+            if (aee < alpha) alpha = aee;
         }
         else for (int k = 0; k < g->S; ++k) {
             int i = surf[k];

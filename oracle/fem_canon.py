@@ -102,15 +102,14 @@ class CanonFem:
         t = np.ascontiguousarray(tri_local, np.float64).reshape(-1, 9)
         lib().fem_set_indenter_mesh(_d(t), C.c_int(len(t)))
 
-    @staticmethod
-    def set_contact_surface(tris) -> None:
-        """Triangles (n, 3) int32 of the gel surface the indenter mesh's VERTICES can touch (second half of the vertex-face contact);
-        ``None`` switches it off. Process-wide like the C global."""
+    def set_contact_surface(self, tris) -> None:
+        """Triangles (n, 3) int32 of the gel surface the indenter mesh's VERTICES (against the triangles) and EDGES (against the
+        triangles' edges) can touch; ``None`` switches both off. Process-wide like the C global."""
         if tris is None:
-            lib().fem_set_contact_surface(None, C.c_int(0))
+            lib().fem_set_contact_surface(None, C.c_int(0), None)
             return
         t = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
-        lib().fem_set_contact_surface(_i(t), C.c_int(len(t)))
+        lib().fem_set_contact_surface(_i(t), C.c_int(len(t)), _d(self.X))
 
     def step(self, x, v, x_prev, aim, ind_prev, ind_next):
         """x, v, x_prev: (N, V, 3) float64 updated in place; aim (N, A, 3); indenters: lists of FemIndenter."""

@@ -16,7 +16,8 @@
 // file outside the repo (deleted after the compile) -- every other reference file is read where it lies.
 #include REF_DISTANCE_FLAGGED_H
 #include <algorithm>
-#include <utils/distance/ccd.h> // + details/ccd.inl (ACCD); instantiated below: point_triangle_ccd only
+#include <utils/distance/ccd.h> // + details/ccd.inl (ACCD); instantiated below: point_triangle_ccd, edge_edge_ccd
+#include <utils/distance/edge_edge_mollifier.h>
 
 using namespace uipc;
 namespace D = uipc::backend::cuda::distance;
@@ -76,6 +77,23 @@ int ref_pt_ccd(const double* p, const double* t0, const double* t1, const double
                const double* dt1, const double* dt2, double eta, double thickness, int max_iter, double* toc)
 {
     return D::point_triangle_ccd(v3(p), v3(t0), v3(t1), v3(t2), v3(dp), v3(dt0), v3(dt1), v3(dt2), eta, thickness, max_iter, *toc) ? 1 : 0;
+}
+
+int ref_ee_ccd(const double* a0, const double* a1, const double* b0, const double* b1, const double* da0, const double* da1,
+               const double* db0, const double* db1, double eta, double thickness, int max_iter, double* toc)
+{
+    return D::edge_edge_ccd(v3(a0), v3(a1), v3(b0), v3(b1), v3(da0), v3(da1), v3(db0), v3(db1), eta, thickness, max_iter, *toc) ? 1 : 0;
+}
+
+// mollifier of nearly parallel edges: threshold from the rest edges, value and 12-gradient
+void ref_ee_mollifier(const double* ra0, const double* ra1, const double* rb0, const double* rb1, const double* a0, const double* a1,
+                      const double* b0, const double* b1, double* eps_x, double* e, double* g)
+{
+    D::edge_edge_mollifier_threshold(v3(ra0), v3(ra1), v3(rb0), v3(rb1), *eps_x);
+    D::edge_edge_mollifier(v3(a0), v3(a1), v3(b0), v3(b1), *eps_x, *e);
+    Vector12 gg;
+    D::edge_edge_mollifier_gradient(v3(a0), v3(a1), v3(b0), v3(b1), *eps_x, gg);
+    for (int i = 0; i < 12; ++i) g[i] = gg(i);
 }
 
 } // extern "C"

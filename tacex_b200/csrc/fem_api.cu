@@ -41,6 +41,10 @@ struct tx_fem {
     double* d_mesh_vert = nullptr;
     int *d_ctri = nullptr, *d_ctri_row_start = nullptr, *d_ctri_row_adj = nullptr, *d_ctri_edge_start = nullptr, *d_ctri_edge_adj = nullptr;
     std::map<std::pair<int, int>, int> edge_of; // (i, j), i < j -> edge number (tx_fem_create)
+    std::vector<double> h_X;                    // rest positions (mollifier threshold of the edge-edge candidates)
+    int n_cedge = 0, mesh_ne = 0;
+    int *d_cedge = nullptr, *d_cedge_row_start = nullptr, *d_cedge_row_adj = nullptr, *d_edge_cedge = nullptr, *d_mesh_edge = nullptr;
+    double* d_cedge_len2 = nullptr;
 };
 
 // Default assembly chunk (see fem_kernel.cu, grad_hess): measured on the B200, profiles/r02_fem_chunk.txt
@@ -77,6 +81,7 @@ extern "C" int tx_fem_create(const tx_fem_config* c, const double* X, const int3
     f->cfg = *c;
     f->device = device;
     f->stream = (cudaStream_t)cuda_stream;
+    f->h_X.assign(X, X + (size_t)3 * c->V);
     {   // tets per assembly chunk: a multiple of 32 in [32, threads]; TX_FEM_CHUNK overrides the default for experiments
         int ch = FEM_DEFAULT_CHUNK;
         if (const char* ev = getenv("TX_FEM_CHUNK")) ch = atoi(ev);
@@ -264,6 +269,7 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
     cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top); cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box); cudaFree(f->d_mesh_vert);
     cudaFree(f->d_ctri); cudaFree(f->d_ctri_row_start); cudaFree(f->d_ctri_row_adj); cudaFree(f->d_ctri_edge_start); cudaFree(f->d_ctri_edge_adj);
+    cudaFree(f->d_cedge); cudaFree(f->d_cedge_row_start); cudaFree(f->d_cedge_row_adj); cudaFree(f->d_edge_cedge); cudaFree(f->d_mesh_edge); cudaFree(f->d_cedge_len2);
     delete f;
 }
 
@@ -297,6 +303,9 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.ctri = f->d_ctri; a.n_ctri = f->mesh_n > 0 ? f->n_ctri : 0;
     a.ctri_row_start = f->d_ctri_row_start; a.ctri_row_adj = f->d_ctri_row_adj;
     a.ctri_edge_start = f->d_ctri_edge_start; a.ctri_edge_adj = f->d_ctri_edge_adj;
+    a.cedge = f->d_cedge; a.cedge_len2 = f->d_cedge_len2; a.n_cedge = f->mesh_n > 0 ? f->n_cedge : 0;
+    a.cedge_row_start = f->d_cedge_row_start; a.cedge_row_adj = f->d_cedge_row_adj; a.edge_cedge = f->d_edge_cedge;
+    a.mesh_edge = f->d_mesh_edge; a.mesh_ne = f->mesh_ne;
     a.dbg_cycles = f->d_cycles;
     a.dbg_mode = getenv("TX_FEM_DBG_MODE") ? atoi(getenv("TX_FEM_DBG_MODE")) : 0;
     a.row_start = f->d_adj_off;
@@ -320,7 +329,7 @@ extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri
     FEM_CUDA(f, cudaStreamSynchronize(f->stream)); // a step in flight may still read the old mesh
     cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box); cudaFree(f->d_mesh_vert);
     f->d_mesh_tri = f->d_mesh_box = f->d_mesh_vert = nullptr;
-    f->mesh_n = f->mesh_nv = 0;
+    f->mesh_n = f->mesh_nv = f->mesh_ne = 0;
     if (n_tris == 0) return TX_OK;
     std::vector<double> box((size_t)6 * n_tris);
     for (int t = 0; t < n_tris; ++t) {
@@ -354,6 +363,27 @@ extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri
         FEM_CUDA(f, cudaMalloc(&f->d_mesh_vert, sizeof(double) * vert.size()));
         FEM_CUDA(f, cudaMemcpy(f->d_mesh_vert, vert.data(), sizeof(double) * vert.size(), cudaMemcpyHostToDevice));
         f->mesh_nv = (int)(vert.size() / 3);
+        // unique edges by vertex id, first occurrence order (edge-edge candidates)
+        std::vector<int> me;
+        for (int t = 0; t < n_tris; ++t) {
+            int id[3];
+            for (int k = 0; k < 3; ++k) {
+                const double* v = tri_local + (size_t)9 * t + 3 * k;
+                id[k] = 0;
+                while (!(vert[3 * id[k]] == v[0] && vert[3 * id[k] + 1] == v[1] && vert[3 * id[k] + 2] == v[2])) ++id[k];
+            }
+            for (int k = 0; k < 3; ++k) {
+                const int a = std::min(id[k], id[(k + 1) % 3]), b = std::max(id[k], id[(k + 1) % 3]);
+                bool found = false;
+                for (size_t j = 0; j < me.size() / 2 && !found; ++j) found = me[2 * j] == a && me[2 * j + 1] == b;
+                if (!found) { me.push_back(a); me.push_back(b); }
+            }
+        }
+        cudaFree(f->d_mesh_edge);
+        f->d_mesh_edge = nullptr;
+        FEM_CUDA(f, cudaMalloc(&f->d_mesh_edge, sizeof(int) * std::max<size_t>(me.size(), 1)));
+        FEM_CUDA(f, cudaMemcpy(f->d_mesh_edge, me.data(), sizeof(int) * me.size(), cudaMemcpyHostToDevice));
+        f->mesh_ne = (int)(me.size() / 2);
     }
     f->mesh_n = n_tris;
     return TX_OK;
@@ -366,8 +396,11 @@ extern "C" int tx_fem_set_contact_surface(tx_fem* f, int n_tris, const int32_t* 
     FEM_CUDA(f, cudaSetDevice(f->device));
     FEM_CUDA(f, cudaStreamSynchronize(f->stream));
     cudaFree(f->d_ctri); cudaFree(f->d_ctri_row_start); cudaFree(f->d_ctri_row_adj); cudaFree(f->d_ctri_edge_start); cudaFree(f->d_ctri_edge_adj);
+    cudaFree(f->d_cedge); cudaFree(f->d_cedge_row_start); cudaFree(f->d_cedge_row_adj); cudaFree(f->d_edge_cedge); cudaFree(f->d_cedge_len2);
     f->d_ctri = f->d_ctri_row_start = f->d_ctri_row_adj = f->d_ctri_edge_start = f->d_ctri_edge_adj = nullptr;
-    f->n_ctri = 0;
+    f->d_cedge = f->d_cedge_row_start = f->d_cedge_row_adj = f->d_edge_cedge = nullptr;
+    f->d_cedge_len2 = nullptr;
+    f->n_ctri = f->n_cedge = 0;
     if (n_tris == 0) return TX_OK;
     const int V = f->cfg.V, nE = f->nE;
     static const int PR[3][2] = {{0, 1}, {0, 2}, {1, 2}};
@@ -399,6 +432,39 @@ extern "C" int tx_fem_set_contact_surface(tx_fem* f, int n_tris, const int32_t* 
     FEM_CUDA(f, cudaMemcpy(f->d_ctri_row_adj, ra.data(), sizeof(int) * ra.size(), cudaMemcpyHostToDevice));
     FEM_CUDA(f, cudaMemcpy(f->d_ctri_edge_start, es.data(), sizeof(int) * es.size(), cudaMemcpyHostToDevice));
     FEM_CUDA(f, cudaMemcpy(f->d_ctri_edge_adj, ea.data(), sizeof(int) * ea.size(), cudaMemcpyHostToDevice));
+    {   // unique edges of the triangles (first occurrence order over the pairs (0,1) (0,2) (1,2)): one edge-edge thread each
+        std::vector<int> ce, ec(nE, -1);
+        std::vector<double> len2;
+        for (int t = 0; t < n_tris; ++t)
+            for (int pr = 0; pr < 3; ++pr) {
+                const int p0 = tris[3 * t + PR[pr][0]], p1 = tris[3 * t + PR[pr][1]];
+                const int a = std::min(p0, p1), b = std::max(p0, p1);
+                const int e = f->edge_of.find({a, b})->second;
+                if (ec[e] >= 0) continue;
+                ec[e] = (int)(ce.size() / 2);
+                ce.push_back(a); ce.push_back(b);
+                double l2 = 0.0;
+                for (int k = 0; k < 3; ++k) l2 += (f->h_X[3 * a + k] - f->h_X[3 * b + k]) * (f->h_X[3 * a + k] - f->h_X[3 * b + k]);
+                len2.push_back(l2);
+            }
+        const int nce = (int)(ce.size() / 2);
+        if (nce > fem_threads()) return ffail(f, TX_ERR_UNSUPPORTED, "tx_fem_set_contact_surface: more contact edges than threads (one edge per thread)");
+        std::vector<std::vector<int>> er(V);
+        for (int q = 0; q < nce; ++q) { er[ce[2 * q]].push_back(q << 1); er[ce[2 * q + 1]].push_back(q << 1 | 1); }
+        std::vector<int> ers(V + 1, 0), era;
+        for (int i = 0; i < V; ++i) { era.insert(era.end(), er[i].begin(), er[i].end()); ers[i + 1] = (int)era.size(); }
+        FEM_CUDA(f, cudaMalloc(&f->d_cedge, sizeof(int) * ce.size()));
+        FEM_CUDA(f, cudaMalloc(&f->d_cedge_len2, sizeof(double) * len2.size()));
+        FEM_CUDA(f, cudaMalloc(&f->d_cedge_row_start, sizeof(int) * ers.size()));
+        FEM_CUDA(f, cudaMalloc(&f->d_cedge_row_adj, sizeof(int) * era.size()));
+        FEM_CUDA(f, cudaMalloc(&f->d_edge_cedge, sizeof(int) * nE));
+        FEM_CUDA(f, cudaMemcpy(f->d_cedge, ce.data(), sizeof(int) * ce.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA(f, cudaMemcpy(f->d_cedge_len2, len2.data(), sizeof(double) * len2.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA(f, cudaMemcpy(f->d_cedge_row_start, ers.data(), sizeof(int) * ers.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA(f, cudaMemcpy(f->d_cedge_row_adj, era.data(), sizeof(int) * era.size(), cudaMemcpyHostToDevice));
+        FEM_CUDA(f, cudaMemcpy(f->d_edge_cedge, ec.data(), sizeof(int) * nE, cudaMemcpyHostToDevice));
+        f->n_cedge = nce;
+    }
     f->n_ctri = n_tris;
     return TX_OK;
 }

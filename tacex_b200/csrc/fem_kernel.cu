@@ -723,6 +723,234 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
     return alpha;
 }
 
+// ---- edge-edge candidates: gel contact EDGE (two unknown vertices) against a static indenter EDGE --------------------------------
+// Decision order of the reference's edge_edge_distance_flag (distance_flagged.h:352-487), squared distance of the resulting EE / PE /
+// PP case, closest-point parameters s (gel edge) and t; gradient 2 r (x) [(1 - s), s] by the envelope theorem (pinned against the
+// reference's 12-gradient). Returns the flag bits 8 a0 + 4 a1 + 2 b0 + b1 (15 = interior: the only mollified case).
+__device__ __forceinline__ int ee_closest(const double a0[3], const double a1[3], const double b0[3], const double b1[3], double& D,
+                                          double r[3], double& s_, double& t_)
+{
+    const double u[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]}, v[3] = {b1[0] - b0[0], b1[1] - b0[1], b1[2] - b0[2]},
+                 w[3] = {a0[0] - b0[0], a0[1] - b0[1], a0[2] - b0[2]};
+    const double a = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], b = u[0] * v[0] + u[1] * v[1] + u[2] * v[2],
+                 c = v[0] * v[0] + v[1] * v[1] + v[2] * v[2], d = u[0] * w[0] + u[1] * w[1] + u[2] * w[2],
+                 e = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+    const double Dn = a * c - b * b;
+    double tD = Dn, tN;
+    const double sN = b * e - c * d;
+    const double x[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double xx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+    int F = 15;
+    if (sN <= 0.0) { tN = e; tD = c; F = 8 | 2 | 1; }
+    else if (sN >= Dn) { tN = e + b; tD = c; F = 4 | 2 | 1; }
+    else {
+        tN = a * e - b * d;
+        if (tN > 0.0 && tN < tD && ((x[0] * w[0] + x[1] * w[1] + x[2] * w[2]) == 0.0 || xx < 1.0e-20 * a * c)) {
+            if (sN < Dn / 2) { tN = e; tD = c; F = 8 | 2 | 1; }
+            else { tN = e + b; tD = c; F = 4 | 2 | 1; }
+        }
+    }
+    if (tN <= 0.0) {
+        if (-d <= 0.0) F = 8 | 2;
+        else if (-d >= a) F = 4 | 2;
+        else F = 8 | 4 | 2;
+    } else if (tN >= tD) {
+        if ((-d + b) <= 0.0) F = 8 | 1;
+        else if ((-d + b) >= a) F = 4 | 1;
+        else F = 8 | 4 | 1;
+    }
+    switch (F) {
+    case 15: s_ = sN / Dn; t_ = tN / Dn; break;
+    case 8 | 2 | 1: s_ = 0.0; t_ = e / c; break;
+    case 4 | 2 | 1: s_ = 1.0; t_ = (e + b) / c; break;
+    case 8 | 4 | 2: t_ = 0.0; s_ = -d / a; break;
+    case 8 | 4 | 1: t_ = 1.0; s_ = (-d + b) / a; break;
+    case 8 | 2: s_ = 0.0; t_ = 0.0; break;
+    case 4 | 2: s_ = 1.0; t_ = 0.0; break;
+    case 8 | 1: s_ = 0.0; t_ = 1.0; break;
+    default: s_ = 1.0; t_ = 1.0; break;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[k] = (a0[k] + s_ * u[k]) - (b0[k] + t_ * v[k]);
+    if (F == 15) {
+        const double q = -(w[0] * x[0] + w[1] * x[1] + w[2] * x[2]);
+        D = q * q / xx;
+    } else if (F == (8 | 2) || F == (4 | 2) || F == (8 | 1) || F == (4 | 1)) {
+        D = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    } else {
+        const double* P = F == (8 | 2 | 1) ? a0 : (F == (4 | 2 | 1) ? a1 : (F == (8 | 4 | 2) ? b0 : b1));
+        const bool on_a = (F & 8) && (F & 4);
+        const double* E0 = on_a ? a0 : b0;
+        const double* E1 = on_a ? a1 : b1;
+        const double p0[3] = {E0[0] - P[0], E0[1] - P[1], E0[2] - P[2]}, p1[3] = {E1[0] - P[0], E1[1] - P[1], E1[2] - P[2]},
+                     ed[3] = {E1[0] - E0[0], E1[1] - E0[1], E1[2] - E0[2]};
+        const double cr[3] = {p0[1] * p1[2] - p0[2] * p1[1], p0[2] * p1[0] - p0[0] * p1[2], p0[0] * p1[1] - p0[1] * p1[0]};
+        D = (cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]) / (ed[0] * ed[0] + ed[1] * ed[1] + ed[2] * ed[2]);
+    }
+    return F;
+}
+
+struct MeshEdges { const double* vert; const int* edge; int ne; double d_hat; };
+// per gel contact edge: k 0..5 gradient of its two vertices, 6..17 their diagonal blocks (symmetric), 18..23 the pair block
+struct EeOut { double E, dmin2, v[24]; int bad; };
+__device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, double3 r1, double3 r2, double3 xa, double3 xb, double len2,
+                                           double kdt2, int derivs, EeOut* o)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double a0[3] = {xa.x, xa.y, xa.z}, a1[3] = {xb.x, xb.y, xb.z};
+    const double D0 = me.d_hat * me.d_hat;
+    double E = 0.0, best = 1e300;
+    int bad = 0;
+    if (derivs)
+        for (int k = 0; k < 24; ++k) o->v[k] = 0.0;
+    for (int q = 0; q < me.ne; ++q) {
+        const double* l0 = me.vert + 3 * me.edge[2 * q];
+        const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
+        double b0[3], b1[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double cc = i == 0 ? c.x : (i == 1 ? c.y : c.z);
+            b0[i] = cc + R[3 * i] * l0[0] + R[3 * i + 1] * l0[1] + R[3 * i + 2] * l0[2];
+            b1[i] = cc + R[3 * i] * l1[0] + R[3 * i + 1] * l1[1] + R[3 * i + 2] * l1[2];
+        }
+        double bd = 0.0, vv = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double blo = fmin(b0[k], b1[k]), bhi = fmax(b0[k], b1[k]), alo = fmin(a0[k], a1[k]), ahi = fmax(a0[k], a1[k]);
+            const double gap = blo > ahi ? blo - ahi : (alo > bhi ? alo - bhi : 0.0);
+            bd += gap * gap;
+            vv += (b1[k] - b0[k]) * (b1[k] - b0[k]);
+        }
+        if (!(bd < best) && !(bd < D0)) continue;
+        double D, r[3], s_, t_;
+        const int F = ee_closest(a0, a1, b0, b1, D, r, s_, t_);
+        if (D < best) best = D;
+        if (!(D < D0)) continue;
+        if (!(D > 0.0)) { bad = 1; continue; }
+        double B, dB, ddB;
+        barrier_fn(D, me.d_hat, kdt2, &B, &dB, &ddB);
+        double ek = 1.0, dek = 0.0, du[3] = {0.0, 0.0, 0.0};
+        if (F == 15) { // mollifier of nearly parallel edges: e_k(|u x v|^2), threshold 1e-3 |u_rest|^2 |v|^2
+            const double u[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]}, v[3] = {b1[0] - b0[0], b1[1] - b0[1], b1[2] - b0[2]};
+            const double uv = u[0] * v[0] + u[1] * v[1] + u[2] * v[2];
+            const double x[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+            const double cn = x[0] * x[0] + x[1] * x[1] + x[2] * x[2], eps = 1.0e-3 * len2 * vv;
+            if (cn < eps) {
+                const double qq = cn / eps;
+                ek = (-qq + 2.0) * qq;
+                dek = 2.0 / eps * (-qq + 1.0);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) du[k] = 2.0 * (vv * u[k] - uv * v[k]);
+            }
+        }
+        E += ek * B;
+        if (derivs) {
+            const double g0 = 2.0 * (1.0 - s_), g1 = 2.0 * s_;
+            const double we = ek * (ddB + dB / (2.0 * D)), wp = we > 0.0 ? we : 0.0;
+            const double rr[6] = {r[0] * r[0], r[0] * r[1], r[0] * r[2], r[1] * r[1], r[1] * r[2], r[2] * r[2]};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                o->v[k] += ek * dB * g0 * r[k] - B * dek * du[k];
+                o->v[3 + k] += ek * dB * g1 * r[k] + B * dek * du[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                o->v[6 + k] += wp * g0 * g0 * rr[k];
+                o->v[12 + k] += wp * g1 * g1 * rr[k];
+                o->v[18 + k] += wp * g0 * g1 * rr[k];
+            }
+        }
+    }
+    o->E = E; o->dmin2 = best; o->bad = bad;
+}
+
+// ACCD of a moving gel edge against the static edges of the indenter (ccd.inl:267-354): min(1, min toc)
+__device__ __forceinline__ double ee_dist2_ccd(const double a0[3], const double a1[3], const double b0[3], const double b1[3])
+{
+    double D, r[3], s_, t_;
+    ee_closest(a0, a1, b0, b1, D, r, s_, t_);
+    if (D <= 0.0) { // far away, nearly parallel: the smallest end-point distance stands in (as in the reference)
+        D = 1e300;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double* P = i ? a1 : a0;
+                const double* Q = j ? b1 : b0;
+                const double q = (P[0] - Q[0]) * (P[0] - Q[0]) + (P[1] - Q[1]) * (P[1] - Q[1]) + (P[2] - Q[2]) * (P[2] - Q[2]);
+                D = fmin(D, q);
+            }
+    }
+    return D;
+}
+__device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, double3 r1, double3 r2, double3 xa, double3 xb, double3 da,
+                                           double3 db)
+{
+    const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
+    const double A0[3] = {xa.x, xa.y, xa.z}, A1[3] = {xb.x, xb.y, xb.z}, dA0[3] = {da.x, da.y, da.z}, dA1[3] = {db.x, db.y, db.z};
+    double lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double u0 = A0[k], u1 = u0 + dA0[k], w0 = A1[k], w1 = w0 + dA1[k];
+        lo[k] = fmin(fmin(u0, u1), fmin(w0, w1));
+        hi[k] = fmax(fmax(u0, u1), fmax(w0, w1));
+    }
+    const double eta = 0.1;
+    double alpha = 1.0;
+    for (int q = 0; q < me.ne; ++q) {
+        const double* l0 = me.vert + 3 * me.edge[2 * q];
+        const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
+        double b0[3], b1[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double cc = i == 0 ? c.x : (i == 1 ? c.y : c.z);
+            b0[i] = cc + R[3 * i] * l0[0] + R[3 * i + 1] * l0[1] + R[3 * i + 2] * l0[2];
+            b1[i] = cc + R[3 * i] * l1[0] + R[3 * i + 1] * l1[1] + R[3 * i + 2] * l1[2];
+        }
+        bool far = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (fmin(b0[k], b1[k]) - hi[k] > me.d_hat || lo[k] - fmax(b0[k], b1[k]) > me.d_hat) far = true;
+        if (far) continue;
+        double a0[3], a1[3], da0[3], da1[3], db0[3], db1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double mov = (dA0[k] + dA1[k] + 0.0 + 0.0) / 4;
+            a0[k] = A0[k]; a1[k] = A1[k];
+            da0[k] = dA0[k] - mov; da1[k] = dA1[k] - mov; db0[k] = 0.0 - mov; db1[k] = 0.0 - mov;
+        }
+        const double na0 = da0[0] * da0[0] + da0[1] * da0[1] + da0[2] * da0[2], na1 = da1[0] * da1[0] + da1[1] * da1[1] + da1[2] * da1[2],
+                     nb0 = db0[0] * db0[0] + db0[1] * db0[1] + db0[2] * db0[2], nb1 = db1[0] * db1[0] + db1[1] * db1[1] + db1[2] * db1[2];
+        const double L = sqrt(na0 > na1 ? na0 : na1) + sqrt(nb0 > nb1 ? nb0 : nb1);
+        if (L == 0.0) continue;
+        double d2 = ee_dist2_ccd(a0, a1, b0, b1), d = sqrt(d2);
+        const double gap = eta * d2 / d, toc_prev = 1.1;
+        double toc = 0.0;
+        bool hit = true;
+        for (int it = 1000;;) {
+            if (--it < 0) break;
+            const double lb = (1 - eta) * d2 / (d * L);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { a0[k] += lb * da0[k]; a1[k] += lb * da1[k]; b0[k] += lb * db0[k]; b1[k] += lb * db1[k]; }
+            d2 = ee_dist2_ccd(a0, a1, b0, b1);
+            d = sqrt(d2);
+            if (toc != 0.0 && d2 / d < gap) break;
+            toc += lb;
+            if (toc > toc_prev) { hit = false; break; }
+        }
+        if (hit && toc < alpha) alpha = toc;
+    }
+    return alpha;
+}
+__device__ __forceinline__ void ee_terms(const FemArgs& a, const FemIndenter& I, const double* xs, int ce, double kdt2, int derivs, EeOut* o)
+{
+    const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat};
+    const int i0 = a.cedge[2 * ce], i1 = a.cedge[2 * ce + 1];
+    ee_terms_impl(me, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
+                  make_double3(I.R[6], I.R[7], I.R[8]), make_double3(xs[3 * i0], xs[3 * i0 + 1], xs[3 * i0 + 2]),
+                  make_double3(xs[3 * i1], xs[3 * i1 + 1], xs[3 * i1 + 2]), a.cedge_len2[ce], kdt2, derivs, o);
+}
+
 __device__ __forceinline__ void tp_terms(const FemArgs& a, const FemIndenter& I, const double* xs, int f, double kdt2, int derivs, TpOut* o)
 {
     const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat};
@@ -1089,6 +1317,13 @@ __device__ double total_energy(const FemArgs& a, const FemShared& s, const doubl
         md = fmin(md, sqrt(o.dmin2));
         if (o.bad) bad = true;
     }
+    if (MESH && ind.type == 2 && a.n_cedge > 0 && threadIdx.x < a.n_cedge) { // indenter edges against this thread's gel edge
+        EeOut o;
+        ee_terms(a, ind, s.x, threadIdx.x, a.kappa * dt2, 0, &o);
+        E += o.E;
+        md = fmin(md, sqrt(o.dmin2));
+        if (o.bad) bad = true;
+    }
     for (int t = threadIdx.x; t < a.T; t += FEM_THREADS) {
         double W[4][3], F[9], e;
         const int4 ev4 = reinterpret_cast<const int4*>(a.tets)[t];
@@ -1220,6 +1455,12 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
 #pragma unroll 5
             for (int k = 0; k < 45; ++k) tsc[(size_t)k * FEM_THREADS + threadIdx.x] = o.v[k];
         }
+        if (threadIdx.x < a.n_cedge) { // edge-edge candidates of this thread's gel edge: rows 45..68 of the scratch
+            EeOut o;
+            ee_terms(a, ind, s.x, threadIdx.x, a.kappa * dt2, 1, &o);
+#pragma unroll 4
+            for (int k = 0; k < 24; ++k) tsc[(size_t)(45 + k) * FEM_THREADS + threadIdx.x] = o.v[k];
+        }
         __syncthreads();
         if (on) {
             for (int q = a.ctri_row_start[i]; q < a.ctri_row_start[i + 1]; ++q) {
@@ -1229,11 +1470,23 @@ __device__ void grad_hess(const FemArgs& a, const FemShared& s, const double* xt
 #pragma unroll
                 for (int k = 0; k < 6; ++k) d6[k] += tf[(size_t)(9 + 6 * j + k) * FEM_THREADS];
             }
+            for (int q = a.cedge_row_start[i]; q < a.cedge_row_start[i + 1]; ++q) {
+                const int ent = a.cedge_row_adj[q], ce = ent >> 1, j = ent & 1;
+                const double* tf = tsc + (size_t)45 * FEM_THREADS + ce;
+                g3[0] += tf[(size_t)(3 * j) * FEM_THREADS]; g3[1] += tf[(size_t)(3 * j + 1) * FEM_THREADS]; g3[2] += tf[(size_t)(3 * j + 2) * FEM_THREADS];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d6[k] += tf[(size_t)(6 + 6 * j + k) * FEM_THREADS];
+            }
         }
         for (int e = threadIdx.x; e < a.nE; e += FEM_THREADS) {
             const int q0 = a.ctri_edge_start[e], q1 = a.ctri_edge_start[e + 1];
-            if (q0 == q1) continue;
+            const int ce = a.n_cedge > 0 ? a.edge_cedge[e] : -1;
+            if (q0 == q1 && ce < 0) continue;
             double b6[6] = {0, 0, 0, 0, 0, 0};
+            if (ce >= 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) b6[k] = tsc[(size_t)(45 + 18 + k) * FEM_THREADS + ce];
+            }
             for (int q = q0; q < q1; ++q) {
                 const int ent = a.ctri_edge_adj[q], f = ent >> 2, pr = ent & 3;
 #pragma unroll
@@ -1450,6 +1703,11 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                     tp_terms(a, cur, s.x, threadIdx.x, 0.0, 0, &o);
                     md = fmin(md, sqrt(o.dmin2));
                 }
+                if (MESH && cur.type == 2 && a.n_cedge > 0 && threadIdx.x < a.n_cedge) {
+                    EeOut o;
+                    ee_terms(a, cur, s.x, threadIdx.x, 0.0, 0, &o);
+                    md = fmin(md, sqrt(o.dmin2));
+                }
                 md = block_reduce<1>(md, s.red, ph);
                 double ds = umax > 0.0 ? 0.5 * md / umax : 1.0;
                 if (ds < 0.0) ds = 0.0;
@@ -1494,6 +1752,16 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                             make_double3(s.x[3 * i2], s.x[3 * i2 + 1], s.x[3 * i2 + 2]), make_double3(s.p[3 * i0], s.p[3 * i0 + 1], s.p[3 * i0 + 2]),
                             make_double3(s.p[3 * i1], s.p[3 * i1 + 1], s.p[3 * i1 + 2]), make_double3(s.p[3 * i2], s.p[3 * i2 + 1], s.p[3 * i2 + 2]));
                         alpha = fmin(alpha, at);
+                    }
+                    if (threadIdx.x < a.n_cedge) {
+                        const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat};
+                        const int i0 = a.cedge[2 * threadIdx.x], i1 = a.cedge[2 * threadIdx.x + 1];
+                        const double ae = ee_ccd_impl(
+                            me, make_double3(ind.c[0], ind.c[1], ind.c[2]), make_double3(ind.R[0], ind.R[1], ind.R[2]),
+                            make_double3(ind.R[3], ind.R[4], ind.R[5]), make_double3(ind.R[6], ind.R[7], ind.R[8]),
+                            make_double3(s.x[3 * i0], s.x[3 * i0 + 1], s.x[3 * i0 + 2]), make_double3(s.x[3 * i1], s.x[3 * i1 + 1], s.x[3 * i1 + 2]),
+                            make_double3(s.p[3 * i0], s.p[3 * i0 + 1], s.p[3 * i0 + 2]), make_double3(s.p[3 * i1], s.p[3 * i1 + 1], s.p[3 * i1 + 2]));
+                        alpha = fmin(alpha, ae);
                     }
                 }
             } else if (is_surf) {

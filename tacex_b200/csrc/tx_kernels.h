@@ -198,6 +198,15 @@ struct FemArgs {
     const int* ctri_row_adj;   // triangle << 2 | local vertex
     const int* ctri_edge_start; // [nE + 1] entries of ctri_edge_adj per mesh edge
     const int* ctri_edge_adj;  // triangle << 2 | pair (0: (0,1), 1: (0,2), 2: (1,2))
+    // edge-edge candidates: the unique edges of the contact triangles (one per thread) against the unique edges of the indenter mesh
+    const int* cedge;          // [n_cedge][2] gel vertex ids (i < j)
+    const double* cedge_len2;  // [n_cedge] squared rest lengths (mollifier threshold)
+    int n_cedge;
+    const int* cedge_row_start; // [V + 1]
+    const int* cedge_row_adj;  // contact edge << 1 | local vertex
+    const int* edge_cedge;     // [nE] mesh edge -> contact edge or -1
+    const int* mesh_edge;      // [mesh_ne][2] ids into mesh_vert
+    int mesh_ne;
     int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
     long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate, friction_mu, eps_velocity;

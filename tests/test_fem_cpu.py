@@ -361,7 +361,7 @@ def test_indenter_vertices_against_gel_triangles_in_the_restatement():
     out = {}
     try:
         for on in (False, True):
-            fc.CanonFem.set_contact_surface(m.top_tris if on else None)
+            cf.set_contact_surface(m.top_tris if on else None)
             x, v, xp = cf.new_state(1)
             for s in range(8):
                 st = cf.step(x, v, xp, aim, [fc.make_indenter(2, ctr(s), (0, 0, 0))], [fc.make_indenter(2, ctr(s + 1), (0, 0, 0))])
@@ -395,5 +395,19 @@ def test_indenter_vertices_against_gel_triangles_in_the_restatement():
             d = np.zeros_like(x); d[touched, a] = 1e-9
             fd = (energy(x + d) - energy(x - d)) / 2e-9
             assert abs(-b[3 * touched + a] - fd) <= 2e-4 * max(abs(fd), np.abs(b).max() * 1e-3), (a, b[3 * touched + a], fd)
+        # edge-edge: a small wedge turned by 90 degrees, its edge along x half-way between two rows of gel vertices
+        th = np.pi / 2
+        R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+        fc.CanonFem.set_indenter_mesh(synth.indenter_mesh(2, 1.0e-3))
+        ctr2 = lambda s: [1.0e-3, 1.05e-3, z0 - 0.9e-3 * s / 8]  # noqa: E731
+        res = {}
+        for on in (False, True):
+            cf.set_contact_surface(m.top_tris if on else None)
+            x, v, xp = cf.new_state(1)
+            for s in range(8):
+                st = cf.step(x, v, xp, aim, [fc.make_indenter(2, ctr2(s), (0, 0, 0), R)], [fc.make_indenter(2, ctr2(s + 1), (0, 0, 0), R)])
+                assert st[0]["converged"] == 1 and st[0]["min_dist"] > 0
+            res[on] = np.abs(x - cf.X).max()
+        assert res[False] < 2e-4 and res[True] > 7e-4, res
     finally:
-        fc.CanonFem.set_contact_surface(None)
+        cf.set_contact_surface(None)

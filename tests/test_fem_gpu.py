@@ -285,9 +285,9 @@ def test_mesh_indenter_argument_checks():
 
 @pytest.mark.parametrize("kind", [3, 2])
 def test_two_sided_vertex_face_contact_matches_cpu_restatement(kind):
-    """Mesh indenter with BOTH halves of the vertex-face contact: gel surface vertices against indenter triangles and -- through
-    tx_fem_set_contact_surface -- indenter vertices against the gel's top triangles (exact energy / gradient, Gauss-Newton Hessian,
-    ACCD with the moving triangle). A cone tip / wedge corner placed BETWEEN the gel's surface vertices (2.1 mm apart) is only seen
+    """Mesh indenter with the full simplex contact: gel surface vertices against indenter triangles and -- through
+    tx_fem_set_contact_surface -- indenter vertices against the gel's top triangles and indenter edges against the gel's surface
+    edges (mollified edge-edge barrier; exact energy / gradient, Gauss-Newton Hessian, ACCD with the moving triangle / edge). A cone tip / wedge corner placed BETWEEN the gel's surface vertices (2.1 mm apart) is only seen
     by the second half: the gel must deform as far as the tip goes, and the kernel must follow the float64 CPU restatement."""
     from tacex_b200 import fem, synth
 
@@ -296,11 +296,12 @@ def test_two_sided_vertex_face_contact_matches_cpu_restatement(kind):
     eng.set_indenter_mesh(tri)
     eng.set_contact_surface(m.top_tris)
     fc.CanonFem.set_indenter_mesh(tri)
-    fc.CanonFem.set_contact_surface(m.top_tris)
+    cf.set_contact_surface(m.top_tris)
     try:
-        N = 4
-        offs = np.array([[1.0e-3, 0.5e-3], [0.0, 0.0], [-3.1e-3, 2.6e-3], [4.2e-3, -1.0e-3]])  # env 0: centre of a surface cell
-        Rs = np.stack([_yaw(t) for t in (0.0, 0.4, 1.1, 2.0)])
+        N = 5
+        # env 0: tip over the centre of a surface cell; env 4: the wedge's edge along x BETWEEN two rows of gel vertices (edge-edge)
+        offs = np.array([[1.0e-3, 0.5e-3], [0.0, 0.0], [-3.1e-3, 2.6e-3], [4.2e-3, -1.0e-3], [1.0e-3, 1.05e-3]])
+        Rs = np.stack([_yaw(t) for t in (0.0, 0.4, 1.1, 2.0, np.pi / 2)])
         z0 = 4.5e-3 + 4e-4
 
         def ctr(s):
@@ -330,7 +331,8 @@ def test_two_sided_vertex_face_contact_matches_cpu_restatement(kind):
         assert worst <= 1e-5
         # env 0: the tip went 0.6 mm below the rest surface between four vertices -- the surface followed it
         assert float((eng.X[:, 2] - x[0, :, 2]).max()) > 4e-4
+        assert float((eng.X[:, 2] - x[4, :, 2]).max()) > 4e-4  # ... and so did the surface under the edge between two vertex rows
     finally:
-        fc.CanonFem.set_contact_surface(None)
+        cf.set_contact_surface(None)
         eng.set_contact_surface(None)
         eng.set_indenter_mesh(None)

@@ -345,3 +345,91 @@ def test_additive_ccd_matches_reference_source_on_mudas_vertex_face_fixtures(can
         assert ha == hb and abs(ta - tb) <= 1e-12 * max(abs(tb), 1e-300), (k, ta, tb)
         hits += ha
     assert 100 < hits < 500
+
+
+@pytest.mark.skipif(not REF_DIST.exists(), reason="oracle/_ref/libuipc_dist.so not built")
+def test_edge_edge_closest_points_mollifier_match_reference_source(canon):
+    """fem_ee_closest vs the reference's edge_edge_distance_flag + flagged distance / 12-gradient (all nine EE / PE / PP cases), and
+    fem_ee_mollifier vs edge_edge_mollifier / its gradient with the reference's threshold."""
+    rd = C.CDLL(str(REF_DIST))
+    canon.fem_ee_closest.restype = C.c_int
+    canon.fem_ee_mollifier.restype = C.c_double
+    IP = C.POINTER(C.c_int)
+    rng = np.random.default_rng(5)
+    seen = set()
+    for k in range(4000):
+        sc = 1e-3 if k % 2 else 1.0
+        a0, a1 = rng.standard_normal(3) * sc, rng.standard_normal(3) * sc
+        if k % 4 == 0:  # nearly parallel pairs
+            b0 = a0 + rng.standard_normal(3) * sc * 0.3
+            b1 = b0 + (a1 - a0) * rng.uniform(0.3, 1.5) + rng.standard_normal(3) * sc * (1e-4 if k % 8 else 0.05)
+        else:
+            b0, b1 = rng.standard_normal(3) * sc, rng.standard_normal(3) * sc
+        a0, a1, b0, b1 = (np.ascontiguousarray(q) for q in (a0, a1, b0, b1))
+        flag = np.zeros(4, np.int32)
+        D2, G2, H2 = C.c_double(), np.zeros(12), np.zeros(144)
+        rd.ref_ee(_d(a0), _d(a1), _d(b0), _d(b1), flag.ctypes.data_as(IP), C.byref(D2), _d(G2), _d(H2))
+        D1, r, s_, t_ = C.c_double(), np.zeros(3), C.c_double(), C.c_double()
+        F = canon.fem_ee_closest(_d(a0), _d(a1), _d(b0), _d(b1), C.byref(D1), _d(r), C.byref(s_), C.byref(t_))
+        assert F == 8 * flag[0] + 4 * flag[1] + 2 * flag[2] + flag[3], (k, F, flag)
+        seen.add(F)
+        scl = max(D2.value, 1e-300)
+        assert abs(D1.value - D2.value) <= 1e-9 * scl, (k, F, D1.value, D2.value)
+        s, t = s_.value, t_.value
+        g12 = np.concatenate([2 * (1 - s) * r, 2 * s * r, -2 * (1 - t) * r, -2 * t * r])
+        if F == 15 and np.linalg.norm(np.cross(a1 - a0, b1 - b0)) ** 2 < 1e-6 * np.dot(a1 - a0, a1 - a0) * np.dot(b1 - b0, b1 - b0):
+            continue  # interior case of nearly parallel lines: the line-line formula is ill-conditioned on both sides
+        assert np.abs(g12 - G2).max() <= 1e-7 * max(np.abs(G2).max(), np.sqrt(scl) * 1e-3), (k, F, g12, G2)
+        # mollifier (threshold from "rest" edges = the same edges here)
+        eps, e2, gm2 = C.c_double(), C.c_double(), np.zeros(12)
+        rd.ref_ee_mollifier(_d(a0), _d(a1), _d(b0), _d(b1), _d(a0), _d(a1), _d(b0), _d(b1), C.byref(eps), C.byref(e2), _d(gm2))
+        de, gc = C.c_double(), np.zeros(12)
+        e1 = canon.fem_ee_mollifier(_d(a0), _d(a1), _d(b0), _d(b1), C.c_double(eps.value), C.byref(de), _d(gc))
+        assert abs(e1 - e2.value) <= 1e-12 and np.abs(de.value * gc - gm2).max() <= 1e-9 * max(np.abs(gm2).max(), 1e-300)
+    assert len(seen) == 9, seen
+
+
+MUDA_EE = Path("/root/reference/source/tacex_uipc/libuipc/external/muda/test/data/unit-tests/edge-edge")
+
+
+@pytest.mark.skipif(not (REF_DIST.exists() and MUDA_EE.exists()), reason="needs oracle/_ref/libuipc_dist.so and the reference tree")
+def test_edge_edge_additive_ccd_matches_reference_source_on_mudas_fixtures(canon):
+    """fem_ee_accd vs the reference's edge_edge_ccd (ccd.inl) on muda's edge-edge queries (rational coordinates + ground truth) and on
+    random sweeps of a moving edge against a static one: identical hit / miss and time of impact; no true collision missed."""
+    rd = C.CDLL(str(REF_DIST))
+    canon.fem_ee_accd.restype = C.c_int
+    qs = []
+    for f in sorted(MUDA_EE.glob("*.csv")):
+        rows = np.loadtxt(f, delimiter=",", dtype=np.float64)
+        pts = np.stack([rows[:, 0] / rows[:, 1], rows[:, 2] / rows[:, 3], rows[:, 4] / rows[:, 5]], 1).reshape(-1, 8, 3)
+        qs += list(zip(pts, rows[:, 6].reshape(-1, 8)[:, 0].astype(bool)))
+    assert len(qs) == 74
+
+    def both(a0, a1, b0, b1, d0, d1, d2, d3, horizon):
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (a0, a1, b0, b1, d0, d1, d2, d3)]
+        ta, tb = C.c_double(horizon), C.c_double(horizon)
+        ha = canon.fem_ee_accd(*[_d(a) for a in arrs], C.c_double(0.1), C.c_double(0.0), 1000, C.byref(ta))
+        hb = rd.ref_ee_ccd(*[_d(a) for a in arrs], C.c_double(0.1), C.c_double(0.0), 1000, C.byref(tb))
+        return ha, ta.value, hb, tb.value
+
+    n_truth = 0
+    for q, truth in qs:
+        if np.linalg.norm(q[1] - q[0]) == 0.0 or np.linalg.norm(q[3] - q[2]) == 0.0:
+            continue  # zero-length edge: 0 / 0 in the classification on both sides
+        ha, ta, hb, tb = both(q[0], q[1], q[2], q[3], q[4] - q[0], q[5] - q[1], q[6] - q[2], q[7] - q[3], 1.0)
+        assert ha == hb and (ta == tb or abs(ta - tb) <= 1e-12 * max(abs(tb), 1e-300) or (np.isnan(ta) and np.isnan(tb))), (q, ta, tb)
+        n_truth += bool(truth)
+        if truth:
+            assert ha == 1, q
+    assert n_truth > 5
+    rng = np.random.default_rng(4)
+    z = np.zeros(3)
+    hits = 0
+    for k in range(500):
+        a0, a1, b0, b1 = (rng.standard_normal(3) * 2e-3 for _ in range(4))
+        mid = 0.5 * (b0 + b1) - 0.5 * (a0 + a1)
+        d = mid * rng.uniform(0.2, 2.5) + rng.standard_normal(3) * 5e-4
+        ha, ta, hb, tb = both(a0, a1, b0, b1, d, d + rng.standard_normal(3) * 2e-4, z, z, 1.1)
+        assert ha == hb and abs(ta - tb) <= 1e-12 * max(abs(tb), 1e-300), (k, ta, tb)
+        hits += ha
+    assert 50 < hits < 500
