@@ -591,6 +591,40 @@ __device__ __forceinline__ double pt_closest(const double* __restrict__ tr, cons
     return D;
 }
 
+// The loops over the indenter's primitives run in the INDENTER'S frame: the gel primitive of the thread is transformed once
+// (R^T (x - c)), the mesh's vertices are used as stored, and the gradients / symmetric blocks are rotated back at the end.
+__device__ __forceinline__ void to_local3(const double R[9], double3 c, double3 x, double o[3])
+{
+    const double q[3] = {x.x - c.x, x.y - c.y, x.z - c.z};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = R[0 * 3 + i] * q[0] + R[1 * 3 + i] * q[1] + R[2 * 3 + i] * q[2];
+}
+__device__ __forceinline__ void rot_dir3(const double R[9], double3 d, double o[3]) // R^T d
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = R[0 * 3 + i] * d.x + R[1 * 3 + i] * d.y + R[2 * 3 + i] * d.z;
+}
+__device__ __forceinline__ void rot_vec_back(const double R[9], double* v) // v <- R v
+{
+    const double a = v[0], b = v[1], c = v[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = R[3 * i] * a + R[3 * i + 1] * b + R[3 * i + 2] * c;
+}
+__device__ __forceinline__ void rot_sym_back(const double R[9], double* h) // symmetric 00 01 02 11 12 22 <- R H R^T
+{
+    const double Hf[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+    double T[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = R[3 * i] * Hf[j] + R[3 * i + 1] * Hf[3 + j] + R[3 * i + 2] * Hf[6 + j];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = i; j < 3; ++j, ++k) h[k] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+}
+
 struct MeshVerts { const double* vert; int nv; double d_hat; };
 // per gel triangle: k 0..8 gradient of its three vertices, 9..26 their diagonal blocks (symmetric 00 01 02 11 12 22), 27..44 the
 // blocks of the pairs (0,1) (0,2) (1,2) (multiples of r r^T: symmetric)
@@ -599,7 +633,8 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
                                            double kdt2, int derivs, TpOut* o)
 {
     const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
-    const double tr[9] = {xa.x, xa.y, xa.z, xb.x, xb.y, xb.z, xc.x, xc.y, xc.z};
+    double tr[9];
+    to_local3(R, c, xa, tr); to_local3(R, c, xb, tr + 3); to_local3(R, c, xc, tr + 6);
     double lo[3], hi[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -613,10 +648,7 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
         for (int k = 0; k < 45; ++k) o->v[k] = 0.0;
     for (int k = 0; k < mv.nv; ++k) {
         const double* l = mv.vert + 3 * k;
-        double pw[3];
-        pw[0] = c.x + R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
-        pw[1] = c.y + R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
-        pw[2] = c.z + R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+        const double pw[3] = {l[0], l[1], l[2]};
         double bd = 0.0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -652,6 +684,12 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
             }
         }
     }
+    if (derivs) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) rot_vec_back(R, o->v + 3 * j);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) rot_sym_back(R, o->v + 9 + 6 * j);
+    }
     o->E = E; o->dmin2 = best; o->bad = bad;
 }
 
@@ -660,8 +698,9 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
                                            double3 da, double3 db, double3 dc)
 {
     const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
-    const double t0[9] = {xa.x, xa.y, xa.z, xb.x, xb.y, xb.z, xc.x, xc.y, xc.z};
-    const double d0[9] = {da.x, da.y, da.z, db.x, db.y, db.z, dc.x, dc.y, dc.z};
+    double t0[9], d0[9];
+    to_local3(R, c, xa, t0); to_local3(R, c, xb, t0 + 3); to_local3(R, c, xc, t0 + 6);
+    rot_dir3(R, da, d0); rot_dir3(R, db, d0 + 3); rot_dir3(R, dc, d0 + 6);
     double lo[3], hi[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -677,10 +716,7 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
     double alpha = 1.0;
     for (int k = 0; k < mv.nv; ++k) {
         const double* l = mv.vert + 3 * k;
-        double p[3];
-        p[0] = c.x + R[0] * l[0] + R[1] * l[1] + R[2] * l[2];
-        p[1] = c.y + R[3] * l[0] + R[4] * l[1] + R[5] * l[2];
-        p[2] = c.z + R[6] * l[0] + R[7] * l[1] + R[8] * l[2];
+        double p[3] = {l[0], l[1], l[2]};
         bool far = false;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -797,7 +833,8 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
                                            double kdt2, int derivs, EeOut* o)
 {
     const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
-    const double a0[3] = {xa.x, xa.y, xa.z}, a1[3] = {xb.x, xb.y, xb.z};
+    double a0[3], a1[3];
+    to_local3(R, c, xa, a0); to_local3(R, c, xb, a1);
     const double D0 = me.d_hat * me.d_hat;
     double E = 0.0, best = 1e300;
     int bad = 0;
@@ -806,13 +843,7 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
     for (int q = 0; q < me.ne; ++q) {
         const double* l0 = me.vert + 3 * me.edge[2 * q];
         const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
-        double b0[3], b1[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double cc = i == 0 ? c.x : (i == 1 ? c.y : c.z);
-            b0[i] = cc + R[3 * i] * l0[0] + R[3 * i + 1] * l0[1] + R[3 * i + 2] * l0[2];
-            b1[i] = cc + R[3 * i] * l1[0] + R[3 * i + 1] * l1[1] + R[3 * i + 2] * l1[2];
-        }
+        double b0[3] = {l0[0], l0[1], l0[2]}, b1[3] = {l1[0], l1[1], l1[2]};
         double bd = 0.0, vv = 0.0;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -861,6 +892,10 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
             }
         }
     }
+    if (derivs) {
+        rot_vec_back(R, o->v); rot_vec_back(R, o->v + 3);
+        rot_sym_back(R, o->v + 6); rot_sym_back(R, o->v + 12); rot_sym_back(R, o->v + 18);
+    }
     o->E = E; o->dmin2 = best; o->bad = bad;
 }
 
@@ -887,7 +922,9 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
                                            double3 db)
 {
     const double R[9] = {r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z};
-    const double A0[3] = {xa.x, xa.y, xa.z}, A1[3] = {xb.x, xb.y, xb.z}, dA0[3] = {da.x, da.y, da.z}, dA1[3] = {db.x, db.y, db.z};
+    double A0[3], A1[3], dA0[3], dA1[3];
+    to_local3(R, c, xa, A0); to_local3(R, c, xb, A1);
+    rot_dir3(R, da, dA0); rot_dir3(R, db, dA1);
     double lo[3], hi[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -900,13 +937,7 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
     for (int q = 0; q < me.ne; ++q) {
         const double* l0 = me.vert + 3 * me.edge[2 * q];
         const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
-        double b0[3], b1[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const double cc = i == 0 ? c.x : (i == 1 ? c.y : c.z);
-            b0[i] = cc + R[3 * i] * l0[0] + R[3 * i + 1] * l0[1] + R[3 * i + 2] * l0[2];
-            b1[i] = cc + R[3 * i] * l1[0] + R[3 * i + 1] * l1[1] + R[3 * i + 2] * l1[2];
-        }
+        double b0[3] = {l0[0], l0[1], l0[2]}, b1[3] = {l1[0], l1[1], l1[2]};
         bool far = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k)
