@@ -242,6 +242,9 @@ void fem_set_indenter_mesh(const double* tri, int n)
     mesh_unique_vertices();
 }
 
+/* search radius of the mesh contact: distances are exact below it and reported as the radius beyond (candidates farther than
+   4 d_hat can neither carry a barrier nor limit a step of the sizes the solver takes); set by fem_step from the config */
+static double g_mesh_cap2 = 1e300;
 static double* g_mesh_vert = 0; /* [nv][3] unique vertices of the indenter mesh (local frame) */
 static int g_mesh_nv = 0;
 static int32_t* g_ctri = 0;     /* [n][3] triangles of the gel's contact surface (vertex ids) */
@@ -428,7 +431,7 @@ static void to_local(const fem_indenter* I, const double* x, double* p)
    best distance so far are skipped (the "broad phase" of a few hundred static triangles) */
 static void mesh_nearest(const fem_indenter* I, const double* x, double* d, double* n)
 {
-    double p[3], best = 1e300, gb[3] = {0, 0, 1};
+    double p[3], best = g_mesh_cap2, gb[3] = {0, 0, 1};
     to_local(I, x, p);
     for (int t = 0; t < g_mesh_n; ++t) {
         if (!(box_dist2(g_mesh_box + 6 * t, p) < best)) continue;
@@ -793,9 +796,9 @@ static void mesh_vertex_world(const fem_indenter* I, int k, double* pw)
  * outputs optional. Returns the energy (INFINITY when a vertex touches a triangle). */
 static double tp_terms(const fem_cfg* g, const fem_indenter* I, const double* x, double* G, double* Dg, fem_tp* tp, double* dmin)
 {
-    double E = 0.0, best = 1e300;
+    double E = 0.0, best = g_mesh_cap2;
     const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
-    if (I->type != 2 || g_nctri == 0) { if (dmin) *dmin = 1e150; return 0.0; }
+    if (I->type != 2 || g_nctri == 0) { if (dmin) *dmin = sqrt(g_mesh_cap2); return 0.0; }
     for (int f = 0; f < g_nctri; ++f) {
         const int32_t* tv = g_ctri + 3 * f;
         const double *xa = x + 3 * tv[0], *xb = x + 3 * tv[1], *xc = x + 3 * tv[2];
@@ -841,9 +844,9 @@ static double tp_terms(const fem_cfg* g, const fem_indenter* I, const double* x,
  * gel edge's two vertices, Gauss-Newton Hessian e_k max(0, B'' + B' / (2 D)) gD gD^T (mollifier curvature dropped). */
 static double ee_terms(const fem_cfg* g, const fem_indenter* I, const double* x, double* G, double* Dg, fem_tp* tp, double* dmin)
 {
-    double E = 0.0, best = 1e300;
+    double E = 0.0, best = g_mesh_cap2;
     const double D0 = g->d_hat * g->d_hat, kdt2 = g->kappa * g->dt * g->dt;
-    if (I->type != 2 || g_ncedge == 0) { if (dmin) *dmin = 1e150; return 0.0; }
+    if (I->type != 2 || g_ncedge == 0) { if (dmin) *dmin = sqrt(g_mesh_cap2); return 0.0; }
     for (int ce = 0; ce < g_ncedge; ++ce) {
         const int32_t vid[3] = {g_cedge[2 * ce], g_cedge[2 * ce + 1], -1};
         const double *a0 = x + 3 * vid[0], *a1 = x + 3 * vid[1];
@@ -1355,6 +1358,7 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     fem_tp tpl;
     memset(&tpl, 0, sizeof(tpl));
     c.tp = &tpl;
+    g_mesh_cap2 = 16.0 * g->d_hat * g->d_hat; /* the same value from every thread of fem_step_batch */
     memset(st, 0, sizeof(*st));
 
     /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */

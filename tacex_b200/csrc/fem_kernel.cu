@@ -451,7 +451,9 @@ __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0,
 #pragma unroll
     for (int i = 0; i < 3; ++i) p[i] = R[0 * 3 + i] * q[0] + R[1 * 3 + i] * q[1] + R[2 * 3 + i] * q[2];
     const double D0 = m.d_hat * m.d_hat, Dcull = kdt2 > 0.0 ? D0 : 0.0;
-    double best = 1e300, gb[3] = {0.0, 0.0, 1.0};
+    // search radius 4 d_hat: distances are exact below it and reported as the radius beyond (a candidate farther away can neither
+    // carry a barrier nor limit a step of the sizes the solver takes), so far gel primitives skip every distance evaluation
+    double best = 16.0 * D0, gb[3] = {0.0, 0.0, 1.0};
     double Es = 0.0, Gl[3] = {0.0, 0.0, 0.0}, Hl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     bool active = false;
     for (int t = 0; t < m.n; ++t) {
@@ -642,7 +644,7 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
         hi[a] = fmax(tr[a], fmax(tr[3 + a], tr[6 + a]));
     }
     const double D0 = mv.d_hat * mv.d_hat;
-    double E = 0.0, best = 1e300;
+    double E = 0.0, best = 16.0 * D0;
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 45; ++k) o->v[k] = 0.0;
@@ -836,7 +838,7 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
     double a0[3], a1[3];
     to_local3(R, c, xa, a0); to_local3(R, c, xb, a1);
     const double D0 = me.d_hat * me.d_hat;
-    double E = 0.0, best = 1e300;
+    double E = 0.0, best = 16.0 * D0;
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 24; ++k) o->v[k] = 0.0;

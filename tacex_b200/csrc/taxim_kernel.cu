@@ -730,7 +730,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) taxim_f
 #ifdef TX_NO_COLOUR_BALANCE
     const int g_begin = q ? nblk0 : 0, g_end = q ? nblk_all : nblk0; // every CTA its own half (A/B reference)
 #else
-    const int g_split = (nblk_all + 1) >> 1;
+    // even split, optionally biased towards the CTA that owns the blocks (debug flags bits 8..11 = bias in sixteenths: the CTA that
+    // takes blocks of its peer also has the larger flat-copy remainder and pays the DSMEM reads)
+    const int g_half = (nblk_all + 1) >> 1;
+    const int g_split = g_half + (((nblk0 - g_half) * (int)((p.dbg >> 8) & 15)) >> 4);
     const int g_begin = q ? g_split : 0, g_end = q ? nblk_all : g_split;
 #endif
     const float inv_nbr = nbr > 0 ? 1.0f / (float)nbr : 0.0f;

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_fem_gpu.py -m gpu -x -q -s > gpurun_out/r02ah_fem_pytest.log 2>&1; tail -8 gpurun_out/r02ah_fem_pytest.log
+TX_TP=1 timeout 300 python tools/fem_time.py 4096 12 3 > gpurun_out/r02ah_fem_time_cone_full.log 2>&1; tail -3 gpurun_out/r02ah_fem_time_cone_full.log
+TX_TP=1 timeout 300 python tools/fem_time.py 4096 12 2 > gpurun_out/r02ah_fem_time_wedge_full.log 2>&1; tail -3 gpurun_out/r02ah_fem_time_wedge_full.log
+timeout 300 python tools/fem_time.py 4096 12 3 2>&1 | tail -1
+timeout 300 python tools/fem_time.py 4096 6 2>&1 | tail -1
