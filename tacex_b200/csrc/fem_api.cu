@@ -3,6 +3,7 @@
 #include <new>
 #include <string>
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <vector>
@@ -43,6 +44,8 @@ struct tx_fem {
     std::map<std::pair<int, int>, int> edge_of; // (i, j), i < j -> edge number (tx_fem_create)
     std::vector<double> h_X;                    // rest positions (mollifier threshold of the edge-edge candidates)
     int n_cedge = 0, mesh_ne = 0;
+    MeshGrid mgrid[3] = {};     // broad phase over the mesh's triangles / vertices / edges (device pointers inside)
+    int* d_grid_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int *d_cedge = nullptr, *d_cedge_row_start = nullptr, *d_cedge_row_adj = nullptr, *d_edge_cedge = nullptr, *d_mesh_edge = nullptr;
     double* d_cedge_len2 = nullptr;
 };
@@ -268,6 +271,7 @@ extern "C" void tx_fem_destroy(tx_fem* f)
     cudaFree(f->d_mass); cudaFree(f->d_X); cudaFree(f->d_tsc); cudaFree(f->d_valg); cudaFree(f->d_xt); cudaFree(f->d_edge_off); cudaFree(f->d_edge_adj);
     cudaFree(f->d_ell); cudaFree(f->d_attach_of); cudaFree(f->d_surf_of); cudaFree(f->d_adj_off); cudaFree(f->d_adj);
     cudaFree(f->d_tri); cudaFree(f->d_w); cudaFree(f->d_top); cudaFree(f->d_mesh_tri); cudaFree(f->d_mesh_box); cudaFree(f->d_mesh_vert);
+    for (int* g : f->d_grid_buf) cudaFree(g);
     cudaFree(f->d_ctri); cudaFree(f->d_ctri_row_start); cudaFree(f->d_ctri_row_adj); cudaFree(f->d_ctri_edge_start); cudaFree(f->d_ctri_edge_adj);
     cudaFree(f->d_cedge); cudaFree(f->d_cedge_row_start); cudaFree(f->d_cedge_row_adj); cudaFree(f->d_edge_cedge); cudaFree(f->d_mesh_edge); cudaFree(f->d_cedge_len2);
     delete f;
@@ -306,6 +310,7 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     a.cedge = f->d_cedge; a.cedge_len2 = f->d_cedge_len2; a.n_cedge = f->mesh_n > 0 ? f->n_cedge : 0;
     a.cedge_row_start = f->d_cedge_row_start; a.cedge_row_adj = f->d_cedge_row_adj; a.edge_cedge = f->d_edge_cedge;
     a.mesh_edge = f->d_mesh_edge; a.mesh_ne = f->mesh_ne;
+    a.grid_tri = f->mgrid[0]; a.grid_vert = f->mgrid[1]; a.grid_edge = f->mgrid[2];
     a.dbg_cycles = f->d_cycles;
     a.dbg_mode = getenv("TX_FEM_DBG_MODE") ? atoi(getenv("TX_FEM_DBG_MODE")) : 0;
     a.row_start = f->d_adj_off;
@@ -319,6 +324,53 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
     const int grid = N < f->grid ? N : f->grid;
     FEM_CUDA(f, launch_fem_step(a, grid, f->stream));
     return TX_OK;
+}
+
+// Uniform grid over reference points `ref` [n][3] (see MeshGrid in tx_kernels.h): every primitive in the cell of its reference point,
+// ids ascending within a cell. Up to 64 primitives: one cell (the brute-force loop). Cell size ~ the search radius 4 d_hat.
+static cudaError_t build_mesh_grid(const std::vector<double>& ref, double rmax, double d_hat, MeshGrid& G, int*& d_start, int*& d_ids)
+{
+    const int n = (int)(ref.size() / 3);
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = 1e300; hi[a] = -1e300;
+        for (int i = 0; i < n; ++i) { lo[a] = std::min(lo[a], ref[3 * i + a]); hi[a] = std::max(hi[a], ref[3 * i + a]); }
+        if (n == 0) lo[a] = hi[a] = 0.0;
+    }
+    int dims[3] = {1, 1, 1};
+    if (n > 64)
+        for (int a = 0; a < 3; ++a) {
+            const double ext = hi[a] - lo[a];
+            dims[a] = ext > 0.0 ? std::max(1, std::min(16, (int)(ext / (4.0 * d_hat)))) : 1;
+        }
+    G.nx = dims[0]; G.ny = dims[1]; G.nz = dims[2];
+    G.rmax = rmax;
+    for (int a = 0; a < 3; ++a) {
+        G.lo[a] = lo[a];
+        G.inv[a] = (dims[a] > 1) ? dims[a] / (hi[a] - lo[a]) : 0.0;
+    }
+    const int nc = dims[0] * dims[1] * dims[2];
+    std::vector<int> start(nc + 1, 0), ids(std::max(n, 1)), cell(n);
+    for (int i = 0; i < n; ++i) {
+        int c[3];
+        for (int a = 0; a < 3; ++a) {
+            int k = (int)std::floor((ref[3 * i + a] - G.lo[a]) * G.inv[a]);
+            c[a] = k < 0 ? 0 : (k >= dims[a] ? dims[a] - 1 : k);
+        }
+        cell[i] = (c[2] * dims[1] + c[1]) * dims[0] + c[0];
+        start[cell[i] + 1]++;
+    }
+    for (int k = 0; k < nc; ++k) start[k + 1] += start[k];
+    std::vector<int> cur(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) ids[cur[cell[i]]++] = i;
+    cudaFree(d_start); cudaFree(d_ids);
+    d_start = d_ids = nullptr;
+    cudaError_t e = cudaMalloc(&d_start, sizeof(int) * start.size());
+    if (e == cudaSuccess) e = cudaMalloc(&d_ids, sizeof(int) * ids.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice);
+    G.start = d_start; G.ids = d_ids;
+    return e;
 }
 
 extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri_local)
@@ -384,6 +436,27 @@ extern "C" int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri
         FEM_CUDA(f, cudaMalloc(&f->d_mesh_edge, sizeof(int) * std::max<size_t>(me.size(), 1)));
         FEM_CUDA(f, cudaMemcpy(f->d_mesh_edge, me.data(), sizeof(int) * me.size(), cudaMemcpyHostToDevice));
         f->mesh_ne = (int)(me.size() / 2);
+        // broad phase: reference points + largest reach of a primitive from its reference point
+        std::vector<double> rt((size_t)3 * n_tris), re((size_t)3 * f->mesh_ne);
+        double rmax_t = 0.0, rmax_e = 0.0;
+        for (int t = 0; t < n_tris; ++t) {
+            const double* tr = tri_local + (size_t)9 * t;
+            for (int a = 0; a < 3; ++a) rt[3 * t + a] = (tr[a] + tr[3 + a] + tr[6 + a]) / 3.0;
+            for (int k = 0; k < 3; ++k) {
+                double d2 = 0.0;
+                for (int a = 0; a < 3; ++a) d2 += (tr[3 * k + a] - rt[3 * t + a]) * (tr[3 * k + a] - rt[3 * t + a]);
+                rmax_t = std::max(rmax_t, std::sqrt(d2));
+            }
+        }
+        for (int q = 0; q < f->mesh_ne; ++q) {
+            const double *v0 = &vert[3 * me[2 * q]], *v1 = &vert[3 * me[2 * q + 1]];
+            double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) { re[3 * q + a] = 0.5 * (v0[a] + v1[a]); d2 += (v1[a] - v0[a]) * (v1[a] - v0[a]); }
+            rmax_e = std::max(rmax_e, 0.5 * std::sqrt(d2));
+        }
+        FEM_CUDA(f, build_mesh_grid(rt, rmax_t, f->cfg.d_hat, f->mgrid[0], f->d_grid_buf[0], f->d_grid_buf[1]));
+        FEM_CUDA(f, build_mesh_grid(vert, 0.0, f->cfg.d_hat, f->mgrid[1], f->d_grid_buf[2], f->d_grid_buf[3]));
+        FEM_CUDA(f, build_mesh_grid(re, rmax_e, f->cfg.d_hat, f->mgrid[2], f->d_grid_buf[4], f->d_grid_buf[5]));
     }
     f->mesh_n = n_tris;
     return TX_OK;

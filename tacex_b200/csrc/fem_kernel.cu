@@ -441,7 +441,29 @@ __device__ __forceinline__ double pt_distance2(const double* __restrict__ tr, co
 // candidate is active. E / G / H6 are ACCUMULATED into.
 // Out-of-line, and every input BY VALUE: a reference to the kernel's parameter struct or to an indenter held in registers would force
 // both onto the local-memory stack of the (register-tight) step kernel for all indenter kinds.
-struct MeshRef { const double* tri; const double* box; int n; double d_hat; };
+// visits the primitives of the cells overlapped by the box [qlo, qhi] inflated by infl + rmax
+template <class F>
+__device__ __forceinline__ void grid_for(const MeshGrid& G, const double qlo[3], const double qhi[3], double infl, F&& body)
+{
+    int c0[3], c1[3];
+    const int dims[3] = {G.nx, G.ny, G.nz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double e = infl + G.rmax;
+        const int i0 = (int)floor((qlo[a] - e - G.lo[a]) * G.inv[a]), i1 = (int)floor((qhi[a] + e - G.lo[a]) * G.inv[a]);
+        if (i1 < 0 || i0 >= dims[a]) return;
+        c0[a] = i0 < 0 ? 0 : i0;
+        c1[a] = i1 >= dims[a] ? dims[a] - 1 : i1;
+    }
+    for (int cz = c0[2]; cz <= c1[2]; ++cz)
+        for (int cy = c0[1]; cy <= c1[1]; ++cy)
+            for (int cx = c0[0]; cx <= c1[0]; ++cx) {
+                const int cell = (cz * G.ny + cy) * G.nx + cx;
+                for (int q = G.start[cell]; q < G.start[cell + 1]; ++q) body(G.ids[q]);
+            }
+}
+
+struct MeshRef { const double* tri; const double* box; int n; double d_hat; MeshGrid grid; };
 struct MeshOut { double d, n[3], E, G[3], H6[6]; };
 __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0, double3 r1, double3 r2, double3 xw, double kdt2, MeshOut* o)
 {
@@ -456,7 +478,7 @@ __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0,
     double best = 16.0 * D0, gb[3] = {0.0, 0.0, 1.0};
     double Es = 0.0, Gl[3] = {0.0, 0.0, 0.0}, Hl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     bool active = false;
-    for (int t = 0; t < m.n; ++t) {
+    grid_for(m.grid, p, p, 4.0 * m.d_hat, [&](int t) {
         const double* bx = m.box + 6 * t;
         double bd = 0.0;
 #pragma unroll
@@ -465,7 +487,7 @@ __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0,
             const double dd = p[c] < lo ? lo - p[c] : (p[c] > hi ? p[c] - hi : 0.0);
             bd += dd * dd;
         }
-        if (!(bd < best) && !(bd < Dcull)) continue;
+        if (!(bd < best) && !(bd < Dcull)) return;
         double g[3];
         const double D = pt_distance2(m.tri + 9 * t, p, g);
         if (D < best) { best = D; gb[0] = g[0]; gb[1] = g[1]; gb[2] = g[2]; }
@@ -481,7 +503,7 @@ __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0,
                 Hl[3] += w * g[1] * g[1]; Hl[4] += w * g[1] * g[2]; Hl[5] += w * g[2] * g[2];
             }
         }
-    }
+    });
     o->d = sqrt(best);
     {
         const double l = sqrt(gb[0] * gb[0] + gb[1] * gb[1] + gb[2] * gb[2]);
@@ -514,7 +536,7 @@ __device__ __forceinline__ bool mesh_contact(const FemArgs& a, const FemIndenter
                                              double* E, double* G, double* H6)
 {
     MeshOut o;
-    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat};
+    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat, a.grid_tri};
     const bool active = mesh_contact_impl(m, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]),
                                           make_double3(I.R[3], I.R[4], I.R[5]), make_double3(I.R[6], I.R[7], I.R[8]),
                                           make_double3(x[0], x[1], x[2]), kdt2, &o);
@@ -627,7 +649,7 @@ __device__ __forceinline__ void rot_sym_back(const double R[9], double* h) // sy
         for (int j = i; j < 3; ++j, ++k) h[k] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
 }
 
-struct MeshVerts { const double* vert; int nv; double d_hat; };
+struct MeshVerts { const double* vert; int nv; double d_hat; MeshGrid grid; };
 // per gel triangle: k 0..8 gradient of its three vertices, 9..26 their diagonal blocks (symmetric 00 01 02 11 12 22), 27..44 the
 // blocks of the pairs (0,1) (0,2) (1,2) (multiples of r r^T: symmetric)
 struct TpOut { double E, dmin2, v[45]; int bad; };
@@ -648,7 +670,7 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 45; ++k) o->v[k] = 0.0;
-    for (int k = 0; k < mv.nv; ++k) {
+    grid_for(mv.grid, lo, hi, 4.0 * mv.d_hat, [&](int k) {
         const double* l = mv.vert + 3 * k;
         const double pw[3] = {l[0], l[1], l[2]};
         double bd = 0.0;
@@ -657,12 +679,12 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
             const double dd = pw[a] < lo[a] ? lo[a] - pw[a] : (pw[a] > hi[a] ? pw[a] - hi[a] : 0.0);
             bd += dd * dd;
         }
-        if (!(bd < best) && !(bd < D0)) continue;
+        if (!(bd < best) && !(bd < D0)) return;
         double r[3], w[3];
         const double D = pt_closest(tr, pw, r, w);
         if (D < best) best = D;
-        if (!(D < D0)) continue;
-        if (!(D > 0.0)) { bad = 1; continue; }
+        if (!(D < D0)) return;
+        if (!(D > 0.0)) { bad = 1; return; }
         double B, dB, ddB;
         barrier_fn(D, mv.d_hat, kdt2, &B, &dB, &ddB);
         E += B;
@@ -685,7 +707,7 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
                 o->v[39 + q] += p12 * rr[q];
             }
         }
-    }
+    });
     if (derivs) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) rot_vec_back(R, o->v + 3 * j);
@@ -716,14 +738,14 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
     }
     const double eta = 0.1;
     double alpha = 1.0;
-    for (int k = 0; k < mv.nv; ++k) {
+    grid_for(mv.grid, lo, hi, mv.d_hat, [&](int k) {
         const double* l = mv.vert + 3 * k;
         double p[3] = {l[0], l[1], l[2]};
         bool far = false;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             if (p[a] - hi[a] > mv.d_hat || lo[a] - p[a] > mv.d_hat) far = true;
-        if (far) continue;
+        if (far) return;
         double tr[9], dt[9], dp[3];
         double mm = 0.0;
 #pragma unroll
@@ -737,7 +759,7 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
 #pragma unroll
         for (int q = 0; q < 9; ++q) tr[q] = t0[q];
         const double L = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) + sqrt(mm);
-        if (L <= 0.0) continue;
+        if (L <= 0.0) return;
         double g[3];
         double d2 = pt_distance2(tr, p, g), d = sqrt(d2);
         const double gap = eta * d2 / d, toc_prev = 1.1;
@@ -757,7 +779,7 @@ __device__ __noinline__ double tp_ccd_impl(MeshVerts mv, double3 c, double3 r0, 
             if (toc > toc_prev) { hit = false; break; }
         }
         if (hit && toc < alpha) alpha = toc;
-    }
+    });
     return alpha;
 }
 
@@ -828,7 +850,7 @@ __device__ __forceinline__ int ee_closest(const double a0[3], const double a1[3]
     return F;
 }
 
-struct MeshEdges { const double* vert; const int* edge; int ne; double d_hat; };
+struct MeshEdges { const double* vert; const int* edge; int ne; double d_hat; MeshGrid grid; };
 // per gel contact edge: k 0..5 gradient of its two vertices, 6..17 their diagonal blocks (symmetric), 18..23 the pair block
 struct EeOut { double E, dmin2, v[24]; int bad; };
 __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, double3 r1, double3 r2, double3 xa, double3 xb, double len2,
@@ -842,7 +864,10 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 24; ++k) o->v[k] = 0.0;
-    for (int q = 0; q < me.ne; ++q) {
+    double elo[3], ehi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { elo[k] = fmin(a0[k], a1[k]); ehi[k] = fmax(a0[k], a1[k]); }
+    grid_for(me.grid, elo, ehi, 4.0 * me.d_hat, [&](int q) {
         const double* l0 = me.vert + 3 * me.edge[2 * q];
         const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
         double b0[3] = {l0[0], l0[1], l0[2]}, b1[3] = {l1[0], l1[1], l1[2]};
@@ -854,12 +879,12 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
             bd += gap * gap;
             vv += (b1[k] - b0[k]) * (b1[k] - b0[k]);
         }
-        if (!(bd < best) && !(bd < D0)) continue;
+        if (!(bd < best) && !(bd < D0)) return;
         double D, r[3], s_, t_;
         const int F = ee_closest(a0, a1, b0, b1, D, r, s_, t_);
         if (D < best) best = D;
-        if (!(D < D0)) continue;
-        if (!(D > 0.0)) { bad = 1; continue; }
+        if (!(D < D0)) return;
+        if (!(D > 0.0)) { bad = 1; return; }
         double B, dB, ddB;
         barrier_fn(D, me.d_hat, kdt2, &B, &dB, &ddB);
         double ek = 1.0, dek = 0.0, du[3] = {0.0, 0.0, 0.0};
@@ -893,7 +918,7 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
                 o->v[18 + k] += wp * g0 * g1 * rr[k];
             }
         }
-    }
+    });
     if (derivs) {
         rot_vec_back(R, o->v); rot_vec_back(R, o->v + 3);
         rot_sym_back(R, o->v + 6); rot_sym_back(R, o->v + 12); rot_sym_back(R, o->v + 18);
@@ -936,7 +961,7 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
     }
     const double eta = 0.1;
     double alpha = 1.0;
-    for (int q = 0; q < me.ne; ++q) {
+    grid_for(me.grid, lo, hi, me.d_hat, [&](int q) {
         const double* l0 = me.vert + 3 * me.edge[2 * q];
         const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
         double b0[3] = {l0[0], l0[1], l0[2]}, b1[3] = {l1[0], l1[1], l1[2]};
@@ -944,7 +969,7 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
 #pragma unroll
         for (int k = 0; k < 3; ++k)
             if (fmin(b0[k], b1[k]) - hi[k] > me.d_hat || lo[k] - fmax(b0[k], b1[k]) > me.d_hat) far = true;
-        if (far) continue;
+        if (far) return;
         double a0[3], a1[3], da0[3], da1[3], db0[3], db1[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -955,7 +980,7 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
         const double na0 = da0[0] * da0[0] + da0[1] * da0[1] + da0[2] * da0[2], na1 = da1[0] * da1[0] + da1[1] * da1[1] + da1[2] * da1[2],
                      nb0 = db0[0] * db0[0] + db0[1] * db0[1] + db0[2] * db0[2], nb1 = db1[0] * db1[0] + db1[1] * db1[1] + db1[2] * db1[2];
         const double L = sqrt(na0 > na1 ? na0 : na1) + sqrt(nb0 > nb1 ? nb0 : nb1);
-        if (L == 0.0) continue;
+        if (L == 0.0) return;
         double d2 = ee_dist2_ccd(a0, a1, b0, b1), d = sqrt(d2);
         const double gap = eta * d2 / d, toc_prev = 1.1;
         double toc = 0.0;
@@ -972,12 +997,12 @@ __device__ __noinline__ double ee_ccd_impl(MeshEdges me, double3 c, double3 r0, 
             if (toc > toc_prev) { hit = false; break; }
         }
         if (hit && toc < alpha) alpha = toc;
-    }
+    });
     return alpha;
 }
 __device__ __forceinline__ void ee_terms(const FemArgs& a, const FemIndenter& I, const double* xs, int ce, double kdt2, int derivs, EeOut* o)
 {
-    const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat};
+    const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat, a.grid_edge};
     const int i0 = a.cedge[2 * ce], i1 = a.cedge[2 * ce + 1];
     ee_terms_impl(me, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
                   make_double3(I.R[6], I.R[7], I.R[8]), make_double3(xs[3 * i0], xs[3 * i0 + 1], xs[3 * i0 + 2]),
@@ -986,7 +1011,7 @@ __device__ __forceinline__ void ee_terms(const FemArgs& a, const FemIndenter& I,
 
 __device__ __forceinline__ void tp_terms(const FemArgs& a, const FemIndenter& I, const double* xs, int f, double kdt2, int derivs, TpOut* o)
 {
-    const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat};
+    const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat, a.grid_vert};
     const int i0 = a.ctri[3 * f], i1 = a.ctri[3 * f + 1], i2 = a.ctri[3 * f + 2];
     tp_terms_impl(mv, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
                   make_double3(I.R[6], I.R[7], I.R[8]), make_double3(xs[3 * i0], xs[3 * i0 + 1], xs[3 * i0 + 2]),
@@ -1011,7 +1036,10 @@ __device__ __noinline__ double mesh_ccd_impl(MeshRef m, double3 c, double3 r0, d
     }
     const double eta = 0.1;
     double alpha = 1.0;
-    for (int t = 0; t < m.n; ++t) {
+    double slo[3], shi[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { slo[a] = dp0[a] < 0 ? p0[a] + dp0[a] : p0[a]; shi[a] = dp0[a] < 0 ? p0[a] : p0[a] + dp0[a]; }
+    grid_for(m.grid, slo, shi, m.d_hat, [&](int t) {
         const double* bx = m.box + 6 * t;
         bool far = false;
 #pragma unroll
@@ -1019,7 +1047,7 @@ __device__ __noinline__ double mesh_ccd_impl(MeshRef m, double3 c, double3 r0, d
             const double lo = dp0[a] < 0 ? p0[a] + dp0[a] : p0[a], hi = dp0[a] < 0 ? p0[a] : p0[a] + dp0[a];
             if (lo - bx[3 + a] > m.d_hat || bx[a] - hi > m.d_hat) far = true;
         }
-        if (far) continue;
+        if (far) return;
         double p[3], tr[9], dp[3], dt[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -1032,7 +1060,7 @@ __device__ __noinline__ double mesh_ccd_impl(MeshRef m, double3 c, double3 r0, d
         for (int k = 0; k < 9; ++k) tr[k] = m.tri[9 * t + k];
         const double mm = dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2];
         const double L = sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) + sqrt(mm);
-        if (L <= 0.0) continue;
+        if (L <= 0.0) return;
         double g[3];
         double d2 = pt_distance2(tr, p, g), d = sqrt(d2);
         const double gap = eta * d2 / d, toc_prev = 1.1;
@@ -1053,12 +1081,12 @@ __device__ __noinline__ double mesh_ccd_impl(MeshRef m, double3 c, double3 r0, d
             if (toc > toc_prev) { hit = false; break; }
         }
         if (hit && toc < alpha) alpha = toc;
-    }
+    });
     return alpha;
 }
 __device__ __forceinline__ double mesh_ccd(const FemArgs& a, const FemIndenter& I, const double* x0, const double* dx)
 {
-    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat};
+    const MeshRef m{a.mesh_tri, a.mesh_box, a.mesh_n, a.d_hat, a.grid_tri};
     return mesh_ccd_impl(m, make_double3(I.c[0], I.c[1], I.c[2]), make_double3(I.R[0], I.R[1], I.R[2]), make_double3(I.R[3], I.R[4], I.R[5]),
                          make_double3(I.R[6], I.R[7], I.R[8]), make_double3(x0[0], x0[1], x0[2]), make_double3(dx[0], dx[1], dx[2]));
 }
@@ -1776,7 +1804,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                     if (on) { s.p[3 * i] = dx[0]; s.p[3 * i + 1] = dx[1]; s.p[3 * i + 2] = dx[2]; }
                     __syncthreads();
                     if (threadIdx.x < a.n_ctri) {
-                        const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat};
+                        const MeshVerts mv{a.mesh_vert, a.mesh_nv, a.d_hat, a.grid_vert};
                         const int f = threadIdx.x, i0 = a.ctri[3 * f], i1 = a.ctri[3 * f + 1], i2 = a.ctri[3 * f + 2];
                         const double at = tp_ccd_impl(
                             mv, make_double3(ind.c[0], ind.c[1], ind.c[2]), make_double3(ind.R[0], ind.R[1], ind.R[2]),
@@ -1787,7 +1815,7 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
                         alpha = fmin(alpha, at);
                     }
                     if (threadIdx.x < a.n_cedge) {
-                        const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat};
+                        const MeshEdges me{a.mesh_vert, a.mesh_edge, a.mesh_ne, a.d_hat, a.grid_edge};
                         const int i0 = a.cedge[2 * threadIdx.x], i1 = a.cedge[2 * threadIdx.x + 1];
                         const double ae = ee_ccd_impl(
                             me, make_double3(ind.c[0], ind.c[1], ind.c[2]), make_double3(ind.R[0], ind.R[1], ind.R[2]),

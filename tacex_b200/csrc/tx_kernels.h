@@ -162,6 +162,18 @@ cudaError_t launch_resize_aa(const ResizeArgs& a, int N, cudaStream_t s);
 typedef tx_fem_indenter FemIndenter;
 typedef tx_fem_stats FemStats;
 
+// Broad phase of the mesh indenter: a uniform grid in the INDENTER'S frame, built once on the host (the soup is rigid, so nothing is
+// rebuilt per step as the reference's LBVH is). Every primitive (triangle / vertex / edge) is listed in exactly ONE cell, that of its
+// reference point (centroid / position / mid-point); a query visits the cells its box -- inflated by the search radius and by rmax,
+// the largest distance of a primitive's points from its reference point -- overlaps. A 1 x 1 x 1 grid is the brute-force loop.
+struct MeshGrid {
+    const int* start; // [nx * ny * nz + 1]
+    const int* ids;   // primitive ids, ascending within a cell
+    int nx, ny, nz;
+    double lo[3], inv[3]; // cell = floor((x - lo) * inv), clamped
+    double rmax;
+};
+
 struct FemArgs {
     int N, V, T, A, S;
     const int* tets;       // [T][4]
@@ -207,6 +219,7 @@ struct FemArgs {
     const int* edge_cedge;     // [nE] mesh edge -> contact edge or -1
     const int* mesh_edge;      // [mesh_ne][2] ids into mesh_vert
     int mesh_ne;
+    MeshGrid grid_tri, grid_vert, grid_edge; // broad phase over the mesh's triangles / unique vertices / unique edges
     int dbg_mode;          // 0: cycles[3..5] = assembly sub-phases, 1: cycles[3] = SpMV, cycles[4] = rest of the PCG iteration
     long long* dbg_cycles; // optional [grid][6] phase cycle counters (grad_hess, pcg, line search, tets, vertices, edges)
     double dt, gravity[3], mu, lambda, attach_strength, d_hat, kappa, velocity_tol, pcg_tol_rate, friction_mu, eps_velocity;

@@ -60,7 +60,7 @@ def indenter_mesh(kind: int, size: float, segments: int = 24):
     """Closed triangle mesh (n, 3, 3) float64 [m] of the config-2 indenters for the gel FEM path (``tx_fem_set_indenter_mesh``), in the
     indenter's own frame: lowest point at the origin, body towards +z -- the same shapes as ``indenter_profile``: kind 1 flat
     cylinder (radius ``size``, height ``size``), 2 wedge (90 deg edge along y, half width ``size``, half length 2 ``size``),
-    3 cone (60 deg apex, base radius ``size``)."""
+    3 cone (60 deg apex, base radius ``size``); kind 0: the sphere of radius ``size`` as an icosphere (1280 triangles by default)."""
     import numpy as np
 
     tris = []
@@ -80,8 +80,30 @@ def indenter_mesh(kind: int, size: float, segments: int = 24):
         hi, apex, c1 = ring(size, h), np.zeros(3), np.array([0.0, 0.0, h])
         for k in range(segments):
             tris += [[apex, hi[k + 1], hi[k]], [c1, hi[k], hi[k + 1]]]
+    elif kind == 0:
+        # sphere of radius ``size`` (lowest point at the origin) as an icosphere: ``segments`` // 8 subdivisions of the icosahedron
+        # (24 -> 3 subdivisions: 1280 triangles, 642 vertices, 1920 edges) -- a "recorded triangle soup" of realistic size
+        t = (1.0 + math.sqrt(5.0)) / 2.0
+        v = [np.array(p, float) / math.sqrt(1 + t * t) for p in
+             [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]]
+        f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+             (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+        cache: dict = {}
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m_ = v[a] + v[b]
+                v.append(m_ / np.linalg.norm(m_))
+                cache[key] = len(v) - 1
+            return cache[key]
+
+        for _ in range(max(segments // 8, 0)):
+            f = [g for a, b, c in f for g in ((a, mid(a, b), mid(c, a)), (b, mid(b, c), mid(a, b)), (c, mid(c, a), mid(b, c)), (mid(a, b), mid(b, c), mid(c, a)))]
+        off = np.array([0.0, 0.0, size])
+        tris = [[size * v[a] + off, size * v[b] + off, size * v[c] + off] for a, b, c in f]
     else:
-        raise ValueError(f"no mesh for indenter kind {kind} (the sphere is analytic)")
+        raise ValueError(f"no mesh for indenter kind {kind}")
     return np.asarray(tris, np.float64)
 
 

@@ -1,6 +1,6 @@
 """Timing of the batched gel FEM substep (config 3: box indenter pressed 0 -> 1 mm over 30 steps).
 
-    python tools/fem_time.py [N] [steps] [mesh_kind]     mesh_kind 1 / 2 / 3: the config-2 cylinder / wedge / cone as a prescribed triangle mesh
+    python tools/fem_time.py [N] [steps] [mesh_kind]     mesh_kind 1 / 2 / 3: the config-2 cylinder / wedge / cone as a prescribed triangle mesh; 4: a 1280-triangle icosphere
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,7 +19,7 @@ ctr = lambda s: np.concatenate([offs, np.full((N, 1), z0 - 1e-3 * s / 30)], 1)
 mesh_kind = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 if mesh_kind:
     from tacex_b200 import synth
-    eng.set_indenter_mesh(synth.indenter_mesh(mesh_kind, 3e-3))
+    eng.set_indenter_mesh(synth.indenter_mesh(mesh_kind % 4, 3e-3))
     if os.environ.get("TX_TP"):  # second half of the vertex-face contact: indenter vertices against the gel's top triangles
         eng.set_contact_surface(m.top_tris)
     z0 = 4.5e-3 + 4e-4
