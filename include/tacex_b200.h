@@ -288,8 +288,8 @@ int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, const double* a
  * d_hat gets the reference's point-triangle barrier with closest-feature classification (ref: libuipc
  * utils/distance/distance_flagged.h:248-350, contact_system/contact_models/ipc_simplex_normal_contact.cu:270-342,
  * collision_detection/filters/lbvh_simplex_trajectory_filter.cu:600-690), restricted to the gel vertex (the indenter is prescribed).
- * n_tris = 0 removes the mesh. Distances to the mesh are searched within 4 d_hat: tx_fem_stats.min_dist is exact below that radius
- * and reported as 4 d_hat beyond it. */
+ * n_tris = 0 removes the mesh. Distances to the mesh are searched within 2 d_hat: tx_fem_stats.min_dist is exact below that radius
+ * and reported as 2 d_hat beyond it. */
 int tx_fem_set_indenter_mesh(tx_fem* f, int n_tris, const double* tri_local);
 /* Second half of the vertex-face contact + the EDGE-EDGE candidates with a mesh indenter: tris HOST [n_tris][3] vertex ids of the gel
  * surface that the indenter's VERTICES (against the triangles) and EDGES (against the triangles' unique edges, mollified as the

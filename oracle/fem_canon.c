@@ -243,7 +243,7 @@ void fem_set_indenter_mesh(const double* tri, int n)
 }
 
 /* search radius of the mesh contact: distances are exact below it and reported as the radius beyond (candidates farther than
-   4 d_hat can neither carry a barrier nor limit a step of the sizes the solver takes); set by fem_step from the config */
+   2 d_hat can neither carry a barrier nor limit a step of the sizes the solver takes); set by fem_step from the config */
 static double g_mesh_cap2 = 1e300;
 static double* g_mesh_vert = 0; /* [nv][3] unique vertices of the indenter mesh (local frame) */
 static int g_mesh_nv = 0;
@@ -1358,7 +1358,7 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     fem_tp tpl;
     memset(&tpl, 0, sizeof(tpl));
     c.tp = &tpl;
-    g_mesh_cap2 = 16.0 * g->d_hat * g->d_hat; /* the same value from every thread of fem_step_batch */
+    g_mesh_cap2 = 4.0 * g->d_hat * g->d_hat; /* the same value from every thread of fem_step_batch */
     memset(st, 0, sizeof(*st));
 
     /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */

@@ -327,7 +327,7 @@ extern "C" int tx_fem_step(tx_fem* f, double* x, double* v, double* x_prev, cons
 }
 
 // Uniform grid over reference points `ref` [n][3] (see MeshGrid in tx_kernels.h): every primitive in the cell of its reference point,
-// ids ascending within a cell. Up to 64 primitives: one cell (the brute-force loop). Cell size ~ the search radius 4 d_hat.
+// ids ascending within a cell. Up to 256 primitives: one cell (the brute-force loop). Cell size ~ the search radius 2 d_hat.
 static cudaError_t build_mesh_grid(const std::vector<double>& ref, double rmax, double d_hat, MeshGrid& G, int*& d_start, int*& d_ids)
 {
     const int n = (int)(ref.size() / 3);
@@ -338,11 +338,13 @@ static cudaError_t build_mesh_grid(const std::vector<double>& ref, double rmax, 
         if (n == 0) lo[a] = hi[a] = 0.0;
     }
     int dims[3] = {1, 1, 1};
-    if (n > 64)
+    if (n > 256) { // cells of about the search radius, but not so many that most stay empty (>= ~4 primitives per cell on average)
+        const int cap = std::max(1, std::min(16, (int)std::cbrt(n / 4.0)));
         for (int a = 0; a < 3; ++a) {
             const double ext = hi[a] - lo[a];
-            dims[a] = ext > 0.0 ? std::max(1, std::min(16, (int)(ext / (4.0 * d_hat)))) : 1;
+            dims[a] = ext > 0.0 ? std::max(1, std::min(cap, (int)(ext / (2.0 * d_hat)))) : 1;
         }
+    }
     G.nx = dims[0]; G.ny = dims[1]; G.nz = dims[2];
     G.rmax = rmax;
     for (int a = 0; a < 3; ++a) {

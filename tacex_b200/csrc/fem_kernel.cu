@@ -473,12 +473,12 @@ __device__ __noinline__ bool mesh_contact_impl(MeshRef m, double3 c, double3 r0,
 #pragma unroll
     for (int i = 0; i < 3; ++i) p[i] = R[0 * 3 + i] * q[0] + R[1 * 3 + i] * q[1] + R[2 * 3 + i] * q[2];
     const double D0 = m.d_hat * m.d_hat, Dcull = kdt2 > 0.0 ? D0 : 0.0;
-    // search radius 4 d_hat: distances are exact below it and reported as the radius beyond (a candidate farther away can neither
+    // search radius 2 d_hat: distances are exact below it and reported as the radius beyond (a candidate farther away can neither
     // carry a barrier nor limit a step of the sizes the solver takes), so far gel primitives skip every distance evaluation
-    double best = 16.0 * D0, gb[3] = {0.0, 0.0, 1.0};
+    double best = 4.0 * D0, gb[3] = {0.0, 0.0, 1.0};
     double Es = 0.0, Gl[3] = {0.0, 0.0, 0.0}, Hl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     bool active = false;
-    grid_for(m.grid, p, p, 4.0 * m.d_hat, [&](int t) {
+    grid_for(m.grid, p, p, 2.0 * m.d_hat, [&](int t) {
         const double* bx = m.box + 6 * t;
         double bd = 0.0;
 #pragma unroll
@@ -666,11 +666,11 @@ __device__ __noinline__ void tp_terms_impl(MeshVerts mv, double3 c, double3 r0, 
         hi[a] = fmax(tr[a], fmax(tr[3 + a], tr[6 + a]));
     }
     const double D0 = mv.d_hat * mv.d_hat;
-    double E = 0.0, best = 16.0 * D0;
+    double E = 0.0, best = 4.0 * D0;
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 45; ++k) o->v[k] = 0.0;
-    grid_for(mv.grid, lo, hi, 4.0 * mv.d_hat, [&](int k) {
+    grid_for(mv.grid, lo, hi, 2.0 * mv.d_hat, [&](int k) {
         const double* l = mv.vert + 3 * k;
         const double pw[3] = {l[0], l[1], l[2]};
         double bd = 0.0;
@@ -860,14 +860,14 @@ __device__ __noinline__ void ee_terms_impl(MeshEdges me, double3 c, double3 r0, 
     double a0[3], a1[3];
     to_local3(R, c, xa, a0); to_local3(R, c, xb, a1);
     const double D0 = me.d_hat * me.d_hat;
-    double E = 0.0, best = 16.0 * D0;
+    double E = 0.0, best = 4.0 * D0;
     int bad = 0;
     if (derivs)
         for (int k = 0; k < 24; ++k) o->v[k] = 0.0;
     double elo[3], ehi[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { elo[k] = fmin(a0[k], a1[k]); ehi[k] = fmax(a0[k], a1[k]); }
-    grid_for(me.grid, elo, ehi, 4.0 * me.d_hat, [&](int q) {
+    grid_for(me.grid, elo, ehi, 2.0 * me.d_hat, [&](int q) {
         const double* l0 = me.vert + 3 * me.edge[2 * q];
         const double* l1 = me.vert + 3 * me.edge[2 * q + 1];
         double b0[3] = {l0[0], l0[1], l0[2]}, b1[3] = {l1[0], l1[1], l1[2]};

@@ -341,7 +341,7 @@ def test_two_sided_vertex_face_contact_matches_cpu_restatement(kind):
 def test_large_triangle_soup_through_the_grid_broad_phase_matches_restatement_and_the_analytic_sphere():
     """A 'recorded triangle soup' of realistic size -- an icosphere of 1280 triangles / 642 vertices / 1920 edges -- with the full
     simplex contact. The kernel finds its candidates through the uniform-grid broad phase built once in the indenter's frame
-    (several cells per axis above 64 primitives); the restatement loops over every pair: same positions, same Newton counts.
+    (several cells per axis above 256 primitives); the restatement loops over every pair: same positions, same Newton counts.
     And the soup presses the gel like the analytic sphere it tessellates, up to the barrier's support."""
     from tacex_b200 import fem, synth
 
