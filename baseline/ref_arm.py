@@ -113,8 +113,14 @@ class RefStep:
 
 def time_cpu(hm_mm, batch: int, reps: int, warmup: int = 1, with_markers: bool = True):
     """frames/s of the reference on the host cores: ``reps`` sensor updates of ``batch`` envs each."""
+    import os
+
     import torch
 
+    # every host thread the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the reference on ONE core
+    n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if torch.get_num_threads() < n_cpu:
+        torch.set_num_threads(n_cpu)
     step = RefStep("cpu", with_markers=with_markers)
     th = torch.zeros(batch)
     n = hm_mm.shape[0]

@@ -236,6 +236,9 @@ def test_reference_arm_under_torchrun_prints_one_json_line_from_rank_0():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["n_gpus"] == 2
     staged = (root / "baseline" / "_ref" / "gpu_taxim" / "sim" / "taxim_torch.py").exists()
     assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port") and d["cpu_baseline"]["cores"] >= 1
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm must still use every host thread it may
+    n_cpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["cores"] == n_cpu, d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
