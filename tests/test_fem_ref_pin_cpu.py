@@ -3,7 +3,10 @@ lies under /root/reference (libuipc cuda backend; oracle/Makefile target `ref` -
 oracle/ref_sym.cpp): the stable Neo-Hookean energy / gradient / Hessian (sym/stable_neo_hookean_3d.inl), the IPC barrier
 (sym/codim_ipc_contact.inl), and the vertex-vs-half-plane normal and frictional contact (ipc_vertex_half_plane_contact_function.h,
 codim_ipc_contact_function.h) that the restatement generalises to analytic indenters: under a flat face of a box indenter the
-two models must coincide. Skipped where the library has not been built (it needs /root/reference; the GPU box has none)."""
+two models must coincide. A second library (oracle/ref_dist.cpp -> oracle/_ref/libuipc_dist.so) holds the reference's closest-feature
+distances (utils/distance/distance_flagged.h, point-triangle and edge-edge), its edge-edge mollifier and its additive CCD
+(details/ccd.inl): they pin the mesh-indenter contact of the restatement, the CCD also on the fixtures with ground truth that muda
+ships. Skipped where the libraries have not been built (they need /root/reference; the GPU box has none)."""
 import ctypes as C
 from pathlib import Path
 
