@@ -40,8 +40,8 @@
  * reference's model; only the curvature terms of a sliding closest point are dropped (stated in DESIGN.md). ACCD with the moving
  * triangle as in the reference. The EDGE-EDGE candidates (gel surface edges against the indenter's edges) are treated the same way:
  * the reference's classification (edge_edge_distance_flag), the squared distance of the EE / PE / PP case, the mollifier of nearly
- * parallel edges on the interior case, the edge-edge ACCD -- fem_ee_closest / fem_ee_mollifier / fem_ee_accd, all pinned. No
- * friction on these two candidate families.
+ * parallel edges on the interior case, the edge-edge ACCD -- fem_ee_closest / fem_ee_mollifier / fem_ee_accd, all pinned. Lagged
+ * friction: one contact per gel vertex, the resultant of the normal forces of all candidates it takes part in (all families).
  * Not restated: LBVH (every primitive pair is tested against its box).
  *
  * PARITY PARTLY PINNED: libuipc as a whole cannot be built or run in this environment (needs vcpkg dependencies and a GPU; it
@@ -630,6 +630,7 @@ typedef struct {
     fem_indenter ind;    /* current (interpolated) indenter */
     fem_indenter ind0;   /* indenter at the start of the step (lagged friction) */
     struct fem_tp_s* tp; /* active (indenter vertex, gel triangle) candidates of the last grad_hess (Gauss-Newton rank-1 terms) */
+    const double* lagG;  /* [V][3] gradient of the vertex-triangle / edge-edge candidate energy at x_prev against ind0 (lagged friction) or NULL */
 } fem_ctx;
 
 /* ---- edge-edge candidates ---------------------------------------------------------------------------------------------------- */
@@ -1027,14 +1028,16 @@ int fem_vertex_barrier_terms(const fem_cfg* g, const fem_indenter* ind, const do
  * The normal force and the tangent frame are taken at the start-of-step position against the start-of-step indenter
  * (lagged); the half-plane of the reference is static, here the tangential slip is measured RELATIVE to the prescribed
  * translation of the indenter over the step. */
-static int friction_lagged(const fem_cfg* g, const fem_indenter* ind0, const double* xp, double* fn, double* e1, double* e2)
+static int friction_lagged(const fem_cfg* g, const fem_indenter* ind0, const double* xp, const double* lagG, double* fn, double* e1, double* e2)
 {
     double d, n[3], dB;
     if (ind0->type == 2) {
-        /* triangle mesh: ONE lagged contact per vertex -- the resultant of the candidates' normal forces (its magnitude and
-           direction); equal to the reference's per-candidate friction when a single candidate is active */
-        double Gb[3];
-        if (!mesh_barrier_terms(g, ind0, xp, 0, Gb, 0)) return 0;
+        /* triangle mesh: ONE lagged contact per vertex -- the resultant of the normal forces of ALL candidates the vertex takes part
+           in (vertex-triangle both ways and edge-edge; lagG holds the part of the families whose unknowns are several vertices);
+           equal to the reference's per-candidate friction when a single candidate is active */
+        double Gb[3] = {0, 0, 0};
+        if (!mesh_barrier_terms(g, ind0, xp, 0, Gb, 0)) Gb[0] = Gb[1] = Gb[2] = 0.0;
+        if (lagG) for (int a = 0; a < 3; ++a) Gb[a] += lagG[a];
         *fn = sqrt(Gb[0] * Gb[0] + Gb[1] * Gb[1] + Gb[2] * Gb[2]);
         if (!(*fn > 0.0)) return 0;
         for (int a = 0; a < 3; ++a) n[a] = -Gb[a] / *fn;
@@ -1056,14 +1059,21 @@ static int friction_lagged(const fem_cfg* g, const fem_indenter* ind0, const dou
 }
 
 /* energy, gradient (3) and Hessian (9, row-major) of mu fn f0(|u|), u = [e1 e2]^T rel, rel = (x - x_prev) - indenter shift */
+static void friction_terms_lag(const fem_cfg* g, const fem_indenter* ind0, const fem_indenter* ind, const double* xp, const double* x,
+                               const double* lagG, double* E, double* G, double* H);
 void fem_friction_terms(const fem_cfg* g, const fem_indenter* ind0, const fem_indenter* ind, const double* xp, const double* x,
                         double* E, double* G, double* H)
+{
+    friction_terms_lag(g, ind0, ind, xp, x, 0, E, G, H);
+}
+static void friction_terms_lag(const fem_cfg* g, const fem_indenter* ind0, const fem_indenter* ind, const double* xp, const double* x,
+                               const double* lagG, double* E, double* G, double* H)
 {
     if (E) *E = 0.0;
     if (G) memset(G, 0, sizeof(double) * 3);
     if (H) memset(H, 0, sizeof(double) * 9);
     double fn, e1[3], e2[3];
-    if (!(g->friction_mu > 0.0) || !friction_lagged(g, ind0, xp, &fn, e1, e2)) return;
+    if (!(g->friction_mu > 0.0) || !friction_lagged(g, ind0, xp, lagG, &fn, e1, e2)) return;
     double rel[3];
     for (int a = 0; a < 3; ++a) rel[a] = (x[a] - xp[a]) - (ind->c[a] - ind0->c[a]);
     const double u0 = e1[0] * rel[0] + e1[1] * rel[1] + e1[2] * rel[2];
@@ -1146,7 +1156,7 @@ static double total_energy(const fem_ctx* c, const double* x, double* min_dist)
         for (int k = 0; k < g->S; ++k) {
             int i = c->surf[k];
             double Ef;
-            fem_friction_terms(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, &Ef, 0, 0);
+            friction_terms_lag(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, c->lagG ? c->lagG + 3 * i : 0, &Ef, 0, 0);
             E += Ef;
         }
     if (min_dist) *min_dist = md;
@@ -1214,7 +1224,7 @@ static void grad_hess(const fem_ctx* c, const double* x, double* G, double* H9, 
         }
         if (g->friction_mu > 0.0) {
             double Gf[3], Hf[9];
-            fem_friction_terms(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, 0, Gf, Hf);
+            friction_terms_lag(g, &c->ind0, &c->ind, c->x_prev + 3 * i, x + 3 * i, c->lagG ? c->lagG + 3 * i : 0, 0, Gf, Hf);
             for (int a = 0; a < 3; ++a) G[3 * i + a] += Gf[a];
             for (int j = 0; j < 9; ++j) Hk[j] += Hf[j];
         }
@@ -1359,6 +1369,12 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     memset(&tpl, 0, sizeof(tpl));
     c.tp = &tpl;
     g_mesh_cap2 = 4.0 * g->d_hat * g->d_hat; /* the same value from every thread of fem_step_batch */
+    double* lagG = (double*)calloc(n, sizeof(double));
+    if (g->friction_mu > 0.0 && ind_prev->type == 2) { /* lagged normal forces of the multi-vertex candidate families at the start of the step */
+        tp_terms(g, ind_prev, x_prev, lagG, 0, 0, 0);
+        ee_terms(g, ind_prev, x_prev, lagG, 0, 0, 0);
+        c.lagG = lagG;
+    }
     memset(st, 0, sizeof(*st));
 
     /* predict (fem_bdf1_time_integrator.cu:19-55): every gel vertex is dynamic and not fixed */
@@ -1453,7 +1469,7 @@ void fem_step(const fem_cfg* g, const int32_t* tets, const double* Dm_inv, const
     /* update velocity (fem_bdf1_time_integrator.cu:58-77) */
     for (int i = 0; i < n; ++i) { v[i] = (x[i] - x_prev[i]) * (1.0 / g->dt); x_prev[i] = x[i]; }
     free(xt); free(G); free(dx); free(x0); free(r); free(z); free(p); free(Ap); free(H9); free(Dg); free(Dinv); free(Hc);
-    free(tpl.tri); free(tpl.g9); free(tpl.w);
+    free(tpl.tri); free(tpl.g9); free(tpl.w); free(lagG);
 }
 
 /* batch driver (OpenMP over gels) */

@@ -1195,11 +1195,14 @@ __device__ __forceinline__ void tet_F(const double* x, const int* e, const doubl
 // Lagged contact of a vertex against the mesh indenter: ONE per vertex, the resultant of the candidates' normal forces at the
 // start-of-step position. It does not change during the step, so the row's thread computes it once (a pass over the triangles).
 struct FrLag { double fn, n[3]; };
-__device__ __forceinline__ FrLag mesh_friction_lag(const FemArgs& a, const FemIndenter& ind0, const double* xp)
+// Glag: the vertex's share of the gradient of the candidate families whose unknowns are several vertices (indenter vertex vs gel
+// triangle, edge-edge) at the same lagged state -- the resultant covers every candidate the vertex takes part in.
+__device__ __forceinline__ FrLag mesh_friction_lag(const FemArgs& a, const FemIndenter& ind0, const double* xp, const double Glag[3])
 {
     FrLag l{0.0, {0.0, 0.0, 1.0}};
     double Gb[3] = {0.0, 0.0, 0.0};
-    if (!mesh_contact(a, ind0, xp, a.kappa * a.dt * a.dt, nullptr, nullptr, nullptr, Gb, nullptr)) return l;
+    mesh_contact(a, ind0, xp, a.kappa * a.dt * a.dt, nullptr, nullptr, nullptr, Gb, nullptr); // accumulates only when a candidate is active
+    Gb[0] += Glag[0]; Gb[1] += Glag[1]; Gb[2] += Glag[2];
     const double fn = sqrt(Gb[0] * Gb[0] + Gb[1] * Gb[1] + Gb[2] * Gb[2]);
     if (!(fn > 0.0)) return l;
     l.fn = fn;
@@ -1743,9 +1746,41 @@ __global__ void __launch_bounds__(FEM_THREADS, 1) fem_step_kernel(const FemArgs 
         umax = sqrt(umax);
         const bool is_surf = on && a.surf_of[i] >= 0;
         FrLag lag{0.0, {0.0, 0.0, 1.0}};
+        double Glag[3] = {0.0, 0.0, 0.0};
+        if (MESH && ind_prev.type == 2 && a.friction_mu > 0.0 && a.n_ctri > 0) {
+            // lagged normal forces of the multi-vertex candidate families at the start-of-step state: the triangle / edge threads
+            // evaluate their candidates at x_prev against ind_prev, the rows gather their share through the static lists
+            const double kdt2 = a.kappa * a.dt * a.dt;
+            if (threadIdx.x < a.n_ctri) {
+                TpOut o;
+                tp_terms(a, ind_prev, xpg, threadIdx.x, kdt2, 1, &o);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) tsc[(size_t)k * FEM_THREADS + threadIdx.x] = o.v[k];
+            }
+            if (threadIdx.x < a.n_cedge) {
+                EeOut o;
+                ee_terms(a, ind_prev, xpg, threadIdx.x, kdt2, 1, &o);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) tsc[(size_t)(45 + k) * FEM_THREADS + threadIdx.x] = o.v[k];
+            }
+            __syncthreads();
+            if (on) {
+                for (int q = a.ctri_row_start[i]; q < a.ctri_row_start[i + 1]; ++q) {
+                    const int ent = a.ctri_row_adj[q], f = ent >> 2, j = ent & 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Glag[c] += tsc[(size_t)(3 * j + c) * FEM_THREADS + f];
+                }
+                for (int q = a.cedge_row_start[i]; q < a.cedge_row_start[i + 1]; ++q) {
+                    const int ent = a.cedge_row_adj[q], ce = ent >> 1, j = ent & 1;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Glag[c] += tsc[(size_t)(45 + 3 * j + c) * FEM_THREADS + ce];
+                }
+            }
+            __syncthreads(); // the assembly reuses the scratch
+        }
         if (MESH && ind_prev.type == 2 && is_surf && a.friction_mu > 0.0) {
             const double xp3[3] = {xpg[3 * i], xpg[3 * i + 1], xpg[3 * i + 2]};
-            lag = mesh_friction_lag(a, ind_prev, xp3);
+            lag = mesh_friction_lag(a, ind_prev, xp3, Glag);
         }
         int it, pcg_total = 0, ls_total = 0, conv = 0;
         for (it = 0; it < a.newton_max_iter; ++it) {

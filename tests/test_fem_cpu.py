@@ -411,3 +411,35 @@ def test_indenter_vertices_against_gel_triangles_in_the_restatement():
         assert res[False] < 2e-4 and res[True] > 7e-4, res
     finally:
         cf.set_contact_surface(None)
+
+
+def test_lagged_friction_covers_the_multi_vertex_candidate_families():
+    """A cone tip resting in the middle of a surface cell touches the gel only through indenter-vertex / gel-triangle (and edge-edge)
+    candidates. Dragged sideways, it must take the gel surface along by friction -- the lagged contact of a vertex is the resultant of
+    ALL candidates it takes part in --, and clearly more than without friction."""
+    from oracle import fem_canon as fc
+    from tacex_b200 import gel_mesh, synth
+
+    m = gel_mesh.box_gel()
+    fc.CanonFem.set_indenter_mesh(synth.indenter_mesh(3, 3e-3))
+    z0 = 4.5e-3 + 4e-4
+
+    def ctr(s):  # 6 steps down (0.8 mm), then 5 steps sideways (0.1 mm each)
+        return [1.0e-3 + 1e-4 * max(s - 6, 0), 0.5e-3, z0 - 0.8e-3 * min(s, 6) / 6]
+
+    drag = {}
+    try:
+        for mu in (0.0, 0.5):
+            cf = fc.CanonFem(m, velocity_tol=1e-3, friction_mu=mu)
+            cf.set_contact_surface(m.top_tris)
+            x, v, xp = cf.new_state(1)
+            aim = cf.X[cf.attach][None]
+            for s in range(11):
+                st = cf.step(x, v, xp, aim, [fc.make_indenter(2, ctr(s), (0, 0, 0))], [fc.make_indenter(2, ctr(s + 1), (0, 0, 0))])
+                assert st[0]["converged"] == 1 and st[0]["min_dist"] > 0
+            top = np.unique(np.asarray(m.top_tris))
+            near = top[np.linalg.norm(cf.X[top][:, :2] - np.array([1.0e-3, 0.5e-3]), axis=1) < 2.2e-3]
+            drag[mu] = float((x[0, near, 0] - cf.X[near, 0]).mean())
+    finally:
+        cf.set_contact_surface(None)
+    assert drag[0.5] > drag[0.0] + 3e-5, drag
