@@ -256,3 +256,28 @@ def test_bench_has_no_cpu_path_for_the_product_arm():
     r = subprocess.run([sys.executable, str(root / "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=300, cwd=str(root))
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout) and not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_indenter_meshes_are_closed_triangle_soups(kind):
+    """The config-2 indenter meshes handed to tx_fem_set_indenter_mesh (sphere as an icosphere, flat cylinder, wedge, cone): no
+    degenerate triangle, every edge shared by exactly two triangles (closed surface), lowest point at the origin, body towards +z."""
+    from collections import Counter
+
+    import numpy as np
+
+    from tacex_b200 import synth
+
+    t = synth.indenter_mesh(kind, 3e-3)
+    assert t.ndim == 3 and t.shape[1:] == (3, 3) and len(t) >= 8
+    n = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    assert (np.linalg.norm(n, axis=1) > 0).all()
+    verts, inv = np.unique(t.reshape(-1, 3).round(12), axis=0, return_inverse=True)
+    ids = inv.reshape(-1, 3)
+    edges = Counter()
+    for a, b, c in ids:
+        for u, v in ((a, b), (b, c), (c, a)):
+            edges[(min(u, v), max(u, v))] += 1
+    assert set(edges.values()) == {2}
+    assert abs(verts[:, 2].min()) < 1e-15 and verts[:, 2].max() > 1e-3
+    assert len(verts) - len(edges) + len(t) == 2  # Euler characteristic of a sphere
